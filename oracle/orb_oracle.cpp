@@ -1,0 +1,819 @@
+// CPU oracle for the ORB front end -- TEST INFRASTRUCTURE ONLY (see orb_oracle.h).
+//
+// Build: g++ -O2 -ffp-contract=off -std=c++17 -fPIC -shared (oracle/Makefile).
+// -ffp-contract=off is part of the definition: the float expressions below are
+// evaluated step by step in binary32, never fused (SURVEY 7 "Float reproducibility").
+#include "orb_oracle.h"
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <climits>
+#include <cmath>
+#include <cstring>
+#include <list>
+#include <thread>
+
+namespace orb_oracle {
+
+// ---------------------------------------------------------------- cvRound
+// OpenCV cvRound == lrint under the default rounding mode (round half to even), A.5.
+int cv_round_f(float v) { return (int)lrintf(v); }
+int cv_round_d(double v) { return (int)lrint(v); }
+
+// ---------------------------------------------------------------- fastAtan2
+// cv::fastAtan2 (A.4); called from IC_Angle, reference ORBextractor.cc:47.
+float fast_atan2(float y, float x) {
+    const float scale = (float)(180.0 / 3.141592653589793238462643383279502884);
+    const float p1 = 0.9997878412794807f * scale;
+    const float p3 = -0.3258083974640975f * scale;
+    const float p5 = 0.1555786518463281f * scale;
+    const float p7 = -0.04432655554792128f * scale;
+    const float eps = (float)2.2204460492503131e-16;
+    float ax = std::fabs(x), ay = std::fabs(y);
+    float a, c, c2;
+    if (ax >= ay) {
+        c = ay / (ax + eps);
+        c2 = c * c;
+        a = (((p7 * c2 + p5) * c2 + p3) * c2 + p1) * c;
+    } else {
+        c = ax / (ay + eps);
+        c2 = c * c;
+        a = 90.f - (((p7 * c2 + p5) * c2 + p3) * c2 + p1) * c;
+    }
+    if (x < 0) a = 180.f - a;
+    if (y < 0) a = 360.f - a;
+    return a;
+}
+
+// ---------------------------------------------------------------- resize
+// cv::resize INTER_LINEAR 8UC1 (A.2); called at reference ORBextractor.cc:511.
+static void linear_axis(int ssize, int dsize, std::vector<int>& ofs, std::vector<int>& c0,
+                        std::vector<int>& c1, bool clamp_coeff) {
+    ofs.resize(dsize);
+    c0.resize(dsize);
+    c1.resize(dsize);
+    double inv_scale = (double)dsize / ssize;
+    double scale = 1.0 / inv_scale;
+    for (int d = 0; d < dsize; ++d) {
+        float f = (float)((d + 0.5) * scale - 0.5);
+        int s = (int)std::floor(f);
+        f -= s;
+        if (clamp_coeff) {  // x axis: coefficients collapse at the image edge
+            if (s < 0) { s = 0; f = 0.f; }
+            if (s >= ssize - 1) { s = ssize - 1; f = 0.f; }
+        }
+        ofs[d] = s;
+        // saturate_cast<short>(float * 2048): cvRound then clamp (never clamps here)
+        c0[d] = cv_round_f((1.f - f) * 2048.f);
+        c1[d] = cv_round_f(f * 2048.f);
+    }
+}
+
+void resize_linear_u8(const Image& src, uint8_t* dst, int drows, int dcols, int dstep) {
+    if (drows == src.rows && dcols == src.cols) {  // same-size resize is a copy
+        for (int y = 0; y < drows; ++y) memcpy(dst + (size_t)y * dstep, src.row(y), dcols);
+        return;
+    }
+    std::vector<int> xo, a0, a1, yo, b0, b1;
+    linear_axis(src.cols, dcols, xo, a0, a1, true);
+    // y axis: OpenCV keeps the coefficients and clips the two row indices instead.
+    linear_axis(src.rows, drows, yo, b0, b1, false);
+    std::vector<int> r0(dcols), r1(dcols);
+    for (int y = 0; y < drows; ++y) {
+        int sy0 = std::min(std::max(yo[y], 0), src.rows - 1);
+        int sy1 = std::min(std::max(yo[y] + 1, 0), src.rows - 1);
+        const uint8_t* S0 = src.row(sy0);
+        const uint8_t* S1 = src.row(sy1);
+        for (int x = 0; x < dcols; ++x) {
+            int s = xo[x];
+            int s1 = std::min(s + 1, src.cols - 1);
+            r0[x] = S0[s] * a0[x] + S0[s1] * a1[x];
+            r1[x] = S1[s] * a0[x] + S1[s1] * a1[x];
+        }
+        uint8_t* D = dst + (size_t)y * dstep;
+        for (int x = 0; x < dcols; ++x)
+            D[x] = (uint8_t)((((b0[y] * (r0[x] >> 4)) >> 16) + ((b1[y] * (r1[x] >> 4)) >> 16) + 2) >> 2);
+    }
+}
+
+// ---------------------------------------------------------------- GaussianBlur
+// cv::GaussianBlur 7x7 sigma 2 REFLECT_101 on 8UC1 (A.3); reference ORBextractor.cc:479.
+static inline int reflect101(int p, int n) {
+    if (n == 1) return 0;
+    while (p < 0 || p >= n) {
+        if (p < 0) p = -p;
+        else p = 2 * n - 2 - p;
+    }
+    return p;
+}
+
+void gaussian_blur7_u8(const Image& src, uint8_t* dst, int dstep) {
+    static const int w[7] = {18, 34, 48, 56, 48, 34, 18};
+    const int R = src.rows, C = src.cols;
+    // horizontal pass: exact 16-bit sums (max 255*256), no intermediate rounding
+    std::vector<uint16_t> h((size_t)R * C);
+    std::vector<uint8_t> padded(C + 6);
+    for (int y = 0; y < R; ++y) {
+        const uint8_t* S = src.row(y);
+        for (int x = -3; x < C + 3; ++x) padded[x + 3] = S[reflect101(x, C)];
+        uint16_t* H = &h[(size_t)y * C];
+        const uint8_t* P = padded.data();
+        for (int x = 0; x < C; ++x)
+            H[x] = (uint16_t)(w[0] * (P[x] + P[x + 6]) + w[1] * (P[x + 1] + P[x + 5]) +
+                              w[2] * (P[x + 2] + P[x + 4]) + w[3] * P[x + 3]);
+    }
+    const bool inplace = (dst == src.data);
+    std::vector<uint8_t> tmp;
+    if (inplace) tmp.resize((size_t)R * C);
+    for (int y = 0; y < R; ++y) {
+        const uint16_t* hr[7];
+        for (int j = 0; j < 7; ++j) hr[j] = &h[(size_t)reflect101(y + j - 3, R) * C];
+        uint8_t* D = inplace ? &tmp[(size_t)y * C] : dst + (size_t)y * dstep;
+        for (int x = 0; x < C; ++x) {
+            int acc = w[0] * (hr[0][x] + hr[6][x]) + w[1] * (hr[1][x] + hr[5][x]) +
+                      w[2] * (hr[2][x] + hr[4][x]) + w[3] * hr[3][x];
+            D[x] = (uint8_t)((acc + 32768) >> 16);
+        }
+    }
+    if (inplace)
+        for (int y = 0; y < R; ++y) memcpy(dst + (size_t)y * dstep, &tmp[(size_t)y * C], C);
+}
+
+// ---------------------------------------------------------------- FAST
+// cv::FAST(img, kps, t, true) TYPE_9_16 (A.1); reference ORBextractor.cc:295,330.
+static const int kRingDx[16] = {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1};
+static const int kRingDy[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3};
+
+int fast_score_at(const Image& img, int x, int y, int threshold) {
+    const int c = img.row(y)[x];
+    int r[16];
+    // necessary condition first (every 9-arc holds one pixel of each opposite pair):
+    // cheap rejection, identical results
+    {
+        const int hi = c + threshold, lo = c - threshold;
+        bool bright = true, dark = true;
+        static const int order[8] = {0, 4, 2, 6, 1, 3, 5, 7};
+        for (int q = 0; q < 8; ++q) {
+            const int k = order[q];
+            const int p0 = img.row(y + kRingDy[k])[x + kRingDx[k]];
+            const int p1 = img.row(y + kRingDy[k + 8])[x + kRingDx[k + 8]];
+            r[k] = p0;
+            r[k + 8] = p1;
+            bright = bright && (p0 > hi || p1 > hi);
+            dark = dark && (p0 < lo || p1 < lo);
+            if (!bright && !dark) return 0;
+        }
+    }
+    // min and max of d over the 16 circular 9-arcs, by window doubling (2,4,8,+1)
+    int lo[16], hi[16], lo2[16], hi2[16];
+    for (int k = 0; k < 16; ++k) lo[k] = hi[k] = c - r[k];
+    for (int k = 0; k < 16; ++k) {
+        lo2[k] = std::min(lo[k], lo[(k + 1) & 15]);
+        hi2[k] = std::max(hi[k], hi[(k + 1) & 15]);
+    }
+    int lo4[16], hi4[16];
+    for (int k = 0; k < 16; ++k) {
+        lo4[k] = std::min(lo2[k], lo2[(k + 2) & 15]);
+        hi4[k] = std::max(hi2[k], hi2[(k + 2) & 15]);
+    }
+    int m = INT_MIN;
+    for (int k = 0; k < 16; ++k) {
+        int l9 = std::min(std::min(lo4[k], lo4[(k + 4) & 15]), lo[(k + 8) & 15]);
+        int h9 = std::max(std::max(hi4[k], hi4[(k + 4) & 15]), hi[(k + 8) & 15]);
+        m = std::max(m, std::max(l9, -h9));
+    }
+    return m > threshold ? m - 1 : 0;
+}
+
+void fast9_16_nms(const Image& img, int threshold, std::vector<FastPoint>& out) {
+    const int R = img.rows, C = img.cols;
+    if (R < 7 || C < 7) return;
+    std::vector<int> score((size_t)R * C, 0);
+    for (int y = 3; y < R - 3; ++y)
+        for (int x = 3; x < C - 3; ++x) score[(size_t)y * C + x] = fast_score_at(img, x, y, threshold);
+    for (int y = 3; y < R - 3; ++y)
+        for (int x = 3; x < C - 3; ++x) {
+            int s = score[(size_t)y * C + x];
+            if (s == 0) continue;  // a corner always scores >= threshold >= 1
+            const int* p = &score[(size_t)y * C + x];
+            if (s > p[-1] && s > p[1] && s > p[-C - 1] && s > p[-C] && s > p[-C + 1] && s > p[C - 1] &&
+                s > p[C] && s > p[C + 1])
+                out.push_back({x, y, s});
+        }
+}
+
+// ---------------------------------------------------------------- ctor tables
+// ORBextractor::ORBextractor, reference ORBextractor.cc:116-170.
+static const int8_t kPairs[728] = {
+#include "brief_pairs_182.inc"
+};
+
+Tables make_tables(const Params& p) {
+    Tables t;
+    const int n = p.nlevels;
+    const double scaleFactorD = (double)p.scaleFactor;  // the member is a double (ORBextractor.h:79)
+    t.scale.assign(n, 1.0f);
+    // std::partial_sum(begin, end-1, begin+1, a*scaleFactor) reading and writing the
+    // same vector shifted by one (:120-124): {1, 1, s, s^2, ...}.
+    if (n >= 2) {
+        float acc = t.scale[0];
+        t.scale[1] = acc;
+        for (int i = 1; i <= n - 2; ++i) {
+            acc = (float)((double)acc * scaleFactorD);
+            t.scale[i + 1] = acc;
+        }
+    }
+    t.sigma2.resize(n);
+    t.inv_scale.resize(n);
+    t.inv_sigma2.resize(n);
+    for (int i = 0; i < n; ++i) t.sigma2[i] = t.scale[i] * t.scale[i];
+    for (int i = 0; i < n; ++i) t.inv_scale[i] = 1.0f / t.scale[i];
+    for (int i = 0; i < n; ++i) t.inv_sigma2[i] = 1.0f / t.sigma2[i];
+
+    t.features_per_level.assign(n, 0);
+    float factor = (float)(1.0 / scaleFactorD);  // 1.0f / double member (:141)
+    // nfeatures*(1-factor) in float, pow(float,int) promotes to double (:142)
+    float desired = (float)((double)((float)p.nfeatures * (1 - factor)) /
+                            (1.0 - std::pow((double)factor, (double)n)));
+    int sum = 0;
+    for (int i = 0; i < n - 1; ++i) {
+        int cur = cv_round_f(desired);
+        sum += cur;
+        desired *= factor;
+        t.features_per_level[i] = cur;
+    }
+    t.features_per_level[n - 1] = std::max(p.nfeatures - sum, 0);
+
+    t.pattern.assign(1024, 0);
+    for (int i = 0; i < 728; ++i) t.pattern[i] = kPairs[i];
+
+    // umax (:155-169)
+    t.umax.assign(16, 0);
+    const float half_diag = 15 * std::sqrt(2.f) / 2;
+    int vmax = (int)std::floor(half_diag + 1);
+    int vmin = (int)std::ceil(half_diag);
+    const double hp2 = 15 * 15;
+    for (int v = 0; v <= vmax; ++v) t.umax[v] = cv_round_d(std::sqrt(hp2 - v * v));
+    for (int v = 15, v0 = 0; v >= vmin; --v) {
+        while (t.umax[v0] == t.umax[v0 + 1]) ++v0;
+        t.umax[v] = v0;
+        ++v0;
+    }
+    return t;
+}
+
+// ---------------------------------------------------------------- octree
+// ExtractorNode::DivideNode + ORBextractor::DistributeOctTree,
+// reference ORBextractor.cc:178-225, :228-286.
+namespace {
+struct Node {
+    int ulx, uly, urx, bly;  // UL=(ulx,uly) UR=(urx,uly) BL=(ulx,bly) BR=(urx,bly)
+    std::vector<int> keys;   // indices into the candidate array, in insertion order
+    bool no_more = false;
+};
+}  // namespace
+
+bool distribute_octree(const std::vector<Cand>& keys, int minX, int maxX, int minY, int maxY, int N,
+                       std::vector<int>& out_idx) {
+    out_idx.clear();
+    const int nIni = (maxX - minX) / (maxY - minY);  // integer division (D3)
+    const float hX = static_cast<float>(maxX - minX) / nIni;
+    std::list<Node> nodes;
+    std::vector<Node*> roots(nIni > 0 ? nIni : 0);
+    for (int i = 0; i < nIni; ++i) {
+        Node n;
+        n.ulx = (int)(hX * i);
+        n.urx = (int)(hX * (i + 1));
+        n.uly = 0;
+        n.bly = maxY - minY;
+        nodes.push_back(n);
+        roots[i] = &nodes.back();
+    }
+    for (int k = 0; k < (int)keys.size(); ++k) {
+        int idx = (int)(keys[k].x / hX);
+        if (idx >= 0 && idx < nIni) roots[idx]->keys.push_back(k);
+    }
+    bool finish = false;
+    int guard = 0;
+    while (!finish) {
+        if (++guard > 64) return false;  // the reference would loop forever (unseparable keys)
+        for (auto it = nodes.begin(); it != nodes.end();) {
+            if (it->keys.size() == 1) {
+                it->no_more = true;
+                ++it;
+            } else if (it->keys.empty()) {
+                it = nodes.erase(it);
+            } else {
+                const int halfX = (it->urx - it->ulx) / 2;  // floor (D4)
+                const int halfY = (it->bly - it->uly) / 2;
+                const int midx = it->ulx + halfX, midy = it->uly + halfY;
+                Node c[4];
+                c[0].ulx = it->ulx; c[0].urx = midx;    c[0].uly = it->uly; c[0].bly = midy;
+                c[1].ulx = midx;    c[1].urx = it->urx; c[1].uly = it->uly; c[1].bly = midy;
+                c[2].ulx = it->ulx; c[2].urx = midx;    c[2].uly = midy;    c[2].bly = it->bly;
+                c[3].ulx = midx;    c[3].urx = it->urx; c[3].uly = midy;    c[3].bly = it->bly;
+                for (int k : it->keys) {
+                    const Cand& kp = keys[k];
+                    if (kp.x < (float)midx) {
+                        if (kp.y < (float)midy) c[0].keys.push_back(k);
+                        else c[2].keys.push_back(k);
+                    } else {
+                        if (kp.y < (float)midy) c[1].keys.push_back(k);
+                        else c[3].keys.push_back(k);
+                    }
+                }
+                for (int q = 0; q < 4; ++q) {
+                    c[q].no_more = c[q].keys.size() == 1;
+                    if (!c[q].keys.empty()) nodes.push_front(c[q]);
+                }
+                it = nodes.erase(it);
+            }
+        }
+        bool all_done = true;
+        for (const Node& n : nodes) all_done = all_done && n.no_more;
+        finish = ((long long)nodes.size() >= (long long)N) || all_done;
+    }
+    for (const Node& n : nodes) {
+        if (n.keys.empty()) continue;
+        int best = n.keys[0];  // std::max_element: first of the maxima
+        for (int k : n.keys)
+            if (keys[best].response < keys[k].response) best = k;
+        out_idx.push_back(best);
+    }
+    return true;
+}
+
+// ---------------------------------------------------------------- orientation
+// IC_Angle, reference ORBextractor.cc:21-48.
+static float ic_angle(const Image& img, int cx, int cy, const std::vector<int>& umax) {
+    int m01 = 0, m10 = 0;
+    const uint8_t* center = img.row(cy) + cx;
+    for (int u = -15; u <= 15; ++u) m10 += u * center[u];
+    const int step = img.step;
+    for (int v = 1; v <= 15; ++v) {
+        int vsum = 0;
+        const int d = umax[v];
+        for (int u = -d; u <= d; ++u) {
+            int below = center[u + v * step], above = center[u - v * step];
+            vsum += (below - above);
+            m10 += u * (below + above);
+        }
+        m01 += v * vsum;
+    }
+    return fast_atan2((float)m01, (float)m10);
+}
+
+// ---------------------------------------------------------------- descriptor
+// computeOrbDescriptor / getRotatedValue, reference ORBextractor.cc:53-73.
+static void describe(const Image& blurred, int cx, int cy, float angle_deg, const int8_t* pattern,
+                     uint8_t* desc) {
+    const float factorPI = (float)(3.141592653589793238462643383279502884 / 180.f);
+    const float angle = angle_deg * factorPI;
+    const float a = cosf(angle), b = sinf(angle);
+    const uint8_t* center = blurred.row(cy) + cx;
+    const int step = blurred.step;
+    auto sample = [&](int idx) -> int {
+        const float px = (float)pattern[2 * idx], py = (float)pattern[2 * idx + 1];
+        const int yy = cv_round_f(px * b + py * a);
+        const int xx = cv_round_f(px * a - py * b);
+        return center[yy * step + xx];
+    };
+    for (int i = 0; i < 32; ++i) {
+        int val = 0;
+        for (int j = 0; j < 8; ++j) {
+            int t0 = sample(16 * i + 2 * j), t1 = sample(16 * i + 2 * j + 1);
+            val |= (t0 < t1) << j;
+        }
+        desc[i] = (uint8_t)val;
+    }
+}
+
+// ---------------------------------------------------------------- operator()
+// ORBextractor::operator(), ComputePyramid, ComputeKeyPointsOctTree;
+// reference ORBextractor.cc:442-495, :497-515, :288-357.
+int extract(const Params& p, const Image& img, ExtractResult& out, bool keep_pyramid) {
+    out = ExtractResult();
+    if (img.rows <= 0 || img.cols <= 0 || !img.data) return 0;  // empty image: silent return (:444)
+    if (p.nlevels < 1) return -1;
+    const Tables t = make_tables(p);
+    const int L = p.nlevels;
+
+    // ComputePyramid (:497-515).  The 19-px reflected border the reference adds
+    // around every level is never read on this path, so levels are tight.
+    std::vector<std::vector<uint8_t>> pyr(L);
+    std::vector<int> lr(L), lc(L);
+    for (int l = 0; l < L; ++l) {
+        const float s = t.inv_scale[l];
+        lc[l] = cv_round_f(img.cols * s);
+        lr[l] = cv_round_f(img.rows * s);
+        if (lc[l] <= 0 || lr[l] <= 0) return -1;
+        pyr[l].resize((size_t)lr[l] * lc[l]);
+        if (l == 0) {
+            for (int y = 0; y < lr[0]; ++y) memcpy(&pyr[0][(size_t)y * lc[0]], img.row(y), lc[0]);
+        } else {
+            Image prev{pyr[l - 1].data(), lr[l - 1], lc[l - 1], lc[l - 1]};
+            resize_linear_u8(prev, pyr[l].data(), lr[l], lc[l], lc[l]);
+        }
+    }
+
+    // ComputeKeyPointsOctTree (:288-357)
+    std::vector<std::vector<KeyPoint>> all(L);
+    out.n_candidates.assign(L, 0);
+    out.n_keypoints.assign(L, 0);
+    for (int l = 0; l < L; ++l) {
+        const Image lev{pyr[l].data(), lr[l], lc[l], lc[l]};
+        const int minBX = 19 - 3, minBY = minBX;
+        const int maxBX = lc[l] - 19 + 3, maxBY = lr[l] - 19 + 3;
+        const float width = (float)(maxBX - minBX), height = (float)(maxBY - minBY);
+        const int nCols = (int)(width / 30.f), nRows = (int)(height / 30.f);
+        // levels smaller than one 30-px cell: the reference's cell loops simply do not run
+        // (the float division by zero only feeds the unused wCell/hCell); a non-positive
+        // height is where it really faults (integer division by zero / negative vector size)
+        // (:230: H == 0 -> SIGFPE; nIni = W/H < 0 -> std::vector(nIni) throws)
+        if (maxBY - minBY == 0 || (maxBX - minBX) / (maxBY - minBY) < 0) return -1;
+        const bool has_cells = nCols > 0 && nRows > 0;
+        const int wCell = has_cells ? (int)std::ceil(width / nCols) : 0;
+        const int hCell = has_cells ? (int)std::ceil(height / nRows) : 0;
+        std::vector<Cand> cands;
+        std::vector<FastPoint> cell;
+        for (int i = 0; has_cells && i < nRows; ++i) {
+            const int iniY = minBY + i * hCell;
+            const int maxY = std::min(iniY + hCell + 6, maxBY);
+            for (int j = 0; j < nCols; ++j) {
+                const int iniX = minBX + j * wCell;
+                const int maxX = std::min(iniX + wCell + 6, maxBX);
+                // negative ROI extent: cv::Mat::operator()(Rect) throws in the reference
+                if (maxX - iniX < 0 || maxY - iniY < 0) return -2;
+                Image roi{lev.row(iniY) + iniX, maxY - iniY, maxX - iniX, lev.step};
+                cell.clear();
+                fast9_16_nms(roi, p.iniThFAST, cell);
+                if (cell.empty()) {  // retry only if the post-NMS list is empty (:293-296)
+                    fast9_16_nms(roi, p.minThFAST, cell);
+                    if (roi.rows >= 7 && roi.cols >= 7) out.n_retry_cells++;
+                }
+                for (const FastPoint& fp : cell)
+                    cands.push_back({(float)(fp.x + j * wCell), (float)(fp.y + i * hCell), (float)fp.score});
+            }
+        }
+        out.n_candidates[l] = (int)cands.size();
+        std::vector<int> keep;
+        if (!distribute_octree(cands, minBX, maxBX, minBY, maxBY, t.features_per_level[l], keep))
+            return -3;
+        const int patch = (int)(31 * t.scale[l]);
+        for (int k : keep) {
+            KeyPoint kp;
+            kp.x = cands[k].x + minBX;
+            kp.y = cands[k].y + minBY;
+            kp.size = (float)patch;
+            kp.angle = -1.f;
+            kp.response = cands[k].response;
+            kp.octave = l;
+            kp.class_id = -1;
+            all[l].push_back(kp);
+        }
+        out.n_keypoints[l] = (int)keep.size();
+    }
+    for (int l = 0; l < L; ++l) {
+        const Image lev{pyr[l].data(), lr[l], lc[l], lc[l]};
+        for (KeyPoint& kp : all[l]) kp.angle = ic_angle(lev, cv_round_f(kp.x), cv_round_f(kp.y), t.umax);
+    }
+
+    size_t total = 0;
+    for (auto& v : all) total += v.size();
+    if (keep_pyramid) {
+        out.pyramid = pyr;
+        out.level_rows = lr;
+        out.level_cols = lc;
+    }
+    if (total == 0) return 0;  // descriptors.release(), keypoints untouched (:460-463)
+    out.descriptors.assign(total * 32, 0);
+    out.keypoints.reserve(total);
+    size_t off = 0;
+    std::vector<uint8_t> blurred;
+    for (int l = 0; l < L; ++l) {
+        if (all[l].empty()) continue;
+        const Image lev{pyr[l].data(), lr[l], lc[l], lc[l]};
+        blurred.resize(pyr[l].size());
+        gaussian_blur7_u8(lev, blurred.data(), lc[l]);
+        const Image bl{blurred.data(), lr[l], lc[l], lc[l]};
+        for (KeyPoint& kp : all[l]) {
+            describe(bl, cv_round_f(kp.x), cv_round_f(kp.y), kp.angle, t.pattern.data(),
+                     &out.descriptors[off * 32]);
+            ++off;
+        }
+        if (l != 0) {
+            const float s = t.scale[l];
+            for (KeyPoint& kp : all[l]) {
+                kp.x *= s;
+                kp.y *= s;
+            }
+        }
+        out.keypoints.insert(out.keypoints.end(), all[l].begin(), all[l].end());
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------- matcher
+// ORBmatcher::DescriptorDistance, reference ORBmatcher.cc:896-908.
+int descriptor_distance(const uint8_t* a, const uint8_t* b) {
+    int dist = 0;
+    for (int i = 0; i < 8; ++i) {
+        uint32_t x, y;
+        memcpy(&x, a + 4 * i, 4);
+        memcpy(&y, b + 4 * i, 4);
+        uint32_t v = x ^ y;
+        v = v - ((v >> 1) & 0x55555555u);
+        v = (v & 0x33333333u) + ((v >> 2) & 0x33333333u);
+        dist += (int)((((v + (v >> 4)) & 0xF0F0F0Fu) * 0x1010101u) >> 24);
+    }
+    return dist;
+}
+
+// ---------------------------------------------------------------- synthetic frames (A.8)
+static inline uint64_t splitmix64(uint64_t k) {
+    uint64_t z = k + 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+void synth_frame(uint8_t* dst, int rows, int cols, int step, uint64_t seed, uint64_t frame,
+                 int variant, int right) {
+    static const int blocksA[4] = {5, 11, 23, 47};
+    static const int blocksB[4] = {4, 8, 16, 32};
+    static const double wts[4] = {0.4, 0.3, 0.2, 0.1};
+    const int* bs = variant == 1 ? blocksB : blocksA;
+    const uint64_t base = (seed << 40) ^ (frame << 24);
+    for (int y = 0; y < rows; ++y) {
+        for (int x = 0; x < cols; ++x) {
+            int sx = x;
+            if (right) {  // per-block disparity 0..40 px: right(x,y) = left(x + d, y)
+                uint64_t dk = base ^ (7ull << 60) ^ ((uint64_t)(y / 47) << 12) ^ (uint64_t)(x / 94);
+                sx = x + (int)((splitmix64(dk) & 0xFF) % 41);
+            }
+            double acc = 0.0;
+            for (int o = 0; o < 4; ++o) {
+                uint64_t k = base ^ ((uint64_t)o << 60) ^ ((uint64_t)(y / bs[o]) << 12) ^ (uint64_t)(sx / bs[o]);
+                acc += wts[o] * (double)(splitmix64(k) & 0xFF);
+            }
+            if (variant == 1 && x < cols / 2) acc = 128.0 + (acc - 128.0) * 0.25;
+            double v = std::floor(acc + 0.5);
+            dst[(size_t)y * step + x] = (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
+        }
+    }
+}
+
+}  // namespace orb_oracle
+
+// ============================================================ C ABI (ctypes)
+using namespace orb_oracle;
+
+extern "C" {
+
+int orc_extract(int nfeatures, float scaleFactor, int nlevels, int iniTh, int minTh,
+                const uint8_t* img, int rows, int cols, int step, KeyPoint* kps, uint8_t* desc,
+                int cap, int* count, int* per_level_candidates, int* per_level_kept,
+                int* n_retry_cells) {
+    Params p{nfeatures, scaleFactor, nlevels, iniTh, minTh};
+    ExtractResult r;
+    int rc = extract(p, Image{img, rows, cols, step}, r, false);
+    if (rc != 0) return rc;
+    int n = (int)r.keypoints.size();
+    if (count) *count = n;
+    if (n > cap) return -10;
+    if (n) {
+        memcpy(kps, r.keypoints.data(), (size_t)n * sizeof(KeyPoint));
+        memcpy(desc, r.descriptors.data(), (size_t)n * 32);
+    }
+    for (int l = 0; l < nlevels; ++l) {
+        if (per_level_candidates) per_level_candidates[l] = l < (int)r.n_candidates.size() ? r.n_candidates[l] : 0;
+        if (per_level_kept) per_level_kept[l] = l < (int)r.n_keypoints.size() ? r.n_keypoints[l] : 0;
+    }
+    if (n_retry_cells) *n_retry_cells = r.n_retry_cells;
+    return 0;
+}
+
+int orc_tables(int nfeatures, float scaleFactor, int nlevels, float* scale, float* inv_scale,
+               float* sigma2, float* inv_sigma2, int* nfeat_per_level, int* umax16) {
+    Tables t = make_tables(Params{nfeatures, scaleFactor, nlevels, 20, 7});
+    for (int i = 0; i < nlevels; ++i) {
+        scale[i] = t.scale[i];
+        inv_scale[i] = t.inv_scale[i];
+        sigma2[i] = t.sigma2[i];
+        inv_sigma2[i] = t.inv_sigma2[i];
+        nfeat_per_level[i] = t.features_per_level[i];
+    }
+    for (int i = 0; i < 16; ++i) umax16[i] = t.umax[i];
+    return 0;
+}
+
+int orc_pyramid(float scaleFactor, int nlevels, const uint8_t* img, int rows, int cols, int step,
+                int level, uint8_t* dst, int dst_cap, int* lrows, int* lcols) {
+    Tables t = make_tables(Params{1000, scaleFactor, nlevels, 20, 7});
+    std::vector<uint8_t> prev((size_t)rows * cols), cur;
+    for (int y = 0; y < rows; ++y) memcpy(&prev[(size_t)y * cols], img + (size_t)y * step, cols);
+    int pr = rows, pc = cols;
+    for (int l = 1; l <= level; ++l) {
+        int c = cv_round_f(cols * t.inv_scale[l]), r = cv_round_f(rows * t.inv_scale[l]);
+        cur.assign((size_t)r * c, 0);
+        resize_linear_u8(Image{prev.data(), pr, pc, pc}, cur.data(), r, c, c);
+        prev.swap(cur);
+        pr = r;
+        pc = c;
+    }
+    *lrows = pr;
+    *lcols = pc;
+    if ((size_t)pr * pc > (size_t)dst_cap) return -10;
+    memcpy(dst, prev.data(), (size_t)pr * pc);
+    return 0;
+}
+
+void orc_resize(const uint8_t* src, int srows, int scols, int sstep, uint8_t* dst, int drows,
+                int dcols, int dstep) {
+    resize_linear_u8(Image{src, srows, scols, sstep}, dst, drows, dcols, dstep);
+}
+
+void orc_blur7(const uint8_t* src, int rows, int cols, int step, uint8_t* dst, int dstep) {
+    gaussian_blur7_u8(Image{src, rows, cols, step}, dst, dstep);
+}
+
+int orc_fast(const uint8_t* img, int rows, int cols, int step, int threshold, int* xys, int cap) {
+    std::vector<FastPoint> v;
+    fast9_16_nms(Image{img, rows, cols, step}, threshold, v);
+    int n = (int)v.size();
+    for (int i = 0; i < n && i < cap; ++i) {
+        xys[3 * i] = v[i].x;
+        xys[3 * i + 1] = v[i].y;
+        xys[3 * i + 2] = v[i].score;
+    }
+    return n;
+}
+
+float orc_fast_atan2(float y, float x) { return fast_atan2(y, x); }
+
+int orc_octree(const float* xyr, int n, int minX, int maxX, int minY, int maxY, int N, int* out_idx,
+               int cap) {
+    std::vector<Cand> keys(n);
+    for (int i = 0; i < n; ++i) keys[i] = Cand{xyr[3 * i], xyr[3 * i + 1], xyr[3 * i + 2]};
+    std::vector<int> out;
+    if (!distribute_octree(keys, minX, maxX, minY, maxY, N, out)) return -3;
+    int k = (int)out.size();
+    for (int i = 0; i < k && i < cap; ++i) out_idx[i] = out[i];
+    return k;
+}
+
+float orc_ic_angle(const uint8_t* img, int rows, int cols, int step, int x, int y) {
+    Tables t = make_tables(Params{1000, 1.2f, 8, 20, 7});
+    return ic_angle(Image{img, rows, cols, step}, x, y, t.umax);
+}
+
+void orc_describe(const uint8_t* blurred, int rows, int cols, int step, int x, int y, float angle,
+                  uint8_t* desc32) {
+    Tables t = make_tables(Params{1000, 1.2f, 8, 20, 7});
+    describe(Image{blurred, rows, cols, step}, x, y, angle, t.pattern.data(), desc32);
+}
+
+int orc_distance(const uint8_t* a, const uint8_t* b) { return descriptor_distance(a, b); }
+
+// The scan every ORBmatcher search shares (reference ORBmatcher.cc:49-55,
+// :225-231, :321-327): candidates in list order, strict '<' updates.
+void orc_match_all(const uint8_t* q, int nq, const uint8_t* t, int nt, int* best_idx,
+                   int* best_dist, int* second_dist) {
+    for (int i = 0; i < nq; ++i) {
+        int best = INT_MAX, second = INT_MAX, idx = -1;
+        for (int j = 0; j < nt; ++j) {
+            int d = descriptor_distance(q + 32 * (size_t)i, t + 32 * (size_t)j);
+            if (d < best) {
+                second = best;
+                best = d;
+                idx = j;
+            } else if (d < second) {
+                second = d;
+            }
+        }
+        best_idx[i] = idx;
+        best_dist[i] = best;
+        second_dist[i] = second;
+    }
+}
+
+// Windowed variant: query i scans cand[offsets[i]..offsets[i+1]).  tie_last=0:
+// the scan above.  tie_last=1: SearchForTriangulation's rule (reference
+// ORBmatcher.cc:404-419): start at max_dist, accept d <= max_dist && d <= best
+// (ties -> last candidate); second is not tracked (INT_MAX).  With tie_last=0
+// max_dist is ignored (thresholds are applied by the caller).
+void orc_match_csr(const uint8_t* q, int nq, const uint8_t* t, int nt, const int* offsets,
+                   const int* cand, int tie_last, int max_dist, int* best_idx, int* best_dist,
+                   int* second_dist) {
+    (void)nt;
+    for (int i = 0; i < nq; ++i) {
+        int best = tie_last ? max_dist : INT_MAX, second = INT_MAX, idx = -1;
+        for (int c = offsets[i]; c < offsets[i + 1]; ++c) {
+            int j = cand[c];
+            int d = descriptor_distance(q + 32 * (size_t)i, t + 32 * (size_t)j);
+            if (tie_last) {
+                if (d > max_dist || d > best) continue;
+                best = d;
+                idx = j;
+            } else if (d < best) {
+                second = best;
+                best = d;
+                idx = j;
+            } else if (d < second) {
+                second = d;
+            }
+        }
+        best_idx[i] = idx;
+        best_dist[i] = best;
+        second_dist[i] = second;
+    }
+}
+
+// Hamming part of Frame::ComputeStereoMatches, reference Frame.cc:446-529.
+// best_r[i] = right index of the best candidate (or -1 when the scan never
+// improved on TH_HIGH=100), best_dist[i] = its distance (100 when none).
+// Returns 0, or -1 if a right keypoint's row band leaves the image (the
+// reference indexes vRowIndices out of bounds there).
+int orc_stereo_match(const KeyPoint* kl, const uint8_t* dl, int nl, const KeyPoint* kr,
+                     const uint8_t* dr, int nr, const float* scale, int nlevels, int rows, float bf,
+                     float fx, int* best_r, int* best_dist) {
+    (void)nlevels;
+    std::vector<std::vector<int>> rowidx(rows);
+    for (int iR = 0; iR < nr; ++iR) {
+        const float y = kr[iR].y;
+        const float r = 2.0f * scale[kr[iR].octave];
+        const int maxr = (int)std::ceil(y + r), minr = (int)std::floor(y - r);
+        if (minr < 0 || maxr >= rows) return -1;
+        for (int yi = minr; yi <= maxr; ++yi) rowidx[yi].push_back(iR);
+    }
+    const float mb = bf / fx;  // Frame.cc:215
+    const float minD = 0, maxD = bf / mb;
+    for (int iL = 0; iL < nl; ++iL) {
+        best_r[iL] = -1;
+        best_dist[iL] = 100;
+        const int levelL = kl[iL].octave;
+        const float vL = kl[iL].y, uL = kl[iL].x;
+        const std::vector<int>& c = rowidx[(size_t)vL];
+        if (c.empty()) continue;
+        const float minU = uL - maxD, maxU = uL - minD;
+        if (maxU < 0) continue;
+        int best = 100, bi = -1;
+        for (int iR : c) {
+            if (kr[iR].octave < levelL - 1 || kr[iR].octave > levelL + 1) continue;
+            const float uR = kr[iR].x;
+            if (uR >= minU && uR <= maxU) {
+                int d = descriptor_distance(dl + 32 * (size_t)iL, dr + 32 * (size_t)iR);
+                if (d < best) {
+                    best = d;
+                    bi = iR;
+                }
+            }
+        }
+        best_r[iL] = bi;
+        best_dist[iL] = best;
+    }
+    return 0;
+}
+
+void orc_synth_frame(uint8_t* dst, int rows, int cols, int step, uint64_t seed, uint64_t frame,
+                     int variant, int right) {
+    synth_frame(dst, rows, cols, step, seed, frame, variant, right);
+}
+
+double orc_extract_many(int nfeatures, float scaleFactor, int nlevels, int iniTh, int minTh,
+                        int rows, int cols, uint64_t seed, int first_frame, int nframes,
+                        int nthreads, long long* total_keypoints) {
+    Params p{nfeatures, scaleFactor, nlevels, iniTh, minTh};
+    std::vector<std::vector<uint8_t>> frames(nframes);
+    {
+        std::atomic<int> next{0};
+        std::vector<std::thread> th;
+        for (int w = 0; w < nthreads; ++w)
+            th.emplace_back([&] {
+                for (int f; (f = next.fetch_add(1)) < nframes;) {
+                    frames[f].resize((size_t)rows * cols);
+                    synth_frame(frames[f].data(), rows, cols, cols, seed, (uint64_t)(first_frame + f), 0, 0);
+                }
+            });
+        for (auto& t : th) t.join();
+    }
+    std::atomic<int> next{0};
+    std::atomic<long long> total{0};
+    auto t0 = std::chrono::steady_clock::now();
+    std::vector<std::thread> th;
+    for (int w = 0; w < nthreads; ++w)
+        th.emplace_back([&] {
+            for (int f; (f = next.fetch_add(1)) < nframes;) {
+                ExtractResult r;
+                extract(p, Image{frames[f].data(), rows, cols, cols}, r, false);
+                total += (long long)r.keypoints.size();
+            }
+        });
+    for (auto& t : th) t.join();
+    auto t1 = std::chrono::steady_clock::now();
+    if (total_keypoints) *total_keypoints = total.load();
+    return std::chrono::duration<double>(t1 - t0).count();
+}
+
+}  // extern "C"
