@@ -1,0 +1,179 @@
+/*
+ * orb_b200.h -- C ABI of the B200-native ORB front end (liborb_b200.so).
+ *
+ * Drop-in boundary for the two data-parallel hot paths of
+ * WangHewei16/ORB-SLAM-System (an ORB-SLAM2 fork): ORBextractor::operator()
+ * and the ORBmatcher / Frame Hamming searches.  The reference has no FFI layer;
+ * the boundary is the C++ ABI of two classes inside libORB_SLAM2.so.  A thin
+ * C++ adapter (orb_slam_system_b200/adapter/) keeps those class signatures and
+ * calls the entry points below; INTEGRATION.md shows the binding.
+ *
+ * Conventions: plain C types only; every function returns an orb_status
+ * (0 = ok); no exceptions cross the boundary; outputs go to caller-owned
+ * buffers with explicit capacities; one handle per calling thread (each handle
+ * owns a CUDA stream and its device memory), mirroring the reference's
+ * one-extractor-instance-per-camera use (reference src/Tracking.cc:76-82,
+ * src/Frame.cc:58-61).  There is no CPU fallback: if no CUDA device is usable
+ * the create calls fail with ORB_ERR_CUDA.
+ *
+ * All file:line citations are relative to the reference repository root.
+ */
+#ifndef ORB_B200_H
+#define ORB_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum orb_status {
+    ORB_OK = 0,
+    ORB_ERR_INVALID = -1,     /* bad argument */
+    ORB_ERR_SHAPE = -2,       /* image shape on which the reference itself faults */
+    ORB_ERR_CAPACITY = -3,    /* caller buffer too small; counts hold the required sizes */
+    ORB_ERR_CUDA = -4,        /* CUDA runtime/driver error; see orb_last_error() */
+    ORB_ERR_UNSEPARABLE = -5  /* octree cannot terminate (the reference would loop forever) */
+} orb_status;
+
+/* Same 28-byte layout as cv::KeyPoint (reference include/Frame.h:117-118 holds
+ * std::vector<cv::KeyPoint>): pt.x, pt.y, size, angle, response, octave, class_id. */
+typedef struct orb_keypoint {
+    float x, y;
+    float size;
+    float angle;
+    float response;
+    int32_t octave;
+    int32_t class_id;
+} orb_keypoint;
+
+/* Arguments of ORBextractor::ORBextractor (include/ORBextractor.h:31-32); read from the
+ * settings YAML keys ORBextractor.{nFeatures,scaleFactor,nLevels,iniThFAST,minThFAST}
+ * (src/Tracking.cc:70-74). */
+typedef struct orb_params {
+    int32_t nfeatures;
+    float scale_factor;
+    int32_t nlevels; /* 1..16 */
+    int32_t ini_th_fast;
+    int32_t min_th_fast;
+} orb_params;
+
+typedef struct orb_extractor orb_extractor; /* opaque */
+typedef struct orb_matcher orb_matcher;     /* opaque */
+
+/* ---- extractor: replaces ORBextractor (include/ORBextractor.h:26-93) -------------------- */
+
+/* ORBextractor::ORBextractor (src/ORBextractor.cc:116-170).  Device buffers are sized for
+ * max_batch frames of up to max_rows x max_cols.  device = CUDA ordinal. */
+int orb_extractor_create(const orb_params* params, int max_rows, int max_cols, int max_batch,
+                         int device, orb_extractor** out);
+void orb_extractor_destroy(orb_extractor* h);
+
+/* GetScaleFactors / GetInverseScaleFactors / GetScaleSigmaSquares /
+ * GetInverseScaleSigmaSquares (include/ORBextractor.h:43-63) and mnFeaturesPerLevel.
+ * Each array receives nlevels entries; NULL pointers are skipped. */
+int orb_extractor_tables(const orb_extractor* h, float* scale, float* inv_scale, float* sigma2,
+                         float* inv_sigma2, int32_t* features_per_level);
+
+/* Upper bound on keypoints per frame for rows x cols images (the fork's octree returns up
+ * to <4x the per-level quota); use it to size kps/desc buffers. */
+int orb_extractor_keypoint_bound(const orb_extractor* h, int rows, int cols, int* bound);
+
+/* ORBextractor::operator() (src/ORBextractor.cc:442-495) on one host image (8-bit gray,
+ * `stride` bytes per row).  Writes *count keypoints (cv::KeyPoint layout) and count x 32
+ * descriptor bytes, rows in keypoint order.  Empty image (rows or cols 0, or img NULL):
+ * returns ORB_OK with *count = 0, like the reference's silent return (:444-445).
+ * Synchronous: results are in the host buffers on return. */
+int orb_extract(orb_extractor* h, const uint8_t* img, int rows, int cols, size_t stride,
+                orb_keypoint* kps, uint8_t* desc, int cap, int* count);
+
+/* n same-shape host frames in one launch sequence (frame f at imgs + f*frame_stride);
+ * outputs for frame f at kps + f*cap, desc + f*cap*32, counts[f].  Host buffers should be
+ * pinned for full PCIe rate; copies overlap the kernels of neighbouring sub-batches. */
+int orb_extract_batch(orb_extractor* h, int n, const uint8_t* imgs, int rows, int cols,
+                      size_t stride, size_t frame_stride, orb_keypoint* kps, uint8_t* desc,
+                      int cap, int* counts);
+
+/* Same, with every buffer resident in device memory (inputs already in HBM; no copies).
+ * Asynchronous on the handle's stream; call orb_extractor_sync before reading results
+ * from another stream.  d_imgs needs stride % 16 == 0 and 16-byte aligned base. */
+int orb_extract_batch_device(orb_extractor* h, int n, const uint8_t* d_imgs, int rows, int cols,
+                             size_t stride, size_t frame_stride, orb_keypoint* d_kps,
+                             uint8_t* d_desc, int cap, int* d_counts);
+int orb_extractor_sync(orb_extractor* h);
+/* The handle's CUDA stream (cudaStream_t) so callers can order their own work after it. */
+void* orb_extractor_stream(orb_extractor* h);
+
+/* Pyramid level `level` of frame `frame` of the last call, tightly cropped (no border), to a
+ * host buffer -- what refills the public ORBextractor::mvImagePyramid
+ * (include/ORBextractor.h:65, read by src/Frame.cc:453,543-560).  dst may be NULL to
+ * query the size only. */
+int orb_get_pyramid_level(orb_extractor* h, int frame, int level, uint8_t* dst, size_t dst_stride,
+                          int* rows, int* cols);
+
+/* Counters of the last call for frame `frame` (arrays of nlevels; NULL skipped):
+ * FAST candidates handed to the octree and keypoints kept, per level. */
+int orb_extractor_level_stats(orb_extractor* h, int frame, int32_t* candidates, int32_t* kept);
+
+/* ---- matcher: replaces the Hamming scans of ORBmatcher / Frame --------------------------- */
+
+int orb_matcher_create(int device, orb_matcher** out);
+void orb_matcher_destroy(orb_matcher* m);
+
+/* ORBmatcher::DescriptorDistance (src/ORBmatcher.cc:896-908) is the unit.  The scan every
+ * search shares (src/ORBmatcher.cc:49-55, :225-231, :321-327): candidates in list order,
+ * `if d<best {second=best; best=d; idx=i} else if d<second {second=d}`, both starting at
+ * INT_MAX.  Outputs per query: best_idx (-1 if no candidate), best_dist, second_dist
+ * (INT_MAX when absent).  Accept rules (:58, :235, :329) stay with the caller. */
+
+/* Brute force: every query against all train rows in index order (BASELINE config 4).
+ * Host buffers; q is nq x 32 bytes, t is nt x 32 bytes. */
+int orb_match_all(orb_matcher* m, const uint8_t* q, int nq, const uint8_t* t, int nt,
+                  int32_t* best_idx, int32_t* best_dist, int32_t* second_dist);
+
+/* npairs independent (query set, train set) pairs with fixed strides, device or host
+ * buffers (on_device != 0: all pointers are device pointers, asynchronous).
+ * Pair p: q + p*q_stride (nq[p] rows), t + p*t_stride (nt[p] rows); outputs at p*out_stride. */
+int orb_match_all_batch(orb_matcher* m, int npairs, const uint8_t* q, const int32_t* nq,
+                        size_t q_stride, const uint8_t* t, const int32_t* nt, size_t t_stride,
+                        int32_t* best_idx, int32_t* best_dist, int32_t* second_dist,
+                        size_t out_stride, int on_device);
+
+typedef enum orb_tie_rule {
+    ORB_TIE_FIRST_MIN = 0, /* the shared scan above */
+    ORB_TIE_LAST_MIN = 1   /* SearchForTriangulation (src/ORBmatcher.cc:404-419): best starts at
+                              max_dist, accept d <= max_dist && d <= best, ties -> last */
+} orb_tie_rule;
+
+/* Windowed search: query i scans train rows cand[offsets[i] .. offsets[i+1]) in that order
+ * (candidate lists from Frame::GetFeaturesInArea src/Frame.cc:307-360, DBoW2 node buckets,
+ * ...).  max_dist is used by ORB_TIE_LAST_MIN only. */
+int orb_match_csr(orb_matcher* m, const uint8_t* q, int nq, const uint8_t* t, int nt,
+                  const int32_t* offsets, const int32_t* cand, int tie_rule, int max_dist,
+                  int32_t* best_idx, int32_t* best_dist, int32_t* second_dist);
+
+/* Hamming part of Frame::ComputeStereoMatches (src/Frame.cc:446-529): row-band candidate
+ * table, octave and disparity gates, first minimum below TH_HIGH=100.  best_r[i] = right
+ * keypoint index or -1; best_dist[i] = its distance (100 when none).  scale = the
+ * extractor's mvScaleFactor (nlevels floats); rows = image rows; bf, fx from the YAML. */
+int orb_stereo_match(orb_matcher* m, const orb_keypoint* kps_left, const uint8_t* desc_left,
+                     int n_left, const orb_keypoint* kps_right, const uint8_t* desc_right,
+                     int n_right, const float* scale, int nlevels, int rows, float bf, float fx,
+                     int32_t* best_r, int32_t* best_dist);
+
+int orb_matcher_sync(orb_matcher* m);
+void* orb_matcher_stream(orb_matcher* m);
+
+/* ---- misc ------------------------------------------------------------------------------- */
+
+/* Thread-local description of the last error on this thread ("" if none). */
+const char* orb_last_error(void);
+/* Number of kernels this library has launched in this process (for bench accounting). */
+uint64_t orb_kernel_launch_count(void);
+const char* orb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ORB_B200_H */

@@ -1,0 +1,825 @@
+// Hand-written sm_100a kernels of the ORB extract + describe path.
+//
+// Path (reference src/ORBextractor.cc): ComputePyramid :497-515 -> k_resize;
+// ComputeKeyPointsOctTree :288-357 (per-cell cv::FAST + retry) -> k_detect;
+// DistributeOctTree :228-286 -> k_octree (closed form of the list surgery);
+// IC_Angle :21-48, GaussianBlur :479, computeOrbDescriptor :57-73 -> k_blur, k_describe.
+// All integer results are bit-exact with the reference semantics; float math is
+// compiled with -fmad=false and IEEE div so it follows the oracle step by step.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "orb_plan.h"
+#include "extract_kernels.h"
+
+// ------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned vmax3(unsigned a, unsigned b, unsigned c) { return __vimax3_u16x2(a, b, c); }
+__device__ __forceinline__ unsigned vmin3(unsigned a, unsigned b, unsigned c) { return __vimin3_u16x2(a, b, c); }
+
+// ------------------------------------------------------------------------------------------
+// k_resize: cv::resize INTER_LINEAR 8UC1 (fixed point), one level from the
+// previous one.  4 output pixels per thread, one 32-bit store.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_resize(const uint8_t* __restrict__ src, int spitch,
+                                                unsigned long long splane, uint8_t* __restrict__ dst,
+                                                int dpitch, unsigned long long dplane, int drows, int dcols,
+                                                const int* __restrict__ xtab, const int* __restrict__ xcoef,
+                                                const int* __restrict__ ytab, const int* __restrict__ ycoef) {
+    const int x4 = (blockIdx.x * 64 + threadIdx.x) * 4;
+    const int y = blockIdx.y * 4 + threadIdx.y;
+    if (x4 >= dcols || y >= drows) return;
+    const int f = blockIdx.z;
+    const int yt = __ldg(ytab + y), yc = __ldg(ycoef + y);
+    const int b0 = yc & 0xffff, b1 = yc >> 16;
+    const uint8_t* S0 = src + f * splane + (size_t)(yt & 0xffff) * spitch;
+    const uint8_t* S1 = src + f * splane + (size_t)(yt >> 16) * spitch;
+    unsigned out = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int x = x4 + k;
+        if (x < dcols) {
+            const int xt = __ldg(xtab + x), xc = __ldg(xcoef + x);
+            const int s = xt & 0xffff, s1 = xt >> 16;
+            const int a0 = xc & 0xffff, a1 = xc >> 16;
+            const int r0 = __ldg(S0 + s) * a0 + __ldg(S0 + s1) * a1;
+            const int r1 = __ldg(S1 + s) * a0 + __ldg(S1 + s1) * a1;
+            const int v = (((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2) >> 2;
+            out |= (unsigned)(v & 0xff) << (8 * k);
+        }
+    }
+    *reinterpret_cast<unsigned*>(dst + f * dplane + (size_t)y * dpitch + x4) = out;
+}
+
+// ------------------------------------------------------------------------------------------
+// k_detect: per-cell FAST-9/16 + cell-local NMS + iniTh/minTh retry.
+//
+// One CTA = one tile = `tileCells` FAST cells of one cell row of one level of one frame,
+// staged in shared memory (image tile <= 256 x 65 px).  Scores never go to HBM.
+//   pass A  exact corner score m = max(c - min_arcs max_arc r, max_arcs min_arc r - c) for
+//           4 pixels per thread on packed u16x2 lanes (VIMNMX3.U16x2), stored as
+//           u = max(m, lowTh) - lowTh in a byte tile (0 = not a corner at lowTh).
+//   pass B  strict 8-neighbour maximum inside the pixel's own cell; per-cell flag
+//           "has a survivor at iniTh" (cv::FAST + NMS returned non-empty).
+//   pass C  emit survivors at iniTh, or at minTh where the cell flag is clear
+//           (reference ORBextractor.cc:293-296,330-331).
+// cv::FAST semantics: candidates exist 3 px inside the cell image, NMS
+// neighbours outside the cell's candidate area count as 0, response = m - 1.
+// ------------------------------------------------------------------------------------------
+struct DetectSmem {
+    unsigned img[DET_TILE_H][DET_SP / 4];    // image tile, later reused as the survivor tile F
+    unsigned sc[DET_TILE_H][DET_SP / 4];     // score tile with a one-word / one-row zero border
+    int cellHasIni[16];
+    int nEmit;
+    int emitBase;
+    int emitFill;
+};
+
+__device__ __forceinline__ void fast_score_pairs(const unsigned (&r)[16], unsigned c2, unsigned low2,
+                                                 unsigned neglow2, unsigned& u) {
+    // M3/m3 over 3 contiguous ring pixels, M9/m9 over 9 contiguous, then the min/max over arcs.
+    unsigned M3[16], m3[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        M3[k] = vmax3(r[k], r[(k + 1) & 15], r[(k + 2) & 15]);
+        m3[k] = vmin3(r[k], r[(k + 1) & 15], r[(k + 2) & 15]);
+    }
+    unsigned A = 0x00ff00ffu, B = 0u;
+#pragma unroll
+    for (int k = 0; k < 16; k += 2) {
+        const unsigned M9a = vmax3(M3[k], M3[(k + 3) & 15], M3[(k + 6) & 15]);
+        const unsigned M9b = vmax3(M3[k + 1], M3[(k + 4) & 15], M3[(k + 7) & 15]);
+        A = vmin3(A, M9a, M9b);
+        const unsigned m9a = vmin3(m3[k], m3[(k + 3) & 15], m3[(k + 6) & 15]);
+        const unsigned m9b = vmin3(m3[k + 1], m3[(k + 4) & 15], m3[(k + 7) & 15]);
+        B = vmax3(B, m9a, m9b);
+    }
+    // m = max(c - A, B - c) per signed 16-bit lane; u = max(m, low) - low
+    const unsigned d1 = __vsub2(c2, A);
+    const unsigned d2 = __vsub2(B, c2);
+    const unsigned m = __vmaxs2(d1, d2);
+    u = __vadd2(__vmaxs2(m, low2), neglow2);
+}
+
+__global__ void __launch_bounds__(DET_THREADS) k_detect(const __grid_constant__ OrbPlan plan) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    DetectSmem& sm = *reinterpret_cast<DetectSmem*>(smem_raw);
+
+    const int f = blockIdx.y;
+    int tile = blockIdx.x;
+    int l = 0;
+    for (; l < plan.nlevels; ++l) {
+        const OrbLevel& L = plan.lv[l];
+        if (L.src == l && tile >= L.tileBase && tile < L.tileBase + L.nTiles) break;
+    }
+    if (l >= plan.nlevels) return;
+    const OrbLevel& L = plan.lv[l];
+    tile -= L.tileBase;
+    const int ci = tile / L.tilesX, tx = tile - ci * L.tilesX;
+    const int j0 = tx * L.tileCells, j1 = min(j0 + L.tileCells, L.nCols);
+    const int maxBX = L.cols - ORB_MINB, maxBY = L.rows - ORB_MINB;
+    const int X0 = ORB_MINB + j0 * L.wCell;
+    const int X1 = min(ORB_MINB + j1 * L.wCell + 6, maxBX);
+    const int Y0 = ORB_MINB + ci * L.hCell;
+    const int Y1 = min(Y0 + L.hCell + 6, maxBY);
+    const int TW = X1 - X0, TH = Y1 - Y0;
+    const int CW = TW - 6, CH = TH - 6;  // candidate area
+    if (CW <= 0 || CH <= 0) return;
+    const int QR = (CW + 3) >> 2;  // 4-pixel groups per candidate row
+    const int tid = threadIdx.x;
+
+    // ---- stage the image tile: smem byte (r, c) = level pixel (Y0 + r, X0 + c)
+    {
+        const uint8_t* base = L.img + (size_t)f * L.plane;
+        const int wb = X0 >> 2, sh = (X0 & 3) * 8;
+        const int nw = min((TW + 9) >> 2, DET_SP / 4);
+        const int pitchW = L.pitch >> 2;
+        for (int i = tid; i < TH * nw; i += DET_THREADS) {
+            const int r = i / nw, k = i - r * nw;
+            const unsigned* g = reinterpret_cast<const unsigned*>(base + (size_t)(Y0 + r) * L.pitch);
+            const int idx = wb + k;
+            const unsigned lo = idx < pitchW ? __ldg(g + idx) : 0u;
+            const unsigned hi = idx + 1 < pitchW ? __ldg(g + idx + 1) : 0u;
+            sm.img[r][k] = __funnelshift_r(lo, hi, sh);
+        }
+        // zero border of the score tile: rows 0 and CH+1, words 0 and QR+1
+        for (int i = tid; i < 2 * (QR + 2); i += DET_THREADS) {
+            const int r = i < QR + 2 ? 0 : CH + 1;
+            sm.sc[r][i < QR + 2 ? i : i - (QR + 2)] = 0u;
+        }
+        for (int i = tid; i < 2 * (CH + 2); i += DET_THREADS) {
+            const int r = i >> 1;
+            sm.sc[r][(i & 1) ? QR + 1 : 0] = 0u;
+        }
+        if (tid < 16) sm.cellHasIni[tid] = 0;
+        if (tid == 0) {
+            sm.nEmit = 0;
+            sm.emitFill = 0;
+        }
+    }
+    __syncthreads();
+
+    // ---- pass A: scores.  thread (q, r): candidate cols 4q..4q+3 of candidate row r;
+    // candidate col cx sits at tile byte column cx + 3.
+    const unsigned low2 = (unsigned)plan.lowTh * 0x00010001u;
+    const unsigned neglow2 = ((unsigned)(-plan.lowTh) & 0xffffu) * 0x00010001u;
+    {
+        const int q = tid & 63;
+        if (q < QR) {
+            for (int r = tid >> 6; r < CH; r += DET_THREADS / 64) {
+                // rows r..r+6 of the tile; words q, q+1, q+2 hold tile bytes 4q..4q+11 = b0..b11,
+                // candidate pixels p0..p3 = b3..b6, ring offset dx reads b(3+dx)..b(6+dx)
+                unsigned w[7][3];
+#pragma unroll
+                for (int rr = 0; rr < 7; ++rr) {
+                    w[rr][0] = sm.img[r + rr][q];
+                    w[rr][1] = sm.img[r + rr][q + 1];
+                    w[rr][2] = sm.img[r + rr][q + 2];
+                }
+                // unaligned 4-byte windows: win(rr, dx) = bytes b(3+dx)..b(6+dx) of row rr
+#define WIN(rr, dx)                                                                   \
+    ((dx) == -3 ? w[rr][0]                                                            \
+     : (dx) == -2 ? __byte_perm(w[rr][0], w[rr][1], 0x4321)                           \
+     : (dx) == -1 ? __byte_perm(w[rr][0], w[rr][1], 0x5432)                           \
+     : (dx) == 0  ? __byte_perm(w[rr][0], w[rr][1], 0x6543)                           \
+     : (dx) == 1  ? w[rr][1]                                                          \
+     : (dx) == 2  ? __byte_perm(w[rr][1], w[rr][2], 0x4321)                           \
+                  : __byte_perm(w[rr][1], w[rr][2], 0x5432))
+                // ring index k -> (dx, dy); tile row = 3 + dy
+                unsigned ring[16];
+                ring[0] = WIN(6, 0);    // (0, 3)
+                ring[1] = WIN(6, 1);    // (1, 3)
+                ring[2] = WIN(5, 2);    // (2, 2)
+                ring[3] = WIN(4, 3);    // (3, 1)
+                ring[4] = WIN(3, 3);    // (3, 0)
+                ring[5] = WIN(2, 3);    // (3,-1)
+                ring[6] = WIN(1, 2);    // (2,-2)
+                ring[7] = WIN(0, 1);    // (1,-3)
+                ring[8] = WIN(0, 0);    // (0,-3)
+                ring[9] = WIN(0, -1);   // (-1,-3)
+                ring[10] = WIN(1, -2);  // (-2,-2)
+                ring[11] = WIN(2, -3);  // (-3,-1)
+                ring[12] = WIN(3, -3);  // (-3, 0)
+                ring[13] = WIN(4, -3);  // (-3, 1)
+                ring[14] = WIN(5, -2);  // (-2, 2)
+                ring[15] = WIN(6, -1);  // (-1, 3)
+                const unsigned cen = WIN(3, 0);
+#undef WIN
+                // even lanes: pixels p0, p2 ; odd lanes: pixels p1, p3
+                unsigned re[16], ro[16];
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    re[k] = ring[k] & 0x00ff00ffu;
+                    ro[k] = (ring[k] >> 8) & 0x00ff00ffu;
+                }
+                unsigned ue, uo;
+                fast_score_pairs(re, cen & 0x00ff00ffu, low2, neglow2, ue);
+                fast_score_pairs(ro, (cen >> 8) & 0x00ff00ffu, low2, neglow2, uo);
+                unsigned word = ue | (uo << 8);  // bytes: p0, p1, p2, p3
+                const int rem = CW - 4 * q;      // candidate cols left in this row
+                if (rem < 4) word &= (1u << (8 * rem)) - 1u;
+                sm.sc[r + 1][q + 1] = word;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- pass B: cell-local NMS -> survivor tile F (reuses the image tile memory)
+    const int iniU = plan.iniTh - plan.lowTh + 1;  // u >= iniU  <=>  m > iniTh
+    const int minU = plan.minTh - plan.lowTh + 1;
+    const int wCell = L.wCell;
+    for (int i = tid; i < CH * QR; i += DET_THREADS) {
+        const int r = i / QR, q = i - r * QR;
+        const unsigned wv = sm.sc[r + 1][q + 1];
+        unsigned outw = 0;
+        if (wv) {
+            // neighbourhood bytes: cols 4q-1 .. 4q+4 of rows r-1, r, r+1 (bordered coords)
+            unsigned long long rows3[3];
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                const unsigned a = sm.sc[r + d][q], b = sm.sc[r + d][q + 1], c = sm.sc[r + d][q + 2];
+                // 6 bytes: a.byte3, b.byte0..3, c.byte0
+                rows3[d] = (unsigned long long)(a >> 24) | ((unsigned long long)b << 8) |
+                           ((unsigned long long)(c & 0xffu) << 40);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int u = (wv >> (8 * k)) & 0xff;
+                if (u == 0) continue;
+                const int cx = 4 * q + k;
+                const int cell = cx / wCell;
+                const bool first = (cx - cell * wCell) == 0;
+                const bool last = (cx - cell * wCell) == wCell - 1;
+                bool ok = true;
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                    const int lft = (int)((rows3[d] >> (8 * k)) & 0xff);
+                    const int mid = (int)((rows3[d] >> (8 * (k + 1))) & 0xff);
+                    const int rgt = (int)((rows3[d] >> (8 * (k + 2))) & 0xff);
+                    if (!first) ok = ok && (u > lft);
+                    if (d != 1) ok = ok && (u > mid);
+                    if (!last) ok = ok && (u > rgt);
+                }
+                if (ok) {
+                    outw |= (unsigned)u << (8 * k);
+                    if (u >= iniU) sm.cellHasIni[cell] = 1;
+                }
+            }
+        }
+        sm.img[r][q] = outw;
+    }
+    __syncthreads();
+
+    // ---- pass C: per-cell threshold choice, count, reserve, emit
+    int myCount = 0;
+    for (int i = tid; i < CH * QR; i += DET_THREADS) {
+        const int r = i / QR, q = i - r * QR;
+        const unsigned wv = sm.img[r][q];
+        if (!wv) continue;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int u = (wv >> (8 * k)) & 0xff;
+            if (u == 0) continue;
+            const int cell = (4 * q + k) / wCell;
+            if (u >= iniU || (!sm.cellHasIni[cell] && u >= minU)) ++myCount;
+        }
+    }
+    if (myCount) atomicAdd(&sm.nEmit, myCount);
+    __syncthreads();
+    if (sm.nEmit == 0) return;
+    if (tid == 0) sm.emitBase = atomicAdd(&plan.candCount[f * ORB_MAX_LEVELS + l], sm.nEmit);
+    __syncthreads();
+    if (myCount) {
+        int slot = atomicAdd(&sm.emitFill, myCount) + sm.emitBase;
+        uint2* out = L.cand + (size_t)f * L.candCap;
+        for (int i = tid; i < CH * QR; i += DET_THREADS) {
+            const int r = i / QR, q = i - r * QR;
+            const unsigned wv = sm.img[r][q];
+            if (!wv) continue;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int u = (wv >> (8 * k)) & 0xff;
+                if (u == 0) continue;
+                const int cx = 4 * q + k;
+                const int cell = cx / wCell;
+                if (u >= iniU || (!sm.cellHasIni[cell] && u >= minU)) {
+                    // coordinates relative to (minBorderX, minBorderY) as in vToDistributeKeys
+                    const unsigned xrel = (unsigned)(X0 + 3 + cx - ORB_MINB);
+                    const unsigned yrel = (unsigned)(Y0 + 3 + r - ORB_MINB);
+                    if ((unsigned)slot < L.candCap) out[slot] = make_uint2(xrel | (yrel << 16), (unsigned)(u + plan.lowTh - 1));
+                    ++slot;
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_octree: ORBextractor::DistributeOctTree in closed form (DESIGN.md "octree").
+//
+// One CTA per (source level, frame).  Every candidate gets a 32-bit path code
+// [root:6][c_1:2]...[c_13:2] by replaying DivideNode's floor-halving on its own box.
+// After sorting by code, `div_j` = depth at which neighbours j-1, j part; the node count
+// after pass t is 1 + #{div_j <= t}; p* = first pass with count >= N or all singletons;
+// final nodes = runs between div_j <= p*; per node the first max-response key; output
+// order = (birth pass desc, alternating-direction path) -- the std::list push_front order.
+// ------------------------------------------------------------------------------------------
+#define OCT_THREADS 512
+#define OCT_SMEM_A 16384
+#define OCT_SMEM_B 4096
+#define OCT_D ORB_OCT_DEPTH
+
+template <typename T>
+__device__ __forceinline__ void bitonic_sort(T* a, unsigned npad) {
+    for (unsigned k = 2; k <= npad; k <<= 1) {
+        for (unsigned j = k >> 1; j > 0; j >>= 1) {
+            for (unsigned i = threadIdx.x; i < (npad >> 1); i += blockDim.x) {
+                const unsigned lo = ((i & ~(j - 1)) << 1) | (i & (j - 1));
+                const unsigned hi = lo | j;
+                const bool up = (lo & k) == 0;
+                const T x = a[lo], y = a[hi];
+                if ((x > y) == up) {
+                    a[lo] = y;
+                    a[hi] = x;
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__device__ __forceinline__ int div_depth(unsigned ca, unsigned cb) {
+    const unsigned x = ca ^ cb;
+    if (x == 0) return OCT_D + 1;
+    const int hb = 31 - __clz(x);
+    if (hb >= 2 * OCT_D) return 0;  // different roots
+    return OCT_D - (hb >> 1);
+}
+
+struct OctShared {
+    int hist[OCT_D + 2];
+    int pstar, K, nvalid, bad;
+    int warpSums[OCT_THREADS / 32];
+};
+
+__global__ void __launch_bounds__(OCT_THREADS) k_octree(const __grid_constant__ OrbPlan plan) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned long long* smA = reinterpret_cast<unsigned long long*>(smem_raw);
+    unsigned long long* smB = smA + OCT_SMEM_A;
+    OctShared& sh = *reinterpret_cast<OctShared*>(smB + OCT_SMEM_B);
+
+    const int f = blockIdx.y;
+    // blockIdx.x enumerates source levels
+    int l = -1;
+    {
+        int c = 0;
+        for (int i = 0; i < plan.nlevels; ++i)
+            if (plan.lv[i].src == i) {
+                if (c == (int)blockIdx.x) { l = i; break; }
+                ++c;
+            }
+    }
+    if (l < 0) return;
+    const OrbLevel& L = plan.lv[l];
+    const int tid = threadIdx.x;
+    int n = plan.candCount[f * ORB_MAX_LEVELS + l];
+    if (n > (int)L.candCap) n = (int)L.candCap;
+    const uint2* cand = L.cand + (size_t)f * L.candCap;
+
+    unsigned npad = 2;
+    while (npad < (unsigned)n) npad <<= 1;
+    unsigned long long* A = npad <= OCT_SMEM_A ? smA : L.sortScratch + (size_t)f * 2 * L.sortCap;
+
+    // ---- path codes
+    if (tid < OCT_D + 2) sh.hist[tid] = 0;
+    if (tid == 0) { sh.nvalid = 0; sh.bad = 0; }
+    __syncthreads();
+    int myValid = 0;
+    for (unsigned i = tid; i < npad; i += OCT_THREADS) {
+        unsigned long long key = ~0ull;
+        if (i < (unsigned)n) {
+            const uint2 c = cand[i];
+            const int x = (int)(c.x & 0xffff), y = (int)(c.x >> 16);
+            // root: int(kp.pt.x / hX) (ORBextractor.cc:248)
+            const int root = (int)__fdiv_rn((float)x, L.hX);
+            if (root >= 0 && root < L.nIni) {
+                int ulx = (int)__fmul_rn(L.hX, (float)root);
+                int urx = (int)__fmul_rn(L.hX, (float)(root + 1));
+                int uly = 0, bly = L.H;
+                unsigned code = (unsigned)root;
+#pragma unroll
+                for (int d = 0; d < OCT_D; ++d) {
+                    const int midx = ulx + ((urx - ulx) >> 1);  // extents are >= 0 here
+                    const int midy = uly + ((bly - uly) >> 1);
+                    const unsigned cx = x >= midx, cy = y >= midy;
+                    if (cx) ulx = midx; else urx = midx;
+                    if (cy) uly = midy; else bly = midy;
+                    code = (code << 2) | (cy << 1) | cx;
+                }
+                key = ((unsigned long long)code << 32) | i;
+                ++myValid;
+            }
+        }
+        A[i] = key;
+    }
+    if (myValid) atomicAdd(&sh.nvalid, myValid);
+    __syncthreads();
+    n = sh.nvalid;  // keys with an out-of-range root are dropped (ORBextractor.cc:249)
+
+    if (n > 0) bitonic_sort(A, npad);
+
+    // ---- histogram of parting depths
+    {
+        int local[OCT_D + 2];
+#pragma unroll
+        for (int d = 0; d < OCT_D + 2; ++d) local[d] = 0;
+        for (int j = tid + 1; j < n; j += OCT_THREADS) {
+            const int dd = div_depth((unsigned)(A[j - 1] >> 32), (unsigned)(A[j] >> 32));
+#pragma unroll
+            for (int d = 0; d < OCT_D + 2; ++d) local[d] += (dd == d);
+        }
+#pragma unroll
+        for (int d = 0; d < OCT_D + 2; ++d) {
+            int v = local[d];
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if ((tid & 31) == 0 && v) atomicAdd(&sh.hist[d], v);
+        }
+    }
+    __syncthreads();
+
+    // ---- every level that shares these candidates (level 1 == level 0)
+    for (int lt = l; lt < plan.nlevels; ++lt) {
+        if (plan.lv[lt].src != l) continue;
+        const OrbLevel& T = plan.lv[lt];
+        uint2* kept = T.kept + (size_t)f * T.kmax;
+        if (n == 0) {
+            if (tid == 0) plan.keptCount[f * ORB_MAX_LEVELS + lt] = 0;
+            continue;
+        }
+        if (tid == 0) {
+            int cnt = 1, p = -1;
+            cnt += sh.hist[0];
+            for (int t = 1; t <= OCT_D; ++t) {
+                cnt += sh.hist[t];
+                if (cnt >= T.nFeat || cnt == n) { p = t; break; }
+            }
+            if (p < 0) {  // unseparable keys: the reference never terminates
+                p = OCT_D;
+                sh.bad = 1;
+            }
+            int K = 1;
+            for (int t = 0; t <= p; ++t) K += sh.hist[t];
+            sh.pstar = p;
+            sh.K = K;
+        }
+        __syncthreads();
+        const int pstar = sh.pstar, K = sh.K;
+        unsigned kpad = 2;
+        while (kpad < (unsigned)K) kpad <<= 1;
+        unsigned long long* B = kpad <= OCT_SMEM_B ? smB : L.sortScratch + (size_t)f * 2 * L.sortCap + L.sortCap;
+
+        // segment ids: block-wide exclusive scan of head flags over contiguous chunks
+        const int chunk = (n + OCT_THREADS - 1) / OCT_THREADS;
+        const int beg = min(tid * chunk, n), end = min(beg + chunk, n);
+        int heads = 0;
+        for (int j = beg; j < end; ++j) {
+            const bool head = j == 0 || div_depth((unsigned)(A[j - 1] >> 32), (unsigned)(A[j] >> 32)) <= pstar;
+            heads += head;
+        }
+        int incl = heads;
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((tid & 31) >= o) incl += v;
+        }
+        if ((tid & 31) == 31) sh.warpSums[tid >> 5] = incl;
+        __syncthreads();
+        if (tid < 32) {
+            int v = tid < OCT_THREADS / 32 ? sh.warpSums[tid] : 0;
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t2 = __shfl_up_sync(0xffffffffu, v, o);
+                if (tid >= o) v += t2;
+            }
+            if (tid < OCT_THREADS / 32) sh.warpSums[tid] = v;
+        }
+        __syncthreads();
+        int seg = incl - heads + ((tid >> 5) ? sh.warpSums[(tid >> 5) - 1] : 0);
+        for (unsigned i = tid + K; i < kpad; i += OCT_THREADS) B[i] = ~0ull;
+
+        for (int j = beg; j < end; ++j) {
+            const unsigned cj = (unsigned)(A[j] >> 32);
+            const int dj = j == 0 ? 0 : div_depth((unsigned)(A[j - 1] >> 32), cj);
+            if (j != 0 && dj > pstar) continue;  // not a head
+            // walk the run, keep the first max-response key in candidate order
+            int e = j + 1, dnext = 0;
+            unsigned bestIdx = (unsigned)A[j];
+            uint2 bc = cand[bestIdx];
+            unsigned bestScore = bc.y;
+            unsigned long long bestOrd = 0;
+            bool haveOrd = false;
+            for (; e < n; ++e) {
+                dnext = div_depth((unsigned)(A[e - 1] >> 32), (unsigned)(A[e] >> 32));
+                if (dnext <= pstar) break;
+                const unsigned idx = (unsigned)A[e];
+                const uint2 c = cand[idx];
+                if (c.y > bestScore) {
+                    bestScore = c.y;
+                    bestIdx = idx;
+                    bc = c;
+                    haveOrd = false;
+                } else if (c.y == bestScore) {
+                    // candidate order: cells row-major, then (y, x) inside the cell
+                    auto ordOf = [&](uint2 v) -> unsigned long long {
+                        const unsigned x = v.x & 0xffff, y = v.x >> 16;
+                        const unsigned cj2 = (x - 3) / (unsigned)L.wCell, ci2 = (y - 3) / (unsigned)L.hCell;
+                        return ((unsigned long long)(ci2 * (unsigned)L.nCols + cj2) << 32) | (y << 16) | x;
+                    };
+                    if (!haveOrd) { bestOrd = ordOf(bc); haveOrd = true; }
+                    const unsigned long long o2 = ordOf(c);
+                    if (o2 < bestOrd) { bestOrd = o2; bestIdx = idx; bc = c; }
+                }
+            }
+            if (e >= n) dnext = 0;
+            const int len = e - j;
+            int birth = len == 1 ? max(dj, dnext) : pstar;
+            if (birth > pstar) birth = pstar;  // (cannot happen for len==1; keeps the key well-formed)
+            // order key: (D - birth) | root' | c'_1..c'_birth ; direction alternates backwards from c_birth
+            const unsigned root = cj >> (2 * OCT_D);
+            unsigned long long ok = (unsigned long long)(OCT_D - birth);
+            bool rootDesc = birth >= 1 && (((birth - 1) & 1) == 0);
+            ok = (ok << 6) | (rootDesc ? 63u - root : root);
+#pragma unroll
+            for (int i = 1; i <= OCT_D; ++i) {
+                unsigned c = (cj >> (2 * (OCT_D - i))) & 3u;
+                if (i <= birth) {
+                    if (((birth - i) & 1) == 0) c = 3u - c;
+                } else {
+                    c = 0;
+                }
+                ok = (ok << 2) | c;
+            }
+            B[seg] = (ok << 24) | bestIdx;
+            ++seg;
+        }
+        __syncthreads();
+        bitonic_sort(B, kpad);
+        for (int r = tid; r < K; r += OCT_THREADS) {
+            const unsigned idx = (unsigned)(B[r] & 0xffffffu);
+            const uint2 c = cand[idx];
+            const unsigned x = (c.x & 0xffff) + ORB_MINB, y = (c.x >> 16) + ORB_MINB;
+            if (r < T.kmax) kept[r] = make_uint2(x | (y << 16), c.y);
+        }
+        if (tid == 0) {
+            plan.keptCount[f * ORB_MAX_LEVELS + lt] = K;
+            if (sh.bad) plan.status[f] = 1;
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_blur: cv::GaussianBlur 7x7 sigma 2, BORDER_REFLECT_101, 8UC1:
+// out = (sum_j sum_i w_j w_i p + 32768) >> 16, w = [18,34,48,56,48,34,18].
+// Tile of 128 x 32 outputs; horizontal pass into 16-bit smem, vertical pass out.
+// ------------------------------------------------------------------------------------------
+#define BLUR_TW 128
+#define BLUR_TH 32
+
+__device__ __forceinline__ int reflect101(int p, int n) {
+    if (n == 1) return 0;
+    while (p < 0 || p >= n) p = p < 0 ? -p : 2 * n - 2 - p;
+    return p;
+}
+
+__global__ void __launch_bounds__(256) k_blur(const __grid_constant__ OrbPlan plan) {
+    __shared__ uint8_t tile[BLUR_TH + 6][BLUR_TW + 8];
+    __shared__ unsigned short hsum[BLUR_TH + 6][BLUR_TW];
+    const int f = blockIdx.y;
+    int t = blockIdx.x, l = 0;
+    int tilesX = 0;
+    for (; l < plan.nlevels; ++l) {
+        const OrbLevel& L = plan.lv[l];
+        if (L.src != l) continue;
+        tilesX = (L.cols + BLUR_TW - 1) / BLUR_TW;
+        const int nt = tilesX * ((L.rows + BLUR_TH - 1) / BLUR_TH);
+        if (t < nt) break;
+        t -= nt;
+    }
+    if (l >= plan.nlevels) return;
+    const OrbLevel& L = plan.lv[l];
+    const int ty = t / tilesX, tx = t - ty * tilesX;
+    const int x0 = tx * BLUR_TW, y0 = ty * BLUR_TH;
+    const uint8_t* src = L.img + (size_t)f * L.plane;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < (BLUR_TH + 6) * (BLUR_TW + 6); i += 256) {
+        const int r = i / (BLUR_TW + 6), c = i - r * (BLUR_TW + 6);
+        const int yy = reflect101(y0 + r - 3, L.rows), xx = reflect101(x0 + c - 3, L.cols);
+        tile[r][c] = __ldg(src + (size_t)yy * L.pitch + xx);
+    }
+    __syncthreads();
+    for (int i = tid; i < (BLUR_TH + 6) * BLUR_TW; i += 256) {
+        const int r = i / BLUR_TW, c = i - r * BLUR_TW;
+        const uint8_t* p = &tile[r][c];
+        hsum[r][c] = (unsigned short)(18 * (p[0] + p[6]) + 34 * (p[1] + p[5]) + 48 * (p[2] + p[4]) + 56 * p[3]);
+    }
+    __syncthreads();
+    uint8_t* dst = L.blur + (size_t)f * L.plane;
+    for (int i = tid; i < BLUR_TH * BLUR_TW; i += 256) {
+        const int r = i / BLUR_TW, c = i - r * BLUR_TW;
+        const int y = y0 + r, x = x0 + c;
+        if (y < L.rows && x < L.cols) {
+            const int acc = 18 * (hsum[r][c] + hsum[r + 6][c]) + 34 * (hsum[r + 1][c] + hsum[r + 5][c]) +
+                            48 * (hsum[r + 2][c] + hsum[r + 4][c]) + 56 * hsum[r + 3][c];
+            dst[(size_t)y * L.pitch + x] = (uint8_t)((acc + 32768) >> 16);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_describe: IC_Angle (ORBextractor.cc:21-48) on the raw level, rBRIEF
+// (computeOrbDescriptor :57-73) on the blurred level, final keypoint record
+// (:345-352, :486-491).  One warp per kept keypoint.
+// ------------------------------------------------------------------------------------------
+__constant__ int8_t c_pairs[728] = {
+#include "brief_pairs_182.inc"
+};
+__constant__ int c_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
+
+__device__ __forceinline__ float fast_atan2_deg(float y, float x) {
+    // cv::fastAtan2, evaluated step by step in binary32, no FMA
+    const float scale = (float)(180.0 / 3.141592653589793238462643383279502884);
+    const float p1 = 0.9997878412794807f * scale, p3 = -0.3258083974640975f * scale;
+    const float p5 = 0.1555786518463281f * scale, p7 = -0.04432655554792128f * scale;
+    const float eps = (float)2.2204460492503131e-16;
+    const float ax = fabsf(x), ay = fabsf(y);
+    float a, c, c2;
+    if (ax >= ay) {
+        c = __fdiv_rn(ay, __fadd_rn(ax, eps));
+        c2 = __fmul_rn(c, c);
+        a = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c);
+    } else {
+        c = __fdiv_rn(ax, __fadd_rn(ay, eps));
+        c2 = __fmul_rn(c, c);
+        a = __fsub_rn(90.f, __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c));
+    }
+    if (x < 0) a = __fsub_rn(180.f, a);
+    if (y < 0) a = __fsub_rn(360.f, a);
+    return a;
+}
+
+__global__ void __launch_bounds__(256) k_describe(const __grid_constant__ OrbPlan plan, orb_keypoint_dev* __restrict__ kps,
+                                                  uint8_t* __restrict__ desc, int cap, int* __restrict__ counts) {
+    __shared__ int8_t s_pairs[728];
+    for (int i = threadIdx.x; i < 728; i += 256) s_pairs[i] = c_pairs[i];
+    const int f = blockIdx.y;
+    const int* kc = plan.keptCount + f * ORB_MAX_LEVELS;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        int tot = 0;
+        for (int i = 0; i < plan.nlevels; ++i) tot += kc[i];
+        counts[f] = tot;
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = blockIdx.x * 8 + warp;  // index in the concatenated [level][kmax] space
+    int l = 0;
+    for (; l < plan.nlevels; ++l)
+        if (g < plan.lv[l].keptBase + plan.lv[l].kmax) break;
+    if (l >= plan.nlevels) return;
+    const OrbLevel& L = plan.lv[l];
+    const int r = g - L.keptBase;
+    if (r >= kc[l]) return;
+    int off = 0;
+    for (int i = 0; i < l; ++i) off += kc[i];
+    const int o = off + r;
+    if (o >= cap) return;
+
+    const uint2 k = L.kept[(size_t)f * L.kmax + r];
+    const int x = (int)(k.x & 0xffff), y = (int)(k.x >> 16);
+    const OrbLevel& S = plan.lv[L.src];
+
+    // ---- IC_Angle: m10 = sum u*I, m01 = sum v*I over the radius-15 disc (exact int32)
+    const uint8_t* img = S.img + (size_t)f * S.plane + (size_t)y * S.pitch + x;
+    int m10 = 0, m01 = 0;
+    {
+        const int u = lane - 15;  // lanes 0..30
+        if (lane < 31) {
+            const int au = u < 0 ? -u : u;
+#pragma unroll
+            for (int v = -15; v <= 15; ++v) {
+                const int av = v < 0 ? -v : v;
+                if (au <= c_umax[av]) {
+                    const int val = __ldg(img + v * S.pitch + u);
+                    m10 += u * val;
+                    m01 += v * val;
+                }
+            }
+        }
+        for (int s = 16; s > 0; s >>= 1) {
+            m10 += __shfl_xor_sync(0xffffffffu, m10, s);
+            m01 += __shfl_xor_sync(0xffffffffu, m01, s);
+        }
+    }
+    const float angle = fast_atan2_deg((float)m01, (float)m10);
+
+    // ---- rBRIEF on the blurred level: 182 live pairs (bits 182..255 are 0)
+    const float factorPI = (float)(3.141592653589793238462643383279502884 / 180.f);
+    const float rad = __fmul_rn(angle, factorPI);
+    const float a = (float)cos((double)rad), b = (float)sin((double)rad);
+    const uint8_t* bl = S.blur + (size_t)f * S.plane + (size_t)y * S.pitch + x;
+    unsigned words[8];
+#pragma unroll
+    for (int wq = 0; wq < 6; ++wq) {
+        const int p = wq * 32 + lane;
+        bool bit = false;
+        if (p < 182) {
+            const float x0 = (float)s_pairs[4 * p], y0 = (float)s_pairs[4 * p + 1];
+            const float x1 = (float)s_pairs[4 * p + 2], y1 = (float)s_pairs[4 * p + 3];
+            const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
+            const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
+            const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
+            const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
+            const int t0 = __ldg(bl + r0 * S.pitch + c0);
+            const int t1 = __ldg(bl + r1 * S.pitch + c1);
+            bit = t0 < t1;
+        }
+        words[wq] = __ballot_sync(0xffffffffu, bit);
+    }
+    words[6] = 0;
+    words[7] = 0;
+
+    if (lane < 8) {
+        unsigned wsel = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (lane == i) wsel = words[i];
+        reinterpret_cast<unsigned*>(desc + ((size_t)f * cap + o) * 32)[lane] = wsel;
+    }
+    if (lane == 8) {
+        orb_keypoint_dev kp;
+        float px = (float)x, py = (float)y;
+        if (l != 0) {  // keypoint.pt *= scale for level != 0 (:486-491)
+            px = __fmul_rn(px, L.scale);
+            py = __fmul_rn(py, L.scale);
+        }
+        kp.x = px;
+        kp.y = py;
+        kp.size = (float)L.patchSize;
+        kp.angle = angle;
+        kp.response = (float)k.y;
+        kp.octave = l;
+        kp.class_id = -1;
+        kps[(size_t)f * cap + o] = kp;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------
+static unsigned long long g_launches = 0;
+unsigned long long orbk_launch_count() { return g_launches; }
+void orbk_count_launch(int n) { g_launches += n; }
+
+static const size_t kDetectSmem = sizeof(DetectSmem);
+static const size_t kOctreeSmem = (size_t)(OCT_SMEM_A + OCT_SMEM_B) * 8 + sizeof(OctShared);
+
+cudaError_t orbk_init_device() {
+    cudaError_t e = cudaFuncSetAttribute(k_detect, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDetectSmem);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kOctreeSmem);
+}
+
+cudaError_t orbk_run_extract(const OrbPlan& plan, int nframes, orb_keypoint_dev* d_kps, uint8_t* d_desc, int cap,
+                             int* d_counts, cudaStream_t st) {
+    cudaError_t e;
+    e = cudaMemsetAsync(plan.candCount, 0, sizeof(int) * ORB_MAX_LEVELS * plan.batch, st);
+    if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(plan.status, 0, sizeof(int) * plan.batch, st);
+    if (e != cudaSuccess) return e;
+    // pyramid: level l = resize(level l-1); same-size levels alias their source
+    for (int l = 1; l < plan.nlevels; ++l) {
+        const OrbLevel& D = plan.lv[l];
+        if (D.src != l) continue;
+        const OrbLevel& S = plan.lv[plan.lv[l - 1].src];
+        dim3 block(64, 4), grid((D.cols + 255) / 256, (D.rows + 3) / 4, nframes);
+        k_resize<<<grid, block, 0, st>>>(S.img, S.pitch, S.plane, D.img, D.pitch, D.plane, D.rows, D.cols, D.xtab,
+                                         D.xcoef, D.ytab, D.ycoef);
+        ++g_launches;
+    }
+    int nsrc = 0, blurTiles = 0;
+    for (int l = 0; l < plan.nlevels; ++l)
+        if (plan.lv[l].src == l) {
+            ++nsrc;
+            blurTiles += ((plan.lv[l].cols + BLUR_TW - 1) / BLUR_TW) * ((plan.lv[l].rows + BLUR_TH - 1) / BLUR_TH);
+        }
+    if (plan.totalTiles > 0) {
+        k_detect<<<dim3(plan.totalTiles, nframes), DET_THREADS, kDetectSmem, st>>>(plan);
+        ++g_launches;
+    }
+    k_octree<<<dim3(nsrc, nframes), OCT_THREADS, kOctreeSmem, st>>>(plan);
+    ++g_launches;
+    k_blur<<<dim3(blurTiles, nframes), 256, 0, st>>>(plan);
+    ++g_launches;
+    k_describe<<<dim3((plan.totalKmax + 7) / 8, nframes), 256, 0, st>>>(plan, d_kps, d_desc, cap, d_counts);
+    ++g_launches;
+    return cudaGetLastError();
+}

@@ -1,0 +1,17 @@
+// Launch interface of the Hamming-search kernels (match_kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+struct orb_kp28 {  // cv::KeyPoint layout
+    float x, y, size, angle, response;
+    int octave, class_id;
+};
+
+cudaError_t orbk_match_all(const uint8_t* q, const int* nq, size_t q_stride, const uint8_t* t, const int* nt,
+                           size_t t_stride, int npairs, int max_nq, int* best_idx, int* best_dist, int* second_dist,
+                           size_t out_stride, cudaStream_t st);
+cudaError_t orbk_match_csr(const uint8_t* q, int nq, const uint8_t* t, const int* offsets, const int* cand, int tie_last,
+                           int max_dist, int* best_idx, int* best_dist, int* second_dist, cudaStream_t st);
+cudaError_t orbk_stereo(const orb_kp28* kl, const uint8_t* dl, int nl, const orb_kp28* kr, const uint8_t* dr, int nr,
+                        const float* d_scale, int4* d_rinfo, float maxD, int* best_r, int* best_dist, cudaStream_t st);

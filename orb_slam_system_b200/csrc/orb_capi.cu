@@ -1,0 +1,709 @@
+// C ABI of liborb_b200.so (include/orb_b200.h): handles, the per-shape plan, device
+// memory and streams.  No torch types, no exceptions across the boundary, no CPU fallback.
+//
+// Host-side arithmetic that decides shapes (ctor tables, level sizes, cell grid, resize
+// coefficient tables) follows reference src/ORBextractor.cc:116-170, :497-515, :288-331 and
+// the cv::resize model float op by float op; this file is compiled with
+// -ffp-contract=off for that reason.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/orb_b200.h"
+#include "extract_kernels.h"
+#include "match_kernels.h"
+#include "orb_plan.h"
+
+static_assert(sizeof(orb_keypoint) == 28, "orb_keypoint must match cv::KeyPoint");
+static_assert(sizeof(orb_keypoint_dev) == 28 && sizeof(orb_kp28) == 28, "device keypoint layout");
+
+// ------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------
+static thread_local std::string t_err;
+static int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    t_err = buf;
+    return code;
+}
+#define CUDA_TRY(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess) return fail(ORB_ERR_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+extern "C" const char* orb_last_error(void) { return t_err.c_str(); }
+extern "C" uint64_t orb_kernel_launch_count(void) { return orbk_launch_count(); }
+extern "C" const char* orb_version(void) { return "orb_b200 0.1 (sm_100a)"; }
+
+// ------------------------------------------------------------------------------------------
+// ctor tables (reference src/ORBextractor.cc:116-151)
+// ------------------------------------------------------------------------------------------
+struct HostTables {
+    std::vector<float> scale, inv_scale, sigma2, inv_sigma2;
+    std::vector<int> nfeat;
+};
+
+static int round_half_even_f(float v) { return (int)lrintf(v); }  // cvRound
+
+static HostTables build_tables(const orb_params& p) {
+    HostTables t;
+    const int n = p.nlevels;
+    const double sf = (double)p.scale_factor;  // the member is a double (ORBextractor.h:79)
+    t.scale.assign(n, 1.0f);
+    if (n >= 2) {  // partial_sum over the vector itself, shifted by one (:120-124)
+        float acc = t.scale[0];
+        t.scale[1] = acc;
+        for (int i = 1; i <= n - 2; ++i) {
+            acc = (float)((double)acc * sf);
+            t.scale[i + 1] = acc;
+        }
+    }
+    t.sigma2.resize(n);
+    t.inv_scale.resize(n);
+    t.inv_sigma2.resize(n);
+    for (int i = 0; i < n; ++i) {
+        t.sigma2[i] = t.scale[i] * t.scale[i];
+        t.inv_scale[i] = 1.0f / t.scale[i];
+        t.inv_sigma2[i] = 1.0f / t.sigma2[i];
+    }
+    t.nfeat.assign(n, 0);
+    const float factor = (float)(1.0 / sf);
+    float desired = (float)((double)((float)p.nfeatures * (1 - factor)) / (1.0 - pow((double)factor, (double)n)));
+    int sum = 0;
+    for (int i = 0; i < n - 1; ++i) {
+        const int cur = round_half_even_f(desired);
+        sum += cur;
+        desired *= factor;
+        t.nfeat[i] = cur;
+    }
+    t.nfeat[n - 1] = std::max(p.nfeatures - sum, 0);
+    return t;
+}
+
+// cv::resize INTER_LINEAR coefficient tables of one axis
+static void linear_axis(int ssize, int dsize, bool is_x, std::vector<int>& tab, std::vector<int>& coef) {
+    tab.resize(dsize);
+    coef.resize(dsize);
+    const double inv_scale = (double)dsize / ssize;
+    const double scale = 1.0 / inv_scale;
+    for (int d = 0; d < dsize; ++d) {
+        float f = (float)((d + 0.5) * scale - 0.5);
+        int s = (int)floorf(f);
+        f -= s;
+        int s0, s1;
+        if (is_x) {  // x: coefficients collapse at the edges
+            if (s < 0) { s = 0; f = 0.f; }
+            if (s >= ssize - 1) { s = ssize - 1; f = 0.f; }
+            s0 = s;
+            s1 = std::min(s + 1, ssize - 1);
+        } else {  // y: coefficients kept, row indices clipped
+            s0 = std::min(std::max(s, 0), ssize - 1);
+            s1 = std::min(std::max(s + 1, 0), ssize - 1);
+        }
+        const int c0 = round_half_even_f((1.f - f) * 2048.f);
+        const int c1 = round_half_even_f(f * 2048.f);
+        tab[d] = s0 | (s1 << 16);
+        coef[d] = (c0 & 0xffff) | (c1 << 16);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// extractor handle
+// ------------------------------------------------------------------------------------------
+struct orb_extractor {
+    orb_params params;
+    HostTables tab;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int max_batch = 1;
+    OrbPlan plan;            // current shape (plan.rows == 0: none)
+    std::vector<void*> allocs;  // everything the plan points at
+    uint8_t* level0 = nullptr;  // internal level-0 buffer (host-input path)
+    // output staging for the host-buffer API
+    orb_keypoint_dev* d_kps = nullptr;
+    uint8_t* d_desc = nullptr;
+    int* d_counts = nullptr;
+    int out_cap = 0;
+    int last_n = 0;
+    std::vector<int> h_status;
+};
+
+static void free_plan(orb_extractor* h) {
+    for (void* p : h->allocs) cudaFree(p);
+    h->allocs.clear();
+    h->level0 = nullptr;
+    memset(&h->plan, 0, sizeof h->plan);
+}
+
+template <typename T>
+static cudaError_t dev_alloc(orb_extractor* h, T** out, size_t count) {
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, std::max<size_t>(count * sizeof(T), 256));
+    if (e != cudaSuccess) return e;
+    h->allocs.push_back(p);
+    *out = (T*)p;
+    return cudaSuccess;
+}
+
+static inline int align_up(int v, int a) { return (v + a - 1) / a * a; }
+
+// Geometry of one level; returns an orb_status.
+static int level_geometry(const orb_params& prm, const HostTables& tab, int rows, int cols, int l, OrbLevel& L) {
+    memset(&L, 0, sizeof L);
+    const float s = tab.inv_scale[l];
+    L.cols = round_half_even_f(cols * s);  // Size sz(cvRound(cols*scale), cvRound(rows*scale)) (:502)
+    L.rows = round_half_even_f(rows * s);
+    if (L.cols <= 0 || L.rows <= 0) return fail(ORB_ERR_SHAPE, "level %d is empty (%dx%d)", l, L.cols, L.rows);
+    L.pitch = align_up(L.cols, 64);
+    L.plane = (unsigned long long)L.pitch * L.rows;
+    L.src = l;
+    L.scale = tab.scale[l];
+    L.patchSize = (int)(31 * tab.scale[l]);
+    L.nFeat = tab.nfeat[l];
+    const int minB = ORB_MINB, maxBX = L.cols - ORB_MINB, maxBY = L.rows - ORB_MINB;
+    L.W = maxBX - minB;
+    L.H = maxBY - minB;
+    if (L.H == 0) return fail(ORB_ERR_SHAPE, "level %d: reference divides by zero (rows == 32)", l);
+    L.nIni = L.W / L.H;  // integer division
+    if (L.nIni < 0) return fail(ORB_ERR_SHAPE, "level %d: reference throws (negative root count)", l);
+    if (L.nIni > 63) return fail(ORB_ERR_SHAPE, "level %d: aspect ratio above 63:1 is not supported", l);
+    L.hX = (float)L.W / L.nIni;  // inf/NaN when nIni == 0, as in the reference; then no key passes the root test
+    const float width = (float)L.W, height = (float)L.H;
+    const int nCols = (int)(width / ORB_CELL), nRows = (int)(height / ORB_CELL);
+    if (nCols > 0 && nRows > 0) {
+        L.nCols = nCols;
+        L.nRows = nRows;
+        L.wCell = (int)ceilf(width / nCols);
+        L.hCell = (int)ceilf(height / nRows);
+        // the reference's Mat::operator()(Rect) throws on a negative cell extent
+        if (minB + (nCols - 1) * L.wCell > maxBX || minB + (nRows - 1) * L.hCell > maxBY)
+            return fail(ORB_ERR_SHAPE, "level %d (%dx%d): reference throws cv::Exception (negative cell ROI)", l, L.cols, L.rows);
+        int tc = std::max(1, (DET_TILE_W - 6) / L.wCell);
+        L.tilesX = (nCols + tc - 1) / tc;
+        L.tileCells = (nCols + L.tilesX - 1) / L.tilesX;
+        L.nTiles = L.tilesX * nRows;
+        // worst-case candidates: NMS survivors are never 8-adjacent inside a cell
+        unsigned long long cap = 0;
+        for (int i = 0; i < nRows; ++i) {
+            const int ch = std::max(0, std::min(ORB_EDGE + (i + 1) * L.hCell, maxBY - 3) - (ORB_EDGE + i * L.hCell));
+            for (int j = 0; j < nCols; ++j) {
+                const int cw = std::max(0, std::min(ORB_EDGE + (j + 1) * L.wCell, maxBX - 3) - (ORB_EDGE + j * L.wCell));
+                cap += (unsigned long long)((cw + 1) / 2) * ((ch + 1) / 2);
+            }
+        }
+        if (cap >= (1ull << 24)) return fail(ORB_ERR_SHAPE, "level %d too large", l);
+        L.candCap = (unsigned)std::max<unsigned long long>(cap, 1);
+    } else {
+        L.candCap = 1;
+    }
+    L.kmax = (int)std::min<long long>(L.candCap, std::max(std::max(4 * L.nIni, 4 * L.nFeat), 1));
+    unsigned sc = 2;
+    while (sc < L.candCap) sc <<= 1;
+    L.sortCap = sc;
+    return ORB_OK;
+}
+
+static int build_plan(orb_extractor* h, int rows, int cols) {
+    if (h->plan.rows == rows && h->plan.cols == cols) return ORB_OK;
+    if (rows > ORB_MAX_DIM || cols > ORB_MAX_DIM) return fail(ORB_ERR_SHAPE, "image larger than %d", ORB_MAX_DIM);
+    OrbPlan P;
+    memset(&P, 0, sizeof P);
+    P.nlevels = h->params.nlevels;
+    P.rows = rows;
+    P.cols = cols;
+    P.iniTh = std::min(std::max(h->params.ini_th_fast, 0), 255);  // cv::FAST clamps its threshold
+    P.minTh = std::min(std::max(h->params.min_th_fast, 0), 255);
+    P.lowTh = std::min(P.iniTh, P.minTh);
+    P.batch = h->max_batch;
+    for (int l = 0; l < P.nlevels; ++l) {
+        int rc = level_geometry(h->params, h->tab, rows, cols, l, P.lv[l]);
+        if (rc != ORB_OK) return rc;
+        // a same-size resize is a byte copy: share pixels and candidates with the source level
+        if (l > 0 && P.lv[l].rows == P.lv[l - 1].rows && P.lv[l].cols == P.lv[l - 1].cols) P.lv[l].src = P.lv[l - 1].src;
+    }
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    free_plan(h);
+    const int B = h->max_batch;
+    int tileBase = 0, keptBase = 0;
+    for (int l = 0; l < P.nlevels; ++l) {
+        OrbLevel& L = P.lv[l];
+        L.keptBase = keptBase;
+        keptBase += L.kmax;
+        CUDA_TRY(dev_alloc(h, &L.kept, (size_t)B * L.kmax));
+        if (L.src != l) continue;
+        L.tileBase = tileBase;
+        tileBase += L.nTiles;
+        CUDA_TRY(dev_alloc(h, &L.img, (size_t)B * L.plane + 256));
+        CUDA_TRY(dev_alloc(h, &L.blur, (size_t)B * L.plane + 256));
+        CUDA_TRY(dev_alloc(h, &L.cand, (size_t)B * L.candCap));
+        CUDA_TRY(dev_alloc(h, &L.sortScratch, (size_t)B * 2 * L.sortCap));
+        if (l > 0) {
+            const OrbLevel& S = P.lv[P.lv[l - 1].src];
+            std::vector<int> xt, xc, yt, yc;
+            linear_axis(S.cols, L.cols, true, xt, xc);
+            linear_axis(S.rows, L.rows, false, yt, yc);
+            int *dxt, *dxc, *dyt, *dyc;
+            CUDA_TRY(dev_alloc(h, &dxt, xt.size()));
+            CUDA_TRY(dev_alloc(h, &dxc, xc.size()));
+            CUDA_TRY(dev_alloc(h, &dyt, yt.size()));
+            CUDA_TRY(dev_alloc(h, &dyc, yc.size()));
+            CUDA_TRY(cudaMemcpy(dxt, xt.data(), xt.size() * 4, cudaMemcpyHostToDevice));
+            CUDA_TRY(cudaMemcpy(dxc, xc.data(), xc.size() * 4, cudaMemcpyHostToDevice));
+            CUDA_TRY(cudaMemcpy(dyt, yt.data(), yt.size() * 4, cudaMemcpyHostToDevice));
+            CUDA_TRY(cudaMemcpy(dyc, yc.data(), yc.size() * 4, cudaMemcpyHostToDevice));
+            L.xtab = dxt;
+            L.xcoef = dxc;
+            L.ytab = dyt;
+            L.ycoef = dyc;
+        }
+    }
+    // aliases share their source's buffers
+    for (int l = 0; l < P.nlevels; ++l) {
+        OrbLevel& L = P.lv[l];
+        if (L.src == l) continue;
+        const OrbLevel& S = P.lv[L.src];
+        L.img = S.img;
+        L.blur = S.blur;
+        L.cand = S.cand;
+        L.candCap = S.candCap;
+        L.kmax = std::min<int>(L.kmax, (int)S.candCap);
+    }
+    P.totalTiles = tileBase;
+    P.totalKmax = keptBase;
+    CUDA_TRY(dev_alloc(h, &P.candCount, (size_t)B * ORB_MAX_LEVELS));
+    CUDA_TRY(dev_alloc(h, &P.keptCount, (size_t)B * ORB_MAX_LEVELS));
+    CUDA_TRY(dev_alloc(h, &P.status, (size_t)B));
+    CUDA_TRY(cudaMemset(P.keptCount, 0, sizeof(int) * B * ORB_MAX_LEVELS));
+    CUDA_TRY(cudaMemset(P.candCount, 0, sizeof(int) * B * ORB_MAX_LEVELS));
+    h->level0 = P.lv[0].img;
+    h->plan = P;
+    return ORB_OK;
+}
+
+static int ensure_out(orb_extractor* h, int cap) {
+    if (cap <= h->out_cap) return ORB_OK;
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if (h->d_kps) cudaFree(h->d_kps);
+    if (h->d_desc) cudaFree(h->d_desc);
+    h->d_kps = nullptr;
+    h->d_desc = nullptr;
+    h->out_cap = 0;
+    CUDA_TRY(cudaMalloc((void**)&h->d_kps, (size_t)h->max_batch * cap * sizeof(orb_keypoint_dev)));
+    CUDA_TRY(cudaMalloc((void**)&h->d_desc, (size_t)h->max_batch * cap * 32));
+    h->out_cap = cap;
+    return ORB_OK;
+}
+
+extern "C" int orb_extractor_create(const orb_params* params, int max_rows, int max_cols, int max_batch, int device,
+                                    orb_extractor** out) {
+    if (!params || !out) return fail(ORB_ERR_INVALID, "null argument");
+    if (params->nlevels < 1 || params->nlevels > ORB_MAX_LEVELS) return fail(ORB_ERR_INVALID, "nlevels must be 1..%d", ORB_MAX_LEVELS);
+    if (max_batch < 1) return fail(ORB_ERR_INVALID, "max_batch must be >= 1");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(ORB_ERR_CUDA, "no CUDA device: %s (liborb_b200 has no CPU fallback)", cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(ORB_ERR_INVALID, "device %d out of range (%d devices)", device, ndev);
+    CUDA_TRY(cudaSetDevice(device));
+    CUDA_TRY(orbk_init_device());
+    orb_extractor* h = new orb_extractor();
+    h->params = *params;
+    h->tab = build_tables(*params);
+    h->device = device;
+    h->max_batch = max_batch;
+    memset(&h->plan, 0, sizeof h->plan);
+    cudaError_t ce = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (ce != cudaSuccess) {
+        delete h;
+        return fail(ORB_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(ce));
+    }
+    ce = cudaMalloc((void**)&h->d_counts, sizeof(int) * max_batch);
+    if (ce != cudaSuccess) {
+        cudaStreamDestroy(h->stream);
+        delete h;
+        return fail(ORB_ERR_CUDA, "cudaMalloc: %s", cudaGetErrorString(ce));
+    }
+    if (max_rows > 0 && max_cols > 0) {
+        int rc = build_plan(h, max_rows, max_cols);
+        if (rc != ORB_OK) {
+            orb_extractor_destroy(h);
+            return rc;
+        }
+    }
+    *out = h;
+    return ORB_OK;
+}
+
+extern "C" void orb_extractor_destroy(orb_extractor* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    free_plan(h);
+    if (h->d_kps) cudaFree(h->d_kps);
+    if (h->d_desc) cudaFree(h->d_desc);
+    if (h->d_counts) cudaFree(h->d_counts);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+extern "C" int orb_extractor_tables(const orb_extractor* h, float* scale, float* inv_scale, float* sigma2, float* inv_sigma2,
+                                    int32_t* features_per_level) {
+    if (!h) return fail(ORB_ERR_INVALID, "null handle");
+    const int n = h->params.nlevels;
+    for (int i = 0; i < n; ++i) {
+        if (scale) scale[i] = h->tab.scale[i];
+        if (inv_scale) inv_scale[i] = h->tab.inv_scale[i];
+        if (sigma2) sigma2[i] = h->tab.sigma2[i];
+        if (inv_sigma2) inv_sigma2[i] = h->tab.inv_sigma2[i];
+        if (features_per_level) features_per_level[i] = h->tab.nfeat[i];
+    }
+    return ORB_OK;
+}
+
+extern "C" int orb_extractor_keypoint_bound(const orb_extractor* h, int rows, int cols, int* bound) {
+    if (!h || !bound) return fail(ORB_ERR_INVALID, "null argument");
+    long long tot = 0;
+    for (int l = 0; l < h->params.nlevels; ++l) {
+        OrbLevel L;
+        int rc = level_geometry(h->params, h->tab, rows, cols, l, L);
+        if (rc != ORB_OK) return rc;
+        tot += L.kmax;
+    }
+    *bound = (int)tot;
+    return ORB_OK;
+}
+
+static int check_status(orb_extractor* h, int n) {
+    h->h_status.assign(n, 0);
+    CUDA_TRY(cudaMemcpyAsync(h->h_status.data(), h->plan.status, sizeof(int) * n, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    for (int i = 0; i < n; ++i)
+        if (h->h_status[i]) return fail(ORB_ERR_UNSEPARABLE, "frame %d: octree cannot separate its keys (reference would not terminate)", i);
+    return ORB_OK;
+}
+
+extern "C" int orb_extract_batch_device(orb_extractor* h, int n, const uint8_t* d_imgs, int rows, int cols, size_t stride,
+                                        size_t frame_stride, orb_keypoint* d_kps, uint8_t* d_desc, int cap, int* d_counts) {
+    if (!h || !d_kps || !d_desc || !d_counts) return fail(ORB_ERR_INVALID, "null argument");
+    if (n < 0 || n > h->max_batch) return fail(ORB_ERR_INVALID, "n=%d exceeds max_batch=%d", n, h->max_batch);
+    if (n == 0) return ORB_OK;
+    if (!d_imgs || rows <= 0 || cols <= 0) {  // empty image: silent return (ORBextractor.cc:444-445)
+        CUDA_TRY(cudaSetDevice(h->device));
+        CUDA_TRY(cudaMemsetAsync(d_counts, 0, sizeof(int) * n, h->stream));
+        h->last_n = 0;
+        return ORB_OK;
+    }
+    if (cap <= 0) return fail(ORB_ERR_INVALID, "cap must be positive");
+    if ((stride & 3) || ((uintptr_t)d_imgs & 3) || (frame_stride & 3) || stride < (size_t)cols)
+        return fail(ORB_ERR_INVALID, "device frames need 4-byte aligned base and strides >= cols");
+    CUDA_TRY(cudaSetDevice(h->device));
+    int rc = build_plan(h, rows, cols);
+    if (rc != ORB_OK) return rc;
+    OrbPlan P = h->plan;
+    if ((int)stride == h->plan.lv[0].pitch && frame_stride == h->plan.lv[0].plane) {
+        // same layout as the internal level-0 buffer: read the caller's frames in place
+        for (int l = 0; l < P.nlevels; ++l)
+            if (P.lv[l].src == 0) P.lv[l].img = const_cast<uint8_t*>(d_imgs);
+    } else {
+        // pitch conversion into the internal level-0 buffer (blur/describe share its pitch)
+        for (int f = 0; f < n; ++f)
+            CUDA_TRY(cudaMemcpy2DAsync(h->level0 + f * h->plan.lv[0].plane, h->plan.lv[0].pitch, d_imgs + f * frame_stride,
+                                       stride, cols, rows, cudaMemcpyDeviceToDevice, h->stream));
+    }
+    h->last_n = n;
+    CUDA_TRY(orbk_run_extract(P, n, reinterpret_cast<orb_keypoint_dev*>(d_kps), d_desc, cap, d_counts, h->stream));
+    return ORB_OK;
+}
+
+extern "C" int orb_extractor_sync(orb_extractor* h) {
+    if (!h) return fail(ORB_ERR_INVALID, "null handle");
+    CUDA_TRY(cudaSetDevice(h->device));
+    if (h->last_n > 0 && h->plan.status) return check_status(h, h->last_n);
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return ORB_OK;
+}
+
+extern "C" void* orb_extractor_stream(orb_extractor* h) { return h ? (void*)h->stream : nullptr; }
+
+extern "C" int orb_extract_batch(orb_extractor* h, int n, const uint8_t* imgs, int rows, int cols, size_t stride,
+                                 size_t frame_stride, orb_keypoint* kps, uint8_t* desc, int cap, int* counts) {
+    if (!h || !counts) return fail(ORB_ERR_INVALID, "null argument");
+    if (n < 0 || n > h->max_batch) return fail(ORB_ERR_INVALID, "n=%d exceeds max_batch=%d", n, h->max_batch);
+    if (n == 0) return ORB_OK;
+    if (!imgs || rows <= 0 || cols <= 0) {
+        for (int f = 0; f < n; ++f) counts[f] = 0;
+        return ORB_OK;
+    }
+    if (!kps || !desc || cap <= 0) return fail(ORB_ERR_INVALID, "null output buffer");
+    if (stride < (size_t)cols) return fail(ORB_ERR_INVALID, "stride < cols");
+    CUDA_TRY(cudaSetDevice(h->device));
+    int rc = build_plan(h, rows, cols);
+    if (rc != ORB_OK) return rc;
+    rc = ensure_out(h, cap);
+    if (rc != ORB_OK) return rc;
+    const OrbLevel& L0 = h->plan.lv[0];
+    if (n == 1 || frame_stride == stride * (size_t)rows) {
+        // frames are consecutive rows on both sides (device plane == pitch * rows): one 2D copy
+        CUDA_TRY(cudaMemcpy2DAsync(h->level0, L0.pitch, imgs, stride, cols, (size_t)rows * n, cudaMemcpyHostToDevice, h->stream));
+    } else {
+        for (int f = 0; f < n; ++f)
+            CUDA_TRY(cudaMemcpy2DAsync(h->level0 + f * L0.plane, L0.pitch, imgs + f * frame_stride, stride, cols, rows,
+                                       cudaMemcpyHostToDevice, h->stream));
+    }
+    h->last_n = n;
+    CUDA_TRY(orbk_run_extract(h->plan, n, h->d_kps, h->d_desc, h->out_cap, h->d_counts, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(counts, h->d_counts, sizeof(int) * n, cudaMemcpyDeviceToHost, h->stream));
+    rc = check_status(h, n);  // synchronises
+    if (rc != ORB_OK) return rc;
+    int maxc = 0;
+    for (int f = 0; f < n; ++f) maxc = std::max(maxc, counts[f]);
+    if (maxc > cap) return fail(ORB_ERR_CAPACITY, "frame needs %d keypoints, cap is %d", maxc, cap);
+    if (maxc > 0) {
+        CUDA_TRY(cudaMemcpy2DAsync(kps, (size_t)cap * sizeof(orb_keypoint), h->d_kps, (size_t)h->out_cap * sizeof(orb_keypoint),
+                                   (size_t)maxc * sizeof(orb_keypoint), n, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(cudaMemcpy2DAsync(desc, (size_t)cap * 32, h->d_desc, (size_t)h->out_cap * 32, (size_t)maxc * 32, n,
+                                   cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+    }
+    return ORB_OK;
+}
+
+extern "C" int orb_extract(orb_extractor* h, const uint8_t* img, int rows, int cols, size_t stride, orb_keypoint* kps,
+                           uint8_t* desc, int cap, int* count) {
+    if (!count) return fail(ORB_ERR_INVALID, "null count");
+    return orb_extract_batch(h, 1, img, rows, cols, stride, stride * (size_t)std::max(rows, 0), kps, desc, cap, count);
+}
+
+extern "C" int orb_get_pyramid_level(orb_extractor* h, int frame, int level, uint8_t* dst, size_t dst_stride, int* rows, int* cols) {
+    if (!h) return fail(ORB_ERR_INVALID, "null handle");
+    if (h->plan.rows == 0) return fail(ORB_ERR_INVALID, "no frame extracted yet");
+    if (level < 0 || level >= h->plan.nlevels || frame < 0 || frame >= h->max_batch) return fail(ORB_ERR_INVALID, "bad frame/level");
+    const OrbLevel& L = h->plan.lv[level];
+    if (rows) *rows = L.rows;
+    if (cols) *cols = L.cols;
+    if (!dst) return ORB_OK;
+    if (dst_stride < (size_t)L.cols) return fail(ORB_ERR_INVALID, "dst_stride < cols");
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaMemcpy2DAsync(dst, dst_stride, L.img + (size_t)frame * L.plane, L.pitch, L.cols, L.rows, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return ORB_OK;
+}
+
+extern "C" int orb_extractor_level_stats(orb_extractor* h, int frame, int32_t* candidates, int32_t* kept) {
+    if (!h || h->plan.rows == 0) return fail(ORB_ERR_INVALID, "no frame extracted yet");
+    if (frame < 0 || frame >= h->max_batch) return fail(ORB_ERR_INVALID, "bad frame");
+    CUDA_TRY(cudaSetDevice(h->device));
+    int c[ORB_MAX_LEVELS], k[ORB_MAX_LEVELS];
+    CUDA_TRY(cudaMemcpyAsync(c, h->plan.candCount + frame * ORB_MAX_LEVELS, sizeof c, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(k, h->plan.keptCount + frame * ORB_MAX_LEVELS, sizeof k, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    for (int l = 0; l < h->plan.nlevels; ++l) {
+        if (candidates) candidates[l] = c[h->plan.lv[l].src];
+        if (kept) kept[l] = k[l];
+    }
+    return ORB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// matcher handle
+// ------------------------------------------------------------------------------------------
+struct orb_matcher {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    // grow-only device scratch for the host-buffer entry points
+    void* buf[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    size_t cap[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+};
+
+static int scratch(orb_matcher* m, int slot, size_t bytes, void** out) {
+    if (bytes > m->cap[slot]) {
+        CUDA_TRY(cudaStreamSynchronize(m->stream));
+        if (m->buf[slot]) cudaFree(m->buf[slot]);
+        m->buf[slot] = nullptr;
+        m->cap[slot] = 0;
+        size_t want = std::max<size_t>(bytes + bytes / 4, 4096);
+        CUDA_TRY(cudaMalloc(&m->buf[slot], want));
+        m->cap[slot] = want;
+    }
+    *out = m->buf[slot];
+    return ORB_OK;
+}
+
+extern "C" int orb_matcher_create(int device, orb_matcher** out) {
+    if (!out) return fail(ORB_ERR_INVALID, "null argument");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(ORB_ERR_CUDA, "no CUDA device: %s (liborb_b200 has no CPU fallback)", cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(ORB_ERR_INVALID, "device %d out of range", device);
+    CUDA_TRY(cudaSetDevice(device));
+    orb_matcher* m = new orb_matcher();
+    m->device = device;
+    cudaError_t ce = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
+    if (ce != cudaSuccess) {
+        delete m;
+        return fail(ORB_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(ce));
+    }
+    *out = m;
+    return ORB_OK;
+}
+
+extern "C" void orb_matcher_destroy(orb_matcher* m) {
+    if (!m) return;
+    cudaSetDevice(m->device);
+    cudaStreamSynchronize(m->stream);
+    for (int i = 0; i < 8; ++i)
+        if (m->buf[i]) cudaFree(m->buf[i]);
+    cudaStreamDestroy(m->stream);
+    delete m;
+}
+
+extern "C" int orb_matcher_sync(orb_matcher* m) {
+    if (!m) return fail(ORB_ERR_INVALID, "null handle");
+    CUDA_TRY(cudaSetDevice(m->device));
+    CUDA_TRY(cudaStreamSynchronize(m->stream));
+    return ORB_OK;
+}
+extern "C" void* orb_matcher_stream(orb_matcher* m) { return m ? (void*)m->stream : nullptr; }
+
+extern "C" int orb_match_all_batch(orb_matcher* m, int npairs, const uint8_t* q, const int32_t* nq, size_t q_stride,
+                                   const uint8_t* t, const int32_t* nt, size_t t_stride, int32_t* best_idx,
+                                   int32_t* best_dist, int32_t* second_dist, size_t out_stride, int on_device) {
+    if (!m || !nq || !nt || !best_idx || !best_dist || !second_dist) return fail(ORB_ERR_INVALID, "null argument");
+    if (npairs <= 0) return ORB_OK;
+    if ((q_stride & 15) || (t_stride & 15)) return fail(ORB_ERR_INVALID, "descriptor strides must be multiples of 16 bytes");
+    CUDA_TRY(cudaSetDevice(m->device));
+    if (on_device) {
+        if (((uintptr_t)q & 15) || ((uintptr_t)t & 15)) return fail(ORB_ERR_INVALID, "descriptor arrays must be 16-byte aligned");
+        // max query count is not known on the host: launch for the stride
+        const int max_nq = (int)(out_stride);
+        CUDA_TRY(orbk_match_all(q, nq, q_stride, t, nt, t_stride, npairs, max_nq, best_idx, best_dist, second_dist, out_stride, m->stream));
+        return ORB_OK;
+    }
+    int max_nq = 0, max_nt = 0;
+    for (int p = 0; p < npairs; ++p) {
+        if (nq[p] < 0 || nt[p] < 0) return fail(ORB_ERR_INVALID, "negative count");
+        max_nq = std::max(max_nq, nq[p]);
+        max_nt = std::max(max_nt, nt[p]);
+    }
+    if ((size_t)max_nq > out_stride) return fail(ORB_ERR_INVALID, "out_stride < nq");
+    if ((size_t)max_nq * 32 > q_stride && npairs > 1) return fail(ORB_ERR_INVALID, "q_stride < nq*32");
+    if ((size_t)max_nt * 32 > t_stride && npairs > 1) return fail(ORB_ERR_INVALID, "t_stride < nt*32");
+    void *dq, *dt, *dn, *dout;
+    const size_t qbytes = (size_t)(npairs - 1) * q_stride + (size_t)max_nq * 32;
+    const size_t tbytes = (size_t)(npairs - 1) * t_stride + (size_t)max_nt * 32;
+    const size_t obytes = ((size_t)(npairs - 1) * out_stride + max_nq) * sizeof(int);
+    int rc;
+    if ((rc = scratch(m, 0, qbytes + 32, &dq)) || (rc = scratch(m, 1, tbytes + 32, &dt)) ||
+        (rc = scratch(m, 2, sizeof(int) * 2 * npairs, &dn)) || (rc = scratch(m, 3, obytes * 3, &dout)))
+        return rc;
+    if (qbytes) CUDA_TRY(cudaMemcpyAsync(dq, q, qbytes, cudaMemcpyHostToDevice, m->stream));
+    if (tbytes) CUDA_TRY(cudaMemcpyAsync(dt, t, tbytes, cudaMemcpyHostToDevice, m->stream));
+    int* dnq = (int*)dn;
+    int* dnt = dnq + npairs;
+    CUDA_TRY(cudaMemcpyAsync(dnq, nq, sizeof(int) * npairs, cudaMemcpyHostToDevice, m->stream));
+    CUDA_TRY(cudaMemcpyAsync(dnt, nt, sizeof(int) * npairs, cudaMemcpyHostToDevice, m->stream));
+    int* o0 = (int*)dout;
+    int* o1 = (int*)((char*)dout + obytes);
+    int* o2 = (int*)((char*)dout + 2 * obytes);
+    CUDA_TRY(orbk_match_all((const uint8_t*)dq, dnq, q_stride, (const uint8_t*)dt, dnt, t_stride, npairs, max_nq, o0, o1, o2, out_stride, m->stream));
+    if (obytes) {
+        CUDA_TRY(cudaMemcpyAsync(best_idx, o0, obytes, cudaMemcpyDeviceToHost, m->stream));
+        CUDA_TRY(cudaMemcpyAsync(best_dist, o1, obytes, cudaMemcpyDeviceToHost, m->stream));
+        CUDA_TRY(cudaMemcpyAsync(second_dist, o2, obytes, cudaMemcpyDeviceToHost, m->stream));
+    }
+    CUDA_TRY(cudaStreamSynchronize(m->stream));
+    return ORB_OK;
+}
+
+extern "C" int orb_match_all(orb_matcher* m, const uint8_t* q, int nq, const uint8_t* t, int nt, int32_t* best_idx,
+                             int32_t* best_dist, int32_t* second_dist) {
+    if (nq < 0 || nt < 0) return fail(ORB_ERR_INVALID, "negative count");
+    if (nq == 0) return ORB_OK;
+    const int32_t a = nq, b = nt;
+    return orb_match_all_batch(m, 1, q, &a, (size_t)(nq + 1) * 32, t, &b, (size_t)(nt + 1) * 32, best_idx, best_dist, second_dist,
+                               (size_t)nq, 0);
+}
+
+extern "C" int orb_match_csr(orb_matcher* m, const uint8_t* q, int nq, const uint8_t* t, int nt, const int32_t* offsets,
+                             const int32_t* cand, int tie_rule, int max_dist, int32_t* best_idx, int32_t* best_dist,
+                             int32_t* second_dist) {
+    if (!m || !offsets || !best_idx || !best_dist || !second_dist) return fail(ORB_ERR_INVALID, "null argument");
+    if (nq < 0 || nt < 0) return fail(ORB_ERR_INVALID, "negative count");
+    if (nq == 0) return ORB_OK;
+    if (tie_rule != ORB_TIE_FIRST_MIN && tie_rule != ORB_TIE_LAST_MIN) return fail(ORB_ERR_INVALID, "bad tie_rule");
+    const int ncand = offsets[nq];
+    if (ncand < 0 || offsets[0] != 0) return fail(ORB_ERR_INVALID, "offsets must start at 0 and be non-decreasing");
+    for (int i = 0; i < nq; ++i)
+        if (offsets[i + 1] < offsets[i]) return fail(ORB_ERR_INVALID, "offsets must be non-decreasing");
+    for (int c = 0; c < ncand; ++c)
+        if (cand[c] < 0 || cand[c] >= nt) return fail(ORB_ERR_INVALID, "candidate %d out of range", c);
+    CUDA_TRY(cudaSetDevice(m->device));
+    void *dq, *dt, *dofs, *dout;
+    int rc;
+    if ((rc = scratch(m, 0, (size_t)nq * 32 + 32, &dq)) || (rc = scratch(m, 1, (size_t)nt * 32 + 32, &dt)) ||
+        (rc = scratch(m, 2, sizeof(int) * ((size_t)nq + 1 + ncand), &dofs)) || (rc = scratch(m, 3, sizeof(int) * 3 * (size_t)nq, &dout)))
+        return rc;
+    CUDA_TRY(cudaMemcpyAsync(dq, q, (size_t)nq * 32, cudaMemcpyHostToDevice, m->stream));
+    if (nt) CUDA_TRY(cudaMemcpyAsync(dt, t, (size_t)nt * 32, cudaMemcpyHostToDevice, m->stream));
+    int* d_off = (int*)dofs;
+    int* d_cand = d_off + nq + 1;
+    CUDA_TRY(cudaMemcpyAsync(d_off, offsets, sizeof(int) * ((size_t)nq + 1), cudaMemcpyHostToDevice, m->stream));
+    if (ncand) CUDA_TRY(cudaMemcpyAsync(d_cand, cand, sizeof(int) * (size_t)ncand, cudaMemcpyHostToDevice, m->stream));
+    int* o = (int*)dout;
+    CUDA_TRY(orbk_match_csr((const uint8_t*)dq, nq, (const uint8_t*)dt, d_off, d_cand, tie_rule == ORB_TIE_LAST_MIN, max_dist, o, o + nq,
+                            o + 2 * (size_t)nq, m->stream));
+    CUDA_TRY(cudaMemcpyAsync(best_idx, o, sizeof(int) * nq, cudaMemcpyDeviceToHost, m->stream));
+    CUDA_TRY(cudaMemcpyAsync(best_dist, o + nq, sizeof(int) * nq, cudaMemcpyDeviceToHost, m->stream));
+    CUDA_TRY(cudaMemcpyAsync(second_dist, o + 2 * (size_t)nq, sizeof(int) * nq, cudaMemcpyDeviceToHost, m->stream));
+    CUDA_TRY(cudaStreamSynchronize(m->stream));
+    return ORB_OK;
+}
+
+extern "C" int orb_stereo_match(orb_matcher* m, const orb_keypoint* kl, const uint8_t* dl, int nl, const orb_keypoint* kr,
+                                const uint8_t* dr, int nr, const float* scale, int nlevels, int rows, float bf, float fx,
+                                int32_t* best_r, int32_t* best_dist) {
+    if (!m || !best_r || !best_dist || !scale) return fail(ORB_ERR_INVALID, "null argument");
+    if (nl < 0 || nr < 0 || nlevels < 1 || nlevels > ORB_MAX_LEVELS) return fail(ORB_ERR_INVALID, "bad count");
+    (void)rows;
+    if (nl == 0) return ORB_OK;
+    for (int i = 0; i < nr; ++i)
+        if (kr[i].octave < 0 || kr[i].octave >= nlevels) return fail(ORB_ERR_INVALID, "right keypoint %d: octave out of range", i);
+    CUDA_TRY(cudaSetDevice(m->device));
+    // mb = mbf/fx (src/Frame.cc:215); maxD = mbf/minZ with minZ = mb (:476-478)
+    const float mb = bf / fx;
+    const float maxD = bf / mb;
+    void *dkl, *ddl, *dkr, *ddr, *dsc, *dri, *dout;
+    int rc;
+    if ((rc = scratch(m, 0, (size_t)nl * 32 + 32, &ddl)) || (rc = scratch(m, 1, (size_t)nr * 32 + 32, &ddr)) ||
+        (rc = scratch(m, 4, (size_t)nl * 28 + 32, &dkl)) || (rc = scratch(m, 5, (size_t)nr * 28 + 32, &dkr)) ||
+        (rc = scratch(m, 6, sizeof(float) * ORB_MAX_LEVELS, &dsc)) || (rc = scratch(m, 7, sizeof(int4) * (size_t)(nr + 1), &dri)) ||
+        (rc = scratch(m, 3, sizeof(int) * 2 * (size_t)nl, &dout)))
+        return rc;
+    CUDA_TRY(cudaMemcpyAsync(dkl, kl, (size_t)nl * 28, cudaMemcpyHostToDevice, m->stream));
+    CUDA_TRY(cudaMemcpyAsync(ddl, dl, (size_t)nl * 32, cudaMemcpyHostToDevice, m->stream));
+    if (nr) {
+        CUDA_TRY(cudaMemcpyAsync(dkr, kr, (size_t)nr * 28, cudaMemcpyHostToDevice, m->stream));
+        CUDA_TRY(cudaMemcpyAsync(ddr, dr, (size_t)nr * 32, cudaMemcpyHostToDevice, m->stream));
+    }
+    CUDA_TRY(cudaMemcpyAsync(dsc, scale, sizeof(float) * nlevels, cudaMemcpyHostToDevice, m->stream));
+    int* o = (int*)dout;
+    CUDA_TRY(orbk_stereo((const orb_kp28*)dkl, (const uint8_t*)ddl, nl, (const orb_kp28*)dkr, (const uint8_t*)ddr, nr, (const float*)dsc,
+                         (int4*)dri, maxD, o, o + nl, m->stream));
+    CUDA_TRY(cudaMemcpyAsync(best_r, o, sizeof(int) * nl, cudaMemcpyDeviceToHost, m->stream));
+    CUDA_TRY(cudaMemcpyAsync(best_dist, o + nl, sizeof(int) * nl, cudaMemcpyDeviceToHost, m->stream));
+    CUDA_TRY(cudaStreamSynchronize(m->stream));
+    return ORB_OK;
+}

@@ -1,0 +1,66 @@
+// Host/device shared plan of one extractor configuration: per-level geometry of the
+// pyramid, the FAST cell grid, the octree roots and the device buffer layout.
+// Mirrors the arithmetic of reference src/ORBextractor.cc:116-170 (ctor tables),
+// :497-515 (level sizes) and :288-357 (cell grid), bit for bit.
+#pragma once
+#include <stdint.h>
+
+#define ORB_MAX_LEVELS 16
+#define ORB_EDGE 19          // EDGE_THRESHOLD (ORBextractor.cc:17)
+#define ORB_MINB 16          // minBorderX/Y = EDGE_THRESHOLD-3 (ORBextractor.cc:300-303)
+#define ORB_CELL 30.f        // W (ORBextractor.cc:290)
+#define ORB_OCT_DEPTH 13     // quadtree depth carried in a 32-bit path code (6 root bits + 2*13)
+#define ORB_MAX_DIM 8192     // rows/cols limit so that 13 halvings reach 1-px nodes
+
+// detect tile: up to DET_TILE_W x DET_TILE_H level pixels staged in shared memory
+#define DET_TILE_W 256
+#define DET_TILE_H 72
+#define DET_SP 272           // smem pitch of the image tile (bytes)
+#define DET_THREADS 256
+
+struct OrbLevel {
+    // image
+    int rows, cols;
+    int pitch;               // bytes per row of this level's device buffers
+    int src;                 // level whose pixels (and FAST candidates) this level shares
+    unsigned long long plane;  // bytes per frame of this level's device buffers
+    uint8_t* img;            // [batch][rows][pitch] (level 0: set per call)
+    uint8_t* blur;           // [batch][rows][pitch] Gaussian-blurred copy
+    // resize tables (level = resize(level-1)), device pointers; null when src != self or level 0
+    const int* xtab;         // [cols] packed: s | s1<<16
+    const int* xcoef;        // [cols] packed: a0 | a1<<16
+    const int* ytab;         // [rows] packed: sy0 | sy1<<16
+    const int* ycoef;        // [rows] packed: b0 | b1<<16
+    // FAST cell grid over [16, cols-16) x [16, rows-16)
+    int W, H;                // maxBorder - minBorder
+    int nCols, nRows, wCell, hCell;  // 0 cells when the level is smaller than one cell
+    int tileCells, tilesX;   // detect tiles: tileCells cells wide, one cell row high
+    int tileBase;            // first tile id of this level in the detect launch (src == self)
+    int nTiles;
+    // octree
+    int nIni;
+    float hX;
+    int nFeat;               // mnFeaturesPerLevel[level]
+    int kmax;                // bound on kept keypoints
+    unsigned candCap;        // worst-case FAST candidates per frame
+    uint2* cand;             // [batch][candCap]: x|y<<16 (relative to minBorder), score
+    unsigned long long* sortScratch;  // [batch][sortCap] global fallback for big problems
+    unsigned sortCap;        // pow2 >= candCap
+    uint2* kept;             // [batch][kmax]: x|y<<16 (level coords), score
+    int keptBase;            // offset of this level in describe launch space
+    float scale;             // mvScaleFactor[level]
+    int patchSize;           // int(31*scale)
+};
+
+struct OrbPlan {
+    int nlevels;
+    int rows, cols;          // level-0 shape this plan was built for
+    int iniTh, minTh, lowTh; // clamped to [0,255]; lowTh = min(ini,min)
+    int batch;               // frames per launch the buffers are sized for
+    int totalTiles;          // detect tiles per frame
+    int totalKmax;           // sum of kmax
+    int* candCount;          // [batch][ORB_MAX_LEVELS]
+    int* keptCount;          // [batch][ORB_MAX_LEVELS]
+    int* status;             // [batch] octree status flags (non-zero: unseparable keys)
+    OrbLevel lv[ORB_MAX_LEVELS];
+};

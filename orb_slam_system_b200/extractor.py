@@ -1,0 +1,149 @@
+"""Host-side mirror of the reference's ``ORB_SLAM2::ORBextractor`` over the C ABI.
+
+Same constructor arguments, getters and call semantics as reference
+include/ORBextractor.h:26-93 / src/ORBextractor.cc:442-495; the work happens in
+hand-written sm_100a kernels behind ``include/orb_b200.h``.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import KP_DTYPE, OrbParams, check, lib, ptr
+
+
+class ORBextractor:
+    HARRIS_SCORE = 0
+    FAST_SCORE = 1
+
+    def __init__(self, nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST, max_batch=1, device=0,
+                 max_rows=0, max_cols=0):
+        self.nfeatures = int(nfeatures)
+        self.scaleFactor = float(np.float32(scaleFactor))
+        self.nlevels = int(nlevels)
+        self.iniThFAST = int(iniThFAST)
+        self.minThFAST = int(minThFAST)
+        self.max_batch = int(max_batch)
+        self.device = int(device)
+        self._h = C.c_void_p()
+        p = OrbParams(self.nfeatures, self.scaleFactor, self.nlevels, self.iniThFAST, self.minThFAST)
+        check(lib().orb_extractor_create(C.byref(p), max_rows, max_cols, self.max_batch, self.device,
+                                         C.byref(self._h)))
+        n = self.nlevels
+        self._scale = np.zeros(n, np.float32)
+        self._inv_scale = np.zeros(n, np.float32)
+        self._sigma2 = np.zeros(n, np.float32)
+        self._inv_sigma2 = np.zeros(n, np.float32)
+        self._nfeat = np.zeros(n, np.int32)
+        check(lib().orb_extractor_tables(self._h, ptr(self._scale), ptr(self._inv_scale), ptr(self._sigma2),
+                                         ptr(self._inv_sigma2), ptr(self._nfeat)))
+        self._last_frames = 0
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            lib().orb_extractor_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- getters (include/ORBextractor.h:43-63) ----
+    def GetLevels(self):
+        return self.nlevels
+
+    def GetScaleFactor(self):
+        return self.scaleFactor
+
+    def GetScaleFactors(self):
+        return self._scale.copy()
+
+    def GetInverseScaleFactors(self):
+        return self._inv_scale.copy()
+
+    def GetScaleSigmaSquares(self):
+        return self._sigma2.copy()
+
+    def GetInverseScaleSigmaSquares(self):
+        return self._inv_sigma2.copy()
+
+    @property
+    def mnFeaturesPerLevel(self):
+        return self._nfeat.copy()
+
+    def keypoint_bound(self, rows, cols):
+        b = C.c_int(0)
+        check(lib().orb_extractor_keypoint_bound(self._h, rows, cols, C.byref(b)))
+        return b.value
+
+    # ---- operator() ----
+    def __call__(self, image, mask=None, cap=None):
+        """ORBextractor::operator()(image, mask, keypoints, descriptors); mask is ignored
+        (include/ORBextractor.h:38).  Returns (keypoints[KP_DTYPE], descriptors uint8[K,32]).
+        An empty image returns empty outputs (src/ORBextractor.cc:444-445)."""
+        image = np.ascontiguousarray(image, np.uint8) if image is not None else None
+        if image is None or image.size == 0:
+            return np.zeros(0, KP_DTYPE), np.zeros((0, 32), np.uint8)
+        assert image.ndim == 2, "CV_8UC1 image expected"
+        res = self.extract_batch(image[None], cap=cap)
+        return res[0]
+
+    def extract_batch(self, images, cap=None):
+        """n same-shape host frames [n, rows, cols] -> list of (keypoints, descriptors)."""
+        images = np.ascontiguousarray(images, np.uint8)
+        n, rows, cols = images.shape
+        assert n <= self.max_batch
+        cap = cap or self.keypoint_bound(rows, cols)
+        kps = np.zeros((n, cap), KP_DTYPE)
+        desc = np.zeros((n, cap, 32), np.uint8)
+        counts = np.zeros(n, np.int32)
+        check(lib().orb_extract_batch(self._h, n, ptr(images), rows, cols, images.strides[1], images.strides[0],
+                                      ptr(kps), ptr(desc), cap, ptr(counts)))
+        self._last_frames = n
+        return [(kps[f, :counts[f]].copy(), desc[f, :counts[f]].copy()) for f in range(n)]
+
+    def extract_batch_pinned(self, images, kps, desc, counts, cap):
+        """Same as extract_batch but with caller-owned (ideally pinned) host buffers, no copies
+        on the Python side.  images uint8 [n, rows, cols]; kps [n, cap] KP_DTYPE (or bytes
+        [n, cap, 28]); desc [n, cap, 32]; counts int32 [n]."""
+        n, rows, cols = images.shape
+        check(lib().orb_extract_batch(self._h, n, ptr(images), rows, cols, int(images.stride(1) if hasattr(images, "stride") else images.strides[1]),
+                                      int(images.stride(0) if hasattr(images, "stride") else images.strides[0]),
+                                      ptr(kps), ptr(desc), cap, ptr(counts)))
+        self._last_frames = n
+
+    def extract_batch_device(self, d_images, d_kps, d_desc, d_counts, cap):
+        """Device-resident batch: torch CUDA tensors (uint8 [n, rows, pitch>=cols] view with the
+        true `cols` given by d_images.shape[2]); asynchronous on the handle's stream."""
+        n, rows, cols = d_images.shape
+        check(lib().orb_extract_batch_device(self._h, n, ptr(d_images), rows, cols, d_images.stride(1),
+                                             d_images.stride(0), ptr(d_kps), ptr(d_desc), cap, ptr(d_counts)))
+        self._last_frames = n
+
+    def sync(self):
+        check(lib().orb_extractor_sync(self._h))
+
+    @property
+    def stream(self):
+        return lib().orb_extractor_stream(self._h)
+
+    def pyramid_level(self, level, frame=0):
+        r, c = C.c_int(0), C.c_int(0)
+        check(lib().orb_get_pyramid_level(self._h, frame, level, None, 0, C.byref(r), C.byref(c)))
+        out = np.zeros((r.value, c.value), np.uint8)
+        check(lib().orb_get_pyramid_level(self._h, frame, level, ptr(out), out.strides[0], C.byref(r), C.byref(c)))
+        return out
+
+    @property
+    def mvImagePyramid(self):
+        """Level images of frame 0 of the last call (tight crops; the reference keeps a 19-px
+        reflected border around each, which nothing on this path reads)."""
+        return [self.pyramid_level(l) for l in range(self.nlevels)]
+
+    def level_stats(self, frame=0):
+        cand = np.zeros(self.nlevels, np.int32)
+        kept = np.zeros(self.nlevels, np.int32)
+        check(lib().orb_extractor_level_stats(self._h, frame, ptr(cand), ptr(kept)))
+        return cand, kept

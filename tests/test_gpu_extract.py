@@ -1,0 +1,120 @@
+"""Parity of the CUDA extractor (through the C ABI) against the CPU oracle.
+
+Bar (BASELINE.json north_star): keypoint coordinates, octave, count, FAST response
+bit-exact; angles within 1e-3 deg; descriptor bit-mismatch rate reported (0 expected).
+"""
+import numpy as np
+import pytest
+
+import oracle
+from orb_slam_system_b200 import ORBextractor
+
+pytestmark = pytest.mark.gpu
+
+ANGLE_TOL_DEG = 1e-3
+
+
+def compare(kg, dg, ko, do, tag=""):
+    assert len(kg) == len(ko), f"{tag}: count {len(kg)} vs oracle {len(ko)}"
+    for fld in ("x", "y", "size", "response", "octave", "class_id"):
+        bad = np.nonzero(kg[fld] != ko[fld])[0]
+        assert bad.size == 0, f"{tag}: field {fld} differs at {bad[:5]}: {kg[fld][bad[:5]]} vs {ko[fld][bad[:5]]}"
+    dang = np.abs(kg["angle"] - ko["angle"])
+    dang = np.minimum(dang, 360.0 - dang)
+    assert dang.max(initial=0.0) <= ANGLE_TOL_DEG, f"{tag}: angle off by {dang.max()}"
+    bits = np.unpackbits(dg ^ do, axis=1).sum()
+    rate = bits / max(1, dg.size * 8)
+    return dict(n=len(kg), angle_exact=int((kg["angle"] == ko["angle"]).sum()), desc_bit_mismatch=int(bits), rate=rate)
+
+
+CASES = [
+    # rows, cols, nfeatures, variant, right, frame
+    (480, 640, 1000, 0, 0, 0),      # BASELINE config 1 (TUM1)
+    (480, 752, 1200, 0, 0, 0),      # config 2 left
+    (480, 752, 1200, 0, 1, 0),      # config 2 right
+    (376, 1241, 2000, 0, 0, 0),     # config 3 (KITTI), 0-wide last cell column
+    (376, 1241, 2000, 1, 0, 1),     # low contrast: minThFAST retries
+    (375, 1242, 2000, 0, 0, 2),     # KITTI03 shape, 1-wide last column
+    (200, 300, 500, 0, 0, 0),
+    (120, 160, 300, 0, 0, 0),       # top levels smaller than one cell
+    (90, 90, 300, 0, 0, 0),         # top level smaller than the 16-px margins
+    (300, 200, 500, 0, 0, 0),       # portrait: nIni == 0, no keypoints at all
+    (250, 250, 400, 1, 0, 3),
+]
+
+
+@pytest.mark.parametrize("rows,cols,nf,variant,right,frame", CASES)
+def test_extract_matches_oracle(rows, cols, nf, variant, right, frame):
+    img = oracle.synth_frame(rows, cols, frame=frame, variant=variant, right=right)
+    ko, do = oracle.extract(img, nfeatures=nf, cap=16 * nf)
+    ex = ORBextractor(nf, 1.2, 8, 20, 7)
+    kg, dg = ex(img)
+    info = compare(kg, dg, ko, do, tag=f"{rows}x{cols}")
+    print(info)
+    assert info["desc_bit_mismatch"] == 0
+    ex.close()
+
+
+def test_level_stats_match_known_answers():
+    # SURVEY A.8 known-answer counts for the KITTI-shape synthetic frame
+    img = oracle.synth_frame(376, 1241)
+    ex = ORBextractor(2000, 1.2, 8, 20, 7)
+    kg, _ = ex(img)
+    cand, kept = ex.level_stats()
+    assert cand.tolist() == [7111, 7111, 9303, 8657, 6734, 4691, 3124, 1921]
+    assert kept.tolist() == [766, 766, 768, 768, 768, 192, 192, 256]
+    assert len(kg) == 4476
+    ex.close()
+
+
+def test_pyramid_levels_match_oracle():
+    img = oracle.synth_frame(376, 1241, frame=4)
+    ex = ORBextractor(2000, 1.2, 8, 20, 7)
+    ex(img)
+    for l in range(8):
+        got = ex.pyramid_level(l)
+        want = oracle.pyramid_level(img, l)
+        assert got.shape == want.shape
+        assert (got == want).all(), f"level {l}"
+    ex.close()
+
+
+def test_batch_equals_single_and_is_deterministic():
+    rows, cols, nf = 376, 1241, 2000
+    frames = np.stack([oracle.synth_frame(rows, cols, frame=f, right=f & 1) for f in range(6)])
+    ex = ORBextractor(nf, 1.2, 8, 20, 7, max_batch=6)
+    res1 = ex.extract_batch(frames)
+    res2 = ex.extract_batch(frames)
+    for f in range(6):
+        ko, do = oracle.extract(frames[f], nfeatures=nf, cap=16 * nf)
+        info = compare(res1[f][0], res1[f][1], ko, do, tag=f"frame {f}")
+        assert info["desc_bit_mismatch"] == 0
+        assert res1[f][0].tobytes() == res2[f][0].tobytes()
+        assert (res1[f][1] == res2[f][1]).all()
+    ex.close()
+
+
+def test_other_parameters():
+    img = oracle.synth_frame(480, 640, frame=9)
+    for (nf, sf, nl, ini, mn) in [(500, 1.2, 8, 20, 7), (1500, 1.1, 6, 30, 10), (800, 1.5, 4, 12, 12), (300, 1.2, 1, 20, 7),
+                                  (1000, 1.2, 8, 40, 5)]:
+        ko, do = oracle.extract(img, nfeatures=nf, scaleFactor=sf, nlevels=nl, iniThFAST=ini, minThFAST=mn, cap=16 * nf)
+        ex = ORBextractor(nf, sf, nl, ini, mn)
+        kg, dg = ex(img)
+        info = compare(kg, dg, ko, do, tag=f"params {(nf, sf, nl, ini, mn)}")
+        assert info["desc_bit_mismatch"] == 0
+        ex.close()
+
+
+def test_empty_and_error_shapes():
+    from orb_slam_system_b200 import OrbError
+    ex = ORBextractor(1000, 1.2, 8, 20, 7)
+    k, d = ex(np.zeros((0, 0), np.uint8))
+    assert len(k) == 0 and d.shape == (0, 32)
+    # flat image: no corners, zero keypoints
+    k, d = ex(np.full((240, 320), 77, np.uint8))
+    assert len(k) == 0
+    # shape on which the reference itself faults (level 7 has rows == 32 -> division by zero)
+    with pytest.raises(OrbError):
+        ex(oracle.synth_frame(96, 300))
+    ex.close()
