@@ -116,6 +116,15 @@ int orb_get_pyramid_level(orb_extractor* h, int frame, int level, uint8_t* dst, 
  * FAST candidates handed to the octree and keypoints kept, per level. */
 int orb_extractor_level_stats(orb_extractor* h, int frame, int32_t* candidates, int32_t* kept);
 
+/* Per-stage device timing (CUDA events on the handle's stream around each kernel stage:
+ * 0 pyramid, 1 detect, 2 octree, 3 blur, 4 describe).  set_profiling(1) clears the records and
+ * starts recording every following extract call; stage_times synchronises and returns the
+ * summed milliseconds per stage and the number of calls recorded. */
+#define ORB_NUM_STAGES 5
+int orb_extractor_set_profiling(orb_extractor* h, int on);
+int orb_extractor_stage_times(orb_extractor* h, double* ms_sum, int* ncalls);
+const char* orb_stage_name(int stage);
+
 /* ---- matcher: replaces the Hamming scans of ORBmatcher / Frame --------------------------- */
 
 int orb_matcher_create(int device, orb_matcher** out);

@@ -55,7 +55,8 @@ EXPORTS = [
     "orb_extractor_create", "orb_extractor_destroy", "orb_extractor_tables",
     "orb_extractor_keypoint_bound", "orb_extract", "orb_extract_batch", "orb_extract_batch_device",
     "orb_extractor_sync", "orb_extractor_stream", "orb_get_pyramid_level",
-    "orb_extractor_level_stats", "orb_matcher_create", "orb_matcher_destroy", "orb_match_all",
+    "orb_extractor_level_stats", "orb_extractor_set_profiling", "orb_extractor_stage_times",
+    "orb_stage_name", "orb_matcher_create", "orb_matcher_destroy", "orb_match_all",
     "orb_match_all_batch", "orb_match_csr", "orb_stereo_match", "orb_matcher_sync",
     "orb_matcher_stream", "orb_last_error", "orb_kernel_launch_count", "orb_version",
 ]
@@ -84,6 +85,10 @@ def lib():
         L.orb_extractor_stream.restype = vp
         L.orb_get_pyramid_level.argtypes = [vp, i32, i32, vp, sz, C.POINTER(i32), C.POINTER(i32)]
         L.orb_extractor_level_stats.argtypes = [vp, i32, vp, vp]
+        L.orb_extractor_set_profiling.argtypes = [vp, i32]
+        L.orb_extractor_stage_times.argtypes = [vp, vp, C.POINTER(i32)]
+        L.orb_stage_name.argtypes = [i32]
+        L.orb_stage_name.restype = C.c_char_p
         L.orb_matcher_create.argtypes = [i32, C.POINTER(vp)]
         L.orb_matcher_destroy.argtypes = [vp]
         L.orb_matcher_destroy.restype = None

@@ -789,12 +789,13 @@ cudaError_t orbk_init_device() {
 }
 
 cudaError_t orbk_run_extract(const OrbPlan& plan, int nframes, orb_keypoint_dev* d_kps, uint8_t* d_desc, int cap,
-                             int* d_counts, cudaStream_t st) {
+                             int* d_counts, cudaStream_t st, cudaEvent_t* ev) {
     cudaError_t e;
     e = cudaMemsetAsync(plan.candCount, 0, sizeof(int) * ORB_MAX_LEVELS * plan.batch, st);
     if (e != cudaSuccess) return e;
     e = cudaMemsetAsync(plan.status, 0, sizeof(int) * plan.batch, st);
     if (e != cudaSuccess) return e;
+    if (ev) cudaEventRecord(ev[0], st);
     // pyramid: level l = resize(level l-1); same-size levels alias their source
     for (int l = 1; l < plan.nlevels; ++l) {
         const OrbLevel& D = plan.lv[l];
@@ -805,6 +806,7 @@ cudaError_t orbk_run_extract(const OrbPlan& plan, int nframes, orb_keypoint_dev*
                                          D.xcoef, D.ytab, D.ycoef);
         ++g_launches;
     }
+    if (ev) cudaEventRecord(ev[1], st);
     int nsrc = 0, blurTiles = 0;
     for (int l = 0; l < plan.nlevels; ++l)
         if (plan.lv[l].src == l) {
@@ -815,11 +817,15 @@ cudaError_t orbk_run_extract(const OrbPlan& plan, int nframes, orb_keypoint_dev*
         k_detect<<<dim3(plan.totalTiles, nframes), DET_THREADS, kDetectSmem, st>>>(plan);
         ++g_launches;
     }
+    if (ev) cudaEventRecord(ev[2], st);
     k_octree<<<dim3(nsrc, nframes), OCT_THREADS, kOctreeSmem, st>>>(plan);
     ++g_launches;
+    if (ev) cudaEventRecord(ev[3], st);
     k_blur<<<dim3(blurTiles, nframes), 256, 0, st>>>(plan);
     ++g_launches;
+    if (ev) cudaEventRecord(ev[4], st);
     k_describe<<<dim3((plan.totalKmax + 7) / 8, nframes), 256, 0, st>>>(plan, d_kps, d_desc, cap, d_counts);
     ++g_launches;
+    if (ev) cudaEventRecord(ev[5], st);
     return cudaGetLastError();
 }

@@ -137,6 +137,26 @@ struct orb_extractor {
     int out_cap = 0;
     int last_n = 0;
     std::vector<int> h_status;
+    // per-stage CUDA-event records (orb_extractor_set_profiling)
+    bool profiling = false;
+    std::vector<cudaEvent_t> events;  // (ORB_STAGES + 1) per recorded call
+    cudaEvent_t* next_events() {
+        if (!profiling) return nullptr;
+        const size_t base = events.size();
+        for (int i = 0; i <= ORB_STAGES; ++i) {
+            cudaEvent_t e;
+            if (cudaEventCreate(&e) != cudaSuccess) {
+                events.resize(base);
+                return nullptr;
+            }
+            events.push_back(e);
+        }
+        return &events[base];
+    }
+    void clear_events() {
+        for (cudaEvent_t e : events) cudaEventDestroy(e);
+        events.clear();
+    }
 };
 
 static void free_plan(orb_extractor* h) {
@@ -351,6 +371,7 @@ extern "C" void orb_extractor_destroy(orb_extractor* h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     free_plan(h);
+    h->clear_events();
     if (h->d_kps) cudaFree(h->d_kps);
     if (h->d_desc) cudaFree(h->d_desc);
     if (h->d_counts) cudaFree(h->d_counts);
@@ -423,7 +444,7 @@ extern "C" int orb_extract_batch_device(orb_extractor* h, int n, const uint8_t* 
                                        stride, cols, rows, cudaMemcpyDeviceToDevice, h->stream));
     }
     h->last_n = n;
-    CUDA_TRY(orbk_run_extract(P, n, reinterpret_cast<orb_keypoint_dev*>(d_kps), d_desc, cap, d_counts, h->stream));
+    CUDA_TRY(orbk_run_extract(P, n, reinterpret_cast<orb_keypoint_dev*>(d_kps), d_desc, cap, d_counts, h->stream, h->next_events()));
     return ORB_OK;
 }
 
@@ -436,6 +457,36 @@ extern "C" int orb_extractor_sync(orb_extractor* h) {
 }
 
 extern "C" void* orb_extractor_stream(orb_extractor* h) { return h ? (void*)h->stream : nullptr; }
+
+extern "C" int orb_extractor_set_profiling(orb_extractor* h, int on) {
+    if (!h) return fail(ORB_ERR_INVALID, "null handle");
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    h->clear_events();
+    h->profiling = on != 0;
+    return ORB_OK;
+}
+
+extern "C" int orb_extractor_stage_times(orb_extractor* h, double* ms_sum, int* ncalls) {
+    if (!h || !ms_sum || !ncalls) return fail(ORB_ERR_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    for (int i = 0; i < ORB_STAGES; ++i) ms_sum[i] = 0.0;
+    const size_t per = ORB_STAGES + 1;
+    *ncalls = (int)(h->events.size() / per);
+    for (size_t c = 0; c < h->events.size() / per; ++c)
+        for (int i = 0; i < ORB_STAGES; ++i) {
+            float ms = 0.f;
+            CUDA_TRY(cudaEventElapsedTime(&ms, h->events[c * per + i], h->events[c * per + i + 1]));
+            ms_sum[i] += ms;
+        }
+    return ORB_OK;
+}
+
+extern "C" const char* orb_stage_name(int stage) {
+    static const char* names[ORB_STAGES] = {"pyramid", "detect", "octree", "blur", "describe"};
+    return stage >= 0 && stage < ORB_STAGES ? names[stage] : "";
+}
 
 extern "C" int orb_extract_batch(orb_extractor* h, int n, const uint8_t* imgs, int rows, int cols, size_t stride,
                                  size_t frame_stride, orb_keypoint* kps, uint8_t* desc, int cap, int* counts) {
@@ -463,7 +514,7 @@ extern "C" int orb_extract_batch(orb_extractor* h, int n, const uint8_t* imgs, i
                                        cudaMemcpyHostToDevice, h->stream));
     }
     h->last_n = n;
-    CUDA_TRY(orbk_run_extract(h->plan, n, h->d_kps, h->d_desc, h->out_cap, h->d_counts, h->stream));
+    CUDA_TRY(orbk_run_extract(h->plan, n, h->d_kps, h->d_desc, h->out_cap, h->d_counts, h->stream, h->next_events()));
     CUDA_TRY(cudaMemcpyAsync(counts, h->d_counts, sizeof(int) * n, cudaMemcpyDeviceToHost, h->stream));
     rc = check_status(h, n);  // synchronises
     if (rc != ORB_OK) return rc;

@@ -142,6 +142,16 @@ class ORBextractor:
         reflected border around each, which nothing on this path reads)."""
         return [self.pyramid_level(l) for l in range(self.nlevels)]
 
+    def set_profiling(self, on=True):
+        check(lib().orb_extractor_set_profiling(self._h, 1 if on else 0))
+
+    def stage_times(self):
+        """{stage name: summed ms} over the calls recorded since set_profiling(True), and the call count."""
+        ms = np.zeros(5, np.float64)
+        n = C.c_int(0)
+        check(lib().orb_extractor_stage_times(self._h, ptr(ms), C.byref(n)))
+        return {lib().orb_stage_name(i).decode(): float(ms[i]) for i in range(5)}, n.value
+
     def level_stats(self, frame=0):
         cand = np.zeros(self.nlevels, np.int32)
         kept = np.zeros(self.nlevels, np.int32)
