@@ -1,6 +1,6 @@
 """Deterministic synthetic frames: counter-based splitmix64 block texture.
 
-Library-free definition shared by the CPU oracle (oracle/orb_oracle.cpp synth_frame) and the
+Library-free definition; the CPU checker restates the same generator and the
 benchmarks; tests assert the two agree byte for byte.  variant 0: blocks (5,11,23,47);
 variant 1: blocks (4,8,16,32) with the left half at quarter contrast (exercises the
 minThFAST retry); right=1: the right image of a stereo pair, i.e. the left texture sampled
