@@ -17,6 +17,12 @@
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned vmax3(unsigned a, unsigned b, unsigned c) { return __vimax3_u16x2(a, b, c); }
 __device__ __forceinline__ unsigned vmin3(unsigned a, unsigned b, unsigned c) { return __vimin3_u16x2(a, b, c); }
+// four unsigned bytes (pixels) times four signed bytes (weights), accumulated into a signed int
+__device__ __forceinline__ int dp4a_us(unsigned a, int b, int c) {
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
 
 // ------------------------------------------------------------------------------------------
 // k_resize: cv::resize INTER_LINEAR 8UC1 (fixed point), one level from the
@@ -60,17 +66,25 @@ __global__ void __launch_bounds__(256) k_resize(const uint8_t* __restrict__ src,
 //   pass A  exact corner score m = max(c - min_arcs max_arc r, max_arcs min_arc r - c) for
 //           4 pixels per thread on packed u16x2 lanes (VIMNMX3.U16x2), stored as
 //           u = max(m, lowTh) - lowTh in a byte tile (0 = not a corner at lowTh).
-//   pass B  strict 8-neighbour maximum inside the pixel's own cell; per-cell flag
-//           "has a survivor at iniTh" (cv::FAST + NMS returned non-empty).
+//   pass B  strict 8-neighbour maximum inside the pixel's own cell, 4 pixels per thread on the
+//           same packed lanes (no per-pixel branches); survivors go to a shared-memory list
+//           and set the per-cell flag "cv::FAST + NMS at iniTh returned non-empty".
 //   pass C  emit survivors at iniTh, or at minTh where the cell flag is clear
 //           (reference ORBextractor.cc:293-296,330-331).
 // cv::FAST semantics: candidates exist 3 px inside the cell image, NMS
 // neighbours outside the cell's candidate area count as 0, response = m - 1.
 // ------------------------------------------------------------------------------------------
+#define DET_MAX_SURV 4096  // >= ceil(250/2) * ceil(59/2): NMS survivors are never 8-adjacent
+
 struct DetectSmem {
-    unsigned img[DET_TILE_H][DET_SP / 4];    // image tile, later reused as the survivor tile F
-    unsigned sc[DET_TILE_H][DET_SP / 4];     // score tile with a one-word / one-row zero border
+    union {
+        unsigned img[DET_TILE_H][DET_SP / 4];  // image tile (passes stage + A)
+        unsigned surv[DET_MAX_SURV];           // survivor list (passes B + C): u | r<<8 | cx<<16 | cell<<24
+    };
+    unsigned sc[DET_TILE_H][DET_SP / 4];       // score tile with a one-word / one-row zero border
+    unsigned char cellOf[DET_TILE_W + 8];      // candidate column -> cell index inside the tile
     int cellHasIni[16];
+    int nSurv;
     int nEmit;
     int emitBase;
     int emitFill;
@@ -102,6 +116,10 @@ __device__ __forceinline__ void fast_score_pairs(const unsigned (&r)[16], unsign
     u = __vadd2(__vmaxs2(m, low2), neglow2);
 }
 
+// bytes 0 and 2 / bytes 1 and 3 of a word as two zero-extended 16-bit lanes
+__device__ __forceinline__ unsigned even_lanes(unsigned w) { return w & 0x00ff00ffu; }
+__device__ __forceinline__ unsigned odd_lanes(unsigned w) { return __byte_perm(w, 0u, 0x4341); }
+
 __global__ void __launch_bounds__(DET_THREADS) k_detect(const __grid_constant__ OrbPlan plan) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     DetectSmem& sm = *reinterpret_cast<DetectSmem*>(smem_raw);
@@ -128,6 +146,7 @@ __global__ void __launch_bounds__(DET_THREADS) k_detect(const __grid_constant__ 
     if (CW <= 0 || CH <= 0) return;
     const int QR = (CW + 3) >> 2;  // 4-pixel groups per candidate row
     const int tid = threadIdx.x;
+    const int wCell = L.wCell;
 
     // ---- stage the image tile: smem byte (r, c) = level pixel (Y0 + r, X0 + c)
     {
@@ -135,13 +154,15 @@ __global__ void __launch_bounds__(DET_THREADS) k_detect(const __grid_constant__ 
         const int wb = X0 >> 2, sh = (X0 & 3) * 8;
         const int nw = min((TW + 9) >> 2, DET_SP / 4);
         const int pitchW = L.pitch >> 2;
-        for (int i = tid; i < TH * nw; i += DET_THREADS) {
-            const int r = i / nw, k = i - r * nw;
+        const int warp = tid >> 5, lane = tid & 31;
+        for (int r = warp; r < TH; r += DET_THREADS / 32) {
             const unsigned* g = reinterpret_cast<const unsigned*>(base + (size_t)(Y0 + r) * L.pitch);
-            const int idx = wb + k;
-            const unsigned lo = idx < pitchW ? __ldg(g + idx) : 0u;
-            const unsigned hi = idx + 1 < pitchW ? __ldg(g + idx + 1) : 0u;
-            sm.img[r][k] = __funnelshift_r(lo, hi, sh);
+            for (int k = lane; k < nw; k += 32) {
+                const int idx = wb + k;
+                const unsigned lo = idx < pitchW ? __ldg(g + idx) : 0u;
+                const unsigned hi = idx + 1 < pitchW ? __ldg(g + idx + 1) : 0u;
+                sm.img[r][k] = __funnelshift_r(lo, hi, sh);
+            }
         }
         // zero border of the score tile: rows 0 and CH+1, words 0 and QR+1
         for (int i = tid; i < 2 * (QR + 2); i += DET_THREADS) {
@@ -152,8 +173,10 @@ __global__ void __launch_bounds__(DET_THREADS) k_detect(const __grid_constant__ 
             const int r = i >> 1;
             sm.sc[r][(i & 1) ? QR + 1 : 0] = 0u;
         }
+        for (int i = tid; i < CW + 4; i += DET_THREADS) sm.cellOf[i] = (unsigned char)(i / wCell);
         if (tid < 16) sm.cellHasIni[tid] = 0;
         if (tid == 0) {
+            sm.nSurv = 0;
             sm.nEmit = 0;
             sm.emitFill = 0;
         }
@@ -164,20 +187,19 @@ __global__ void __launch_bounds__(DET_THREADS) k_detect(const __grid_constant__ 
     // candidate col cx sits at tile byte column cx + 3.
     const unsigned low2 = (unsigned)plan.lowTh * 0x00010001u;
     const unsigned neglow2 = ((unsigned)(-plan.lowTh) & 0xffffu) * 0x00010001u;
-    {
-        const int q = tid & 63;
-        if (q < QR) {
-            for (int r = tid >> 6; r < CH; r += DET_THREADS / 64) {
-                // rows r..r+6 of the tile; words q, q+1, q+2 hold tile bytes 4q..4q+11 = b0..b11,
-                // candidate pixels p0..p3 = b3..b6, ring offset dx reads b(3+dx)..b(6+dx)
-                unsigned w[7][3];
+    const int q = tid & 63, grp = tid >> 6;
+    if (q < QR) {
+        for (int r = grp; r < CH; r += DET_THREADS / 64) {
+            // rows r..r+6 of the tile; words q, q+1, q+2 hold tile bytes 4q..4q+11 = b0..b11,
+            // candidate pixels p0..p3 = b3..b6, ring offset dx reads b(3+dx)..b(6+dx)
+            unsigned w[7][3];
 #pragma unroll
-                for (int rr = 0; rr < 7; ++rr) {
-                    w[rr][0] = sm.img[r + rr][q];
-                    w[rr][1] = sm.img[r + rr][q + 1];
-                    w[rr][2] = sm.img[r + rr][q + 2];
-                }
-                // unaligned 4-byte windows: win(rr, dx) = bytes b(3+dx)..b(6+dx) of row rr
+            for (int rr = 0; rr < 7; ++rr) {
+                w[rr][0] = sm.img[r + rr][q];
+                w[rr][1] = sm.img[r + rr][q + 1];
+                w[rr][2] = sm.img[r + rr][q + 2];
+            }
+            // unaligned 4-byte windows: win(rr, dx) = bytes b(3+dx)..b(6+dx) of row rr
 #define WIN(rr, dx)                                                                   \
     ((dx) == -3 ? w[rr][0]                                                            \
      : (dx) == -2 ? __byte_perm(w[rr][0], w[rr][1], 0x4321)                           \
@@ -186,104 +208,117 @@ __global__ void __launch_bounds__(DET_THREADS) k_detect(const __grid_constant__ 
      : (dx) == 1  ? w[rr][1]                                                          \
      : (dx) == 2  ? __byte_perm(w[rr][1], w[rr][2], 0x4321)                           \
                   : __byte_perm(w[rr][1], w[rr][2], 0x5432))
-                // ring index k -> (dx, dy); tile row = 3 + dy
-                unsigned ring[16];
-                ring[0] = WIN(6, 0);    // (0, 3)
-                ring[1] = WIN(6, 1);    // (1, 3)
-                ring[2] = WIN(5, 2);    // (2, 2)
-                ring[3] = WIN(4, 3);    // (3, 1)
-                ring[4] = WIN(3, 3);    // (3, 0)
-                ring[5] = WIN(2, 3);    // (3,-1)
-                ring[6] = WIN(1, 2);    // (2,-2)
-                ring[7] = WIN(0, 1);    // (1,-3)
-                ring[8] = WIN(0, 0);    // (0,-3)
-                ring[9] = WIN(0, -1);   // (-1,-3)
-                ring[10] = WIN(1, -2);  // (-2,-2)
-                ring[11] = WIN(2, -3);  // (-3,-1)
-                ring[12] = WIN(3, -3);  // (-3, 0)
-                ring[13] = WIN(4, -3);  // (-3, 1)
-                ring[14] = WIN(5, -2);  // (-2, 2)
-                ring[15] = WIN(6, -1);  // (-1, 3)
-                const unsigned cen = WIN(3, 0);
+            // ring index k -> (dx, dy); tile row = 3 + dy
+            unsigned ring[16];
+            ring[0] = WIN(6, 0);    // (0, 3)
+            ring[1] = WIN(6, 1);    // (1, 3)
+            ring[2] = WIN(5, 2);    // (2, 2)
+            ring[3] = WIN(4, 3);    // (3, 1)
+            ring[4] = WIN(3, 3);    // (3, 0)
+            ring[5] = WIN(2, 3);    // (3,-1)
+            ring[6] = WIN(1, 2);    // (2,-2)
+            ring[7] = WIN(0, 1);    // (1,-3)
+            ring[8] = WIN(0, 0);    // (0,-3)
+            ring[9] = WIN(0, -1);   // (-1,-3)
+            ring[10] = WIN(1, -2);  // (-2,-2)
+            ring[11] = WIN(2, -3);  // (-3,-1)
+            ring[12] = WIN(3, -3);  // (-3, 0)
+            ring[13] = WIN(4, -3);  // (-3, 1)
+            ring[14] = WIN(5, -2);  // (-2, 2)
+            ring[15] = WIN(6, -1);  // (-1, 3)
+            const unsigned cen = WIN(3, 0);
 #undef WIN
-                // even lanes: pixels p0, p2 ; odd lanes: pixels p1, p3
-                unsigned re[16], ro[16];
+            // even lanes: pixels p0, p2 ; odd lanes: pixels p1, p3
+            unsigned re[16], ro[16];
 #pragma unroll
-                for (int k = 0; k < 16; ++k) {
-                    re[k] = ring[k] & 0x00ff00ffu;
-                    ro[k] = (ring[k] >> 8) & 0x00ff00ffu;
-                }
-                unsigned ue, uo;
-                fast_score_pairs(re, cen & 0x00ff00ffu, low2, neglow2, ue);
-                fast_score_pairs(ro, (cen >> 8) & 0x00ff00ffu, low2, neglow2, uo);
-                unsigned word = ue | (uo << 8);  // bytes: p0, p1, p2, p3
-                const int rem = CW - 4 * q;      // candidate cols left in this row
-                if (rem < 4) word &= (1u << (8 * rem)) - 1u;
-                sm.sc[r + 1][q + 1] = word;
+            for (int k = 0; k < 16; ++k) {
+                re[k] = even_lanes(ring[k]);
+                ro[k] = odd_lanes(ring[k]);
             }
+            unsigned ue, uo;
+            fast_score_pairs(re, even_lanes(cen), low2, neglow2, ue);
+            fast_score_pairs(ro, odd_lanes(cen), low2, neglow2, uo);
+            unsigned word = ue | (uo << 8);  // bytes: p0, p1, p2, p3
+            const int rem = CW - 4 * q;      // candidate cols left in this row
+            if (rem < 4) word &= (1u << (8 * rem)) - 1u;
+            sm.sc[r + 1][q + 1] = word;
         }
     }
     __syncthreads();
 
-    // ---- pass B: cell-local NMS -> survivor tile F (reuses the image tile memory)
+    // ---- pass B: cell-local NMS on packed lanes.  Thread (q, grp) walks a strip of rows with a
+    // 3-row sliding window.  For candidate col 4q+k the left / right neighbours are dropped when
+    // they belong to another cell (maskL / maskR).
     const int iniU = plan.iniTh - plan.lowTh + 1;  // u >= iniU  <=>  m > iniTh
     const int minU = plan.minTh - plan.lowTh + 1;
-    const int wCell = L.wCell;
-    for (int i = tid; i < CH * QR; i += DET_THREADS) {
-        const int r = i / QR, q = i - r * QR;
-        const unsigned wv = sm.sc[r + 1][q + 1];
-        unsigned outw = 0;
-        if (wv) {
-            // neighbourhood bytes: cols 4q-1 .. 4q+4 of rows r-1, r, r+1 (bordered coords)
-            unsigned long long rows3[3];
+    if (q < QR) {
+        unsigned mLe = 0, mLo = 0, mRe = 0, mRo = 0;  // 0x00ff per lane where the neighbour counts
 #pragma unroll
-            for (int d = 0; d < 3; ++d) {
-                const unsigned a = sm.sc[r + d][q], b = sm.sc[r + d][q + 1], c = sm.sc[r + d][q + 2];
-                // 6 bytes: a.byte3, b.byte0..3, c.byte0
-                rows3[d] = (unsigned long long)(a >> 24) | ((unsigned long long)b << 8) |
-                           ((unsigned long long)(c & 0xffu) << 40);
+        for (int k = 0; k < 4; ++k) {
+            const int cx = 4 * q + k;
+            const bool first = cx == 0 || sm.cellOf[cx - 1] != sm.cellOf[cx];
+            const bool last = sm.cellOf[cx + 1] != sm.cellOf[cx];
+            const unsigned lane = 0xffu << (16 * (k >> 1));
+            if (!first) { if (k & 1) mLo |= lane; else mLe |= lane; }
+            if (!last) { if (k & 1) mRo |= lane; else mRe |= lane; }
+        }
+        const int rpg = (CH + 3) >> 2;
+        const int r0 = grp * rpg, r1 = min(r0 + rpg, CH);
+        if (r0 < r1) {
+            // window rows in bordered coordinates: up = r, mid = r + 1, dn = r + 2
+            unsigned upAo, upBe, upBo, upCe, midAo, midBe, midBo, midCe;
+            {
+                const unsigned a = sm.sc[r0][q], b = sm.sc[r0][q + 1], c = sm.sc[r0][q + 2];
+                upAo = odd_lanes(a); upBe = even_lanes(b); upBo = odd_lanes(b); upCe = even_lanes(c);
+                const unsigned a2 = sm.sc[r0 + 1][q], b2 = sm.sc[r0 + 1][q + 1], c2 = sm.sc[r0 + 1][q + 2];
+                midAo = odd_lanes(a2); midBe = even_lanes(b2); midBo = odd_lanes(b2); midCe = even_lanes(c2);
             }
+            for (int r = r0; r < r1; ++r) {
+                const unsigned a = sm.sc[r + 2][q], b = sm.sc[r + 2][q + 1], c = sm.sc[r + 2][q + 2];
+                const unsigned dnAo = odd_lanes(a), dnBe = even_lanes(b), dnBo = odd_lanes(b), dnCe = even_lanes(c);
+                // vertical maxima of the neighbour columns (centre column without the centre row)
+                const unsigned vAo = vmax3(upAo, midAo, dnAo), vBe = vmax3(upBe, midBe, dnBe);
+                const unsigned vBo = vmax3(upBo, midBo, dnBo), vCe = vmax3(upCe, midCe, dnCe);
+                const unsigned vCenE = __vmaxu2(upBe, dnBe), vCenO = __vmaxu2(upBo, dnBo);
+                // even pixels (k=0,2): left = bytes 4q-1, 4q+1 ; right = bytes 4q+1, 4q+3
+                const unsigned Le = __byte_perm(vAo, vBo, 0x5432) & mLe;
+                const unsigned Re = vBo & mRe;
+                // odd pixels (k=1,3): left = bytes 4q, 4q+2 ; right = bytes 4q+2, 4q+4
+                const unsigned Lo = vBe & mLo;
+                const unsigned Ro = __byte_perm(vBe, vCe, 0x5432) & mRo;
+                const unsigned nbE = vmax3(Le, Re, vCenE), nbO = vmax3(Lo, Ro, vCenO);
+                // keep u where u > nb: t = u - min(u, nb) is non-zero exactly there
+                const unsigned tE = midBe - __vminu2(midBe, nbE), tO = midBo - __vminu2(midBo, nbO);
+                const unsigned kE = __vminu2(tE, 0x00010001u) * 0xffu, kO = __vminu2(tO, 0x00010001u) * 0xffu;
+                const unsigned outw = (midBe & kE) | ((midBo & kO) << 8);
+                if (outw) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int u = (wv >> (8 * k)) & 0xff;
-                if (u == 0) continue;
-                const int cx = 4 * q + k;
-                const int cell = cx / wCell;
-                const bool first = (cx - cell * wCell) == 0;
-                const bool last = (cx - cell * wCell) == wCell - 1;
-                bool ok = true;
-#pragma unroll
-                for (int d = 0; d < 3; ++d) {
-                    const int lft = (int)((rows3[d] >> (8 * k)) & 0xff);
-                    const int mid = (int)((rows3[d] >> (8 * (k + 1))) & 0xff);
-                    const int rgt = (int)((rows3[d] >> (8 * (k + 2))) & 0xff);
-                    if (!first) ok = ok && (u > lft);
-                    if (d != 1) ok = ok && (u > mid);
-                    if (!last) ok = ok && (u > rgt);
+                    for (int k = 0; k < 4; ++k) {
+                        const unsigned u = (outw >> (8 * k)) & 0xffu;
+                        if (u) {
+                            const int cx = 4 * q + k;
+                            const unsigned cell = sm.cellOf[cx];
+                            const int slot = atomicAdd(&sm.nSurv, 1);
+                            if (slot < DET_MAX_SURV) sm.surv[slot] = u | ((unsigned)r << 8) | ((unsigned)cx << 16) | (cell << 24);
+                            if ((int)u >= iniU) sm.cellHasIni[cell] = 1;
+                        }
+                    }
                 }
-                if (ok) {
-                    outw |= (unsigned)u << (8 * k);
-                    if (u >= iniU) sm.cellHasIni[cell] = 1;
-                }
+                upAo = midAo; upBe = midBe; upBo = midBo; upCe = midCe;
+                midAo = dnAo; midBe = dnBe; midBo = dnBo; midCe = dnCe;
             }
         }
-        sm.img[r][q] = outw;
     }
     __syncthreads();
 
-    // ---- pass C: per-cell threshold choice, count, reserve, emit
+    // ---- pass C: per-cell threshold choice, reserve, emit
+    const int nS = min(sm.nSurv, DET_MAX_SURV);
+    if (nS == 0) return;
     int myCount = 0;
-    for (int i = tid; i < CH * QR; i += DET_THREADS) {
-        const int r = i / QR, q = i - r * QR;
-        const unsigned wv = sm.img[r][q];
-        if (!wv) continue;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int u = (wv >> (8 * k)) & 0xff;
-            if (u == 0) continue;
-            const int cell = (4 * q + k) / wCell;
-            if (u >= iniU || (!sm.cellHasIni[cell] && u >= minU)) ++myCount;
-        }
+    for (int i = tid; i < nS; i += DET_THREADS) {
+        const unsigned e = sm.surv[i];
+        const int u = e & 0xff;
+        myCount += (u >= iniU || (!sm.cellHasIni[e >> 24] && u >= minU)) ? 1 : 0;
     }
     if (myCount) atomicAdd(&sm.nEmit, myCount);
     __syncthreads();
@@ -293,23 +328,15 @@ __global__ void __launch_bounds__(DET_THREADS) k_detect(const __grid_constant__ 
     if (myCount) {
         int slot = atomicAdd(&sm.emitFill, myCount) + sm.emitBase;
         uint2* out = L.cand + (size_t)f * L.candCap;
-        for (int i = tid; i < CH * QR; i += DET_THREADS) {
-            const int r = i / QR, q = i - r * QR;
-            const unsigned wv = sm.img[r][q];
-            if (!wv) continue;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int u = (wv >> (8 * k)) & 0xff;
-                if (u == 0) continue;
-                const int cx = 4 * q + k;
-                const int cell = cx / wCell;
-                if (u >= iniU || (!sm.cellHasIni[cell] && u >= minU)) {
-                    // coordinates relative to (minBorderX, minBorderY) as in vToDistributeKeys
-                    const unsigned xrel = (unsigned)(X0 + 3 + cx - ORB_MINB);
-                    const unsigned yrel = (unsigned)(Y0 + 3 + r - ORB_MINB);
-                    if ((unsigned)slot < L.candCap) out[slot] = make_uint2(xrel | (yrel << 16), (unsigned)(u + plan.lowTh - 1));
-                    ++slot;
-                }
+        for (int i = tid; i < nS; i += DET_THREADS) {
+            const unsigned e = sm.surv[i];
+            const int u = e & 0xff;
+            if (u >= iniU || (!sm.cellHasIni[e >> 24] && u >= minU)) {
+                // coordinates relative to (minBorderX, minBorderY) as in vToDistributeKeys
+                const unsigned xrel = (unsigned)(X0 + 3 - ORB_MINB) + ((e >> 16) & 0xffu);
+                const unsigned yrel = (unsigned)(Y0 + 3 - ORB_MINB) + ((e >> 8) & 0xffu);
+                if ((unsigned)slot < L.candCap) out[slot] = make_uint2(xrel | (yrel << 16), (unsigned)(u + plan.lowTh - 1));
+                ++slot;
             }
         }
     }
@@ -363,6 +390,230 @@ struct OctShared {
     int warpSums[OCT_THREADS / 32];
 };
 
+// Path code of one candidate: root = int(x / hX) (ORBextractor.cc:248), then OCT_D floor-halving
+// splits of the root box exactly as DivideNode does (:179-218).  Returns false when the root
+// index is out of range (the reference drops such keys, :249).
+__device__ __forceinline__ bool path_code(const OrbLevel& L, int x, int y, unsigned& code) {
+    const int root = (int)__fdiv_rn((float)x, L.hX);
+    if (!(root >= 0 && root < L.nIni)) return false;
+    int ulx = (int)__fmul_rn(L.hX, (float)root);
+    int urx = (int)__fmul_rn(L.hX, (float)(root + 1));
+    int uly = 0, bly = L.H;
+    code = (unsigned)root;
+#pragma unroll
+    for (int d = 0; d < OCT_D; ++d) {
+        const int midx = ulx + ((urx - ulx) >> 1);  // extents are >= 0 here
+        const int midy = uly + ((bly - uly) >> 1);
+        const unsigned cx = x >= midx, cy = y >= midy;
+        if (cx) ulx = midx; else urx = midx;
+        if (cy) uly = midy; else bly = midy;
+        code = (code << 2) | (cy << 1) | cx;
+    }
+    return true;
+}
+
+// Candidate order (cells row-major, then row-major inside the cell) as one integer that also
+// carries the coordinates: cell index << 26 | y << 13 | x.
+__device__ __forceinline__ unsigned long long cand_order(const OrbLevel& L, unsigned x, unsigned y) {
+    const unsigned cj = (x - 3) / (unsigned)L.wCell, ci = (y - 3) / (unsigned)L.hCell;
+    return ((unsigned long long)(ci * (unsigned)L.nCols + cj) << 26) | (y << 13) | x;
+}
+
+// ------------------------------------------------------------------------------------------
+// k_octree_fast: sort-free path for the common case where the stopping depth p* is shallow
+// (nIni * 4^p* <= OCTF_MAX_NODES).  The quadtree nodes of depth t form a table indexed by
+// the t-level path prefix; one pass of shared-memory atomics fills the per-depth occupancy
+// counts of every candidate's ancestors.  Then: Count_t = non-empty entries of table t; p* as
+// in the reference's stop rule; per node of depth p* a 64-bit atomicMax picks the first
+// max-response key; each non-empty depth-p* entry maps to one final node (itself, or the
+// ancestor where it became a singleton = its birth pass); output rank = position of the final
+// node in (birth desc, alternating-direction path) order, obtained by scattering into
+// per-birth tables in transformed-index order and one block-wide prefix sum.
+// Problems it cannot take (deep p*) are flagged for the generic sort-based kernel below.
+// ------------------------------------------------------------------------------------------
+#define OCTF_THREADS 256
+#define OCTF_MAX_NODES 6144
+#define OCTF_MAX_TOTAL 8192
+#define OCTF_MAX_DEPTH 7
+
+struct OctFastSmem {
+    unsigned cnt[OCTF_MAX_TOTAL];              // occupancy counts, tables of depth 0..tmax back to back
+    unsigned long long best[OCTF_MAX_NODES];   // per depth-p* node: score << 48 | (ORDMAX - order)
+    unsigned short ordTab[OCTF_MAX_TOTAL];     // final nodes in output order: depth-p* entry + 1
+    int nonEmpty[OCTF_MAX_DEPTH + 1];
+    int warpSums[OCTF_THREADS / 32];
+    int pstar, K, nvalid;
+};
+
+__global__ void __launch_bounds__(OCTF_THREADS) k_octree_fast(const __grid_constant__ OrbPlan plan) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    OctFastSmem& sm = *reinterpret_cast<OctFastSmem*>(smem_raw);
+    const int lt = blockIdx.x, f = blockIdx.y, tid = threadIdx.x;
+    const OrbLevel& T = plan.lv[lt];
+    const OrbLevel& L = plan.lv[T.src];
+    int n = plan.candCount[f * ORB_MAX_LEVELS + T.src];
+    if (n > (int)L.candCap) n = (int)L.candCap;
+    int* needGeneric = plan.needGeneric + f * ORB_MAX_LEVELS + lt;
+    if (n == 0 || L.nIni <= 0) {
+        if (tid == 0) {
+            plan.keptCount[f * ORB_MAX_LEVELS + lt] = 0;
+            *needGeneric = 0;
+        }
+        return;
+    }
+    const uint2* cand = L.cand + (size_t)f * L.candCap;
+    unsigned* codes = reinterpret_cast<unsigned*>(T.sortScratch + (size_t)f * 2 * T.sortCap);
+    const int nIni = L.nIni;
+    // deepest table depth that fits, and table offsets off(t) = nIni * (4^t - 1) / 3
+    int tmax = 0;
+    while (tmax < OCTF_MAX_DEPTH && nIni * (1 << (2 * (tmax + 1))) <= OCTF_MAX_NODES &&
+           nIni * (((1 << (2 * (tmax + 2))) - 1) / 3) <= OCTF_MAX_TOTAL)
+        ++tmax;
+    const int total = nIni * (((1 << (2 * (tmax + 1))) - 1) / 3);
+    for (int i = tid; i < total; i += OCTF_THREADS) sm.cnt[i] = 0;
+    if (tid <= OCTF_MAX_DEPTH) sm.nonEmpty[tid] = 0;
+    __syncthreads();
+
+    // ---- pass 1: codes + ancestor occupancy counts for depths 0..tmax
+    for (int i = tid; i < n; i += OCTF_THREADS) {
+        const uint2 c = cand[i];
+        unsigned code = 0xffffffffu;
+        if (path_code(L, (int)(c.x & 0xffff), (int)(c.x >> 16), code)) {
+            int off = 0;
+            for (int t = 0; t <= tmax; ++t) {
+                atomicAdd(&sm.cnt[off + (code >> (2 * (OCT_D - t)))], 1u);
+                off += nIni << (2 * t);
+            }
+        } else {
+            code = 0xffffffffu;
+        }
+        codes[i] = code;
+    }
+    __syncthreads();
+    // ---- Count_t
+    {
+        int local[OCTF_MAX_DEPTH + 1];
+#pragma unroll
+        for (int t = 0; t <= OCTF_MAX_DEPTH; ++t) local[t] = 0;
+        int off = 0;
+        for (int t = 0; t <= tmax; ++t) {
+            const int sz = nIni << (2 * t);
+            int c = 0;
+            for (int i = tid; i < sz; i += OCTF_THREADS) c += sm.cnt[off + i] != 0;
+            local[t] = c;
+            off += sz;
+        }
+        int nv = 0;
+        for (int i = tid; i < nIni; i += OCTF_THREADS) nv += (int)sm.cnt[i];
+#pragma unroll
+        for (int t = 0; t <= OCTF_MAX_DEPTH; ++t) {
+            int v = local[t];
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if ((tid & 31) == 0 && v) atomicAdd(&sm.nonEmpty[t], v);
+        }
+        for (int o = 16; o > 0; o >>= 1) nv += __shfl_xor_sync(0xffffffffu, nv, o);
+        if (tid == 0) sm.nvalid = 0;
+        __syncthreads();
+        if ((tid & 31) == 0 && nv) atomicAdd(&sm.nvalid, nv);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int p = -1;
+        for (int t = 1; t <= tmax; ++t)
+            if (sm.nonEmpty[t] >= T.nFeat || sm.nonEmpty[t] == sm.nvalid) { p = t; break; }
+        sm.pstar = p;
+        sm.K = p >= 0 ? sm.nonEmpty[p] : 0;
+    }
+    __syncthreads();
+    const int pstar = sm.pstar;
+    if (sm.nvalid == 0) {
+        if (tid == 0) {
+            plan.keptCount[f * ORB_MAX_LEVELS + lt] = 0;
+            *needGeneric = 0;
+        }
+        return;
+    }
+    if (pstar < 0) {  // deeper than the tables: hand over to the sort-based kernel
+        if (tid == 0) *needGeneric = 1;
+        return;
+    }
+    const int nodes = nIni << (2 * pstar);
+    const int offP = nIni * (((1 << (2 * pstar)) - 1) / 3);
+    const int totalP = offP + nodes;  // tables of depth 0..p*
+    for (int i = tid; i < nodes; i += OCTF_THREADS) sm.best[i] = 0ull;
+    for (int i = tid; i < totalP; i += OCTF_THREADS) sm.ordTab[i] = 0;
+    __syncthreads();
+    // ---- pass 2: first max-response key per depth-p* node
+    const unsigned long long ORDMAX = (1ull << 44) - 1;
+    for (int i = tid; i < n; i += OCTF_THREADS) {
+        const unsigned code = codes[i];
+        if (code == 0xffffffffu) continue;
+        const uint2 c = cand[i];
+        const unsigned long long key = ((unsigned long long)c.y << 48) | (ORDMAX - cand_order(L, c.x & 0xffff, c.x >> 16));
+        atomicMax(&sm.best[code >> (2 * (OCT_D - pstar))], key);
+    }
+    __syncthreads();
+    // ---- final node of every non-empty depth-p* entry -> slot in the ordered tables
+    for (int e = tid; e < nodes; e += OCTF_THREADS) {
+        if (sm.cnt[offP + e] == 0) continue;
+        int b = pstar, off = 0;
+        for (int d = 0; d < pstar; ++d) {  // birth = first depth at which the key is alone
+            if (sm.cnt[off + (e >> (2 * (pstar - d)))] == 1) { b = d; break; }
+            off += nIni << (2 * d);
+        }
+        const unsigned pb = (unsigned)e >> (2 * (pstar - b));
+        const unsigned cb = pb & ((1u << (2 * b)) - 1u);
+        unsigned root = pb >> (2 * b);
+        if (b >= 1 && (((b - 1) & 1) == 0)) root = (unsigned)nIni - 1u - root;  // root follows c_1's direction
+        const unsigned tb = (root << (2 * b)) | (cb ^ (0x33333333u & ((1u << (2 * b)) - 1u)));
+        // groups in output order: birth p*, p*-1, ..., 0
+        int goff = 0;
+        for (int d = pstar; d > b; --d) goff += nIni << (2 * d);
+        sm.ordTab[goff + tb] = (unsigned short)(e + 1);
+    }
+    __syncthreads();
+    // ---- rank = exclusive prefix count of occupied slots
+    const int chunk = (totalP + OCTF_THREADS - 1) / OCTF_THREADS;
+    const int beg = min(tid * chunk, totalP), end = min(beg + chunk, totalP);
+    int mine = 0;
+    for (int i = beg; i < end; ++i) mine += sm.ordTab[i] != 0;
+    int incl = mine;
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((tid & 31) >= o) incl += v;
+    }
+    if ((tid & 31) == 31) sm.warpSums[tid >> 5] = incl;
+    __syncthreads();
+    if (tid < 32) {
+        int v = tid < OCTF_THREADS / 32 ? sm.warpSums[tid] : 0;
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t2 = __shfl_up_sync(0xffffffffu, v, o);
+            if (tid >= o) v += t2;
+        }
+        if (tid < OCTF_THREADS / 32) sm.warpSums[tid] = v;
+    }
+    __syncthreads();
+    int rank = incl - mine + ((tid >> 5) ? sm.warpSums[(tid >> 5) - 1] : 0);
+    uint2* kept = T.kept + (size_t)f * T.kmax;
+    for (int i = beg; i < end; ++i) {
+        const int e1 = sm.ordTab[i];
+        if (!e1) continue;
+        const unsigned long long key = sm.best[e1 - 1];
+        const unsigned long long ord = ORDMAX - (key & ORDMAX);
+        const unsigned x = (unsigned)(ord & 0x1fff) + ORB_MINB, y = (unsigned)((ord >> 13) & 0x1fff) + ORB_MINB;
+        if (rank < T.kmax) kept[rank] = make_uint2(x | (y << 16), (unsigned)(key >> 48));
+        ++rank;
+    }
+    if (tid == 0) {
+        plan.keptCount[f * ORB_MAX_LEVELS + lt] = sm.K;
+        *needGeneric = 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_octree (generic): sort-based closed form, any depth up to OCT_D.  Runs only for the
+// (level, frame) problems k_octree_fast flagged.
+// ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(OCT_THREADS) k_octree(const __grid_constant__ OrbPlan plan) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned long long* smA = reinterpret_cast<unsigned long long*>(smem_raw);
@@ -370,26 +621,19 @@ __global__ void __launch_bounds__(OCT_THREADS) k_octree(const __grid_constant__ 
     OctShared& sh = *reinterpret_cast<OctShared*>(smB + OCT_SMEM_B);
 
     const int f = blockIdx.y;
-    // blockIdx.x enumerates source levels
-    int l = -1;
-    {
-        int c = 0;
-        for (int i = 0; i < plan.nlevels; ++i)
-            if (plan.lv[i].src == i) {
-                if (c == (int)blockIdx.x) { l = i; break; }
-                ++c;
-            }
-    }
-    if (l < 0) return;
+    const int lt = blockIdx.x;
+    if (!plan.needGeneric[f * ORB_MAX_LEVELS + lt]) return;
+    const int l = plan.lv[lt].src;
     const OrbLevel& L = plan.lv[l];
     const int tid = threadIdx.x;
     int n = plan.candCount[f * ORB_MAX_LEVELS + l];
     if (n > (int)L.candCap) n = (int)L.candCap;
     const uint2* cand = L.cand + (size_t)f * L.candCap;
+    unsigned long long* scratch = plan.lv[lt].sortScratch + (size_t)f * 2 * plan.lv[lt].sortCap;
 
     unsigned npad = 2;
     while (npad < (unsigned)n) npad <<= 1;
-    unsigned long long* A = npad <= OCT_SMEM_A ? smA : L.sortScratch + (size_t)f * 2 * L.sortCap;
+    unsigned long long* A = npad <= OCT_SMEM_A ? smA : scratch;
 
     // ---- path codes
     if (tid < OCT_D + 2) sh.hist[tid] = 0;
@@ -400,23 +644,8 @@ __global__ void __launch_bounds__(OCT_THREADS) k_octree(const __grid_constant__ 
         unsigned long long key = ~0ull;
         if (i < (unsigned)n) {
             const uint2 c = cand[i];
-            const int x = (int)(c.x & 0xffff), y = (int)(c.x >> 16);
-            // root: int(kp.pt.x / hX) (ORBextractor.cc:248)
-            const int root = (int)__fdiv_rn((float)x, L.hX);
-            if (root >= 0 && root < L.nIni) {
-                int ulx = (int)__fmul_rn(L.hX, (float)root);
-                int urx = (int)__fmul_rn(L.hX, (float)(root + 1));
-                int uly = 0, bly = L.H;
-                unsigned code = (unsigned)root;
-#pragma unroll
-                for (int d = 0; d < OCT_D; ++d) {
-                    const int midx = ulx + ((urx - ulx) >> 1);  // extents are >= 0 here
-                    const int midy = uly + ((bly - uly) >> 1);
-                    const unsigned cx = x >= midx, cy = y >= midy;
-                    if (cx) ulx = midx; else urx = midx;
-                    if (cy) uly = midy; else bly = midy;
-                    code = (code << 2) | (cy << 1) | cx;
-                }
+            unsigned code;
+            if (path_code(L, (int)(c.x & 0xffff), (int)(c.x >> 16), code)) {
                 key = ((unsigned long long)code << 32) | i;
                 ++myValid;
             }
@@ -448,14 +677,12 @@ __global__ void __launch_bounds__(OCT_THREADS) k_octree(const __grid_constant__ 
     }
     __syncthreads();
 
-    // ---- every level that shares these candidates (level 1 == level 0)
-    for (int lt = l; lt < plan.nlevels; ++lt) {
-        if (plan.lv[lt].src != l) continue;
+    {
         const OrbLevel& T = plan.lv[lt];
         uint2* kept = T.kept + (size_t)f * T.kmax;
         if (n == 0) {
             if (tid == 0) plan.keptCount[f * ORB_MAX_LEVELS + lt] = 0;
-            continue;
+            return;
         }
         if (tid == 0) {
             int cnt = 1, p = -1;
@@ -477,7 +704,7 @@ __global__ void __launch_bounds__(OCT_THREADS) k_octree(const __grid_constant__ 
         const int pstar = sh.pstar, K = sh.K;
         unsigned kpad = 2;
         while (kpad < (unsigned)K) kpad <<= 1;
-        unsigned long long* B = kpad <= OCT_SMEM_B ? smB : L.sortScratch + (size_t)f * 2 * L.sortCap + L.sortCap;
+        unsigned long long* B = kpad <= OCT_SMEM_B ? smB : scratch + plan.lv[lt].sortCap;
 
         // segment ids: block-wide exclusive scan of head flags over contiguous chunks
         const int chunk = (n + OCT_THREADS - 1) / OCT_THREADS;
@@ -529,11 +756,7 @@ __global__ void __launch_bounds__(OCT_THREADS) k_octree(const __grid_constant__ 
                     haveOrd = false;
                 } else if (c.y == bestScore) {
                     // candidate order: cells row-major, then (y, x) inside the cell
-                    auto ordOf = [&](uint2 v) -> unsigned long long {
-                        const unsigned x = v.x & 0xffff, y = v.x >> 16;
-                        const unsigned cj2 = (x - 3) / (unsigned)L.wCell, ci2 = (y - 3) / (unsigned)L.hCell;
-                        return ((unsigned long long)(ci2 * (unsigned)L.nCols + cj2) << 32) | (y << 16) | x;
-                    };
+                    auto ordOf = [&](uint2 v) -> unsigned long long { return cand_order(L, v.x & 0xffff, v.x >> 16); };
                     if (!haveOrd) { bestOrd = ordOf(bc); haveOrd = true; }
                     const unsigned long long o2 = ordOf(c);
                     if (o2 < bestOrd) { bestOrd = o2; bestIdx = idx; bc = c; }
@@ -580,10 +803,15 @@ __global__ void __launch_bounds__(OCT_THREADS) k_octree(const __grid_constant__ 
 // ------------------------------------------------------------------------------------------
 // k_blur: cv::GaussianBlur 7x7 sigma 2, BORDER_REFLECT_101, 8UC1:
 // out = (sum_j sum_i w_j w_i p + 32768) >> 16, w = [18,34,48,56,48,34,18].
-// Tile of 128 x 32 outputs; horizontal pass into 16-bit smem, vertical pass out.
+// Tile of 256 x 64 outputs staged in shared memory (with the 3-px reflected halo).  Each
+// thread owns a 4-pixel column group and walks 16 output rows: the horizontal pass is two
+// IDP.4A per pixel on byte windows cut from three aligned words, the vertical pass runs on a
+// 7-row register window.  Exact integers throughout, one 32-bit store per 4 pixels.
 // ------------------------------------------------------------------------------------------
-#define BLUR_TW 128
-#define BLUR_TH 32
+#define BLUR_TW 256
+#define BLUR_TH 64
+#define BLUR_RPT 16                    // output rows per thread
+#define BLUR_SW ((BLUR_TW + 16) / 4)   // smem words per row (4-byte left pad + tile + right halo)
 
 __device__ __forceinline__ int reflect101(int p, int n) {
     if (n == 1) return 0;
@@ -592,8 +820,7 @@ __device__ __forceinline__ int reflect101(int p, int n) {
 }
 
 __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ OrbPlan plan) {
-    __shared__ uint8_t tile[BLUR_TH + 6][BLUR_TW + 8];
-    __shared__ unsigned short hsum[BLUR_TH + 6][BLUR_TW];
+    __shared__ unsigned tile[BLUR_TH + 6][BLUR_SW];
     const int f = blockIdx.y;
     int t = blockIdx.x, l = 0;
     int tilesX = 0;
@@ -610,27 +837,66 @@ __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ OrbPlan pl
     const int ty = t / tilesX, tx = t - ty * tilesX;
     const int x0 = tx * BLUR_TW, y0 = ty * BLUR_TH;
     const uint8_t* src = L.img + (size_t)f * L.plane;
-    const int tid = threadIdx.x;
-    for (int i = tid; i < (BLUR_TH + 6) * (BLUR_TW + 6); i += 256) {
-        const int r = i / (BLUR_TW + 6), c = i - r * (BLUR_TW + 6);
-        const int yy = reflect101(y0 + r - 3, L.rows), xx = reflect101(x0 + c - 3, L.cols);
-        tile[r][c] = __ldg(src + (size_t)yy * L.pitch + xx);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int rowsHere = min(BLUR_TH, L.rows - y0) + 6;
+    // smem byte column c of tile row r  <->  pixel (reflect(y0 - 3 + r), reflect(x0 - 4 + c))
+    for (int r = warp; r < rowsHere; r += 8) {
+        const int yy = reflect101(y0 - 3 + r, L.rows);
+        const uint8_t* row = src + (size_t)yy * L.pitch;
+        for (int k = lane; k < BLUR_SW - 1; k += 32) {
+            const int x = x0 - 4 + 4 * k;
+            unsigned w;
+            if (x >= 0 && x + 3 < L.cols) {
+                w = __ldg(reinterpret_cast<const unsigned*>(row + x));
+            } else if (x - 3 >= L.cols + 3 || x + 3 < -3) {
+                w = 0;  // beyond the halo: never read
+            } else {
+                w = 0;
+#pragma unroll
+                for (int b = 0; b < 4; ++b) w |= (unsigned)__ldg(row + reflect101(x + b, L.cols)) << (8 * b);
+            }
+            tile[r][k] = w;
+        }
     }
     __syncthreads();
-    for (int i = tid; i < (BLUR_TH + 6) * BLUR_TW; i += 256) {
-        const int r = i / BLUR_TW, c = i - r * BLUR_TW;
-        const uint8_t* p = &tile[r][c];
-        hsum[r][c] = (unsigned short)(18 * (p[0] + p[6]) + 34 * (p[1] + p[5]) + 48 * (p[2] + p[4]) + 56 * p[3]);
-    }
-    __syncthreads();
+    const int q = tid & 63, g = tid >> 6;
+    const int xq = x0 + 4 * q;
+    if (xq >= L.cols) return;
+    const int rbase = g * BLUR_RPT;  // first output row of this thread inside the tile
+    if (y0 + rbase >= L.rows) return;
     uint8_t* dst = L.blur + (size_t)f * L.plane;
-    for (int i = tid; i < BLUR_TH * BLUR_TW; i += 256) {
-        const int r = i / BLUR_TW, c = i - r * BLUR_TW;
-        const int y = y0 + r, x = x0 + c;
-        if (y < L.rows && x < L.cols) {
-            const int acc = 18 * (hsum[r][c] + hsum[r + 6][c]) + 34 * (hsum[r + 1][c] + hsum[r + 5][c]) +
-                            48 * (hsum[r + 2][c] + hsum[r + 4][c]) + 56 * hsum[r + 3][c];
-            dst[(size_t)y * L.pitch + x] = (uint8_t)((acc + 32768) >> 16);
+    const unsigned WLO = 18u | (34u << 8) | (48u << 16) | (56u << 24);
+    const unsigned WHI = 48u | (34u << 8) | (18u << 16);
+    int H[7][4];
+#pragma unroll
+    for (int rr = 0; rr < BLUR_RPT + 6; ++rr) {
+        const int r = rbase + rr;
+        int h0 = 0, h1 = 0, h2 = 0, h3 = 0;
+        if (r < rowsHere) {
+            // words q, q+1, q+2 = smem bytes 4q .. 4q+11 = b0..b11; output pixel k reads b(1+k)..b(7+k)
+            const unsigned w0 = tile[r][q], w1 = tile[r][q + 1], w2 = tile[r][q + 2];
+            h0 = __dp4a(__byte_perm(w0, w1, 0x4321), WLO, __dp4a(__byte_perm(w1, w2, 0x4321), WHI, 0u));
+            h1 = __dp4a(__byte_perm(w0, w1, 0x5432), WLO, __dp4a(__byte_perm(w1, w2, 0x5432), WHI, 0u));
+            h2 = __dp4a(__byte_perm(w0, w1, 0x6543), WLO, __dp4a(__byte_perm(w1, w2, 0x6543), WHI, 0u));
+            h3 = __dp4a(w1, WLO, __dp4a(w2, WHI, 0u));
+        }
+        H[rr % 7][0] = h0;
+        H[rr % 7][1] = h1;
+        H[rr % 7][2] = h2;
+        H[rr % 7][3] = h3;
+        if (rr >= 6) {
+            const int y = y0 + rbase + rr - 6;
+            if (y < L.rows) {
+                unsigned outw = 0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    // rows rr-6 .. rr of the window, taps 18 34 48 56 48 34 18
+                    const int acc = 18 * (H[(rr - 6) % 7][k] + H[rr % 7][k]) + 34 * (H[(rr - 5) % 7][k] + H[(rr - 1) % 7][k]) +
+                                    48 * (H[(rr - 4) % 7][k] + H[(rr - 2) % 7][k]) + 56 * H[(rr - 3) % 7][k];
+                    outw |= (unsigned)((acc + 32768) >> 16) << (8 * k);
+                }
+                *reinterpret_cast<unsigned*>(dst + (size_t)y * L.pitch + xq) = outw;
+            }
         }
     }
 }
@@ -643,7 +909,6 @@ __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ OrbPlan pl
 __constant__ int8_t c_pairs[728] = {
 #include "brief_pairs_182.inc"
 };
-__constant__ int c_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
 
 __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
     // cv::fastAtan2, evaluated step by step in binary32, no FMA
@@ -667,10 +932,15 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
     return a;
 }
 
+// IC_Angle weight table (built on the host by orbk_build_ic_table, plan.icTab):
+// entry [a][v + 15][k] for patch alignment a = (x - 15) & 3, row v, aligned word k (9 words
+// cover u = -15 - a .. 20 - a): .x = four signed bytes u (0 outside the disc |u| <= umax[|v|]),
+// .y = four 0/1 bytes (inside the disc).  m10 += dp4a(pixels, .x); m01 += v * dp4a(pixels, .y).
 __global__ void __launch_bounds__(256) k_describe(const __grid_constant__ OrbPlan plan, orb_keypoint_dev* __restrict__ kps,
                                                   uint8_t* __restrict__ desc, int cap, int* __restrict__ counts) {
-    __shared__ int8_t s_pairs[728];
-    for (int i = threadIdx.x; i < 728; i += 256) s_pairs[i] = c_pairs[i];
+    __shared__ float4 s_pairs[182];
+    for (int i = threadIdx.x; i < 182; i += 256)
+        s_pairs[i] = make_float4((float)c_pairs[4 * i], (float)c_pairs[4 * i + 1], (float)c_pairs[4 * i + 2], (float)c_pairs[4 * i + 3]);
     const int f = blockIdx.y;
     const int* kc = plan.keptCount + f * ORB_MAX_LEVELS;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -681,42 +951,49 @@ __global__ void __launch_bounds__(256) k_describe(const __grid_constant__ OrbPla
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = blockIdx.x * 8 + warp;  // index in the concatenated [level][kmax] space
-    int l = 0;
-    for (; l < plan.nlevels; ++l)
-        if (g < plan.lv[l].keptBase + plan.lv[l].kmax) break;
-    if (l >= plan.nlevels) return;
-    const OrbLevel& L = plan.lv[l];
-    const int r = g - L.keptBase;
-    if (r >= kc[l]) return;
-    int off = 0;
-    for (int i = 0; i < l; ++i) off += kc[i];
+    // level of g: lane i tests level i
+    int myBase = 0x7fffffff, myK = 0, myMax = 0;
+    if (lane < plan.nlevels) {
+        myBase = plan.lv[lane].keptBase;
+        myMax = plan.lv[lane].kmax;
+        myK = kc[lane];
+    }
+    const bool mine = lane < plan.nlevels && g >= myBase && g < myBase + myMax;
+    const unsigned hit = __ballot_sync(0xffffffffu, mine);
+    if (!hit) return;
+    const int l = __ffs(hit) - 1;
+    const int r = g - __shfl_sync(0xffffffffu, myBase, l);
+    if (r >= __shfl_sync(0xffffffffu, myK, l)) return;
+    int off = lane < l ? myK : 0;  // keypoints of the levels before l
+    for (int sft = 16; sft > 0; sft >>= 1) off += __shfl_xor_sync(0xffffffffu, off, sft);
     const int o = off + r;
     if (o >= cap) return;
+    const OrbLevel& L = plan.lv[l];
+    const OrbLevel& S = plan.lv[L.src];
 
     const uint2 k = L.kept[(size_t)f * L.kmax + r];
     const int x = (int)(k.x & 0xffff), y = (int)(k.x >> 16);
-    const OrbLevel& S = plan.lv[L.src];
 
     // ---- IC_Angle: m10 = sum u*I, m01 = sum v*I over the radius-15 disc (exact int32)
-    const uint8_t* img = S.img + (size_t)f * S.plane + (size_t)y * S.pitch + x;
     int m10 = 0, m01 = 0;
     {
-        const int u = lane - 15;  // lanes 0..30
-        if (lane < 31) {
-            const int au = u < 0 ? -u : u;
+        const int a = (x - 15) & 3;
+        const uint8_t* base = S.img + (size_t)f * S.plane + (size_t)(y - 15) * S.pitch + (x - 15 - a);
+        const int2* tab = plan.icTab + a * (31 * 9);
 #pragma unroll
-            for (int v = -15; v <= 15; ++v) {
-                const int av = v < 0 ? -v : v;
-                if (au <= c_umax[av]) {
-                    const int val = __ldg(img + v * S.pitch + u);
-                    m10 += u * val;
-                    m01 += v * val;
-                }
+        for (int it = 0; it < 9; ++it) {
+            const int item = it * 32 + lane;
+            if (item < 31 * 9) {
+                const int vr = item / 9, kk = item - vr * 9;
+                const unsigned w = __ldg(reinterpret_cast<const unsigned*>(base + vr * S.pitch + 4 * kk));
+                const int2 t = __ldg(tab + item);
+                m10 = dp4a_us(w, t.x, m10);
+                m01 += (vr - 15) * (int)__dp4a(w, (unsigned)t.y, 0u);
             }
         }
-        for (int s = 16; s > 0; s >>= 1) {
-            m10 += __shfl_xor_sync(0xffffffffu, m10, s);
-            m01 += __shfl_xor_sync(0xffffffffu, m01, s);
+        for (int sft = 16; sft > 0; sft >>= 1) {
+            m10 += __shfl_xor_sync(0xffffffffu, m10, sft);
+            m01 += __shfl_xor_sync(0xffffffffu, m01, sft);
         }
     }
     const float angle = fast_atan2_deg((float)m01, (float)m10);
@@ -724,22 +1001,24 @@ __global__ void __launch_bounds__(256) k_describe(const __grid_constant__ OrbPla
     // ---- rBRIEF on the blurred level: 182 live pairs (bits 182..255 are 0)
     const float factorPI = (float)(3.141592653589793238462643383279502884 / 180.f);
     const float rad = __fmul_rn(angle, factorPI);
-    const float a = (float)cos((double)rad), b = (float)sin((double)rad);
+    double sd, cd;
+    sincos((double)rad, &sd, &cd);
+    const float a = (float)cd, b = (float)sd;
     const uint8_t* bl = S.blur + (size_t)f * S.plane + (size_t)y * S.pitch + x;
+    const int pitch = S.pitch;
     unsigned words[8];
 #pragma unroll
     for (int wq = 0; wq < 6; ++wq) {
         const int p = wq * 32 + lane;
         bool bit = false;
         if (p < 182) {
-            const float x0 = (float)s_pairs[4 * p], y0 = (float)s_pairs[4 * p + 1];
-            const float x1 = (float)s_pairs[4 * p + 2], y1 = (float)s_pairs[4 * p + 3];
-            const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
-            const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
-            const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
-            const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
-            const int t0 = __ldg(bl + r0 * S.pitch + c0);
-            const int t1 = __ldg(bl + r1 * S.pitch + c1);
+            const float4 pr = s_pairs[p];
+            const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(pr.x, b), __fmul_rn(pr.y, a)));
+            const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(pr.x, a), __fmul_rn(pr.y, b)));
+            const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(pr.z, b), __fmul_rn(pr.w, a)));
+            const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(pr.z, a), __fmul_rn(pr.w, b)));
+            const int t0 = __ldg(bl + (r0 * pitch + c0));
+            const int t1 = __ldg(bl + (r1 * pitch + c1));
             bit = t0 < t1;
         }
         words[wq] = __ballot_sync(0xffffffffu, bit);
@@ -772,6 +1051,26 @@ __global__ void __launch_bounds__(256) k_describe(const __grid_constant__ OrbPla
     }
 }
 
+// Host-side construction of the IC_Angle weight table (4 x 31 x 9 int2).
+void orbk_build_ic_table(int2* out) {
+    static const int umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
+    for (int a = 0; a < 4; ++a)
+        for (int vr = 0; vr < 31; ++vr)
+            for (int k = 0; k < 9; ++k) {
+                const int v = vr - 15, av = v < 0 ? -v : v;
+                unsigned wu = 0, wm = 0;
+                for (int b = 0; b < 4; ++b) {
+                    const int u = 4 * k + b - a - 15;
+                    const int au = u < 0 ? -u : u;
+                    if (au <= umax[av]) {
+                        wu |= (unsigned)(u & 0xff) << (8 * b);
+                        wm |= 1u << (8 * b);
+                    }
+                }
+                out[(a * 31 + vr) * 9 + k] = make_int2((int)wu, (int)wm);
+            }
+}
+
 // ------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------
@@ -781,9 +1080,12 @@ void orbk_count_launch(int n) { g_launches += n; }
 
 static const size_t kDetectSmem = sizeof(DetectSmem);
 static const size_t kOctreeSmem = (size_t)(OCT_SMEM_A + OCT_SMEM_B) * 8 + sizeof(OctShared);
+static const size_t kOctFastSmem = sizeof(OctFastSmem);
 
 cudaError_t orbk_init_device() {
     cudaError_t e = cudaFuncSetAttribute(k_detect, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDetectSmem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_octree_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kOctFastSmem);
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kOctreeSmem);
 }
@@ -818,8 +1120,9 @@ cudaError_t orbk_run_extract(const OrbPlan& plan, int nframes, orb_keypoint_dev*
         ++g_launches;
     }
     if (ev) cudaEventRecord(ev[2], st);
-    k_octree<<<dim3(nsrc, nframes), OCT_THREADS, kOctreeSmem, st>>>(plan);
-    ++g_launches;
+    k_octree_fast<<<dim3(plan.nlevels, nframes), OCTF_THREADS, kOctFastSmem, st>>>(plan);
+    k_octree<<<dim3(plan.nlevels, nframes), OCT_THREADS, kOctreeSmem, st>>>(plan);
+    g_launches += 2;
     if (ev) cudaEventRecord(ev[3], st);
     k_blur<<<dim3(blurTiles, nframes), 256, 0, st>>>(plan);
     ++g_launches;

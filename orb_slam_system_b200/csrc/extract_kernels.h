@@ -19,5 +19,6 @@ cudaError_t orbk_init_device();
 #define ORB_STAGES 5
 cudaError_t orbk_run_extract(const OrbPlan& plan, int nframes, orb_keypoint_dev* d_kps, uint8_t* d_desc, int cap,
                              int* d_counts, cudaStream_t st, cudaEvent_t* ev = nullptr);
+void orbk_build_ic_table(int2* out /* 4*31*9 */);
 unsigned long long orbk_launch_count();
 void orbk_count_launch(int n);

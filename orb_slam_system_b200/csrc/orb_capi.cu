@@ -262,7 +262,11 @@ static int build_plan(orb_extractor* h, int rows, int cols) {
         L.keptBase = keptBase;
         keptBase += L.kmax;
         CUDA_TRY(dev_alloc(h, &L.kept, (size_t)B * L.kmax));
-        if (L.src != l) continue;
+        if (L.src != l) {  // an alias runs its own octree problem: own scratch, sized like its source's
+            L.sortCap = P.lv[L.src].sortCap;
+            CUDA_TRY(dev_alloc(h, &L.sortScratch, (size_t)B * 2 * L.sortCap));
+            continue;
+        }
         L.tileBase = tileBase;
         tileBase += L.nTiles;
         CUDA_TRY(dev_alloc(h, &L.img, (size_t)B * L.plane + 256));
@@ -305,6 +309,16 @@ static int build_plan(orb_extractor* h, int rows, int cols) {
     CUDA_TRY(dev_alloc(h, &P.candCount, (size_t)B * ORB_MAX_LEVELS));
     CUDA_TRY(dev_alloc(h, &P.keptCount, (size_t)B * ORB_MAX_LEVELS));
     CUDA_TRY(dev_alloc(h, &P.status, (size_t)B));
+    {
+        std::vector<int2> ic(4 * 31 * 9);
+        orbk_build_ic_table(ic.data());
+        int2* d_ic;
+        CUDA_TRY(dev_alloc(h, &d_ic, ic.size()));
+        CUDA_TRY(cudaMemcpy(d_ic, ic.data(), ic.size() * sizeof(int2), cudaMemcpyHostToDevice));
+        P.icTab = d_ic;
+    }
+    CUDA_TRY(dev_alloc(h, &P.needGeneric, (size_t)B * ORB_MAX_LEVELS));
+    CUDA_TRY(cudaMemset(P.needGeneric, 0, sizeof(int) * B * ORB_MAX_LEVELS));
     CUDA_TRY(cudaMemset(P.keptCount, 0, sizeof(int) * B * ORB_MAX_LEVELS));
     CUDA_TRY(cudaMemset(P.candCount, 0, sizeof(int) * B * ORB_MAX_LEVELS));
     h->level0 = P.lv[0].img;

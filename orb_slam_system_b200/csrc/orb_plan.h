@@ -4,6 +4,7 @@
 // :497-515 (level sizes) and :288-357 (cell grid), bit for bit.
 #pragma once
 #include <stdint.h>
+#include <vector_types.h>
 
 #define ORB_MAX_LEVELS 16
 #define ORB_EDGE 19          // EDGE_THRESHOLD (ORBextractor.cc:17)
@@ -62,5 +63,7 @@ struct OrbPlan {
     int* candCount;          // [batch][ORB_MAX_LEVELS]
     int* keptCount;          // [batch][ORB_MAX_LEVELS]
     int* status;             // [batch] octree status flags (non-zero: unseparable keys)
+    int* needGeneric;        // [batch][ORB_MAX_LEVELS] problems the table-based octree handed over
+    const int2* icTab;       // [4][31][9] IC_Angle dp4a weights (k_describe)
     OrbLevel lv[ORB_MAX_LEVELS];
 };
