@@ -119,7 +119,9 @@ int orb_extractor_level_stats(orb_extractor* h, int frame, int32_t* candidates, 
 /* Per-stage device timing (CUDA events on the handle's stream around each kernel stage:
  * 0 pyramid, 1 detect, 2 octree, 3 blur, 4 describe).  set_profiling(1) clears the records and
  * starts recording every following extract call; stage_times synchronises and returns the
- * summed milliseconds per stage and the number of calls recorded. */
+ * summed milliseconds per stage and the number of calls recorded.  While profiling is on the
+ * stages run back to back on one stream (each duration is the kernel's own); with profiling
+ * off the blur runs on a second stream concurrently with detect + octree. */
 #define ORB_NUM_STAGES 5
 int orb_extractor_set_profiling(orb_extractor* h, int on);
 int orb_extractor_stage_times(orb_extractor* h, double* ms_sum, int* ncalls);

@@ -79,11 +79,16 @@ __global__ void __launch_bounds__(256) k_resize(const uint8_t* __restrict__ src,
 struct DetectSmem {
     union {
         unsigned img[DET_TILE_H][DET_SP / 4];  // image tile (passes stage + A)
-        unsigned surv[DET_MAX_SURV];           // survivor list (passes B + C): u | r<<8 | cx<<16 | cell<<24
+        unsigned F[DET_TILE_H][DET_SP / 4];    // NMS survivors, 4 candidate columns per word (pass B)
     };
-    unsigned sc[DET_TILE_H][DET_SP / 4];       // score tile with a one-word / one-row zero border
+    union {
+        unsigned sc[DET_TILE_H][DET_SP / 4];   // score tile with a one-word / one-row zero border
+        unsigned surv[DET_MAX_SURV];           // survivor list (pass C): u | r<<8 | cx<<16 | cell<<24
+    };
+    unsigned short wlist[DET_TILE_H * 64];     // compacted (row << 6 | word) of the non-zero F words
     unsigned char cellOf[DET_TILE_W + 8];      // candidate column -> cell index inside the tile
     int cellHasIni[16];
+    int nWords;
     int nSurv;
     int nEmit;
     int emitBase;
@@ -176,6 +181,7 @@ __global__ void __launch_bounds__(DET_THREADS) k_detect(const __grid_constant__ 
         for (int i = tid; i < CW + 4; i += DET_THREADS) sm.cellOf[i] = (unsigned char)(i / wCell);
         if (tid < 16) sm.cellHasIni[tid] = 0;
         if (tid == 0) {
+            sm.nWords = 0;
             sm.nSurv = 0;
             sm.nEmit = 0;
             sm.emitFill = 0;
@@ -248,22 +254,27 @@ __global__ void __launch_bounds__(DET_THREADS) k_detect(const __grid_constant__ 
 
     // ---- pass B: cell-local NMS on packed lanes.  Thread (q, grp) walks a strip of rows with a
     // 3-row sliding window.  For candidate col 4q+k the left / right neighbours are dropped when
-    // they belong to another cell (maskL / maskR).
+    // they belong to another cell (maskL / maskR).  Non-zero survivor words are compacted with
+    // one ballot per row step (no per-pixel branches).
     const int iniU = plan.iniTh - plan.lowTh + 1;  // u >= iniU  <=>  m > iniTh
     const int minU = plan.minTh - plan.lowTh + 1;
-    if (q < QR) {
+    {
+        const bool active = q < QR;
+        const int lane = tid & 31;
         unsigned mLe = 0, mLo = 0, mRe = 0, mRo = 0;  // 0x00ff per lane where the neighbour counts
+        if (active) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int cx = 4 * q + k;
-            const bool first = cx == 0 || sm.cellOf[cx - 1] != sm.cellOf[cx];
-            const bool last = sm.cellOf[cx + 1] != sm.cellOf[cx];
-            const unsigned lane = 0xffu << (16 * (k >> 1));
-            if (!first) { if (k & 1) mLo |= lane; else mLe |= lane; }
-            if (!last) { if (k & 1) mRo |= lane; else mRe |= lane; }
+            for (int k = 0; k < 4; ++k) {
+                const int cx = 4 * q + k;
+                const bool first = cx == 0 || sm.cellOf[cx - 1] != sm.cellOf[cx];
+                const bool last = sm.cellOf[cx + 1] != sm.cellOf[cx];
+                const unsigned ln = 0xffu << (16 * (k >> 1));
+                if (!first) { if (k & 1) mLo |= ln; else mLe |= ln; }
+                if (!last) { if (k & 1) mRo |= ln; else mRe |= ln; }
+            }
         }
         const int rpg = (CH + 3) >> 2;
-        const int r0 = grp * rpg, r1 = min(r0 + rpg, CH);
+        const int r0 = grp * rpg, r1 = min(r0 + rpg, CH);  // identical for the whole warp
         if (r0 < r1) {
             // window rows in bordered coordinates: up = r, mid = r + 1, dn = r + 2
             unsigned upAo, upBe, upBo, upCe, midAo, midBe, midBo, midCe;
@@ -290,22 +301,40 @@ __global__ void __launch_bounds__(DET_THREADS) k_detect(const __grid_constant__ 
                 // keep u where u > nb: t = u - min(u, nb) is non-zero exactly there
                 const unsigned tE = midBe - __vminu2(midBe, nbE), tO = midBo - __vminu2(midBo, nbO);
                 const unsigned kE = __vminu2(tE, 0x00010001u) * 0xffu, kO = __vminu2(tO, 0x00010001u) * 0xffu;
-                const unsigned outw = (midBe & kE) | ((midBo & kO) << 8);
-                if (outw) {
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const unsigned u = (outw >> (8 * k)) & 0xffu;
-                        if (u) {
-                            const int cx = 4 * q + k;
-                            const unsigned cell = sm.cellOf[cx];
-                            const int slot = atomicAdd(&sm.nSurv, 1);
-                            if (slot < DET_MAX_SURV) sm.surv[slot] = u | ((unsigned)r << 8) | ((unsigned)cx << 16) | (cell << 24);
-                            if ((int)u >= iniU) sm.cellHasIni[cell] = 1;
-                        }
+                const unsigned outw = active ? ((midBe & kE) | ((midBo & kO) << 8)) : 0u;
+                const unsigned nz = __ballot_sync(0xffffffffu, outw != 0u);
+                if (nz) {  // warp-uniform
+                    int base = 0;
+                    if (lane == 0) base = atomicAdd(&sm.nWords, __popc(nz));
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (outw) {
+                        sm.F[r][q] = outw;
+                        sm.wlist[base + __popc(nz & ((1u << lane) - 1u))] = (unsigned short)((r << 6) | q);
                     }
                 }
                 upAo = midAo; upBe = midBe; upBo = midBo; upCe = midCe;
                 midAo = dnAo; midBe = dnBe; midBo = dnBo; midCe = dnCe;
+            }
+        }
+    }
+    __syncthreads();
+    // ---- survivors out of the compacted words; per-cell "non-empty at iniTh" flags
+    {
+        const int nW = sm.nWords;
+        if (nW == 0) return;
+        for (int i = tid; i < nW; i += DET_THREADS) {
+            const int idx = sm.wlist[i];
+            const int r = idx >> 6, qq = idx & 63;
+            unsigned w = sm.F[r][qq];
+            while (w) {  // at most two survivors per word (never 8-adjacent)
+                const int k = (__ffs(w) - 1) >> 3;
+                const unsigned u = (w >> (8 * k)) & 0xffu;
+                w &= ~(0xffu << (8 * k));
+                const int cx = 4 * qq + k;
+                const unsigned cell = sm.cellOf[cx];
+                const int slot = atomicAdd(&sm.nSurv, 1);
+                if (slot < DET_MAX_SURV) sm.surv[slot] = u | ((unsigned)r << 8) | ((unsigned)cx << 16) | (cell << 24);
+                if ((int)u >= iniU) sm.cellHasIni[cell] = 1;
             }
         }
     }
@@ -811,7 +840,7 @@ __global__ void __launch_bounds__(OCT_THREADS) k_octree(const __grid_constant__ 
 #define BLUR_TW 256
 #define BLUR_TH 64
 #define BLUR_RPT 16                    // output rows per thread
-#define BLUR_SW ((BLUR_TW + 16) / 4)   // smem words per row (4-byte left pad + tile + right halo)
+#define BLUR_SW ((BLUR_TW + 32) / 4)   // smem words per row: 16-byte left pad + tile + 16-byte right halo
 
 __device__ __forceinline__ int reflect101(int p, int n) {
     if (n == 1) return 0;
@@ -820,7 +849,7 @@ __device__ __forceinline__ int reflect101(int p, int n) {
 }
 
 __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ OrbPlan plan) {
-    __shared__ unsigned tile[BLUR_TH + 6][BLUR_SW];
+    __shared__ __align__(16) unsigned tile[BLUR_TH + 6][BLUR_SW];
     const int f = blockIdx.y;
     int t = blockIdx.x, l = 0;
     int tilesX = 0;
@@ -837,26 +866,31 @@ __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ OrbPlan pl
     const int ty = t / tilesX, tx = t - ty * tilesX;
     const int x0 = tx * BLUR_TW, y0 = ty * BLUR_TH;
     const uint8_t* src = L.img + (size_t)f * L.plane;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x;
     const int rowsHere = min(BLUR_TH, L.rows - y0) + 6;
-    // smem byte column c of tile row r  <->  pixel (reflect(y0 - 3 + r), reflect(x0 - 4 + c))
-    for (int r = warp; r < rowsHere; r += 8) {
+    // smem byte column c of tile row r  <->  pixel (reflect(y0 - 3 + r), reflect(x0 - 16 + c));
+    // staged as 16-byte vectors (18 per row) when the level rows are 16-byte aligned
+    const bool vec_ok = ((L.pitch & 15) == 0) && ((((size_t)src) & 15) == 0);
+    for (int i = tid; i < rowsHere * (BLUR_SW / 4); i += 256) {
+        const int r = i / (BLUR_SW / 4), j = i - r * (BLUR_SW / 4);
         const int yy = reflect101(y0 - 3 + r, L.rows);
         const uint8_t* row = src + (size_t)yy * L.pitch;
-        for (int k = lane; k < BLUR_SW - 1; k += 32) {
-            const int x = x0 - 4 + 4 * k;
-            unsigned w;
-            if (x >= 0 && x + 3 < L.cols) {
-                w = __ldg(reinterpret_cast<const unsigned*>(row + x));
-            } else if (x - 3 >= L.cols + 3 || x + 3 < -3) {
-                w = 0;  // beyond the halo: never read
-            } else {
-                w = 0;
+        const int x = x0 - 16 + 16 * j;
+        uint4 v;
+        if (vec_ok && x >= 0 && x + 15 < L.cols) {
+            v = __ldg(reinterpret_cast<const uint4*>(row + x));
+        } else {
+            unsigned w[4] = {0u, 0u, 0u, 0u};
+            if (x + 15 >= -3 && x < L.cols + 3) {  // touches the 3-px halo or the image
 #pragma unroll
-                for (int b = 0; b < 4; ++b) w |= (unsigned)__ldg(row + reflect101(x + b, L.cols)) << (8 * b);
+                for (int b = 0; b < 16; ++b) {
+                    const int xx = x + b;
+                    if (xx >= -3 && xx < L.cols + 3) w[b >> 2] |= (unsigned)__ldg(row + reflect101(xx, L.cols)) << (8 * (b & 3));
+                }
             }
-            tile[r][k] = w;
+            v = make_uint4(w[0], w[1], w[2], w[3]);
         }
+        *reinterpret_cast<uint4*>(&tile[r][4 * j]) = v;
     }
     __syncthreads();
     const int q = tid & 63, g = tid >> 6;
@@ -873,8 +907,9 @@ __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ OrbPlan pl
         const int r = rbase + rr;
         int h0 = 0, h1 = 0, h2 = 0, h3 = 0;
         if (r < rowsHere) {
-            // words q, q+1, q+2 = smem bytes 4q .. 4q+11 = b0..b11; output pixel k reads b(1+k)..b(7+k)
-            const unsigned w0 = tile[r][q], w1 = tile[r][q + 1], w2 = tile[r][q + 2];
+            // words q+3, q+4, q+5 = smem bytes 4q+12 .. 4q+23 = b0..b11; output pixel k (smem byte
+            // 16 + 4q + k) reads b(1+k)..b(7+k)
+            const unsigned w0 = tile[r][q + 3], w1 = tile[r][q + 4], w2 = tile[r][q + 5];
             h0 = __dp4a(__byte_perm(w0, w1, 0x4321), WLO, __dp4a(__byte_perm(w1, w2, 0x4321), WHI, 0u));
             h1 = __dp4a(__byte_perm(w0, w1, 0x5432), WLO, __dp4a(__byte_perm(w1, w2, 0x5432), WHI, 0u));
             h2 = __dp4a(__byte_perm(w0, w1, 0x6543), WLO, __dp4a(__byte_perm(w1, w2, 0x6543), WHI, 0u));
@@ -906,9 +941,6 @@ __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ OrbPlan pl
 // (computeOrbDescriptor :57-73) on the blurred level, final keypoint record
 // (:345-352, :486-491).  One warp per kept keypoint.
 // ------------------------------------------------------------------------------------------
-__constant__ int8_t c_pairs[728] = {
-#include "brief_pairs_182.inc"
-};
 
 __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
     // cv::fastAtan2, evaluated step by step in binary32, no FMA
@@ -932,15 +964,18 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
     return a;
 }
 
+// cvRound (round half to even) of a float with |v| < 2^22 without the conversion unit: adding
+// 1.5 * 2^23 leaves rint(v) in the low mantissa bits under round-to-nearest-even.
+__device__ __forceinline__ int cv_round_small(float v) {
+    return __float_as_int(__fadd_rn(v, 12582912.f)) - 0x4B400000;
+}
+
 // IC_Angle weight table (built on the host by orbk_build_ic_table, plan.icTab):
 // entry [a][v + 15][k] for patch alignment a = (x - 15) & 3, row v, aligned word k (9 words
 // cover u = -15 - a .. 20 - a): .x = four signed bytes u (0 outside the disc |u| <= umax[|v|]),
 // .y = four 0/1 bytes (inside the disc).  m10 += dp4a(pixels, .x); m01 += v * dp4a(pixels, .y).
 __global__ void __launch_bounds__(256) k_describe(const __grid_constant__ OrbPlan plan, orb_keypoint_dev* __restrict__ kps,
                                                   uint8_t* __restrict__ desc, int cap, int* __restrict__ counts) {
-    __shared__ float4 s_pairs[182];
-    for (int i = threadIdx.x; i < 182; i += 256)
-        s_pairs[i] = make_float4((float)c_pairs[4 * i], (float)c_pairs[4 * i + 1], (float)c_pairs[4 * i + 2], (float)c_pairs[4 * i + 3]);
     const int f = blockIdx.y;
     const int* kc = plan.keptCount + f * ORB_MAX_LEVELS;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -948,7 +983,6 @@ __global__ void __launch_bounds__(256) k_describe(const __grid_constant__ OrbPla
         for (int i = 0; i < plan.nlevels; ++i) tot += kc[i];
         counts[f] = tot;
     }
-    __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = blockIdx.x * 8 + warp;  // index in the concatenated [level][kmax] space
     // level of g: lane i tests level i
@@ -1006,33 +1040,25 @@ __global__ void __launch_bounds__(256) k_describe(const __grid_constant__ OrbPla
     const float a = (float)cd, b = (float)sd;
     const uint8_t* bl = S.blur + (size_t)f * S.plane + (size_t)y * S.pitch + x;
     const int pitch = S.pitch;
-    unsigned words[8];
+    unsigned myWord = 0;  // lane i < 8 ends up holding descriptor word i (words 6, 7 are zero)
 #pragma unroll
     for (int wq = 0; wq < 6; ++wq) {
         const int p = wq * 32 + lane;
         bool bit = false;
         if (p < 182) {
-            const float4 pr = s_pairs[p];
-            const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(pr.x, b), __fmul_rn(pr.y, a)));
-            const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(pr.x, a), __fmul_rn(pr.y, b)));
-            const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(pr.z, b), __fmul_rn(pr.w, a)));
-            const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(pr.z, a), __fmul_rn(pr.w, b)));
+            const float4 pr = __ldg(plan.pairTab + p);
+            const int r0 = cv_round_small(__fadd_rn(__fmul_rn(pr.x, b), __fmul_rn(pr.y, a)));
+            const int c0 = cv_round_small(__fsub_rn(__fmul_rn(pr.x, a), __fmul_rn(pr.y, b)));
+            const int r1 = cv_round_small(__fadd_rn(__fmul_rn(pr.z, b), __fmul_rn(pr.w, a)));
+            const int c1 = cv_round_small(__fsub_rn(__fmul_rn(pr.z, a), __fmul_rn(pr.w, b)));
             const int t0 = __ldg(bl + (r0 * pitch + c0));
             const int t1 = __ldg(bl + (r1 * pitch + c1));
             bit = t0 < t1;
         }
-        words[wq] = __ballot_sync(0xffffffffu, bit);
+        const unsigned wbits = __ballot_sync(0xffffffffu, bit);
+        if (lane == wq) myWord = wbits;
     }
-    words[6] = 0;
-    words[7] = 0;
-
-    if (lane < 8) {
-        unsigned wsel = 0;
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-            if (lane == i) wsel = words[i];
-        reinterpret_cast<unsigned*>(desc + ((size_t)f * cap + o) * 32)[lane] = wsel;
-    }
+    if (lane < 8) reinterpret_cast<unsigned*>(desc + ((size_t)f * cap + o) * 32)[lane] = myWord;
     if (lane == 8) {
         orb_keypoint_dev kp;
         float px = (float)x, py = (float)y;
@@ -1049,6 +1075,15 @@ __global__ void __launch_bounds__(256) k_describe(const __grid_constant__ OrbPla
         kp.class_id = -1;
         kps[(size_t)f * cap + o] = kp;
     }
+}
+
+// The 182 live rBRIEF test pairs as float4 (x0, y0, x1, y1) for plan.pairTab.
+void orbk_build_pair_table(float4* out) {
+    static const int8_t pairs[728] = {
+#include "brief_pairs_182.inc"
+    };
+    for (int i = 0; i < 182; ++i)
+        out[i] = make_float4((float)pairs[4 * i], (float)pairs[4 * i + 1], (float)pairs[4 * i + 2], (float)pairs[4 * i + 3]);
 }
 
 // Host-side construction of the IC_Angle weight table (4 x 31 x 9 int2).
@@ -1091,7 +1126,10 @@ cudaError_t orbk_init_device() {
 }
 
 cudaError_t orbk_run_extract(const OrbPlan& plan, int nframes, orb_keypoint_dev* d_kps, uint8_t* d_desc, int cap,
-                             int* d_counts, cudaStream_t st, cudaEvent_t* ev) {
+                             int* d_counts, const OrbStreams& ss, cudaEvent_t* ev) {
+    // with per-stage events requested everything runs on one stream, so that every stage's
+    // event-timed duration is its own (no overlap); otherwise the blur overlaps detect + octree
+    cudaStream_t st = ss.st, st2 = ev ? ss.st : ss.st2;
     cudaError_t e;
     e = cudaMemsetAsync(plan.candCount, 0, sizeof(int) * ORB_MAX_LEVELS * plan.batch, st);
     if (e != cudaSuccess) return e;
@@ -1109,12 +1147,21 @@ cudaError_t orbk_run_extract(const OrbPlan& plan, int nframes, orb_keypoint_dev*
         ++g_launches;
     }
     if (ev) cudaEventRecord(ev[1], st);
-    int nsrc = 0, blurTiles = 0;
+    // fork: the blur needs only the pyramid
+    int blurTiles = 0;
     for (int l = 0; l < plan.nlevels; ++l)
-        if (plan.lv[l].src == l) {
-            ++nsrc;
+        if (plan.lv[l].src == l)
             blurTiles += ((plan.lv[l].cols + BLUR_TW - 1) / BLUR_TW) * ((plan.lv[l].rows + BLUR_TH - 1) / BLUR_TH);
-        }
+    e = cudaEventRecord(ss.fork, st);
+    if (e != cudaSuccess) return e;
+    e = cudaStreamWaitEvent(st2, ss.fork, 0);
+    if (e != cudaSuccess) return e;
+    if (ev) cudaEventRecord(ev[6], st2);
+    k_blur<<<dim3(blurTiles, nframes), 256, 0, st2>>>(plan);
+    ++g_launches;
+    if (ev) cudaEventRecord(ev[7], st2);
+    e = cudaEventRecord(ss.join, st2);
+    if (e != cudaSuccess) return e;
     if (plan.totalTiles > 0) {
         k_detect<<<dim3(plan.totalTiles, nframes), DET_THREADS, kDetectSmem, st>>>(plan);
         ++g_launches;
@@ -1124,8 +1171,8 @@ cudaError_t orbk_run_extract(const OrbPlan& plan, int nframes, orb_keypoint_dev*
     k_octree<<<dim3(plan.nlevels, nframes), OCT_THREADS, kOctreeSmem, st>>>(plan);
     g_launches += 2;
     if (ev) cudaEventRecord(ev[3], st);
-    k_blur<<<dim3(blurTiles, nframes), 256, 0, st>>>(plan);
-    ++g_launches;
+    e = cudaStreamWaitEvent(st, ss.join, 0);
+    if (e != cudaSuccess) return e;
     if (ev) cudaEventRecord(ev[4], st);
     k_describe<<<dim3((plan.totalKmax + 7) / 8, nframes), 256, 0, st>>>(plan, d_kps, d_desc, cap, d_counts);
     ++g_launches;

@@ -15,10 +15,19 @@ cudaError_t orbk_init_device();
 // Runs pyramid -> detect -> octree -> blur -> describe for `nframes` frames on stream `st`.
 // plan.lv[0].img must point at the level-0 frames.  Outputs: d_kps [nframes][cap],
 // d_desc [nframes][cap][32], d_counts [nframes] (device memory).
-// `ev` (optional): ORB_STAGES+1 events recorded before the first stage and after each stage.
+// Two streams: `st` runs pyramid -> detect -> octree -> describe, `st2` runs the blur (which only
+// needs the pyramid) concurrently with detect + octree; `fork` / `join` are the events that order
+// them.  `ev` (optional, ORB_EVENTS entries): ev[0..5] on `st` before the first stage and after
+// pyramid, detect, octree, the join, describe; ev[6], ev[7] around the blur on `st2`.
 #define ORB_STAGES 5
+#define ORB_EVENTS 8
+struct OrbStreams {
+    cudaStream_t st, st2;
+    cudaEvent_t fork, join;
+};
 cudaError_t orbk_run_extract(const OrbPlan& plan, int nframes, orb_keypoint_dev* d_kps, uint8_t* d_desc, int cap,
-                             int* d_counts, cudaStream_t st, cudaEvent_t* ev = nullptr);
+                             int* d_counts, const OrbStreams& ss, cudaEvent_t* ev = nullptr);
 void orbk_build_ic_table(int2* out /* 4*31*9 */);
+void orbk_build_pair_table(float4* out /* 182 */);
 unsigned long long orbk_launch_count();
 void orbk_count_launch(int n);

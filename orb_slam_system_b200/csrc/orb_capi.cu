@@ -126,6 +126,9 @@ struct orb_extractor {
     HostTables tab;
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;  // blur runs here, concurrently with detect + octree
+    cudaEvent_t evFork = nullptr, evJoin = nullptr;
+    OrbStreams streams() const { return OrbStreams{stream, stream2, evFork, evJoin}; }
     int max_batch = 1;
     OrbPlan plan;            // current shape (plan.rows == 0: none)
     std::vector<void*> allocs;  // everything the plan points at
@@ -139,11 +142,11 @@ struct orb_extractor {
     std::vector<int> h_status;
     // per-stage CUDA-event records (orb_extractor_set_profiling)
     bool profiling = false;
-    std::vector<cudaEvent_t> events;  // (ORB_STAGES + 1) per recorded call
+    std::vector<cudaEvent_t> events;  // ORB_EVENTS per recorded call
     cudaEvent_t* next_events() {
         if (!profiling) return nullptr;
         const size_t base = events.size();
-        for (int i = 0; i <= ORB_STAGES; ++i) {
+        for (int i = 0; i < ORB_EVENTS; ++i) {
             cudaEvent_t e;
             if (cudaEventCreate(&e) != cudaSuccess) {
                 events.resize(base);
@@ -316,6 +319,12 @@ static int build_plan(orb_extractor* h, int rows, int cols) {
         CUDA_TRY(dev_alloc(h, &d_ic, ic.size()));
         CUDA_TRY(cudaMemcpy(d_ic, ic.data(), ic.size() * sizeof(int2), cudaMemcpyHostToDevice));
         P.icTab = d_ic;
+        std::vector<float4> pt(182);
+        orbk_build_pair_table(pt.data());
+        float4* d_pt;
+        CUDA_TRY(dev_alloc(h, &d_pt, pt.size()));
+        CUDA_TRY(cudaMemcpy(d_pt, pt.data(), pt.size() * sizeof(float4), cudaMemcpyHostToDevice));
+        P.pairTab = d_pt;
     }
     CUDA_TRY(dev_alloc(h, &P.needGeneric, (size_t)B * ORB_MAX_LEVELS));
     CUDA_TRY(cudaMemset(P.needGeneric, 0, sizeof(int) * B * ORB_MAX_LEVELS));
@@ -359,15 +368,13 @@ extern "C" int orb_extractor_create(const orb_params* params, int max_rows, int 
     h->max_batch = max_batch;
     memset(&h->plan, 0, sizeof h->plan);
     cudaError_t ce = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking);
+    if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&h->evFork, cudaEventDisableTiming);
+    if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&h->evJoin, cudaEventDisableTiming);
+    if (ce == cudaSuccess) ce = cudaMalloc((void**)&h->d_counts, sizeof(int) * max_batch);
     if (ce != cudaSuccess) {
-        delete h;
-        return fail(ORB_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(ce));
-    }
-    ce = cudaMalloc((void**)&h->d_counts, sizeof(int) * max_batch);
-    if (ce != cudaSuccess) {
-        cudaStreamDestroy(h->stream);
-        delete h;
-        return fail(ORB_ERR_CUDA, "cudaMalloc: %s", cudaGetErrorString(ce));
+        orb_extractor_destroy(h);
+        return fail(ORB_ERR_CUDA, "stream/event/alloc setup: %s", cudaGetErrorString(ce));
     }
     if (max_rows > 0 && max_cols > 0) {
         int rc = build_plan(h, max_rows, max_cols);
@@ -389,6 +396,9 @@ extern "C" void orb_extractor_destroy(orb_extractor* h) {
     if (h->d_kps) cudaFree(h->d_kps);
     if (h->d_desc) cudaFree(h->d_desc);
     if (h->d_counts) cudaFree(h->d_counts);
+    if (h->evFork) cudaEventDestroy(h->evFork);
+    if (h->evJoin) cudaEventDestroy(h->evJoin);
+    if (h->stream2) cudaStreamDestroy(h->stream2);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -458,7 +468,7 @@ extern "C" int orb_extract_batch_device(orb_extractor* h, int n, const uint8_t* 
                                        stride, cols, rows, cudaMemcpyDeviceToDevice, h->stream));
     }
     h->last_n = n;
-    CUDA_TRY(orbk_run_extract(P, n, reinterpret_cast<orb_keypoint_dev*>(d_kps), d_desc, cap, d_counts, h->stream, h->next_events()));
+    CUDA_TRY(orbk_run_extract(P, n, reinterpret_cast<orb_keypoint_dev*>(d_kps), d_desc, cap, d_counts, h->streams(), h->next_events()));
     return ORB_OK;
 }
 
@@ -485,13 +495,17 @@ extern "C" int orb_extractor_stage_times(orb_extractor* h, double* ms_sum, int* 
     if (!h || !ms_sum || !ncalls) return fail(ORB_ERR_INVALID, "null argument");
     CUDA_TRY(cudaSetDevice(h->device));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream2));
     for (int i = 0; i < ORB_STAGES; ++i) ms_sum[i] = 0.0;
-    const size_t per = ORB_STAGES + 1;
+    const size_t per = ORB_EVENTS;
     *ncalls = (int)(h->events.size() / per);
+    // event pairs of the stages: pyramid, detect, octree on the main stream; blur on the second
+    // stream (it overlaps detect + octree); describe after the join
+    static const int first[ORB_STAGES] = {0, 1, 2, 6, 4}, last[ORB_STAGES] = {1, 2, 3, 7, 5};
     for (size_t c = 0; c < h->events.size() / per; ++c)
         for (int i = 0; i < ORB_STAGES; ++i) {
             float ms = 0.f;
-            CUDA_TRY(cudaEventElapsedTime(&ms, h->events[c * per + i], h->events[c * per + i + 1]));
+            CUDA_TRY(cudaEventElapsedTime(&ms, h->events[c * per + first[i]], h->events[c * per + last[i]]));
             ms_sum[i] += ms;
         }
     return ORB_OK;
@@ -528,7 +542,7 @@ extern "C" int orb_extract_batch(orb_extractor* h, int n, const uint8_t* imgs, i
                                        cudaMemcpyHostToDevice, h->stream));
     }
     h->last_n = n;
-    CUDA_TRY(orbk_run_extract(h->plan, n, h->d_kps, h->d_desc, h->out_cap, h->d_counts, h->stream, h->next_events()));
+    CUDA_TRY(orbk_run_extract(h->plan, n, h->d_kps, h->d_desc, h->out_cap, h->d_counts, h->streams(), h->next_events()));
     CUDA_TRY(cudaMemcpyAsync(counts, h->d_counts, sizeof(int) * n, cudaMemcpyDeviceToHost, h->stream));
     rc = check_status(h, n);  // synchronises
     if (rc != ORB_OK) return rc;

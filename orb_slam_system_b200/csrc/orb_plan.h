@@ -65,5 +65,6 @@ struct OrbPlan {
     int* status;             // [batch] octree status flags (non-zero: unseparable keys)
     int* needGeneric;        // [batch][ORB_MAX_LEVELS] problems the table-based octree handed over
     const int2* icTab;       // [4][31][9] IC_Angle dp4a weights (k_describe)
+    const float4* pairTab;   // [182] rBRIEF test pairs (x0, y0, x1, y1)
     OrbLevel lv[ORB_MAX_LEVELS];
 };
