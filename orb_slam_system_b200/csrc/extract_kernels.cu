@@ -75,17 +75,19 @@ __global__ void __launch_bounds__(256) k_resize(const uint8_t* __restrict__ src,
 // neighbours outside the cell's candidate area count as 0, response = m - 1.
 // ------------------------------------------------------------------------------------------
 #define DET_MAX_SURV 4096  // >= ceil(250/2) * ceil(59/2): NMS survivors are never 8-adjacent
+#define DET_WLIST_PER_WARP 512  // >= ceil(59/4) rows x 32 words handled by one warp in pass B
 
 struct DetectSmem {
-    union {
-        unsigned img[DET_TILE_H][DET_SP / 4];  // image tile (passes stage + A)
-        unsigned F[DET_TILE_H][DET_SP / 4];    // NMS survivors, 4 candidate columns per word (pass B)
+    union {                                    // (first member: the TMA destination, 128-byte aligned)
+        unsigned img[DET_TILE_H + 1][DET_TILE_W / 4];  // image tile, dense 256-byte rows (TMA box) + one slack row
+        unsigned F[DET_TILE_H + 1][DET_TILE_W / 4];    // NMS survivors, 4 candidate columns per word (pass B)
     };
     union {
         unsigned sc[DET_TILE_H][DET_SP / 4];   // score tile with a one-word / one-row zero border
         unsigned surv[DET_MAX_SURV];           // survivor list (pass C): u | r<<8 | cx<<16 | cell<<24
     };
-    unsigned short wlist[DET_TILE_H * 64];     // compacted (row << 6 | word) of the non-zero F words
+    unsigned short wlist[(DET_THREADS / 32) * DET_WLIST_PER_WARP];  // per warp: (row << 6 | word) of its non-zero F words
+    int wcount[DET_THREADS / 32];
     unsigned char cellOf[DET_TILE_W + 8];      // candidate column -> cell index inside the tile
     int cellHasIni[16];
     int nWords;
@@ -93,7 +95,33 @@ struct DetectSmem {
     int nEmit;
     int emitBase;
     int emitFill;
+    unsigned long long bar;                    // mbarrier the TMA load completes on
 };
+
+// ---- TMA / mbarrier primitives (PTX; SASS: UTMALDG, SYNCS) ----
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra LAB_DONE;\n"
+        "bra LAB_WAIT;\n"
+        "LAB_DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(unsigned dst, const CUtensorMap* map, int x, int y, int z, unsigned bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(dst), "l"((unsigned long long)map), "r"(x), "r"(y), "r"(z), "r"(bar) : "memory");
+}
 
 __device__ __forceinline__ void fast_score_pairs(const unsigned (&r)[16], unsigned c2, unsigned low2,
                                                  unsigned neglow2, unsigned& u) {
@@ -125,8 +153,9 @@ __device__ __forceinline__ void fast_score_pairs(const unsigned (&r)[16], unsign
 __device__ __forceinline__ unsigned even_lanes(unsigned w) { return w & 0x00ff00ffu; }
 __device__ __forceinline__ unsigned odd_lanes(unsigned w) { return __byte_perm(w, 0u, 0x4341); }
 
-__global__ void __launch_bounds__(DET_THREADS) k_detect(const __grid_constant__ OrbPlan plan) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+__global__ void __launch_bounds__(DET_THREADS) k_detect(const __grid_constant__ OrbPlan plan,
+                                                        const CUtensorMap* __restrict__ maps) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
     DetectSmem& sm = *reinterpret_cast<DetectSmem*>(smem_raw);
 
     const int f = blockIdx.y;
@@ -149,26 +178,23 @@ __global__ void __launch_bounds__(DET_THREADS) k_detect(const __grid_constant__ 
     const int TW = X1 - X0, TH = Y1 - Y0;
     const int CW = TW - 6, CH = TH - 6;  // candidate area
     if (CW <= 0 || CH <= 0) return;
-    const int QR = (CW + 3) >> 2;  // 4-pixel groups per candidate row
     const int tid = threadIdx.x;
     const int wCell = L.wCell;
 
-    // ---- stage the image tile: smem byte (r, c) = level pixel (Y0 + r, X0 + c)
+    // ---- stage the image tile with one TMA box load.  The TMA unit needs a 16-byte aligned start
+    // address, so the 256 x boxH box starts at X0a = X0 & ~15: smem byte (r, c) = level pixel
+    // (Y0 + r, X0a + c).  Candidate column cx (level x = X0 + 3 + cx) sits at smem byte
+    // 4*wo + ph + 3 + cx.  Out-of-image parts of the box are zero-filled by the TMA unit.
+    const int a0 = X0 & 15, wo = a0 >> 2, ph = a0 & 3;
+    const int QR = (CW + ph + 3) >> 2;  // 4-pixel groups per candidate row; group q, byte k <-> cx = 4q + k - ph
+    const unsigned bar = smem_u32(&sm.bar);
+    if (tid == 0) mbar_init(bar, 1);
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(bar, (unsigned)(DET_TILE_W * L.boxH));
+        tma_load_3d(smem_u32(&sm.img[0][0]), maps + l, X0 - a0, Y0, f, bar);
+    }
     {
-        const uint8_t* base = L.img + (size_t)f * L.plane;
-        const int wb = X0 >> 2, sh = (X0 & 3) * 8;
-        const int nw = min((TW + 9) >> 2, DET_SP / 4);
-        const int pitchW = L.pitch >> 2;
-        const int warp = tid >> 5, lane = tid & 31;
-        for (int r = warp; r < TH; r += DET_THREADS / 32) {
-            const unsigned* g = reinterpret_cast<const unsigned*>(base + (size_t)(Y0 + r) * L.pitch);
-            for (int k = lane; k < nw; k += 32) {
-                const int idx = wb + k;
-                const unsigned lo = idx < pitchW ? __ldg(g + idx) : 0u;
-                const unsigned hi = idx + 1 < pitchW ? __ldg(g + idx + 1) : 0u;
-                sm.img[r][k] = __funnelshift_r(lo, hi, sh);
-            }
-        }
         // zero border of the score tile: rows 0 and CH+1, words 0 and QR+1
         for (int i = tid; i < 2 * (QR + 2); i += DET_THREADS) {
             const int r = i < QR + 2 ? 0 : CH + 1;
@@ -178,7 +204,8 @@ __global__ void __launch_bounds__(DET_THREADS) k_detect(const __grid_constant__ 
             const int r = i >> 1;
             sm.sc[r][(i & 1) ? QR + 1 : 0] = 0u;
         }
-        for (int i = tid; i < CW + 4; i += DET_THREADS) sm.cellOf[i] = (unsigned char)(i / wCell);
+        // cellOf[cx + 4] for cx in [-4, CW + 4): cell index of candidate column cx (255 left of the tile)
+        for (int i = tid; i < CW + 8; i += DET_THREADS) sm.cellOf[i] = i < 4 ? (unsigned char)255 : (unsigned char)((i - 4) / wCell);
         if (tid < 16) sm.cellHasIni[tid] = 0;
         if (tid == 0) {
             sm.nWords = 0;
@@ -187,23 +214,23 @@ __global__ void __launch_bounds__(DET_THREADS) k_detect(const __grid_constant__ 
             sm.emitFill = 0;
         }
     }
+    mbar_wait(bar, 0);  // the tile has landed (async-proxy writes are visible after the wait)
     __syncthreads();
 
-    // ---- pass A: scores.  thread (q, r): candidate cols 4q..4q+3 of candidate row r;
-    // candidate col cx sits at tile byte column cx + 3.
+    // ---- pass A: scores.  thread (q, r): candidate cols 4q-ph .. 4q-ph+3 of candidate row r
     const unsigned low2 = (unsigned)plan.lowTh * 0x00010001u;
     const unsigned neglow2 = ((unsigned)(-plan.lowTh) & 0xffffu) * 0x00010001u;
     const int q = tid & 63, grp = tid >> 6;
     if (q < QR) {
         for (int r = grp; r < CH; r += DET_THREADS / 64) {
-            // rows r..r+6 of the tile; words q, q+1, q+2 hold tile bytes 4q..4q+11 = b0..b11,
+            // rows r..r+6 of the tile; words wo+q .. wo+q+2 hold 12 tile bytes b0..b11,
             // candidate pixels p0..p3 = b3..b6, ring offset dx reads b(3+dx)..b(6+dx)
             unsigned w[7][3];
 #pragma unroll
             for (int rr = 0; rr < 7; ++rr) {
-                w[rr][0] = sm.img[r + rr][q];
-                w[rr][1] = sm.img[r + rr][q + 1];
-                w[rr][2] = sm.img[r + rr][q + 2];
+                w[rr][0] = sm.img[r + rr][wo + q];
+                w[rr][1] = sm.img[r + rr][wo + q + 1];
+                w[rr][2] = sm.img[r + rr][wo + q + 2];
             }
             // unaligned 4-byte windows: win(rr, dx) = bytes b(3+dx)..b(6+dx) of row rr
 #define WIN(rr, dx)                                                                   \
@@ -245,8 +272,9 @@ __global__ void __launch_bounds__(DET_THREADS) k_detect(const __grid_constant__ 
             fast_score_pairs(re, even_lanes(cen), low2, neglow2, ue);
             fast_score_pairs(ro, odd_lanes(cen), low2, neglow2, uo);
             unsigned word = ue | (uo << 8);  // bytes: p0, p1, p2, p3
-            const int rem = CW - 4 * q;      // candidate cols left in this row
+            const int rem = CW + ph - 4 * q;  // bytes of this group left of the candidate area's end
             if (rem < 4) word &= (1u << (8 * rem)) - 1u;
+            if (q == 0) word &= 0xffffffffu << (8 * ph);  // bytes before candidate column 0
             sm.sc[r + 1][q + 1] = word;
         }
     }
@@ -265,9 +293,9 @@ __global__ void __launch_bounds__(DET_THREADS) k_detect(const __grid_constant__ 
         if (active) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const int cx = 4 * q + k;
-                const bool first = cx == 0 || sm.cellOf[cx - 1] != sm.cellOf[cx];
-                const bool last = sm.cellOf[cx + 1] != sm.cellOf[cx];
+                const int cx = 4 * q + k - ph;
+                const bool first = sm.cellOf[cx + 3] != sm.cellOf[cx + 4];
+                const bool last = sm.cellOf[cx + 5] != sm.cellOf[cx + 4];
                 const unsigned ln = 0xffu << (16 * (k >> 1));
                 if (!first) { if (k & 1) mLo |= ln; else mLe |= ln; }
                 if (!last) { if (k & 1) mRo |= ln; else mRe |= ln; }
@@ -275,6 +303,8 @@ __global__ void __launch_bounds__(DET_THREADS) k_detect(const __grid_constant__ 
         }
         const int rpg = (CH + 3) >> 2;
         const int r0 = grp * rpg, r1 = min(r0 + rpg, CH);  // identical for the whole warp
+        const int wbase = (tid >> 5) * DET_WLIST_PER_WARP;
+        int wcount = 0;  // warp-uniform
         if (r0 < r1) {
             // window rows in bordered coordinates: up = r, mid = r + 1, dn = r + 2
             unsigned upAo, upBe, upBo, upCe, midAo, midBe, midBo, midCe;
@@ -303,35 +333,35 @@ __global__ void __launch_bounds__(DET_THREADS) k_detect(const __grid_constant__ 
                 const unsigned kE = __vminu2(tE, 0x00010001u) * 0xffu, kO = __vminu2(tO, 0x00010001u) * 0xffu;
                 const unsigned outw = active ? ((midBe & kE) | ((midBo & kO) << 8)) : 0u;
                 const unsigned nz = __ballot_sync(0xffffffffu, outw != 0u);
-                if (nz) {  // warp-uniform
-                    int base = 0;
-                    if (lane == 0) base = atomicAdd(&sm.nWords, __popc(nz));
-                    base = __shfl_sync(0xffffffffu, base, 0);
-                    if (outw) {
-                        sm.F[r][q] = outw;
-                        sm.wlist[base + __popc(nz & ((1u << lane) - 1u))] = (unsigned short)((r << 6) | q);
-                    }
+                if (outw) {  // this warp's private list region: no atomics
+                    sm.F[r][q] = outw;
+                    sm.wlist[wbase + wcount + __popc(nz & ((1u << lane) - 1u))] = (unsigned short)((r << 6) | q);
                 }
+                wcount += __popc(nz);
                 upAo = midAo; upBe = midBe; upBo = midBo; upCe = midCe;
                 midAo = dnAo; midBe = dnBe; midBo = dnBo; midCe = dnCe;
             }
         }
+        if (lane == 0) sm.wcount[tid >> 5] = wcount;
     }
-    __syncthreads();
+    __syncthreads();  // F / wlist complete, score tile dead (its memory becomes the survivor list)
     // ---- survivors out of the compacted words; per-cell "non-empty at iniTh" flags
     {
-        const int nW = sm.nWords;
+        int nW = 0;
+#pragma unroll
+        for (int w = 0; w < DET_THREADS / 32; ++w) nW += sm.wcount[w];
         if (nW == 0) return;
-        for (int i = tid; i < nW; i += DET_THREADS) {
-            const int idx = sm.wlist[i];
+        const int myW = sm.wcount[tid >> 5], wb = (tid >> 5) * DET_WLIST_PER_WARP;
+        for (int i = tid & 31; i < myW; i += 32) {
+            const int idx = sm.wlist[wb + i];
             const int r = idx >> 6, qq = idx & 63;
             unsigned w = sm.F[r][qq];
             while (w) {  // at most two survivors per word (never 8-adjacent)
                 const int k = (__ffs(w) - 1) >> 3;
                 const unsigned u = (w >> (8 * k)) & 0xffu;
                 w &= ~(0xffu << (8 * k));
-                const int cx = 4 * qq + k;
-                const unsigned cell = sm.cellOf[cx];
+                const int cx = 4 * qq + k - ph;
+                const unsigned cell = sm.cellOf[cx + 4];
                 const int slot = atomicAdd(&sm.nSurv, 1);
                 if (slot < DET_MAX_SURV) sm.surv[slot] = u | ((unsigned)r << 8) | ((unsigned)cx << 16) | (cell << 24);
                 if ((int)u >= iniU) sm.cellHasIni[cell] = 1;
@@ -475,7 +505,7 @@ struct OctFastSmem {
 };
 
 __global__ void __launch_bounds__(OCTF_THREADS) k_octree_fast(const __grid_constant__ OrbPlan plan) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
     OctFastSmem& sm = *reinterpret_cast<OctFastSmem*>(smem_raw);
     const int lt = blockIdx.x, f = blockIdx.y, tid = threadIdx.x;
     const OrbLevel& T = plan.lv[lt];
@@ -644,7 +674,7 @@ __global__ void __launch_bounds__(OCTF_THREADS) k_octree_fast(const __grid_const
 // (level, frame) problems k_octree_fast flagged.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(OCT_THREADS) k_octree(const __grid_constant__ OrbPlan plan) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned long long* smA = reinterpret_cast<unsigned long long*>(smem_raw);
     unsigned long long* smB = smA + OCT_SMEM_A;
     OctShared& sh = *reinterpret_cast<OctShared*>(smB + OCT_SMEM_B);
@@ -1109,6 +1139,30 @@ void orbk_build_ic_table(int2* out) {
 // ------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------
+cudaError_t orbk_encode_level_map(CUtensorMap* out, const uint8_t* base, int cols, int rows, int frames, int pitch,
+                                  unsigned long long plane, int boxH) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+        if (e != cudaSuccess) return e;
+        if (q != cudaDriverEntryPointSuccess || !p) return cudaErrorNotSupported;
+        fn = (EncodeFn)p;
+    }
+    if (((uintptr_t)base & 15) || (pitch & 15) || (plane & 15)) return cudaErrorMisalignedAddress;
+    cuuint64_t gdim[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)(frames > 0 ? frames : 1)};
+    cuuint64_t gstr[2] = {(cuuint64_t)pitch, (cuuint64_t)plane};
+    cuuint32_t box[3] = {(cuuint32_t)DET_TILE_W, (cuuint32_t)boxH, 1u};
+    cuuint32_t estr[3] = {1u, 1u, 1u};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
 static unsigned long long g_launches = 0;
 unsigned long long orbk_launch_count() { return g_launches; }
 void orbk_count_launch(int n) { g_launches += n; }
@@ -1126,10 +1180,10 @@ cudaError_t orbk_init_device() {
 }
 
 cudaError_t orbk_run_extract(const OrbPlan& plan, int nframes, orb_keypoint_dev* d_kps, uint8_t* d_desc, int cap,
-                             int* d_counts, const OrbStreams& ss, cudaEvent_t* ev) {
+                             int* d_counts, const OrbStreams& ss, const CUtensorMap* d_maps, cudaEvent_t* ev) {
     // with per-stage events requested everything runs on one stream, so that every stage's
     // event-timed duration is its own (no overlap); otherwise the blur overlaps detect + octree
-    cudaStream_t st = ss.st, st2 = ev ? ss.st : ss.st2;
+    cudaStream_t st = ss.st, st2 = ss.st2;
     cudaError_t e;
     e = cudaMemsetAsync(plan.candCount, 0, sizeof(int) * ORB_MAX_LEVELS * plan.batch, st);
     if (e != cudaSuccess) return e;
@@ -1147,32 +1201,40 @@ cudaError_t orbk_run_extract(const OrbPlan& plan, int nframes, orb_keypoint_dev*
         ++g_launches;
     }
     if (ev) cudaEventRecord(ev[1], st);
-    // fork: the blur needs only the pyramid
     int blurTiles = 0;
     for (int l = 0; l < plan.nlevels; ++l)
         if (plan.lv[l].src == l)
             blurTiles += ((plan.lv[l].cols + BLUR_TW - 1) / BLUR_TW) * ((plan.lv[l].rows + BLUR_TH - 1) / BLUR_TH);
-    e = cudaEventRecord(ss.fork, st);
-    if (e != cudaSuccess) return e;
-    e = cudaStreamWaitEvent(st2, ss.fork, 0);
-    if (e != cudaSuccess) return e;
-    if (ev) cudaEventRecord(ev[6], st2);
-    k_blur<<<dim3(blurTiles, nframes), 256, 0, st2>>>(plan);
-    ++g_launches;
-    if (ev) cudaEventRecord(ev[7], st2);
-    e = cudaEventRecord(ss.join, st2);
-    if (e != cudaSuccess) return e;
+    if (!ev) {
+        // fork: the blur needs only the pyramid and overlaps detect + octree on the second stream
+        e = cudaEventRecord(ss.fork, st);
+        if (e != cudaSuccess) return e;
+        e = cudaStreamWaitEvent(st2, ss.fork, 0);
+        if (e != cudaSuccess) return e;
+        k_blur<<<dim3(blurTiles, nframes), 256, 0, st2>>>(plan);
+        ++g_launches;
+        e = cudaEventRecord(ss.join, st2);
+        if (e != cudaSuccess) return e;
+    }
     if (plan.totalTiles > 0) {
-        k_detect<<<dim3(plan.totalTiles, nframes), DET_THREADS, kDetectSmem, st>>>(plan);
+        k_detect<<<dim3(plan.totalTiles, nframes), DET_THREADS, kDetectSmem, st>>>(plan, d_maps);
         ++g_launches;
     }
     if (ev) cudaEventRecord(ev[2], st);
     k_octree_fast<<<dim3(plan.nlevels, nframes), OCTF_THREADS, kOctFastSmem, st>>>(plan);
     k_octree<<<dim3(plan.nlevels, nframes), OCT_THREADS, kOctreeSmem, st>>>(plan);
     g_launches += 2;
-    if (ev) cudaEventRecord(ev[3], st);
-    e = cudaStreamWaitEvent(st, ss.join, 0);
-    if (e != cudaSuccess) return e;
+    if (ev) {
+        // profiling: stages back to back on one stream, blur after the octree
+        cudaEventRecord(ev[3], st);
+        cudaEventRecord(ev[6], st);
+        k_blur<<<dim3(blurTiles, nframes), 256, 0, st>>>(plan);
+        ++g_launches;
+        cudaEventRecord(ev[7], st);
+    } else {
+        e = cudaStreamWaitEvent(st, ss.join, 0);
+        if (e != cudaSuccess) return e;
+    }
     if (ev) cudaEventRecord(ev[4], st);
     k_describe<<<dim3((plan.totalKmax + 7) / 8, nframes), 256, 0, st>>>(plan, d_kps, d_desc, cap, d_counts);
     ++g_launches;

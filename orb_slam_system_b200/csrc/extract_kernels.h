@@ -1,5 +1,6 @@
 // Launch interface of the extractor kernels (extract_kernels.cu) used by the C ABI layer.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -21,12 +22,22 @@ cudaError_t orbk_init_device();
 // pyramid, detect, octree, the join, describe; ev[6], ev[7] around the blur on `st2`.
 #define ORB_STAGES 5
 #define ORB_EVENTS 8
+// TMA descriptors of the level images (x, y, frame) for k_detect's tile staging: encoded on the
+// host by orbk_encode_level_map, copied to device global memory, read by the TMA unit from there.
+struct DetectMaps {
+    CUtensorMap m[ORB_MAX_LEVELS];
+};
+// Encodes the (cols x rows x frames) uint8 tensor of one level with a 256 x boxH x 1 box.
+// Returns cudaSuccess or an error (the driver entry point is looked up at run time).
+cudaError_t orbk_encode_level_map(CUtensorMap* out, const uint8_t* base, int cols, int rows, int frames, int pitch,
+                                  unsigned long long plane, int boxH);
+
 struct OrbStreams {
     cudaStream_t st, st2;
     cudaEvent_t fork, join;
 };
 cudaError_t orbk_run_extract(const OrbPlan& plan, int nframes, orb_keypoint_dev* d_kps, uint8_t* d_desc, int cap,
-                             int* d_counts, const OrbStreams& ss, cudaEvent_t* ev = nullptr);
+                             int* d_counts, const OrbStreams& ss, const CUtensorMap* d_maps, cudaEvent_t* ev = nullptr);
 void orbk_build_ic_table(int2* out /* 4*31*9 */);
 void orbk_build_pair_table(float4* out /* 182 */);
 unsigned long long orbk_launch_count();

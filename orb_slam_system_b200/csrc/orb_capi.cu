@@ -10,6 +10,7 @@
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <string>
@@ -131,6 +132,11 @@ struct orb_extractor {
     OrbStreams streams() const { return OrbStreams{stream, stream2, evFork, evJoin}; }
     int max_batch = 1;
     OrbPlan plan;            // current shape (plan.rows == 0: none)
+    DetectMaps maps;         // TMA descriptors of the internal level buffers (host copy)
+    DetectMaps maps_user;    // same with level 0 pointing at the caller's device frames
+    CUtensorMap* d_maps = nullptr;       // device copies (global memory), ORB_MAX_LEVELS each
+    CUtensorMap* d_maps_user = nullptr;
+    const uint8_t* user_base = nullptr;
     std::vector<void*> allocs;  // everything the plan points at
     uint8_t* level0 = nullptr;  // internal level-0 buffer (host-input path)
     // output staging for the host-buffer API
@@ -166,6 +172,8 @@ static void free_plan(orb_extractor* h) {
     for (void* p : h->allocs) cudaFree(p);
     h->allocs.clear();
     h->level0 = nullptr;
+    h->d_maps = nullptr;
+    h->d_maps_user = nullptr;
     memset(&h->plan, 0, sizeof h->plan);
 }
 
@@ -212,7 +220,9 @@ static int level_geometry(const orb_params& prm, const HostTables& tab, int rows
         // the reference's Mat::operator()(Rect) throws on a negative cell extent
         if (minB + (nCols - 1) * L.wCell > maxBX || minB + (nRows - 1) * L.hCell > maxBY)
             return fail(ORB_ERR_SHAPE, "level %d (%dx%d): reference throws cv::Exception (negative cell ROI)", l, L.cols, L.rows);
-        int tc = std::max(1, (DET_TILE_W - 6) / L.wCell);
+        // tile width + 6-px halo + up to 15 bytes of TMA start alignment must fit the 256-byte box
+        int tc = std::max(1, (DET_TILE_W - 6 - 15) / L.wCell);
+        L.boxH = L.hCell + 6;
         L.tilesX = (nCols + tc - 1) / tc;
         L.tileCells = (nCols + L.tilesX - 1) / L.tilesX;
         L.nTiles = L.tilesX * nRows;
@@ -330,6 +340,18 @@ static int build_plan(orb_extractor* h, int rows, int cols) {
     CUDA_TRY(cudaMemset(P.needGeneric, 0, sizeof(int) * B * ORB_MAX_LEVELS));
     CUDA_TRY(cudaMemset(P.keptCount, 0, sizeof(int) * B * ORB_MAX_LEVELS));
     CUDA_TRY(cudaMemset(P.candCount, 0, sizeof(int) * B * ORB_MAX_LEVELS));
+    memset(&h->maps, 0, sizeof h->maps);
+    for (int l = 0; l < P.nlevels; ++l) {
+        const OrbLevel& L = P.lv[l];
+        if (L.src != l || L.nTiles == 0) continue;
+        CUDA_TRY(orbk_encode_level_map(&h->maps.m[l], L.img, L.cols, L.rows, B, L.pitch, L.plane, L.boxH));
+    }
+    h->maps_user = h->maps;
+    h->user_base = nullptr;
+    CUDA_TRY(dev_alloc(h, &h->d_maps, (size_t)ORB_MAX_LEVELS));
+    CUDA_TRY(dev_alloc(h, &h->d_maps_user, (size_t)ORB_MAX_LEVELS));
+    CUDA_TRY(cudaMemcpy(h->d_maps, &h->maps, sizeof(DetectMaps), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(h->d_maps_user, &h->maps, sizeof(DetectMaps), cudaMemcpyHostToDevice));
     h->level0 = P.lv[0].img;
     h->plan = P;
     return ORB_OK;
@@ -457,10 +479,19 @@ extern "C" int orb_extract_batch_device(orb_extractor* h, int n, const uint8_t* 
     int rc = build_plan(h, rows, cols);
     if (rc != ORB_OK) return rc;
     OrbPlan P = h->plan;
-    if ((int)stride == h->plan.lv[0].pitch && frame_stride == h->plan.lv[0].plane) {
+    const CUtensorMap* maps = h->d_maps;
+    if ((int)stride == h->plan.lv[0].pitch && frame_stride == h->plan.lv[0].plane && ((uintptr_t)d_imgs & 15) == 0) {
         // same layout as the internal level-0 buffer: read the caller's frames in place
         for (int l = 0; l < P.nlevels; ++l)
             if (P.lv[l].src == 0) P.lv[l].img = const_cast<uint8_t*>(d_imgs);
+        if (h->user_base != d_imgs && P.lv[0].nTiles > 0) {
+            CUDA_TRY(orbk_encode_level_map(&h->maps_user.m[0], d_imgs, P.lv[0].cols, P.lv[0].rows, n, P.lv[0].pitch, P.lv[0].plane,
+                                           P.lv[0].boxH));
+            // stream-ordered update of the device copy (pageable source: staged before the call returns)
+            CUDA_TRY(cudaMemcpyAsync(h->d_maps_user, &h->maps_user, sizeof(CUtensorMap), cudaMemcpyHostToDevice, h->stream));
+            h->user_base = d_imgs;
+        }
+        maps = h->d_maps_user;
     } else {
         // pitch conversion into the internal level-0 buffer (blur/describe share its pitch)
         for (int f = 0; f < n; ++f)
@@ -468,7 +499,7 @@ extern "C" int orb_extract_batch_device(orb_extractor* h, int n, const uint8_t* 
                                        stride, cols, rows, cudaMemcpyDeviceToDevice, h->stream));
     }
     h->last_n = n;
-    CUDA_TRY(orbk_run_extract(P, n, reinterpret_cast<orb_keypoint_dev*>(d_kps), d_desc, cap, d_counts, h->streams(), h->next_events()));
+    CUDA_TRY(orbk_run_extract(P, n, reinterpret_cast<orb_keypoint_dev*>(d_kps), d_desc, cap, d_counts, h->streams(), maps, h->next_events()));
     return ORB_OK;
 }
 
@@ -542,7 +573,7 @@ extern "C" int orb_extract_batch(orb_extractor* h, int n, const uint8_t* imgs, i
                                        cudaMemcpyHostToDevice, h->stream));
     }
     h->last_n = n;
-    CUDA_TRY(orbk_run_extract(h->plan, n, h->d_kps, h->d_desc, h->out_cap, h->d_counts, h->streams(), h->next_events()));
+    CUDA_TRY(orbk_run_extract(h->plan, n, h->d_kps, h->d_desc, h->out_cap, h->d_counts, h->streams(), h->d_maps, h->next_events()));
     CUDA_TRY(cudaMemcpyAsync(counts, h->d_counts, sizeof(int) * n, cudaMemcpyDeviceToHost, h->stream));
     rc = check_status(h, n);  // synchronises
     if (rc != ORB_OK) return rc;

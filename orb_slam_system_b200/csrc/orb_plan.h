@@ -36,6 +36,7 @@ struct OrbLevel {
     int W, H;                // maxBorder - minBorder
     int nCols, nRows, wCell, hCell;  // 0 cells when the level is smaller than one cell
     int tileCells, tilesX;   // detect tiles: tileCells cells wide, one cell row high
+    int boxH;                // rows of the TMA box that stages one detect tile (hCell + 6)
     int tileBase;            // first tile id of this level in the detect launch (src == self)
     int nTiles;
     // octree
