@@ -59,6 +59,61 @@ __global__ void __launch_bounds__(256) k_resize(const uint8_t* __restrict__ src,
 }
 
 // ------------------------------------------------------------------------------------------
+// k_resize4: the same fixed-point resize, 4 output pixels x 4 output rows per thread.
+// Per group of 4 output columns the host precomputes (xgrp): the first aligned source word wb
+// and PRMT selectors that gather the 8 source bytes (S[s_k], S[s1_k], k = 0..3) out of three
+// aligned words into two words laid out [A0 B0 A1 B1] [A2 B2 A3 B3]; the horizontal pass is then
+// one IDP.2A per pixel and row (16-bit coefficient pair x 8-bit pixel pair).  Used when every
+// group's bytes fit the 12-byte window (scale factors up to ~2.3); k_resize is the general form.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned gather8(unsigned w0, unsigned w1, unsigned w2, unsigned s01, unsigned s2) {
+    const unsigned t0 = __byte_perm(w0, w1, s01 & 0xffffu), t1 = __byte_perm(w1, w2, s01 >> 16);
+    return __byte_perm(t0, t1, s2);
+}
+
+__global__ void __launch_bounds__(256) k_resize4(const uint8_t* __restrict__ src, int spitch, unsigned long long splane,
+                                                 uint8_t* __restrict__ dst, int dpitch, unsigned long long dplane, int drows,
+                                                 int dcols, const int4* __restrict__ xgrp, const int4* __restrict__ xcoef4,
+                                                 const int* __restrict__ ytab, const int* __restrict__ ycoef) {
+    const int g = blockIdx.x * 64 + threadIdx.x;
+    const int ngroups = (dcols + 3) >> 2;
+    const int y0 = (blockIdx.y * 4 + threadIdx.y) * 4;
+    if (g >= ngroups || y0 >= drows) return;
+    const int f = blockIdx.z;
+    const int4 xg = __ldg(xgrp + g);   // wb, sel01 of word 0, sel01 of word 1, sel2 word0 | sel2 word1 << 16
+    const int4 xc = __ldg(xcoef4 + g); // a0 | a1 << 16 for the 4 columns
+    const unsigned pw = (unsigned)spitch >> 2;
+    const unsigned i0 = (unsigned)xg.x, i1 = min(i0 + 1u, pw - 1u), i2 = min(i0 + 2u, pw - 1u);
+    const unsigned* S = reinterpret_cast<const unsigned*>(src + f * splane);
+    uint8_t* D = dst + f * dplane + 4 * g;
+#pragma unroll
+    for (int dy = 0; dy < 4; ++dy) {
+        const int y = y0 + dy;
+        if (y < drows) {
+            const int yt = __ldg(ytab + y), yc = __ldg(ycoef + y);
+            const int b0 = yc & 0xffff, b1 = yc >> 16;
+            const unsigned* R0 = S + (unsigned)(yt & 0xffff) * pw;
+            const unsigned* R1 = S + (unsigned)(yt >> 16) * pw;
+            const unsigned u0 = __ldg(R0 + i0), u1 = __ldg(R0 + i1), u2 = __ldg(R0 + i2);
+            const unsigned v0 = __ldg(R1 + i0), v1 = __ldg(R1 + i1), v2 = __ldg(R1 + i2);
+            const unsigned p0 = gather8(u0, u1, u2, (unsigned)xg.y, (unsigned)xg.w & 0xffffu);
+            const unsigned p1 = gather8(u0, u1, u2, (unsigned)xg.z, (unsigned)xg.w >> 16);
+            const unsigned q0 = gather8(v0, v1, v2, (unsigned)xg.y, (unsigned)xg.w & 0xffffu);
+            const unsigned q1 = gather8(v0, v1, v2, (unsigned)xg.z, (unsigned)xg.w >> 16);
+            const int ra0 = (int)__dp2a_lo((unsigned)xc.x, p0, 0u), ra1 = (int)__dp2a_hi((unsigned)xc.y, p0, 0u);
+            const int ra2 = (int)__dp2a_lo((unsigned)xc.z, p1, 0u), ra3 = (int)__dp2a_hi((unsigned)xc.w, p1, 0u);
+            const int rb0 = (int)__dp2a_lo((unsigned)xc.x, q0, 0u), rb1 = (int)__dp2a_hi((unsigned)xc.y, q0, 0u);
+            const int rb2 = (int)__dp2a_lo((unsigned)xc.z, q1, 0u), rb3 = (int)__dp2a_hi((unsigned)xc.w, q1, 0u);
+            const unsigned o0 = (unsigned)((((b0 * (ra0 >> 4)) >> 16) + ((b1 * (rb0 >> 4)) >> 16) + 2) >> 2);
+            const unsigned o1 = (unsigned)((((b0 * (ra1 >> 4)) >> 16) + ((b1 * (rb1 >> 4)) >> 16) + 2) >> 2);
+            const unsigned o2 = (unsigned)((((b0 * (ra2 >> 4)) >> 16) + ((b1 * (rb2 >> 4)) >> 16) + 2) >> 2);
+            const unsigned o3 = (unsigned)((((b0 * (ra3 >> 4)) >> 16) + ((b1 * (rb3 >> 4)) >> 16) + 2) >> 2);
+            *reinterpret_cast<unsigned*>(D + (size_t)y * dpitch) = o0 | (o1 << 8) | (o2 << 16) | (o3 << 24);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // k_detect: per-cell FAST-9/16 + cell-local NMS + iniTh/minTh retry.
 //
 // One CTA = one tile = `tileCells` FAST cells of one cell row of one level of one frame,
@@ -1006,6 +1061,7 @@ __device__ __forceinline__ int cv_round_small(float v) {
 // .y = four 0/1 bytes (inside the disc).  m10 += dp4a(pixels, .x); m01 += v * dp4a(pixels, .y).
 __global__ void __launch_bounds__(256) k_describe(const __grid_constant__ OrbPlan plan, orb_keypoint_dev* __restrict__ kps,
                                                   uint8_t* __restrict__ desc, int cap, int* __restrict__ counts) {
+    __shared__ unsigned s_patch[8][372];  // per warp: 37 rows x 10 words of the blurred level
     const int f = blockIdx.y;
     const int* kc = plan.keptCount + f * ORB_MAX_LEVELS;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -1038,21 +1094,27 @@ __global__ void __launch_bounds__(256) k_describe(const __grid_constant__ OrbPla
     const uint2 k = L.kept[(size_t)f * L.kmax + r];
     const int x = (int)(k.x & 0xffff), y = (int)(k.x >> 16);
 
-    // ---- IC_Angle: m10 = sum u*I, m01 = sum v*I over the radius-15 disc (exact int32)
+    // ---- IC_Angle: m10 = sum u*I, m01 = sum v*I over the radius-15 disc (exact int32).
+    // Lane (r3, kk) = (lane / 9, lane % 9) for lanes 0..26 reads aligned word kk of patch rows
+    // r3, r3 + 3, r3 + 6, ... (11 steps cover the 31 rows).
     int m10 = 0, m01 = 0;
     {
         const int a = (x - 15) & 3;
-        const uint8_t* base = S.img + (size_t)f * S.plane + (size_t)(y - 15) * S.pitch + (x - 15 - a);
-        const int2* tab = plan.icTab + a * (31 * 9);
+        const unsigned pw = (unsigned)S.pitch >> 2;  // level rows are 4-byte aligned
+        const int r3 = lane / 9, kk = lane - r3 * 9;
+        const unsigned* p = reinterpret_cast<const unsigned*>(S.img + (size_t)f * S.plane + (size_t)(y - 15) * S.pitch + (x - 15 - a)) +
+                            (unsigned)r3 * pw + (unsigned)kk;
+        const int2* tab = plan.icTab + a * (31 * 9) + lane;
+        if (lane < 27) {
 #pragma unroll
-        for (int it = 0; it < 9; ++it) {
-            const int item = it * 32 + lane;
-            if (item < 31 * 9) {
-                const int vr = item / 9, kk = item - vr * 9;
-                const unsigned w = __ldg(reinterpret_cast<const unsigned*>(base + vr * S.pitch + 4 * kk));
-                const int2 t = __ldg(tab + item);
-                m10 = dp4a_us(w, t.x, m10);
-                m01 += (vr - 15) * (int)__dp4a(w, (unsigned)t.y, 0u);
+            for (int it = 0; it < 11; ++it) {
+                const int vr = it * 3 + r3;
+                if (vr < 31) {
+                    const unsigned w = __ldg(p + (unsigned)(it * 3) * pw);
+                    const int2 t = __ldg(tab + it * 27);
+                    m10 = dp4a_us(w, t.x, m10);
+                    m01 += (vr - 15) * (int)__dp4a(w, (unsigned)t.y, 0u);
+                }
             }
         }
         for (int sft = 16; sft > 0; sft >>= 1) {
@@ -1068,21 +1130,40 @@ __global__ void __launch_bounds__(256) k_describe(const __grid_constant__ OrbPla
     double sd, cd;
     sincos((double)rad, &sd, &cd);
     const float a = (float)cd, b = (float)sd;
-    const uint8_t* bl = S.blur + (size_t)f * S.plane + (size_t)y * S.pitch + x;
+    // The 182 x 2 samples lie within +-18 px of the keypoint.  Gathering them straight from global
+    // memory costs one L1 wavefront per touched sector per load; instead each warp stages its
+    // 37-row x 40-byte patch (aligned words) in shared memory with coalesced loads and gathers there.
     const int pitch = S.pitch;
+    unsigned* patch = s_patch[warp];
+    {
+        const int xa = (x - 18) & ~3;
+        const unsigned pw = (unsigned)pitch >> 2;
+        const unsigned* gsrc = reinterpret_cast<const unsigned*>(S.blur + (size_t)f * S.plane + (size_t)(y - 18) * pitch + xa);
+#pragma unroll
+        for (int it = 0; it < 12; ++it) {
+            const int wi = it * 32 + lane;
+            if (wi < 370) {
+                const int row = wi / 10, col = wi - row * 10;
+                patch[wi] = __ldg(gsrc + (unsigned)row * pw + (unsigned)col);
+            }
+        }
+    }
+    __syncwarp();
+    const uint8_t* pb = reinterpret_cast<const uint8_t*>(patch) + 18 * 40 + 18 + ((x - 18) & 3);  // the keypoint's byte
+    const float4* pairs = plan.pairTab + lane;
     unsigned myWord = 0;  // lane i < 8 ends up holding descriptor word i (words 6, 7 are zero)
 #pragma unroll
     for (int wq = 0; wq < 6; ++wq) {
         const int p = wq * 32 + lane;
         bool bit = false;
         if (p < 182) {
-            const float4 pr = __ldg(plan.pairTab + p);
+            const float4 pr = __ldg(pairs + wq * 32);
             const int r0 = cv_round_small(__fadd_rn(__fmul_rn(pr.x, b), __fmul_rn(pr.y, a)));
             const int c0 = cv_round_small(__fsub_rn(__fmul_rn(pr.x, a), __fmul_rn(pr.y, b)));
             const int r1 = cv_round_small(__fadd_rn(__fmul_rn(pr.z, b), __fmul_rn(pr.w, a)));
             const int c1 = cv_round_small(__fsub_rn(__fmul_rn(pr.z, a), __fmul_rn(pr.w, b)));
-            const int t0 = __ldg(bl + (r0 * pitch + c0));
-            const int t1 = __ldg(bl + (r1 * pitch + c1));
+            const int t0 = pb[r0 * 40 + c0];
+            const int t1 = pb[r1 * 40 + c1];
             bit = t0 < t1;
         }
         const unsigned wbits = __ballot_sync(0xffffffffu, bit);
@@ -1195,9 +1276,15 @@ cudaError_t orbk_run_extract(const OrbPlan& plan, int nframes, orb_keypoint_dev*
         const OrbLevel& D = plan.lv[l];
         if (D.src != l) continue;
         const OrbLevel& S = plan.lv[plan.lv[l - 1].src];
-        dim3 block(64, 4), grid((D.cols + 255) / 256, (D.rows + 3) / 4, nframes);
-        k_resize<<<grid, block, 0, st>>>(S.img, S.pitch, S.plane, D.img, D.pitch, D.plane, D.rows, D.cols, D.xtab,
-                                         D.xcoef, D.ytab, D.ycoef);
+        if (D.xgrp) {
+            dim3 block(64, 4), grid((D.cols + 255) / 256, (D.rows + 15) / 16, nframes);
+            k_resize4<<<grid, block, 0, st>>>(S.img, S.pitch, S.plane, D.img, D.pitch, D.plane, D.rows, D.cols, D.xgrp,
+                                              D.xcoef4, D.ytab, D.ycoef);
+        } else {
+            dim3 block(64, 4), grid((D.cols + 255) / 256, (D.rows + 3) / 4, nframes);
+            k_resize<<<grid, block, 0, st>>>(S.img, S.pitch, S.plane, D.img, D.pitch, D.plane, D.rows, D.cols, D.xtab,
+                                             D.xcoef, D.ytab, D.ycoef);
+        }
         ++g_launches;
     }
     if (ev) cudaEventRecord(ev[1], st);

@@ -304,6 +304,47 @@ static int build_plan(orb_extractor* h, int rows, int cols) {
             L.xcoef = dxc;
             L.ytab = dyt;
             L.ycoef = dyc;
+            // k_resize4 descriptors: per group of 4 output columns, gather 8 source bytes
+            // (S[s_k], S[s1_k]) from three aligned words starting at word wb
+            const int ng = (L.cols + 3) / 4;
+            std::vector<int4> xg(ng), xc4(ng);
+            bool fits = true;
+            for (int g = 0; g < ng && fits; ++g) {
+                int sA[4], sB[4], cf[4];
+                for (int k = 0; k < 4; ++k) {
+                    const int x = std::min(4 * g + k, L.cols - 1);
+                    sA[k] = xt[x] & 0xffff;
+                    sB[k] = xt[x] >> 16;
+                    cf[k] = xc[x];
+                }
+                int lo = sA[0];
+                for (int k = 0; k < 4; ++k) lo = std::min(lo, std::min(sA[k], sB[k]));
+                const int wb = lo >> 2;
+                unsigned sel01[2] = {0, 0}, sel2[2] = {0, 0};
+                for (int i = 0; i < 8; ++i) {  // output byte i: word i/4, position i%4: A0 B0 A1 B1 | A2 B2 A3 B3
+                    const int k = i >> 1, j = ((i & 1) ? sB[k] : sA[k]) - 4 * wb;
+                    if (j < 0 || j >= 12) { fits = false; break; }
+                    const int w = i >> 2, pos = i & 3;
+                    if (j < 8) {
+                        sel01[w] |= (unsigned)j << (4 * pos);            // stage 1a: from (W0, W1)
+                        sel2[w] |= (unsigned)pos << (4 * pos);           // stage 2: take t0.byte[pos]
+                    } else {
+                        sel01[w] |= (unsigned)(j - 4) << (16 + 4 * pos); // stage 1b: from (W1, W2)
+                        sel2[w] |= (unsigned)(4 + pos) << (4 * pos);     // stage 2: take t1.byte[pos]
+                    }
+                }
+                xg[g] = make_int4(wb, (int)sel01[0], (int)sel01[1], (int)(sel2[0] | (sel2[1] << 16)));
+                xc4[g] = make_int4(cf[0], cf[1], cf[2], cf[3]);
+            }
+            if (fits && (S.pitch & 3) == 0) {
+                int4 *dxg, *dxc4;
+                CUDA_TRY(dev_alloc(h, &dxg, xg.size()));
+                CUDA_TRY(dev_alloc(h, &dxc4, xc4.size()));
+                CUDA_TRY(cudaMemcpy(dxg, xg.data(), xg.size() * sizeof(int4), cudaMemcpyHostToDevice));
+                CUDA_TRY(cudaMemcpy(dxc4, xc4.data(), xc4.size() * sizeof(int4), cudaMemcpyHostToDevice));
+                L.xgrp = dxg;
+                L.xcoef4 = dxc4;
+            }
         }
     }
     // aliases share their source's buffers

@@ -32,6 +32,8 @@ struct OrbLevel {
     const int* xcoef;        // [cols] packed: a0 | a1<<16
     const int* ytab;         // [rows] packed: sy0 | sy1<<16
     const int* ycoef;        // [rows] packed: b0 | b1<<16
+    const int4* xgrp;        // [ceil(cols/4)] k_resize4 gather descriptors (null: use k_resize)
+    const int4* xcoef4;      // [ceil(cols/4)] a0 | a1<<16 of the 4 columns of a group
     // FAST cell grid over [16, cols-16) x [16, rows-16)
     int W, H;                // maxBorder - minBorder
     int nCols, nRows, wCell, hCell;  // 0 cells when the level is smaller than one cell
