@@ -9,6 +9,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <algorithm>
+
 #include "orb_plan.h"
 #include "extract_kernels.h"
 
@@ -247,7 +249,7 @@ __global__ void __launch_bounds__(DET_THREADS) k_detect(const __grid_constant__ 
     __syncthreads();
     if (tid == 0) {
         mbar_expect_tx(bar, (unsigned)(DET_TILE_W * L.boxH));
-        tma_load_3d(smem_u32(&sm.img[0][0]), maps + l, X0 - a0, Y0, f, bar);
+        tma_load_3d(smem_u32(&sm.img[0][0]), maps + l, X0 - a0, Y0, f + plan.frameBase, bar);
     }
     {
         // zero border of the score tile: rows 0 and CH+1, words 0 and QR+1
@@ -1070,24 +1072,23 @@ __global__ void __launch_bounds__(256) k_describe(const __grid_constant__ OrbPla
         counts[f] = tot;
     }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int g = blockIdx.x * 8 + warp;  // index in the concatenated [level][kmax] space
-    // level of g: lane i tests level i
-    int myBase = 0x7fffffff, myK = 0, myMax = 0;
-    if (lane < plan.nlevels) {
-        myBase = plan.lv[lane].keptBase;
-        myMax = plan.lv[lane].kmax;
-        myK = kc[lane];
+    // Warps stride over the frame's keypoints in output order (levels concatenated): lane j
+    // holds the number of keypoints of the levels before level j.
+    int myK = lane < plan.nlevels ? kc[lane] : 0;
+    int pre = myK;
+    for (int sft = 1; sft < 32; sft <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, pre, sft);
+        if (lane >= sft) pre += v;
     }
-    const bool mine = lane < plan.nlevels && g >= myBase && g < myBase + myMax;
-    const unsigned hit = __ballot_sync(0xffffffffu, mine);
-    if (!hit) return;
-    const int l = __ffs(hit) - 1;
-    const int r = g - __shfl_sync(0xffffffffu, myBase, l);
-    if (r >= __shfl_sync(0xffffffffu, myK, l)) return;
-    int off = lane < l ? myK : 0;  // keypoints of the levels before l
-    for (int sft = 16; sft > 0; sft >>= 1) off += __shfl_xor_sync(0xffffffffu, off, sft);
-    const int o = off + r;
-    if (o >= cap) return;
+    const int total = min(__shfl_sync(0xffffffffu, pre, 31), cap);
+    pre -= myK;  // exclusive prefix
+    const float4* pairs = plan.pairTab + lane;
+    unsigned* patch = s_patch[warp];
+    for (int o = blockIdx.x * 8 + warp; o < total; o += gridDim.x * 8) {
+    // level of output index o: the last level whose prefix is <= o (empty levels share a prefix)
+    const unsigned le = __ballot_sync(0xffffffffu, lane < plan.nlevels && pre <= o && myK > 0);
+    const int l = 31 - __clz(le);
+    const int r = o - __shfl_sync(0xffffffffu, pre, l);
     const OrbLevel& L = plan.lv[l];
     const OrbLevel& S = plan.lv[L.src];
 
@@ -1134,7 +1135,7 @@ __global__ void __launch_bounds__(256) k_describe(const __grid_constant__ OrbPla
     // memory costs one L1 wavefront per touched sector per load; instead each warp stages its
     // 37-row x 40-byte patch (aligned words) in shared memory with coalesced loads and gathers there.
     const int pitch = S.pitch;
-    unsigned* patch = s_patch[warp];
+    __syncwarp();  // the previous keypoint's gathers are done before the patch is overwritten
     {
         const int xa = (x - 18) & ~3;
         const unsigned pw = (unsigned)pitch >> 2;
@@ -1150,7 +1151,6 @@ __global__ void __launch_bounds__(256) k_describe(const __grid_constant__ OrbPla
     }
     __syncwarp();
     const uint8_t* pb = reinterpret_cast<const uint8_t*>(patch) + 18 * 40 + 18 + ((x - 18) & 3);  // the keypoint's byte
-    const float4* pairs = plan.pairTab + lane;
     unsigned myWord = 0;  // lane i < 8 ends up holding descriptor word i (words 6, 7 are zero)
 #pragma unroll
     for (int wq = 0; wq < 6; ++wq) {
@@ -1186,6 +1186,7 @@ __global__ void __launch_bounds__(256) k_describe(const __grid_constant__ OrbPla
         kp.class_id = -1;
         kps[(size_t)f * cap + o] = kp;
     }
+    }  // keypoint loop
 }
 
 // The 182 live rBRIEF test pairs as float4 (x0, y0, x1, y1) for plan.pairTab.
@@ -1215,6 +1216,29 @@ void orbk_build_ic_table(int2* out) {
                 }
                 out[(a * 31 + vr) * 9 + k] = make_int2((int)wu, (int)wm);
             }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_repitch: densely packed host frames (row stride == cols), copied to the device with ONE
+// linear transfer per chunk (row-by-row 2D copies are several times slower over PCIe), are laid
+// out with the internal 64-byte aligned pitch here.  4 bytes per thread, funnel-shifted loads.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_repitch(const uint8_t* __restrict__ dense, int rows, int cols, uint8_t* __restrict__ dst,
+                                                 int pitch, unsigned long long plane) {
+    const int k = blockIdx.x * 256 + threadIdx.x;  // output word in the row
+    const int y = blockIdx.y, f = blockIdx.z;
+    if (4 * k >= cols) return;
+    const size_t off = ((size_t)f * rows + y) * cols + 4 * (size_t)k;  // byte offset in the dense buffer
+    const unsigned* w = reinterpret_cast<const unsigned*>(dense) + (off >> 2);
+    const unsigned lo = __ldg(w), hi = __ldg(w + 1);  // the staging buffer has 8 bytes of slack
+    *reinterpret_cast<unsigned*>(dst + f * plane + (size_t)y * pitch + 4 * k) = __funnelshift_r(lo, hi, (unsigned)(off & 3) * 8);
+}
+
+cudaError_t orbk_repitch(const uint8_t* dense, int nframes, int rows, int cols, uint8_t* dst, int pitch, unsigned long long plane,
+                         cudaStream_t st) {
+    k_repitch<<<dim3((cols + 1023) / 1024, rows, nframes), 256, 0, st>>>(dense, rows, cols, dst, pitch, plane);
+    orbk_count_launch(1);
+    return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1266,9 +1290,9 @@ cudaError_t orbk_run_extract(const OrbPlan& plan, int nframes, orb_keypoint_dev*
     // event-timed duration is its own (no overlap); otherwise the blur overlaps detect + octree
     cudaStream_t st = ss.st, st2 = ss.st2;
     cudaError_t e;
-    e = cudaMemsetAsync(plan.candCount, 0, sizeof(int) * ORB_MAX_LEVELS * plan.batch, st);
+    e = cudaMemsetAsync(plan.candCount, 0, sizeof(int) * ORB_MAX_LEVELS * nframes, st);
     if (e != cudaSuccess) return e;
-    e = cudaMemsetAsync(plan.status, 0, sizeof(int) * plan.batch, st);
+    e = cudaMemsetAsync(plan.status, 0, sizeof(int) * nframes, st);
     if (e != cudaSuccess) return e;
     if (ev) cudaEventRecord(ev[0], st);
     // pyramid: level l = resize(level l-1); same-size levels alias their source
@@ -1323,7 +1347,12 @@ cudaError_t orbk_run_extract(const OrbPlan& plan, int nframes, orb_keypoint_dev*
         if (e != cudaSuccess) return e;
     }
     if (ev) cudaEventRecord(ev[4], st);
-    k_describe<<<dim3((plan.totalKmax + 7) / 8, nframes), 256, 0, st>>>(plan, d_kps, d_desc, cap, d_counts);
+    {
+        // warps stride over the keypoints: about four waves of 8-warp CTAs, split evenly over the frames
+        int ctasPerFrame = (148 * 8 * 4 + nframes - 1) / nframes;
+        ctasPerFrame = std::max(1, std::min(ctasPerFrame, (plan.totalKmax + 7) / 8));
+        k_describe<<<dim3(ctasPerFrame, nframes), 256, 0, st>>>(plan, d_kps, d_desc, cap, d_counts);
+    }
     ++g_launches;
     if (ev) cudaEventRecord(ev[5], st);
     return cudaGetLastError();

@@ -40,5 +40,8 @@ cudaError_t orbk_run_extract(const OrbPlan& plan, int nframes, orb_keypoint_dev*
                              int* d_counts, const OrbStreams& ss, const CUtensorMap* d_maps, cudaEvent_t* ev = nullptr);
 void orbk_build_ic_table(int2* out /* 4*31*9 */);
 void orbk_build_pair_table(float4* out /* 182 */);
+// Dense frames (row stride == cols) in `dense` -> pitched level-0 layout.
+cudaError_t orbk_repitch(const uint8_t* dense, int nframes, int rows, int cols, uint8_t* dst, int pitch, unsigned long long plane,
+                         cudaStream_t st);
 unsigned long long orbk_launch_count();
 void orbk_count_launch(int n);

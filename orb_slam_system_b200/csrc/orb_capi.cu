@@ -129,6 +129,10 @@ struct orb_extractor {
     cudaStream_t stream = nullptr;
     cudaStream_t stream2 = nullptr;  // blur runs here, concurrently with detect + octree
     cudaEvent_t evFork = nullptr, evJoin = nullptr;
+    // host-buffer pipeline: copies in and out run on their own streams, chunk by chunk
+    cudaStream_t streamIn = nullptr, streamOut = nullptr;
+    enum { MAX_CHUNKS = 8 };
+    cudaEvent_t evIn[MAX_CHUNKS] = {}, evDone[MAX_CHUNKS] = {}, evFree = nullptr;
     OrbStreams streams() const { return OrbStreams{stream, stream2, evFork, evJoin}; }
     int max_batch = 1;
     OrbPlan plan;            // current shape (plan.rows == 0: none)
@@ -139,6 +143,8 @@ struct orb_extractor {
     const uint8_t* user_base = nullptr;
     std::vector<void*> allocs;  // everything the plan points at
     uint8_t* level0 = nullptr;  // internal level-0 buffer (host-input path)
+    uint8_t* d_dense = nullptr; // landing buffer for densely packed host frames (one linear copy per chunk)
+    size_t dense_cap = 0;
     // output staging for the host-buffer API
     orb_keypoint_dev* d_kps = nullptr;
     uint8_t* d_desc = nullptr;
@@ -434,6 +440,13 @@ extern "C" int orb_extractor_create(const orb_params* params, int max_rows, int 
     if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking);
     if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&h->evFork, cudaEventDisableTiming);
     if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&h->evJoin, cudaEventDisableTiming);
+    if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&h->streamIn, cudaStreamNonBlocking);
+    if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&h->streamOut, cudaStreamNonBlocking);
+    for (int i = 0; i < orb_extractor::MAX_CHUNKS && ce == cudaSuccess; ++i) {
+        ce = cudaEventCreateWithFlags(&h->evIn[i], cudaEventDisableTiming);
+        if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&h->evDone[i], cudaEventDisableTiming);
+    }
+    if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&h->evFree, cudaEventDisableTiming);
     if (ce == cudaSuccess) ce = cudaMalloc((void**)&h->d_counts, sizeof(int) * max_batch);
     if (ce != cudaSuccess) {
         orb_extractor_destroy(h);
@@ -459,6 +472,14 @@ extern "C" void orb_extractor_destroy(orb_extractor* h) {
     if (h->d_kps) cudaFree(h->d_kps);
     if (h->d_desc) cudaFree(h->d_desc);
     if (h->d_counts) cudaFree(h->d_counts);
+    if (h->d_dense) cudaFree(h->d_dense);
+    for (int i = 0; i < orb_extractor::MAX_CHUNKS; ++i) {
+        if (h->evIn[i]) cudaEventDestroy(h->evIn[i]);
+        if (h->evDone[i]) cudaEventDestroy(h->evDone[i]);
+    }
+    if (h->evFree) cudaEventDestroy(h->evFree);
+    if (h->streamIn) cudaStreamDestroy(h->streamIn);
+    if (h->streamOut) cudaStreamDestroy(h->streamOut);
     if (h->evFork) cudaEventDestroy(h->evFork);
     if (h->evJoin) cudaEventDestroy(h->evJoin);
     if (h->stream2) cudaStreamDestroy(h->stream2);
@@ -491,6 +512,26 @@ extern "C" int orb_extractor_keypoint_bound(const orb_extractor* h, int rows, in
     }
     *bound = (int)tot;
     return ORB_OK;
+}
+
+// The plan with every per-frame pointer advanced to frame f0 (one chunk of a batch).
+static OrbPlan plan_slice(const OrbPlan& P, int f0) {
+    OrbPlan Q = P;
+    if (f0 == 0) return Q;
+    Q.frameBase = P.frameBase + f0;
+    for (int l = 0; l < P.nlevels; ++l) {
+        OrbLevel& L = Q.lv[l];
+        L.img += (size_t)f0 * L.plane;
+        L.blur += (size_t)f0 * L.plane;
+        L.cand += (size_t)f0 * L.candCap;
+        L.kept += (size_t)f0 * L.kmax;
+        L.sortScratch += (size_t)f0 * 2 * L.sortCap;
+    }
+    Q.candCount += (size_t)f0 * ORB_MAX_LEVELS;
+    Q.keptCount += (size_t)f0 * ORB_MAX_LEVELS;
+    Q.needGeneric += (size_t)f0 * ORB_MAX_LEVELS;
+    Q.status += f0;
+    return Q;
 }
 
 static int check_status(orb_extractor* h, int n) {
@@ -605,29 +646,75 @@ extern "C" int orb_extract_batch(orb_extractor* h, int n, const uint8_t* imgs, i
     rc = ensure_out(h, cap);
     if (rc != ORB_OK) return rc;
     const OrbLevel& L0 = h->plan.lv[0];
-    if (n == 1 || frame_stride == stride * (size_t)rows) {
-        // frames are consecutive rows on both sides (device plane == pitch * rows): one 2D copy
-        CUDA_TRY(cudaMemcpy2DAsync(h->level0, L0.pitch, imgs, stride, cols, (size_t)rows * n, cudaMemcpyHostToDevice, h->stream));
-    } else {
-        for (int f = 0; f < n; ++f)
-            CUDA_TRY(cudaMemcpy2DAsync(h->level0 + f * L0.plane, L0.pitch, imgs + f * frame_stride, stride, cols, rows,
-                                       cudaMemcpyHostToDevice, h->stream));
+    // Pipeline over chunks of frames: H2D copy (streamIn) -> kernels (stream, stream2) -> counts and
+    // results D2H (streamOut), so that PCIe in, compute and PCIe out of neighbouring chunks overlap.
+    // While per-stage profiling is on, one chunk is used (stage times describe whole-batch launches).
+    int nchunks = h->profiling ? 1 : std::min<int>(orb_extractor::MAX_CHUNKS, std::max(1, n / 16));
+    const int per = (n + nchunks - 1) / nchunks;
+    nchunks = (n + per - 1) / per;
+    const bool dense = stride == (size_t)cols && frame_stride == (size_t)rows * cols && ((uintptr_t)imgs & 3) == 0 && cols >= 4;
+    if (dense && h->dense_cap < (size_t)n * rows * cols + 16) {
+        CUDA_TRY(cudaStreamSynchronize(h->streamIn));
+        if (h->d_dense) cudaFree(h->d_dense);
+        h->d_dense = nullptr;
+        h->dense_cap = 0;
+        const size_t want = (size_t)h->max_batch * rows * cols + 16;
+        CUDA_TRY(cudaMalloc((void**)&h->d_dense, want));
+        h->dense_cap = want;
     }
+    // the input buffer may still be read by the previous call's kernels
+    CUDA_TRY(cudaEventRecord(h->evFree, h->stream));
+    CUDA_TRY(cudaStreamWaitEvent(h->streamIn, h->evFree, 0));
+    CUDA_TRY(cudaStreamWaitEvent(h->streamOut, h->evFree, 0));
     h->last_n = n;
-    CUDA_TRY(orbk_run_extract(h->plan, n, h->d_kps, h->d_desc, h->out_cap, h->d_counts, h->streams(), h->d_maps, h->next_events()));
-    CUDA_TRY(cudaMemcpyAsync(counts, h->d_counts, sizeof(int) * n, cudaMemcpyDeviceToHost, h->stream));
-    rc = check_status(h, n);  // synchronises
-    if (rc != ORB_OK) return rc;
-    int maxc = 0;
-    for (int f = 0; f < n; ++f) maxc = std::max(maxc, counts[f]);
-    if (maxc > cap) return fail(ORB_ERR_CAPACITY, "frame needs %d keypoints, cap is %d", maxc, cap);
-    if (maxc > 0) {
-        CUDA_TRY(cudaMemcpy2DAsync(kps, (size_t)cap * sizeof(orb_keypoint), h->d_kps, (size_t)h->out_cap * sizeof(orb_keypoint),
-                                   (size_t)maxc * sizeof(orb_keypoint), n, cudaMemcpyDeviceToHost, h->stream));
-        CUDA_TRY(cudaMemcpy2DAsync(desc, (size_t)cap * 32, h->d_desc, (size_t)h->out_cap * 32, (size_t)maxc * 32, n,
-                                   cudaMemcpyDeviceToHost, h->stream));
-        CUDA_TRY(cudaStreamSynchronize(h->stream));
+    for (int c = 0; c < nchunks; ++c) {
+        const int f0 = c * per, nf = std::min(per, n - f0);
+        if (dense) {
+            // densely packed frames: one linear copy, then the pitch conversion on the device
+            uint8_t* land = h->d_dense + (size_t)f0 * rows * cols;
+            CUDA_TRY(cudaMemcpyAsync(land, imgs + (size_t)f0 * frame_stride, (size_t)nf * rows * cols, cudaMemcpyHostToDevice, h->streamIn));
+            CUDA_TRY(orbk_repitch(land, nf, rows, cols, h->level0 + f0 * L0.plane, L0.pitch, L0.plane, h->streamIn));
+        } else if (nf == 1 || frame_stride == stride * (size_t)rows) {
+            // frames are consecutive rows on both sides (device plane == pitch * rows): one 2D copy
+            CUDA_TRY(cudaMemcpy2DAsync(h->level0 + f0 * L0.plane, L0.pitch, imgs + f0 * frame_stride, stride, cols, (size_t)rows * nf,
+                                       cudaMemcpyHostToDevice, h->streamIn));
+        } else {
+            for (int f = f0; f < f0 + nf; ++f)
+                CUDA_TRY(cudaMemcpy2DAsync(h->level0 + f * L0.plane, L0.pitch, imgs + f * frame_stride, stride, cols, rows,
+                                           cudaMemcpyHostToDevice, h->streamIn));
+        }
+        CUDA_TRY(cudaEventRecord(h->evIn[c], h->streamIn));
+        CUDA_TRY(cudaStreamWaitEvent(h->stream, h->evIn[c], 0));
+        const OrbPlan P = plan_slice(h->plan, f0);
+        CUDA_TRY(orbk_run_extract(P, nf, h->d_kps + (size_t)f0 * h->out_cap, h->d_desc + (size_t)f0 * h->out_cap * 32, h->out_cap,
+                                  h->d_counts + f0, h->streams(), h->d_maps, h->next_events()));
+        CUDA_TRY(cudaEventRecord(h->evDone[c], h->stream));
+        CUDA_TRY(cudaStreamWaitEvent(h->streamOut, h->evDone[c], 0));
+        CUDA_TRY(cudaMemcpyAsync(counts + f0, h->d_counts + f0, sizeof(int) * nf, cudaMemcpyDeviceToHost, h->streamOut));
     }
+    // results: as each chunk's counts arrive, copy exactly the rows it produced
+    int maxAll = 0;
+    for (int c = 0; c < nchunks; ++c) {
+        const int f0 = c * per, nf = std::min(per, n - f0);
+        CUDA_TRY(cudaEventRecord(h->evIn[c], h->streamOut));  // (reuse: marks "counts of chunk c are on the host")
+        CUDA_TRY(cudaEventSynchronize(h->evIn[c]));
+        int maxc = 0;
+        for (int f = f0; f < f0 + nf; ++f) maxc = std::max(maxc, counts[f]);
+        maxAll = std::max(maxAll, maxc);
+        const int w = std::min(maxc, cap);
+        if (w > 0) {
+            CUDA_TRY(cudaMemcpy2DAsync(kps + (size_t)f0 * cap, (size_t)cap * sizeof(orb_keypoint), h->d_kps + (size_t)f0 * h->out_cap,
+                                       (size_t)h->out_cap * sizeof(orb_keypoint), (size_t)w * sizeof(orb_keypoint), nf,
+                                       cudaMemcpyDeviceToHost, h->streamOut));
+            CUDA_TRY(cudaMemcpy2DAsync(desc + (size_t)f0 * cap * 32, (size_t)cap * 32, h->d_desc + (size_t)f0 * h->out_cap * 32,
+                                       (size_t)h->out_cap * 32, (size_t)w * 32, nf, cudaMemcpyDeviceToHost, h->streamOut));
+        }
+    }
+    CUDA_TRY(cudaStreamSynchronize(h->streamOut));
+    // later work on the main stream (next call, pyramid read-back) must see the copies done
+    rc = check_status(h, n);  // synchronises the main stream
+    if (rc != ORB_OK) return rc;
+    if (maxAll > cap) return fail(ORB_ERR_CAPACITY, "frame needs %d keypoints, cap is %d", maxAll, cap);
     return ORB_OK;
 }
 

@@ -61,6 +61,7 @@ struct OrbPlan {
     int rows, cols;          // level-0 shape this plan was built for
     int iniTh, minTh, lowTh; // clamped to [0,255]; lowTh = min(ini,min)
     int batch;               // frames per launch the buffers are sized for
+    int frameBase;           // first frame of this launch inside the batch buffers (TMA z offset)
     int totalTiles;          // detect tiles per frame
     int totalKmax;           // sum of kmax
     int* candCount;          // [batch][ORB_MAX_LEVELS]
