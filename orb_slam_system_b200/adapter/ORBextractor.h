@@ -1,0 +1,66 @@
+// Drop-in replacement for the reference's include/ORBextractor.h: same namespace, class name,
+// constructor, operator(), getters and public mvImagePyramid (reference include/ORBextractor.h:26-93),
+// so Frame.cc / Tracking.cc compile and behave unchanged.  The work is done by liborb_b200.so
+// (include/orb_b200.h); this file only adapts cv:: containers to the C ABI.
+//
+// Build where OpenCV exists (the reference's own environment): put this directory before the
+// reference's include/ in the include path, drop src/ORBextractor.cc from the source list and
+// link liborb_b200.so.  In this repository it is syntax-checked against
+// oracle/cvshim because the image has no OpenCV C++ headers.
+#ifndef ORBEXTRACTOR_H
+#define ORBEXTRACTOR_H
+
+#include <list>
+#include <vector>
+
+#include <opencv/cv.h>
+
+struct orb_extractor;  // include/orb_b200.h
+
+namespace ORB_SLAM2 {
+
+class ORBextractor {
+public:
+    enum { HARRIS_SCORE = 0, FAST_SCORE = 1 };
+
+    ORBextractor(int nfeatures, float scaleFactor, int nlevels, int iniThFAST, int minThFAST);
+    ~ORBextractor();
+    ORBextractor(const ORBextractor&) = delete;
+    ORBextractor& operator=(const ORBextractor&) = delete;
+
+    // Compute the ORB features and descriptors on an image.  Mask is ignored, as in the reference.
+    void operator()(cv::InputArray image, cv::InputArray mask, std::vector<cv::KeyPoint>& keypoints,
+                    cv::OutputArray descriptors);
+
+    int inline GetLevels() { return nlevels; }
+    float inline GetScaleFactor() { return scaleFactor; }
+    std::vector<float> inline GetScaleFactors() { return mvScaleFactor; }
+    std::vector<float> inline GetInverseScaleFactors() { return mvInvScaleFactor; }
+    std::vector<float> inline GetScaleSigmaSquares() { return mvLevelSigma2; }
+    std::vector<float> inline GetInverseScaleSigmaSquares() { return mvInvLevelSigma2; }
+
+    // Refilled after every call (tight level images inside a 19-px reflected border, exactly the
+    // layout Frame::ComputeStereoMatches reads, reference src/Frame.cc:453,543-560).
+    std::vector<cv::Mat> mvImagePyramid;
+
+protected:
+    int nfeatures;
+    double scaleFactor;
+    int nlevels;
+    int iniThFAST;
+    int minThFAST;
+
+    std::vector<int> mnFeaturesPerLevel;
+    std::vector<float> mvScaleFactor;
+    std::vector<float> mvInvScaleFactor;
+    std::vector<float> mvLevelSigma2;
+    std::vector<float> mvInvLevelSigma2;
+
+private:
+    orb_extractor* handle_;
+    std::vector<unsigned char> kpbuf_;
+};
+
+}  // namespace ORB_SLAM2
+
+#endif

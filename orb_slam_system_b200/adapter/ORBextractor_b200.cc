@@ -1,0 +1,84 @@
+// ORB_SLAM2::ORBextractor over the liborb_b200 C ABI (replaces the reference's src/ORBextractor.cc).
+// Error behaviour follows the reference: empty image -> silent return with outputs untouched
+// (src/ORBextractor.cc:444-445); zero keypoints -> descriptors released, keypoints not cleared
+// (:460-463); anything the CUDA path refuses (a shape on which the reference itself faults, a CUDA
+// error) is raised as cv::Exception, the only error channel operator() has.
+#include "ORBextractor.h"
+
+#include <string>
+
+#include <opencv2/core/core.hpp>
+#include <opencv2/imgproc/imgproc.hpp>
+
+#include "orb_b200.h"
+
+namespace ORB_SLAM2 {
+
+static const int EDGE_THRESHOLD = 19;
+
+[[noreturn]] static void raise(const char* what) {
+    throw cv::Exception(std::string("orb_b200: ") + what + ": " + orb_last_error());
+}
+
+ORBextractor::ORBextractor(int _nfeatures, float _scaleFactor, int _nlevels, int _iniThFAST, int _minThFAST)
+    : nfeatures(_nfeatures), scaleFactor(_scaleFactor), nlevels(_nlevels), iniThFAST(_iniThFAST), minThFAST(_minThFAST),
+      handle_(nullptr) {
+    orb_params p;
+    p.nfeatures = _nfeatures;
+    p.scale_factor = _scaleFactor;
+    p.nlevels = _nlevels;
+    p.ini_th_fast = _iniThFAST;
+    p.min_th_fast = _minThFAST;
+    if (orb_extractor_create(&p, 0, 0, 1, 0, &handle_) != ORB_OK) raise("orb_extractor_create");
+    mvScaleFactor.resize(nlevels);
+    mvInvScaleFactor.resize(nlevels);
+    mvLevelSigma2.resize(nlevels);
+    mvInvLevelSigma2.resize(nlevels);
+    mnFeaturesPerLevel.resize(nlevels);
+    orb_extractor_tables(handle_, mvScaleFactor.data(), mvInvScaleFactor.data(), mvLevelSigma2.data(), mvInvLevelSigma2.data(),
+                         mnFeaturesPerLevel.data());
+    mvImagePyramid.resize(nlevels);
+}
+
+ORBextractor::~ORBextractor() { orb_extractor_destroy(handle_); }
+
+void ORBextractor::operator()(cv::InputArray _image, cv::InputArray /*mask*/, std::vector<cv::KeyPoint>& _keypoints,
+                              cv::OutputArray _descriptors) {
+    if (_image.empty()) return;
+    cv::Mat image = _image.getMat();
+    assert(image.type() == CV_8UC1);
+
+    int bound = 0;
+    if (orb_extractor_keypoint_bound(handle_, image.rows, image.cols, &bound) != ORB_OK) raise("unsupported image shape");
+    static_assert(sizeof(cv::KeyPoint) == sizeof(orb_keypoint), "cv::KeyPoint must be the 28-byte POD the C ABI writes");
+    kpbuf_.resize((size_t)bound * sizeof(orb_keypoint));
+    cv::Mat desc(bound, 32, CV_8UC1);
+    int count = 0;
+    if (orb_extract(handle_, image.ptr<uint8_t>(0), image.rows, image.cols, (size_t)image.step, (orb_keypoint*)kpbuf_.data(),
+                    desc.ptr<uint8_t>(0), bound, &count) != ORB_OK)
+        raise("orb_extract");
+
+    // mvImagePyramid: level ROI inside a (w+38) x (h+38) buffer with a reflected border (src/ORBextractor.cc:497-515)
+    for (int level = 0; level < nlevels; ++level) {
+        int r = 0, c = 0;
+        if (orb_get_pyramid_level(handle_, 0, level, nullptr, 0, &r, &c) != ORB_OK) raise("orb_get_pyramid_level");
+        cv::Mat temp(cv::Size(c + 2 * EDGE_THRESHOLD, r + 2 * EDGE_THRESHOLD), image.type());
+        mvImagePyramid[level] = temp(cv::Rect(EDGE_THRESHOLD, EDGE_THRESHOLD, c, r));
+        if (orb_get_pyramid_level(handle_, 0, level, mvImagePyramid[level].ptr<uint8_t>(0), (size_t)mvImagePyramid[level].step, &r, &c) != ORB_OK)
+            raise("orb_get_pyramid_level");
+        cv::copyMakeBorder(mvImagePyramid[level], temp, EDGE_THRESHOLD, EDGE_THRESHOLD, EDGE_THRESHOLD, EDGE_THRESHOLD,
+                           cv::BORDER_REFLECT_101 + cv::BORDER_ISOLATED);
+    }
+
+    if (count == 0) {
+        _descriptors.release();
+        return;
+    }
+    _descriptors.create(count, 32, CV_8U);
+    cv::Mat out = _descriptors.getMat();
+    for (int i = 0; i < count; ++i) memcpy(out.ptr<uint8_t>(i), desc.ptr<uint8_t>(i), 32);
+    const cv::KeyPoint* k = reinterpret_cast<const cv::KeyPoint*>(kpbuf_.data());
+    _keypoints.assign(k, k + count);
+}
+
+}  // namespace ORB_SLAM2
