@@ -263,10 +263,40 @@ def main():
     h2d = B * ROWS * COLS
     d2h = B * 4 + B * maxc * 28 + B * maxc * 32
 
+    # ---- second half of the metric: brute-force Hamming matching (BASELINE config 4): 256 keyframe
+    # pairs of 2000 x 2000 descriptors drawn from the extractor's own output, device resident
+    from orb_slam_system_b200 import ORBmatcher
+    NP, NQ = 256, 2000
+    m = ORBmatcher(0.6, True, device=local_rank)
+    pool = d_desc[:, :NQ, :].contiguous()  # [B, 2000, 32] real descriptors of the last step
+    qsel = torch.arange(NP, device="cuda") % B
+    tsel = (torch.arange(NP, device="cuda") + 1) % B
+    dq, dt = pool[qsel].contiguous(), pool[tsel].contiguous()
+    nq = torch.full((NP,), NQ, dtype=torch.int32, device="cuda")
+    nt = torch.full((NP,), NQ, dtype=torch.int32, device="cuda")
+    obi = torch.empty((NP, NQ), dtype=torch.int32, device="cuda")
+    obd = torch.empty_like(obi)
+    osd = torch.empty_like(obi)
+    torch.cuda.synchronize()
+    mstream = torch.cuda.ExternalStream(m.stream, device=torch.device("cuda", local_rank))
+    for _ in range(3):
+        m.match_all_batch_device(dq, nq, dt, nt, obi, obd, osd)
+    m.sync()
+    barrier()
+    m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    MREP = 10
+    m0.record(mstream)
+    for _ in range(MREP):
+        m.match_all_batch_device(dq, nq, dt, nt, obi, obd, osd)
+    m1.record(mstream)
+    m.sync()
+    barrier()
+    match_ms = m0.elapsed_time(m1) / MREP
+
     if world > 1:
-        t = torch.tensor([ms_total, e2e_s], dtype=torch.float64, device="cuda")
+        t = torch.tensor([ms_total, e2e_s, match_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total, e2e_s = float(t[0].item()), float(t[1].item())
+        ms_total, e2e_s, match_ms = float(t[0].item()), float(t[1].item()), float(t[2].item())
 
     if rank == 0:
         frames = B * K * world
@@ -304,6 +334,12 @@ def main():
                          "path": {"algo_bytes_per_step": path_bytes, "achieved": path_gbs, "frac": path_gbs / peak}},
             "e2e": {"value": frames / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches), "clocks": clocks,
+            "hamming": {"metric": "Hamming pairs/s (brute force, best + second best)", "value": world * NP * NQ * NQ / (match_ms * 1e-3),
+                        "unit": "pairs/s", "workload": f"{NP} keyframe pairs x {NQ} x {NQ} descriptors per GPU (BASELINE config 4)",
+                        "ms_per_launch": match_ms,
+                        "algo_bytes_per_launch": NP * (32 * 2 * NQ + 12 * NQ),
+                        "hbm_frac": NP * (32 * 2 * NQ + 12 * NQ) / (match_ms * 1e-3) / 1e9 / peak,
+                        "popc_per_s": world * 8 * NP * NQ * NQ / (match_ms * 1e-3)},
         }
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
