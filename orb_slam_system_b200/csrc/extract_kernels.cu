@@ -277,9 +277,13 @@ __global__ void __launch_bounds__(DET_THREADS) k_detect(const __grid_constant__ 
     // ---- pass A: scores.  thread (q, r): candidate cols 4q-ph .. 4q-ph+3 of candidate row r
     const unsigned low2 = (unsigned)plan.lowTh * 0x00010001u;
     const unsigned neglow2 = ((unsigned)(-plan.lowTh) & 0xffffu) * 0x00010001u;
-    const int q = tid & 63, grp = tid >> 6;
-    if (q < QR) {
-        for (int r = grp; r < CH; r += DET_THREADS / 64) {
+    const int q = tid & 63, grp = tid >> 6;  // (pass B mapping)
+    {
+        // items (row, group) flattened over all threads so that no lane idles when QR < 64
+        const unsigned qrMagic = 0xffffffffu / (unsigned)QR + 1u;  // item / QR == umulhi(item, magic) for item < 2^16
+        for (int item = tid; item < CH * QR; item += DET_THREADS) {
+            const int r = (int)__umulhi((unsigned)item, qrMagic);
+            const int q = item - r * QR;
             // rows r..r+6 of the tile; words wo+q .. wo+q+2 hold 12 tile bytes b0..b11,
             // candidate pixels p0..p3 = b3..b6, ring offset dx reads b(3+dx)..b(6+dx)
             unsigned w[7][3];
