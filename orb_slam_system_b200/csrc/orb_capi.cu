@@ -129,8 +129,15 @@ struct orb_extractor {
     cudaStream_t stream = nullptr;
     cudaStream_t stream2 = nullptr;  // blur runs here, concurrently with detect + octree
     cudaEvent_t evFork = nullptr, evJoin = nullptr;
+    // second kernel lane: the device-resident path runs the two halves of a batch concurrently
+    enum { MAX_LANES = 4 };
+    cudaStream_t laneSt[MAX_LANES] = {}, laneSt2[MAX_LANES] = {};
+    cudaEvent_t laneFork[MAX_LANES] = {}, laneJoin[MAX_LANES] = {}, laneMerge[MAX_LANES] = {}, evSplit = nullptr;
+    OrbStreams lane(int i) const { return i == 0 ? streams() : OrbStreams{laneSt[i], laneSt2[i], laneFork[i], laneJoin[i]}; }
+    int lanes = 2;
     // host-buffer pipeline: copies in and out run on their own streams, chunk by chunk
-    cudaStream_t streamIn = nullptr, streamOut = nullptr;
+    cudaStream_t streamIn = nullptr, streamOut = nullptr, streamCnt = nullptr;
+    cudaEvent_t evCnt[8] = {};
     enum { MAX_CHUNKS = 8 };
     cudaEvent_t evIn[MAX_CHUNKS] = {}, evDone[MAX_CHUNKS] = {}, evFree = nullptr;
     OrbStreams streams() const { return OrbStreams{stream, stream2, evFork, evJoin}; }
@@ -440,8 +447,19 @@ extern "C" int orb_extractor_create(const orb_params* params, int max_rows, int 
     if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking);
     if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&h->evFork, cudaEventDisableTiming);
     if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&h->evJoin, cudaEventDisableTiming);
+    for (int i = 1; i < orb_extractor::MAX_LANES && ce == cudaSuccess; ++i) {
+        ce = cudaStreamCreateWithFlags(&h->laneSt[i], cudaStreamNonBlocking);
+        if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&h->laneSt2[i], cudaStreamNonBlocking);
+        if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&h->laneFork[i], cudaEventDisableTiming);
+        if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&h->laneJoin[i], cudaEventDisableTiming);
+        if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&h->laneMerge[i], cudaEventDisableTiming);
+    }
+    if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&h->evSplit, cudaEventDisableTiming);
+    if (const char* e = getenv("ORB_B200_LANES")) h->lanes = std::min<int>(orb_extractor::MAX_LANES, std::max(1, atoi(e)));
     if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&h->streamIn, cudaStreamNonBlocking);
     if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&h->streamOut, cudaStreamNonBlocking);
+    if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&h->streamCnt, cudaStreamNonBlocking);
+    for (int i = 0; i < 8 && ce == cudaSuccess; ++i) ce = cudaEventCreateWithFlags(&h->evCnt[i], cudaEventDisableTiming);
     for (int i = 0; i < orb_extractor::MAX_CHUNKS && ce == cudaSuccess; ++i) {
         ce = cudaEventCreateWithFlags(&h->evIn[i], cudaEventDisableTiming);
         if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&h->evDone[i], cudaEventDisableTiming);
@@ -478,8 +496,19 @@ extern "C" void orb_extractor_destroy(orb_extractor* h) {
         if (h->evDone[i]) cudaEventDestroy(h->evDone[i]);
     }
     if (h->evFree) cudaEventDestroy(h->evFree);
+    for (int i = 1; i < orb_extractor::MAX_LANES; ++i) {
+        if (h->laneFork[i]) cudaEventDestroy(h->laneFork[i]);
+        if (h->laneJoin[i]) cudaEventDestroy(h->laneJoin[i]);
+        if (h->laneMerge[i]) cudaEventDestroy(h->laneMerge[i]);
+        if (h->laneSt2[i]) cudaStreamDestroy(h->laneSt2[i]);
+        if (h->laneSt[i]) cudaStreamDestroy(h->laneSt[i]);
+    }
+    if (h->evSplit) cudaEventDestroy(h->evSplit);
     if (h->streamIn) cudaStreamDestroy(h->streamIn);
     if (h->streamOut) cudaStreamDestroy(h->streamOut);
+    if (h->streamCnt) cudaStreamDestroy(h->streamCnt);
+    for (int i = 0; i < 8; ++i)
+        if (h->evCnt[i]) cudaEventDestroy(h->evCnt[i]);
     if (h->evFork) cudaEventDestroy(h->evFork);
     if (h->evJoin) cudaEventDestroy(h->evJoin);
     if (h->stream2) cudaStreamDestroy(h->stream2);
@@ -581,7 +610,28 @@ extern "C" int orb_extract_batch_device(orb_extractor* h, int n, const uint8_t* 
                                        stride, cols, rows, cudaMemcpyDeviceToDevice, h->stream));
     }
     h->last_n = n;
-    CUDA_TRY(orbk_run_extract(P, n, reinterpret_cast<orb_keypoint_dev*>(d_kps), d_desc, cap, d_counts, h->streams(), maps, h->next_events()));
+    const int lanes = h->profiling ? 1 : std::min(h->lanes, std::max(1, n / 16));
+    if (lanes < 2) {
+        CUDA_TRY(orbk_run_extract(P, n, reinterpret_cast<orb_keypoint_dev*>(d_kps), d_desc, cap, d_counts, h->streams(), maps, h->next_events()));
+        return ORB_OK;
+    }
+    // independent slices of the batch on concurrent kernel lanes: one slice's launch gaps, wave tails and
+    // latency-bound phases (octree) are filled by the other slices' kernels
+    CUDA_TRY(cudaEventRecord(h->evSplit, h->stream));
+    const int per = (n + lanes - 1) / lanes;
+    for (int i = 0; i < lanes; ++i) {
+        const int f0 = i * per, nf = std::min(per, n - f0);
+        if (nf <= 0) break;
+        const OrbStreams ls = h->lane(i);
+        if (i > 0) CUDA_TRY(cudaStreamWaitEvent(ls.st, h->evSplit, 0));
+        const OrbPlan PS = plan_slice(P, f0);
+        CUDA_TRY(orbk_run_extract(PS, nf, reinterpret_cast<orb_keypoint_dev*>(d_kps) + (size_t)f0 * cap, d_desc + (size_t)f0 * cap * 32, cap,
+                                  d_counts + f0, ls, maps, nullptr));
+        if (i > 0) {
+            CUDA_TRY(cudaEventRecord(h->laneMerge[i], ls.st));
+            CUDA_TRY(cudaStreamWaitEvent(h->stream, h->laneMerge[i], 0));
+        }
+    }
     return ORB_OK;
 }
 
@@ -666,6 +716,7 @@ extern "C" int orb_extract_batch(orb_extractor* h, int n, const uint8_t* imgs, i
     CUDA_TRY(cudaEventRecord(h->evFree, h->stream));
     CUDA_TRY(cudaStreamWaitEvent(h->streamIn, h->evFree, 0));
     CUDA_TRY(cudaStreamWaitEvent(h->streamOut, h->evFree, 0));
+    CUDA_TRY(cudaStreamWaitEvent(h->streamCnt, h->evFree, 0));
     h->last_n = n;
     for (int c = 0; c < nchunks; ++c) {
         const int f0 = c * per, nf = std::min(per, n - f0);
@@ -684,20 +735,26 @@ extern "C" int orb_extract_batch(orb_extractor* h, int n, const uint8_t* imgs, i
                                            cudaMemcpyHostToDevice, h->streamIn));
         }
         CUDA_TRY(cudaEventRecord(h->evIn[c], h->streamIn));
-        CUDA_TRY(cudaStreamWaitEvent(h->stream, h->evIn[c], 0));
+        // consecutive chunks alternate between the kernel lanes so that their kernels overlap
+        const OrbStreams ls = h->lane(nchunks > 1 ? c % std::max(1, h->lanes) : 0);
+        if (ls.st != h->stream) CUDA_TRY(cudaStreamWaitEvent(ls.st, h->evFree, 0));
+        CUDA_TRY(cudaStreamWaitEvent(ls.st, h->evIn[c], 0));
         const OrbPlan P = plan_slice(h->plan, f0);
         CUDA_TRY(orbk_run_extract(P, nf, h->d_kps + (size_t)f0 * h->out_cap, h->d_desc + (size_t)f0 * h->out_cap * 32, h->out_cap,
-                                  h->d_counts + f0, h->streams(), h->d_maps, h->next_events()));
-        CUDA_TRY(cudaEventRecord(h->evDone[c], h->stream));
-        CUDA_TRY(cudaStreamWaitEvent(h->streamOut, h->evDone[c], 0));
-        CUDA_TRY(cudaMemcpyAsync(counts + f0, h->d_counts + f0, sizeof(int) * nf, cudaMemcpyDeviceToHost, h->streamOut));
+                                  h->d_counts + f0, ls, h->d_maps, h->next_events()));
+        CUDA_TRY(cudaEventRecord(h->evDone[c], ls.st));
+        if (ls.st != h->stream) CUDA_TRY(cudaStreamWaitEvent(h->stream, h->evDone[c], 0));  // the main stream stays the join point
+        // counts travel on their own small stream so that the bulk result copies of chunk c (issued below,
+        // once its counts are known) are not queued behind the kernels of later chunks
+        CUDA_TRY(cudaStreamWaitEvent(h->streamCnt, h->evDone[c], 0));
+        CUDA_TRY(cudaMemcpyAsync(counts + f0, h->d_counts + f0, sizeof(int) * nf, cudaMemcpyDeviceToHost, h->streamCnt));
+        CUDA_TRY(cudaEventRecord(h->evCnt[c], h->streamCnt));
     }
     // results: as each chunk's counts arrive, copy exactly the rows it produced
     int maxAll = 0;
     for (int c = 0; c < nchunks; ++c) {
         const int f0 = c * per, nf = std::min(per, n - f0);
-        CUDA_TRY(cudaEventRecord(h->evIn[c], h->streamOut));  // (reuse: marks "counts of chunk c are on the host")
-        CUDA_TRY(cudaEventSynchronize(h->evIn[c]));
+        CUDA_TRY(cudaEventSynchronize(h->evCnt[c]));  // counts of chunk c are on the host, its kernels are done
         int maxc = 0;
         for (int f = f0; f < f0 + nf; ++f) maxc = std::max(maxc, counts[f]);
         maxAll = std::max(maxAll, maxc);
