@@ -551,7 +551,7 @@ __device__ __forceinline__ unsigned long long cand_order(const OrbLevel& L, unsi
 // per-birth tables in transformed-index order and one block-wide prefix sum.
 // Problems it cannot take (deep p*) are flagged for the generic sort-based kernel below.
 // ------------------------------------------------------------------------------------------
-#define OCTF_THREADS 256
+#define OCTF_THREADS 1024
 #define OCTF_MAX_NODES 6144
 #define OCTF_MAX_TOTAL 8192
 #define OCTF_MAX_DEPTH 7
