@@ -962,26 +962,41 @@ __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ OrbPlan pl
     // smem byte column c of tile row r  <->  pixel (reflect(y0 - 3 + r), reflect(x0 - 16 + c));
     // staged as 16-byte vectors (18 per row) when the level rows are 16-byte aligned
     const bool vec_ok = ((L.pitch & 15) == 0) && ((((size_t)src) & 15) == 0);
-    for (int i = tid; i < rowsHere * (BLUR_SW / 4); i += 256) {
-        const int r = i / (BLUR_SW / 4), j = i - r * (BLUR_SW / 4);
+    // vectors jlo..jhi of a tile row lie completely inside the image row (x0 is a multiple of 256)
+    int jlo = x0 >= 16 ? 0 : 1;
+    int jhi = min((L.cols - x0) / 16, BLUR_SW / 4 - 1);  // x0 - 16 + 16 j + 15 < cols  <=>  j <= (cols - x0) / 16; may be < jlo
+    if (!vec_ok) { jlo = 0; jhi = -1; }
+    const int nvec = max(jhi - jlo + 1, 0);
+    // pass 1: the inside vectors, 16 bytes per thread
+    for (int i = tid; i < rowsHere * nvec; i += 256) {
+        const int r = i / nvec, j = jlo + (i - r * nvec);
         const int yy = reflect101(y0 - 3 + r, L.rows);
-        const uint8_t* row = src + (size_t)yy * L.pitch;
-        const int x = x0 - 16 + 16 * j;
-        uint4 v;
-        if (vec_ok && x >= 0 && x + 15 < L.cols) {
-            v = __ldg(reinterpret_cast<const uint4*>(row + x));
-        } else {
-            unsigned w[4] = {0u, 0u, 0u, 0u};
-            if (x + 15 >= -3 && x < L.cols + 3) {  // touches the 3-px halo or the image
+        *reinterpret_cast<uint4*>(&tile[r][4 * j]) = __ldg(reinterpret_cast<const uint4*>(src + (size_t)yy * L.pitch + (x0 - 16 + 16 * j)));
+    }
+    // pass 2: the words left and right of them (row ends of the image only): reflect-101 per byte
+    const int nleft = nvec ? 4 * jlo : BLUR_SW, nright = nvec ? BLUR_SW - 4 * (jhi + 1) : 0;
+    const int nb = nleft + nright;
+    for (int i = tid; i < rowsHere * nb; i += 256) {
+        const int r = i / nb, kk = i - r * nb;
+        const int k = kk < nleft ? kk : 4 * (jhi + 1) + (kk - nleft);
+        const int x = x0 - 16 + 4 * k;
+        unsigned w = 0;
+        if (x + 3 >= -3 && x < L.cols + 3) {  // touches the image or its 3-px halo
+            const int yy = reflect101(y0 - 3 + r, L.rows);
+            const uint8_t* row = src + (size_t)yy * L.pitch;
+            if (x >= 0 && x + 3 < L.cols) {
+                w = __ldg(reinterpret_cast<const unsigned*>(row + x));
+            } else {
 #pragma unroll
-                for (int b = 0; b < 16; ++b) {
-                    const int xx = x + b;
-                    if (xx >= -3 && xx < L.cols + 3) w[b >> 2] |= (unsigned)__ldg(row + reflect101(xx, L.cols)) << (8 * (b & 3));
+                for (int bb = 0; bb < 4; ++bb) {
+                    int xx = x + bb;
+                    xx = xx < 0 ? -xx : (xx >= L.cols ? 2 * L.cols - 2 - xx : xx);  // one reflection is enough within 3 px
+                    xx = min(max(xx, 0), L.cols - 1);                               // (degenerate tiny levels)
+                    w |= (unsigned)__ldg(row + xx) << (8 * bb);
                 }
             }
-            v = make_uint4(w[0], w[1], w[2], w[3]);
         }
-        *reinterpret_cast<uint4*>(&tile[r][4 * j]) = v;
+        tile[r][k] = w;
     }
     __syncthreads();
     const int q = tid & 63, g = tid >> 6;
@@ -1061,6 +1076,34 @@ __device__ __forceinline__ int cv_round_small(float v) {
     return __float_as_int(__fadd_rn(v, 12582912.f)) - 0x4B400000;
 }
 
+// sin and cos of x in [0, 2*pi] in double precision (fdlibm kernels after a two-constant reduction
+// by pi/2; error ~1 ulp of double), so that rounding to float gives the correctly rounded
+// cosf / sinf the reference gets from libm.  Much shorter than the general sincos().
+__device__ __forceinline__ void sincos_0_2pi(double x, double& s, double& c) {
+    const int q = __double2int_rn(x * 0.63661977236758134308);  // x * 2/pi
+    const double qd = (double)q;
+    double r = fma(-qd, 1.57079632679489655800e+00, x);
+    r = fma(-qd, 6.12323399573676603587e-17, r);
+    const double z = r * r;
+    double ps = 1.58969099521155010221e-10;
+    ps = fma(ps, z, -2.50507602534068634195e-08);
+    ps = fma(ps, z, 2.75573137070700676789e-06);
+    ps = fma(ps, z, -1.98412698298579493134e-04);
+    ps = fma(ps, z, 8.33333333332248946124e-03);
+    ps = fma(ps, z, -1.66666666666666324348e-01);
+    const double sr = fma(r * z, ps, r);
+    double pc = -1.13596475577881948265e-11;
+    pc = fma(pc, z, 2.08757232129817482790e-09);
+    pc = fma(pc, z, -2.75573143513906633035e-07);
+    pc = fma(pc, z, 2.48015872894767294178e-05);
+    pc = fma(pc, z, -1.38888888888741095749e-03);
+    pc = fma(pc, z, 4.16666666666666019037e-02);
+    const double cr = fma(z * z, pc, fma(-0.5, z, 1.0));
+    const double s1 = (q & 1) ? cr : sr, c1 = (q & 1) ? sr : cr;
+    s = (q & 2) ? -s1 : s1;
+    c = ((q + 1) & 2) ? -c1 : c1;
+}
+
 // IC_Angle weight table (built on the host by orbk_build_ic_table, plan.icTab):
 // entry [a][v + 15][k] for patch alignment a = (x - 15) & 3, row v, aligned word k (9 words
 // cover u = -15 - a .. 20 - a): .x = four signed bytes u (0 outside the disc |u| <= umax[|v|]),
@@ -1111,15 +1154,16 @@ __global__ void __launch_bounds__(256) k_describe(const __grid_constant__ OrbPla
                             (unsigned)r3 * pw + (unsigned)kk;
         const int2* tab = plan.icTab + a * (31 * 9) + lane;
         if (lane < 27) {
+            const size_t step = (size_t)3 * pw;  // three rows down, in words
 #pragma unroll
             for (int it = 0; it < 11; ++it) {
-                const int vr = it * 3 + r3;
-                if (vr < 31) {
-                    const unsigned w = __ldg(p + (unsigned)(it * 3) * pw);
+                if (it < 10 || r3 == 0) {  // row it*3 + r3 < 31
+                    const unsigned w = __ldg(p);
                     const int2 t = __ldg(tab + it * 27);
                     m10 = dp4a_us(w, t.x, m10);
-                    m01 += (vr - 15) * (int)__dp4a(w, (unsigned)t.y, 0u);
+                    m01 += (it * 3 + r3 - 15) * (int)__dp4a(w, (unsigned)t.y, 0u);
                 }
+                p += step;
             }
         }
         for (int sft = 16; sft > 0; sft >>= 1) {
@@ -1133,7 +1177,7 @@ __global__ void __launch_bounds__(256) k_describe(const __grid_constant__ OrbPla
     const float factorPI = (float)(3.141592653589793238462643383279502884 / 180.f);
     const float rad = __fmul_rn(angle, factorPI);
     double sd, cd;
-    sincos((double)rad, &sd, &cd);
+    sincos_0_2pi((double)rad, sd, cd);
     const float a = (float)cd, b = (float)sd;
     // The 182 x 2 samples lie within +-18 px of the keypoint.  Gathering them straight from global
     // memory costs one L1 wavefront per touched sector per load; instead each warp stages its
