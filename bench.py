@@ -250,13 +250,38 @@ def main():
     ex.set_profiling(False)
     clocks = sampler.stop() if rank == 0 else None
 
-    # ---- end to end through the host-buffer C ABI (e2e)
+    # ---- end to end through the host-buffer C ABI (e2e): pinned host frames in, keypoints + descriptors
+    # back in pinned host memory, every step.  (a) the synchronous call orb_extract_batch, one step at a
+    # time; (b) the asynchronous pair orb_extract_batch_submit / _wait with two steps in flight (step i+1's
+    # upload overlaps step i's kernels, step i's download overlaps step i+1's kernels) -- the serving form,
+    # reported as e2e; both move the same bytes per step inside the timed region.
     for i in range(W):
         step_host(i)
     barrier()
     t0 = time.perf_counter()
     for i in range(K):
         step_host(W + i)
+    barrier()
+    e2e_sync_s = time.perf_counter() - t0
+    h_kps2 = torch.empty_like(h_kps).pin_memory()
+    h_desc2 = torch.empty_like(h_desc).pin_memory()
+    h_counts2 = torch.empty_like(h_counts).pin_memory()
+    outs = [(h_kps, h_desc, h_counts), (h_kps2, h_desc2, h_counts2)]
+
+    def submit(i):
+        o = outs[i & 1]
+        return ex.submit_batch_pinned(pinned_in[i % R], o[0], o[1], o[2], cap)
+
+    for i in range(W):
+        ex.wait_batch(submit(i))
+    barrier()
+    t0 = time.perf_counter()
+    pending = submit(0)
+    for i in range(1, K):
+        nxt = submit(i)
+        ex.wait_batch(pending)
+        pending = nxt
+    ex.wait_batch(pending)
     barrier()
     e2e_s = time.perf_counter() - t0
     maxc = int(h_counts.max().item())
@@ -294,9 +319,9 @@ def main():
     match_ms = m0.elapsed_time(m1) / MREP
 
     if world > 1:
-        t = torch.tensor([ms_total, e2e_s, match_ms], dtype=torch.float64, device="cuda")
+        t = torch.tensor([ms_total, e2e_s, match_ms, e2e_sync_s], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total, e2e_s, match_ms = float(t[0].item()), float(t[1].item()), float(t[2].item())
+        ms_total, e2e_s, match_ms, e2e_sync_s = float(t[0].item()), float(t[1].item()), float(t[2].item()), float(t[3].item())
 
     if rank == 0:
         frames = B * K * world
@@ -326,20 +351,27 @@ def main():
                        "frames_per_gpu_per_step": B, "keypoints_per_frame": k_mean,
                        "l2": f"inputs rotate through {R} distinct batches ({R * B * ROWS * pitch / 1e6:.0f} MB > 126 MB L2)"},
             "roofline": {"bound": "hbm", "kernel": "k_" + dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_kind,
+                         "frac": achieved / peak,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of k_detect, ncu --set full (profiles/r01f: 2 x 32-frame launches)
+                         "traffic": 87.9e6 if dom == "detect" else None, "traffic_source": "profiles/r01f_ncu_summary.txt",
+                         "peak_source": peak_kind,
                          "algo_bytes_per_launch": algo, "launch_ms": per_launch_ms,
                          "stage_ms_per_step": {k: v / max(ncalls, 1) for k, v in stage_ms.items()},
                          "stage_note": "stage times from a second pass of the same steps with the stages serialised on one stream; "
                                        "in the timed region the blur overlaps detect + octree on a second stream",
                          "path": {"algo_bytes_per_step": path_bytes, "achieved": path_gbs, "frac": path_gbs / peak}},
-            "e2e": {"value": frames / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "e2e": {"value": frames / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "api": "orb_extract_batch_submit/_wait, two 64-frame steps in flight, pinned host buffers",
+                    "sync_call_value": frames / e2e_sync_s, "sync_call_api": "orb_extract_batch, one step at a time"},
             "gpu_launches": int(launches), "clocks": clocks,
             "hamming": {"metric": "Hamming pairs/s (brute force, best + second best)", "value": world * NP * NQ * NQ / (match_ms * 1e-3),
                         "unit": "pairs/s", "workload": f"{NP} keyframe pairs x {NQ} x {NQ} descriptors per GPU (BASELINE config 4)",
                         "ms_per_launch": match_ms,
                         "algo_bytes_per_launch": NP * (32 * 2 * NQ + 12 * NQ),
                         "hbm_frac": NP * (32 * 2 * NQ + 12 * NQ) / (match_ms * 1e-3) / 1e9 / peak,
-                        "popc_per_s": world * 8 * NP * NQ * NQ / (match_ms * 1e-3)},
+                        "popc_per_s": world * 6 * NP * NQ * NQ / (match_ms * 1e-3),
+                        "note": "POPC-pipe bound (quarter-rate pipe, ~4.5e12 POPC/s per GPU); 6 POPC per pair because words 6-7 of "
+                                "this fork's descriptors are zero (checked on the data, 8 otherwise)"},
         }
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1

@@ -95,6 +95,17 @@ int orb_extract_batch(orb_extractor* h, int n, const uint8_t* imgs, int rows, in
                       size_t stride, size_t frame_stride, orb_keypoint* kps, uint8_t* desc,
                       int cap, int* counts);
 
+/* Asynchronous form of orb_extract_batch for throughput serving: submit enqueues the copies and
+ * kernels of one batch and returns a ticket; wait blocks until that batch's keypoints, descriptors
+ * and counts are in the caller's buffers.  Up to two batches may be in flight per handle: the H2D
+ * copies of batch i+1 run while batch i computes and the D2H copies of batch i run while batch
+ * i+1 computes.  The buffers must stay valid (and the inputs unchanged) until wait returns.
+ * orb_extract_batch == submit + wait. */
+int orb_extract_batch_submit(orb_extractor* h, int n, const uint8_t* imgs, int rows, int cols,
+                             size_t stride, size_t frame_stride, orb_keypoint* kps, uint8_t* desc,
+                             int cap, int* counts, int* ticket);
+int orb_extract_batch_wait(orb_extractor* h, int ticket);
+
 /* Same, with every buffer resident in device memory (inputs already in HBM; no copies).
  * Asynchronous on the handle's stream; call orb_extractor_sync before reading results
  * from another stream.  d_imgs needs stride % 16 == 0 and 16-byte aligned base. */

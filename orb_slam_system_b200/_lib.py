@@ -53,7 +53,7 @@ _lib = None
 # every symbol include/orb_b200.h declares
 EXPORTS = [
     "orb_extractor_create", "orb_extractor_destroy", "orb_extractor_tables",
-    "orb_extractor_keypoint_bound", "orb_extract", "orb_extract_batch", "orb_extract_batch_device",
+    "orb_extractor_keypoint_bound", "orb_extract", "orb_extract_batch", "orb_extract_batch_submit", "orb_extract_batch_wait", "orb_extract_batch_device",
     "orb_extractor_sync", "orb_extractor_stream", "orb_get_pyramid_level",
     "orb_extractor_level_stats", "orb_extractor_set_profiling", "orb_extractor_stage_times",
     "orb_stage_name", "orb_matcher_create", "orb_matcher_destroy", "orb_match_all",
@@ -79,6 +79,8 @@ def lib():
         L.orb_extractor_keypoint_bound.argtypes = [vp, i32, i32, C.POINTER(i32)]
         L.orb_extract.argtypes = [vp, vp, i32, i32, sz, vp, vp, i32, C.POINTER(i32)]
         L.orb_extract_batch.argtypes = [vp, i32, vp, i32, i32, sz, sz, vp, vp, i32, vp]
+        L.orb_extract_batch_submit.argtypes = [vp, i32, vp, i32, i32, sz, sz, vp, vp, i32, vp, C.POINTER(i32)]
+        L.orb_extract_batch_wait.argtypes = [vp, i32]
         L.orb_extract_batch_device.argtypes = [vp, i32, vp, i32, i32, sz, sz, vp, vp, i32, vp]
         L.orb_extractor_sync.argtypes = [vp]
         L.orb_extractor_stream.argtypes = [vp]

@@ -137,9 +137,26 @@ struct orb_extractor {
     int lanes = 2;
     // host-buffer pipeline: copies in and out run on their own streams, chunk by chunk
     cudaStream_t streamIn = nullptr, streamOut = nullptr, streamCnt = nullptr;
-    cudaEvent_t evCnt[8] = {};
-    enum { MAX_CHUNKS = 8 };
-    cudaEvent_t evIn[MAX_CHUNKS] = {}, evDone[MAX_CHUNKS] = {}, evFree = nullptr;
+    enum { MAX_CHUNKS = 8, NUM_SLOTS = 2 };
+    cudaEvent_t evFree = nullptr;
+    // One in-flight host batch: its landing / result staging buffers, its events, and where the results go.
+    struct HostSlot {
+        bool busy = false;
+        uint8_t* d_dense = nullptr;  // landing buffer for densely packed host frames (one linear copy per chunk)
+        size_t dense_cap = 0;
+        orb_keypoint_dev* d_kps = nullptr;
+        uint8_t* d_desc = nullptr;
+        int* d_counts = nullptr;
+        int out_cap = 0;
+        cudaEvent_t evIn[MAX_CHUNKS] = {}, evDone[MAX_CHUNKS] = {}, evCnt[MAX_CHUNKS] = {};
+        // the submitted call
+        int n = 0, cap = 0, nchunks = 0, per = 0;
+        orb_keypoint* kps = nullptr;
+        uint8_t* desc = nullptr;
+        int* counts = nullptr;
+        int* h_status = nullptr;  // pinned, max_batch ints: octree status flags of the submitted batch
+    } slot[NUM_SLOTS];
+    int next_slot = 0;
     OrbStreams streams() const { return OrbStreams{stream, stream2, evFork, evJoin}; }
     int max_batch = 1;
     OrbPlan plan;            // current shape (plan.rows == 0: none)
@@ -150,13 +167,6 @@ struct orb_extractor {
     const uint8_t* user_base = nullptr;
     std::vector<void*> allocs;  // everything the plan points at
     uint8_t* level0 = nullptr;  // internal level-0 buffer (host-input path)
-    uint8_t* d_dense = nullptr; // landing buffer for densely packed host frames (one linear copy per chunk)
-    size_t dense_cap = 0;
-    // output staging for the host-buffer API
-    orb_keypoint_dev* d_kps = nullptr;
-    uint8_t* d_desc = nullptr;
-    int* d_counts = nullptr;
-    int out_cap = 0;
     int last_n = 0;
     std::vector<int> h_status;
     // per-stage CUDA-event records (orb_extractor_set_profiling)
@@ -411,17 +421,19 @@ static int build_plan(orb_extractor* h, int rows, int cols) {
     return ORB_OK;
 }
 
-static int ensure_out(orb_extractor* h, int cap) {
-    if (cap <= h->out_cap) return ORB_OK;
-    CUDA_TRY(cudaStreamSynchronize(h->stream));
-    if (h->d_kps) cudaFree(h->d_kps);
-    if (h->d_desc) cudaFree(h->d_desc);
-    h->d_kps = nullptr;
-    h->d_desc = nullptr;
-    h->out_cap = 0;
-    CUDA_TRY(cudaMalloc((void**)&h->d_kps, (size_t)h->max_batch * cap * sizeof(orb_keypoint_dev)));
-    CUDA_TRY(cudaMalloc((void**)&h->d_desc, (size_t)h->max_batch * cap * 32));
-    h->out_cap = cap;
+static int ensure_out(orb_extractor* h, orb_extractor::HostSlot& S, int cap) {
+    if (!S.d_counts) CUDA_TRY(cudaMalloc((void**)&S.d_counts, sizeof(int) * h->max_batch));
+    if (!S.h_status) CUDA_TRY(cudaMallocHost((void**)&S.h_status, sizeof(int) * h->max_batch));
+    if (cap <= S.out_cap) return ORB_OK;
+    CUDA_TRY(cudaStreamSynchronize(h->streamOut));
+    if (S.d_kps) cudaFree(S.d_kps);
+    if (S.d_desc) cudaFree(S.d_desc);
+    S.d_kps = nullptr;
+    S.d_desc = nullptr;
+    S.out_cap = 0;
+    CUDA_TRY(cudaMalloc((void**)&S.d_kps, (size_t)h->max_batch * cap * sizeof(orb_keypoint_dev)));
+    CUDA_TRY(cudaMalloc((void**)&S.d_desc, (size_t)h->max_batch * cap * 32));
+    S.out_cap = cap;
     return ORB_OK;
 }
 
@@ -459,13 +471,13 @@ extern "C" int orb_extractor_create(const orb_params* params, int max_rows, int 
     if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&h->streamIn, cudaStreamNonBlocking);
     if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&h->streamOut, cudaStreamNonBlocking);
     if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&h->streamCnt, cudaStreamNonBlocking);
-    for (int i = 0; i < 8 && ce == cudaSuccess; ++i) ce = cudaEventCreateWithFlags(&h->evCnt[i], cudaEventDisableTiming);
-    for (int i = 0; i < orb_extractor::MAX_CHUNKS && ce == cudaSuccess; ++i) {
-        ce = cudaEventCreateWithFlags(&h->evIn[i], cudaEventDisableTiming);
-        if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&h->evDone[i], cudaEventDisableTiming);
-    }
+    for (int k = 0; k < orb_extractor::NUM_SLOTS; ++k)
+        for (int i = 0; i < orb_extractor::MAX_CHUNKS && ce == cudaSuccess; ++i) {
+            ce = cudaEventCreateWithFlags(&h->slot[k].evIn[i], cudaEventDisableTiming);
+            if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&h->slot[k].evDone[i], cudaEventDisableTiming);
+            if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&h->slot[k].evCnt[i], cudaEventDisableTiming);
+        }
     if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&h->evFree, cudaEventDisableTiming);
-    if (ce == cudaSuccess) ce = cudaMalloc((void**)&h->d_counts, sizeof(int) * max_batch);
     if (ce != cudaSuccess) {
         orb_extractor_destroy(h);
         return fail(ORB_ERR_CUDA, "stream/event/alloc setup: %s", cudaGetErrorString(ce));
@@ -487,13 +499,18 @@ extern "C" void orb_extractor_destroy(orb_extractor* h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     free_plan(h);
     h->clear_events();
-    if (h->d_kps) cudaFree(h->d_kps);
-    if (h->d_desc) cudaFree(h->d_desc);
-    if (h->d_counts) cudaFree(h->d_counts);
-    if (h->d_dense) cudaFree(h->d_dense);
-    for (int i = 0; i < orb_extractor::MAX_CHUNKS; ++i) {
-        if (h->evIn[i]) cudaEventDestroy(h->evIn[i]);
-        if (h->evDone[i]) cudaEventDestroy(h->evDone[i]);
+    for (int k = 0; k < orb_extractor::NUM_SLOTS; ++k) {
+        orb_extractor::HostSlot& S = h->slot[k];
+        if (S.d_kps) cudaFree(S.d_kps);
+        if (S.d_desc) cudaFree(S.d_desc);
+        if (S.d_counts) cudaFree(S.d_counts);
+        if (S.d_dense) cudaFree(S.d_dense);
+        if (S.h_status) cudaFreeHost(S.h_status);
+        for (int i = 0; i < orb_extractor::MAX_CHUNKS; ++i) {
+            if (S.evIn[i]) cudaEventDestroy(S.evIn[i]);
+            if (S.evDone[i]) cudaEventDestroy(S.evDone[i]);
+            if (S.evCnt[i]) cudaEventDestroy(S.evCnt[i]);
+        }
     }
     if (h->evFree) cudaEventDestroy(h->evFree);
     for (int i = 1; i < orb_extractor::MAX_LANES; ++i) {
@@ -507,8 +524,6 @@ extern "C" void orb_extractor_destroy(orb_extractor* h) {
     if (h->streamIn) cudaStreamDestroy(h->streamIn);
     if (h->streamOut) cudaStreamDestroy(h->streamOut);
     if (h->streamCnt) cudaStreamDestroy(h->streamCnt);
-    for (int i = 0; i < 8; ++i)
-        if (h->evCnt[i]) cudaEventDestroy(h->evCnt[i]);
     if (h->evFork) cudaEventDestroy(h->evFork);
     if (h->evJoin) cudaEventDestroy(h->evJoin);
     if (h->stream2) cudaStreamDestroy(h->stream2);
@@ -679,100 +694,147 @@ extern "C" const char* orb_stage_name(int stage) {
     return stage >= 0 && stage < ORB_STAGES ? names[stage] : "";
 }
 
-extern "C" int orb_extract_batch(orb_extractor* h, int n, const uint8_t* imgs, int rows, int cols, size_t stride,
-                                 size_t frame_stride, orb_keypoint* kps, uint8_t* desc, int cap, int* counts) {
-    if (!h || !counts) return fail(ORB_ERR_INVALID, "null argument");
+extern "C" int orb_extract_batch_submit(orb_extractor* h, int n, const uint8_t* imgs, int rows, int cols, size_t stride,
+                                        size_t frame_stride, orb_keypoint* kps, uint8_t* desc, int cap, int* counts, int* ticket) {
+    if (!h || !counts || !ticket) return fail(ORB_ERR_INVALID, "null argument");
+    *ticket = -1;
     if (n < 0 || n > h->max_batch) return fail(ORB_ERR_INVALID, "n=%d exceeds max_batch=%d", n, h->max_batch);
     if (n == 0) return ORB_OK;
-    if (!imgs || rows <= 0 || cols <= 0) {
+    if (!imgs || rows <= 0 || cols <= 0) {  // empty image: silent return (ORBextractor.cc:444-445)
         for (int f = 0; f < n; ++f) counts[f] = 0;
         return ORB_OK;
     }
     if (!kps || !desc || cap <= 0) return fail(ORB_ERR_INVALID, "null output buffer");
     if (stride < (size_t)cols) return fail(ORB_ERR_INVALID, "stride < cols");
+    orb_extractor::HostSlot& S = h->slot[h->next_slot];
+    if (S.busy) return fail(ORB_ERR_INVALID, "two batches are already in flight: call orb_extract_batch_wait first");
     CUDA_TRY(cudaSetDevice(h->device));
+    if (h->plan.rows != rows || h->plan.cols != cols) {
+        for (int k = 0; k < orb_extractor::NUM_SLOTS; ++k)
+            if (h->slot[k].busy) return fail(ORB_ERR_INVALID, "cannot change the image shape while a batch is in flight");
+    }
     int rc = build_plan(h, rows, cols);
     if (rc != ORB_OK) return rc;
-    rc = ensure_out(h, cap);
+    rc = ensure_out(h, S, cap);
     if (rc != ORB_OK) return rc;
     const OrbLevel& L0 = h->plan.lv[0];
-    // Pipeline over chunks of frames: H2D copy (streamIn) -> kernels (stream, stream2) -> counts and
-    // results D2H (streamOut), so that PCIe in, compute and PCIe out of neighbouring chunks overlap.
-    // While per-stage profiling is on, one chunk is used (stage times describe whole-batch launches).
-    int nchunks = h->profiling ? 1 : std::min<int>(orb_extractor::MAX_CHUNKS, std::max(1, n / 16));
+    // Pipeline over chunks of frames: H2D copy (streamIn) -> kernels (kernel lanes) -> counts (streamCnt) and
+    // results D2H (streamOut, issued by orb_extract_batch_wait), so that PCIe in, compute and PCIe out of
+    // neighbouring chunks -- and of the neighbouring batch in flight -- overlap.  While per-stage profiling is
+    // on, one chunk is used (stage times then describe whole-batch launches).
+    const int chunkFrames = getenv("ORB_B200_CHUNK") ? std::max(1, atoi(getenv("ORB_B200_CHUNK"))) : 16;
+    int nchunks = h->profiling ? 1 : std::min<int>(orb_extractor::MAX_CHUNKS, std::max(1, n / chunkFrames));
     const int per = (n + nchunks - 1) / nchunks;
     nchunks = (n + per - 1) / per;
     const bool dense = stride == (size_t)cols && frame_stride == (size_t)rows * cols && ((uintptr_t)imgs & 3) == 0 && cols >= 4;
-    if (dense && h->dense_cap < (size_t)n * rows * cols + 16) {
+    if (dense && S.dense_cap < (size_t)n * rows * cols + 16) {
         CUDA_TRY(cudaStreamSynchronize(h->streamIn));
-        if (h->d_dense) cudaFree(h->d_dense);
-        h->d_dense = nullptr;
-        h->dense_cap = 0;
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        if (S.d_dense) cudaFree(S.d_dense);
+        S.d_dense = nullptr;
+        S.dense_cap = 0;
         const size_t want = (size_t)h->max_batch * rows * cols + 16;
-        CUDA_TRY(cudaMalloc((void**)&h->d_dense, want));
-        h->dense_cap = want;
+        CUDA_TRY(cudaMalloc((void**)&S.d_dense, want));
+        S.dense_cap = want;
     }
-    // the input buffer may still be read by the previous call's kernels
+    // everything enqueued so far on the main stream (the previous batch's kernels: every lane joins there)
+    // must finish before this batch touches the shared level / scratch buffers -- including the small
+    // count / status copies of a batch still in flight, which read the shared status flags
+    for (int k = 0; k < orb_extractor::NUM_SLOTS; ++k)
+        if (h->slot[k].busy)
+            for (int c = 0; c < h->slot[k].nchunks; ++c) CUDA_TRY(cudaStreamWaitEvent(h->stream, h->slot[k].evCnt[c], 0));
     CUDA_TRY(cudaEventRecord(h->evFree, h->stream));
-    CUDA_TRY(cudaStreamWaitEvent(h->streamIn, h->evFree, 0));
-    CUDA_TRY(cudaStreamWaitEvent(h->streamOut, h->evFree, 0));
-    CUDA_TRY(cudaStreamWaitEvent(h->streamCnt, h->evFree, 0));
+    if (!dense) CUDA_TRY(cudaStreamWaitEvent(h->streamIn, h->evFree, 0));  // non-dense copies write level 0 directly
     h->last_n = n;
     for (int c = 0; c < nchunks; ++c) {
         const int f0 = c * per, nf = std::min(per, n - f0);
-        if (dense) {
-            // densely packed frames: one linear copy, then the pitch conversion on the device
-            uint8_t* land = h->d_dense + (size_t)f0 * rows * cols;
-            CUDA_TRY(cudaMemcpyAsync(land, imgs + (size_t)f0 * frame_stride, (size_t)nf * rows * cols, cudaMemcpyHostToDevice, h->streamIn));
-            CUDA_TRY(orbk_repitch(land, nf, rows, cols, h->level0 + f0 * L0.plane, L0.pitch, L0.plane, h->streamIn));
-        } else if (nf == 1 || frame_stride == stride * (size_t)rows) {
-            // frames are consecutive rows on both sides (device plane == pitch * rows): one 2D copy
-            CUDA_TRY(cudaMemcpy2DAsync(h->level0 + f0 * L0.plane, L0.pitch, imgs + f0 * frame_stride, stride, cols, (size_t)rows * nf,
-                                       cudaMemcpyHostToDevice, h->streamIn));
-        } else {
-            for (int f = f0; f < f0 + nf; ++f)
-                CUDA_TRY(cudaMemcpy2DAsync(h->level0 + f * L0.plane, L0.pitch, imgs + f * frame_stride, stride, cols, rows,
-                                           cudaMemcpyHostToDevice, h->streamIn));
-        }
-        CUDA_TRY(cudaEventRecord(h->evIn[c], h->streamIn));
-        // consecutive chunks alternate between the kernel lanes so that their kernels overlap
         const OrbStreams ls = h->lane(nchunks > 1 ? c % std::max(1, h->lanes) : 0);
         if (ls.st != h->stream) CUDA_TRY(cudaStreamWaitEvent(ls.st, h->evFree, 0));
-        CUDA_TRY(cudaStreamWaitEvent(ls.st, h->evIn[c], 0));
+        if (dense) {
+            // densely packed frames: one linear copy into this batch's own landing buffer (it may run while the
+            // previous batch still computes), then the pitch conversion on the kernel lane
+            uint8_t* land = S.d_dense + (size_t)f0 * rows * cols;
+            CUDA_TRY(cudaMemcpyAsync(land, imgs + (size_t)f0 * frame_stride, (size_t)nf * rows * cols, cudaMemcpyHostToDevice, h->streamIn));
+            CUDA_TRY(cudaEventRecord(S.evIn[c], h->streamIn));
+            CUDA_TRY(cudaStreamWaitEvent(ls.st, S.evIn[c], 0));
+            CUDA_TRY(orbk_repitch(land, nf, rows, cols, h->level0 + f0 * L0.plane, L0.pitch, L0.plane, ls.st));
+        } else {
+            if (nf == 1 || frame_stride == stride * (size_t)rows) {
+                // frames are consecutive rows on both sides (device plane == pitch * rows): one 2D copy
+                CUDA_TRY(cudaMemcpy2DAsync(h->level0 + f0 * L0.plane, L0.pitch, imgs + f0 * frame_stride, stride, cols, (size_t)rows * nf,
+                                           cudaMemcpyHostToDevice, h->streamIn));
+            } else {
+                for (int f = f0; f < f0 + nf; ++f)
+                    CUDA_TRY(cudaMemcpy2DAsync(h->level0 + f * L0.plane, L0.pitch, imgs + f * frame_stride, stride, cols, rows,
+                                               cudaMemcpyHostToDevice, h->streamIn));
+            }
+            CUDA_TRY(cudaEventRecord(S.evIn[c], h->streamIn));
+            CUDA_TRY(cudaStreamWaitEvent(ls.st, S.evIn[c], 0));
+        }
         const OrbPlan P = plan_slice(h->plan, f0);
-        CUDA_TRY(orbk_run_extract(P, nf, h->d_kps + (size_t)f0 * h->out_cap, h->d_desc + (size_t)f0 * h->out_cap * 32, h->out_cap,
-                                  h->d_counts + f0, ls, h->d_maps, h->next_events()));
-        CUDA_TRY(cudaEventRecord(h->evDone[c], ls.st));
-        if (ls.st != h->stream) CUDA_TRY(cudaStreamWaitEvent(h->stream, h->evDone[c], 0));  // the main stream stays the join point
-        // counts travel on their own small stream so that the bulk result copies of chunk c (issued below,
-        // once its counts are known) are not queued behind the kernels of later chunks
-        CUDA_TRY(cudaStreamWaitEvent(h->streamCnt, h->evDone[c], 0));
-        CUDA_TRY(cudaMemcpyAsync(counts + f0, h->d_counts + f0, sizeof(int) * nf, cudaMemcpyDeviceToHost, h->streamCnt));
-        CUDA_TRY(cudaEventRecord(h->evCnt[c], h->streamCnt));
+        CUDA_TRY(orbk_run_extract(P, nf, S.d_kps + (size_t)f0 * S.out_cap, S.d_desc + (size_t)f0 * S.out_cap * 32, S.out_cap,
+                                  S.d_counts + f0, ls, h->d_maps, h->next_events()));
+        CUDA_TRY(cudaEventRecord(S.evDone[c], ls.st));
+        if (ls.st != h->stream) CUDA_TRY(cudaStreamWaitEvent(h->stream, S.evDone[c], 0));  // the main stream stays the join point
+        // counts (and the octree status flags) travel on their own small stream so that the bulk result copies
+        // of chunk c -- issued once its counts are known -- are not queued behind the kernels of later chunks
+        CUDA_TRY(cudaStreamWaitEvent(h->streamCnt, S.evDone[c], 0));
+        CUDA_TRY(cudaMemcpyAsync(counts + f0, S.d_counts + f0, sizeof(int) * nf, cudaMemcpyDeviceToHost, h->streamCnt));
+        CUDA_TRY(cudaMemcpyAsync(S.h_status + f0, h->plan.status + f0, sizeof(int) * nf, cudaMemcpyDeviceToHost, h->streamCnt));
+        CUDA_TRY(cudaEventRecord(S.evCnt[c], h->streamCnt));
     }
+    S.busy = true;
+    S.n = n;
+    S.cap = cap;
+    S.nchunks = nchunks;
+    S.per = per;
+    S.kps = kps;
+    S.desc = desc;
+    S.counts = counts;
+    *ticket = h->next_slot;
+    h->next_slot = (h->next_slot + 1) % orb_extractor::NUM_SLOTS;
+    return ORB_OK;
+}
+
+extern "C" int orb_extract_batch_wait(orb_extractor* h, int ticket) {
+    if (!h) return fail(ORB_ERR_INVALID, "null handle");
+    if (ticket < 0) return ORB_OK;  // nothing was submitted (empty batch)
+    if (ticket >= orb_extractor::NUM_SLOTS || !h->slot[ticket].busy) return fail(ORB_ERR_INVALID, "bad ticket");
+    orb_extractor::HostSlot& S = h->slot[ticket];
+    S.busy = false;
+    CUDA_TRY(cudaSetDevice(h->device));
     // results: as each chunk's counts arrive, copy exactly the rows it produced
-    int maxAll = 0;
-    for (int c = 0; c < nchunks; ++c) {
-        const int f0 = c * per, nf = std::min(per, n - f0);
-        CUDA_TRY(cudaEventSynchronize(h->evCnt[c]));  // counts of chunk c are on the host, its kernels are done
+    int maxAll = 0, bad = -1;
+    for (int c = 0; c < S.nchunks; ++c) {
+        const int f0 = c * S.per, nf = std::min(S.per, S.n - f0);
+        CUDA_TRY(cudaEventSynchronize(S.evCnt[c]));  // counts of chunk c are on the host, its kernels are done
         int maxc = 0;
-        for (int f = f0; f < f0 + nf; ++f) maxc = std::max(maxc, counts[f]);
+        for (int f = f0; f < f0 + nf; ++f) {
+            maxc = std::max(maxc, S.counts[f]);
+            if (S.h_status[f] && bad < 0) bad = f;
+        }
         maxAll = std::max(maxAll, maxc);
-        const int w = std::min(maxc, cap);
+        const int w = std::min(maxc, S.cap);
         if (w > 0) {
-            CUDA_TRY(cudaMemcpy2DAsync(kps + (size_t)f0 * cap, (size_t)cap * sizeof(orb_keypoint), h->d_kps + (size_t)f0 * h->out_cap,
-                                       (size_t)h->out_cap * sizeof(orb_keypoint), (size_t)w * sizeof(orb_keypoint), nf,
+            CUDA_TRY(cudaMemcpy2DAsync(S.kps + (size_t)f0 * S.cap, (size_t)S.cap * sizeof(orb_keypoint), S.d_kps + (size_t)f0 * S.out_cap,
+                                       (size_t)S.out_cap * sizeof(orb_keypoint), (size_t)w * sizeof(orb_keypoint), nf,
                                        cudaMemcpyDeviceToHost, h->streamOut));
-            CUDA_TRY(cudaMemcpy2DAsync(desc + (size_t)f0 * cap * 32, (size_t)cap * 32, h->d_desc + (size_t)f0 * h->out_cap * 32,
-                                       (size_t)h->out_cap * 32, (size_t)w * 32, nf, cudaMemcpyDeviceToHost, h->streamOut));
+            CUDA_TRY(cudaMemcpy2DAsync(S.desc + (size_t)f0 * S.cap * 32, (size_t)S.cap * 32, S.d_desc + (size_t)f0 * S.out_cap * 32,
+                                       (size_t)S.out_cap * 32, (size_t)w * 32, nf, cudaMemcpyDeviceToHost, h->streamOut));
         }
     }
     CUDA_TRY(cudaStreamSynchronize(h->streamOut));
-    // later work on the main stream (next call, pyramid read-back) must see the copies done
-    rc = check_status(h, n);  // synchronises the main stream
-    if (rc != ORB_OK) return rc;
-    if (maxAll > cap) return fail(ORB_ERR_CAPACITY, "frame needs %d keypoints, cap is %d", maxAll, cap);
+    if (bad >= 0) return fail(ORB_ERR_UNSEPARABLE, "frame %d: octree cannot separate its keys (reference would not terminate)", bad);
+    if (maxAll > S.cap) return fail(ORB_ERR_CAPACITY, "frame needs %d keypoints, cap is %d", maxAll, S.cap);
     return ORB_OK;
+}
+
+extern "C" int orb_extract_batch(orb_extractor* h, int n, const uint8_t* imgs, int rows, int cols, size_t stride,
+                                 size_t frame_stride, orb_keypoint* kps, uint8_t* desc, int cap, int* counts) {
+    int ticket = -1;
+    int rc = orb_extract_batch_submit(h, n, imgs, rows, cols, stride, frame_stride, kps, desc, cap, counts, &ticket);
+    if (rc != ORB_OK) return rc;
+    return orb_extract_batch_wait(h, ticket);
 }
 
 extern "C" int orb_extract(orb_extractor* h, const uint8_t* img, int rows, int cols, size_t stride, orb_keypoint* kps,

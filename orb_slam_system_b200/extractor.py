@@ -114,6 +114,20 @@ class ORBextractor:
                                       ptr(kps), ptr(desc), cap, ptr(counts)))
         self._last_frames = n
 
+    def submit_batch_pinned(self, images, kps, desc, counts, cap):
+        """Asynchronous extract_batch_pinned: returns a ticket for wait_batch; two batches may be in flight."""
+        n, rows, cols = images.shape
+        t = C.c_int(-1)
+        check(lib().orb_extract_batch_submit(self._h, n, ptr(images), rows, cols,
+                                             int(images.stride(1) if hasattr(images, "stride") else images.strides[1]),
+                                             int(images.stride(0) if hasattr(images, "stride") else images.strides[0]),
+                                             ptr(kps), ptr(desc), cap, ptr(counts), C.byref(t)))
+        self._last_frames = n
+        return t.value
+
+    def wait_batch(self, ticket):
+        check(lib().orb_extract_batch_wait(self._h, ticket))
+
     def extract_batch_device(self, d_images, d_kps, d_desc, d_counts, cap):
         """Device-resident batch: torch CUDA tensors (uint8 [n, rows, pitch>=cols] view with the
         true `cols` given by d_images.shape[2]); asynchronous on the handle's stream."""

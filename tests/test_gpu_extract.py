@@ -118,3 +118,78 @@ def test_empty_and_error_shapes():
     with pytest.raises(OrbError):
         ex(oracle.synth_frame(96, 300))
     ex.close()
+
+
+def test_async_submit_wait_two_in_flight():
+    # orb_extract_batch_submit / _wait: two batches in flight give the same bytes as the synchronous call
+    rows, cols, nf, B = 200, 300, 500, 8
+    ex = ORBextractor(nf, 1.2, 8, 20, 7, max_batch=B)
+    cap = ex.keypoint_bound(rows, cols)
+    batches = [np.stack([oracle.synth_frame(rows, cols, frame=10 * b + f) for f in range(B)]) for b in range(3)]
+    want = [ex.extract_batch(b, cap=cap) for b in batches]
+    from orb_slam_system_b200 import KP_DTYPE
+    outs = [(np.zeros((B, cap), KP_DTYPE), np.zeros((B, cap, 32), np.uint8), np.zeros(B, np.int32)) for _ in range(3)]
+    t0 = ex.submit_batch_pinned(batches[0], *outs[0], cap)
+    t1 = ex.submit_batch_pinned(batches[1], *outs[1], cap)
+    from orb_slam_system_b200 import OrbError
+    with pytest.raises(OrbError):  # a third batch needs a wait first
+        ex.submit_batch_pinned(batches[2], *outs[2], cap)
+    ex.wait_batch(t0)
+    t2 = ex.submit_batch_pinned(batches[2], *outs[2], cap)
+    ex.wait_batch(t1)
+    ex.wait_batch(t2)
+    for b in range(3):
+        k, d, c = outs[b]
+        for f in range(B):
+            wk, wd = want[b][f]
+            assert c[f] == len(wk)
+            assert k[f, :c[f]].tobytes() == wk.tobytes()
+            assert (d[f, :c[f]] == wd).all()
+    ex.close()
+
+
+def test_device_resident_batch_matches_host_path():
+    import torch
+    rows, cols, nf, B = 376, 1241, 2000, 4
+    frames = np.stack([oracle.synth_frame(rows, cols, frame=f, right=f & 1) for f in range(B)])
+    ex = ORBextractor(nf, 1.2, 8, 20, 7, max_batch=B)
+    cap = ex.keypoint_bound(rows, cols)
+    want = ex.extract_batch(frames, cap=cap)
+    pitch = (cols + 63) // 64 * 64
+    d_in = torch.zeros((B, rows, pitch), dtype=torch.uint8, device="cuda")
+    d_in[:, :, :cols] = torch.from_numpy(frames).cuda()
+    d_k = torch.zeros((B, cap, 28), dtype=torch.uint8, device="cuda")
+    d_d = torch.zeros((B, cap, 32), dtype=torch.uint8, device="cuda")
+    d_c = torch.zeros((B,), dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    ex.extract_batch_device(d_in[:, :, :cols], d_k, d_d, d_c, cap)   # zero-copy: same pitch as the internal level 0
+    ex.sync()
+    # a different pitch goes through the internal pitch conversion
+    d_in2 = torch.zeros((B, rows, pitch + 64), dtype=torch.uint8, device="cuda")
+    d_in2[:, :, :cols] = torch.from_numpy(frames).cuda()
+    d_k2, d_d2, d_c2 = torch.zeros_like(d_k), torch.zeros_like(d_d), torch.zeros_like(d_c)
+    torch.cuda.synchronize()
+    ex.extract_batch_device(d_in2[:, :, :cols], d_k2, d_d2, d_c2, cap)
+    ex.sync()
+    for (k, d, c) in ((d_k, d_d, d_c), (d_k2, d_d2, d_c2)):
+        k, d, c = k.cpu().numpy(), d.cpu().numpy(), c.cpu().numpy()
+        for f in range(B):
+            wk, wd = want[f]
+            assert c[f] == len(wk)
+            assert k[f, :c[f]].tobytes() == wk.tobytes()
+            assert (d[f, :c[f]] == wd).all()
+    ex.close()
+
+
+def test_stage_profiling_counts_calls():
+    ex = ORBextractor(1000, 1.2, 8, 20, 7, max_batch=2)
+    img = oracle.synth_frame(480, 640)
+    ex(img)
+    ex.set_profiling(True)
+    ex(img)
+    ex(img)
+    times, ncalls = ex.stage_times()
+    assert ncalls == 2
+    assert set(times) == {"pyramid", "detect", "octree", "blur", "describe"} and all(v > 0 for v in times.values())
+    ex.set_profiling(False)
+    ex.close()
