@@ -318,6 +318,56 @@ def main():
     barrier()
     match_ms = m0.elapsed_time(m1) / MREP
 
+    # ---- BASELINE config 5 (N > 1): NCCL all-gather of every rank's keyframe descriptor block over NVLink,
+    # then each rank brute-force matches its local frames against the same-index keyframes of the next rank
+    shard = None
+    if world > 1:
+        from orb_slam_system_b200.sharding import all_gather_descriptors, cross_shard_pairs
+        KF = 2000  # descriptor rows exchanged per keyframe (fixed stride, counts travel with them)
+        block = d_desc[:, :KF, :].contiguous()
+        cnts = torch.clamp(d_counts, max=KF).to(torch.int32)
+        for _ in range(2):
+            all_d, all_c = all_gather_descriptors(block, cnts)
+        torch.cuda.synchronize()
+        dist.barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        GREP = 5
+        for _ in range(GREP):
+            all_d, all_c = all_gather_descriptors(block, cnts)
+        g1.record()
+        torch.cuda.synchronize()
+        gather_ms = g0.elapsed_time(g1) / GREP
+        pairs = torch.from_numpy(cross_shard_pairs(B, rank, world, neighbours=1)).cuda()
+        tq = block[pairs[:, 0]].contiguous()
+        tt = all_d[pairs[:, 1]].contiguous()
+        tnq = cnts[pairs[:, 0]].contiguous()
+        tnt = all_c[pairs[:, 1]].contiguous()
+        sb = torch.empty((len(pairs), KF), dtype=torch.int32, device="cuda")
+        sd1, sd2 = torch.empty_like(sb), torch.empty_like(sb)
+        torch.cuda.synchronize()
+        for _ in range(2):
+            m.match_all_batch_device(tq, tnq, tt, tnt, sb, sd1, sd2)
+        m.sync()
+        dist.barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record(mstream)
+        for _ in range(GREP):
+            m.match_all_batch_device(tq, tnq, tt, tnt, sb, sd1, sd2)
+        s1.record(mstream)
+        m.sync()
+        smatch_ms = s0.elapsed_time(s1) / GREP
+        tt2 = torch.tensor([gather_ms, smatch_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt2, op=dist.ReduceOp.MAX)
+        gather_ms, smatch_ms = float(tt2[0].item()), float(tt2[1].item())
+        recv_bytes = (world - 1) * (block.numel() + cnts.numel() * 4)
+        npairs_total = float((tnq.double() * tnt.double()).sum().item())
+        tp = torch.tensor([npairs_total], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tp)
+        shard = {"workload": f"all-gather of {B} keyframes x {KF} x 32 B per rank + cross-shard brute-force matching (BASELINE config 5)",
+                 "allgather_ms": gather_ms, "allgather_recv_GBps_per_gpu": recv_bytes / (gather_ms * 1e-3) / 1e9,
+                 "match_ms": smatch_ms, "match_pairs_per_s": float(tp[0].item()) / (smatch_ms * 1e-3)}
+
     if world > 1:
         t = torch.tensor([ms_total, e2e_s, match_ms, e2e_sync_s], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -373,6 +423,8 @@ def main():
                         "note": "POPC-pipe bound (quarter-rate pipe, ~4.5e12 POPC/s per GPU); 6 POPC per pair because words 6-7 of "
                                 "this fork's descriptors are zero (checked on the data, 8 otherwise)"},
         }
+        if shard is not None:
+            line["shard_match"] = shard
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             nfr = max(16, 2 * cores)
