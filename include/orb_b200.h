@@ -175,6 +175,14 @@ int orb_match_csr(orb_matcher* m, const uint8_t* q, int nq, const uint8_t* t, in
                   const int32_t* offsets, const int32_t* cand, int tie_rule, int max_dist,
                   int32_t* best_idx, int32_t* best_dist, int32_t* second_dist);
 
+/* Every candidate distance of a windowed search: dist[c] = DescriptorDistance(query i, train cand[c])
+ * for c in [offsets[i], offsets[i+1]).  For the searches whose candidate eligibility depends on
+ * earlier accepts -- vbMatched2 in SearchByBoW (src/ORBmatcher.cc:316,331), vMatchedDistance in
+ * SearchForInitialization (:224), claimed features in SearchByProjection (:38,59) -- the adapter
+ * replays the reference's sequential scan over these numbers on the host. */
+int orb_distances_csr(orb_matcher* m, const uint8_t* q, int nq, const uint8_t* t, int nt,
+                      const int32_t* offsets, const int32_t* cand, int32_t* dist);
+
 /* Hamming part of Frame::ComputeStereoMatches (src/Frame.cc:446-529): row-band candidate
  * table, octave and disparity gates, first minimum below TH_HIGH=100.  best_r[i] = right
  * keypoint index or -1; best_dist[i] = its distance (100 when none).  scale = the
@@ -186,6 +194,99 @@ int orb_stereo_match(orb_matcher* m, const orb_keypoint* kps_left, const uint8_t
 
 int orb_matcher_sync(orb_matcher* m);
 void* orb_matcher_stream(orb_matcher* m);
+
+/* ---- the reference's search methods, whole: windows and distances on the GPU, the method's own
+ *      accept rule and greedy state replayed in query order on the host ----------------------
+ * Everything a method needs from Frame / KeyFrame / MapPoint objects arrives as plain arrays; the
+ * adapter gathers them.  3-D projection of map points (cv::Mat pose arithmetic)
+ * stays with the caller: queries arrive as projected pixel positions. */
+
+/* What Frame::GetFeaturesInArea (src/Frame.cc:307-360) and KeyFrame::GetFeaturesInArea
+ * (src/KeyFrame.cc:549-588) read.  The 64 x 48 grid of Frame::AssignFeaturesToGrid
+ * (src/Frame.cc:210-225, PosInGrid :362-372) is rebuilt on the device from keys_un. */
+typedef struct orb_frame_view {
+    const orb_keypoint* keys_un; /* mvKeysUn, n entries */
+    const uint8_t* desc;         /* mDescriptors, n x 32 */
+    int32_t n;
+    float min_x, min_y;           /* mnMinX, mnMinY */
+    float grid_w_inv, grid_h_inv; /* mfGridElementWidthInv, mfGridElementHeightInv */
+} orb_frame_view;
+
+/* GetFeaturesInArea(x[i], y[i], r[i], min_level[i], max_level[i]) for nq queries, candidate order as
+ * in the reference (cells ix outer / iy inner, ascending index inside a cell), plus
+ * dist[c] = DescriptorDistance(qdesc row i, F.desc row cand[c]).  min_level / max_level may be NULL
+ * (= -1: no level check, the KeyFrame form).  offsets gets nq+1 entries; *total the candidate count.
+ * If total > cap: ORB_ERR_CAPACITY, offsets and *total are valid, cand/dist untouched. */
+int orb_window_search(orb_matcher* m, const orb_frame_view* F, int nq, const uint8_t* qdesc, const float* x,
+                      const float* y, const float* r, const int32_t* min_level, const int32_t* max_level,
+                      int32_t* offsets, int32_t* cand, int32_t* dist, int cap, int* total);
+
+/* ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th) (src/ORBmatcher.cc:19-65).
+ * Queries = the map points that pass `:24` (non-null, not bad, mbTrackInView), in vector order:
+ * proj_x/proj_y/proj_xr = mTrackProjX/Y/XR, level = mnTrackScaleLevel, view_cos = mTrackViewCos,
+ * q_observed[i] = (Observations() > 0) of that point (NULL: all observed).  u_right = F.mvuRight
+ * (NULL: monocular, all -1).  occupied[idx] (in/out) = F.mvpMapPoints[idx] && Observations() > 0 (:38).
+ * feature_of_query[i] = index the point was written to (F.mvpMapPoints[best] = pMP, :59) or -1. */
+int orb_search_by_projection_map(orb_matcher* m, const orb_frame_view* F, const float* u_right, uint8_t* occupied,
+                                 const float* scale_factors, int nlevels, int nq, const uint8_t* qdesc,
+                                 const float* proj_x, const float* proj_y, const float* proj_xr, const int32_t* level,
+                                 const float* view_cos, const uint8_t* q_observed, float th, float nnratio,
+                                 int32_t* feature_of_query, int* nmatches);
+
+typedef enum orb_rot_mode {
+    ORB_ROT_NONE = 0,   /* no rotation histogram (mbCheckOrientation false, or the method has none) */
+    ORB_ROT_WRAP = 1,   /* rot < 0 -> rot += 360; bin = round(rot/30) % 30 (src/ORBmatcher.cc:873-876) */
+    ORB_ROT_NOWRAP = 2  /* SearchByProjection(Current, Last): no wrap (:796-797); a negative bin
+                           indexes rotHist out of bounds in the reference -> ORB_ERR_SHAPE here */
+} orb_rot_mode;
+
+/* The best-only projection searches: SearchByProjection(Frame&, const Frame&, th, bMono) (:732-818),
+ * SearchByProjection(Frame&, KeyFrame*, set&, th, ORBdist) (:820-894), SearchByProjection(KeyFrame*, Scw,
+ * ...) (:121-195), SearchBySim3 (:636-730) and the search part of Fuse (:504-634).  Query i: window
+ * GetFeaturesInArea(u, v, radius, min_level, max_level); candidates whose claimed[idx] != 0 are skipped
+ * (claimed == NULL: no such state -- SearchBySim3 / Fuse); first minimum; accepted iff best <= max_dist;
+ * an accept sets claimed[best].  q_angle / rot_mode: rotation-consistency histogram over
+ * q_angle[i] - F.keys_un[best].angle ... the reference uses mvKeys angles, which equal mvKeysUn's
+ * (UndistortKeyPoints copies the keypoint and moves pt only, src/Frame.cc:384-414).  Matches in the discarded bins are reset
+ * (feature_of_query = -1, claimed cleared) and subtracted from *nmatches. */
+int orb_search_by_projection_best(orb_matcher* m, const orb_frame_view* F, uint8_t* claimed, int nq,
+                                  const uint8_t* qdesc, const float* u, const float* v, const float* radius,
+                                  const int32_t* min_level, const int32_t* max_level, const float* q_angle,
+                                  int rot_mode, int max_dist, int32_t* feature_of_query, int* nmatches);
+
+/* ORBmatcher::SearchForInitialization (src/ORBmatcher.cc:197-276).  keys1/desc1/n1 = F1.mvKeysUn /
+ * mDescriptors; prev_matched = vbPrevMatched as n1 (x, y) float pairs, updated like :270-273;
+ * matches12 = vnMatches12 (n1 ints). */
+int orb_search_for_initialization(orb_matcher* m, const orb_keypoint* keys1, const uint8_t* desc1, int n1,
+                                  const orb_frame_view* F2, float* prev_matched, int window_size, float nnratio,
+                                  int check_ori, int32_t* matches12, int* nmatches);
+
+/* DBoW2::FeatureVector (std::map<NodeId, std::vector<unsigned>>) as CSR: ascending node ids, and for
+ * node k the feature indices idx[off[k] .. off[k+1]) in stored order. */
+typedef struct orb_feature_vector {
+    const int32_t* nodes;
+    const int32_t* off;
+    const int32_t* idx;
+    int32_t n_nodes;
+} orb_feature_vector;
+
+/* ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, vpMatches12) (src/ORBmatcher.cc:278-366).
+ * has_mp1/has_mp2[i] = the keypoint holds a map point that is not bad (:306-307, :315-316); angle =
+ * mvKeysUn[i].angle.  matches12[i1] = i2 (the caller maps it to vpMapPoints2[i2]) or -1. */
+int orb_search_by_bow(orb_matcher* m, const uint8_t* desc1, const float* angle1, const uint8_t* has_mp1, int n1,
+                      const uint8_t* desc2, const float* angle2, const uint8_t* has_mp2, int n2,
+                      const orb_feature_vector* fv1, const orb_feature_vector* fv2, float nnratio, int check_ori,
+                      int32_t* matches12, int* nmatches);
+
+/* ORBmatcher::SearchForTriangulation (src/ORBmatcher.cc:368-467) with bOnlyStereo = false, the only
+ * way the fork calls it (src/LocalMapping.cc:187).  keys = mvKeysUn; has_mp = GetMapPoint(i) != NULL;
+ * f12 = the 3x3 fundamental matrix row-major; sigma2 = KF2's mvLevelSigma2 (nlevels floats).
+ * matches12[i1] = i2 or -1 (vMatchedPairs = the pairs with i2 >= 0 in i1 order, :456-462). */
+int orb_search_for_triangulation(orb_matcher* m, const orb_keypoint* keys1, const uint8_t* desc1,
+                                 const uint8_t* has_mp1, int n1, const orb_keypoint* keys2, const uint8_t* desc2,
+                                 const uint8_t* has_mp2, int n2, const orb_feature_vector* fv1,
+                                 const orb_feature_vector* fv2, const float* f12, const float* sigma2, int nlevels,
+                                 int check_ori, int32_t* matches12, int* nmatches);
 
 /* ---- misc ------------------------------------------------------------------------------- */
 

@@ -222,6 +222,155 @@ def stereo_match(kl, dl, kr, dr, scale, rows, bf, fx):
     return br, bd
 
 
+def _featvec_csr(fv):
+    """dict node -> list of feature indices  ->  (sorted nodes, offsets, flat indices) int32 arrays."""
+    nodes = np.array(sorted(fv), np.int32)
+    off = np.zeros(len(nodes) + 1, np.int32)
+    flat = []
+    for i, nd in enumerate(nodes):
+        flat.extend(fv[int(nd)])
+        off[i + 1] = len(flat)
+    return nodes, off, np.array(flat, np.int32)
+
+
+def search_by_bow_kf(kf1, kf2, nnratio=0.6, checkOri=True):
+    """ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*): kf = dict(desc, keys[KP_DTYPE], has_mp[bool], featvec{node: [idx]})."""
+    d1, d2 = np.ascontiguousarray(kf1["desc"], np.uint8), np.ascontiguousarray(kf2["desc"], np.uint8)
+    a1, a2 = np.ascontiguousarray(kf1["keys"]["angle"], np.float32), np.ascontiguousarray(kf2["keys"]["angle"], np.float32)
+    h1, h2 = np.ascontiguousarray(kf1["has_mp"], np.uint8), np.ascontiguousarray(kf2["has_mp"], np.uint8)
+    n1, o1, i1 = _featvec_csr(kf1["featvec"])
+    n2, o2, i2 = _featvec_csr(kf2["featvec"])
+    out = np.zeros(len(d1), np.int32)
+    lib().orc_search_by_bow_kf.restype = C.c_int
+    n = lib().orc_search_by_bow_kf(_p(d1), _p(a1), _p(h1), len(d1), _p(d2), _p(a2), _p(h2), len(d2), _p(n1), _p(o1), _p(i1), len(n1),
+                                   _p(n2), _p(o2), _p(i2), len(n2), C.c_float(nnratio), int(checkOri), _p(out))
+    return int(n), out
+
+
+def search_for_triangulation(kf1, kf2, F12, checkOri=False):
+    """ORBmatcher::SearchForTriangulation (bOnlyStereo=false): kf as above plus 'sigma2' (mvLevelSigma2) for kf2."""
+    d1, d2 = np.ascontiguousarray(kf1["desc"], np.uint8), np.ascontiguousarray(kf2["desc"], np.uint8)
+    k1, k2 = kf1["keys"], kf2["keys"]
+    f = lambda a, t=np.float32: np.ascontiguousarray(a, t)
+    h1, h2 = f(kf1["has_mp"], np.uint8), f(kf2["has_mp"], np.uint8)
+    n1, o1, i1 = _featvec_csr(kf1["featvec"])
+    n2, o2, i2 = _featvec_csr(kf2["featvec"])
+    x1, y1, a1 = f(k1["x"]), f(k1["y"]), f(k1["angle"])
+    x2, y2, a2, oc2 = f(k2["x"]), f(k2["y"]), f(k2["angle"]), f(k2["octave"], np.int32)
+    F = f(np.asarray(F12, np.float32).reshape(9))
+    s2 = f(kf2["sigma2"])
+    out = np.zeros(len(d1), np.int32)
+    lib().orc_search_for_triangulation.restype = C.c_int
+    n = lib().orc_search_for_triangulation(_p(d1), _p(x1), _p(y1), _p(a1), _p(h1), len(d1), _p(d2), _p(x2), _p(y2), _p(a2), _p(oc2),
+                                           _p(h2), len(d2), _p(n1), _p(o1), _p(i1), len(n1), _p(n2), _p(o2), _p(i2), len(n2), _p(F),
+                                           _p(s2), int(checkOri), _p(out))
+    return int(n), out
+
+
+class _OrcFrame(C.Structure):
+    _fields_ = [("keysUn", C.c_void_p), ("desc", C.c_void_p), ("N", C.c_int), ("mnMinX", C.c_float), ("mnMinY", C.c_float),
+                ("mfGridElementWidthInv", C.c_float), ("mfGridElementHeightInv", C.c_float)]
+
+
+def _frame(F):
+    """F: any object with keys_un, desc, mnMinX, mnMinY, mfGridElementWidthInv, mfGridElementHeightInv."""
+    k = np.ascontiguousarray(F.keys_un, KP_DTYPE)
+    d = np.ascontiguousarray(F.desc, np.uint8)
+    fr = _OrcFrame(k.ctypes.data, d.ctypes.data, len(k), F.mnMinX, F.mnMinY, F.mfGridElementWidthInv, F.mfGridElementHeightInv)
+    fr._keep = (k, d)
+    return fr
+
+
+def _opt(a, dt):
+    return None if a is None else np.ascontiguousarray(a, dt)
+
+
+def _pp(a):
+    return None if a is None else _p(a)
+
+
+def features_in_area(F, x, y, r, min_level=None, max_level=None):
+    """Frame::GetFeaturesInArea per query: (offsets, cand) in the reference's order."""
+    x, y, r = (np.ascontiguousarray(a, np.float32) for a in (x, y, r))
+    lo, hi = _opt(min_level, np.int32), _opt(max_level, np.int32)
+    fr = _frame(F)
+    off = np.zeros(len(x) + 1, np.int32)
+    cap = 64
+    while True:
+        cand = np.zeros(cap, np.int32)
+        lib().orc_features_in_area.restype = C.c_int
+        tot = lib().orc_features_in_area(C.byref(fr), len(x), _p(x), _p(y), _p(r), _pp(lo), _pp(hi), _p(off), _p(cand), cap)
+        if tot <= cap:
+            return off, cand[:tot].copy()
+        cap = tot
+
+
+def search_by_projection_map(F, occupied, qdesc, proj_x, proj_y, proj_xr, level, view_cos, th, nnratio, q_observed=None):
+    q = np.ascontiguousarray(qdesc, np.uint8).reshape(-1, 32)
+    out = np.zeros(len(q), np.int32)
+    fr = _frame(F)
+    f = lambda a: np.ascontiguousarray(a, np.float32)
+    px, py, pxr, vc = f(proj_x), f(proj_y), f(proj_xr), f(view_cos)
+    lv = np.ascontiguousarray(level, np.int32)
+    qo = _opt(q_observed, np.uint8)
+    lib().orc_search_by_projection_map.restype = C.c_int
+    n = lib().orc_search_by_projection_map(C.byref(fr), _pp(_opt(F.mvuRight, np.float32)), _p(occupied), _p(f(F.mvScaleFactors)), len(q),
+                                           _p(q), _p(px), _p(py), _p(pxr), _p(lv), _p(vc), _pp(qo), C.c_float(th), C.c_float(nnratio),
+                                           _p(out))
+    return int(n), out
+
+
+def search_by_projection_last(Cur, claimed, qdesc, u, v, last_octave, last_angle, th, forward, backward, checkOri):
+    """Returns (nmatches, feature_of_query); nmatches is None when the reference would index rotHist out of bounds (D9)."""
+    q = np.ascontiguousarray(qdesc, np.uint8).reshape(-1, 32)
+    out = np.zeros(len(q), np.int32)
+    fr = _frame(Cur)
+    f = lambda a: np.ascontiguousarray(a, np.float32)
+    uu, vv, la = f(u), f(v), f(last_angle)
+    lo = np.ascontiguousarray(last_octave, np.int32)
+    lib().orc_search_by_projection_last.restype = C.c_int
+    n = lib().orc_search_by_projection_last(C.byref(fr), _p(claimed), _p(f(Cur.mvScaleFactors)), len(q), _p(q), _p(uu), _p(vv), _p(lo),
+                                            _p(la), C.c_float(th), int(forward), int(backward), int(checkOri), _p(out))
+    return (None if n == -2147483648 else int(n)), out
+
+
+def search_by_projection_reloc(Cur, claimed, qdesc, u, v, predicted_level, kf_angle, th, ORBdist, checkOri):
+    q = np.ascontiguousarray(qdesc, np.uint8).reshape(-1, 32)
+    out = np.zeros(len(q), np.int32)
+    fr = _frame(Cur)
+    f = lambda a: np.ascontiguousarray(a, np.float32)
+    uu, vv, ka = f(u), f(v), f(kf_angle)
+    pl = np.ascontiguousarray(predicted_level, np.int32)
+    lib().orc_search_by_projection_reloc.restype = C.c_int
+    n = lib().orc_search_by_projection_reloc(C.byref(fr), _p(claimed), _p(f(Cur.mvScaleFactors)), len(q), _p(q), _p(uu), _p(vv), _p(pl),
+                                             _p(ka), C.c_float(th), int(ORBdist), int(checkOri), _p(out))
+    return int(n), out
+
+
+def search_kf_window(KF, claimed, qdesc, u, v, radius, level, max_dist):
+    q = np.ascontiguousarray(qdesc, np.uint8).reshape(-1, 32)
+    out = np.zeros(len(q), np.int32)
+    fr = _frame(KF)
+    f = lambda a: np.ascontiguousarray(a, np.float32)
+    uu, vv, rr = f(u), f(v), f(radius)
+    lv = _opt(level, np.int32)
+    lib().orc_search_kf_window.restype = C.c_int
+    n = lib().orc_search_kf_window(C.byref(fr), _pp(claimed), len(q), _p(q), _p(uu), _p(vv), _p(rr), _pp(lv), int(max_dist), _p(out))
+    return int(n), out
+
+
+def search_for_initialization(keys1, desc1, F2, prev_matched, window_size, nnratio, checkOri):
+    k1 = np.ascontiguousarray(keys1, KP_DTYPE)
+    d1 = np.ascontiguousarray(desc1, np.uint8).reshape(-1, 32)
+    assert prev_matched.dtype == np.float32 and prev_matched.flags.c_contiguous
+    out = np.zeros(len(k1), np.int32)
+    fr = _frame(F2)
+    lib().orc_search_for_initialization.restype = C.c_int
+    n = lib().orc_search_for_initialization(_p(k1), _p(d1), len(k1), C.byref(fr), _p(prev_matched), int(window_size), C.c_float(nnratio),
+                                            int(checkOri), _p(out))
+    return int(n), out
+
+
 def extract_many(rows, cols, nframes, nthreads, first_frame=0, seed=7, **params):
     p = dict(DEFAULT)
     p.update(params)

@@ -776,6 +776,534 @@ int orc_stereo_match(const KeyPoint* kl, const uint8_t* dl, int nl, const KeyPoi
     return 0;
 }
 
+// ---- ORBmatcher::ComputeThreeMaxima, reference ORBmatcher.cc:469-502 ----
+static void three_maxima(const std::vector<int>* histo, int L, int& ind1, int& ind2, int& ind3) {
+    int topIdx[3] = {-1, -1, -1}, topVal[3] = {0, 0, 0};
+    for (int i = 0; i < L; ++i) {
+        const int value = (int)histo[i].size();
+        for (int j = 0; j < 3; ++j) {
+            if (value > topVal[j]) {
+                for (int k = 2; k > j; --k) {
+                    topVal[k] = topVal[k - 1];
+                    topIdx[k] = topIdx[k - 1];
+                }
+                topVal[j] = value;
+                topIdx[j] = i;
+                break;
+            }
+        }
+    }
+    ind1 = topIdx[0];
+    ind2 = topIdx[1];
+    ind3 = topIdx[2];
+    if (topVal[1] < 0.1f * topVal[0]) {
+        ind2 = -1;
+        ind3 = -1;
+    } else if (topVal[2] < 0.1f * topVal[0]) {
+        ind3 = -1;
+    }
+}
+
+// Feature vectors arrive as sorted node ids with CSR index lists (DBoW2::FeatureVector is a
+// std::map<NodeId, std::vector<unsigned>>, so iteration is by ascending node id and the
+// lower_bound jumps of the reference are a plain merge of the two id lists).
+
+// ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, ...), reference ORBmatcher.cc:278-366.
+// has1/has2: the keypoint holds a good map point.  matches12[i1] = i2 or -1.  Returns nmatches.
+int orc_search_by_bow_kf(const uint8_t* d1, const float* ang1, const uint8_t* has1, int n1, const uint8_t* d2, const float* ang2,
+                         const uint8_t* has2, int n2, const int* nodes1, const int* off1, const int* idx1, int nn1, const int* nodes2,
+                         const int* off2, const int* idx2, int nn2, float nnratio, int checkOri, int* matches12) {
+    const int TH_LOW = 50, HISTO = 30;
+    for (int i = 0; i < n1; ++i) matches12[i] = -1;
+    std::vector<bool> matched2(n2, false);
+    std::vector<int> rotHist[30];
+    const float factor = 1.0f / HISTO;
+    int nmatches = 0;
+    int a = 0, b = 0;
+    while (a < nn1 && b < nn2) {
+        if (nodes1[a] == nodes2[b]) {
+            for (int ia = off1[a]; ia < off1[a + 1]; ++ia) {
+                const int i1 = idx1[ia];
+                if (!has1[i1]) continue;
+                int best1 = INT_MAX, bestIdx2 = -1, best2 = INT_MAX;
+                for (int ib = off2[b]; ib < off2[b + 1]; ++ib) {
+                    const int i2 = idx2[ib];
+                    if (matched2[i2] || !has2[i2]) continue;
+                    const int dist = descriptor_distance(d1 + 32 * (size_t)i1, d2 + 32 * (size_t)i2);
+                    if (dist < best1) {
+                        best2 = best1;
+                        best1 = dist;
+                        bestIdx2 = i2;
+                    } else if (dist < best2) {
+                        best2 = dist;
+                    }
+                }
+                if (best1 < TH_LOW && static_cast<float>(best1) < nnratio * static_cast<float>(best2)) {
+                    matches12[i1] = bestIdx2;
+                    matched2[bestIdx2] = true;
+                    nmatches++;
+                    if (checkOri) {
+                        float rot = ang1[i1] - ang2[bestIdx2];
+                        if (rot < 0.0f) rot += 360.0f;
+                        int bin = (int)std::round(rot * factor);
+                        if (bin == HISTO) bin = 0;
+                        rotHist[bin].push_back(i1);
+                    }
+                }
+            }
+            ++a;
+            ++b;
+        } else if (nodes1[a] < nodes2[b]) {
+            ++a;
+        } else {
+            ++b;
+        }
+    }
+    if (checkOri) {
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        three_maxima(rotHist, HISTO, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO; ++i) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (int i1 : rotHist[i]) {
+                matches12[i1] = -1;
+                nmatches--;
+            }
+        }
+    }
+    return nmatches;
+}
+
+// ORBmatcher::SearchForTriangulation + CheckDistEpipolarLine, reference ORBmatcher.cc:368-467, :71-85
+// (bOnlyStereo = false, the only way it is called: LocalMapping.cc:187).  x/y/octave: undistorted
+// keypoints; has1/has2: the keypoint already holds a map point; F12 row-major 3x3; sigma2 =
+// KF2's mvLevelSigma2.  matches12[i1] = i2 or -1.  Returns nmatches.
+int orc_search_for_triangulation(const uint8_t* d1, const float* x1, const float* y1, const float* ang1, const uint8_t* has1, int n1,
+                                 const uint8_t* d2, const float* x2, const float* y2, const float* ang2, const int* oct2,
+                                 const uint8_t* has2, int n2, const int* nodes1, const int* off1, const int* idx1, int nn1,
+                                 const int* nodes2, const int* off2, const int* idx2, int nn2, const float* F12, const float* sigma2,
+                                 int checkOri, int* matches12) {
+    const int TH_LOW = 50, HISTO = 30;
+    for (int i = 0; i < n1; ++i) matches12[i] = -1;
+    std::vector<int> rotHist[30];
+    const float factor = 1.0f / HISTO;
+    int nmatches = 0;
+    int a = 0, b = 0;
+    while (a < nn1 && b < nn2) {
+        if (nodes1[a] == nodes2[b]) {
+            for (int ia = off1[a]; ia < off1[a + 1]; ++ia) {
+                const int i1 = idx1[ia];
+                if (has1[i1]) continue;
+                int bestDist = TH_LOW, bestIdx2 = -1;
+                for (int ib = off2[b]; ib < off2[b + 1]; ++ib) {
+                    const int i2 = idx2[ib];
+                    if (has2[i2]) continue;  // vbMatched2 is never set in this fork
+                    const int dist = descriptor_distance(d1 + 32 * (size_t)i1, d2 + 32 * (size_t)i2);
+                    if (dist > TH_LOW || dist > bestDist) continue;
+                    // CheckDistEpipolarLine
+                    const float ea = x1[i1] * F12[0] + y1[i1] * F12[3] + F12[6];
+                    const float eb = x1[i1] * F12[1] + y1[i1] * F12[4] + F12[7];
+                    const float ec = x1[i1] * F12[2] + y1[i1] * F12[5] + F12[8];
+                    const float num = ea * x2[i2] + eb * y2[i2] + ec;
+                    const float den = ea * ea + eb * eb;
+                    bool ok = false;
+                    if (den != 0) {
+                        const float dsqr = num * num / den;
+                        ok = dsqr < 3.84 * sigma2[oct2[i2]];
+                    }
+                    if (ok) {
+                        bestIdx2 = i2;
+                        bestDist = dist;
+                        if (checkOri) {
+                            float rot = ang1[i1] - ang2[i2];
+                            if (rot < 0.0) rot += 360.0f;
+                            int bin = static_cast<int>(std::round(rot * factor)) % HISTO;
+                            rotHist[bin].push_back(i1);
+                        }
+                    }
+                }
+                if (bestIdx2 >= 0) {
+                    matches12[i1] = bestIdx2;
+                    nmatches++;
+                }
+            }
+            ++a;
+            ++b;
+        } else if (nodes1[a] < nodes2[b]) {
+            ++a;
+        } else {
+            ++b;
+        }
+    }
+    if (checkOri) {
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        three_maxima(rotHist, HISTO, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO; ++i) {
+            if (i != ind1 && i != ind2 && i != ind3) {
+                for (int i1 : rotHist[i]) {
+                    if (matches12[i1] >= 0) {
+                        matches12[i1] = -1;
+                        nmatches--;
+                    }
+                }
+            }
+        }
+    }
+    return nmatches;
+}
+
+// ---- Frame grid and windowed searches ------------------------------------------------------
+// The Frame / KeyFrame members the searches read, as plain arrays (KeyPoint = mvKeysUn).
+struct OrcFrame {
+    const KeyPoint* keysUn;
+    const uint8_t* desc;
+    int N;
+    float mnMinX, mnMinY, mfGridElementWidthInv, mfGridElementHeightInv;
+};
+
+namespace {
+const int FRAME_GRID_ROWS = 48, FRAME_GRID_COLS = 64;  // reference include/Frame.h:17-18
+
+struct Grid {
+    std::vector<size_t> cell[64][48];
+};
+
+// Frame::PosInGrid + Frame::AssignFeaturesToGrid, reference src/Frame.cc:362-372, :210-225.
+void assign_features_to_grid(const OrcFrame& F, Grid& g) {
+    for (int i = 0; i < F.N; i++) {
+        const KeyPoint& kp = F.keysUn[i];
+        int posX = round((kp.x - F.mnMinX) * F.mfGridElementWidthInv);
+        int posY = round((kp.y - F.mnMinY) * F.mfGridElementHeightInv);
+        if (posX < 0 || posX >= FRAME_GRID_COLS || posY < 0 || posY >= FRAME_GRID_ROWS) continue;
+        g.cell[posX][posY].push_back(i);
+    }
+}
+
+// Frame::GetFeaturesInArea, reference src/Frame.cc:307-360 (KeyFrame::GetFeaturesInArea,
+// src/KeyFrame.cc:549-588, is the same walk without the level test: minLevel = maxLevel = -1).
+std::vector<size_t> features_in_area(const OrcFrame& F, const Grid& g, float x, float y, float r, int minLevel, int maxLevel) {
+    std::vector<size_t> vIndices;
+    const int nMinCellX = std::max(0, (int)floor((x - F.mnMinX - r) * F.mfGridElementWidthInv));
+    if (nMinCellX >= FRAME_GRID_COLS) return vIndices;
+    const int nMaxCellX = std::min((int)FRAME_GRID_COLS - 1, (int)ceil((x - F.mnMinX + r) * F.mfGridElementWidthInv));
+    if (nMaxCellX < 0) return vIndices;
+    const int nMinCellY = std::max(0, (int)floor((y - F.mnMinY - r) * F.mfGridElementHeightInv));
+    if (nMinCellY >= FRAME_GRID_ROWS) return vIndices;
+    const int nMaxCellY = std::min((int)FRAME_GRID_ROWS - 1, (int)ceil((y - F.mnMinY + r) * F.mfGridElementHeightInv));
+    if (nMaxCellY < 0) return vIndices;
+    const bool bCheckLevels = (minLevel > 0) || (maxLevel >= 0);
+    for (int ix = nMinCellX; ix <= nMaxCellX; ix++) {
+        for (int iy = nMinCellY; iy <= nMaxCellY; iy++) {
+            const std::vector<size_t>& vCell = g.cell[ix][iy];
+            for (size_t j = 0, jend = vCell.size(); j < jend; j++) {
+                const KeyPoint& kpUn = F.keysUn[vCell[j]];
+                if (bCheckLevels) {
+                    if (kpUn.octave < minLevel) continue;
+                    if (maxLevel >= 0)
+                        if (kpUn.octave > maxLevel) continue;
+                }
+                const float distx = kpUn.x - x;
+                const float disty = kpUn.y - y;
+                if (fabs(distx) < r && fabs(disty) < r) vIndices.push_back(vCell[j]);
+            }
+        }
+    }
+    return vIndices;
+}
+}  // namespace
+
+// Candidate lists alone (for testing the window generation): CSR offsets + indices.  Returns the total.
+int orc_features_in_area(const OrcFrame* F, int nq, const float* x, const float* y, const float* r, const int* minLevel,
+                         const int* maxLevel, int* offsets, int* cand, int cap) {
+    Grid* g = new Grid();
+    assign_features_to_grid(*F, *g);
+    int total = 0;
+    offsets[0] = 0;
+    for (int i = 0; i < nq; ++i) {
+        auto v = features_in_area(*F, *g, x[i], y[i], r[i], minLevel ? minLevel[i] : -1, maxLevel ? maxLevel[i] : -1);
+        for (size_t idx : v) {
+            if (total < cap) cand[total] = (int)idx;
+            ++total;
+        }
+        offsets[i + 1] = total;
+    }
+    delete g;
+    return total;
+}
+
+// ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th), reference ORBmatcher.cc:19-65.
+// Queries = the map points that survive :24.  occupied[idx] stands for
+// `F.mvpMapPoints[idx] && F.mvpMapPoints[idx]->Observations() > 0`; qObserved for the query's Observations() > 0.
+int orc_search_by_projection_map(const OrcFrame* F, const float* mvuRight, uint8_t* occupied, const float* mvScaleFactors, int nq,
+                                 const uint8_t* qdesc, const float* projX, const float* projY, const float* projXR, const int* level,
+                                 const float* viewCos, const uint8_t* qObserved, float th, float mfNNratio, int* featureOfQuery) {
+    const int TH_HIGH = 100;
+    Grid* g = new Grid();
+    assign_features_to_grid(*F, *g);
+    int nmatches = 0;
+    const bool bFactor = th != 1.0;
+    for (int q = 0; q < nq; ++q) {
+        featureOfQuery[q] = -1;
+        const int nPredictedLevel = level[q];
+        const float r = ((viewCos[q] > 0.998) ? 2.5f : 4.0f) * (bFactor ? th : 1);
+        auto vIndices = features_in_area(*F, *g, projX[q], projY[q], r * mvScaleFactors[nPredictedLevel], nPredictedLevel - 1, nPredictedLevel);
+        if (vIndices.empty()) continue;
+        int bestDist = INT_MAX, bestIdx = -1, secondBestDist = INT_MAX;
+        for (auto idx : vIndices) {
+            if (occupied[idx]) continue;
+            if (mvuRight && mvuRight[idx] > 0) {
+                float er = fabs(projXR[q] - mvuRight[idx]);
+                if (er > r * mvScaleFactors[nPredictedLevel]) continue;
+            }
+            int dist = descriptor_distance(qdesc + 32 * (size_t)q, F->desc + 32 * idx);
+            if (dist < bestDist) {
+                secondBestDist = bestDist;
+                bestDist = dist;
+                bestIdx = (int)idx;
+            } else if (dist < secondBestDist) {
+                secondBestDist = dist;
+            }
+        }
+        if (bestDist <= TH_HIGH && (bestDist <= mfNNratio * secondBestDist)) {
+            featureOfQuery[q] = bestIdx;
+            if (!qObserved || qObserved[q]) occupied[bestIdx] = 1;
+            nmatches++;
+        }
+    }
+    delete g;
+    return nmatches;
+}
+
+// ORBmatcher::SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, th, bMono), reference
+// ORBmatcher.cc:732-818, from the projected (u, v) on (:755-761 are the caller's).  Queries = last-frame
+// features that reach :763.  Returns nmatches, or INT_MIN when a negative bin would index rotHist out of
+// bounds (D9: the reference has no `rot += 360`).
+int orc_search_by_projection_last(const OrcFrame* Cur, uint8_t* curHasMapPoint, const float* mvScaleFactors, int nq, const uint8_t* qdesc,
+                                  const float* u, const float* v, const int* lastOctave, const float* lastAngle, float th, int bForward,
+                                  int bBackward, int checkOri, int* featureOfQuery) {
+    const int TH_HIGH = 100, HISTO = 30;
+    Grid* g = new Grid();
+    assign_features_to_grid(*Cur, *g);
+    std::vector<int> rotHist[30];
+    std::vector<int> owner(Cur->N, -1);
+    const float factor = 1.0f / HISTO;
+    int nmatches = 0;
+    bool ub = false;
+    for (int i = 0; i < nq && !ub; ++i) {
+        featureOfQuery[i] = -1;
+        int nLastOctave = lastOctave[i];
+        float radius = th * mvScaleFactors[nLastOctave];
+        std::vector<size_t> vIndices2;
+        if (bForward)
+            vIndices2 = features_in_area(*Cur, *g, u[i], v[i], radius, nLastOctave, -1);
+        else if (bBackward)
+            vIndices2 = features_in_area(*Cur, *g, u[i], v[i], radius, 0, nLastOctave);
+        else
+            vIndices2 = features_in_area(*Cur, *g, u[i], v[i], radius, nLastOctave - 1, nLastOctave + 1);
+        if (vIndices2.empty()) continue;
+        int bestDist = INT_MAX, bestIdx2 = -1;
+        for (auto idx : vIndices2) {
+            if (curHasMapPoint[idx]) continue;
+            int dist = descriptor_distance(qdesc + 32 * (size_t)i, Cur->desc + 32 * idx);
+            if (dist < bestDist) {
+                bestDist = dist;
+                bestIdx2 = (int)idx;
+            }
+        }
+        if (bestDist <= TH_HIGH) {
+            curHasMapPoint[bestIdx2] = 1;
+            featureOfQuery[i] = bestIdx2;
+            owner[bestIdx2] = i;
+            nmatches++;
+            if (checkOri) {
+                float rot = lastAngle[i] - Cur->keysUn[bestIdx2].angle;
+                int bin = static_cast<int>(round(rot * factor)) % HISTO;
+                if (bin < 0) {
+                    ub = true;
+                    break;
+                }
+                rotHist[bin].push_back(bestIdx2);
+            }
+        }
+    }
+    if (checkOri && !ub) {
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        three_maxima(rotHist, HISTO, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO; i++) {
+            if (i != ind1 && i != ind2 && i != ind3) {
+                for (auto idx : rotHist[i]) {
+                    curHasMapPoint[idx] = 0;
+                    featureOfQuery[owner[idx]] = -1;
+                    nmatches--;
+                }
+            }
+        }
+    }
+    delete g;
+    return ub ? INT_MIN : nmatches;
+}
+
+// ORBmatcher::SearchByProjection(Frame &CurrentFrame, KeyFrame *pKF, const set<MapPoint*>&, th, ORBdist),
+// reference ORBmatcher.cc:820-894, from the projected (u, v) and predicted level on.
+int orc_search_by_projection_reloc(const OrcFrame* Cur, uint8_t* curHasMapPoint, const float* mvScaleFactors, int nq, const uint8_t* qdesc,
+                                   const float* u, const float* v, const int* predictedLevel, const float* kfAngle, float th,
+                                   int ORBdist, int checkOri, int* featureOfQuery) {
+    const int HISTO = 30;
+    Grid* g = new Grid();
+    assign_features_to_grid(*Cur, *g);
+    std::vector<int> rotationHistogram[30];
+    std::vector<int> owner(Cur->N, -1);
+    float histogramFactor = 1.0f / HISTO;
+    int matchesCount = 0;
+    for (int i = 0; i < nq; ++i) {
+        featureOfQuery[i] = -1;
+        float radius = th * mvScaleFactors[predictedLevel[i]];
+        auto candidates = features_in_area(*Cur, *g, u[i], v[i], radius, predictedLevel[i] - 1, predictedLevel[i] + 1);
+        if (candidates.empty()) continue;
+        int bestDist = INT_MAX, bestIdx = -1;
+        for (size_t idx : candidates) {
+            if (curHasMapPoint[idx]) continue;
+            int dist = descriptor_distance(qdesc + 32 * (size_t)i, Cur->desc + 32 * idx);
+            if (dist < bestDist) {
+                bestDist = dist;
+                bestIdx = (int)idx;
+            }
+        }
+        if (bestDist <= ORBdist) {
+            curHasMapPoint[bestIdx] = 1;
+            featureOfQuery[i] = bestIdx;
+            owner[bestIdx] = i;
+            matchesCount++;
+            if (checkOri) {
+                float rotationDiff = kfAngle[i] - Cur->keysUn[bestIdx].angle;
+                if (rotationDiff < 0) rotationDiff += 360.0f;
+                int bin = static_cast<int>(round(rotationDiff * histogramFactor)) % HISTO;
+                rotationHistogram[bin].push_back(bestIdx);
+            }
+        }
+    }
+    if (checkOri) {
+        int topBins[3];
+        three_maxima(rotationHistogram, HISTO, topBins[0], topBins[1], topBins[2]);
+        for (int i = 0; i < HISTO; ++i) {
+            if (i != topBins[0] && i != topBins[1] && i != topBins[2]) {
+                for (size_t idx : rotationHistogram[i]) {
+                    curHasMapPoint[idx] = 0;
+                    featureOfQuery[owner[idx]] = -1;
+                    matchesCount--;
+                }
+            }
+        }
+    }
+    delete g;
+    return matchesCount;
+}
+
+// The KeyFrame-window searches from the projected (u, v, radius) on: SearchByProjection(KeyFrame*, Scw, ...)
+// reference ORBmatcher.cc:166-191 (vpMatched = claimed, no octave gate: level == NULL, accept <= TH_LOW);
+// SearchBySim3 :694-714 and Fuse :533-547 / :597-611 (no claims: claimed == NULL, octave gate
+// `kp.octave < level-1 || kp.octave > level`, accept <= maxDist).
+int orc_search_kf_window(const OrcFrame* KF, uint8_t* claimed, int nq, const uint8_t* qdesc, const float* u, const float* v,
+                         const float* radius, const int* level, int maxDist, int* featureOfQuery) {
+    Grid* g = new Grid();
+    assign_features_to_grid(*KF, *g);
+    int nmatches = 0;
+    for (int i = 0; i < nq; ++i) {
+        featureOfQuery[i] = -1;
+        const auto vIndices = features_in_area(*KF, *g, u[i], v[i], radius[i], -1, -1);
+        if (vIndices.empty()) continue;
+        int bestDist = INT_MAX, bestIdx = -1;
+        for (auto idx : vIndices) {
+            if (claimed && claimed[idx]) continue;
+            if (level) {
+                const KeyPoint& kp = KF->keysUn[idx];
+                if (kp.octave < level[i] - 1 || kp.octave > level[i]) continue;
+            }
+            int dist = descriptor_distance(qdesc + 32 * (size_t)i, KF->desc + 32 * idx);
+            if (dist < bestDist) {
+                bestDist = dist;
+                bestIdx = (int)idx;
+            }
+        }
+        if (bestDist <= maxDist) {
+            if (claimed) claimed[bestIdx] = 1;
+            featureOfQuery[i] = bestIdx;
+            nmatches++;
+        }
+    }
+    delete g;
+    return nmatches;
+}
+
+// ORBmatcher::SearchForInitialization, reference ORBmatcher.cc:197-276.  vbPrevMatched as (x, y) pairs.
+int orc_search_for_initialization(const KeyPoint* keys1, const uint8_t* desc1, int n1, const OrcFrame* F2, float* vbPrevMatched,
+                                  int windowSize, float mfNNratio, int checkOri, int* vnMatches12) {
+    const int TH_LOW = 50, HISTO = 30;
+    Grid* g = new Grid();
+    assign_features_to_grid(*F2, *g);
+    int nmatches = 0;
+    for (int i = 0; i < n1; ++i) vnMatches12[i] = -1;
+    std::vector<int> rotHist[30];
+    const float factor = 1.0f / HISTO;
+    std::vector<int> vMatchedDistance(F2->N, INT_MAX);
+    std::vector<int> vnMatches21(F2->N, -1);
+    for (int i1 = 0; i1 < n1; ++i1) {
+        const KeyPoint& kp1 = keys1[i1];
+        if (kp1.octave > 0) continue;
+        auto vIndices2 = features_in_area(*F2, *g, vbPrevMatched[2 * i1], vbPrevMatched[2 * i1 + 1], windowSize, kp1.octave, kp1.octave);
+        if (vIndices2.empty()) continue;
+        int bestDist = INT_MAX, bestDist2 = INT_MAX, bestIdx2 = -1;
+        for (auto i2 : vIndices2) {
+            int dist = descriptor_distance(desc1 + 32 * (size_t)i1, F2->desc + 32 * i2);
+            if (dist < vMatchedDistance[i2]) {
+                if (dist < bestDist) {
+                    bestDist2 = bestDist;
+                    bestDist = dist;
+                    bestIdx2 = (int)i2;
+                } else if (dist < bestDist2) {
+                    bestDist2 = dist;
+                }
+            }
+        }
+        if (bestDist <= TH_LOW && bestDist < static_cast<float>(bestDist2) * mfNNratio) {
+            if (vnMatches21[bestIdx2] >= 0) {
+                vnMatches12[vnMatches21[bestIdx2]] = -1;
+                nmatches--;
+            }
+            vnMatches12[i1] = bestIdx2;
+            vnMatches21[bestIdx2] = i1;
+            vMatchedDistance[bestIdx2] = bestDist;
+            nmatches++;
+            if (checkOri) {
+                float rot = kp1.angle - F2->keysUn[bestIdx2].angle;
+                if (rot < 0.0) rot += 360.0f;
+                int bin = round(rot * factor);
+                if (bin == HISTO) bin = 0;
+                rotHist[bin].push_back(i1);
+            }
+        }
+    }
+    if (checkOri) {
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        three_maxima(rotHist, HISTO, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO; ++i) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (int idx1 : rotHist[i]) {
+                if (vnMatches12[idx1] >= 0) {
+                    vnMatches12[idx1] = -1;
+                    nmatches--;
+                }
+            }
+        }
+    }
+    for (int i1 = 0; i1 < n1; ++i1)
+        if (vnMatches12[i1] >= 0) {
+            vbPrevMatched[2 * i1] = F2->keysUn[vnMatches12[i1]].x;
+            vbPrevMatched[2 * i1 + 1] = F2->keysUn[vnMatches12[i1]].y;
+        }
+    delete g;
+    return nmatches;
+}
+
 void orc_synth_frame(uint8_t* dst, int rows, int cols, int step, uint64_t seed, uint64_t frame,
                      int variant, int right) {
     synth_frame(dst, rows, cols, step, seed, frame, variant, right);

@@ -130,6 +130,14 @@ void orc_match_csr(const uint8_t* q, int nq, const uint8_t* t, int nt, const int
 int orc_stereo_match(const orb_oracle::KeyPoint* kl, const uint8_t* dl, int nl,
                      const orb_oracle::KeyPoint* kr, const uint8_t* dr, int nr, const float* scale,
                      int nlevels, int rows, float bf, float fx, int* best_r, int* best_dist);
+int orc_search_by_bow_kf(const uint8_t* d1, const float* ang1, const uint8_t* has1, int n1, const uint8_t* d2, const float* ang2,
+                         const uint8_t* has2, int n2, const int* nodes1, const int* off1, const int* idx1, int nn1, const int* nodes2,
+                         const int* off2, const int* idx2, int nn2, float nnratio, int checkOri, int* matches12);
+int orc_search_for_triangulation(const uint8_t* d1, const float* x1, const float* y1, const float* ang1, const uint8_t* has1, int n1,
+                                 const uint8_t* d2, const float* x2, const float* y2, const float* ang2, const int* oct2,
+                                 const uint8_t* has2, int n2, const int* nodes1, const int* off1, const int* idx1, int nn1,
+                                 const int* nodes2, const int* off2, const int* idx2, int nn2, const float* F12, const float* sigma2,
+                                 int checkOri, int* matches12);
 void orc_synth_frame(uint8_t* dst, int rows, int cols, int step, uint64_t seed, uint64_t frame,
                      int variant, int right);
 // Multi-threaded CPU baseline: n frames of the synthetic generator, one frame

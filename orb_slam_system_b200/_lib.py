@@ -33,6 +33,17 @@ class OrbParams(C.Structure):
                 ("ini_th_fast", C.c_int32), ("min_th_fast", C.c_int32)]
 
 
+class OrbFrameView(C.Structure):
+    """orb_frame_view: what Frame::GetFeaturesInArea reads (src/Frame.cc:307-360)."""
+    _fields_ = [("keys_un", C.c_void_p), ("desc", C.c_void_p), ("n", C.c_int32), ("min_x", C.c_float),
+                ("min_y", C.c_float), ("grid_w_inv", C.c_float), ("grid_h_inv", C.c_float)]
+
+
+class OrbFeatureVector(C.Structure):
+    """orb_feature_vector: DBoW2::FeatureVector as CSR."""
+    _fields_ = [("nodes", C.c_void_p), ("off", C.c_void_p), ("idx", C.c_void_p), ("n_nodes", C.c_int32)]
+
+
 class OrbError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"orb_b200 error {code}: {msg}")
@@ -57,8 +68,9 @@ EXPORTS = [
     "orb_extractor_sync", "orb_extractor_stream", "orb_get_pyramid_level",
     "orb_extractor_level_stats", "orb_extractor_set_profiling", "orb_extractor_stage_times",
     "orb_stage_name", "orb_matcher_create", "orb_matcher_destroy", "orb_match_all",
-    "orb_match_all_batch", "orb_match_csr", "orb_stereo_match", "orb_matcher_sync",
-    "orb_matcher_stream", "orb_last_error", "orb_kernel_launch_count", "orb_version",
+    "orb_match_all_batch", "orb_match_csr", "orb_distances_csr", "orb_stereo_match", "orb_matcher_sync",
+    "orb_matcher_stream", "orb_window_search", "orb_search_by_projection_map", "orb_search_by_projection_best",
+    "orb_search_for_initialization", "orb_search_by_bow", "orb_search_for_triangulation", "orb_last_error", "orb_kernel_launch_count", "orb_version",
 ]
 
 
@@ -97,10 +109,18 @@ def lib():
         L.orb_match_all.argtypes = [vp, vp, i32, vp, i32, vp, vp, vp]
         L.orb_match_all_batch.argtypes = [vp, i32, vp, vp, sz, vp, vp, sz, vp, vp, vp, sz, i32]
         L.orb_match_csr.argtypes = [vp, vp, i32, vp, i32, vp, vp, i32, i32, vp, vp, vp]
+        L.orb_distances_csr.argtypes = [vp, vp, i32, vp, i32, vp, vp, vp]
         L.orb_stereo_match.argtypes = [vp, vp, vp, i32, vp, vp, i32, vp, i32, i32, C.c_float, C.c_float, vp, vp]
         L.orb_matcher_sync.argtypes = [vp]
         L.orb_matcher_stream.argtypes = [vp]
         L.orb_matcher_stream.restype = vp
+        f32 = C.c_float
+        L.orb_window_search.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp]
+        L.orb_search_by_projection_map.argtypes = [vp, vp, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, f32, f32, vp, vp]
+        L.orb_search_by_projection_best.argtypes = [vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp, vp]
+        L.orb_search_for_initialization.argtypes = [vp, vp, vp, i32, vp, vp, i32, f32, i32, vp, vp]
+        L.orb_search_by_bow.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp, i32, vp, vp, f32, i32, vp, vp]
+        L.orb_search_for_triangulation.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp, i32, vp, vp, vp, vp, i32, i32, vp, vp]
         L.orb_last_error.restype = C.c_char_p
         L.orb_kernel_launch_count.restype = C.c_uint64
         L.orb_version.restype = C.c_char_p

@@ -147,6 +147,215 @@ __global__ void __launch_bounds__(256) k_match_csr(const uint8_t* __restrict__ q
 }
 
 // ------------------------------------------------------------------------------------------
+// All candidate distances of a windowed search: out[c] = distance(query i, train cand[c]) for
+// c in [offsets[i], offsets[i+1]).  For the searches whose candidate eligibility depends on
+// earlier accepts (vbMatched2 in SearchByBoW, vMatchedDistance in SearchForInitialization,
+// claimed features in SearchByProjection): the host replays the reference's sequential scan
+// over these numbers.  One warp per query, one candidate per lane and step.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_dist_csr(const uint8_t* __restrict__ q, int nq, const uint8_t* __restrict__ t,
+                                                  const int* __restrict__ offsets, const int* __restrict__ cand,
+                                                  int* __restrict__ out) {
+    const int warp = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= nq) return;
+    const uint4* Q = reinterpret_cast<const uint4*>(q) + 2 * (size_t)warp;
+    const uint4 q0 = __ldg(Q), q1 = __ldg(Q + 1);
+    const uint4* T = reinterpret_cast<const uint4*>(t);
+    const int beg = __ldg(offsets + warp), end = __ldg(offsets + warp + 1);
+    for (int c = beg + lane; c < end; c += 32) {
+        const int j = __ldg(cand + c);
+        out[c] = hamming256(q0, q1, __ldg(T + 2 * (size_t)j), __ldg(T + 2 * (size_t)j + 1));
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Candidate windows on the device: Frame::AssignFeaturesToGrid / PosInGrid (reference
+// src/Frame.cc:210-225, :362-372) and Frame::GetFeaturesInArea (:307-360; KeyFrame twin
+// src/KeyFrame.cc:549-588).
+//
+// The 64 x 48 grid is kept in CSR form with cells numbered ix*48 + iy.  GetFeaturesInArea walks
+// `for ix { for iy { members } }`, so for one ix the cells iy = minY..maxY are one contiguous
+// slice of the member array: a query is at most 64 slices, each read with coalesced lanes.
+// Members of a cell are in ascending keypoint index (the reference push_back's in index order).
+// ------------------------------------------------------------------------------------------
+#define GRID_COLS 64
+#define GRID_ROWS 48
+#define GRID_CELLS (GRID_COLS * GRID_ROWS)
+
+__device__ __forceinline__ int pos_in_grid(const orb_kp28& k, float minX, float minY, float wInv, float hInv) {
+    // posX = round((kp.pt.x - mnMinX) * mfGridElementWidthInv): float product, C round() (half away from zero)
+    const float fx = roundf(__fmul_rn(__fsub_rn(k.x, minX), wInv));
+    const float fy = roundf(__fmul_rn(__fsub_rn(k.y, minY), hInv));
+    // NaN and out-of-range both fall out here; (int) of a huge float is UB in the reference, keys that far out never occur
+    if (!(fx >= 0.0f && fx < (float)GRID_COLS && fy >= 0.0f && fy < (float)GRID_ROWS)) return -1;
+    return (int)fx * GRID_ROWS + (int)fy;
+}
+
+// One CTA per frame view.  cell_start[GRID_CELLS + 1], members[n].
+__global__ void __launch_bounds__(1024) k_grid_assign(const orb_kp28* __restrict__ keys, int n, float minX, float minY,
+                                                      float wInv, float hInv, int* __restrict__ cell_start,
+                                                      int* __restrict__ members) {
+    __shared__ int cnt[GRID_CELLS];
+    __shared__ int warp_sum[32];
+    const int tid = threadIdx.x;
+    for (int c = tid; c < GRID_CELLS; c += 1024) cnt[c] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += 1024) {
+        const int c = pos_in_grid(keys[i], minX, minY, wInv, hInv);
+        if (c >= 0) atomicAdd(&cnt[c], 1);
+    }
+    __syncthreads();
+    // exclusive scan of 3072 counters: 3 per thread
+    const int a0 = cnt[3 * tid], a1 = cnt[3 * tid + 1], a2 = cnt[3 * tid + 2];
+    int v = a0 + a1 + a2;
+    const int lane = tid & 31, w = tid >> 5;
+    int inc = v;
+    for (int s = 1; s < 32; s <<= 1) {
+        const int o = __shfl_up_sync(0xffffffffu, inc, s);
+        if (lane >= s) inc += o;
+    }
+    if (lane == 31) warp_sum[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        int ws = warp_sum[lane];
+        for (int s = 1; s < 32; s <<= 1) {
+            const int o = __shfl_up_sync(0xffffffffu, ws, s);
+            if (lane >= s) ws += o;
+        }
+        warp_sum[lane] = ws;
+    }
+    __syncthreads();
+    const int base = inc - v + (w ? warp_sum[w - 1] : 0);
+    __syncthreads();
+    cnt[3 * tid] = base;
+    cnt[3 * tid + 1] = base + a0;
+    cnt[3 * tid + 2] = base + a0 + a1;
+    cell_start[3 * tid] = base;
+    cell_start[3 * tid + 1] = base + a0;
+    cell_start[3 * tid + 2] = base + a0 + a1;
+    if (tid == 1023) cell_start[GRID_CELLS] = base + v;
+    __syncthreads();
+    // scatter (any order), then order every cell's few members by index
+    for (int i = tid; i < n; i += 1024) {
+        const int c = pos_in_grid(keys[i], minX, minY, wInv, hInv);
+        if (c >= 0) members[atomicAdd(&cnt[c], 1)] = i;
+    }
+    __syncthreads();
+    for (int c = tid; c < GRID_CELLS; c += 1024) {
+        const int b = cell_start[c], e = cnt[c];  // cnt[c] now = end of cell c
+        for (int i = b + 1; i < e; ++i) {
+            const int key = members[i];
+            int j = i - 1;
+            while (j >= b && members[j] > key) {
+                members[j + 1] = members[j];
+                --j;
+            }
+            members[j + 1] = key;
+        }
+    }
+}
+
+// One warp per query.  FILL = false: counts[q] = number of candidates.  FILL = true: writes the
+// candidate indices (reference order) and their Hamming distances at offsets[q].
+template <bool FILL>
+__global__ void __launch_bounds__(256) k_window(const orb_kp28* __restrict__ keys, const uint8_t* __restrict__ tdesc,
+                                                const int* __restrict__ cell_start, const int* __restrict__ members,
+                                                float minX, float minY, float wInv, float hInv, int nq,
+                                                const uint8_t* __restrict__ qdesc, const float* __restrict__ qx,
+                                                const float* __restrict__ qy, const float* __restrict__ qr,
+                                                const int* __restrict__ qmin, const int* __restrict__ qmax,
+                                                int* __restrict__ counts, const int* __restrict__ offsets,
+                                                int* __restrict__ cand, int* __restrict__ dist) {
+    const int warp = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= nq) return;
+    const float x = qx[warp], y = qy[warp], r = qr[warp];
+    const int minLevel = qmin ? qmin[warp] : -1, maxLevel = qmax ? qmax[warp] : -1;
+    int total = 0;
+    // (int)floor((x - mnMinX - r) * inv), (int)ceil((x - mnMinX + r) * inv): float ops in source order
+    const float fx0 = floorf(__fmul_rn(__fsub_rn(__fsub_rn(x, minX), r), wInv));
+    const float fx1 = ceilf(__fmul_rn(__fadd_rn(__fsub_rn(x, minX), r), wInv));
+    const float fy0 = floorf(__fmul_rn(__fsub_rn(__fsub_rn(y, minY), r), hInv));
+    const float fy1 = ceilf(__fmul_rn(__fadd_rn(__fsub_rn(y, minY), r), hInv));
+    // the comparisons below are the reference's early returns, done on floats so that huge values cannot overflow an int
+    const bool empty = !(fx0 < (float)GRID_COLS) || !(fx1 >= 0.0f) || !(fy0 < (float)GRID_ROWS) || !(fy1 >= 0.0f);
+    if (!empty) {
+        const int cx0 = max(0, (int)fmaxf(fx0, -1.0f)), cx1 = min(GRID_COLS - 1, (int)fminf(fx1, (float)GRID_COLS));
+        const int cy0 = max(0, (int)fmaxf(fy0, -1.0f)), cy1 = min(GRID_ROWS - 1, (int)fminf(fy1, (float)GRID_ROWS));
+        const bool checkLevels = (minLevel > 0) || (maxLevel >= 0);
+        uint4 q0, q1;
+        int base = 0;
+        if (FILL) {
+            const uint4* Q = reinterpret_cast<const uint4*>(qdesc) + 2 * (size_t)warp;
+            q0 = __ldg(Q);
+            q1 = __ldg(Q + 1);
+            base = offsets[warp];
+        }
+        const uint4* T = reinterpret_cast<const uint4*>(tdesc);
+        for (int ix = cx0; ix <= cx1; ++ix) {
+            const int b = __ldg(cell_start + ix * GRID_ROWS + cy0), e = __ldg(cell_start + ix * GRID_ROWS + cy1 + 1);
+            for (int s = b; s < e; s += 32) {
+                const int m = s + lane;
+                bool ok = false;
+                int j = 0;
+                if (m < e) {
+                    j = __ldg(members + m);
+                    const orb_kp28 k = keys[j];
+                    ok = true;
+                    if (checkLevels) {
+                        if (k.octave < minLevel) ok = false;
+                        if (maxLevel >= 0 && k.octave > maxLevel) ok = false;
+                    }
+                    if (!(fabsf(__fsub_rn(k.x, x)) < r && fabsf(__fsub_rn(k.y, y)) < r)) ok = false;
+                }
+                const unsigned bal = __ballot_sync(0xffffffffu, ok);
+                if (FILL && ok) {
+                    const int o = base + total + __popc(bal & ((1u << lane) - 1u));
+                    cand[o] = j;
+                    dist[o] = hamming256(q0, q1, __ldg(T + 2 * (size_t)j), __ldg(T + 2 * (size_t)j + 1));
+                }
+                total += __popc(bal);
+            }
+        }
+    }
+    if (!FILL && lane == 0) counts[warp] = total;
+}
+
+// Exclusive scan of n ints by one CTA (n is a few thousand queries): out[0..n], out[n] = total.
+__global__ void __launch_bounds__(1024) k_scan_counts(const int* __restrict__ in, int n, int* __restrict__ out) {
+    __shared__ int warp_sum[32];
+    __shared__ int carry;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    if (tid == 0) carry = 0;
+    __syncthreads();
+    for (int b = 0; b < n; b += 1024) {
+        const int i = b + tid;
+        const int v = i < n ? in[i] : 0;
+        int inc = v;
+        for (int s = 1; s < 32; s <<= 1) {
+            const int o = __shfl_up_sync(0xffffffffu, inc, s);
+            if (lane >= s) inc += o;
+        }
+        if (lane == 31) warp_sum[w] = inc;
+        __syncthreads();
+        if (w == 0) {
+            int ws = warp_sum[lane];
+            for (int s = 1; s < 32; s <<= 1) {
+                const int o = __shfl_up_sync(0xffffffffu, ws, s);
+                if (lane >= s) ws += o;
+            }
+            warp_sum[lane] = ws;
+        }
+        __syncthreads();
+        const int c = carry;
+        if (i < n) out[i] = c + inc - v + (w ? warp_sum[w - 1] : 0);
+        __syncthreads();
+        if (tid == 0) carry = c + warp_sum[31];
+        __syncthreads();
+    }
+    if (tid == 0) out[n] = carry;
+}
+
+// ------------------------------------------------------------------------------------------
 // Stereo: Hamming part of Frame::ComputeStereoMatches (reference src/Frame.cc:446-529).
 // k_stereo_prep turns every right keypoint into (minr, maxr, x, octave) -- the rows of
 // vRowIndices it would be listed in (:463-473).  k_stereo_match: one warp per left keypoint,
@@ -228,6 +437,13 @@ cudaError_t orbk_match_csr(const uint8_t* q, int nq, const uint8_t* t, const int
     return cudaGetLastError();
 }
 
+cudaError_t orbk_dist_csr(const uint8_t* q, int nq, const uint8_t* t, const int* offsets, const int* cand, int* out, cudaStream_t st) {
+    if (nq <= 0) return cudaSuccess;
+    k_dist_csr<<<(nq + 7) / 8, 256, 0, st>>>(q, nq, t, offsets, cand, out);
+    orbk_count_launch(1);
+    return cudaGetLastError();
+}
+
 cudaError_t orbk_stereo(const orb_kp28* kl, const uint8_t* dl, int nl, const orb_kp28* kr, const uint8_t* dr, int nr,
                         const float* d_scale, int4* d_rinfo, float maxD, int* best_r, int* best_dist, cudaStream_t st) {
     if (nl <= 0) return cudaSuccess;
@@ -236,6 +452,35 @@ cudaError_t orbk_stereo(const orb_kp28* kl, const uint8_t* dl, int nl, const orb
         orbk_count_launch(1);
     }
     k_stereo_match<<<(nl + 7) / 8, 256, 0, st>>>(kl, dl, nl, d_rinfo, dr, nr, maxD, best_r, best_dist);
+    orbk_count_launch(1);
+    return cudaGetLastError();
+}
+
+cudaError_t orbk_grid_assign(const orb_kp28* keys, int n, float minX, float minY, float wInv, float hInv, int* cell_start, int* members,
+                             cudaStream_t st) {
+    k_grid_assign<<<1, 1024, 0, st>>>(keys, n, minX, minY, wInv, hInv, cell_start, members);
+    orbk_count_launch(1);
+    return cudaGetLastError();
+}
+
+cudaError_t orbk_window_count(const orb_kp28* keys, const int* cell_start, const int* members, float minX, float minY, float wInv,
+                              float hInv, int nq, const float* qx, const float* qy, const float* qr, const int* qmin, const int* qmax,
+                              int* counts, int* offsets, cudaStream_t st) {
+    if (nq <= 0) return cudaSuccess;
+    k_window<false><<<(nq + 7) / 8, 256, 0, st>>>(keys, nullptr, cell_start, members, minX, minY, wInv, hInv, nq, nullptr, qx, qy, qr,
+                                                   qmin, qmax, counts, nullptr, nullptr, nullptr);
+    k_scan_counts<<<1, 1024, 0, st>>>(counts, nq, offsets);
+    orbk_count_launch(2);
+    return cudaGetLastError();
+}
+
+cudaError_t orbk_window_fill(const orb_kp28* keys, const uint8_t* tdesc, const int* cell_start, const int* members, float minX,
+                             float minY, float wInv, float hInv, int nq, const uint8_t* qdesc, const float* qx, const float* qy,
+                             const float* qr, const int* qmin, const int* qmax, const int* offsets, int* cand, int* dist,
+                             cudaStream_t st) {
+    if (nq <= 0) return cudaSuccess;
+    k_window<true><<<(nq + 7) / 8, 256, 0, st>>>(keys, tdesc, cell_start, members, minX, minY, wInv, hInv, nq, qdesc, qx, qy, qr, qmin,
+                                                  qmax, nullptr, offsets, cand, dist);
     orbk_count_launch(1);
     return cudaGetLastError();
 }

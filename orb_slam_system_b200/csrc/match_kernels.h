@@ -13,5 +13,17 @@ cudaError_t orbk_match_all(const uint8_t* q, const int* nq, size_t q_stride, con
                            size_t out_stride, cudaStream_t st);
 cudaError_t orbk_match_csr(const uint8_t* q, int nq, const uint8_t* t, const int* offsets, const int* cand, int tie_last,
                            int max_dist, int* best_idx, int* best_dist, int* second_dist, cudaStream_t st);
+cudaError_t orbk_dist_csr(const uint8_t* q, int nq, const uint8_t* t, const int* offsets, const int* cand, int* out, cudaStream_t st);
 cudaError_t orbk_stereo(const orb_kp28* kl, const uint8_t* dl, int nl, const orb_kp28* kr, const uint8_t* dr, int nr,
                         const float* d_scale, int4* d_rinfo, float maxD, int* best_r, int* best_dist, cudaStream_t st);
+// Frame grid (Frame::AssignFeaturesToGrid) and Frame::GetFeaturesInArea windows with their distances.
+// cell_start: 64*48+1 ints, members: n ints.  window_count writes counts[nq] and offsets[nq+1].
+cudaError_t orbk_grid_assign(const orb_kp28* keys, int n, float minX, float minY, float wInv, float hInv, int* cell_start, int* members,
+                             cudaStream_t st);
+cudaError_t orbk_window_count(const orb_kp28* keys, const int* cell_start, const int* members, float minX, float minY, float wInv,
+                              float hInv, int nq, const float* qx, const float* qy, const float* qr, const int* qmin, const int* qmax,
+                              int* counts, int* offsets, cudaStream_t st);
+cudaError_t orbk_window_fill(const orb_kp28* keys, const uint8_t* tdesc, const int* cell_start, const int* members, float minX,
+                             float minY, float wInv, float hInv, int nq, const uint8_t* qdesc, const float* qx, const float* qy,
+                             const float* qr, const int* qmin, const int* qmax, const int* offsets, int* cand, int* dist,
+                             cudaStream_t st);

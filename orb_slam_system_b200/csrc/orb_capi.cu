@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "../../include/orb_b200.h"
+#include "capi_internal.h"
 #include "extract_kernels.h"
 #include "match_kernels.h"
 #include "orb_plan.h"
@@ -28,7 +29,7 @@ static_assert(sizeof(orb_keypoint_dev) == 28 && sizeof(orb_kp28) == 28, "device 
 // errors
 // ------------------------------------------------------------------------------------------
 static thread_local std::string t_err;
-static int fail(int code, const char* fmt, ...) {
+int orb_fail(int code, const char* fmt, ...) {
     char buf[512];
     va_list ap;
     va_start(ap, fmt);
@@ -37,11 +38,7 @@ static int fail(int code, const char* fmt, ...) {
     t_err = buf;
     return code;
 }
-#define CUDA_TRY(expr)                                                                              \
-    do {                                                                                            \
-        cudaError_t _e = (expr);                                                                    \
-        if (_e != cudaSuccess) return fail(ORB_ERR_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
-    } while (0)
+#define fail orb_fail
 
 extern "C" const char* orb_last_error(void) { return t_err.c_str(); }
 extern "C" uint64_t orb_kernel_launch_count(void) { return orbk_launch_count(); }
@@ -876,15 +873,7 @@ extern "C" int orb_extractor_level_stats(orb_extractor* h, int frame, int32_t* c
 // ------------------------------------------------------------------------------------------
 // matcher handle
 // ------------------------------------------------------------------------------------------
-struct orb_matcher {
-    int device = 0;
-    cudaStream_t stream = nullptr;
-    // grow-only device scratch for the host-buffer entry points
-    void* buf[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    size_t cap[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-};
-
-static int scratch(orb_matcher* m, int slot, size_t bytes, void** out) {
+int orb_matcher_scratch(orb_matcher* m, int slot, size_t bytes, void** out) {
     if (bytes > m->cap[slot]) {
         CUDA_TRY(cudaStreamSynchronize(m->stream));
         if (m->buf[slot]) cudaFree(m->buf[slot]);
@@ -897,6 +886,7 @@ static int scratch(orb_matcher* m, int slot, size_t bytes, void** out) {
     *out = m->buf[slot];
     return ORB_OK;
 }
+#define scratch orb_matcher_scratch
 
 extern "C" int orb_matcher_create(int device, orb_matcher** out) {
     if (!out) return fail(ORB_ERR_INVALID, "null argument");
@@ -921,7 +911,7 @@ extern "C" void orb_matcher_destroy(orb_matcher* m) {
     if (!m) return;
     cudaSetDevice(m->device);
     cudaStreamSynchronize(m->stream);
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < orb_matcher::kSlots; ++i)
         if (m->buf[i]) cudaFree(m->buf[i]);
     cudaStreamDestroy(m->stream);
     delete m;
@@ -1025,6 +1015,37 @@ extern "C" int orb_match_csr(orb_matcher* m, const uint8_t* q, int nq, const uin
     CUDA_TRY(cudaMemcpyAsync(best_idx, o, sizeof(int) * nq, cudaMemcpyDeviceToHost, m->stream));
     CUDA_TRY(cudaMemcpyAsync(best_dist, o + nq, sizeof(int) * nq, cudaMemcpyDeviceToHost, m->stream));
     CUDA_TRY(cudaMemcpyAsync(second_dist, o + 2 * (size_t)nq, sizeof(int) * nq, cudaMemcpyDeviceToHost, m->stream));
+    CUDA_TRY(cudaStreamSynchronize(m->stream));
+    return ORB_OK;
+}
+
+extern "C" int orb_distances_csr(orb_matcher* m, const uint8_t* q, int nq, const uint8_t* t, int nt, const int32_t* offsets,
+                                 const int32_t* cand, int32_t* dist) {
+    if (!m || !offsets) return fail(ORB_ERR_INVALID, "null argument");
+    if (nq < 0 || nt < 0) return fail(ORB_ERR_INVALID, "negative count");
+    if (nq == 0) return ORB_OK;
+    const int ncand = offsets[nq];
+    if (ncand < 0 || offsets[0] != 0) return fail(ORB_ERR_INVALID, "offsets must start at 0 and be non-decreasing");
+    for (int i = 0; i < nq; ++i)
+        if (offsets[i + 1] < offsets[i]) return fail(ORB_ERR_INVALID, "offsets must be non-decreasing");
+    if (ncand == 0) return ORB_OK;
+    if (!cand || !dist) return fail(ORB_ERR_INVALID, "null argument");
+    for (int c = 0; c < ncand; ++c)
+        if (cand[c] < 0 || cand[c] >= nt) return fail(ORB_ERR_INVALID, "candidate %d out of range", c);
+    CUDA_TRY(cudaSetDevice(m->device));
+    void *dq, *dt, *dofs, *dout;
+    int rc;
+    if ((rc = scratch(m, 0, (size_t)nq * 32 + 32, &dq)) || (rc = scratch(m, 1, (size_t)nt * 32 + 32, &dt)) ||
+        (rc = scratch(m, 2, sizeof(int) * ((size_t)nq + 1 + ncand), &dofs)) || (rc = scratch(m, 3, sizeof(int) * (size_t)ncand, &dout)))
+        return rc;
+    CUDA_TRY(cudaMemcpyAsync(dq, q, (size_t)nq * 32, cudaMemcpyHostToDevice, m->stream));
+    CUDA_TRY(cudaMemcpyAsync(dt, t, (size_t)nt * 32, cudaMemcpyHostToDevice, m->stream));
+    int* d_off = (int*)dofs;
+    int* d_cand = d_off + nq + 1;
+    CUDA_TRY(cudaMemcpyAsync(d_off, offsets, sizeof(int) * ((size_t)nq + 1), cudaMemcpyHostToDevice, m->stream));
+    CUDA_TRY(cudaMemcpyAsync(d_cand, cand, sizeof(int) * (size_t)ncand, cudaMemcpyHostToDevice, m->stream));
+    CUDA_TRY(orbk_dist_csr((const uint8_t*)dq, nq, (const uint8_t*)dt, d_off, d_cand, (int*)dout, m->stream));
+    CUDA_TRY(cudaMemcpyAsync(dist, dout, sizeof(int) * (size_t)ncand, cudaMemcpyDeviceToHost, m->stream));
     CUDA_TRY(cudaStreamSynchronize(m->stream));
     return ORB_OK;
 }
