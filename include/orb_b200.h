@@ -192,6 +192,18 @@ int orb_stereo_match(orb_matcher* m, const orb_keypoint* kps_left, const uint8_t
                      int n_right, const float* scale, int nlevels, int rows, float bf, float fx,
                      int32_t* best_r, int32_t* best_dist);
 
+/* Frame::ComputeStereoMatches whole (src/Frame.cc:446-619): the Hamming search above, the 11x11 SAD sliding
+ * window on the pyramid level of the left keypoint (:531-575), the parabola fit (:577-586), the disparity
+ * gate (:588-603) and the median * 2.1 cut (:606-619).  The pyramids are read where the two extractor
+ * handles left them on the device (frame `frame_left` of ex_left's last call, `frame_right` of ex_right's;
+ * the two may be the same handle holding the pair in one batch), so mvImagePyramid never travels to the host.
+ * u_right / depth = Frame::mvuRight / mvDepth (n_left floats, -1 where there is no match).  Inputs on which
+ * the reference itself faults (row band outside the image, SAD window outside its level) -> ORB_ERR_SHAPE. */
+int orb_compute_stereo_matches(orb_matcher* m, orb_extractor* ex_left, int frame_left, orb_extractor* ex_right,
+                               int frame_right, const orb_keypoint* kps_left, const uint8_t* desc_left, int n_left,
+                               const orb_keypoint* kps_right, const uint8_t* desc_right, int n_right, float bf,
+                               float fx, float* u_right, float* depth);
+
 int orb_matcher_sync(orb_matcher* m);
 void* orb_matcher_stream(orb_matcher* m);
 

@@ -222,6 +222,25 @@ def stereo_match(kl, dl, kr, dr, scale, rows, bf, fx):
     return br, bd
 
 
+def compute_stereo_matches(img_l, img_r, kl, dl, kr, dr, bf, fx, scaleFactor=1.2, nlevels=8):
+    """Frame::ComputeStereoMatches whole (Hamming search, SAD refinement, parabola, median cut): (mvuRight, mvDepth)."""
+    img_l, img_r = _img(img_l), _img(img_r)
+    assert img_l.shape == img_r.shape and img_l.strides == img_r.strides
+    kl = np.ascontiguousarray(kl, KP_DTYPE)
+    kr = np.ascontiguousarray(kr, KP_DTYPE)
+    dl = np.ascontiguousarray(dl, np.uint8)
+    dr = np.ascontiguousarray(dr, np.uint8)
+    ur = np.zeros(len(kl), np.float32)
+    dep = np.zeros(len(kl), np.float32)
+    lib().orc_compute_stereo_matches.restype = C.c_int
+    rc = lib().orc_compute_stereo_matches(C.c_float(scaleFactor), nlevels, _p(img_l), _p(img_r), img_l.shape[0], img_l.shape[1],
+                                          img_l.strides[0], _p(kl), _p(dl), len(kl), _p(kr), _p(dr), len(kr), C.c_float(bf),
+                                          C.c_float(fx), _p(ur), _p(dep))
+    if rc != 0:
+        raise RuntimeError(f"reference faults on this input (rc={rc})")
+    return ur, dep
+
+
 def _featvec_csr(fv):
     """dict node -> list of feature indices  ->  (sorted nodes, offsets, flat indices) int32 arrays."""
     nodes = np.array(sorted(fv), np.int32)

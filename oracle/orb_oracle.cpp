@@ -776,6 +776,161 @@ int orc_stereo_match(const KeyPoint* kl, const uint8_t* dl, int nl, const KeyPoi
     return 0;
 }
 
+// Frame::ComputeStereoMatches whole, reference Frame.cc:446-619: the Hamming search above, then the
+// 11x11 SAD sliding window on the pyramid level of the left keypoint (:531-575), the parabola fit
+// (:577-586), the disparity gate (:588-603) and the median*2.1 outlier cut (:606-619).
+// The pyramids are ComputePyramid's (ORBextractor.cc:497-515) of the two level-0 images.
+// mvuRight / mvDepth get nl floats.  Returns 0; -1 if a right keypoint's row band leaves the image
+// (out-of-bounds vRowIndices); -2 if a rowRange / colRange leaves its level image (cv::Exception in
+// the reference).  An empty vDistIdx (the reference then reads vDistIdx[0] of an empty vector) is
+// treated as "nothing to cut".
+int orc_compute_stereo_matches(float scaleFactor, int nlevels, const uint8_t* imgL, const uint8_t* imgR, int rows, int cols, int step,
+                               const KeyPoint* kl, const uint8_t* dl, int nl, const KeyPoint* kr, const uint8_t* dr, int nr, float mbf,
+                               float fx, float* mvuRight, float* mvDepth) {
+    const int TH_HIGH = 100, TH_LOW = 50;
+    Tables t = make_tables(Params{1000, scaleFactor, nlevels, 20, 7});
+    const std::vector<float>& mvScaleFactors = t.scale;
+    const std::vector<float>& mvInvScaleFactors = t.inv_scale;
+    // both pyramids
+    std::vector<std::vector<uint8_t>> pyr[2];
+    std::vector<int> lr(nlevels), lc(nlevels);
+    for (int side = 0; side < 2; ++side) {
+        const uint8_t* img = side ? imgR : imgL;
+        pyr[side].resize(nlevels);
+        for (int l = 0; l < nlevels; ++l) {
+            lc[l] = l ? cv_round_f(cols * t.inv_scale[l]) : cols;
+            lr[l] = l ? cv_round_f(rows * t.inv_scale[l]) : rows;
+            pyr[side][l].assign((size_t)lr[l] * lc[l], 0);
+            if (l == 0)
+                for (int y = 0; y < rows; ++y) memcpy(&pyr[side][0][(size_t)y * cols], img + (size_t)y * step, cols);
+            else
+                resize_linear_u8(Image{pyr[side][l - 1].data(), lr[l - 1], lc[l - 1], lc[l - 1]}, pyr[side][l].data(), lr[l], lc[l], lc[l]);
+        }
+    }
+    const int N = nl;
+    for (int i = 0; i < N; ++i) {
+        mvuRight[i] = -1.0f;
+        mvDepth[i] = -1.0f;
+    }
+    const int thOrbDist = (TH_HIGH + TH_LOW) / 2;
+    const int nRows = rows;
+    std::vector<std::vector<size_t>> vRowIndices(nRows);
+    for (int iR = 0; iR < nr; iR++) {
+        const float kpY = kr[iR].y;
+        const float r = 2.0f * mvScaleFactors[kr[iR].octave];
+        const int maxr = ceil(kpY + r);
+        const int minr = floor(kpY - r);
+        if (minr < 0 || maxr >= nRows) return -1;
+        for (int yi = minr; yi <= maxr; yi++) vRowIndices[yi].push_back(iR);
+    }
+    const float mb = mbf / fx;
+    const float minZ = mb;
+    const float minD = 0;
+    const float maxD = mbf / minZ;
+    std::vector<std::pair<int, int>> vDistIdx;
+    for (int iL = 0; iL < N; iL++) {
+        const KeyPoint& kpL = kl[iL];
+        const int levelL = kpL.octave;
+        const float vL = kpL.y;
+        const float uL = kpL.x;
+        const std::vector<size_t>& vCandidates = vRowIndices[(size_t)vL];
+        if (vCandidates.empty()) continue;
+        const float minU = uL - maxD;
+        const float maxU = uL - minD;
+        if (maxU < 0) continue;
+        int bestDist = TH_HIGH;
+        size_t bestIdxR = 0;
+        for (size_t iC = 0; iC < vCandidates.size(); iC++) {
+            const size_t iR = vCandidates[iC];
+            const KeyPoint& kpR = kr[iR];
+            if (kpR.octave < levelL - 1 || kpR.octave > levelL + 1) continue;
+            const float uR = kpR.x;
+            if (uR >= minU && uR <= maxU) {
+                const int dist = descriptor_distance(dl + 32 * (size_t)iL, dr + 32 * iR);
+                if (dist < bestDist) {
+                    bestDist = dist;
+                    bestIdxR = iR;
+                }
+            }
+        }
+        if (bestDist < thOrbDist) {
+            const float uR0 = kr[bestIdxR].x;
+            const float scaleFactorL = mvInvScaleFactors[kpL.octave];
+            const float scaleduL = round(kpL.x * scaleFactorL);
+            const float scaledvL = round(kpL.y * scaleFactorL);
+            const float scaleduR0 = round(uR0 * scaleFactorL);
+            const int w = 5;
+            const int R = lr[kpL.octave], C = lc[kpL.octave];
+            const uint8_t* PL = pyr[0][kpL.octave].data();
+            const uint8_t* PR = pyr[1][kpL.octave].data();
+            // IL = left.rowRange(scaledvL-w, scaledvL+w+1).colRange(scaleduL-w, scaleduL+w+1)
+            const int r0 = (int)(scaledvL - w), r1 = (int)(scaledvL + w + 1);
+            const int c0 = (int)(scaleduL - w), c1 = (int)(scaleduL + w + 1);
+            if (r0 < 0 || r1 > R || c0 < 0 || c1 > C) return -2;
+            float IL[11][11];
+            for (int a = 0; a < 11; ++a)
+                for (int b = 0; b < 11; ++b) IL[a][b] = (float)PL[(size_t)(r0 + a) * C + c0 + b];
+            const float cL = IL[w][w];
+            for (int a = 0; a < 11; ++a)
+                for (int b = 0; b < 11; ++b) IL[a][b] = IL[a][b] - cL * 1.0f;
+            int bestDistS = INT_MAX;
+            int bestincR = 0;
+            const int L = 5;
+            std::vector<float> vDists(2 * L + 1);
+            const float iniu = scaleduR0 + L - w;
+            const float endu = scaleduR0 + L + w + 1;
+            if (iniu < 0 || endu >= C) continue;
+            for (int incR = -L; incR <= +L; incR++) {
+                const int q0 = (int)(scaleduR0 + incR - w), q1 = (int)(scaleduR0 + incR + w + 1);
+                if (q0 < 0 || q1 > C) return -2;
+                float IR[11][11];
+                for (int a = 0; a < 11; ++a)
+                    for (int b = 0; b < 11; ++b) IR[a][b] = (float)PR[(size_t)(r0 + a) * C + q0 + b];
+                const float cR = IR[w][w];
+                double acc = 0;  // cv::norm(IL, IR, NORM_L1): sum of |a - b| in double
+                for (int a = 0; a < 11; ++a)
+                    for (int b = 0; b < 11; ++b) acc += std::fabs((double)(IL[a][b] - (IR[a][b] - cR * 1.0f)));
+                float dist = (float)acc;
+                if (dist < bestDistS) {
+                    bestDistS = dist;
+                    bestincR = incR;
+                }
+                vDists[L + incR] = dist;
+            }
+            if (bestincR == -L || bestincR == L) continue;
+            const float dist1 = vDists[L + bestincR - 1];
+            const float dist2 = vDists[L + bestincR];
+            const float dist3 = vDists[L + bestincR + 1];
+            const float deltaR = (dist1 - dist3) / (2.0f * (dist1 + dist3 - 2.0f * dist2));
+            if (deltaR < -1 || deltaR > 1) continue;
+            float bestuR = mvScaleFactors[kpL.octave] * ((float)scaleduR0 + (float)bestincR + deltaR);
+            float disparity = (uL - bestuR);
+            if (disparity >= minD && disparity < maxD) {
+                if (disparity <= 0) {
+                    disparity = 0.01;
+                    bestuR = uL - 0.01;
+                }
+                mvDepth[iL] = mbf / disparity;
+                mvuRight[iL] = bestuR;
+                vDistIdx.push_back(std::pair<int, int>(bestDistS, iL));
+            }
+        }
+    }
+    if (vDistIdx.empty()) return 0;
+    sort(vDistIdx.begin(), vDistIdx.end());
+    const float median = vDistIdx[vDistIdx.size() / 2].first;
+    const float thDist = 1.5f * 1.4f * median;
+    for (int i = (int)vDistIdx.size() - 1; i >= 0; i--) {
+        if (vDistIdx[i].first < thDist)
+            break;
+        else {
+            mvuRight[vDistIdx[i].second] = -1;
+            mvDepth[vDistIdx[i].second] = -1;
+        }
+    }
+    return 0;
+}
+
 // ---- ORBmatcher::ComputeThreeMaxima, reference ORBmatcher.cc:469-502 ----
 static void three_maxima(const std::vector<int>* histo, int L, int& ind1, int& ind2, int& ind3) {
     int topIdx[3] = {-1, -1, -1}, topVal[3] = {0, 0, 0};

@@ -415,6 +415,103 @@ __global__ void __launch_bounds__(256) k_stereo_match(const orb_kp28* __restrict
 }
 
 // ------------------------------------------------------------------------------------------
+// Stereo refinement: the rest of Frame::ComputeStereoMatches after the Hamming search
+// (reference src/Frame.cc:531-603): 11x11 SAD of the centre-subtracted patches over 11 shifts on the
+// pyramid level of the left keypoint, first minimum, parabola fit, disparity gate.  One warp per left
+// keypoint; the left patch and the 11 x 21 right strip are staged in shared memory, lane s < 11 sums
+// shift s.  Pixels are integers, so the float sums of the reference are exact integers here.
+// Outputs per left keypoint: uRight / depth (-1 when rejected) and the best SAD (-1 when rejected) for
+// the median cut (:606-619), which the caller does once it has all of them.
+// flags[0] |= 1 when a rowRange / colRange would leave the level image (cv::Exception in the reference).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_stereo_refine(const orb_kp28* __restrict__ kl, int nl, const orb_kp28* __restrict__ kr,
+                                                       const int* __restrict__ best_r, const int* __restrict__ best_dist,
+                                                       const OrbStereoLevels lv, float mbf, float maxD, float* __restrict__ u_right,
+                                                       float* __restrict__ depth, int* __restrict__ sad, int* __restrict__ flags) {
+    __shared__ int s_l[8][121];
+    __shared__ int s_r[8][11 * 21];
+    __shared__ int s_d[8][12];
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int i = (blockIdx.x * 256 + threadIdx.x) >> 5;
+    if (i >= nl) return;
+    float outU = -1.0f, outD = -1.0f;
+    int outS = -1;
+    const int bi = best_r[i];
+    if (bi >= 0 && best_dist[i] < 75) {  // thOrbDist = (TH_HIGH + TH_LOW) / 2, :451, :532
+        const orb_kp28 kpL = kl[i];
+        const int oct = kpL.octave;
+        const float uR0 = kr[bi].x;
+        const float sf = lv.inv_scale[oct];
+        const float scaleduL = roundf(__fmul_rn(kpL.x, sf));
+        const float scaledvL = roundf(__fmul_rn(kpL.y, sf));
+        const float scaleduR0 = roundf(__fmul_rn(uR0, sf));
+        const int R = lv.rows[oct], C = lv.cols[oct];
+        const int r0 = (int)(scaledvL - 5.0f), c0 = (int)(scaleduL - 5.0f), q0 = (int)(scaleduR0 - 10.0f);
+        bool ok = true;
+        if (r0 < 0 || r0 + 11 > R || c0 < 0 || c0 + 11 > C) {  // IL's rowRange / colRange (:542)
+            if (lane == 0) atomicOr(flags, 1);
+            ok = false;
+        }
+        // iniu = scaleduR0 + L - w, endu = scaleduR0 + L + w + 1 (:553-556)
+        if (ok && (scaleduR0 < 0.0f || scaleduR0 + 11.0f >= (float)C)) ok = false;
+        if (ok && q0 < 0) {  // first colRange of the loop starts at scaleduR0 - L - w (:560)
+            if (lane == 0) atomicOr(flags, 1);
+            ok = false;
+        }
+        if (ok) {
+            const uint8_t* PL = lv.left[oct] + (size_t)r0 * lv.pitch[oct] + c0;
+            const uint8_t* PR = lv.right[oct] + (size_t)r0 * lv.pitch[oct] + q0;
+            for (int e = lane; e < 121; e += 32) s_l[wib][e] = PL[(e / 11) * lv.pitch[oct] + (e % 11)];
+            for (int e = lane; e < 231; e += 32) s_r[wib][e] = PR[(e / 21) * lv.pitch[oct] + (e % 21)];
+            __syncwarp();
+            if (lane < 11) {
+                const int cL = s_l[wib][5 * 11 + 5], cR = s_r[wib][5 * 21 + lane + 5];
+                const int dc = cL - cR;
+                int acc = 0;
+                for (int a = 0; a < 11; ++a)
+#pragma unroll
+                    for (int b = 0; b < 11; ++b) acc += abs(s_l[wib][a * 11 + b] - s_r[wib][a * 21 + b + lane] - dc);
+                s_d[wib][lane] = acc;
+            }
+            __syncwarp();
+            if (lane == 0) {
+                int bestS = 2147483647, bestinc = 0;
+                for (int s2 = 0; s2 < 11; ++s2)
+                    if (s_d[wib][s2] < bestS) {  // float dist < int bestDist, exact
+                        bestS = s_d[wib][s2];
+                        bestinc = s2 - 5;
+                    }
+                if (bestinc != -5 && bestinc != 5) {
+                    const float dist1 = (float)s_d[wib][5 + bestinc - 1], dist2 = (float)s_d[wib][5 + bestinc];
+                    const float dist3 = (float)s_d[wib][5 + bestinc + 1];
+                    const float deltaR = __fdiv_rn(__fsub_rn(dist1, dist3),
+                                                   __fmul_rn(2.0f, __fsub_rn(__fadd_rn(dist1, dist3), __fmul_rn(2.0f, dist2))));
+                    if (!(deltaR < -1.0f || deltaR > 1.0f)) {
+                        float bestuR = __fmul_rn(lv.scale[oct], __fadd_rn(__fadd_rn(scaleduR0, (float)bestinc), deltaR));
+                        float disparity = __fsub_rn(kpL.x, bestuR);
+                        if (disparity >= 0.0f && disparity < maxD) {
+                            if (disparity <= 0.0f) {
+                                disparity = 0.01f;                       // float(0.01)
+                                bestuR = (float)((double)kpL.x - 0.01);  // uL - 0.01 in double, then to float
+                            }
+                            outD = __fdiv_rn(mbf, disparity);
+                            outU = bestuR;
+                            outS = bestS;
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    }
+    if (lane == 0) {
+        u_right[i] = outU;
+        depth[i] = outD;
+        sad[i] = outS;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------
 void orbk_count_launch(int n);
@@ -481,6 +578,15 @@ cudaError_t orbk_window_fill(const orb_kp28* keys, const uint8_t* tdesc, const i
     if (nq <= 0) return cudaSuccess;
     k_window<true><<<(nq + 7) / 8, 256, 0, st>>>(keys, tdesc, cell_start, members, minX, minY, wInv, hInv, nq, qdesc, qx, qy, qr, qmin,
                                                   qmax, nullptr, offsets, cand, dist);
+    orbk_count_launch(1);
+    return cudaGetLastError();
+}
+
+cudaError_t orbk_stereo_refine(const orb_kp28* kl, int nl, const orb_kp28* kr, const int* best_r, const int* best_dist,
+                               const OrbStereoLevels& lv, float mbf, float maxD, float* u_right, float* depth, int* sad, int* flags,
+                               cudaStream_t st) {
+    if (nl <= 0) return cudaSuccess;
+    k_stereo_refine<<<(nl + 7) / 8, 256, 0, st>>>(kl, nl, kr, best_r, best_dist, lv, mbf, maxD, u_right, depth, sad, flags);
     orbk_count_launch(1);
     return cudaGetLastError();
 }

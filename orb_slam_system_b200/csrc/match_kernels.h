@@ -8,6 +8,15 @@ struct orb_kp28 {  // cv::KeyPoint layout
     int octave, class_id;
 };
 
+// Pyramid levels of a stereo pair as the refinement kernel reads them (device pointers, level l of the left and
+// the right image have the same shape and pitch).
+struct OrbStereoLevels {
+    const uint8_t* left[16];
+    const uint8_t* right[16];
+    int pitch[16], rows[16], cols[16];
+    float scale[16], inv_scale[16];
+};
+
 cudaError_t orbk_match_all(const uint8_t* q, const int* nq, size_t q_stride, const uint8_t* t, const int* nt,
                            size_t t_stride, int npairs, int max_nq, int* best_idx, int* best_dist, int* second_dist,
                            size_t out_stride, cudaStream_t st);
@@ -27,3 +36,7 @@ cudaError_t orbk_window_fill(const orb_kp28* keys, const uint8_t* tdesc, const i
                              float minY, float wInv, float hInv, int nq, const uint8_t* qdesc, const float* qx, const float* qy,
                              const float* qr, const int* qmin, const int* qmax, const int* offsets, int* cand, int* dist,
                              cudaStream_t st);
+// Frame::ComputeStereoMatches after the Hamming search (src/Frame.cc:531-603): SAD refinement, parabola, disparity gate.
+cudaError_t orbk_stereo_refine(const orb_kp28* kl, int nl, const orb_kp28* kr, const int* best_r, const int* best_dist,
+                               const OrbStereoLevels& lv, float mbf, float maxD, float* u_right, float* depth, int* sad, int* flags,
+                               cudaStream_t st);

@@ -179,6 +179,19 @@ class ORBmatcher:
                                      rows, C.c_float(bf), C.c_float(fx), ptr(br), ptr(bd)))
         return br, bd
 
+    # ---- Frame::ComputeStereoMatches whole (src/Frame.cc:446-619) ----
+    def ComputeStereoMatches(self, ex_left, ex_right, kps_left, desc_left, kps_right, desc_right, bf, fx, frame_left=0, frame_right=0):
+        """Hamming search + SAD sub-pixel refinement + median cut; the pyramids are read on the device from the two
+        ORBextractor objects (their last call).  Returns (mvuRight, mvDepth)."""
+        kl = np.ascontiguousarray(kps_left, KP_DTYPE)
+        kr = np.ascontiguousarray(kps_right, KP_DTYPE)
+        dl, dr = _desc(desc_left), _desc(desc_right)
+        ur = np.full(len(kl), -1, np.float32)
+        dep = np.full(len(kl), -1, np.float32)
+        check(lib().orb_compute_stereo_matches(self._h, ex_left._h, frame_left, ex_right._h, frame_right, ptr(kl), ptr(dl), len(kl),
+                                               ptr(kr), ptr(dr), len(kr), C.c_float(bf), C.c_float(fx), ptr(ur), ptr(dep)))
+        return ur, dep
+
     # ---- candidate windows: Frame::GetFeaturesInArea for many queries (src/Frame.cc:307-360) ----
     def window_search(self, F, qdesc, x, y, r, min_level=None, max_level=None):
         """Returns (offsets[nq+1], cand, dist): reference candidate order and DescriptorDistance of each."""

@@ -115,3 +115,29 @@ def test_stereo_match(rows, cols, nf):
     assert (br >= 0).sum() > 100
     ex.close()
     m.close()
+
+
+@pytest.mark.parametrize("rows,cols,nf,frame", [(480, 752, 1200, 1), (376, 1241, 2000, 0), (376, 1241, 2000, 5)])
+def test_compute_stereo_matches_whole(rows, cols, nf, frame):
+    # Frame::ComputeStereoMatches end to end: Hamming search, SAD refinement on the device pyramids, parabola,
+    # disparity gate, median cut -> mvuRight / mvDepth identical to the oracle (float ops replayed in order)
+    img_l = oracle.synth_frame(rows, cols, frame=frame)
+    img_r = oracle.synth_frame(rows, cols, frame=frame, right=1)
+    bf, fx = 47.90639384423901, 435.2046959714599
+    exl, exr = ORBextractor(nf, 1.2, 8, 20, 7), ORBextractor(nf, 1.2, 8, 20, 7)  # one instance per camera (Tracking.cc:76-82)
+    kl, dl = exl(img_l)
+    kr, dr = exr(img_r)
+    m = ORBmatcher()
+    ur, dep = m.ComputeStereoMatches(exl, exr, kl, dl, kr, dr, bf, fx)
+    our, odep = oracle.compute_stereo_matches(img_l, img_r, kl, dl, kr, dr, bf, fx)
+    assert ur.tobytes() == our.tobytes() and dep.tobytes() == odep.tobytes()
+    assert (ur >= 0).sum() > 500
+    # the pair inside one batch of a single extractor (frames 0 and 1)
+    exb = ORBextractor(nf, 1.2, 8, 20, 7, max_batch=2)
+    res = exb.extract_batch(np.stack([img_l, img_r]))
+    (kl2, dl2), (kr2, dr2) = res[0], res[1]
+    ur2, dep2 = m.ComputeStereoMatches(exb, exb, kl2, dl2, kr2, dr2, bf, fx, frame_left=0, frame_right=1)
+    assert ur2.tobytes() == our.tobytes() and dep2.tobytes() == odep.tobytes()
+    for e in (exl, exr, exb):
+        e.close()
+    m.close()

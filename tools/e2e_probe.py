@@ -1,4 +1,5 @@
-"""Quick end-to-end timing of orb_extract_batch with pinned host buffers (no device-resident pass)."""
+"""End-to-end timing of the async host API (submit/wait, two batches in flight, pinned buffers) with the host
+time spent inside submit and wait, for the chunk size / lane count given in ORB_B200_CHUNK / ORB_B200_LANES."""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -10,11 +11,23 @@ pin = torch.empty((R, B, ROWS, COLS), dtype=torch.uint8, pin_memory=True)
 for r in range(R): pin.numpy()[r] = np.roll(frames, r, axis=0)
 ex = ORBextractor(2000, 1.2, 8, 20, 7, max_batch=B, max_rows=ROWS, max_cols=COLS)
 cap = ex.keypoint_bound(ROWS, COLS)
-hk = torch.empty((B, cap, 28), dtype=torch.uint8, pin_memory=True)
-hd = torch.empty((B, cap, 32), dtype=torch.uint8, pin_memory=True)
-hc = torch.empty((B,), dtype=torch.int32, pin_memory=True)
-for i in range(5): ex.extract_batch_pinned(pin[i % R], hk, hd, hc, cap)
-t0 = time.perf_counter(); K = 60
-for i in range(K): ex.extract_batch_pinned(pin[i % R], hk, hd, hc, cap)
-dt = (time.perf_counter() - t0) / K
-print(os.environ.get("ORB_B200_CHUNK", "16"), os.environ.get("ORB_B200_LANES", "2"), f"{dt*1e3:.3f} ms/step  {B/dt:.0f} frames/s")
+bufs = [(torch.empty((B, cap, 28), dtype=torch.uint8, pin_memory=True), torch.empty((B, cap, 32), dtype=torch.uint8, pin_memory=True),
+         torch.empty((B,), dtype=torch.int32, pin_memory=True)) for _ in range(2)]
+def run(K):
+    ts = tw = 0.0
+    t = ex.submit_batch_pinned(pin[0], *bufs[0], cap)
+    t0 = time.perf_counter()
+    for i in range(1, K + 1):
+        a = time.perf_counter()
+        t2 = ex.submit_batch_pinned(pin[i % R], *bufs[i & 1], cap)
+        b = time.perf_counter()
+        ex.wait_batch(t)
+        c = time.perf_counter()
+        ts += b - a; tw += c - b
+        t = t2
+    dt = (time.perf_counter() - t0) / K
+    ex.wait_batch(t)
+    return dt, ts / K, tw / K
+run(5)
+dt, ts, tw = run(60)
+print(f"chunk {os.environ.get('ORB_B200_CHUNK', '16')} lanes {os.environ.get('ORB_B200_LANES', '2')}: {dt*1e3:.3f} ms/step {B/dt:.0f} frames/s; host in submit {ts*1e3:.3f} ms, in wait {tw*1e3:.3f} ms")

@@ -1,15 +1,18 @@
-// Which pipe runs fp16x2 min/max on sm_100a?  Throughput of VIMNMX3.U16x2 alone, HMNMX2 alone,
-// HFMA2 alone, and interleaved mixes.  If a mix takes max(a, b) instead of a + b, the two
-// instruction classes issue to different pipes.
+// Which pipes do the integer / fp16x2 instructions of the detect, blur and describe kernels use on
+// sm_100a?  Each mode runs independent chains of one instruction class (or an interleaved mix of two)
+// and reports warp-instructions per clock per SM for each class.  If a mix takes max(a, b) instead of
+// a + b, the two classes issue to different pipes.
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdio.h>
 
-#define ITERS 4096
+#define ITERS 2048
 #define CHAINS 8
 
+enum { VIMNMX3 = 1, HMNMX2 = 2, HFMA2 = 4, PRMT = 8, LOP3 = 16, IMAD = 32, IDP4A = 64, HRELU = 128, POPC = 256, IADD3 = 512, SHF = 1024 };
+
 template <int MODE>
-__global__ void k(unsigned* out, unsigned seed) {
+__global__ void k(unsigned* out, unsigned seed, long long* cycles) {
     unsigned a[CHAINS], b[CHAINS];
 #pragma unroll
     for (int i = 0; i < CHAINS; ++i) {
@@ -17,50 +20,91 @@ __global__ void k(unsigned* out, unsigned seed) {
         b[i] = (threadIdx.x * 40503u + i * 2654435761u + seed) & 0x00ff00ffu | 0x64006400u;
     }
     const unsigned c = (seed * 77u) & 0x00ff00ffu | 0x64006400u;
+    const long long t0 = clock64();
     for (int it = 0; it < ITERS; ++it) {
 #pragma unroll
         for (int i = 0; i < CHAINS; ++i) {
-            if (MODE == 0 || MODE == 3 || MODE == 4) a[i] = __vimax3_u16x2(a[i], b[i], c + it);  // VIMNMX3
-            if (MODE == 1 || MODE == 3) {  // HMNMX2
-                __half2 x = *reinterpret_cast<__half2*>(&b[i]), y = *reinterpret_cast<__half2*>(&a[(i + 1) % CHAINS]);
+            if (MODE & VIMNMX3) a[i] = __vimax3_u16x2(a[i], a[(i + 1) % CHAINS], c + it);
+            if (MODE & HMNMX2) {
+                __half2 x = *reinterpret_cast<__half2*>(&b[i]), y = *reinterpret_cast<const __half2*>(&c);
                 x = __hmin2(x, y);
-                b[i] = *reinterpret_cast<unsigned*>(&x) + 1;
+                b[i] = *reinterpret_cast<unsigned*>(&x);
             }
-            if (MODE == 2 || MODE == 4) {  // HFMA2
+            if (MODE & HFMA2) {
                 __half2 x = *reinterpret_cast<__half2*>(&b[i]), y = *reinterpret_cast<const __half2*>(&c);
                 x = __hfma2(x, y, x);
                 b[i] = *reinterpret_cast<unsigned*>(&x);
             }
-            if (MODE == 5) a[i] = __vimax3_u16x2(a[i], b[i], c + it), b[i] = __vimin3_u16x2(b[i], a[i], c);  // 2x VIMNMX3
+            if (MODE & HRELU) {
+                __half2 x = *reinterpret_cast<__half2*>(&b[i]), y = *reinterpret_cast<const __half2*>(&c);
+                x = __hfma2_relu(x, y, x);
+                b[i] = *reinterpret_cast<unsigned*>(&x);
+            }
+            if (MODE & PRMT) b[i] = __byte_perm(b[i], c, b[(i + 3) % CHAINS]);
+            if (MODE & LOP3) b[i] = (b[i] & (c + it)) ^ b[(i + 3) % CHAINS];
+            if (MODE & IMAD) b[i] = b[i] * c + b[(i + 3) % CHAINS];
+            if (MODE & IDP4A) b[i] = __dp4a(b[i], c, b[i]);
+            if (MODE & POPC) b[i] = __popc(b[i]) + 0x5555;
+            if (MODE & IADD3) b[i] = b[i] + (c ^ it) + b[(i + 3) % CHAINS];
+            if (MODE & SHF) b[i] = __funnelshift_l(b[i], c, it);
         }
     }
+    const long long t1 = clock64();
     unsigned r = 0;
 #pragma unroll
     for (int i = 0; i < CHAINS; ++i) r ^= a[i] ^ b[i];
     out[blockIdx.x * blockDim.x + threadIdx.x] = r;
+    if (threadIdx.x == 0 && blockIdx.x == 0) *cycles = t1 - t0;
 }
 
 template <int MODE>
-float run(unsigned* d) {
+void run(unsigned* d, long long* dc, const char* name, int nclasses) {
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
-    k<MODE><<<148 * 8, 256>>>(d, 1);
+    int nb = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k<MODE>, 256, 0);
+    k<MODE><<<148 * 8, 256>>>(d, 1, dc);
     cudaEventRecord(e0);
-    k<MODE><<<148 * 8, 256>>>(d, 2);
+    k<MODE><<<148 * 8, 256>>>(d, 2, dc);
     cudaEventRecord(e1);
-    cudaEventSynchronize(e1);
+    cudaDeviceSynchronize();
     float ms;
     cudaEventElapsedTime(&ms, e0, e1);
-    return ms;
+    long long cyc;
+    cudaMemcpy(&cyc, dc, 8, cudaMemcpyDeviceToHost);
+    // 8 CTAs x 8 warps per SM (64 warps)
+    const double per_class = 64.0 * ITERS * CHAINS / (double)cyc;
+    printf("%-24s occ %d  %8.1f us  %10lld cycles  %.3f warp-instr/clk/SM per class, %.3f total\n", name, nb, ms * 1e3, cyc, per_class, per_class * nclasses);
 }
 
 int main() {
     unsigned* d;
+    long long* dc;
     cudaMalloc(&d, 148 * 8 * 256 * 4);
-    const char* names[] = {"VIMNMX3 only", "HMNMX2 only", "HFMA2 only", "VIMNMX3 + HMNMX2", "VIMNMX3 + HFMA2", "2x VIMNMX3"};
-    float t[6] = {run<0>(d), run<1>(d), run<2>(d), run<3>(d), run<4>(d), run<5>(d)};
-    const double ops = 148.0 * 8 * 256 / 32 * ITERS * CHAINS;  // warp-instructions of each class
-    for (int i = 0; i < 6; ++i) printf("%-20s %8.3f ms  (%.2f warp-instr/clk/SM per class at 1.9 GHz)\n", names[i], t[i], ops / (t[i] * 1e-3) / 148 / 1.9e9);
+    cudaMalloc(&dc, 8);
+    run<VIMNMX3>(d, dc, "VIMNMX3.U16x2", 1);
+    run<HMNMX2>(d, dc, "HMNMX2", 1);
+    run<HFMA2>(d, dc, "HFMA2", 1);
+    run<HRELU>(d, dc, "HFMA2.RELU", 1);
+    run<PRMT>(d, dc, "PRMT", 1);
+    run<LOP3>(d, dc, "LOP3", 1);
+    run<IMAD>(d, dc, "IMAD", 1);
+    run<IDP4A>(d, dc, "IDP.4A", 1);
+    run<POPC>(d, dc, "POPC+IADD", 2);
+    run<IADD3>(d, dc, "IADD3", 1);
+    run<SHF>(d, dc, "SHF", 1);
+    run<VIMNMX3 | HMNMX2>(d, dc, "VIMNMX3 + HMNMX2", 2);
+    run<VIMNMX3 | HFMA2>(d, dc, "VIMNMX3 + HFMA2", 2);
+    run<VIMNMX3 | HRELU>(d, dc, "VIMNMX3 + HFMA2.RELU", 2);
+    run<VIMNMX3 | PRMT>(d, dc, "VIMNMX3 + PRMT", 2);
+    run<VIMNMX3 | LOP3>(d, dc, "VIMNMX3 + LOP3", 2);
+    run<VIMNMX3 | IMAD>(d, dc, "VIMNMX3 + IMAD", 2);
+    run<VIMNMX3 | IDP4A>(d, dc, "VIMNMX3 + IDP.4A", 2);
+    run<IDP4A | IMAD>(d, dc, "IDP.4A + IMAD", 2);
+    run<PRMT | IMAD>(d, dc, "PRMT + IMAD", 2);
+    run<LOP3 | IADD3>(d, dc, "LOP3 + IADD3", 2);
+    run<SHF | VIMNMX3>(d, dc, "SHF + VIMNMX3", 2);
+    run<SHF | IMAD>(d, dc, "SHF + IMAD", 2);
     return 0;
 }
