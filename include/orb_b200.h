@@ -300,6 +300,34 @@ int orb_search_for_triangulation(orb_matcher* m, const orb_keypoint* keys1, cons
                                  const orb_feature_vector* fv2, const float* f12, const float* sigma2, int nlevels,
                                  int check_ori, int32_t* matches12, int* nmatches);
 
+/* ---- DBoW2 vocabulary transform: replaces ORBVocabulary::transform as called by Frame::ComputeBoW
+ *      (src/Frame.cc:375-382) and KeyFrame::ComputeBoW (src/KeyFrame.cc:39-47) ------------------------
+ * The vocabulary tree (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h, m_nodes) arrives flattened: node 0 is the
+ * root; node i has children children[child_off[i] .. child_off[i+1]) in m_nodes[i].children order, a 32-byte
+ * descriptor, a weight and (leaves) a word id.  It is uploaded once and stays resident on the device. */
+typedef struct orb_vocabulary orb_vocabulary; /* opaque */
+
+typedef enum orb_voc_weighting { ORB_VOC_TF_IDF = 0, ORB_VOC_TF = 1, ORB_VOC_IDF = 2, ORB_VOC_BINARY = 3 } orb_voc_weighting; /* BowVector.h:36-42 */
+typedef enum orb_voc_scoring {  /* BowVector.h:45-53; decides the normalisation (ScoringObject.h:74-89) */
+    ORB_VOC_L1_NORM = 0, ORB_VOC_L2_NORM = 1, ORB_VOC_CHI_SQUARE = 2, ORB_VOC_KL = 3, ORB_VOC_BHATTACHARYYA = 4, ORB_VOC_DOT_PRODUCT = 5
+} orb_voc_scoring;
+
+/* depth_l = m_L.  node_weight: n_nodes doubles; node_word: n_nodes ints (meaningful for leaves). */
+int orb_vocabulary_create(int device, int n_nodes, const int32_t* child_off, const int32_t* children,
+                          const uint8_t* node_desc, const double* node_weight, const int32_t* node_word, int depth_l,
+                          int weighting, int scoring, orb_vocabulary** out);
+void orb_vocabulary_destroy(orb_vocabulary* v);
+
+/* transform(features, BowVector&, FeatureVector&, levelsup) (TemplatedVocabulary.h:1126-1187): the tree descent
+ * of all n descriptors runs on the device; the two std::map results are assembled on the host in feature order
+ * with the reference's double arithmetic.  BowVector -> (bow_ids ascending, bow_values), *bow_n entries;
+ * FeatureVector -> orb_feature_vector layout (fv_nodes ascending, fv_off, fv_idx), *fv_n nodes.
+ * word_of_feature / node_of_feature (n ints each, may be NULL): per-feature word id and node id.
+ * Capacities too small -> ORB_ERR_CAPACITY with *bow_n / *fv_n holding the needed sizes (fv_idx needs n). */
+int orb_vocabulary_transform(orb_vocabulary* v, const uint8_t* desc, int n, int levelsup, int32_t* word_of_feature,
+                             int32_t* node_of_feature, int32_t* bow_ids, double* bow_values, int bow_cap, int* bow_n,
+                             int32_t* fv_nodes, int32_t* fv_off, int32_t* fv_idx, int fv_cap, int* fv_n);
+
 /* ---- misc ------------------------------------------------------------------------------- */
 
 /* Thread-local description of the last error on this thread ("" if none). */

@@ -390,6 +390,77 @@ def search_for_initialization(keys1, desc1, F2, prev_matched, window_size, nnrat
     return int(n), out
 
 
+_REF_DBOW = os.path.join(_HERE, "_ref", "libref_dbow.so")
+
+
+def _voc_arrays(voc):
+    """voc: object with child_off, children, node_desc, node_weight, node_word, L, weighting, scoring."""
+    return (np.ascontiguousarray(voc.child_off, np.int32), np.ascontiguousarray(voc.children, np.int32),
+            np.ascontiguousarray(voc.node_desc, np.uint8), np.ascontiguousarray(voc.node_weight, np.float64),
+            np.ascontiguousarray(voc.node_word, np.int32))
+
+
+def voc_transform(voc, desc, levelsup=4):
+    """Oracle restatement of TemplatedVocabulary::transform: returns dict(words, nodes, bow_ids, bow_values, fv)."""
+    co, ch, nd, nw, wd = _voc_arrays(voc)
+    d = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+    n = len(d)
+    words, nodes = np.zeros(n, np.int32), np.zeros(n, np.int32)
+    bi, bv = np.zeros(n + 1, np.int32), np.zeros(n + 1, np.float64)
+    fn, fo, fi = np.zeros(n + 1, np.int32), np.zeros(n + 2, np.int32), np.zeros(n + 1, np.int32)
+    nb, nf = C.c_int(0), C.c_int(0)
+    lib().orc_voc_transform.restype = C.c_int
+    rc = lib().orc_voc_transform(len(co) - 1, _p(co), _p(ch), _p(nd), _p(nw), _p(wd), int(voc.L), int(voc.weighting), int(voc.scoring),
+                                 _p(d), n, int(levelsup), _p(words), _p(nodes), _p(bi), _p(bv), n + 1, C.byref(nb), _p(fn), _p(fo),
+                                 _p(fi), n + 1, C.byref(nf))
+    if rc != 0:
+        raise RuntimeError(f"oracle voc_transform rc={rc}")
+    fv = {int(fn[k]): fi[fo[k]:fo[k + 1]].tolist() for k in range(nf.value)}
+    return dict(words=words, nodes=nodes, bow_ids=bi[: nb.value].copy(), bow_values=bv[: nb.value].copy(), fv=fv)
+
+
+class RefVocabulary:
+    """The reference's own DBoW2 TemplatedVocabulary<FORB> (oracle/_ref/libref_dbow.so), loaded from the fork's
+    text format exactly as ORB_SLAM2::System does (src/System.cc:43-51: loadFromTextFile)."""
+
+    def __init__(self, text_path):
+        if not os.path.exists(_REF_DBOW):
+            subprocess.check_call(["make", "-s", "-C", _HERE, "refdbow"])
+        if not os.path.exists(_REF_DBOW):
+            raise FileNotFoundError(_REF_DBOW)
+        self._L = C.CDLL(_REF_DBOW)
+        self._L.refvoc_load_text.restype = C.c_void_p
+        self._L.refvoc_load_text.argtypes = [C.c_char_p]
+        self._L.refvoc_free.argtypes = [C.c_void_p]
+        self._L.refvoc_size.argtypes = [C.c_void_p]
+        self._h = self._L.refvoc_load_text(text_path.encode())
+        if not self._h:
+            raise RuntimeError("loadFromTextFile failed")
+
+    def size(self):
+        return self._L.refvoc_size(self._h)
+
+    def transform(self, desc, levelsup=4):
+        d = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        n = len(d)
+        bi, bv = np.zeros(n + 1, np.int32), np.zeros(n + 1, np.float64)
+        fn, fo, fi = np.zeros(n + 1, np.int32), np.zeros(n + 2, np.int32), np.zeros(n + 1, np.int32)
+        nb, nf = C.c_int(0), C.c_int(0)
+        self._L.refvoc_transform.argtypes = [C.c_void_p] + [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        rc = self._L.refvoc_transform(self._h, _p(d), n, int(levelsup), _p(bi), _p(bv), n + 1, C.byref(nb), _p(fn), _p(fo), _p(fi), n + 1,
+                                      C.byref(nf))
+        assert rc == 0
+        fv = {int(fn[k]): fi[fo[k]:fo[k + 1]].tolist() for k in range(nf.value)}
+        return dict(bow_ids=bi[: nb.value].copy(), bow_values=bv[: nb.value].copy(), fv=fv)
+
+    def __del__(self):
+        try:
+            self._L.refvoc_free(self._h)
+        except Exception:
+            pass
+
+
 def extract_many(rows, cols, nframes, nthreads, first_frame=0, seed=7, **params):
     p = dict(DEFAULT)
     p.update(params)

@@ -16,6 +16,7 @@
 #include <cstring>
 #include <iterator>
 #include <memory>
+#include <sstream>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -27,6 +28,7 @@ typedef unsigned char uchar;
 #define CV_PI 3.1415926535897932384626433832795
 #define CV_8U 0
 #define CV_8UC1 0
+#define CV_32F 5  // only named by code paths the oracle never runs (DBoW2 FORB::toMat32F)
 
 inline int cvRound(double v) { return orb_oracle::cv_round_d(v); }
 inline int cvRound(float v) { return orb_oracle::cv_round_f(v); }
@@ -107,6 +109,12 @@ public:
         cols = c;
         step = (size_t)c;
         data = buf_->data();
+    }
+    static Mat zeros(int r, int c, int type) {
+        Mat m;
+        m.create(r, c, type);
+        std::memset(m.data, 0, (size_t)r * c);
+        return m;
     }
     void release() { *this = Mat(); }
     bool empty() const { return data == nullptr || rows == 0 || cols == 0; }
@@ -219,6 +227,28 @@ inline void copyMakeBorder(InputArray src, OutputArray dst, int top, int bottom,
         for (int x = 0; x < d.cols; ++x) D[x] = S[refl(x - left, s.cols)];
     }
 }
+
+// cv::FileStorage / cv::FileNode: named by DBoW2's YAML save()/load() (TemplatedVocabulary.h:1456-1610), which the
+// oracle never calls (vocabularies travel as the fork's text format, loadFromTextFile).  Syntax only.
+class FileNode {
+public:
+    FileNode operator[](const std::string&) const { return FileNode(); }
+    FileNode operator[](const char*) const { return FileNode(); }
+    FileNode operator[](int) const { return FileNode(); }
+    size_t size() const { return 0; }
+    operator int() const { return 0; }
+    operator double() const { return 0; }
+    operator std::string() const { return std::string(); }
+};
+class FileStorage {
+public:
+    enum { READ = 0, WRITE = 1 };
+    FileStorage(const std::string&, int) {}
+    bool isOpened() const { return false; }
+    FileNode operator[](const std::string&) const { return FileNode(); }
+    template <typename T>
+    FileStorage& operator<<(const T&) { return *this; }
+};
 
 struct KeyPointsFilter {  // only referenced by the dead ComputeKeyPointsOld (ORBextractor.cc:423)
     static void retainBest(std::vector<KeyPoint>& kps, int n) {

@@ -12,6 +12,7 @@
 #include <cmath>
 #include <cstring>
 #include <list>
+#include <map>
 #include <thread>
 
 namespace orb_oracle {
@@ -1457,6 +1458,99 @@ int orc_search_for_initialization(const KeyPoint* keys1, const uint8_t* desc1, i
         }
     delete g;
     return nmatches;
+}
+
+// ---- DBoW2 vocabulary transform ------------------------------------------------------------------
+// TemplatedVocabulary::transform(features, BowVector&, FeatureVector&, levelsup), reference
+// Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1126-1187, with the per-feature descent :1218-1260,
+// FORB::distance (FORB.cpp:81-101), BowVector::addWeight / addIfNotExist / normalize (BowVector.cpp:34-84)
+// and FeatureVector::addFeature (FeatureVector.cpp:32-46).  The tree arrives flattened (node 0 = root,
+// children of node i = children[child_off[i] .. child_off[i+1]) in m_nodes[i].children order).
+// Pinned against the reference's own DBoW2 compiled from source (oracle/_ref/libref_dbow.so) in
+// tests/test_vocabulary_oracle.py.  Returns 0; -1 capacity; -3 when a feature with weight > 0 ends above
+// level L - levelsup (the reference then stores an uninitialised NodeId).
+int orc_voc_transform(int n_nodes, const int* child_off, const int* children, const uint8_t* node_desc, const double* node_weight,
+                      const int* node_word, int m_L, int weighting, int scoring, const uint8_t* feat, int n, int levelsup,
+                      int* word_of_feature, int* node_of_feature, int* bow_ids, double* bow_vals, int bow_cap, int* bow_n,
+                      int* fv_nodes, int* fv_off, int* fv_idx, int fv_cap, int* fv_n) {
+    *bow_n = 0;
+    *fv_n = 0;
+    fv_off[0] = 0;
+    if (n_nodes < 2) return 0;  // empty()
+    std::map<unsigned, double> v;
+    std::map<unsigned, std::vector<unsigned>> fv;
+    const bool must = scoring != 5;                 // DotProductScoring is the only MUSTNORMALIZE = false
+    const bool normL2 = scoring == 1;
+    const bool tf = weighting == 0 || weighting == 1;  // TF_IDF, TF
+    for (int i_feature = 0; i_feature < n; ++i_feature) {
+        const uint8_t* feature = feat + 32 * (size_t)i_feature;
+        // transform(feature, id, w, &nid, levelsup)
+        const int nid_level = m_L - levelsup;
+        long nid = -1;
+        if (nid_level <= 0) nid = 0;
+        int final_id = 0, current_level = 0;
+        do {
+            ++current_level;
+            const int b = child_off[final_id], e = child_off[final_id + 1];
+            final_id = children[b];
+            double best_d = descriptor_distance(feature, node_desc + 32 * (size_t)final_id);
+            for (int c = b + 1; c < e; ++c) {
+                const int id = children[c];
+                double d = descriptor_distance(feature, node_desc + 32 * (size_t)id);
+                if (d < best_d) {
+                    best_d = d;
+                    final_id = id;
+                }
+            }
+            if (current_level == nid_level) nid = final_id;
+        } while (child_off[final_id] != child_off[final_id + 1]);
+        const unsigned id = (unsigned)node_word[final_id];
+        const double w = node_weight[final_id];
+        if (word_of_feature) word_of_feature[i_feature] = (int)id;
+        if (node_of_feature) node_of_feature[i_feature] = (int)nid;
+        if (w > 0) {
+            if (nid < 0) return -3;
+            auto vit = v.lower_bound(id);
+            if (vit != v.end() && !(v.key_comp()(id, vit->first))) {
+                if (tf) vit->second += w;
+            } else {
+                v.insert(vit, std::make_pair(id, w));
+            }
+            fv[(unsigned)nid].push_back((unsigned)i_feature);
+        }
+    }
+    if (tf && !v.empty() && !must) {
+        const double nd = v.size();
+        for (auto& e : v) e.second /= nd;
+    }
+    if (must) {
+        double norm = 0.0;
+        if (!normL2) {
+            for (auto& e : v) norm += fabs(e.second);
+        } else {
+            for (auto& e : v) norm += e.second * e.second;
+            norm = sqrt(norm);
+        }
+        if (norm > 0.0)
+            for (auto& e : v) e.second /= norm;
+    }
+    *bow_n = (int)v.size();
+    *fv_n = (int)fv.size();
+    if ((int)v.size() > bow_cap || (int)fv.size() > fv_cap) return -1;
+    int k = 0;
+    for (auto& e : v) {
+        bow_ids[k] = (int)e.first;
+        bow_vals[k] = e.second;
+        ++k;
+    }
+    k = 0;
+    int c = 0;
+    for (auto& e : fv) {
+        fv_nodes[k] = (int)e.first;
+        for (unsigned idx : e.second) fv_idx[c++] = (int)idx;
+        fv_off[++k] = c;
+    }
+    return 0;
 }
 
 void orc_synth_frame(uint8_t* dst, int rows, int cols, int step, uint64_t seed, uint64_t frame,

@@ -7,3 +7,4 @@ raises if liborb_b200.so has not been built or no GPU is usable (no CPU fallback
 from ._lib import KP_DTYPE, LIB_PATH, OrbError, build, kernel_launch_count, lib  # noqa: F401
 from .extractor import ORBextractor  # noqa: F401
 from .matcher import FeatureVector, FrameView, ORBmatcher  # noqa: F401
+from .vocabulary import ORBVocabulary  # noqa: F401

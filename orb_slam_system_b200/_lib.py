@@ -70,7 +70,8 @@ EXPORTS = [
     "orb_stage_name", "orb_matcher_create", "orb_matcher_destroy", "orb_match_all",
     "orb_match_all_batch", "orb_match_csr", "orb_distances_csr", "orb_stereo_match", "orb_compute_stereo_matches", "orb_matcher_sync",
     "orb_matcher_stream", "orb_window_search", "orb_search_by_projection_map", "orb_search_by_projection_best",
-    "orb_search_for_initialization", "orb_search_by_bow", "orb_search_for_triangulation", "orb_last_error", "orb_kernel_launch_count", "orb_version",
+    "orb_search_for_initialization", "orb_search_by_bow", "orb_search_for_triangulation", "orb_vocabulary_create", "orb_vocabulary_destroy", "orb_vocabulary_transform",
+    "orb_last_error", "orb_kernel_launch_count", "orb_version",
 ]
 
 
@@ -122,6 +123,10 @@ def lib():
         L.orb_search_for_initialization.argtypes = [vp, vp, vp, i32, vp, vp, i32, f32, i32, vp, vp]
         L.orb_search_by_bow.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp, i32, vp, vp, f32, i32, vp, vp]
         L.orb_search_for_triangulation.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp, i32, vp, vp, vp, vp, i32, i32, vp, vp]
+        L.orb_vocabulary_create.argtypes = [i32, i32, vp, vp, vp, vp, vp, i32, i32, i32, vp]
+        L.orb_vocabulary_destroy.argtypes = [vp]
+        L.orb_vocabulary_destroy.restype = None
+        L.orb_vocabulary_transform.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp, i32, vp, vp, vp, vp, i32, vp]
         L.orb_last_error.restype = C.c_char_p
         L.orb_kernel_launch_count.restype = C.c_uint64
         L.orb_version.restype = C.c_char_p

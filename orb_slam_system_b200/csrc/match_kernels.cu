@@ -512,6 +512,55 @@ __global__ void __launch_bounds__(256) k_stereo_refine(const orb_kp28* __restric
 }
 
 // ------------------------------------------------------------------------------------------
+// DBoW2 vocabulary descent: TemplatedVocabulary::transform(feature, word_id, weight, nid, levelsup)
+// (reference Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1218-1260) with F::distance = FORB::distance
+// (FORB.cpp:81-101, the same 256-bit Hamming distance).  16 lanes per feature: lane c takes child c
+// (c, c+16, ... for wider nodes), the 16-lane argmin keeps the FIRST minimum in child order (`d < best_d`).
+// node_at_level = the node reached when current_level == L - levelsup (0 = root when that level is <= 0,
+// -1 when the descent ends above it: the reference then leaves *nid unset).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_voc_descent(const uint8_t* __restrict__ feat, int n, const int* __restrict__ child_off,
+                                                     const int* __restrict__ children, const uint8_t* __restrict__ node_desc,
+                                                     int nid_level, int* __restrict__ leaf_node, int* __restrict__ node_at_level) {
+    const int g = (blockIdx.x * 256 + threadIdx.x) >> 4, sub = threadIdx.x & 15;
+    const unsigned gmask = 0xffffu << (threadIdx.x & 16);
+    if (g >= n) return;  // a whole 16-lane group leaves together; the shuffles below name only the own group
+    const uint4* Fp = reinterpret_cast<const uint4*>(feat) + 2 * (size_t)g;
+    const uint4 f0 = __ldg(Fp), f1 = __ldg(Fp + 1);
+    const uint4* D = reinterpret_cast<const uint4*>(node_desc);
+    int node = 0, level = 0, nid = nid_level <= 0 ? 0 : -1;
+    int b = __ldg(child_off), e = __ldg(child_off + 1);
+    while (b < e) {  // do { ... } while (!isLeaf()): the root of a non-empty vocabulary has children
+        ++level;
+        int best = 0x7fffffff, pos = 0x7fffffff;
+        for (int c = b + sub; c < e; c += 16) {
+            const int id = __ldg(children + c);
+            const int d = hamming256(f0, f1, __ldg(D + 2 * (size_t)id), __ldg(D + 2 * (size_t)id + 1));
+            if (d < best) {
+                best = d;
+                pos = c;
+            }
+        }
+#pragma unroll
+        for (int s2 = 8; s2 > 0; s2 >>= 1) {
+            const int ob = __shfl_xor_sync(gmask, best, s2), op = __shfl_xor_sync(gmask, pos, s2);
+            if (ob < best || (ob == best && op < pos)) {
+                best = ob;
+                pos = op;
+            }
+        }
+        node = __ldg(children + pos);
+        if (level == nid_level) nid = node;
+        b = __ldg(child_off + node);
+        e = __ldg(child_off + node + 1);
+    }
+    if (sub == 0) {
+        leaf_node[g] = node;
+        node_at_level[g] = nid;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------
 void orbk_count_launch(int n);
@@ -587,6 +636,14 @@ cudaError_t orbk_stereo_refine(const orb_kp28* kl, int nl, const orb_kp28* kr, c
                                cudaStream_t st) {
     if (nl <= 0) return cudaSuccess;
     k_stereo_refine<<<(nl + 7) / 8, 256, 0, st>>>(kl, nl, kr, best_r, best_dist, lv, mbf, maxD, u_right, depth, sad, flags);
+    orbk_count_launch(1);
+    return cudaGetLastError();
+}
+
+cudaError_t orbk_voc_descent(const uint8_t* feat, int n, const int* child_off, const int* children, const uint8_t* node_desc,
+                             int nid_level, int* leaf_node, int* node_at_level, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    k_voc_descent<<<(n + 15) / 16, 256, 0, st>>>(feat, n, child_off, children, node_desc, nid_level, leaf_node, node_at_level);
     orbk_count_launch(1);
     return cudaGetLastError();
 }

@@ -40,3 +40,6 @@ cudaError_t orbk_window_fill(const orb_kp28* keys, const uint8_t* tdesc, const i
 cudaError_t orbk_stereo_refine(const orb_kp28* kl, int nl, const orb_kp28* kr, const int* best_r, const int* best_dist,
                                const OrbStereoLevels& lv, float mbf, float maxD, float* u_right, float* depth, int* sad, int* flags,
                                cudaStream_t st);
+// DBoW2 TemplatedVocabulary::transform descent for n features: leaf node and the node at level nid_level of each.
+cudaError_t orbk_voc_descent(const uint8_t* feat, int n, const int* child_off, const int* children, const uint8_t* node_desc,
+                             int nid_level, int* leaf_node, int* node_at_level, cudaStream_t st);

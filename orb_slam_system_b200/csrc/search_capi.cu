@@ -5,7 +5,10 @@
 // (this file is compiled with -ffp-contract=off).  Citations: reference src/ORBmatcher.cc.
 #include <limits.h>
 #include <math.h>
+#include <string.h>
 
+#include <algorithm>
+#include <map>
 #include <vector>
 
 #include "capi_internal.h"
@@ -545,5 +548,188 @@ extern "C" int orb_search_for_triangulation(orb_matcher* m, const orb_keypoint* 
         }
     }
     *nmatches = count;
+    return ORB_OK;
+}
+
+// ---- DBoW2 vocabulary: TemplatedVocabulary::transform, TemplatedVocabulary.h:1126-1187, :1218-1260 --------------
+struct orb_vocabulary {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int n_nodes = 0, depth_l = 0, weighting = 0, scoring = 0;
+    int* d_child_off = nullptr;
+    int* d_children = nullptr;
+    uint8_t* d_desc = nullptr;
+    std::vector<double> weight;
+    std::vector<int32_t> word, nchild;
+    // grow-only scratch for the features and the per-feature results
+    uint8_t* d_feat = nullptr;
+    int* d_out = nullptr;
+    size_t cap = 0;
+};
+
+extern "C" void orb_vocabulary_destroy(orb_vocabulary* v) {
+    if (!v) return;
+    cudaSetDevice(v->device);
+    if (v->stream) cudaStreamSynchronize(v->stream);
+    cudaFree(v->d_child_off);
+    cudaFree(v->d_children);
+    cudaFree(v->d_desc);
+    cudaFree(v->d_feat);
+    cudaFree(v->d_out);
+    if (v->stream) cudaStreamDestroy(v->stream);
+    delete v;
+}
+
+static int vocabulary_upload(orb_vocabulary* v, const int32_t* child_off, const int32_t* children, const uint8_t* node_desc) {
+    const int n = v->n_nodes, nc = child_off[n];
+    CUDA_TRY(cudaStreamCreateWithFlags(&v->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaMalloc((void**)&v->d_child_off, sizeof(int) * ((size_t)n + 1)));
+    CUDA_TRY(cudaMalloc((void**)&v->d_children, sizeof(int) * (size_t)std::max(nc, 1)));
+    CUDA_TRY(cudaMalloc((void**)&v->d_desc, (size_t)n * 32));
+    CUDA_TRY(cudaMemcpyAsync(v->d_child_off, child_off, sizeof(int) * ((size_t)n + 1), cudaMemcpyHostToDevice, v->stream));
+    if (nc) CUDA_TRY(cudaMemcpyAsync(v->d_children, children, sizeof(int) * (size_t)nc, cudaMemcpyHostToDevice, v->stream));
+    CUDA_TRY(cudaMemcpyAsync(v->d_desc, node_desc, (size_t)n * 32, cudaMemcpyHostToDevice, v->stream));
+    CUDA_TRY(cudaStreamSynchronize(v->stream));
+    return ORB_OK;
+}
+
+extern "C" int orb_vocabulary_create(int device, int n_nodes, const int32_t* child_off, const int32_t* children, const uint8_t* node_desc,
+                                     const double* node_weight, const int32_t* node_word, int depth_l, int weighting, int scoring,
+                                     orb_vocabulary** out) {
+    if (!out || !child_off || !node_desc || !node_weight || !node_word) return orb_fail(ORB_ERR_INVALID, "null argument");
+    if (n_nodes < 1) return orb_fail(ORB_ERR_INVALID, "a vocabulary has at least the root node");
+    if (weighting < 0 || weighting > 3 || scoring < 0 || scoring > 5) return orb_fail(ORB_ERR_INVALID, "bad weighting / scoring type");
+    if (child_off[0] != 0) return orb_fail(ORB_ERR_INVALID, "child_off[0] != 0");
+    for (int i = 0; i < n_nodes; ++i)
+        if (child_off[i + 1] < child_off[i]) return orb_fail(ORB_ERR_INVALID, "child_off must not decrease");
+    const int nc = child_off[n_nodes];
+    if (nc && !children) return orb_fail(ORB_ERR_INVALID, "null children");
+    // every child id in range and below... a tree: each non-root node is the child of exactly one node, no cycles
+    std::vector<uint8_t> seen((size_t)n_nodes, 0);
+    for (int c = 0; c < nc; ++c) {
+        if (children[c] <= 0 || children[c] >= n_nodes) return orb_fail(ORB_ERR_INVALID, "child id out of range");
+        if (seen[children[c]]++) return orb_fail(ORB_ERR_INVALID, "node %d has two parents", children[c]);
+    }
+    {  // reachability from the root without revisiting = no cycles among the listed nodes
+        std::vector<int> stack(1, 0);
+        size_t visited = 0;
+        while (!stack.empty()) {
+            const int u = stack.back();
+            stack.pop_back();
+            if (++visited > (size_t)n_nodes) return orb_fail(ORB_ERR_INVALID, "the node graph has a cycle");
+            for (int c = child_off[u]; c < child_off[u + 1]; ++c) stack.push_back(children[c]);
+        }
+    }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return orb_fail(ORB_ERR_CUDA, "no CUDA device: %s (liborb_b200 has no CPU fallback)", cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return orb_fail(ORB_ERR_INVALID, "device %d out of range", device);
+    CUDA_TRY(cudaSetDevice(device));
+    orb_vocabulary* v = new orb_vocabulary();
+    v->device = device;
+    v->n_nodes = n_nodes;
+    v->depth_l = depth_l;
+    v->weighting = weighting;
+    v->scoring = scoring;
+    v->weight.assign(node_weight, node_weight + n_nodes);
+    v->word.assign(node_word, node_word + n_nodes);
+    const int rc = vocabulary_upload(v, child_off, children, node_desc);
+    if (rc != ORB_OK) {
+        orb_vocabulary_destroy(v);
+        return rc;
+    }
+    *out = v;
+    return ORB_OK;
+}
+
+extern "C" int orb_vocabulary_transform(orb_vocabulary* v, const uint8_t* desc, int n, int levelsup, int32_t* word_of_feature,
+                                        int32_t* node_of_feature, int32_t* bow_ids, double* bow_values, int bow_cap, int* bow_n,
+                                        int32_t* fv_nodes, int32_t* fv_off, int32_t* fv_idx, int fv_cap, int* fv_n) {
+    if (!v || !bow_n || !fv_n) return orb_fail(ORB_ERR_INVALID, "null argument");
+    if (n < 0 || bow_cap < 0 || fv_cap < 0) return orb_fail(ORB_ERR_INVALID, "bad count");
+    *bow_n = 0;
+    *fv_n = 0;
+    // empty(): a vocabulary without words (TemplatedVocabulary.h:1133-1136) -> both results stay empty
+    if (v->n_nodes < 2 || n == 0) {
+        if (fv_off && fv_cap >= 0) fv_off[0] = 0;
+        return ORB_OK;
+    }
+    if (!desc) return orb_fail(ORB_ERR_INVALID, "null descriptors");
+    CUDA_TRY(cudaSetDevice(v->device));
+    if ((size_t)n > v->cap) {
+        CUDA_TRY(cudaStreamSynchronize(v->stream));
+        cudaFree(v->d_feat);
+        cudaFree(v->d_out);
+        v->d_feat = nullptr;
+        v->d_out = nullptr;
+        v->cap = 0;
+        const size_t want = (size_t)n + (size_t)n / 4 + 64;
+        CUDA_TRY(cudaMalloc((void**)&v->d_feat, want * 32));
+        CUDA_TRY(cudaMalloc((void**)&v->d_out, want * 2 * sizeof(int)));
+        v->cap = want;
+    }
+    std::vector<int32_t> leaf((size_t)n), nid((size_t)n);
+    CUDA_TRY(cudaMemcpyAsync(v->d_feat, desc, (size_t)n * 32, cudaMemcpyHostToDevice, v->stream));
+    CUDA_TRY(orbk_voc_descent(v->d_feat, n, v->d_child_off, v->d_children, v->d_desc, v->depth_l - levelsup, v->d_out, v->d_out + n, v->stream));
+    CUDA_TRY(cudaMemcpyAsync(leaf.data(), v->d_out, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, v->stream));
+    CUDA_TRY(cudaMemcpyAsync(nid.data(), v->d_out + n, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, v->stream));
+    CUDA_TRY(cudaStreamSynchronize(v->stream));
+    // ---- the two maps, in feature order (:1143-1180)
+    const bool tf = v->weighting == ORB_VOC_TF_IDF || v->weighting == ORB_VOC_TF;
+    const bool must = v->scoring != ORB_VOC_DOT_PRODUCT;       // ScoringObject.h:74-89
+    const bool l2 = v->scoring == ORB_VOC_L2_NORM;
+    std::map<int32_t, double> bow;                              // BowVector
+    std::map<int32_t, std::vector<int32_t>> fvec;               // FeatureVector
+    for (int i = 0; i < n; ++i) {
+        const int32_t id = v->word[leaf[i]];
+        const double w = v->weight[leaf[i]];
+        if (word_of_feature) word_of_feature[i] = id;
+        if (node_of_feature) node_of_feature[i] = nid[i];
+        if (w > 0) {  // not stopped
+            if (nid[i] < 0)
+                return orb_fail(ORB_ERR_SHAPE, "feature %d reaches a leaf above level L - levelsup (the reference stores an unset node id)", i);
+            auto it = bow.lower_bound(id);
+            if (it != bow.end() && it->first == id) {
+                if (tf) it->second += w;  // addWeight; addIfNotExist leaves an existing entry alone
+            } else {
+                bow.insert(it, std::make_pair(id, w));
+            }
+            fvec[nid[i]].push_back(i);
+        }
+    }
+    if (tf && !bow.empty() && !must) {  // :1159-1165
+        const double nd = (double)bow.size();
+        for (auto& e : bow) e.second /= nd;
+    }
+    if (must) {  // BowVector::normalize, BowVector.cpp:62-84
+        double norm = 0.0;
+        if (!l2) {
+            for (auto& e : bow) norm += fabs(e.second);
+        } else {
+            for (auto& e : bow) norm += e.second * e.second;
+            norm = sqrt(norm);
+        }
+        if (norm > 0.0)
+            for (auto& e : bow) e.second /= norm;
+    }
+    *bow_n = (int)bow.size();
+    *fv_n = (int)fvec.size();
+    if (*bow_n > bow_cap || *fv_n > fv_cap) return orb_fail(ORB_ERR_CAPACITY, "needs %d BoW entries and %d feature-vector nodes", *bow_n, *fv_n);
+    if ((*bow_n && (!bow_ids || !bow_values)) || !fv_off || (*fv_n && (!fv_nodes || !fv_idx))) return orb_fail(ORB_ERR_INVALID, "null output arrays");
+    int k = 0;
+    for (auto& e : bow) {
+        bow_ids[k] = e.first;
+        bow_values[k] = e.second;
+        ++k;
+    }
+    k = 0;
+    int c = 0;
+    fv_off[0] = 0;
+    for (auto& e : fvec) {
+        fv_nodes[k] = e.first;
+        for (int32_t idx : e.second) fv_idx[c++] = idx;
+        fv_off[++k] = c;
+    }
     return ORB_OK;
 }
