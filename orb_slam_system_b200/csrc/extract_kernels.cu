@@ -1104,13 +1104,41 @@ __device__ __forceinline__ void sincos_0_2pi(double x, double& s, double& c) {
     c = ((q + 1) & 2) ? -c1 : c1;
 }
 
+// Output index o of frame f -> (level, rank inside the level's kept list).  Levels are concatenated 0..n-1
+// (ORBextractor.cc:466-494); lane j of the calling warp holds `pre` = keypoints of the levels before level j and
+// `myK` = its own count.  Warp-uniform arguments and result.
+__device__ __forceinline__ void locate_keypoint(int o, int pre, int myK, int nlevels, int lane, int& l, int& r) {
+    // the last level whose prefix is <= o (empty levels share a prefix)
+    const unsigned le = __ballot_sync(0xffffffffu, lane < nlevels && pre <= o && myK > 0);
+    l = 31 - __clz(le);
+    r = o - __shfl_sync(0xffffffffu, pre, l);
+}
+
+__device__ __forceinline__ int level_prefix(const int* kc, int nlevels, int lane, int cap, int& myK, int& total) {
+    myK = lane < nlevels ? kc[lane] : 0;
+    int pre = myK;
+    for (int sft = 1; sft < 32; sft <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, pre, sft);
+        if (lane >= sft) pre += v;
+    }
+    total = min(__shfl_sync(0xffffffffu, pre, 31), cap);
+    return pre - myK;  // exclusive prefix
+}
+
+// The describe stage is three kernels that hand their intermediate values over in the output record itself
+// (orb_keypoint_dev slots x, y hold m01, m10 after k_orient; angle, size, response hold angle, cos, sin after
+// k_angle; k_brief writes the final record):
+//   k_orient  one warp per keypoint: the two intensity-centroid moments (IC_Angle :21-48), exact int32
+//   k_angle   one THREAD per keypoint: cv::fastAtan2 and the cos / sin of the descriptor rotation (:59-60) --
+//             warp-uniform scalar work in a warp-per-keypoint kernel, done here 32 keypoints per instruction
+//   k_brief   one warp per keypoint: the 182 rBRIEF tests on the blurred level (:57-73) and the final record
+//
 // IC_Angle weight table (built on the host by orbk_build_ic_table, plan.icTab):
 // entry [a][v + 15][k] for patch alignment a = (x - 15) & 3, row v, aligned word k (9 words
 // cover u = -15 - a .. 20 - a): .x = four signed bytes u (0 outside the disc |u| <= umax[|v|]),
-// .y = four 0/1 bytes (inside the disc).  m10 += dp4a(pixels, .x); m01 += v * dp4a(pixels, .y).
-__global__ void __launch_bounds__(256) k_describe(const __grid_constant__ OrbPlan plan, orb_keypoint_dev* __restrict__ kps,
-                                                  uint8_t* __restrict__ desc, int cap, int* __restrict__ counts) {
-    __shared__ unsigned s_patch[8][372];  // per warp: 37 rows x 10 words of the blurred level
+// .y = four signed bytes v (0 outside the disc).  m10 += dp4a(pixels, .x); m01 += dp4a(pixels, .y).
+__global__ void __launch_bounds__(256) k_orient(const __grid_constant__ OrbPlan plan, orb_keypoint_dev* __restrict__ kps, int cap,
+                                                int* __restrict__ counts) {
     const int f = blockIdx.y;
     const int* kc = plan.keptCount + f * ORB_MAX_LEVELS;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -1119,41 +1147,25 @@ __global__ void __launch_bounds__(256) k_describe(const __grid_constant__ OrbPla
         counts[f] = tot;
     }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // Warps stride over the frame's keypoints in output order (levels concatenated): lane j
-    // holds the number of keypoints of the levels before level j.
-    int myK = lane < plan.nlevels ? kc[lane] : 0;
-    int pre = myK;
-    for (int sft = 1; sft < 32; sft <<= 1) {
-        const int v = __shfl_up_sync(0xffffffffu, pre, sft);
-        if (lane >= sft) pre += v;
-    }
-    const int total = min(__shfl_sync(0xffffffffu, pre, 31), cap);
-    pre -= myK;  // exclusive prefix
-    const float4* pairs = plan.pairTab + lane;
-    unsigned* patch = s_patch[warp];
-    for (int o = blockIdx.x * 8 + warp; o < total; o += gridDim.x * 8) {
-    // level of output index o: the last level whose prefix is <= o (empty levels share a prefix)
-    const unsigned le = __ballot_sync(0xffffffffu, lane < plan.nlevels && pre <= o && myK > 0);
-    const int l = 31 - __clz(le);
-    const int r = o - __shfl_sync(0xffffffffu, pre, l);
-    const OrbLevel& L = plan.lv[l];
-    const OrbLevel& S = plan.lv[L.src];
-
-    const uint2 k = L.kept[(size_t)f * L.kmax + r];
-    const int x = (int)(k.x & 0xffff), y = (int)(k.x >> 16);
-
-    // ---- IC_Angle: m10 = sum u*I, m01 = sum v*I over the radius-15 disc (exact int32).
+    int myK, total;
+    const int pre = level_prefix(kc, plan.nlevels, lane, cap, myK, total);
     // Lane (r3, kk) = (lane / 9, lane % 9) for lanes 0..26 reads aligned word kk of patch rows
     // r3, r3 + 3, r3 + 6, ... (11 steps cover the 31 rows).
-    int m10 = 0, m01 = 0;
-    {
+    const int r3 = lane / 9, kk = lane - r3 * 9;
+    for (int o = blockIdx.x * 8 + warp; o < total; o += gridDim.x * 8) {
+        int l, r;
+        locate_keypoint(o, pre, myK, plan.nlevels, lane, l, r);
+        const OrbLevel& L = plan.lv[l];
+        const OrbLevel& S = plan.lv[L.src];
+        const uint2 k = L.kept[(size_t)f * L.kmax + r];
+        const int x = (int)(k.x & 0xffff), y = (int)(k.x >> 16);
+        int m10 = 0, m01 = 0;
         const int a = (x - 15) & 3;
         const unsigned pw = (unsigned)S.pitch >> 2;  // level rows are 4-byte aligned
-        const int r3 = lane / 9, kk = lane - r3 * 9;
-        const unsigned* p = reinterpret_cast<const unsigned*>(S.img + (size_t)f * S.plane + (size_t)(y - 15) * S.pitch + (x - 15 - a)) +
-                            (unsigned)r3 * pw + (unsigned)kk;
-        const int2* tab = plan.icTab + a * (31 * 9) + lane;
         if (lane < 27) {
+            const unsigned* p = reinterpret_cast<const unsigned*>(S.img + (size_t)f * S.plane + (size_t)(y - 15) * S.pitch + (x - 15 - a)) +
+                                (unsigned)r3 * pw + (unsigned)kk;
+            const int2* tab = plan.icTab + a * (31 * 9) + lane;
             const size_t step = (size_t)3 * pw;  // three rows down, in words
 #pragma unroll
             for (int it = 0; it < 11; ++it) {
@@ -1161,7 +1173,7 @@ __global__ void __launch_bounds__(256) k_describe(const __grid_constant__ OrbPla
                     const unsigned w = __ldg(p);
                     const int2 t = __ldg(tab + it * 27);
                     m10 = dp4a_us(w, t.x, m10);
-                    m01 += (it * 3 + r3 - 15) * (int)__dp4a(w, (unsigned)t.y, 0u);
+                    m01 = dp4a_us(w, t.y, m01);
                 }
                 p += step;
             }
@@ -1170,70 +1182,130 @@ __global__ void __launch_bounds__(256) k_describe(const __grid_constant__ OrbPla
             m10 += __shfl_xor_sync(0xffffffffu, m10, sft);
             m01 += __shfl_xor_sync(0xffffffffu, m01, sft);
         }
+        if (lane == 0) {
+            int2* slot = reinterpret_cast<int2*>(kps + (size_t)f * cap + o);  // .x, .y of the record (the record array is 4-byte aligned)
+            reinterpret_cast<int*>(slot)[0] = m01;
+            reinterpret_cast<int*>(slot)[1] = m10;
+        }
     }
-    const float angle = fast_atan2_deg((float)m01, (float)m10);
+}
 
-    // ---- rBRIEF on the blurred level: 182 live pairs (bits 182..255 are 0)
-    const float factorPI = (float)(3.141592653589793238462643383279502884 / 180.f);
-    const float rad = __fmul_rn(angle, factorPI);
-    double sd, cd;
-    sincos_0_2pi((double)rad, sd, cd);
-    const float a = (float)cd, b = (float)sd;
-    // The 182 x 2 samples lie within +-18 px of the keypoint.  Gathering them straight from global
-    // memory costs one L1 wavefront per touched sector per load; instead each warp stages its
-    // 37-row x 40-byte patch (aligned words) in shared memory with coalesced loads and gathers there.
-    const int pitch = S.pitch;
-    __syncwarp();  // the previous keypoint's gathers are done before the patch is overwritten
-    {
-        const int xa = (x - 18) & ~3;
-        const unsigned pw = (unsigned)pitch >> 2;
-        const unsigned* gsrc = reinterpret_cast<const unsigned*>(S.blur + (size_t)f * S.plane + (size_t)(y - 18) * pitch + xa);
+__global__ void __launch_bounds__(256) k_angle(const __grid_constant__ OrbPlan plan, orb_keypoint_dev* __restrict__ kps, int cap) {
+    const int f = blockIdx.y;
+    const int* kc = plan.keptCount + f * ORB_MAX_LEVELS;
+    int total = 0;
+    for (int i = 0; i < plan.nlevels; ++i) total += kc[i];
+    total = min(total, cap);
+    for (int o = blockIdx.x * 256 + threadIdx.x; o < total; o += gridDim.x * 256) {
+        orb_keypoint_dev* kp = kps + (size_t)f * cap + o;
+        const int m01 = __float_as_int(kp->x), m10 = __float_as_int(kp->y);
+        const float angle = fast_atan2_deg((float)m01, (float)m10);
+        const float factorPI = (float)(3.141592653589793238462643383279502884 / 180.f);
+        const float rad = __fmul_rn(angle, factorPI);
+        double sd, cd;
+        sincos_0_2pi((double)rad, sd, cd);
+        kp->angle = angle;
+        kp->size = (float)cd;      // a = cos
+        kp->response = (float)sd;  // b = sin
+    }
+}
+
+// Patch of the blurred level around a keypoint: rows y-18 .. y+18, 48 bytes per row starting at the 8-byte aligned
+// column xa = (x - 18) & ~7 (the 37 needed bytes end at most 44 bytes after xa).  Level pitches are multiples of 64 and
+// the levels' allocations leave slack after the last row, so the 8-byte loads stay inside the allocation.
+#define BRIEF_PW 48               // smem bytes per patch row
+#define BRIEF_ROWS 37
+#define BRIEF_LOADS 8             // 8-byte loads per lane: lane -> (row lane / 6, chunk lane % 6), 5 rows per step, 30 lanes busy
+
+struct BriefKey {                 // what the tests and the final record need from one keypoint
+    int x, y, l, o;
+    unsigned response;
+    float angle, a, b;
+};
+
+__global__ void __launch_bounds__(256) k_brief(const __grid_constant__ OrbPlan plan, orb_keypoint_dev* __restrict__ kps,
+                                               uint8_t* __restrict__ desc, int cap) {
+    __shared__ uint2 s_patch[8][BRIEF_ROWS * BRIEF_PW / 8 + 18];  // per warp (the last step stores 3 rows past row 36)
+    const int f = blockIdx.y;
+    const int* kc = plan.keptCount + f * ORB_MAX_LEVELS;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int myK, total;
+    const int pre = level_prefix(kc, plan.nlevels, lane, cap, myK, total);
+    // the 182 test pairs stay in registers: lane i holds pairs i, i + 32, ... (keypoint independent)
+    float4 pr[6];
 #pragma unroll
-        for (int it = 0; it < 12; ++it) {
-            const int wi = it * 32 + lane;
-            if (wi < 370) {
-                const int row = wi / 10, col = wi - row * 10;
-                patch[wi] = __ldg(gsrc + (unsigned)row * pw + (unsigned)col);
+    for (int wq = 0; wq < 6; ++wq) pr[wq] = (wq * 32 + lane < 182) ? __ldg(plan.pairTab + wq * 32 + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const int prow = lane / 6, pchunk = lane - prow * 6;  // lanes 30, 31 idle while staging
+    uint2* patch = s_patch[warp];
+    const int stride = gridDim.x * 8;
+
+    for (int o = blockIdx.x * 8 + warp; o < total; o += stride) {
+        BriefKey ck;
+        {
+            int l, r;
+            locate_keypoint(o, pre, myK, plan.nlevels, lane, l, r);
+            const OrbLevel& L = plan.lv[l];
+            const OrbLevel& S = plan.lv[L.src];
+            const uint2 k = L.kept[(size_t)f * L.kmax + r];
+            ck.x = (int)(k.x & 0xffff);
+            ck.y = (int)(k.x >> 16);
+            ck.l = l;
+            ck.o = o;
+            ck.response = k.y;
+            const orb_keypoint_dev* rec = kps + (size_t)f * cap + o;
+            ck.angle = rec->angle;
+            ck.a = rec->size;
+            ck.b = rec->response;
+            const int rowsLeft = S.rows - (ck.y - 18);  // rows of the level at and below the patch's first row
+            const uint8_t* g = S.blur + (size_t)f * S.plane + (size_t)(ck.y - 18 + prow) * S.pitch + ((ck.x - 18) & ~7) + pchunk * 8;
+            const size_t step = (size_t)5 * S.pitch;
+            uint2 regs[BRIEF_LOADS];
+#pragma unroll
+            for (int it = 0; it < BRIEF_LOADS; ++it) {
+                // rows past the patch (step 7 covers rows 35..39) are skipped when they would leave the level
+                regs[it] = (lane < 30 && it * 5 + prow < rowsLeft) ? __ldg(reinterpret_cast<const uint2*>(g)) : make_uint2(0u, 0u);
+                g += step;
             }
-        }
-    }
-    __syncwarp();
-    const uint8_t* pb = reinterpret_cast<const uint8_t*>(patch) + 18 * 40 + 18 + ((x - 18) & 3);  // the keypoint's byte
-    unsigned myWord = 0;  // lane i < 8 ends up holding descriptor word i (words 6, 7 are zero)
+            __syncwarp();  // the previous keypoint's gathers are done
+            if (lane < 30) {
 #pragma unroll
-    for (int wq = 0; wq < 6; ++wq) {
-        const int p = wq * 32 + lane;
-        bool bit = false;
-        if (p < 182) {
-            const float4 pr = __ldg(pairs + wq * 32);
-            const int r0 = cv_round_small(__fadd_rn(__fmul_rn(pr.x, b), __fmul_rn(pr.y, a)));
-            const int c0 = cv_round_small(__fsub_rn(__fmul_rn(pr.x, a), __fmul_rn(pr.y, b)));
-            const int r1 = cv_round_small(__fadd_rn(__fmul_rn(pr.z, b), __fmul_rn(pr.w, a)));
-            const int c1 = cv_round_small(__fsub_rn(__fmul_rn(pr.z, a), __fmul_rn(pr.w, b)));
-            const int t0 = pb[r0 * 40 + c0];
-            const int t1 = pb[r1 * 40 + c1];
-            bit = t0 < t1;
+                for (int it = 0; it < BRIEF_LOADS; ++it) patch[(it * 5 + prow) * (BRIEF_PW / 8) + pchunk] = regs[it];
+            }
+            __syncwarp();
         }
-        const unsigned wbits = __ballot_sync(0xffffffffu, bit);
-        if (lane == wq) myWord = wbits;
-    }
-    if (lane < 8) reinterpret_cast<unsigned*>(desc + ((size_t)f * cap + o) * 32)[lane] = myWord;
-    if (lane == 8) {
-        orb_keypoint_dev kp;
-        float px = (float)x, py = (float)y;
-        if (l != 0) {  // keypoint.pt *= scale for level != 0 (:486-491)
-            px = __fmul_rn(px, L.scale);
-            py = __fmul_rn(py, L.scale);
+        const float a = ck.a, b = ck.b;
+        const uint8_t* pb = reinterpret_cast<const uint8_t*>(patch) + 18 * BRIEF_PW + 18 + ((ck.x - 18) & 7);  // the keypoint's byte
+        unsigned myWord = 0;  // lane i < 8 ends up holding descriptor word i (words 6, 7 are zero)
+#pragma unroll
+        for (int wq = 0; wq < 6; ++wq) {
+            // pairs beyond 181 are (0,0)-(0,0): t0 == t1, bit 0 -- like the fork's zero-filled pattern tail
+            const int r0 = cv_round_small(__fadd_rn(__fmul_rn(pr[wq].x, b), __fmul_rn(pr[wq].y, a)));
+            const int c0 = cv_round_small(__fsub_rn(__fmul_rn(pr[wq].x, a), __fmul_rn(pr[wq].y, b)));
+            const int r1 = cv_round_small(__fadd_rn(__fmul_rn(pr[wq].z, b), __fmul_rn(pr[wq].w, a)));
+            const int c1 = cv_round_small(__fsub_rn(__fmul_rn(pr[wq].z, a), __fmul_rn(pr[wq].w, b)));
+            const int t0 = pb[r0 * BRIEF_PW + c0];
+            const int t1 = pb[r1 * BRIEF_PW + c1];
+            const unsigned wbits = __ballot_sync(0xffffffffu, t0 < t1);
+            if (lane == wq) myWord = wbits;
         }
-        kp.x = px;
-        kp.y = py;
-        kp.size = (float)L.patchSize;
-        kp.angle = angle;
-        kp.response = (float)k.y;
-        kp.octave = l;
-        kp.class_id = -1;
-        kps[(size_t)f * cap + o] = kp;
-    }
+        if (lane < 8) reinterpret_cast<unsigned*>(desc + ((size_t)f * cap + ck.o) * 32)[lane] = myWord;
+        if (lane == 8) {
+            const OrbLevel& L = plan.lv[ck.l];
+            orb_keypoint_dev kp;
+            float px = (float)ck.x, py = (float)ck.y;
+            if (ck.l != 0) {  // keypoint.pt *= scale for level != 0 (:486-491)
+                px = __fmul_rn(px, L.scale);
+                py = __fmul_rn(py, L.scale);
+            }
+            kp.x = px;
+            kp.y = py;
+            kp.size = (float)L.patchSize;
+            kp.angle = ck.angle;
+            kp.response = (float)ck.response;
+            kp.octave = ck.l;
+            kp.class_id = -1;
+            kps[(size_t)f * cap + ck.o] = kp;
+        }
     }  // keypoint loop
 }
 
@@ -1259,7 +1331,7 @@ void orbk_build_ic_table(int2* out) {
                     const int au = u < 0 ? -u : u;
                     if (au <= umax[av]) {
                         wu |= (unsigned)(u & 0xff) << (8 * b);
-                        wm |= 1u << (8 * b);
+                        wm |= (unsigned)(v & 0xff) << (8 * b);
                     }
                 }
                 out[(a * 31 + vr) * 9 + k] = make_int2((int)wu, (int)wm);
@@ -1390,18 +1462,22 @@ cudaError_t orbk_run_extract(const OrbPlan& plan, int nframes, orb_keypoint_dev*
         k_blur<<<dim3(blurTiles, nframes), 256, 0, st>>>(plan);
         ++g_launches;
         cudaEventRecord(ev[7], st);
-    } else {
-        e = cudaStreamWaitEvent(st, ss.join, 0);
-        if (e != cudaSuccess) return e;
     }
     if (ev) cudaEventRecord(ev[4], st);
     {
         // warps stride over the keypoints: about four waves of 8-warp CTAs, split evenly over the frames
         int ctasPerFrame = (148 * 8 * 4 + nframes - 1) / nframes;
         ctasPerFrame = std::max(1, std::min(ctasPerFrame, (plan.totalKmax + 7) / 8));
-        k_describe<<<dim3(ctasPerFrame, nframes), 256, 0, st>>>(plan, d_kps, d_desc, cap, d_counts);
+        // orientation reads the raw levels only: it does not wait for the blur
+        k_orient<<<dim3(ctasPerFrame, nframes), 256, 0, st>>>(plan, d_kps, cap, d_counts);
+        k_angle<<<dim3(std::max(1, std::min(8, (plan.totalKmax + 255) / 256)), nframes), 256, 0, st>>>(plan, d_kps, cap);
+        if (!ev) {
+            e = cudaStreamWaitEvent(st, ss.join, 0);
+            if (e != cudaSuccess) return e;
+        }
+        k_brief<<<dim3(ctasPerFrame, nframes), 256, 0, st>>>(plan, d_kps, d_desc, cap);
+        g_launches += 3;
     }
-    ++g_launches;
     if (ev) cudaEventRecord(ev[5], st);
     return cudaGetLastError();
 }
