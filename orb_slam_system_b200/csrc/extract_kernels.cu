@@ -134,15 +134,13 @@ __global__ void __launch_bounds__(256) k_resize4(const uint8_t* __restrict__ src
 #define DET_MAX_SURV 4096  // >= ceil(250/2) * ceil(59/2): NMS survivors are never 8-adjacent
 #define DET_WLIST_PER_WARP 512  // >= ceil(59/4) rows x 32 words handled by one warp in pass B
 
-struct DetectSmem {
-    union {                                    // (first member: the TMA destination, 128-byte aligned)
-        unsigned img[DET_TILE_H + 1][DET_TILE_W / 4];  // image tile, dense 256-byte rows (TMA box) + one slack row
-        unsigned F[DET_TILE_H + 1][DET_TILE_W / 4];    // NMS survivors, 4 candidate columns per word (pass B)
-    };
-    union {
-        unsigned sc[DET_TILE_H][DET_SP / 4];   // score tile with a one-word / one-row zero border
-        unsigned surv[DET_MAX_SURV];           // survivor list (pass C): u | r<<8 | cx<<16 | cell<<24
-    };
+// Dynamic shared memory of k_detect, sized by the plan's tallest tile (plan.detRows = max boxH):
+//   img   (detRows + 1) x 256 B   image tile, dense 256-byte rows (the TMA box) + one slack row; after pass A the
+//                                 same memory holds F, the NMS survivors (4 candidate columns per word)
+//   sc    (detRows - 4) x DET_SP  score tile with a one-word / one-row zero border; later the survivor list
+//                                 (u | r<<8 | cx<<16 | cell<<24)
+//   tail  DetectTail
+struct DetectTail {
     unsigned short wlist[(DET_THREADS / 32) * DET_WLIST_PER_WARP];  // per warp: (row << 6 | word) of its non-zero F words
     int wcount[DET_THREADS / 32];
     unsigned char cellOf[DET_TILE_W + 8];      // candidate column -> cell index inside the tile
@@ -154,6 +152,15 @@ struct DetectSmem {
     int emitFill;
     unsigned long long bar;                    // mbarrier the TMA load completes on
 };
+
+__host__ __device__ inline size_t det_img_bytes(int detRows) { return (size_t)(detRows + 1) * DET_TILE_W; }
+__host__ __device__ inline size_t det_sc_bytes(int detRows) {
+    const size_t a = (size_t)(detRows - 4) * DET_SP, b = (size_t)DET_MAX_SURV * 4;
+    return ((a > b ? a : b) + 15) & ~(size_t)15;
+}
+static size_t detect_smem_bytes(int detRows) {
+    return det_img_bytes(detRows) + det_sc_bytes(detRows) + sizeof(DetectTail);
+}
 
 // ---- TMA / mbarrier primitives (PTX; SASS: UTMALDG, SYNCS) ----
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -182,23 +189,31 @@ __device__ __forceinline__ void tma_load_3d(unsigned dst, const CUtensorMap* map
 
 __device__ __forceinline__ void fast_score_pairs(const unsigned (&r)[16], unsigned c2, unsigned low2,
                                                  unsigned neglow2, unsigned& u) {
-    // M3/m3 over 3 contiguous ring pixels, M9/m9 over 9 contiguous, then the min/max over arcs.
-    unsigned M3[16], m3[16];
+    // A = min over the 16 arcs of 9 contiguous ring pixels of the arc's maximum, B = max over arcs of the arc's
+    // minimum.  The arcs starting at k and k + 1 (k even) share the 8 pixels W = r[k+1 .. k+8]:
+    //   min(max(r[k], W), max(W, r[k+9])) = max(W, min(r[k], r[k+9])),   W = max(M4[k+1], M4[k+5]),
+    // with M4[j] = max(r[j .. j+3]) built from pair maxima at the odd positions.  36 min/max per polarity.
+    unsigned M2[8], m2[8], M4[8], m4[8];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
-        M3[k] = vmax3(r[k], r[(k + 1) & 15], r[(k + 2) & 15]);
-        m3[k] = vmin3(r[k], r[(k + 1) & 15], r[(k + 2) & 15]);
+    for (int i = 0; i < 8; ++i) {  // odd position j = 2i + 1
+        M2[i] = __vmaxu2(r[2 * i + 1], r[(2 * i + 2) & 15]);
+        m2[i] = __vminu2(r[2 * i + 1], r[(2 * i + 2) & 15]);
     }
-    unsigned A = 0x00ff00ffu, B = 0u;
 #pragma unroll
-    for (int k = 0; k < 16; k += 2) {
-        const unsigned M9a = vmax3(M3[k], M3[(k + 3) & 15], M3[(k + 6) & 15]);
-        const unsigned M9b = vmax3(M3[k + 1], M3[(k + 4) & 15], M3[(k + 7) & 15]);
-        A = vmin3(A, M9a, M9b);
-        const unsigned m9a = vmin3(m3[k], m3[(k + 3) & 15], m3[(k + 6) & 15]);
-        const unsigned m9b = vmin3(m3[k + 1], m3[(k + 4) & 15], m3[(k + 7) & 15]);
-        B = vmax3(B, m9a, m9b);
+    for (int i = 0; i < 8; ++i) {
+        M4[i] = __vmaxu2(M2[i], M2[(i + 1) & 7]);
+        m4[i] = __vminu2(m2[i], m2[(i + 1) & 7]);
     }
+    unsigned tA[8], tB[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {  // even position k = 2i: W = M4[k+1] u M4[k+5] = M4 index i and i + 2
+        const unsigned mn = __vminu2(r[2 * i], r[(2 * i + 9) & 15]);
+        const unsigned mx = __vmaxu2(r[2 * i], r[(2 * i + 9) & 15]);
+        tA[i] = vmax3(M4[i], M4[(i + 2) & 7], mn);
+        tB[i] = vmin3(m4[i], m4[(i + 2) & 7], mx);
+    }
+    const unsigned A = __vminu2(vmin3(tA[0], tA[1], tA[2]), vmin3(vmin3(tA[3], tA[4], tA[5]), tA[6], tA[7]));
+    const unsigned B = __vmaxu2(vmax3(tB[0], tB[1], tB[2]), vmax3(vmax3(tB[3], tB[4], tB[5]), tB[6], tB[7]));
     // m = max(c - A, B - c) per signed 16-bit lane; u = max(m, low) - low
     const unsigned d1 = __vsub2(c2, A);
     const unsigned d2 = __vsub2(B, c2);
@@ -213,7 +228,11 @@ __device__ __forceinline__ unsigned odd_lanes(unsigned w) { return __byte_perm(w
 __global__ void __launch_bounds__(DET_THREADS) k_detect(const __grid_constant__ OrbPlan plan,
                                                         const CUtensorMap* __restrict__ maps) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    DetectSmem& sm = *reinterpret_cast<DetectSmem*>(smem_raw);
+    const int detRows = plan.detRows;
+    unsigned (*img)[DET_TILE_W / 4] = reinterpret_cast<unsigned (*)[DET_TILE_W / 4]>(smem_raw);
+    unsigned (*sc)[DET_SP / 4] = reinterpret_cast<unsigned (*)[DET_SP / 4]>(smem_raw + det_img_bytes(detRows));
+    unsigned* surv = reinterpret_cast<unsigned*>(sc);
+    DetectTail& sm = *reinterpret_cast<DetectTail*>(smem_raw + det_img_bytes(detRows) + det_sc_bytes(detRows));
 
     const int f = blockIdx.y;
     int tile = blockIdx.x;
@@ -249,17 +268,17 @@ __global__ void __launch_bounds__(DET_THREADS) k_detect(const __grid_constant__ 
     __syncthreads();
     if (tid == 0) {
         mbar_expect_tx(bar, (unsigned)(DET_TILE_W * L.boxH));
-        tma_load_3d(smem_u32(&sm.img[0][0]), maps + l, X0 - a0, Y0, f + plan.frameBase, bar);
+        tma_load_3d(smem_u32(&img[0][0]), maps + l, X0 - a0, Y0, f + plan.frameBase, bar);
     }
     {
         // zero border of the score tile: rows 0 and CH+1, words 0 and QR+1
         for (int i = tid; i < 2 * (QR + 2); i += DET_THREADS) {
             const int r = i < QR + 2 ? 0 : CH + 1;
-            sm.sc[r][i < QR + 2 ? i : i - (QR + 2)] = 0u;
+            sc[r][i < QR + 2 ? i : i - (QR + 2)] = 0u;
         }
         for (int i = tid; i < 2 * (CH + 2); i += DET_THREADS) {
             const int r = i >> 1;
-            sm.sc[r][(i & 1) ? QR + 1 : 0] = 0u;
+            sc[r][(i & 1) ? QR + 1 : 0] = 0u;
         }
         // cellOf[cx + 4] for cx in [-4, CW + 4): cell index of candidate column cx (255 left of the tile)
         for (int i = tid; i < CW + 8; i += DET_THREADS) sm.cellOf[i] = i < 4 ? (unsigned char)255 : (unsigned char)((i - 4) / wCell);
@@ -289,9 +308,9 @@ __global__ void __launch_bounds__(DET_THREADS) k_detect(const __grid_constant__ 
             unsigned w[7][3];
 #pragma unroll
             for (int rr = 0; rr < 7; ++rr) {
-                w[rr][0] = sm.img[r + rr][wo + q];
-                w[rr][1] = sm.img[r + rr][wo + q + 1];
-                w[rr][2] = sm.img[r + rr][wo + q + 2];
+                w[rr][0] = img[r + rr][wo + q];
+                w[rr][1] = img[r + rr][wo + q + 1];
+                w[rr][2] = img[r + rr][wo + q + 2];
             }
             // unaligned 4-byte windows: win(rr, dx) = bytes b(3+dx)..b(6+dx) of row rr
 #define WIN(rr, dx)                                                                   \
@@ -336,7 +355,7 @@ __global__ void __launch_bounds__(DET_THREADS) k_detect(const __grid_constant__ 
             const int rem = CW + ph - 4 * q;  // bytes of this group left of the candidate area's end
             if (rem < 4) word &= (1u << (8 * rem)) - 1u;
             if (q == 0) word &= 0xffffffffu << (8 * ph);  // bytes before candidate column 0
-            sm.sc[r + 1][q + 1] = word;
+            sc[r + 1][q + 1] = word;
         }
     }
     __syncthreads();
@@ -370,13 +389,13 @@ __global__ void __launch_bounds__(DET_THREADS) k_detect(const __grid_constant__ 
             // window rows in bordered coordinates: up = r, mid = r + 1, dn = r + 2
             unsigned upAo, upBe, upBo, upCe, midAo, midBe, midBo, midCe;
             {
-                const unsigned a = sm.sc[r0][q], b = sm.sc[r0][q + 1], c = sm.sc[r0][q + 2];
+                const unsigned a = sc[r0][q], b = sc[r0][q + 1], c = sc[r0][q + 2];
                 upAo = odd_lanes(a); upBe = even_lanes(b); upBo = odd_lanes(b); upCe = even_lanes(c);
-                const unsigned a2 = sm.sc[r0 + 1][q], b2 = sm.sc[r0 + 1][q + 1], c2 = sm.sc[r0 + 1][q + 2];
+                const unsigned a2 = sc[r0 + 1][q], b2 = sc[r0 + 1][q + 1], c2 = sc[r0 + 1][q + 2];
                 midAo = odd_lanes(a2); midBe = even_lanes(b2); midBo = odd_lanes(b2); midCe = even_lanes(c2);
             }
             for (int r = r0; r < r1; ++r) {
-                const unsigned a = sm.sc[r + 2][q], b = sm.sc[r + 2][q + 1], c = sm.sc[r + 2][q + 2];
+                const unsigned a = sc[r + 2][q], b = sc[r + 2][q + 1], c = sc[r + 2][q + 2];
                 const unsigned dnAo = odd_lanes(a), dnBe = even_lanes(b), dnBo = odd_lanes(b), dnCe = even_lanes(c);
                 // vertical maxima of the neighbour columns (centre column without the centre row)
                 const unsigned vAo = vmax3(upAo, midAo, dnAo), vBe = vmax3(upBe, midBe, dnBe);
@@ -395,7 +414,7 @@ __global__ void __launch_bounds__(DET_THREADS) k_detect(const __grid_constant__ 
                 const unsigned outw = active ? ((midBe & kE) | ((midBo & kO) << 8)) : 0u;
                 const unsigned nz = __ballot_sync(0xffffffffu, outw != 0u);
                 if (outw) {  // this warp's private list region: no atomics
-                    sm.F[r][q] = outw;
+                    img[r][q] = outw;
                     sm.wlist[wbase + wcount + __popc(nz & ((1u << lane) - 1u))] = (unsigned short)((r << 6) | q);
                 }
                 wcount += __popc(nz);
@@ -416,7 +435,7 @@ __global__ void __launch_bounds__(DET_THREADS) k_detect(const __grid_constant__ 
         for (int i = tid & 31; i < myW; i += 32) {
             const int idx = sm.wlist[wb + i];
             const int r = idx >> 6, qq = idx & 63;
-            unsigned w = sm.F[r][qq];
+            unsigned w = img[r][qq];
             while (w) {  // at most two survivors per word (never 8-adjacent)
                 const int k = (__ffs(w) - 1) >> 3;
                 const unsigned u = (w >> (8 * k)) & 0xffu;
@@ -424,7 +443,7 @@ __global__ void __launch_bounds__(DET_THREADS) k_detect(const __grid_constant__ 
                 const int cx = 4 * qq + k - ph;
                 const unsigned cell = sm.cellOf[cx + 4];
                 const int slot = atomicAdd(&sm.nSurv, 1);
-                if (slot < DET_MAX_SURV) sm.surv[slot] = u | ((unsigned)r << 8) | ((unsigned)cx << 16) | (cell << 24);
+                if (slot < DET_MAX_SURV) surv[slot] = u | ((unsigned)r << 8) | ((unsigned)cx << 16) | (cell << 24);
                 if ((int)u >= iniU) sm.cellHasIni[cell] = 1;
             }
         }
@@ -436,7 +455,7 @@ __global__ void __launch_bounds__(DET_THREADS) k_detect(const __grid_constant__ 
     if (nS == 0) return;
     int myCount = 0;
     for (int i = tid; i < nS; i += DET_THREADS) {
-        const unsigned e = sm.surv[i];
+        const unsigned e = surv[i];
         const int u = e & 0xff;
         myCount += (u >= iniU || (!sm.cellHasIni[e >> 24] && u >= minU)) ? 1 : 0;
     }
@@ -449,7 +468,7 @@ __global__ void __launch_bounds__(DET_THREADS) k_detect(const __grid_constant__ 
         int slot = atomicAdd(&sm.emitFill, myCount) + sm.emitBase;
         uint2* out = L.cand + (size_t)f * L.candCap;
         for (int i = tid; i < nS; i += DET_THREADS) {
-            const unsigned e = sm.surv[i];
+            const unsigned e = surv[i];
             const int u = e & 0xff;
             if (u >= iniU || (!sm.cellHasIni[e >> 24] && u >= minU)) {
                 // coordinates relative to (minBorderX, minBorderY) as in vToDistributeKeys
@@ -1392,12 +1411,11 @@ static unsigned long long g_launches = 0;
 unsigned long long orbk_launch_count() { return g_launches; }
 void orbk_count_launch(int n) { g_launches += n; }
 
-static const size_t kDetectSmem = sizeof(DetectSmem);
 static const size_t kOctreeSmem = (size_t)(OCT_SMEM_A + OCT_SMEM_B) * 8 + sizeof(OctShared);
 static const size_t kOctFastSmem = sizeof(OctFastSmem);
 
 cudaError_t orbk_init_device() {
-    cudaError_t e = cudaFuncSetAttribute(k_detect, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDetectSmem);
+    cudaError_t e = cudaFuncSetAttribute(k_detect, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)detect_smem_bytes(DET_TILE_H));
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_octree_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kOctFastSmem);
     if (e != cudaSuccess) return e;
@@ -1448,7 +1466,7 @@ cudaError_t orbk_run_extract(const OrbPlan& plan, int nframes, orb_keypoint_dev*
         if (e != cudaSuccess) return e;
     }
     if (plan.totalTiles > 0) {
-        k_detect<<<dim3(plan.totalTiles, nframes), DET_THREADS, kDetectSmem, st>>>(plan, d_maps);
+        k_detect<<<dim3(plan.totalTiles, nframes), DET_THREADS, detect_smem_bytes(plan.detRows), st>>>(plan, d_maps);
         ++g_launches;
     }
     if (ev) cudaEventRecord(ev[2], st);

@@ -380,6 +380,10 @@ static int build_plan(orb_extractor* h, int rows, int cols) {
         L.kmax = std::min<int>(L.kmax, (int)S.candCap);
     }
     P.totalTiles = tileBase;
+    P.detRows = 8;  // k_detect sizes its shared memory by the tallest tile
+    for (int l = 0; l < P.nlevels; ++l)
+        if (P.lv[l].src == l && P.lv[l].nTiles > 0) P.detRows = std::max(P.detRows, P.lv[l].boxH);
+    if (P.detRows > DET_TILE_H) return fail(ORB_ERR_SHAPE, "detect tile of %d rows exceeds %d", P.detRows, DET_TILE_H);
     P.totalKmax = keptBase;
     CUDA_TRY(dev_alloc(h, &P.candCount, (size_t)B * ORB_MAX_LEVELS));
     CUDA_TRY(dev_alloc(h, &P.keptCount, (size_t)B * ORB_MAX_LEVELS));

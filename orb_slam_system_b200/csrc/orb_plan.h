@@ -63,6 +63,7 @@ struct OrbPlan {
     int batch;               // frames per launch the buffers are sized for
     int frameBase;           // first frame of this launch inside the batch buffers (TMA z offset)
     int totalTiles;          // detect tiles per frame
+    int detRows;             // tallest detect tile (max boxH over the levels), sizes k_detect's shared memory
     int totalKmax;           // sum of kmax
     int* candCount;          // [batch][ORB_MAX_LEVELS]
     int* keptCount;          // [batch][ORB_MAX_LEVELS]

@@ -9,11 +9,14 @@
 #define ITERS 2048
 #define CHAINS 8
 
-enum { VIMNMX3 = 1, HMNMX2 = 2, HFMA2 = 4, PRMT = 8, LOP3 = 16, IMAD = 32, IDP4A = 64, HRELU = 128, POPC = 256, IADD3 = 512, SHF = 1024 };
+enum { HMAX2B = 2048, PRMTI = 4096, LDS = 8192, VIMNMX2 = 16384, HADD2 = 32768, VIMNMX3 = 1, HMNMX2 = 2, HFMA2 = 4, PRMT = 8, LOP3 = 16, IMAD = 32, IDP4A = 64, HRELU = 128, POPC = 256, IADD3 = 512, SHF = 1024 };
 
 template <int MODE>
 __global__ void k(unsigned* out, unsigned seed, long long* cycles) {
     unsigned a[CHAINS], b[CHAINS];
+    __shared__ unsigned sm[1024];
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) sm[i] = i * seed;
+    __syncthreads();
 #pragma unroll
     for (int i = 0; i < CHAINS; ++i) {
         a[i] = (threadIdx.x * 2654435761u + i * 40503u + seed) & 0x00ff00ffu | 0x64006400u;
@@ -38,6 +41,19 @@ __global__ void k(unsigned* out, unsigned seed, long long* cycles) {
             if (MODE & HRELU) {
                 __half2 x = *reinterpret_cast<__half2*>(&b[i]), y = *reinterpret_cast<const __half2*>(&c);
                 x = __hfma2_relu(x, y, x);
+                b[i] = *reinterpret_cast<unsigned*>(&x);
+            }
+            if (MODE & HMAX2B) {  // a second, independent HMNMX2 stream on the a[] registers
+                __half2 x = *reinterpret_cast<__half2*>(&a[i]), y = *reinterpret_cast<__half2*>(&a[(i + 1) % CHAINS]);
+                x = __hmax2(x, y);
+                a[i] = *reinterpret_cast<unsigned*>(&x);
+            }
+            if (MODE & PRMTI) b[i] = __byte_perm(b[i], c, 0x5432);
+            if (MODE & LDS) b[i] ^= sm[(threadIdx.x + i * 32 + (b[i] & 1)) & 1023];
+            if (MODE & VIMNMX2) a[i] = __vmaxu2(a[i], a[(i + 1) % CHAINS]);
+            if (MODE & HADD2) {
+                __half2 x = *reinterpret_cast<__half2*>(&b[i]), y = *reinterpret_cast<const __half2*>(&c);
+                x = __hadd2(x, y);
                 b[i] = *reinterpret_cast<unsigned*>(&x);
             }
             if (MODE & PRMT) b[i] = __byte_perm(b[i], c, b[(i + 3) % CHAINS]);
@@ -83,6 +99,19 @@ int main() {
     long long* dc;
     cudaMalloc(&d, 148 * 8 * 256 * 4);
     cudaMalloc(&dc, 8);
+    run<HMAX2B>(d, dc, "HMNMX2 (a-chain)", 1);
+    run<VIMNMX2>(d, dc, "VIMNMX.U16x2 2-input", 1);
+    run<PRMTI>(d, dc, "PRMT imm", 1);
+    run<LDS>(d, dc, "LDS+LOP", 2);
+    run<HADD2>(d, dc, "HADD2", 1);
+    run<HMAX2B | HMNMX2>(d, dc, "HMNMX2 + HMNMX2", 2);
+    run<HMAX2B | PRMTI>(d, dc, "HMNMX2 + PRMT imm", 2);
+    run<HMAX2B | LOP3>(d, dc, "HMNMX2 + LOP3", 2);
+    run<HMAX2B | IADD3>(d, dc, "HMNMX2 + IADD3", 2);
+    run<HMAX2B | LDS>(d, dc, "HMNMX2 + LDS+LOP", 3);
+    run<HMAX2B | HADD2>(d, dc, "HMNMX2 + HADD2", 2);
+    run<HMAX2B | IMAD>(d, dc, "HMNMX2 + IMAD", 2);
+    run<VIMNMX3 | LDS>(d, dc, "VIMNMX3 + LDS+LOP", 3);
     run<VIMNMX3>(d, dc, "VIMNMX3.U16x2", 1);
     run<HMNMX2>(d, dc, "HMNMX2", 1);
     run<HFMA2>(d, dc, "HFMA2", 1);
