@@ -117,6 +117,97 @@ def make_frames(n, first):
     return np.stack(frames)
 
 
+def next_rows(device):
+    """The rows of SURVEY 8f / the search methods of 8a served through the C ABI, each timed through its public
+    host-buffer call (copies inside) next to the oracle on one host core: stereo (BASELINE config 2), windowed search,
+    DBoW2 transform.  Small, bounded samples: a few seconds in total."""
+    import oracle
+    from orb_slam_system_b200 import FrameView, ORBextractor, ORBmatcher, ORBVocabulary
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from voc_cases import make_vocabulary
+
+    def best_of(fn, reps):
+        fn()
+        ts = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            fn()
+            ts.append(time.perf_counter() - t0)
+        return min(ts)
+
+    out = {}
+    # ---- BASELINE config 2: EuRoC-shape stereo pair, 1200 features per image, extraction of both images in one
+    # batch + Frame::ComputeStereoMatches whole (Hamming search, SAD refinement on the resident pyramids, median cut)
+    rows, cols, nf = 480, 752, 1200
+    bf, fx = 47.90639384423901, 435.2046959714599
+    il = oracle.synth_frame(rows, cols, frame=1)
+    ir = oracle.synth_frame(rows, cols, frame=1, right=1)
+    ex = ORBextractor(nf, SCALE, NLEVELS, INI_TH, MIN_TH, max_batch=2, device=device)
+    m = ORBmatcher(0.6, True, device=device)
+    pair = np.stack([il, ir])
+    res = ex.extract_batch(pair)
+    (kl, dl), (kr, dr) = res
+
+    def gpu_pair():
+        r = ex.extract_batch(pair)
+        return m.ComputeStereoMatches(ex, ex, r[0][0], r[0][1], r[1][0], r[1][1], bf, fx, 0, 1)
+
+    t_pair = best_of(gpu_pair, 10)
+    t_stereo = best_of(lambda: m.ComputeStereoMatches(ex, ex, kl, dl, kr, dr, bf, fx, 0, 1), 10)
+    ur, _ = m.ComputeStereoMatches(ex, ex, kl, dl, kr, dr, bf, fx, 0, 1)
+    t0 = time.perf_counter()
+    okl, odl = oracle.extract(il, nfeatures=nf, cap=16000)
+    okr, odr = oracle.extract(ir, nfeatures=nf, cap=16000)
+    t_cpu_ex = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    our, _ = oracle.compute_stereo_matches(il, ir, okl, odl, okr, odr, bf, fx)
+    t_cpu_st = time.perf_counter() - t0
+    out["stereo_euroc"] = {
+        "workload": "752x480 stereo pair, 1200 features per image: extract both + Frame::ComputeStereoMatches (BASELINE config 2)",
+        "pairs_per_s": 1.0 / t_pair, "ms_per_pair": 1e3 * t_pair, "stereo_match_ms": 1e3 * t_stereo,
+        "keypoints_left": int(len(kl)), "stereo_matches": int((ur >= 0).sum()), "identical_to_oracle": bool(ur.tobytes() == our.tobytes()),
+        "cpu_ms_per_pair": 1e3 * (t_cpu_ex + t_cpu_st), "cpu_stereo_match_ms": 1e3 * t_cpu_st, "cpu_cores": 1,
+        "note": "one pair per call through the host API (latency form); the frames/s metric above is the batched form"}
+    # ---- windowed search: SearchByProjection(Frame, MapPoints) over the frame grid built on the device
+    F = FrameView(kl, dl, 0, cols, 0, rows, scale_factors=ex.GetScaleFactors())
+    rng = np.random.default_rng(0)
+    nq = 2000
+    src = rng.integers(0, len(kr), nq)
+    q = dr[src]
+    u = kr["x"][src] + rng.normal(0, 3, nq).astype(np.float32) + 10
+    v = kr["y"][src] + rng.normal(0, 2, nq).astype(np.float32)
+    lvl = kr["octave"][src].astype(np.int32)
+    vc = np.full(nq, 0.9, np.float32)
+    occ0 = np.zeros(len(kl), np.uint8)
+    t_sp = best_of(lambda: m.SearchByProjection(F, occ0.copy(), q, u, v, u, lvl, vc, 3.0), 10)
+    occ_g, occ_o = occ0.copy(), occ0.copy()
+    n_g, f_g = m.SearchByProjection(F, occ_g, q, u, v, u, lvl, vc, 3.0)
+    t0 = time.perf_counter()
+    n_o, f_o = oracle.search_by_projection_map(F, occ_o, q, u, v, u, lvl, vc, 3.0, 0.6)
+    t_cpu_sp = time.perf_counter() - t0
+    out["search_by_projection"] = {"workload": f"{nq} projected map points against a {len(kl)}-keypoint frame, th = 3",
+                                   "ms_per_call": 1e3 * t_sp, "queries_per_s": nq / t_sp, "matches": int(n_g),
+                                   "identical_to_oracle": bool(n_g == n_o and (f_g == f_o).all()), "cpu_ms_per_call": 1e3 * t_cpu_sp,
+                                   "cpu_cores": 1}
+    # ---- DBoW2 transform (Frame::ComputeBoW): ORBvoc-shaped synthetic tree, k = 10, L = 5 (111 111 nodes), levelsup 4
+    voc_a = make_vocabulary(np.random.default_rng(1), 10, 5)
+    voc = ORBVocabulary(voc_a.child_off, voc_a.children, voc_a.node_desc, voc_a.node_weight, voc_a.node_word, 10, 5, device=device)
+    t_voc = best_of(lambda: voc.transform(dl, 4), 10)
+    g = voc.transform(dl, 4)
+    t0 = time.perf_counter()
+    o = oracle.voc_transform(voc_a, dl, 4)
+    t_cpu_voc = time.perf_counter() - t0
+    out["dbow2_transform"] = {"workload": f"{len(dl)} descriptors through a k=10, L=5 vocabulary ({len(voc_a.parent)} nodes), levelsup 4",
+                              "ms_per_call": 1e3 * t_voc, "features_per_s": len(dl) / t_voc,
+                              "identical_to_oracle": bool((g["bow_ids"] == o["bow_ids"]).all() and g["bow_values"].tobytes() == o["bow_values"].tobytes()
+                                                          and g["fv"] == o["fv"]),
+                              "cpu_ms_per_call": 1e3 * t_cpu_voc, "cpu_cores": 1}
+    voc.close()
+    ex.close()
+    m.close()
+    return out
+
+
 def cpu_reference_rate(nframes, threads):
     """The reference's own CPU extractor (oracle/_ref, compiled from the reference sources
     against oracle/cvshim) when present, else the oracle port; one frame per host thread."""
@@ -169,6 +260,7 @@ def main():
     ap.add_argument("--frames-per-gpu", type=int, default=64)
     ap.add_argument("--rotate", type=int, default=5, help="distinct input batches cycled through (5 x 30 MB > L2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-next-rows", action="store_true", help="skip the stereo / search / vocabulary side measurements")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -431,6 +523,11 @@ def main():
             rate, kind, _ = cpu_reference_rate(nfr, cores)
             line["cpu_baseline"] = {"value": rate, "unit": "frames/s", "cores": cores, "kind": kind,
                                     "sample": f"{nfr} synthetic KITTI-shape frames, one frame per host thread"}
+            if not args.no_next_rows:
+                try:
+                    line["next_rows"] = next_rows(local_rank)
+                except Exception as e:  # side measurements must never cost the headline line
+                    line["next_rows"] = {"error": repr(e)}
         print(json.dumps(line), flush=True)
     ex.close()
     if world > 1:
