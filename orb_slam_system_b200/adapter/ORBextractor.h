@@ -39,6 +39,10 @@ public:
     std::vector<float> inline GetScaleSigmaSquares() { return mvLevelSigma2; }
     std::vector<float> inline GetInverseScaleSigmaSquares() { return mvInvLevelSigma2; }
 
+    // The C-ABI handle behind this instance: what orb_b200::Matcher::ComputeStereoMatches needs to read the pyramids of
+    // the last call where they live on the device (an addition; nothing in the reference calls it).
+    orb_extractor* handle() const { return handle_; }
+
     // Refilled after every call (tight level images inside a 19-px reflected border, exactly the
     // layout Frame::ComputeStereoMatches reads, reference src/Frame.cc:453,543-560).
     std::vector<cv::Mat> mvImagePyramid;
