@@ -116,6 +116,43 @@ int orb_extractor_sync(orb_extractor* h);
 /* The handle's CUDA stream (cudaStream_t) so callers can order their own work after it. */
 void* orb_extractor_stream(orb_extractor* h);
 
+/* ---- image ingest: the step before the path, fused into the level-0 load -------------------------
+ * What the reference does to a raw camera frame before ORBextractor::operator() sees it:
+ *   cv::remap(raw, rect, M1, M2, cv::INTER_LINEAR) with the CV_32FC1 maps of cv::initUndistortRectifyMap
+ *   (Examples/Stereo/stereo_euroc.cc:97-98, :136-137; default BORDER_CONSTANT 0), and
+ *   cv::cvtColor(im, mImGray, CV_RGB2GRAY / CV_BGR2GRAY) when channels() > 1, in
+ *   Tracking::GrabImageStereo / GrabImageRGBD / GrabImageMonocular (src/Tracking.cc:118-126, :136-141, :155-160).
+ * With an ingest configuration set, the orb_ingest_* calls take RAW frames (src_rows x src_cols x channels, 8 bit)
+ * and one kernel writes remap -> gray straight into the extractor's level-0 buffer (the rectified / gray image
+ * never makes its own round trip through HBM); level 0 of orb_get_pyramid_level is then the reference's mImGray.
+ * The maps are computed once per sequence by the caller (cv::initUndistortRectifyMap is setup code, not on the
+ * per-frame path) and stay resident on the device.  remap applies to each channel before the gray conversion,
+ * the reference's order (remap in the example driver, cvtColor inside Tracking). */
+typedef struct orb_ingest_config {
+    int32_t src_rows, src_cols; /* raw frame */
+    int32_t channels;           /* 1 (gray: no conversion), 3 or 4 (alpha ignored) */
+    int32_t bgr;                /* first channel is blue (mbRGB false = Camera.RGB: 0 in the YAML, src/Tracking.cc:68, :119-125) */
+    int32_t gray_variant;       /* 4: OpenCV 4.x coefficients (R*9798 + G*19235 + B*3735 + 2^14) >> 15, pinned against
+                                   cv2 4.13; 3: OpenCV 2.4 - 3.4 (R*4899 + G*9617 + B*1868 + 2^13) >> 14, what the
+                                   reference's 3.4.15 build computes */
+    int32_t dst_rows, dst_cols; /* size of the maps = the image the extractor sees; without maps must equal src */
+    const float* map_x;         /* host, dst_rows x dst_cols floats, dense; NULL (both): no remap */
+    const float* map_y;
+} orb_ingest_config;
+
+/* Installs (cfg != NULL) or clears (cfg == NULL) the ingest configuration; uploads the maps. */
+int orb_extractor_set_ingest(orb_extractor* h, const orb_ingest_config* cfg);
+
+/* orb_extract_batch / _submit / _device on raw frames: frame f at raw + f*frame_stride, `stride` bytes per raw
+ * row (>= src_cols * channels).  Outputs exactly as orb_extract_batch; tickets are waited on with
+ * orb_extract_batch_wait.  ORB_ERR_INVALID without a configuration. */
+int orb_ingest_extract_batch(orb_extractor* h, int n, const uint8_t* raw, size_t stride, size_t frame_stride,
+                             orb_keypoint* kps, uint8_t* desc, int cap, int* counts);
+int orb_ingest_extract_batch_submit(orb_extractor* h, int n, const uint8_t* raw, size_t stride, size_t frame_stride,
+                                    orb_keypoint* kps, uint8_t* desc, int cap, int* counts, int* ticket);
+int orb_ingest_extract_batch_device(orb_extractor* h, int n, const uint8_t* d_raw, size_t stride, size_t frame_stride,
+                                    orb_keypoint* d_kps, uint8_t* d_desc, int cap, int* d_counts);
+
 /* Pyramid level `level` of frame `frame` of the last call, tightly cropped (no border), to a
  * host buffer -- what refills the public ORBextractor::mvImagePyramid
  * (include/ORBextractor.h:65, read by src/Frame.cc:453,543-560).  dst may be NULL to

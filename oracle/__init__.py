@@ -461,6 +461,28 @@ class RefVocabulary:
             pass
 
 
+def cvt_gray(img, bgr=False, variant=4):
+    """cv::cvtColor(img, CV_RGB2GRAY / CV_BGR2GRAY) model on an 8-bit [rows, cols, 3|4] image."""
+    img = np.ascontiguousarray(img, np.uint8)
+    rows, cols, ch = img.shape
+    dst = np.zeros((rows, cols), np.uint8)
+    lib().orc_cvt_gray(_p(img), rows, cols, img.strides[0], ch, int(bgr), int(variant), _p(dst), cols)
+    return dst
+
+
+def remap_linear(img, mapx, mapy):
+    """cv::remap(img, map1, map2, INTER_LINEAR) model (CV_32FC1 maps, BORDER_CONSTANT 0); img [rows, cols] or [rows, cols, ch]."""
+    img = np.ascontiguousarray(img, np.uint8)
+    ch = 1 if img.ndim == 2 else img.shape[2]
+    mx = np.ascontiguousarray(mapx, np.float32)
+    my = np.ascontiguousarray(mapy, np.float32)
+    assert mx.shape == my.shape
+    dr, dc = mx.shape
+    dst = np.zeros((dr, dc) if img.ndim == 2 else (dr, dc, ch), np.uint8)
+    lib().orc_remap_linear(_p(img), img.shape[0], img.shape[1], img.strides[0], ch, _p(mx), _p(my), dc, dr, dc, _p(dst), dc * ch)
+    return dst
+
+
 def extract_many(rows, cols, nframes, nthreads, first_frame=0, seed=7, **params):
     p = dict(DEFAULT)
     p.update(params)

@@ -1553,6 +1553,60 @@ int orc_voc_transform(int n_nodes, const int* child_off, const int* children, co
     return 0;
 }
 
+// ---- image ingest -----------------------------------------------------------------------------------
+// cv::cvtColor(src, dst, CV_RGB2GRAY / CV_BGR2GRAY) on 8-bit images, as called by Tracking::GrabImage*
+// (reference src/Tracking.cc:118-126, :136-141, :155-160).  OpenCV is an external dependency of the reference
+// (3.4.15); the arithmetic restated here is its published fixed-point form:
+//   variant 4 (OpenCV 4.x, pinned against cv2 4.13.0): (R*9798 + G*19235 + B*3735 + (1 << 14)) >> 15
+//   variant 3 (OpenCV 2.4 - 3.4 color.cpp: yuv_shift = 14, R2Y = 4899, G2Y = 9617, B2Y = 1868; not checkable here):
+//             (R*4899 + G*9617 + B*1868 + (1 << 13)) >> 14
+// channels = 3 or 4 (alpha ignored); bgr != 0: the first channel is blue.
+void orc_cvt_gray(const uint8_t* src, int rows, int cols, int step, int channels, int bgr, int variant, uint8_t* dst, int dstep) {
+    for (int y = 0; y < rows; ++y)
+        for (int x = 0; x < cols; ++x) {
+            const uint8_t* p = src + (size_t)y * step + (size_t)x * channels;
+            const int r = bgr ? p[2] : p[0], g = p[1], b = bgr ? p[0] : p[2];
+            dst[(size_t)y * dstep + x] = variant == 3 ? (uint8_t)((r * 4899 + g * 9617 + b * 1868 + (1 << 13)) >> 14)
+                                                      : (uint8_t)((r * 9798 + g * 19235 + b * 3735 + (1 << 14)) >> 15);
+        }
+}
+
+// cv::remap(src, dst, map1, map2, cv::INTER_LINEAR) with CV_32FC1 maps and the default BORDER_CONSTANT 0, as called by
+// Examples/Stereo/stereo_euroc.cc:136-137 (maps from cv::initUndistortRectifyMap, :97-98).  OpenCV imgwarp.cpp:
+// coordinates are rounded to 1/32 px (sx = cvRound(map1 * 32), ix = sx >> 5 saturated to short, fx = sx & 31), the four
+// taps are blended with the 15-bit table BilinearTab_i[fy][fx] = cvRound of the float products, saturated to short
+// (so 1.0 becomes 32767 and the missing unit goes to the last tap), result (sum + (1 << 14)) >> 15; taps outside the
+// source read 0.  Pinned against cv2 4.13.0 (0 mismatches, tests/test_ingest_oracle.py).
+void orc_remap_linear(const uint8_t* src, int srows, int scols, int sstep, int channels, const float* mapx, const float* mapy,
+                      int mstep, int drows, int dcols, uint8_t* dst, int dstep) {
+    for (int y = 0; y < drows; ++y)
+        for (int x = 0; x < dcols; ++x) {
+            const int sx = cv_round_f(mapx[(size_t)y * mstep + x] * 32.0f), sy = cv_round_f(mapy[(size_t)y * mstep + x] * 32.0f);
+            const int fx = sx & 31, fy = sy & 31;
+            int ix = sx >> 5, iy = sy >> 5;
+            ix = ix < -32768 ? -32768 : (ix > 32767 ? 32767 : ix);
+            iy = iy < -32768 ? -32768 : (iy > 32767 ? 32767 : iy);
+            const float a = 1.0f - fy / 32.0f, b = fy / 32.0f, c = 1.0f - fx / 32.0f, d = fx / 32.0f;
+            const float t[4] = {a * c, a * d, b * c, b * d};
+            int w[4], isum = 0;
+            for (int k = 0; k < 4; ++k) {
+                int v = cv_round_f(t[k] * 32768.0f);
+                w[k] = v > 32767 ? 32767 : (v < -32768 ? -32768 : v);
+                isum += w[k];
+            }
+            if (isum != 32768) w[3] -= isum - 32768;  // only (fy, fx) = (0, 0): {32767, 0, 0, 1}
+            for (int ch = 0; ch < channels; ++ch) {
+                auto tap = [&](int yy, int xx) -> int {
+                    return (xx >= 0 && yy >= 0 && xx < scols && yy < srows) ? src[(size_t)yy * sstep + (size_t)xx * channels + ch] : 0;
+                };
+                const int v = tap(iy, ix) * w[0] + tap(iy, ix + 1) * w[1] + tap(iy + 1, ix) * w[2] + tap(iy + 1, ix + 1) * w[3];
+                int o = (v + (1 << 14)) >> 15;
+                o = o < 0 ? 0 : (o > 255 ? 255 : o);
+                dst[(size_t)y * dstep + (size_t)x * channels + ch] = (uint8_t)o;
+            }
+        }
+}
+
 void orc_synth_frame(uint8_t* dst, int rows, int cols, int step, uint64_t seed, uint64_t frame,
                      int variant, int right) {
     synth_frame(dst, rows, cols, step, seed, frame, variant, right);

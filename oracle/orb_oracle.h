@@ -138,6 +138,10 @@ int orc_search_for_triangulation(const uint8_t* d1, const float* x1, const float
                                  const uint8_t* has2, int n2, const int* nodes1, const int* off1, const int* idx1, int nn1,
                                  const int* nodes2, const int* off2, const int* idx2, int nn2, const float* F12, const float* sigma2,
                                  int checkOri, int* matches12);
+// Image ingest models: cv::cvtColor RGB/BGR(A) -> gray and cv::remap INTER_LINEAR with CV_32FC1 maps (BORDER_CONSTANT 0).
+void orc_cvt_gray(const uint8_t* src, int rows, int cols, int step, int channels, int bgr, int variant, uint8_t* dst, int dstep);
+void orc_remap_linear(const uint8_t* src, int srows, int scols, int sstep, int channels, const float* mapx, const float* mapy,
+                      int mstep, int drows, int dcols, uint8_t* dst, int dstep);
 void orc_synth_frame(uint8_t* dst, int rows, int cols, int step, uint64_t seed, uint64_t frame,
                      int variant, int right);
 // Multi-threaded CPU baseline: n frames of the synthetic generator, one frame

@@ -44,6 +44,13 @@ class OrbFeatureVector(C.Structure):
     _fields_ = [("nodes", C.c_void_p), ("off", C.c_void_p), ("idx", C.c_void_p), ("n_nodes", C.c_int32)]
 
 
+class OrbIngestConfig(C.Structure):
+    """orb_ingest_config: raw frame -> cv::remap -> cv::cvtColor gray (include/orb_b200.h)."""
+    _fields_ = [("src_rows", C.c_int32), ("src_cols", C.c_int32), ("channels", C.c_int32), ("bgr", C.c_int32),
+                ("gray_variant", C.c_int32), ("dst_rows", C.c_int32), ("dst_cols", C.c_int32),
+                ("map_x", C.c_void_p), ("map_y", C.c_void_p)]
+
+
 class OrbError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"orb_b200 error {code}: {msg}")
@@ -66,6 +73,7 @@ EXPORTS = [
     "orb_extractor_create", "orb_extractor_destroy", "orb_extractor_tables",
     "orb_extractor_keypoint_bound", "orb_extract", "orb_extract_batch", "orb_extract_batch_submit", "orb_extract_batch_wait", "orb_extract_batch_device",
     "orb_extractor_sync", "orb_extractor_stream", "orb_get_pyramid_level",
+    "orb_extractor_set_ingest", "orb_ingest_extract_batch", "orb_ingest_extract_batch_submit", "orb_ingest_extract_batch_device",
     "orb_extractor_level_stats", "orb_extractor_set_profiling", "orb_extractor_stage_times",
     "orb_stage_name", "orb_matcher_create", "orb_matcher_destroy", "orb_match_all",
     "orb_match_all_batch", "orb_match_csr", "orb_distances_csr", "orb_stereo_match", "orb_compute_stereo_matches", "orb_matcher_sync",
@@ -96,6 +104,10 @@ def lib():
         L.orb_extract_batch_wait.argtypes = [vp, i32]
         L.orb_extract_batch_device.argtypes = [vp, i32, vp, i32, i32, sz, sz, vp, vp, i32, vp]
         L.orb_extractor_sync.argtypes = [vp]
+        L.orb_extractor_set_ingest.argtypes = [vp, C.POINTER(OrbIngestConfig)]
+        L.orb_ingest_extract_batch.argtypes = [vp, i32, vp, sz, sz, vp, vp, i32, vp]
+        L.orb_ingest_extract_batch_submit.argtypes = [vp, i32, vp, sz, sz, vp, vp, i32, vp, C.POINTER(i32)]
+        L.orb_ingest_extract_batch_device.argtypes = [vp, i32, vp, sz, sz, vp, vp, i32, vp]
         L.orb_extractor_stream.argtypes = [vp]
         L.orb_extractor_stream.restype = vp
         L.orb_get_pyramid_level.argtypes = [vp, i32, i32, vp, sz, C.POINTER(i32), C.POINTER(i32)]

@@ -14,6 +14,8 @@
 #include "orb_plan.h"
 #include "extract_kernels.h"
 
+static unsigned long long g_launches = 0;
+
 // ------------------------------------------------------------------------------------------
 // small helpers
 // ------------------------------------------------------------------------------------------
@@ -1358,6 +1360,79 @@ void orbk_build_ic_table(int2* out) {
 }
 
 // ------------------------------------------------------------------------------------------
+// k_ingest: the step before the path, fused into the level-0 load: cv::remap(INTER_LINEAR, CV_32FC1 maps,
+// BORDER_CONSTANT 0) of the raw frame (reference Examples/Stereo/stereo_euroc.cc:136-137) and / or
+// cv::cvtColor RGB/BGR(A) -> gray (src/Tracking.cc:118-126), written straight into the pitched level-0 buffer,
+// so the rectified / gray image never makes its own round trip through HBM.
+// remap: sx = cvRound(mapx * 32), (ix, fx) = (sx >> 5, sx & 31); taps blended with cvRound((1-fy)(1-fx) * 32768) ...
+// (exact multiples of 32; (0,0) is {32767, 0, 0, 1} after the saturation to short), (sum + 2^14) >> 15.
+// gray: variant 4 (R*9798 + G*19235 + B*3735 + 2^14) >> 15, variant 3 (R*4899 + G*9617 + B*1868 + 2^13) >> 14.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int ingest_pixel(const uint8_t* __restrict__ S, int srows, int scols, size_t sstride, int channels, int bgr,
+                                            int variant, const float* __restrict__ mapx, const float* __restrict__ mapy, int dcols,
+                                            int x, int y) {
+    int v[3] = {0, 0, 0};
+    const int nch = channels >= 3 ? 3 : 1;
+    if (mapx) {
+        const int sx = __float2int_rn(__fmul_rn(mapx[(size_t)y * dcols + x], 32.0f));
+        const int sy = __float2int_rn(__fmul_rn(mapy[(size_t)y * dcols + x], 32.0f));
+        const int fx = sx & 31, fy = sy & 31;
+        const int ix = max(-32768, min(32767, sx >> 5)), iy = max(-32768, min(32767, sy >> 5));
+        int w0 = (32 - fy) * (32 - fx) * 32, w3 = fy * fx * 32;
+        const int w1 = (32 - fy) * fx * 32, w2 = fy * (32 - fx) * 32;
+        if (w0 == 32768) {
+            w0 = 32767;
+            w3 = 1;
+        }
+        const bool x0 = ix >= 0 && ix < scols, x1 = ix + 1 >= 0 && ix + 1 < scols;
+        const bool y0 = iy >= 0 && iy < srows, y1 = iy + 1 >= 0 && iy + 1 < srows;
+        const uint8_t* r0 = S + (size_t)(y0 ? iy : 0) * sstride;
+        const uint8_t* r1 = S + (size_t)(y1 ? iy + 1 : 0) * sstride;
+        const size_t c0 = (size_t)(x0 ? ix : 0) * channels, c1 = (size_t)(x1 ? ix + 1 : 0) * channels;
+        for (int ch = 0; ch < nch; ++ch) {
+            const int t00 = (x0 && y0) ? r0[c0 + ch] : 0, t01 = (x1 && y0) ? r0[c1 + ch] : 0;
+            const int t10 = (x0 && y1) ? r1[c0 + ch] : 0, t11 = (x1 && y1) ? r1[c1 + ch] : 0;
+            v[ch] = min(255, max(0, (t00 * w0 + t01 * w1 + t10 * w2 + t11 * w3 + (1 << 14)) >> 15));
+        }
+    } else {
+        const uint8_t* p = S + (size_t)y * sstride + (size_t)x * channels;
+        for (int ch = 0; ch < nch; ++ch) v[ch] = p[ch];
+    }
+    int g = v[0];
+    if (nch == 3) {
+        const int r = bgr ? v[2] : v[0], b = bgr ? v[0] : v[2];
+        g = variant == 3 ? (r * 4899 + v[1] * 9617 + b * 1868 + (1 << 13)) >> 14 : (r * 9798 + v[1] * 19235 + b * 3735 + (1 << 14)) >> 15;
+    }
+    return g;
+}
+
+// four output pixels per thread, one aligned 32-bit store (the level-0 pitch is a multiple of 64; columns past
+// dcols inside the last word are written as 0)
+__global__ void __launch_bounds__(256) k_ingest(const uint8_t* __restrict__ raw, int srows, int scols, size_t sstride, size_t sframe,
+                                                int channels, int bgr, int variant, const float* __restrict__ mapx,
+                                                const float* __restrict__ mapy, int drows, int dcols, uint8_t* __restrict__ dst,
+                                                int dpitch, unsigned long long dplane) {
+    const int x4 = (blockIdx.x * 64 + threadIdx.x) * 4, y = blockIdx.y * 4 + threadIdx.y, f = blockIdx.z;
+    if (x4 >= dcols || y >= drows) return;
+    const uint8_t* S = raw + (size_t)f * sframe;
+    uint32_t word = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        if (x4 + i < dcols)
+            word |= (uint32_t)ingest_pixel(S, srows, scols, sstride, channels, bgr, variant, mapx, mapy, dcols, x4 + i, y) << (8 * i);
+    *reinterpret_cast<uint32_t*>(dst + (size_t)f * dplane + (size_t)y * dpitch + x4) = word;
+}
+
+cudaError_t orbk_ingest(const uint8_t* raw, int nframes, int srows, int scols, size_t sstride, size_t sframe, int channels, int bgr,
+                        int variant, const float* mapx, const float* mapy, int drows, int dcols, uint8_t* dst, int dpitch,
+                        unsigned long long dplane, cudaStream_t st) {
+    dim3 block(64, 4), grid((dcols + 255) / 256, (drows + 3) / 4, nframes);
+    k_ingest<<<grid, block, 0, st>>>(raw, srows, scols, sstride, sframe, channels, bgr, variant, mapx, mapy, drows, dcols, dst, dpitch, dplane);
+    ++g_launches;
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
 // k_repitch: densely packed host frames (row stride == cols), copied to the device with ONE
 // linear transfer per chunk (row-by-row 2D copies are several times slower over PCIe), are laid
 // out with the internal 64-byte aligned pitch here.  4 bytes per thread, funnel-shifted loads.
@@ -1407,7 +1482,6 @@ cudaError_t orbk_encode_level_map(CUtensorMap* out, const uint8_t* base, int col
     return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
 
-static unsigned long long g_launches = 0;
 unsigned long long orbk_launch_count() { return g_launches; }
 void orbk_count_launch(int n) { g_launches += n; }
 

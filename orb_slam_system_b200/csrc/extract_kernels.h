@@ -45,3 +45,8 @@ cudaError_t orbk_repitch(const uint8_t* dense, int nframes, int rows, int cols, 
                          cudaStream_t st);
 unsigned long long orbk_launch_count();
 void orbk_count_launch(int n);
+// Ingest fused into the level-0 load: cv::remap (INTER_LINEAR, CV_32FC1 maps; mapx == NULL: none) and / or
+// cv::cvtColor to gray of nframes raw frames, written into the pitched level-0 buffer.
+cudaError_t orbk_ingest(const uint8_t* raw, int nframes, int srows, int scols, size_t sstride, size_t sframe, int channels, int bgr,
+                        int variant, const float* mapx, const float* mapy, int drows, int dcols, uint8_t* dst, int dpitch,
+                        unsigned long long dplane, cudaStream_t st);

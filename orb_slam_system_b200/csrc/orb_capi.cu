@@ -154,6 +154,12 @@ struct orb_extractor {
         int* h_status = nullptr;  // pinned, max_batch ints: octree status flags of the submitted batch
     } slot[NUM_SLOTS];
     int next_slot = 0;
+    // image ingest (orb_extractor_set_ingest): raw frames -> remap -> gray, fused into the level-0 load
+    struct Ingest {
+        bool on = false;
+        int srows = 0, scols = 0, channels = 1, bgr = 0, variant = 4, drows = 0, dcols = 0;
+        float *d_mapx = nullptr, *d_mapy = nullptr;
+    } ing;
     OrbStreams streams() const { return OrbStreams{stream, stream2, evFork, evJoin}; }
     int max_batch = 1;
     OrbPlan plan;            // current shape (plan.rows == 0: none)
@@ -515,6 +521,8 @@ extern "C" void orb_extractor_destroy(orb_extractor* h) {
         }
     }
     if (h->evFree) cudaEventDestroy(h->evFree);
+    if (h->ing.d_mapx) cudaFree(h->ing.d_mapx);
+    if (h->ing.d_mapy) cudaFree(h->ing.d_mapy);
     for (int i = 1; i < orb_extractor::MAX_LANES; ++i) {
         if (h->laneFork[i]) cudaEventDestroy(h->laneFork[i]);
         if (h->laneJoin[i]) cudaEventDestroy(h->laneJoin[i]);
@@ -589,8 +597,8 @@ static int check_status(orb_extractor* h, int n) {
     return ORB_OK;
 }
 
-extern "C" int orb_extract_batch_device(orb_extractor* h, int n, const uint8_t* d_imgs, int rows, int cols, size_t stride,
-                                        size_t frame_stride, orb_keypoint* d_kps, uint8_t* d_desc, int cap, int* d_counts) {
+static int extract_device_impl(orb_extractor* h, int n, const uint8_t* d_imgs, int rows, int cols, size_t stride, size_t frame_stride,
+                               orb_keypoint* d_kps, uint8_t* d_desc, int cap, int* d_counts, bool ingest) {
     if (!h || !d_kps || !d_desc || !d_counts) return fail(ORB_ERR_INVALID, "null argument");
     if (n < 0 || n > h->max_batch) return fail(ORB_ERR_INVALID, "n=%d exceeds max_batch=%d", n, h->max_batch);
     if (n == 0) return ORB_OK;
@@ -601,14 +609,20 @@ extern "C" int orb_extract_batch_device(orb_extractor* h, int n, const uint8_t* 
         return ORB_OK;
     }
     if (cap <= 0) return fail(ORB_ERR_INVALID, "cap must be positive");
-    if ((stride & 3) || ((uintptr_t)d_imgs & 3) || (frame_stride & 3) || stride < (size_t)cols)
+    if (!ingest && ((stride & 3) || ((uintptr_t)d_imgs & 3) || (frame_stride & 3) || stride < (size_t)cols))
         return fail(ORB_ERR_INVALID, "device frames need 4-byte aligned base and strides >= cols");
     CUDA_TRY(cudaSetDevice(h->device));
     int rc = build_plan(h, rows, cols);
     if (rc != ORB_OK) return rc;
     OrbPlan P = h->plan;
     const CUtensorMap* maps = h->d_maps;
-    if ((int)stride == h->plan.lv[0].pitch && frame_stride == h->plan.lv[0].plane && ((uintptr_t)d_imgs & 15) == 0) {
+    if (ingest) {
+        const orb_extractor::Ingest& I = h->ing;
+        if (stride < (size_t)I.scols * I.channels) return fail(ORB_ERR_INVALID, "stride < src_cols * channels");
+        h->last_l0 = h->level0;
+        CUDA_TRY(orbk_ingest(d_imgs, n, I.srows, I.scols, stride, frame_stride, I.channels, I.bgr, I.variant, I.d_mapx, I.d_mapy, rows, cols,
+                             h->level0, h->plan.lv[0].pitch, h->plan.lv[0].plane, h->stream));
+    } else if ((int)stride == h->plan.lv[0].pitch && frame_stride == h->plan.lv[0].plane && ((uintptr_t)d_imgs & 15) == 0) {
         // same layout as the internal level-0 buffer: read the caller's frames in place
         for (int l = 0; l < P.nlevels; ++l)
             if (P.lv[l].src == 0) P.lv[l].img = const_cast<uint8_t*>(d_imgs);
@@ -652,6 +666,11 @@ extern "C" int orb_extract_batch_device(orb_extractor* h, int n, const uint8_t* 
         }
     }
     return ORB_OK;
+}
+
+extern "C" int orb_extract_batch_device(orb_extractor* h, int n, const uint8_t* d_imgs, int rows, int cols, size_t stride,
+                                        size_t frame_stride, orb_keypoint* d_kps, uint8_t* d_desc, int cap, int* d_counts) {
+    return extract_device_impl(h, n, d_imgs, rows, cols, stride, frame_stride, d_kps, d_desc, cap, d_counts, false);
 }
 
 extern "C" int orb_extractor_sync(orb_extractor* h) {
@@ -698,8 +717,10 @@ extern "C" const char* orb_stage_name(int stage) {
     return stage >= 0 && stage < ORB_STAGES ? names[stage] : "";
 }
 
-extern "C" int orb_extract_batch_submit(orb_extractor* h, int n, const uint8_t* imgs, int rows, int cols, size_t stride,
-                                        size_t frame_stride, orb_keypoint* kps, uint8_t* desc, int cap, int* counts, int* ticket) {
+// rows x cols: the image the extractor sees.  ingest: imgs holds raw frames described by h->ing (stride / frame_stride are
+// theirs), which land in the slot's dense buffer and reach level 0 through k_ingest instead of k_repitch.
+static int submit_impl(orb_extractor* h, int n, const uint8_t* imgs, int rows, int cols, size_t stride, size_t frame_stride,
+                       orb_keypoint* kps, uint8_t* desc, int cap, int* counts, int* ticket, bool ingest) {
     if (!h || !counts || !ticket) return fail(ORB_ERR_INVALID, "null argument");
     *ticket = -1;
     if (n < 0 || n > h->max_batch) return fail(ORB_ERR_INVALID, "n=%d exceeds max_batch=%d", n, h->max_batch);
@@ -709,7 +730,10 @@ extern "C" int orb_extract_batch_submit(orb_extractor* h, int n, const uint8_t* 
         return ORB_OK;
     }
     if (!kps || !desc || cap <= 0) return fail(ORB_ERR_INVALID, "null output buffer");
-    if (stride < (size_t)cols) return fail(ORB_ERR_INVALID, "stride < cols");
+    const orb_extractor::Ingest& I = h->ing;
+    const size_t rowBytes = ingest ? (size_t)I.scols * I.channels : (size_t)cols;
+    const int srcRows = ingest ? I.srows : rows;
+    if (stride < rowBytes) return fail(ORB_ERR_INVALID, ingest ? "stride < src_cols * channels" : "stride < cols");
     orb_extractor::HostSlot& S = h->slot[h->next_slot];
     if (S.busy) return fail(ORB_ERR_INVALID, "two batches are already in flight: call orb_extract_batch_wait first");
     CUDA_TRY(cudaSetDevice(h->device));
@@ -735,14 +759,16 @@ extern "C" int orb_extract_batch_submit(orb_extractor* h, int n, const uint8_t* 
     int nchunks = h->profiling ? 1 : std::min<int>(orb_extractor::MAX_CHUNKS, std::max(1, n / chunkFrames));
     const int per = (n + nchunks - 1) / nchunks;
     nchunks = (n + per - 1) / per;
-    const bool dense = stride == (size_t)cols && frame_stride == (size_t)rows * cols && ((uintptr_t)imgs & 3) == 0 && cols >= 4;
-    if (dense && S.dense_cap < (size_t)n * rows * cols + 16) {
+    const size_t landFrame = rowBytes * srcRows;  // one frame in the dense landing buffer
+    const bool linear = stride == rowBytes && frame_stride == landFrame;
+    const bool dense = ingest || (linear && ((uintptr_t)imgs & 3) == 0 && cols >= 4);
+    if (dense && S.dense_cap < (size_t)n * landFrame + 16) {
         CUDA_TRY(cudaStreamSynchronize(h->streamIn));
         CUDA_TRY(cudaStreamSynchronize(h->stream));
         if (S.d_dense) cudaFree(S.d_dense);
         S.d_dense = nullptr;
         S.dense_cap = 0;
-        const size_t want = (size_t)h->max_batch * rows * cols + 16;
+        const size_t want = (size_t)h->max_batch * landFrame + 16;
         CUDA_TRY(cudaMalloc((void**)&S.d_dense, want));
         S.dense_cap = want;
     }
@@ -763,11 +789,22 @@ extern "C" int orb_extract_batch_submit(orb_extractor* h, int n, const uint8_t* 
         if (dense) {
             // densely packed frames: one linear copy into this batch's own landing buffer (it may run while the
             // previous batch still computes), then the pitch conversion on the kernel lane
-            uint8_t* land = S.d_dense + (size_t)f0 * rows * cols;
-            CUDA_TRY(cudaMemcpyAsync(land, imgs + (size_t)f0 * frame_stride, (size_t)nf * rows * cols, cudaMemcpyHostToDevice, h->streamIn));
+            uint8_t* land = S.d_dense + (size_t)f0 * landFrame;
+            if (linear) {
+                CUDA_TRY(cudaMemcpyAsync(land, imgs + (size_t)f0 * frame_stride, (size_t)nf * landFrame, cudaMemcpyHostToDevice, h->streamIn));
+            } else {  // raw frames with padded rows: packed on the way in
+                for (int f = 0; f < nf; ++f)
+                    CUDA_TRY(cudaMemcpy2DAsync(land + (size_t)f * landFrame, rowBytes, imgs + (size_t)(f0 + f) * frame_stride, stride, rowBytes,
+                                               srcRows, cudaMemcpyHostToDevice, h->streamIn));
+            }
             CUDA_TRY(cudaEventRecord(S.evIn[c], h->streamIn));
             CUDA_TRY(cudaStreamWaitEvent(ls.st, S.evIn[c], 0));
-            CUDA_TRY(orbk_repitch(land, nf, rows, cols, h->level0 + f0 * L0.plane, L0.pitch, L0.plane, ls.st));
+            if (ingest) {
+                CUDA_TRY(orbk_ingest(land, nf, I.srows, I.scols, rowBytes, landFrame, I.channels, I.bgr, I.variant, I.d_mapx, I.d_mapy, rows, cols,
+                                     h->level0 + f0 * L0.plane, L0.pitch, L0.plane, ls.st));
+            } else {
+                CUDA_TRY(orbk_repitch(land, nf, rows, cols, h->level0 + f0 * L0.plane, L0.pitch, L0.plane, ls.st));
+            }
         } else {
             if (nf == 1 || frame_stride == stride * (size_t)rows) {
                 // frames are consecutive rows on both sides (device plane == pitch * rows): one 2D copy
@@ -804,6 +841,72 @@ extern "C" int orb_extract_batch_submit(orb_extractor* h, int n, const uint8_t* 
     *ticket = h->next_slot;
     h->next_slot = (h->next_slot + 1) % orb_extractor::NUM_SLOTS;
     return ORB_OK;
+}
+
+extern "C" int orb_extract_batch_submit(orb_extractor* h, int n, const uint8_t* imgs, int rows, int cols, size_t stride,
+                                        size_t frame_stride, orb_keypoint* kps, uint8_t* desc, int cap, int* counts, int* ticket) {
+    return submit_impl(h, n, imgs, rows, cols, stride, frame_stride, kps, desc, cap, counts, ticket, false);
+}
+
+// ------------------------------------------------------------------------------------------
+// image ingest (reference src/Tracking.cc:118-126, Examples/Stereo/stereo_euroc.cc:136-137)
+// ------------------------------------------------------------------------------------------
+extern "C" int orb_extractor_set_ingest(orb_extractor* h, const orb_ingest_config* cfg) {
+    if (!h) return fail(ORB_ERR_INVALID, "null handle");
+    for (int k = 0; k < orb_extractor::NUM_SLOTS; ++k)
+        if (h->slot[k].busy) return fail(ORB_ERR_INVALID, "cannot change the ingest configuration while a batch is in flight");
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    orb_extractor::Ingest& I = h->ing;
+    if (I.d_mapx) cudaFree(I.d_mapx);
+    if (I.d_mapy) cudaFree(I.d_mapy);
+    I = orb_extractor::Ingest();
+    if (!cfg) return ORB_OK;
+    if (cfg->src_rows <= 0 || cfg->src_cols <= 0 || cfg->dst_rows <= 0 || cfg->dst_cols <= 0)
+        return fail(ORB_ERR_INVALID, "ingest: sizes must be positive");
+    if (cfg->channels != 1 && cfg->channels != 3 && cfg->channels != 4) return fail(ORB_ERR_INVALID, "ingest: channels must be 1, 3 or 4");
+    if (cfg->gray_variant != 3 && cfg->gray_variant != 4) return fail(ORB_ERR_INVALID, "ingest: gray_variant must be 3 or 4");
+    if ((cfg->map_x == nullptr) != (cfg->map_y == nullptr)) return fail(ORB_ERR_INVALID, "ingest: map_x and map_y go together");
+    if (!cfg->map_x && (cfg->dst_rows != cfg->src_rows || cfg->dst_cols != cfg->src_cols))
+        return fail(ORB_ERR_INVALID, "ingest: without maps dst must equal src");
+    if (cfg->map_x) {
+        const size_t bytes = sizeof(float) * (size_t)cfg->dst_rows * cfg->dst_cols;
+        CUDA_TRY(cudaMalloc((void**)&I.d_mapx, bytes));
+        CUDA_TRY(cudaMalloc((void**)&I.d_mapy, bytes));
+        CUDA_TRY(cudaMemcpy(I.d_mapx, cfg->map_x, bytes, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(I.d_mapy, cfg->map_y, bytes, cudaMemcpyHostToDevice));
+    }
+    I.srows = cfg->src_rows;
+    I.scols = cfg->src_cols;
+    I.channels = cfg->channels;
+    I.bgr = cfg->bgr != 0;
+    I.variant = cfg->gray_variant;
+    I.drows = cfg->dst_rows;
+    I.dcols = cfg->dst_cols;
+    I.on = true;
+    return ORB_OK;
+}
+
+extern "C" int orb_ingest_extract_batch_submit(orb_extractor* h, int n, const uint8_t* raw, size_t stride, size_t frame_stride,
+                                               orb_keypoint* kps, uint8_t* desc, int cap, int* counts, int* ticket) {
+    if (!h) return fail(ORB_ERR_INVALID, "null handle");
+    if (!h->ing.on) return fail(ORB_ERR_INVALID, "no ingest configuration: call orb_extractor_set_ingest first");
+    return submit_impl(h, n, raw, h->ing.drows, h->ing.dcols, stride, frame_stride, kps, desc, cap, counts, ticket, true);
+}
+
+extern "C" int orb_ingest_extract_batch(orb_extractor* h, int n, const uint8_t* raw, size_t stride, size_t frame_stride,
+                                        orb_keypoint* kps, uint8_t* desc, int cap, int* counts) {
+    int ticket = -1;
+    int rc = orb_ingest_extract_batch_submit(h, n, raw, stride, frame_stride, kps, desc, cap, counts, &ticket);
+    if (rc != ORB_OK) return rc;
+    return orb_extract_batch_wait(h, ticket);
+}
+
+extern "C" int orb_ingest_extract_batch_device(orb_extractor* h, int n, const uint8_t* d_raw, size_t stride, size_t frame_stride,
+                                               orb_keypoint* d_kps, uint8_t* d_desc, int cap, int* d_counts) {
+    if (!h) return fail(ORB_ERR_INVALID, "null handle");
+    if (!h->ing.on) return fail(ORB_ERR_INVALID, "no ingest configuration: call orb_extractor_set_ingest first");
+    return extract_device_impl(h, n, d_raw, h->ing.drows, h->ing.dcols, stride, frame_stride, d_kps, d_desc, cap, d_counts, true);
 }
 
 extern "C" int orb_extract_batch_wait(orb_extractor* h, int ticket) {

@@ -9,7 +9,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import KP_DTYPE, OrbParams, check, lib, ptr
+from ._lib import KP_DTYPE, OrbIngestConfig, OrbParams, check, lib, ptr
 
 
 class ORBextractor:
@@ -138,6 +138,66 @@ class ORBextractor:
 
     def sync(self):
         check(lib().orb_extractor_sync(self._h))
+
+    # ---- image ingest: cv::remap + cv::cvtColor fused into the level-0 load ----
+    def set_ingest(self, src_shape=None, maps=None, bgr=False, gray_variant=4):
+        """What the reference does to a raw frame before operator(): cv::remap(raw, M1, M2, INTER_LINEAR)
+        (Examples/Stereo/stereo_euroc.cc:136-137) and cv::cvtColor(..., CV_RGB2GRAY / CV_BGR2GRAY)
+        (src/Tracking.cc:118-126).  src_shape = (rows, cols[, channels]); maps = (map_x, map_y) float32
+        [dst_rows, dst_cols] from cv::initUndistortRectifyMap, or None; bgr = not Camera.RGB.
+        src_shape None clears the configuration."""
+        if src_shape is None:
+            check(lib().orb_extractor_set_ingest(self._h, None))
+            self._ingest = None
+            return
+        rows, cols = int(src_shape[0]), int(src_shape[1])
+        ch = int(src_shape[2]) if len(src_shape) > 2 else 1
+        cfg = OrbIngestConfig(rows, cols, ch, int(bool(bgr)), int(gray_variant), rows, cols, None, None)
+        keep = None
+        if maps is not None:
+            mx = np.ascontiguousarray(maps[0], np.float32)
+            my = np.ascontiguousarray(maps[1], np.float32)
+            assert mx.ndim == 2 and mx.shape == my.shape
+            cfg.dst_rows, cfg.dst_cols = mx.shape
+            cfg.map_x, cfg.map_y = mx.ctypes.data, my.ctypes.data
+            keep = (mx, my)
+        check(lib().orb_extractor_set_ingest(self._h, C.byref(cfg)))
+        del keep
+        self._ingest = (rows, cols, ch, cfg.dst_rows, cfg.dst_cols)
+
+    def ingest_extract_batch(self, raw, cap=None):
+        """n raw host frames [n, rows, cols] or [n, rows, cols, channels] -> list of (keypoints, descriptors)
+        of the remapped / gray-converted frames."""
+        raw = np.ascontiguousarray(raw, np.uint8)
+        n = raw.shape[0]
+        assert getattr(self, "_ingest", None) is not None, "set_ingest first"
+        assert n <= self.max_batch and raw.shape[1:3] == self._ingest[:2]
+        drows, dcols = self._ingest[3:5]
+        cap = cap or self.keypoint_bound(drows, dcols)
+        kps = np.zeros((n, cap), KP_DTYPE)
+        desc = np.zeros((n, cap, 32), np.uint8)
+        counts = np.zeros(n, np.int32)
+        check(lib().orb_ingest_extract_batch(self._h, n, ptr(raw), raw.strides[1], raw.strides[0], ptr(kps), ptr(desc),
+                                             cap, ptr(counts)))
+        self._last_frames = n
+        return [(kps[f, :counts[f]].copy(), desc[f, :counts[f]].copy()) for f in range(n)]
+
+    def submit_ingest_pinned(self, raw, kps, desc, counts, cap):
+        """Asynchronous form on caller-owned (pinned) buffers; raw [n, rows, cols(, channels)]; wait with wait_batch."""
+        n = raw.shape[0]
+        st = (lambda i: int(raw.stride(i))) if hasattr(raw, "stride") else (lambda i: int(raw.strides[i]))
+        t = C.c_int(-1)
+        check(lib().orb_ingest_extract_batch_submit(self._h, n, ptr(raw), st(1), st(0), ptr(kps), ptr(desc), cap, ptr(counts),
+                                                    C.byref(t)))
+        self._last_frames = n
+        return t.value
+
+    def ingest_extract_batch_device(self, d_raw, d_kps, d_desc, d_counts, cap):
+        """Device-resident raw frames (torch CUDA uint8 [n, rows, cols(, channels)]); asynchronous on the handle's stream."""
+        n = d_raw.shape[0]
+        check(lib().orb_ingest_extract_batch_device(self._h, n, ptr(d_raw), d_raw.stride(1), d_raw.stride(0), ptr(d_kps),
+                                                    ptr(d_desc), cap, ptr(d_counts)))
+        self._last_frames = n
 
     @property
     def stream(self):
