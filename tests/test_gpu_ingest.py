@@ -88,7 +88,7 @@ def test_rectify_colour_changes_size_and_strides():
 def test_level0_equals_cv2_vectors():
     """GPU ingest against cv2 4.13 outputs directly (committed vectors): remap of a colour frame, then gray."""
     raw = G["raw_color"][None]
-    ex = ORBextractor(300, 1.2, 8, 20, 7)
+    ex = ORBextractor(300, 1.2, 2, 20, 7)   # two levels: the vectors are small images
     ex.set_ingest(raw.shape[1:], maps=(G["map_x"], G["map_y"]))
     ex.ingest_extract_batch(raw)
     assert np.array_equal(ex.pyramid_level(0), oracle.cvt_gray(G["rect_color"]))
