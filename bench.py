@@ -353,8 +353,10 @@ def main():
     l0 = kernel_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
+    th0 = time.perf_counter()
     for i in range(K):
         step_device(W + i)
+    host_enqueue_ms = 1e3 * (time.perf_counter() - th0) / K
     e1.record(stream)
     ex.sync()
     barrier()
@@ -532,7 +534,7 @@ def main():
             "e2e": {"value": frames / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "orb_extract_batch_submit/_wait, two 64-frame steps in flight, pinned host buffers",
                     "sync_call_value": frames / e2e_sync_s, "sync_call_api": "orb_extract_batch, one step at a time"},
-            "gpu_launches": int(launches), "clocks": clocks,
+            "gpu_launches": int(launches), "host_enqueue_ms_per_step": host_enqueue_ms, "clocks": clocks,
             "hamming": {"metric": "Hamming pairs/s (brute force, best + second best)", "value": world * NP * NQ * NQ / (match_ms * 1e-3),
                         "unit": "pairs/s", "workload": f"{NP} keyframe pairs x {NQ} x {NQ} descriptors per GPU (BASELINE config 4)",
                         "ms_per_launch": match_ms,

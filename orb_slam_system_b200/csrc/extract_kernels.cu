@@ -1146,188 +1146,243 @@ __device__ __forceinline__ int level_prefix(const int* kc, int nlevels, int lane
     return pre - myK;  // exclusive prefix
 }
 
-// The describe stage is three kernels that hand their intermediate values over in the output record itself
-// (orb_keypoint_dev slots x, y hold m01, m10 after k_orient; angle, size, response hold angle, cos, sin after
-// k_angle; k_brief writes the final record):
-//   k_orient  one warp per keypoint: the two intensity-centroid moments (IC_Angle :21-48), exact int32
-//   k_angle   one THREAD per keypoint: cv::fastAtan2 and the cos / sin of the descriptor rotation (:59-60) --
-//             warp-uniform scalar work in a warp-per-keypoint kernel, done here 32 keypoints per instruction
-//   k_brief   one warp per keypoint: the 182 rBRIEF tests on the blurred level (:57-73) and the final record
+// ------------------------------------------------------------------------------------------
+// k_describe_tile: orientation, angle, rBRIEF and the final record for the keypoints of one describe tile.
 //
-// IC_Angle weight table (built on the host by orbk_build_ic_table, plan.icTab):
-// entry [a][v + 15][k] for patch alignment a = (x - 15) & 3, row v, aligned word k (9 words
-// cover u = -15 - a .. 20 - a): .x = four signed bytes u (0 outside the disc |u| <= umax[|v|]),
-// .y = four signed bytes v (0 outside the disc).  m10 += dp4a(pixels, .x); m01 += dp4a(pixels, .y).
-__global__ void __launch_bounds__(256) k_orient(const __grid_constant__ OrbPlan plan, orb_keypoint_dev* __restrict__ kps, int cap,
-                                                int* __restrict__ counts) {
-    const int f = blockIdx.y;
+// One CTA = one tile of one source level of one frame (DSC_W x DSC_H keypoint positions).  The raw and the
+// blurred level around it (18-px halo) are staged by one TMA box load each, so every level pixel crosses
+// L2 -> SM about twice per frame instead of once per keypoint patch that covers it (the patches of a
+// KITTI-shape frame cover the pyramid ~5x).  The CTA then
+//   scan     walks the kept lists of the levels that share this source (a level and its same-size alias) and
+//            collects the keypoints inside its core -- no binning pass, the lists are a few KB;
+//   phase 1  warp per keypoint: IC_Angle moments (ORBextractor.cc:21-48) from the raw tile.  The patch row is
+//            brought to a canonical alignment with a funnel shift, so the dp4a weights are keypoint
+//            independent and live in registers (lane = row % 4, word 0..7; 8 steps cover the 31 rows);
+//   phase 2  thread per keypoint: cv::fastAtan2 and the cos / sin of the descriptor rotation (:59-60);
+//   phase 3  warp per keypoint: the 182 rBRIEF tests (:57-73) gathered from the blurred tile, bits packed by
+//            ballot, and the final record (:345-352, :486-491).
+// A tile holding more than DSC_LIST keypoints (dense adversarial input) is processed in rounds over slices of
+// the kept lists.
+// ------------------------------------------------------------------------------------------
+struct DescTileSmem {
+    unsigned xy[DSC_LIST];        // x | y << 16, level coordinates
+    unsigned resp[DSC_LIST];      // FAST response
+    unsigned lo[DSC_LIST];        // level << 24 | output index
+    int m01[DSC_LIST], m10[DSC_LIST];
+    float angle[DSC_LIST], ca[DSC_LIST], sb[DSC_LIST];
+    int levels[ORB_MAX_LEVELS];   // levels whose keypoints live on this source's pixels
+    int nLevels;
+    int count;
+    unsigned long long bar;
+};
+static const size_t kDescTileBytes = (size_t)DSC_BOX_W * DSC_BOX_H;
+static const size_t kDescSmem = kDescTileBytes + sizeof(DescTileSmem);
+
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__global__ void __launch_bounds__(DSC_THREADS, 4) k_describe_tile(const __grid_constant__ OrbPlan plan, const DetectMaps* __restrict__ maps,
+                                                                  orb_keypoint_dev* __restrict__ kps, uint8_t* __restrict__ desc,
+                                                                  int cap, int* __restrict__ counts) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const unsigned char* tileT = smem_raw;  // the raw tile (phase 1), then the blurred tile (phase 3)
+    DescTileSmem& sm = *reinterpret_cast<DescTileSmem*>(smem_raw + kDescTileBytes);
+    const int f = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int* kc = plan.keptCount + f * ORB_MAX_LEVELS;
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (blockIdx.x == 0 && tid == 0) {
         int tot = 0;
         for (int i = 0; i < plan.nlevels; ++i) tot += kc[i];
         counts[f] = tot;
     }
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int tile = blockIdx.x, s = 0;
+    for (; s < plan.nlevels; ++s) {
+        const OrbLevel& L = plan.lv[s];
+        if (L.src == s && tile >= L.dTileBase && tile < L.dTileBase + L.dTiles) break;
+    }
+    if (s >= plan.nlevels) return;
+    const OrbLevel& S = plan.lv[s];
+    tile -= S.dTileBase;
+    const int ty = tile / S.dTilesX, tx = tile - ty * S.dTilesX;
+    const int bx0 = DSC_W * tx, by0 = 1 + DSC_H * ty;            // level pixel of box byte (0, 0)
+    const unsigned xlo = ORB_EDGE + DSC_W * tx, ylo = ORB_EDGE + DSC_H * ty;  // core: [xlo, xlo + DSC_W) x [ylo, ylo + DSC_H)
+
+    // ---- output offsets of the levels (levels are concatenated 0..n-1, ORBextractor.cc:466-494) and the levels on this source
     int myK, total;
     const int pre = level_prefix(kc, plan.nlevels, lane, cap, myK, total);
-    // Lane (r3, kk) = (lane / 9, lane % 9) for lanes 0..26 reads aligned word kk of patch rows
-    // r3, r3 + 3, r3 + 6, ... (11 steps cover the 31 rows).
-    const int r3 = lane / 9, kk = lane - r3 * 9;
-    for (int o = blockIdx.x * 8 + warp; o < total; o += gridDim.x * 8) {
-        int l, r;
-        locate_keypoint(o, pre, myK, plan.nlevels, lane, l, r);
-        const OrbLevel& L = plan.lv[l];
-        const OrbLevel& S = plan.lv[L.src];
-        const uint2 k = L.kept[(size_t)f * L.kmax + r];
-        const int x = (int)(k.x & 0xffff), y = (int)(k.x >> 16);
-        int m10 = 0, m01 = 0;
-        const int a = (x - 15) & 3;
-        const unsigned pw = (unsigned)S.pitch >> 2;  // level rows are 4-byte aligned
-        if (lane < 27) {
-            const unsigned* p = reinterpret_cast<const unsigned*>(S.img + (size_t)f * S.plane + (size_t)(y - 15) * S.pitch + (x - 15 - a)) +
-                                (unsigned)r3 * pw + (unsigned)kk;
-            const int2* tab = plan.icTab + a * (31 * 9) + lane;
-            const size_t step = (size_t)3 * pw;  // three rows down, in words
-#pragma unroll
-            for (int it = 0; it < 11; ++it) {
-                if (it < 10 || r3 == 0) {  // row it*3 + r3 < 31
-                    const unsigned w = __ldg(p);
-                    const int2 t = __ldg(tab + it * 27);
-                    m10 = dp4a_us(w, t.x, m10);
-                    m01 = dp4a_us(w, t.y, m01);
-                }
-                p += step;
-            }
-        }
-        for (int sft = 16; sft > 0; sft >>= 1) {
-            m10 += __shfl_xor_sync(0xffffffffu, m10, sft);
-            m01 += __shfl_xor_sync(0xffffffffu, m01, sft);
-        }
-        if (lane == 0) {
-            int2* slot = reinterpret_cast<int2*>(kps + (size_t)f * cap + o);  // .x, .y of the record (the record array is 4-byte aligned)
-            reinterpret_cast<int*>(slot)[0] = m01;
-            reinterpret_cast<int*>(slot)[1] = m10;
-        }
+    int nOnSrc = 0;  // keypoints of all levels that live on this source
+    for (int l = s; l < plan.nlevels; ++l)
+        if (plan.lv[l].src == s) nOnSrc += __shfl_sync(0xffffffffu, myK, l);
+    if (nOnSrc == 0) return;  // uniform over the CTA: nothing was issued yet
+    const unsigned bar = smem_u32(&sm.bar);
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        int n = 0;
+        for (int l = s; l < plan.nlevels; ++l)
+            if (plan.lv[l].src == s) sm.levels[n++] = l;
+        sm.nLevels = n;
+        sm.count = 0;
     }
-}
-
-__global__ void __launch_bounds__(256) k_angle(const __grid_constant__ OrbPlan plan, orb_keypoint_dev* __restrict__ kps, int cap) {
-    const int f = blockIdx.y;
-    const int* kc = plan.keptCount + f * ORB_MAX_LEVELS;
-    int total = 0;
-    for (int i = 0; i < plan.nlevels; ++i) total += kc[i];
-    total = min(total, cap);
-    for (int o = blockIdx.x * 256 + threadIdx.x; o < total; o += gridDim.x * 256) {
-        orb_keypoint_dev* kp = kps + (size_t)f * cap + o;
-        const int m01 = __float_as_int(kp->x), m10 = __float_as_int(kp->y);
-        const float angle = fast_atan2_deg((float)m01, (float)m10);
-        const float factorPI = (float)(3.141592653589793238462643383279502884 / 180.f);
-        const float rad = __fmul_rn(angle, factorPI);
-        double sd, cd;
-        sincos_0_2pi((double)rad, sd, cd);
-        kp->angle = angle;
-        kp->size = (float)cd;      // a = cos
-        kp->response = (float)sd;  // b = sin
-    }
-}
-
-// Patch of the blurred level around a keypoint: rows y-18 .. y+18, 48 bytes per row starting at the 8-byte aligned
-// column xa = (x - 18) & ~7 (the 37 needed bytes end at most 44 bytes after xa).  Level pitches are multiples of 64 and
-// the levels' allocations leave slack after the last row, so the 8-byte loads stay inside the allocation.
-#define BRIEF_PW 48               // smem bytes per patch row
-#define BRIEF_ROWS 37
-#define BRIEF_LOADS 8             // 8-byte loads per lane: lane -> (row lane / 6, chunk lane % 6), 5 rows per step, 30 lanes busy
-
-struct BriefKey {                 // what the tests and the final record need from one keypoint
-    int x, y, l, o;
-    unsigned response;
-    float angle, a, b;
-};
-
-__global__ void __launch_bounds__(256) k_brief(const __grid_constant__ OrbPlan plan, orb_keypoint_dev* __restrict__ kps,
-                                               uint8_t* __restrict__ desc, int cap) {
-    __shared__ uint2 s_patch[8][BRIEF_ROWS * BRIEF_PW / 8 + 18];  // per warp (the last step stores 3 rows past row 36)
-    const int f = blockIdx.y;
-    const int* kc = plan.keptCount + f * ORB_MAX_LEVELS;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int myK, total;
-    const int pre = level_prefix(kc, plan.nlevels, lane, cap, myK, total);
-    // the 182 test pairs stay in registers: lane i holds pairs i, i + 32, ... (keypoint independent)
-    float4 pr[6];
-#pragma unroll
-    for (int wq = 0; wq < 6; ++wq) pr[wq] = (wq * 32 + lane < 182) ? __ldg(plan.pairTab + wq * 32 + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
-    const int prow = lane / 6, pchunk = lane - prow * 6;  // lanes 30, 31 idle while staging
-    uint2* patch = s_patch[warp];
-    const int stride = gridDim.x * 8;
-
-    for (int o = blockIdx.x * 8 + warp; o < total; o += stride) {
-        BriefKey ck;
-        {
-            int l, r;
-            locate_keypoint(o, pre, myK, plan.nlevels, lane, l, r);
+    __syncthreads();
+    const int nLv = sm.nLevels;
+    unsigned parity = 0;  // phase of the mbarrier the next TMA load completes
+    bool sliced = false;
+    int sl = 0, sr0 = 0;  // sliced mode: level slot and first rank of the current slice
+    for (;;) {
+        // the raw tile travels while the lists are scanned (every earlier read of the buffer is behind a barrier)
+        if (tid == 0) {
+            fence_proxy_async();
+            mbar_expect_tx(bar, (unsigned)kDescTileBytes);
+            tma_load_3d(smem_u32(tileT), &maps->raw[s], bx0, by0, f + plan.frameBase, bar);
+        }
+        // ---- scan: keypoints of this tile (whole lists, or one slice of DSC_LIST ranks of one level)
+        for (int j = sliced ? sl : 0; j < (sliced ? sl + 1 : nLv); ++j) {
+            const int l = sm.levels[j];
             const OrbLevel& L = plan.lv[l];
-            const OrbLevel& S = plan.lv[L.src];
-            const uint2 k = L.kept[(size_t)f * L.kmax + r];
-            ck.x = (int)(k.x & 0xffff);
-            ck.y = (int)(k.x >> 16);
-            ck.l = l;
-            ck.o = o;
-            ck.response = k.y;
-            const orb_keypoint_dev* rec = kps + (size_t)f * cap + o;
-            ck.angle = rec->angle;
-            ck.a = rec->size;
-            ck.b = rec->response;
-            const int rowsLeft = S.rows - (ck.y - 18);  // rows of the level at and below the patch's first row
-            const uint8_t* g = S.blur + (size_t)f * S.plane + (size_t)(ck.y - 18 + prow) * S.pitch + ((ck.x - 18) & ~7) + pchunk * 8;
-            const size_t step = (size_t)5 * S.pitch;
-            uint2 regs[BRIEF_LOADS];
-#pragma unroll
-            for (int it = 0; it < BRIEF_LOADS; ++it) {
-                // rows past the patch (step 7 covers rows 35..39) are skipped when they would leave the level
-                regs[it] = (lane < 30 && it * 5 + prow < rowsLeft) ? __ldg(reinterpret_cast<const uint2*>(g)) : make_uint2(0u, 0u);
-                g += step;
+            const int nK = min(__shfl_sync(0xffffffffu, myK, l), L.kmax);
+            const int base = __shfl_sync(0xffffffffu, pre, l);
+            const uint2* kept = L.kept + (size_t)f * L.kmax;
+            const int r1 = sliced ? min(nK, sr0 + DSC_LIST) : nK;
+            for (int r = (sliced ? sr0 : 0) + tid; r < r1; r += DSC_THREADS) {
+                const uint2 k = kept[r];
+                const unsigned x = k.x & 0xffffu, y = k.x >> 16;
+                if (x - xlo < (unsigned)DSC_W && y - ylo < (unsigned)DSC_H && base + r < cap) {
+                    const int slot = atomicAdd(&sm.count, 1);
+                    if (slot < DSC_LIST) {
+                        sm.xy[slot] = k.x;
+                        sm.resp[slot] = k.y;
+                        sm.lo[slot] = ((unsigned)l << 24) | (unsigned)(base + r);
+                    }
+                }
             }
-            __syncwarp();  // the previous keypoint's gathers are done
-            if (lane < 30) {
+        }
+        __syncthreads();
+        const int cnt = sm.count;
+        mbar_wait(bar, parity);  // the raw tile has landed (also: never leave with a load in flight)
+        parity ^= 1u;
+        if (!sliced && cnt > DSC_LIST) {  // too many for one round: start over, slice by slice
+            sliced = true;
+            sl = 0;
+            sr0 = 0;
+            __syncthreads();
+            if (tid == 0) sm.count = 0;
+            __syncthreads();
+            continue;
+        }
+        if (cnt > 0) {
+            // ---- phase 1: moments.  lane (r4, j) = (lane / 8, lane % 8): canonical word j of patch rows it*4 + r4
+            {
+                int2 icw[8];  // IC_Angle weights of this lane (keypoint independent)
 #pragma unroll
-                for (int it = 0; it < BRIEF_LOADS; ++it) patch[(it * 5 + prow) * (BRIEF_PW / 8) + pchunk] = regs[it];
-            }
-            __syncwarp();
-        }
-        const float a = ck.a, b = ck.b;
-        const uint8_t* pb = reinterpret_cast<const uint8_t*>(patch) + 18 * BRIEF_PW + 18 + ((ck.x - 18) & 7);  // the keypoint's byte
-        unsigned myWord = 0;  // lane i < 8 ends up holding descriptor word i (words 6, 7 are zero)
+                for (int it = 0; it < 8; ++it) icw[it] = __ldg(plan.icTab + it * 32 + lane);
+                const int r4 = lane >> 3, j = lane & 7;
+                for (int i = warp; i < cnt; i += DSC_THREADS / 32) {
+                    const unsigned xy = sm.xy[i];
+                    const int px = (int)(xy & 0xffffu) - bx0 - 15, py = (int)(xy >> 16) - by0 - 15;  // patch origin in the box
+                    const unsigned sh = (unsigned)(px & 3) * 8u;
+                    const unsigned* p = reinterpret_cast<const unsigned*>(tileT) + (py + r4) * (DSC_BOX_W / 4) + (px >> 2) + j;
+                    int m10 = 0, m01 = 0;
 #pragma unroll
-        for (int wq = 0; wq < 6; ++wq) {
-            // pairs beyond 181 are (0,0)-(0,0): t0 == t1, bit 0 -- like the fork's zero-filled pattern tail
-            const int r0 = cv_round_small(__fadd_rn(__fmul_rn(pr[wq].x, b), __fmul_rn(pr[wq].y, a)));
-            const int c0 = cv_round_small(__fsub_rn(__fmul_rn(pr[wq].x, a), __fmul_rn(pr[wq].y, b)));
-            const int r1 = cv_round_small(__fadd_rn(__fmul_rn(pr[wq].z, b), __fmul_rn(pr[wq].w, a)));
-            const int c1 = cv_round_small(__fsub_rn(__fmul_rn(pr[wq].z, a), __fmul_rn(pr[wq].w, b)));
-            const int t0 = pb[r0 * BRIEF_PW + c0];
-            const int t1 = pb[r1 * BRIEF_PW + c1];
-            const unsigned wbits = __ballot_sync(0xffffffffu, t0 < t1);
-            if (lane == wq) myWord = wbits;
-        }
-        if (lane < 8) reinterpret_cast<unsigned*>(desc + ((size_t)f * cap + ck.o) * 32)[lane] = myWord;
-        if (lane == 8) {
-            const OrbLevel& L = plan.lv[ck.l];
-            orb_keypoint_dev kp;
-            float px = (float)ck.x, py = (float)ck.y;
-            if (ck.l != 0) {  // keypoint.pt *= scale for level != 0 (:486-491)
-                px = __fmul_rn(px, L.scale);
-                py = __fmul_rn(py, L.scale);
+                    for (int it = 0; it < 8; ++it) {  // row 31 (it = 7, r4 = 3) carries zero weights; it is inside the box
+                        const unsigned w = __funnelshift_r(p[0], p[1], sh);
+                        m10 = dp4a_us(w, icw[it].x, m10);
+                        m01 = dp4a_us(w, icw[it].y, m01);
+                        p += 4 * (DSC_BOX_W / 4);
+                    }
+#pragma unroll
+                    for (int sft = 16; sft > 0; sft >>= 1) {
+                        m10 += __shfl_xor_sync(0xffffffffu, m10, sft);
+                        m01 += __shfl_xor_sync(0xffffffffu, m01, sft);
+                    }
+                    if (lane == 0) {
+                        sm.m01[i] = m01;
+                        sm.m10[i] = m10;
+                    }
+                }
             }
-            kp.x = px;
-            kp.y = py;
-            kp.size = (float)L.patchSize;
-            kp.angle = ck.angle;
-            kp.response = (float)ck.response;
-            kp.octave = ck.l;
-            kp.class_id = -1;
-            kps[(size_t)f * cap + ck.o] = kp;
+            __syncthreads();
+            // the blurred tile replaces the raw one while the angles are computed
+            if (tid == 0) {
+                fence_proxy_async();
+                mbar_expect_tx(bar, (unsigned)kDescTileBytes);
+                tma_load_3d(smem_u32(tileT), &maps->blur[s], bx0, by0, f + plan.frameBase, bar);
+            }
+            // ---- phase 2: angle, cos, sin -- one thread per keypoint
+            for (int i = tid; i < cnt; i += DSC_THREADS) {
+                const float angle = fast_atan2_deg((float)sm.m01[i], (float)sm.m10[i]);
+                const float factorPI = (float)(3.141592653589793238462643383279502884 / 180.f);
+                const float rad = __fmul_rn(angle, factorPI);
+                double sd, cd;
+                sincos_0_2pi((double)rad, sd, cd);
+                sm.angle[i] = angle;
+                sm.ca[i] = (float)cd;
+                sm.sb[i] = (float)sd;
+            }
+            __syncthreads();
+            mbar_wait(bar, parity);
+            parity ^= 1u;
+            // ---- phase 3: rBRIEF on the blurred tile + final record
+            {
+                // the 182 test pairs: lane i holds pairs i, i + 32, ... (keypoint independent)
+                float4 pr[6];
+#pragma unroll
+                for (int wq = 0; wq < 6; ++wq)
+                    pr[wq] = (wq * 32 + lane < 182) ? __ldg(plan.pairTab + wq * 32 + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int i = warp; i < cnt; i += DSC_THREADS / 32) {
+                    const unsigned xy = sm.xy[i];
+                    const int x = (int)(xy & 0xffffu), y = (int)(xy >> 16);
+                    const float a = sm.ca[i], b = sm.sb[i];
+                    const unsigned char* pb = tileT + (y - by0) * DSC_BOX_W + (x - bx0);  // the keypoint's byte
+                    unsigned myWord = 0;  // lane i < 8 ends up holding descriptor word i (words 6, 7 are zero)
+#pragma unroll
+                    for (int wq = 0; wq < 6; ++wq) {
+                        // pairs beyond 181 are (0,0)-(0,0): t0 == t1, bit 0 -- like the fork's zero-filled pattern tail
+                        const int r0 = cv_round_small(__fadd_rn(__fmul_rn(pr[wq].x, b), __fmul_rn(pr[wq].y, a)));
+                        const int c0 = cv_round_small(__fsub_rn(__fmul_rn(pr[wq].x, a), __fmul_rn(pr[wq].y, b)));
+                        const int r1 = cv_round_small(__fadd_rn(__fmul_rn(pr[wq].z, b), __fmul_rn(pr[wq].w, a)));
+                        const int c1 = cv_round_small(__fsub_rn(__fmul_rn(pr[wq].z, a), __fmul_rn(pr[wq].w, b)));
+                        const int t0 = pb[r0 * DSC_BOX_W + c0];
+                        const int t1 = pb[r1 * DSC_BOX_W + c1];
+                        const unsigned wbits = __ballot_sync(0xffffffffu, t0 < t1);
+                        if (lane == wq) myWord = wbits;
+                    }
+                    const unsigned lo = sm.lo[i];
+                    const int o = (int)(lo & 0xffffffu), l = (int)(lo >> 24);
+                    if (lane < 8) reinterpret_cast<unsigned*>(desc + ((size_t)f * cap + o) * 32)[lane] = myWord;
+                    if (lane == 8) {
+                        const OrbLevel& L = plan.lv[l];
+                        orb_keypoint_dev kp;
+                        float fx = (float)x, fy = (float)y;
+                        if (l != 0) {  // keypoint.pt *= scale for level != 0 (:486-491)
+                            fx = __fmul_rn(fx, L.scale);
+                            fy = __fmul_rn(fy, L.scale);
+                        }
+                        kp.x = fx;
+                        kp.y = fy;
+                        kp.size = (float)L.patchSize;
+                        kp.angle = sm.angle[i];
+                        kp.response = (float)sm.resp[i];
+                        kp.octave = l;
+                        kp.class_id = -1;
+                        kps[(size_t)f * cap + o] = kp;
+                    }
+                }
+            }
         }
-    }  // keypoint loop
+        if (!sliced) break;
+        // next slice
+        {
+            const int l = sm.levels[sl];
+            const int nK = min(__shfl_sync(0xffffffffu, myK, l), plan.lv[l].kmax);
+            sr0 += DSC_LIST;
+            if (sr0 >= nK) {
+                sr0 = 0;
+                ++sl;
+            }
+        }
+        if (sl >= nLv) break;
+        __syncthreads();  // phase 3 of every warp is done with the tile and the list
+        if (tid == 0) sm.count = 0;
+        __syncthreads();
+    }
 }
 
 // The 182 live rBRIEF test pairs as float4 (x0, y0, x1, y1) for plan.pairTab.
@@ -1339,24 +1394,29 @@ void orbk_build_pair_table(float4* out) {
         out[i] = make_float4((float)pairs[4 * i], (float)pairs[4 * i + 1], (float)pairs[4 * i + 2], (float)pairs[4 * i + 3]);
 }
 
-// Host-side construction of the IC_Angle weight table (4 x 31 x 9 int2).
+// Host-side construction of the IC_Angle weight table: entry [it][lane] for patch row vr = it * 4 + lane / 8 and
+// canonical word j = lane % 8 (patch columns u = 4j - 15 .. 4j - 12): .x = four signed bytes u, .y = four signed
+// bytes v = vr - 15, both 0 outside the disc |u| <= umax[|v|] (ORBextractor.cc:155-169) and on the padding row 31.
+// m10 += dp4a(pixels, .x); m01 += dp4a(pixels, .y).
 void orbk_build_ic_table(int2* out) {
     static const int umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
-    for (int a = 0; a < 4; ++a)
-        for (int vr = 0; vr < 31; ++vr)
-            for (int k = 0; k < 9; ++k) {
+    for (int it = 0; it < 8; ++it)
+        for (int lane = 0; lane < 32; ++lane) {
+            const int vr = it * 4 + lane / 8, j = lane % 8;
+            unsigned wu = 0, wm = 0;
+            if (vr < 31) {
                 const int v = vr - 15, av = v < 0 ? -v : v;
-                unsigned wu = 0, wm = 0;
                 for (int b = 0; b < 4; ++b) {
-                    const int u = 4 * k + b - a - 15;
+                    const int u = 4 * j + b - 15;
                     const int au = u < 0 ? -u : u;
                     if (au <= umax[av]) {
                         wu |= (unsigned)(u & 0xff) << (8 * b);
                         wm |= (unsigned)(v & 0xff) << (8 * b);
                     }
                 }
-                out[(a * 31 + vr) * 9 + k] = make_int2((int)wu, (int)wm);
             }
+            out[it * 32 + lane] = make_int2((int)wu, (int)wm);
+        }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1459,7 +1519,7 @@ cudaError_t orbk_repitch(const uint8_t* dense, int nframes, int rows, int cols, 
 // launchers
 // ------------------------------------------------------------------------------------------
 cudaError_t orbk_encode_level_map(CUtensorMap* out, const uint8_t* base, int cols, int rows, int frames, int pitch,
-                                  unsigned long long plane, int boxH) {
+                                  unsigned long long plane, int boxW, int boxH) {
     typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -1475,7 +1535,7 @@ cudaError_t orbk_encode_level_map(CUtensorMap* out, const uint8_t* base, int col
     if (((uintptr_t)base & 15) || (pitch & 15) || (plane & 15)) return cudaErrorMisalignedAddress;
     cuuint64_t gdim[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)(frames > 0 ? frames : 1)};
     cuuint64_t gstr[2] = {(cuuint64_t)pitch, (cuuint64_t)plane};
-    cuuint32_t box[3] = {(cuuint32_t)DET_TILE_W, (cuuint32_t)boxH, 1u};
+    cuuint32_t box[3] = {(cuuint32_t)boxW, (cuuint32_t)boxH, 1u};
     cuuint32_t estr[3] = {1u, 1u, 1u};
     CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1491,13 +1551,15 @@ static const size_t kOctFastSmem = sizeof(OctFastSmem);
 cudaError_t orbk_init_device() {
     cudaError_t e = cudaFuncSetAttribute(k_detect, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)detect_smem_bytes(DET_TILE_H));
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_describe_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDescSmem);
+    if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_octree_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kOctFastSmem);
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kOctreeSmem);
 }
 
 cudaError_t orbk_run_extract(const OrbPlan& plan, int nframes, orb_keypoint_dev* d_kps, uint8_t* d_desc, int cap,
-                             int* d_counts, const OrbStreams& ss, const CUtensorMap* d_maps, cudaEvent_t* ev) {
+                             int* d_counts, const OrbStreams& ss, const DetectMaps* d_maps, cudaEvent_t* ev) {
     // with per-stage events requested everything runs on one stream, so that every stage's
     // event-timed duration is its own (no overlap); otherwise the blur overlaps detect + octree
     cudaStream_t st = ss.st, st2 = ss.st2;
@@ -1540,7 +1602,7 @@ cudaError_t orbk_run_extract(const OrbPlan& plan, int nframes, orb_keypoint_dev*
         if (e != cudaSuccess) return e;
     }
     if (plan.totalTiles > 0) {
-        k_detect<<<dim3(plan.totalTiles, nframes), DET_THREADS, detect_smem_bytes(plan.detRows), st>>>(plan, d_maps);
+        k_detect<<<dim3(plan.totalTiles, nframes), DET_THREADS, detect_smem_bytes(plan.detRows), st>>>(plan, d_maps->m);
         ++g_launches;
     }
     if (ev) cudaEventRecord(ev[2], st);
@@ -1556,20 +1618,13 @@ cudaError_t orbk_run_extract(const OrbPlan& plan, int nframes, orb_keypoint_dev*
         cudaEventRecord(ev[7], st);
     }
     if (ev) cudaEventRecord(ev[4], st);
-    {
-        // warps stride over the keypoints: about four waves of 8-warp CTAs, split evenly over the frames
-        int ctasPerFrame = (148 * 8 * 4 + nframes - 1) / nframes;
-        ctasPerFrame = std::max(1, std::min(ctasPerFrame, (plan.totalKmax + 7) / 8));
-        // orientation reads the raw levels only: it does not wait for the blur
-        k_orient<<<dim3(ctasPerFrame, nframes), 256, 0, st>>>(plan, d_kps, cap, d_counts);
-        k_angle<<<dim3(std::max(1, std::min(8, (plan.totalKmax + 255) / 256)), nframes), 256, 0, st>>>(plan, d_kps, cap);
-        if (!ev) {
-            e = cudaStreamWaitEvent(st, ss.join, 0);
-            if (e != cudaSuccess) return e;
-        }
-        k_brief<<<dim3(ctasPerFrame, nframes), 256, 0, st>>>(plan, d_kps, d_desc, cap);
-        g_launches += 3;
+    // describe: one CTA per tile of keypoint positions; needs the kept lists (this stream) and the blurred levels
+    if (!ev) {
+        e = cudaStreamWaitEvent(st, ss.join, 0);
+        if (e != cudaSuccess) return e;
     }
+    k_describe_tile<<<dim3(std::max(1, plan.totalDescTiles), nframes), DSC_THREADS, kDescSmem, st>>>(plan, d_maps, d_kps, d_desc, cap, d_counts);
+    ++g_launches;
     if (ev) cudaEventRecord(ev[5], st);
     return cudaGetLastError();
 }

@@ -25,20 +25,22 @@ cudaError_t orbk_init_device();
 // TMA descriptors of the level images (x, y, frame) for k_detect's tile staging: encoded on the
 // host by orbk_encode_level_map, copied to device global memory, read by the TMA unit from there.
 struct DetectMaps {
-    CUtensorMap m[ORB_MAX_LEVELS];
+    CUtensorMap m[ORB_MAX_LEVELS];     // raw level, 256 x boxH box (k_detect)
+    CUtensorMap raw[ORB_MAX_LEVELS];   // raw level, DSC_BOX_W x DSC_BOX_H box (k_describe_tile: IC_Angle)
+    CUtensorMap blur[ORB_MAX_LEVELS];  // blurred level, same box (k_describe_tile: rBRIEF)
 };
-// Encodes the (cols x rows x frames) uint8 tensor of one level with a 256 x boxH x 1 box.
+// Encodes the (cols x rows x frames) uint8 tensor of one level with a boxW x boxH x 1 box.
 // Returns cudaSuccess or an error (the driver entry point is looked up at run time).
 cudaError_t orbk_encode_level_map(CUtensorMap* out, const uint8_t* base, int cols, int rows, int frames, int pitch,
-                                  unsigned long long plane, int boxH);
+                                  unsigned long long plane, int boxW, int boxH);
 
 struct OrbStreams {
     cudaStream_t st, st2;
     cudaEvent_t fork, join;
 };
 cudaError_t orbk_run_extract(const OrbPlan& plan, int nframes, orb_keypoint_dev* d_kps, uint8_t* d_desc, int cap,
-                             int* d_counts, const OrbStreams& ss, const CUtensorMap* d_maps, cudaEvent_t* ev = nullptr);
-void orbk_build_ic_table(int2* out /* 4*31*9 */);
+                             int* d_counts, const OrbStreams& ss, const DetectMaps* d_maps, cudaEvent_t* ev = nullptr);
+void orbk_build_ic_table(int2* out /* 8*32 */);
 void orbk_build_pair_table(float4* out /* 182 */);
 // Dense frames (row stride == cols) in `dense` -> pitched level-0 layout.
 cudaError_t orbk_repitch(const uint8_t* dense, int nframes, int rows, int cols, uint8_t* dst, int pitch, unsigned long long plane,

@@ -165,8 +165,8 @@ struct orb_extractor {
     OrbPlan plan;            // current shape (plan.rows == 0: none)
     DetectMaps maps;         // TMA descriptors of the internal level buffers (host copy)
     DetectMaps maps_user;    // same with level 0 pointing at the caller's device frames
-    CUtensorMap* d_maps = nullptr;       // device copies (global memory), ORB_MAX_LEVELS each
-    CUtensorMap* d_maps_user = nullptr;
+    DetectMaps* d_maps = nullptr;        // device copies (global memory)
+    DetectMaps* d_maps_user = nullptr;
     const uint8_t* user_base = nullptr;
     std::vector<void*> allocs;  // everything the plan points at
     uint8_t* level0 = nullptr;  // internal level-0 buffer (host-input path)
@@ -296,7 +296,7 @@ static int build_plan(orb_extractor* h, int rows, int cols) {
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     free_plan(h);
     const int B = h->max_batch;
-    int tileBase = 0, keptBase = 0;
+    int tileBase = 0, keptBase = 0, descTileBase = 0;
     for (int l = 0; l < P.nlevels; ++l) {
         OrbLevel& L = P.lv[l];
         L.keptBase = keptBase;
@@ -309,6 +309,13 @@ static int build_plan(orb_extractor* h, int rows, int cols) {
         }
         L.tileBase = tileBase;
         tileBase += L.nTiles;
+        // describe tiles over the keypoint area [19, cols - 19) x [19, rows - 19)
+        if (L.cols > 2 * ORB_EDGE && L.rows > 2 * ORB_EDGE) {
+            L.dTilesX = (L.cols - 2 * ORB_EDGE + DSC_W - 1) / DSC_W;
+            L.dTiles = L.dTilesX * ((L.rows - 2 * ORB_EDGE + DSC_H - 1) / DSC_H);
+        }
+        L.dTileBase = descTileBase;
+        descTileBase += L.dTiles;
         CUDA_TRY(dev_alloc(h, &L.img, (size_t)B * L.plane + 256));
         CUDA_TRY(dev_alloc(h, &L.blur, (size_t)B * L.plane + 256));
         CUDA_TRY(dev_alloc(h, &L.cand, (size_t)B * L.candCap));
@@ -386,6 +393,7 @@ static int build_plan(orb_extractor* h, int rows, int cols) {
         L.kmax = std::min<int>(L.kmax, (int)S.candCap);
     }
     P.totalTiles = tileBase;
+    P.totalDescTiles = descTileBase;
     P.detRows = 8;  // k_detect sizes its shared memory by the tallest tile
     for (int l = 0; l < P.nlevels; ++l)
         if (P.lv[l].src == l && P.lv[l].nTiles > 0) P.detRows = std::max(P.detRows, P.lv[l].boxH);
@@ -395,7 +403,7 @@ static int build_plan(orb_extractor* h, int rows, int cols) {
     CUDA_TRY(dev_alloc(h, &P.keptCount, (size_t)B * ORB_MAX_LEVELS));
     CUDA_TRY(dev_alloc(h, &P.status, (size_t)B));
     {
-        std::vector<int2> ic(4 * 31 * 9);
+        std::vector<int2> ic(8 * 32);
         orbk_build_ic_table(ic.data());
         int2* d_ic;
         CUDA_TRY(dev_alloc(h, &d_ic, ic.size()));
@@ -415,13 +423,17 @@ static int build_plan(orb_extractor* h, int rows, int cols) {
     memset(&h->maps, 0, sizeof h->maps);
     for (int l = 0; l < P.nlevels; ++l) {
         const OrbLevel& L = P.lv[l];
-        if (L.src != l || L.nTiles == 0) continue;
-        CUDA_TRY(orbk_encode_level_map(&h->maps.m[l], L.img, L.cols, L.rows, B, L.pitch, L.plane, L.boxH));
+        if (L.src != l) continue;
+        if (L.nTiles > 0) CUDA_TRY(orbk_encode_level_map(&h->maps.m[l], L.img, L.cols, L.rows, B, L.pitch, L.plane, DET_TILE_W, L.boxH));
+        if (L.dTiles > 0) {
+            CUDA_TRY(orbk_encode_level_map(&h->maps.raw[l], L.img, L.cols, L.rows, B, L.pitch, L.plane, DSC_BOX_W, DSC_BOX_H));
+            CUDA_TRY(orbk_encode_level_map(&h->maps.blur[l], L.blur, L.cols, L.rows, B, L.pitch, L.plane, DSC_BOX_W, DSC_BOX_H));
+        }
     }
     h->maps_user = h->maps;
     h->user_base = nullptr;
-    CUDA_TRY(dev_alloc(h, &h->d_maps, (size_t)ORB_MAX_LEVELS));
-    CUDA_TRY(dev_alloc(h, &h->d_maps_user, (size_t)ORB_MAX_LEVELS));
+    CUDA_TRY(dev_alloc(h, &h->d_maps, (size_t)1));
+    CUDA_TRY(dev_alloc(h, &h->d_maps_user, (size_t)1));
     CUDA_TRY(cudaMemcpy(h->d_maps, &h->maps, sizeof(DetectMaps), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(h->d_maps_user, &h->maps, sizeof(DetectMaps), cudaMemcpyHostToDevice));
     h->level0 = P.lv[0].img;
@@ -615,7 +627,7 @@ static int extract_device_impl(orb_extractor* h, int n, const uint8_t* d_imgs, i
     int rc = build_plan(h, rows, cols);
     if (rc != ORB_OK) return rc;
     OrbPlan P = h->plan;
-    const CUtensorMap* maps = h->d_maps;
+    const DetectMaps* maps = h->d_maps;
     if (ingest) {
         const orb_extractor::Ingest& I = h->ing;
         if (stride < (size_t)I.scols * I.channels) return fail(ORB_ERR_INVALID, "stride < src_cols * channels");
@@ -626,11 +638,15 @@ static int extract_device_impl(orb_extractor* h, int n, const uint8_t* d_imgs, i
         // same layout as the internal level-0 buffer: read the caller's frames in place
         for (int l = 0; l < P.nlevels; ++l)
             if (P.lv[l].src == 0) P.lv[l].img = const_cast<uint8_t*>(d_imgs);
-        if (h->user_base != d_imgs && P.lv[0].nTiles > 0) {
-            CUDA_TRY(orbk_encode_level_map(&h->maps_user.m[0], d_imgs, P.lv[0].cols, P.lv[0].rows, n, P.lv[0].pitch, P.lv[0].plane,
-                                           P.lv[0].boxH));
+        if (h->user_base != d_imgs && (P.lv[0].nTiles > 0 || P.lv[0].dTiles > 0)) {
+            const OrbLevel& L0 = P.lv[0];
+            if (L0.nTiles > 0)
+                CUDA_TRY(orbk_encode_level_map(&h->maps_user.m[0], d_imgs, L0.cols, L0.rows, n, L0.pitch, L0.plane, DET_TILE_W, L0.boxH));
+            if (L0.dTiles > 0)
+                CUDA_TRY(orbk_encode_level_map(&h->maps_user.raw[0], d_imgs, L0.cols, L0.rows, n, L0.pitch, L0.plane, DSC_BOX_W, DSC_BOX_H));
             // stream-ordered update of the device copy (pageable source: staged before the call returns)
-            CUDA_TRY(cudaMemcpyAsync(h->d_maps_user, &h->maps_user, sizeof(CUtensorMap), cudaMemcpyHostToDevice, h->stream));
+            CUDA_TRY(cudaMemcpyAsync(&h->d_maps_user->m[0], &h->maps_user.m[0], sizeof(CUtensorMap), cudaMemcpyHostToDevice, h->stream));
+            CUDA_TRY(cudaMemcpyAsync(&h->d_maps_user->raw[0], &h->maps_user.raw[0], sizeof(CUtensorMap), cudaMemcpyHostToDevice, h->stream));
             h->user_base = d_imgs;
         }
         maps = h->d_maps_user;

@@ -19,6 +19,20 @@
 #define DET_SP 272           // smem pitch of the image tile (bytes)
 #define DET_THREADS 256
 
+// describe tile: keypoints whose level position lies in a DSC_W x DSC_H core; the raw and the blurred level are
+// staged with an 18-px halo (the rBRIEF pattern reaches 18 px after rotation, IC_Angle 15) by one TMA box each,
+// one after the other into the same shared-memory buffer.
+// Keypoints sit at x, y >= 19, so the box of tile (tx, ty) starts at level pixel (DSC_W * tx, 1 + DSC_H * ty):
+// 16-byte aligned for the TMA unit without any slack.  The 224-byte box pitch (56 words) puts four consecutive
+// tile rows into four disjoint 8-bank groups, which makes the IC_Angle loads conflict-free.
+#define DSC_W 160
+#define DSC_H 96
+#define DSC_HALO 18
+#define DSC_BOX_W 224
+#define DSC_BOX_H (DSC_H + 2 * DSC_HALO)
+#define DSC_THREADS 256
+#define DSC_LIST 256         // keypoints of one tile handled per round
+
 struct OrbLevel {
     // image
     int rows, cols;
@@ -41,6 +55,7 @@ struct OrbLevel {
     int boxH;                // rows of the TMA box that stages one detect tile (hCell + 6)
     int tileBase;            // first tile id of this level in the detect launch (src == self)
     int nTiles;
+    int dTilesX, dTiles, dTileBase;  // describe tiles of this level's pixels (src == self)
     // octree
     int nIni;
     float hX;
@@ -65,11 +80,12 @@ struct OrbPlan {
     int totalTiles;          // detect tiles per frame
     int detRows;             // tallest detect tile (max boxH over the levels), sizes k_detect's shared memory
     int totalKmax;           // sum of kmax
+    int totalDescTiles;      // describe tiles per frame
     int* candCount;          // [batch][ORB_MAX_LEVELS]
     int* keptCount;          // [batch][ORB_MAX_LEVELS]
     int* status;             // [batch] octree status flags (non-zero: unseparable keys)
     int* needGeneric;        // [batch][ORB_MAX_LEVELS] problems the table-based octree handed over
-    const int2* icTab;       // [4][31][9] IC_Angle dp4a weights (k_describe)
+    const int2* icTab;       // [8][32] IC_Angle dp4a weights: step it, lane (row it*4 + lane/8, word lane%8)
     const float4* pairTab;   // [182] rBRIEF test pairs (x0, y0, x1, y1)
     OrbLevel lv[ORB_MAX_LEVELS];
 };
