@@ -1170,7 +1170,9 @@ struct DescTileSmem {
     unsigned lo[DSC_LIST];        // level << 24 | output index
     int m01[DSC_LIST], m10[DSC_LIST];
     float angle[DSC_LIST], ca[DSC_LIST], sb[DSC_LIST];
-    int levels[ORB_MAX_LEVELS];   // levels whose keypoints live on this source's pixels
+    int levels[ORB_MAX_LEVELS];   // levels whose keypoints live on this source's pixels,
+    int lvCount[ORB_MAX_LEVELS];  // their kept counts
+    int lvBase[ORB_MAX_LEVELS];   // and the output index of their first keypoint
     int nLevels;
     int count;
     unsigned long long bar;
@@ -1178,6 +1180,13 @@ struct DescTileSmem {
 static const size_t kDescTileBytes = (size_t)DSC_BOX_W * DSC_BOX_H;
 static const size_t kDescSmem = kDescTileBytes + sizeof(DescTileSmem);
 
+__device__ __forceinline__ unsigned lds_u8(unsigned addr) {
+    unsigned v;
+    // not volatile, no clobber: the address always depends on shared-memory values read after the barrier that
+    // publishes the tile, so the load cannot move above it, and the compiler stays free to batch the gathers
+    asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 __global__ void __launch_bounds__(DSC_THREADS, 4) k_describe_tile(const __grid_constant__ OrbPlan plan, const DetectMaps* __restrict__ maps,
@@ -1205,24 +1214,33 @@ __global__ void __launch_bounds__(DSC_THREADS, 4) k_describe_tile(const __grid_c
     const int bx0 = DSC_W * tx, by0 = 1 + DSC_H * ty;            // level pixel of box byte (0, 0)
     const unsigned xlo = ORB_EDGE + DSC_W * tx, ylo = ORB_EDGE + DSC_H * ty;  // core: [xlo, xlo + DSC_W) x [ylo, ylo + DSC_H)
 
-    // ---- output offsets of the levels (levels are concatenated 0..n-1, ORBextractor.cc:466-494) and the levels on this source
-    int myK, total;
-    const int pre = level_prefix(kc, plan.nlevels, lane, cap, myK, total);
-    int nOnSrc = 0;  // keypoints of all levels that live on this source
-    for (int l = s; l < plan.nlevels; ++l)
-        if (plan.lv[l].src == s) nOnSrc += __shfl_sync(0xffffffffu, myK, l);
-    if (nOnSrc == 0) return;  // uniform over the CTA: nothing was issued yet
+    // ---- warp 0: output offsets of the levels (levels are concatenated 0..n-1, ORBextractor.cc:466-494), the levels
+    // that live on this source's pixels, their keypoint counts
     const unsigned bar = smem_u32(&sm.bar);
-    if (tid == 0) {
-        mbar_init(bar, 1);
-        int n = 0;
-        for (int l = s; l < plan.nlevels; ++l)
-            if (plan.lv[l].src == s) sm.levels[n++] = l;
-        sm.nLevels = n;
-        sm.count = 0;
+    if (warp == 0) {
+        int myK, total;
+        const int pre = level_prefix(kc, plan.nlevels, lane, cap, myK, total);
+        const bool mine = lane < plan.nlevels && plan.lv[lane].src == s;
+        const unsigned onSrc = __ballot_sync(0xffffffffu, mine);
+        if (mine) {
+            const int slot = __popc(onSrc & ((1u << lane) - 1u));
+            sm.levels[slot] = lane;
+            sm.lvCount[slot] = min(myK, plan.lv[lane].kmax);
+            sm.lvBase[slot] = pre;
+        }
+        if (lane == 0) {
+            sm.nLevels = __popc(onSrc);
+            sm.count = 0;
+            mbar_init(bar, 1);
+        }
     }
     __syncthreads();
     const int nLv = sm.nLevels;
+    {
+        int nOnSrc = 0;
+        for (int j = 0; j < nLv; ++j) nOnSrc += sm.lvCount[j];
+        if (nOnSrc == 0) return;  // uniform over the CTA: nothing was issued yet
+    }
     unsigned parity = 0;  // phase of the mbarrier the next TMA load completes
     bool sliced = false;
     int sl = 0, sr0 = 0;  // sliced mode: level slot and first rank of the current slice
@@ -1237,8 +1255,8 @@ __global__ void __launch_bounds__(DSC_THREADS, 4) k_describe_tile(const __grid_c
         for (int j = sliced ? sl : 0; j < (sliced ? sl + 1 : nLv); ++j) {
             const int l = sm.levels[j];
             const OrbLevel& L = plan.lv[l];
-            const int nK = min(__shfl_sync(0xffffffffu, myK, l), L.kmax);
-            const int base = __shfl_sync(0xffffffffu, pre, l);
+            const int nK = sm.lvCount[j];
+            const int base = sm.lvBase[j];
             const uint2* kept = L.kept + (size_t)f * L.kmax;
             const int r1 = sliced ? min(nK, sr0 + DSC_LIST) : nK;
             for (int r = (sliced ? sr0 : 0) + tid; r < r1; r += DSC_THREADS) {
@@ -1330,17 +1348,20 @@ __global__ void __launch_bounds__(DSC_THREADS, 4) k_describe_tile(const __grid_c
                     const unsigned xy = sm.xy[i];
                     const int x = (int)(xy & 0xffffu), y = (int)(xy >> 16);
                     const float a = sm.ca[i], b = sm.sb[i];
-                    const unsigned char* pb = tileT + (y - by0) * DSC_BOX_W + (x - bx0);  // the keypoint's byte
+                    // cvRound by the 1.5 * 2^23 trick (cv_round_small) with the constant's integer image folded into the
+                    // base address: byte (r, c) of the patch = pb[R * DSC_BOX_W + C], R = float_as_int(r + magic) etc.
+                    // (32-bit shared-window addresses, wrap-around arithmetic)
+                    const unsigned pb = smem_u32(tileT) + (unsigned)((y - by0) * DSC_BOX_W + (x - bx0)) - 0x4B400000u * (unsigned)(DSC_BOX_W + 1);
                     unsigned myWord = 0;  // lane i < 8 ends up holding descriptor word i (words 6, 7 are zero)
 #pragma unroll
                     for (int wq = 0; wq < 6; ++wq) {
                         // pairs beyond 181 are (0,0)-(0,0): t0 == t1, bit 0 -- like the fork's zero-filled pattern tail
-                        const int r0 = cv_round_small(__fadd_rn(__fmul_rn(pr[wq].x, b), __fmul_rn(pr[wq].y, a)));
-                        const int c0 = cv_round_small(__fsub_rn(__fmul_rn(pr[wq].x, a), __fmul_rn(pr[wq].y, b)));
-                        const int r1 = cv_round_small(__fadd_rn(__fmul_rn(pr[wq].z, b), __fmul_rn(pr[wq].w, a)));
-                        const int c1 = cv_round_small(__fsub_rn(__fmul_rn(pr[wq].z, a), __fmul_rn(pr[wq].w, b)));
-                        const int t0 = pb[r0 * DSC_BOX_W + c0];
-                        const int t1 = pb[r1 * DSC_BOX_W + c1];
+                        const unsigned r0 = (unsigned)__float_as_int(__fadd_rn(__fadd_rn(__fmul_rn(pr[wq].x, b), __fmul_rn(pr[wq].y, a)), 12582912.f));
+                        const unsigned c0 = (unsigned)__float_as_int(__fadd_rn(__fsub_rn(__fmul_rn(pr[wq].x, a), __fmul_rn(pr[wq].y, b)), 12582912.f));
+                        const unsigned r1 = (unsigned)__float_as_int(__fadd_rn(__fadd_rn(__fmul_rn(pr[wq].z, b), __fmul_rn(pr[wq].w, a)), 12582912.f));
+                        const unsigned c1 = (unsigned)__float_as_int(__fadd_rn(__fsub_rn(__fmul_rn(pr[wq].z, a), __fmul_rn(pr[wq].w, b)), 12582912.f));
+                        const unsigned t0 = lds_u8(pb + r0 * DSC_BOX_W + c0);
+                        const unsigned t1 = lds_u8(pb + r1 * DSC_BOX_W + c1);
                         const unsigned wbits = __ballot_sync(0xffffffffu, t0 < t1);
                         if (lane == wq) myWord = wbits;
                     }
@@ -1349,14 +1370,10 @@ __global__ void __launch_bounds__(DSC_THREADS, 4) k_describe_tile(const __grid_c
                     if (lane < 8) reinterpret_cast<unsigned*>(desc + ((size_t)f * cap + o) * 32)[lane] = myWord;
                     if (lane == 8) {
                         const OrbLevel& L = plan.lv[l];
+                        const float sc = l != 0 ? L.scale : 1.0f;  // keypoint.pt *= scale for level != 0 (:486-491)
                         orb_keypoint_dev kp;
-                        float fx = (float)x, fy = (float)y;
-                        if (l != 0) {  // keypoint.pt *= scale for level != 0 (:486-491)
-                            fx = __fmul_rn(fx, L.scale);
-                            fy = __fmul_rn(fy, L.scale);
-                        }
-                        kp.x = fx;
-                        kp.y = fy;
+                        kp.x = __fmul_rn((float)x, sc);
+                        kp.y = __fmul_rn((float)y, sc);
                         kp.size = (float)L.patchSize;
                         kp.angle = sm.angle[i];
                         kp.response = (float)sm.resp[i];
@@ -1370,8 +1387,7 @@ __global__ void __launch_bounds__(DSC_THREADS, 4) k_describe_tile(const __grid_c
         if (!sliced) break;
         // next slice
         {
-            const int l = sm.levels[sl];
-            const int nK = min(__shfl_sync(0xffffffffu, myK, l), plan.lv[l].kmax);
+            const int nK = sm.lvCount[sl];
             sr0 += DSC_LIST;
             if (sr0 >= nK) {
                 sr0 = 0;
