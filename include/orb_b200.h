@@ -97,10 +97,11 @@ int orb_extract_batch(orb_extractor* h, int n, const uint8_t* imgs, int rows, in
 
 /* Asynchronous form of orb_extract_batch for throughput serving: submit enqueues the copies and
  * kernels of one batch and returns a ticket; wait blocks until that batch's keypoints, descriptors
- * and counts are in the caller's buffers.  Up to two batches may be in flight per handle: the H2D
+ * and counts are in the caller's buffers.  Up to three batches may be in flight per handle (ORB_MAX_IN_FLIGHT): the H2D
  * copies of batch i+1 run while batch i computes and the D2H copies of batch i run while batch
  * i+1 computes.  The buffers must stay valid (and the inputs unchanged) until wait returns.
  * orb_extract_batch == submit + wait. */
+#define ORB_MAX_IN_FLIGHT 3
 int orb_extract_batch_submit(orb_extractor* h, int n, const uint8_t* imgs, int rows, int cols,
                              size_t stride, size_t frame_stride, orb_keypoint* kps, uint8_t* desc,
                              int cap, int* counts, int* ticket);

@@ -137,11 +137,15 @@ __global__ void __launch_bounds__(256) k_resize4(const uint8_t* __restrict__ src
 #define DET_WLIST_PER_WARP 512  // >= ceil(59/4) rows x 32 words handled by one warp in pass B
 
 // Dynamic shared memory of k_detect, sized by the plan's tallest tile (plan.detRows = max boxH):
-//   img   (detRows + 1) x 256 B   image tile, dense 256-byte rows (the TMA box) + one slack row; after pass A the
-//                                 same memory holds F, the NMS survivors (4 candidate columns per word)
-//   sc    (detRows - 4) x DET_SP  score tile with a one-word / one-row zero border; later the survivor list
-//                                 (u | r<<8 | cx<<16 | cell<<24)
+//   E, O  2 x detRows x DET_EP words: the image tile expanded to one pixel per 16-bit lane, twice: word i of a row of
+//         E holds pixels (2i, 2i + 1), of O pixels (2i + 1, 2i + 2), so the pixel pair starting at ANY column is one
+//         aligned word and pass A gathers its ring with plain loads (no byte permutes on the ALU pipe).  After pass A
+//         the E rows hold F, the NMS survivors (4 candidate columns per word)
+//   sc    first the TMA landing buffer (dense 256-byte rows, the box), then (detRows - 4) x DET_SP score tile with a
+//         one-word / one-row zero border; later the survivor list (u | r<<8 | cx<<16 | cell<<24)
 //   tail  DetectTail
+#define DET_EP 136   // words per E / O row: 4 words of left padding (ring columns left of the tile), 128 pixel pairs, 4 right
+#define DET_EPAD 4
 struct DetectTail {
     unsigned short wlist[(DET_THREADS / 32) * DET_WLIST_PER_WARP];  // per warp: (row << 6 | word) of its non-zero F words
     int wcount[DET_THREADS / 32];
@@ -155,10 +159,12 @@ struct DetectTail {
     unsigned long long bar;                    // mbarrier the TMA load completes on
 };
 
-__host__ __device__ inline size_t det_img_bytes(int detRows) { return (size_t)(detRows + 1) * DET_TILE_W; }
+// (rounded to 128 bytes: the TMA landing buffer follows)
+__host__ __device__ inline size_t det_img_bytes(int detRows) { return ((size_t)2 * detRows * DET_EP * 4 + 127) & ~(size_t)127; }
 __host__ __device__ inline size_t det_sc_bytes(int detRows) {
-    const size_t a = (size_t)(detRows - 4) * DET_SP, b = (size_t)DET_MAX_SURV * 4;
-    return ((a > b ? a : b) + 15) & ~(size_t)15;
+    const size_t a = (size_t)(detRows - 4) * DET_SP, b = (size_t)DET_MAX_SURV * 4, c = (size_t)detRows * DET_TILE_W + 16;
+    const size_t m = a > b ? (a > c ? a : c) : (b > c ? b : c);
+    return (m + 15) & ~(size_t)15;
 }
 static size_t detect_smem_bytes(int detRows) {
     return det_img_bytes(detRows) + det_sc_bytes(detRows) + sizeof(DetectTail);
@@ -189,18 +195,29 @@ __device__ __forceinline__ void tma_load_3d(unsigned dst, const CUtensorMap* map
                  ::"r"(dst), "l"((unsigned long long)map), "r"(x), "r"(y), "r"(z), "r"(bar) : "memory");
 }
 
+// Minimum and maximum of two packed lanes on the FMA pipe.  A lane holding a pixel value 0..255 in 16 bits is, read as
+// binary16, the subnormal p * 2^-24; sums and differences of such values are exact (|result| < 2^10 ulps), the clamp of
+// sub.sat is max(a - b, 0) because everything is far below 1.0, and no .ftz is applied to f16 arithmetic.  So
+//   d = max(a - b, 0);  hi = b + d = max(a, b);  lo = a - d = min(a, b)
+// are three HADD2 that produce exactly the bit patterns VIMNMX.U16x2 would -- on the pipe k_detect leaves idle.
+__device__ __forceinline__ void minmax_fma(unsigned a, unsigned b, unsigned& lo, unsigned& hi) {
+    unsigned d;
+    asm("sub.sat.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    asm("add.f16x2 %0, %1, %2;" : "=r"(hi) : "r"(b), "r"(d));
+    asm("sub.f16x2 %0, %1, %2;" : "=r"(lo) : "r"(a), "r"(d));
+}
+
 __device__ __forceinline__ void fast_score_pairs(const unsigned (&r)[16], unsigned c2, unsigned low2,
                                                  unsigned neglow2, unsigned& u) {
     // A = min over the 16 arcs of 9 contiguous ring pixels of the arc's maximum, B = max over arcs of the arc's
     // minimum.  The arcs starting at k and k + 1 (k even) share the 8 pixels W = r[k+1 .. k+8]:
     //   min(max(r[k], W), max(W, r[k+9])) = max(W, min(r[k], r[k+9])),   W = max(M4[k+1], M4[k+5]),
-    // with M4[j] = max(r[j .. j+3]) built from pair maxima at the odd positions.  36 min/max per polarity.
+    // with M4[j] = max(r[j .. j+3]) built from pair maxima at the odd positions.  36 min/max per polarity; the 16
+    // (min, max) pairs of two ring pixels run on the FMA pipe (minmax_fma), the rest on the ALU pipe.
     unsigned M2[8], m2[8], M4[8], m4[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {  // odd position j = 2i + 1
-        M2[i] = __vmaxu2(r[2 * i + 1], r[(2 * i + 2) & 15]);
-        m2[i] = __vminu2(r[2 * i + 1], r[(2 * i + 2) & 15]);
-    }
+    for (int i = 0; i < 8; ++i)  // odd position j = 2i + 1
+        minmax_fma(r[2 * i + 1], r[(2 * i + 2) & 15], m2[i], M2[i]);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         M4[i] = __vmaxu2(M2[i], M2[(i + 1) & 7]);
@@ -209,8 +226,8 @@ __device__ __forceinline__ void fast_score_pairs(const unsigned (&r)[16], unsign
     unsigned tA[8], tB[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {  // even position k = 2i: W = M4[k+1] u M4[k+5] = M4 index i and i + 2
-        const unsigned mn = __vminu2(r[2 * i], r[(2 * i + 9) & 15]);
-        const unsigned mx = __vmaxu2(r[2 * i], r[(2 * i + 9) & 15]);
+        unsigned mn, mx;
+        minmax_fma(r[2 * i], r[(2 * i + 9) & 15], mn, mx);
         tA[i] = vmax3(M4[i], M4[(i + 2) & 7], mn);
         tB[i] = vmin3(m4[i], m4[(i + 2) & 7], mx);
     }
@@ -231,7 +248,8 @@ __global__ void __launch_bounds__(DET_THREADS) k_detect(const __grid_constant__ 
                                                         const CUtensorMap* __restrict__ maps) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int detRows = plan.detRows;
-    unsigned (*img)[DET_TILE_W / 4] = reinterpret_cast<unsigned (*)[DET_TILE_W / 4]>(smem_raw);
+    unsigned (*E)[DET_EP] = reinterpret_cast<unsigned (*)[DET_EP]>(smem_raw);
+    unsigned (*O)[DET_EP] = E + detRows;
     unsigned (*sc)[DET_SP / 4] = reinterpret_cast<unsigned (*)[DET_SP / 4]>(smem_raw + det_img_bytes(detRows));
     unsigned* surv = reinterpret_cast<unsigned*>(sc);
     DetectTail& sm = *reinterpret_cast<DetectTail*>(smem_raw + det_img_bytes(detRows) + det_sc_bytes(detRows));
@@ -260,28 +278,21 @@ __global__ void __launch_bounds__(DET_THREADS) k_detect(const __grid_constant__ 
     const int wCell = L.wCell;
 
     // ---- stage the image tile with one TMA box load.  The TMA unit needs a 16-byte aligned start
-    // address, so the 256 x boxH box starts at X0a = X0 & ~15: smem byte (r, c) = level pixel
-    // (Y0 + r, X0a + c).  Candidate column cx (level x = X0 + 3 + cx) sits at smem byte
-    // 4*wo + ph + 3 + cx.  Out-of-image parts of the box are zero-filled by the TMA unit.
-    const int a0 = X0 & 15, wo = a0 >> 2, ph = a0 & 3;
-    const int QR = (CW + ph + 3) >> 2;  // 4-pixel groups per candidate row; group q, byte k <-> cx = 4q + k - ph
+    // address, so the 256 x boxH box starts at X0a = X0 & ~15: box byte (r, c) = level pixel (Y0 + r, X0a + c).
+    // Candidate column cx (level x = X0 + 3 + cx) is box column a0 + cx with a0 = (X0 & 15) + 3; pass A works on
+    // aligned groups of four box columns 4(wo + q) .. + 3, so group q, byte k <-> cx = 4q + k - ph.
+    // Out-of-image parts of the box are zero-filled by the TMA unit.
+    const int a0 = (X0 & 15) + 3, wo = a0 >> 2, ph = a0 & 3;
+    const int QR = (CW + ph + 3) >> 2;  // 4-pixel groups per candidate row
     const unsigned bar = smem_u32(&sm.bar);
+    unsigned* stage = reinterpret_cast<unsigned*>(sc);  // the landing buffer shares the score tile's memory
     if (tid == 0) mbar_init(bar, 1);
     __syncthreads();
     if (tid == 0) {
         mbar_expect_tx(bar, (unsigned)(DET_TILE_W * L.boxH));
-        tma_load_3d(smem_u32(&img[0][0]), maps + l, X0 - a0, Y0, f + plan.frameBase, bar);
+        tma_load_3d(smem_u32(stage), maps + l, X0 - (X0 & 15), Y0, f + plan.frameBase, bar);
     }
     {
-        // zero border of the score tile: rows 0 and CH+1, words 0 and QR+1
-        for (int i = tid; i < 2 * (QR + 2); i += DET_THREADS) {
-            const int r = i < QR + 2 ? 0 : CH + 1;
-            sc[r][i < QR + 2 ? i : i - (QR + 2)] = 0u;
-        }
-        for (int i = tid; i < 2 * (CH + 2); i += DET_THREADS) {
-            const int r = i >> 1;
-            sc[r][(i & 1) ? QR + 1 : 0] = 0u;
-        }
         // cellOf[cx + 4] for cx in [-4, CW + 4): cell index of candidate column cx (255 left of the tile)
         for (int i = tid; i < CW + 8; i += DET_THREADS) sm.cellOf[i] = i < 4 ? (unsigned char)255 : (unsigned char)((i - 4) / wCell);
         if (tid < 16) sm.cellHasIni[tid] = 0;
@@ -293,9 +304,33 @@ __global__ void __launch_bounds__(DET_THREADS) k_detect(const __grid_constant__ 
         }
     }
     mbar_wait(bar, 0);  // the tile has landed (async-proxy writes are visible after the wait)
-    __syncthreads();
+    // ---- expand: box words wo - 1 .. wo + QR of the TH tile rows -> E / O pixel-pair words
+    {
+        const int nw = QR + 2;  // one word of ring halo on each side
+        const unsigned nwMagic = 0xffffffffu / (unsigned)nw + 1u;
+        for (int item = tid; item < TH * nw; item += DET_THREADS) {
+            const int r = (int)__umulhi((unsigned)item, nwMagic);
+            const int wv = wo - 1 + (item - r * nw);
+            const unsigned w = stage[r * (DET_TILE_W / 4) + wv], wn = stage[r * (DET_TILE_W / 4) + wv + 1];
+            const unsigned v = __funnelshift_r(w, wn, 8);  // pixels 4wv + 1 .. 4wv + 4
+            *reinterpret_cast<uint2*>(&E[r][DET_EPAD + 2 * wv]) = make_uint2(__byte_perm(w, 0u, 0x4140), __byte_perm(w, 0u, 0x4342));
+            *reinterpret_cast<uint2*>(&O[r][DET_EPAD + 2 * wv]) = make_uint2(__byte_perm(v, 0u, 0x4140), __byte_perm(v, 0u, 0x4342));
+        }
+    }
+    __syncthreads();  // E / O complete, the landing buffer is dead: its memory becomes the score tile
+    {
+        // zero border of the score tile: rows 0 and CH+1, words 0 and QR+1
+        for (int i = tid; i < 2 * (QR + 2); i += DET_THREADS) {
+            const int r = i < QR + 2 ? 0 : CH + 1;
+            sc[r][i < QR + 2 ? i : i - (QR + 2)] = 0u;
+        }
+        for (int i = tid; i < 2 * (CH + 2); i += DET_THREADS) {
+            const int r = i >> 1;
+            sc[r][(i & 1) ? QR + 1 : 0] = 0u;
+        }
+    }
 
-    // ---- pass A: scores.  thread (q, r): candidate cols 4q-ph .. 4q-ph+3 of candidate row r
+    // ---- pass A: scores.  item (r, q): candidate row r, box columns 4(wo + q) .. + 3 as the pixel pairs P0 = (0, 1), P1 = (2, 3)
     const unsigned low2 = (unsigned)plan.lowTh * 0x00010001u;
     const unsigned neglow2 = ((unsigned)(-plan.lowTh) & 0xffffu) * 0x00010001u;
     const int q = tid & 63, grp = tid >> 6;  // (pass B mapping)
@@ -305,55 +340,58 @@ __global__ void __launch_bounds__(DET_THREADS) k_detect(const __grid_constant__ 
         for (int item = tid; item < CH * QR; item += DET_THREADS) {
             const int r = (int)__umulhi((unsigned)item, qrMagic);
             const int q = item - r * QR;
-            // rows r..r+6 of the tile; words wo+q .. wo+q+2 hold 12 tile bytes b0..b11,
-            // candidate pixels p0..p3 = b3..b6, ring offset dx reads b(3+dx)..b(6+dx)
-            unsigned w[7][3];
-#pragma unroll
-            for (int rr = 0; rr < 7; ++rr) {
-                w[rr][0] = img[r + rr][wo + q];
-                w[rr][1] = img[r + rr][wo + q + 1];
-                w[rr][2] = img[r + rr][wo + q + 2];
+            // h = word of pixel pair P0 in E; ring offset dx: even -> E[h + dx/2], odd -> O[h + (dx-1)/2]; P1 is the next word
+            const unsigned* e = &E[r][DET_EPAD + 2 * (wo + q)];
+            const unsigned* o = &O[r][DET_EPAD + 2 * (wo + q)];
+#define ROWE(rr, i) e[(rr) * DET_EP + (i)]
+#define ROWO(rr, i) o[(rr) * DET_EP + (i)]
+            unsigned r0[16], r1[16];  // ring of P0, ring of P1
+            // rows 6 and 0 (dy = +3, -3): dx = 0, 1, -1
+            {
+                const uint2 e6 = *reinterpret_cast<const uint2*>(&ROWE(6, 0)), o6 = *reinterpret_cast<const uint2*>(&ROWO(6, 0));
+                const unsigned o6m = ROWO(6, -1);
+                r0[0] = e6.x; r1[0] = e6.y;      // (0, 3)
+                r0[1] = o6.x; r1[1] = o6.y;      // (1, 3)
+                r0[15] = o6m; r1[15] = o6.x;     // (-1, 3)
+                const uint2 e0 = *reinterpret_cast<const uint2*>(&ROWE(0, 0)), o0 = *reinterpret_cast<const uint2*>(&ROWO(0, 0));
+                const unsigned o0m = ROWO(0, -1);
+                r0[8] = e0.x; r1[8] = e0.y;      // (0, -3)
+                r0[7] = o0.x; r1[7] = o0.y;      // (1, -3)
+                r0[9] = o0m; r1[9] = o0.x;       // (-1, -3)
             }
-            // unaligned 4-byte windows: win(rr, dx) = bytes b(3+dx)..b(6+dx) of row rr
-#define WIN(rr, dx)                                                                   \
-    ((dx) == -3 ? w[rr][0]                                                            \
-     : (dx) == -2 ? __byte_perm(w[rr][0], w[rr][1], 0x4321)                           \
-     : (dx) == -1 ? __byte_perm(w[rr][0], w[rr][1], 0x5432)                           \
-     : (dx) == 0  ? __byte_perm(w[rr][0], w[rr][1], 0x6543)                           \
-     : (dx) == 1  ? w[rr][1]                                                          \
-     : (dx) == 2  ? __byte_perm(w[rr][1], w[rr][2], 0x4321)                           \
-                  : __byte_perm(w[rr][1], w[rr][2], 0x5432))
-            // ring index k -> (dx, dy); tile row = 3 + dy
-            unsigned ring[16];
-            ring[0] = WIN(6, 0);    // (0, 3)
-            ring[1] = WIN(6, 1);    // (1, 3)
-            ring[2] = WIN(5, 2);    // (2, 2)
-            ring[3] = WIN(4, 3);    // (3, 1)
-            ring[4] = WIN(3, 3);    // (3, 0)
-            ring[5] = WIN(2, 3);    // (3,-1)
-            ring[6] = WIN(1, 2);    // (2,-2)
-            ring[7] = WIN(0, 1);    // (1,-3)
-            ring[8] = WIN(0, 0);    // (0,-3)
-            ring[9] = WIN(0, -1);   // (-1,-3)
-            ring[10] = WIN(1, -2);  // (-2,-2)
-            ring[11] = WIN(2, -3);  // (-3,-1)
-            ring[12] = WIN(3, -3);  // (-3, 0)
-            ring[13] = WIN(4, -3);  // (-3, 1)
-            ring[14] = WIN(5, -2);  // (-2, 2)
-            ring[15] = WIN(6, -1);  // (-1, 3)
-            const unsigned cen = WIN(3, 0);
-#undef WIN
-            // even lanes: pixels p0, p2 ; odd lanes: pixels p1, p3
-            unsigned re[16], ro[16];
-#pragma unroll
-            for (int k = 0; k < 16; ++k) {
-                re[k] = even_lanes(ring[k]);
-                ro[k] = odd_lanes(ring[k]);
+            // rows 5 and 1 (dy = +2, -2): dx = 2, -2
+            {
+                const uint2 e5 = *reinterpret_cast<const uint2*>(&ROWE(5, 0));
+                const unsigned e5m = ROWE(5, -1), e5p = ROWE(5, 2);
+                r0[2] = e5.y; r1[2] = e5p;       // (2, 2)
+                r0[14] = e5m; r1[14] = e5.x;     // (-2, 2)
+                const uint2 e1 = *reinterpret_cast<const uint2*>(&ROWE(1, 0));
+                const unsigned e1m = ROWE(1, -1), e1p = ROWE(1, 2);
+                r0[6] = e1.y; r1[6] = e1p;       // (2, -2)
+                r0[10] = e1m; r1[10] = e1.x;     // (-2, -2)
             }
-            unsigned ue, uo;
-            fast_score_pairs(re, even_lanes(cen), low2, neglow2, ue);
-            fast_score_pairs(ro, odd_lanes(cen), low2, neglow2, uo);
-            unsigned word = ue | (uo << 8);  // bytes: p0, p1, p2, p3
+            // rows 4, 3, 2 (dy = +1, 0, -1): dx = 3, -3
+            {
+                const uint2 o4m = *reinterpret_cast<const uint2*>(&ROWO(4, -2));
+                const unsigned o4a = ROWO(4, 1), o4b = ROWO(4, 2);
+                r0[3] = o4a; r1[3] = o4b;        // (3, 1)
+                r0[13] = o4m.x; r1[13] = o4m.y;  // (-3, 1)
+                const uint2 o3m = *reinterpret_cast<const uint2*>(&ROWO(3, -2));
+                const unsigned o3a = ROWO(3, 1), o3b = ROWO(3, 2);
+                r0[4] = o3a; r1[4] = o3b;        // (3, 0)
+                r0[12] = o3m.x; r1[12] = o3m.y;  // (-3, 0)
+                const uint2 o2m = *reinterpret_cast<const uint2*>(&ROWO(2, -2));
+                const unsigned o2a = ROWO(2, 1), o2b = ROWO(2, 2);
+                r0[5] = o2a; r1[5] = o2b;        // (3, -1)
+                r0[11] = o2m.x; r1[11] = o2m.y;  // (-3, -1)
+            }
+            const uint2 cen = *reinterpret_cast<const uint2*>(&ROWE(3, 0));
+#undef ROWE
+#undef ROWO
+            unsigned u01, u23;
+            fast_score_pairs(r0, cen.x, low2, neglow2, u01);
+            fast_score_pairs(r1, cen.y, low2, neglow2, u23);
+            unsigned word = __byte_perm(u01, u23, 0x6420);  // bytes: p0, p1, p2, p3
             const int rem = CW + ph - 4 * q;  // bytes of this group left of the candidate area's end
             if (rem < 4) word &= (1u << (8 * rem)) - 1u;
             if (q == 0) word &= 0xffffffffu << (8 * ph);  // bytes before candidate column 0
@@ -416,7 +454,7 @@ __global__ void __launch_bounds__(DET_THREADS) k_detect(const __grid_constant__ 
                 const unsigned outw = active ? ((midBe & kE) | ((midBo & kO) << 8)) : 0u;
                 const unsigned nz = __ballot_sync(0xffffffffu, outw != 0u);
                 if (outw) {  // this warp's private list region: no atomics
-                    img[r][q] = outw;
+                    E[r][q] = outw;
                     sm.wlist[wbase + wcount + __popc(nz & ((1u << lane) - 1u))] = (unsigned short)((r << 6) | q);
                 }
                 wcount += __popc(nz);
@@ -437,7 +475,7 @@ __global__ void __launch_bounds__(DET_THREADS) k_detect(const __grid_constant__ 
         for (int i = tid & 31; i < myW; i += 32) {
             const int idx = sm.wlist[wb + i];
             const int r = idx >> 6, qq = idx & 63;
-            unsigned w = img[r][qq];
+            unsigned w = E[r][qq];
             while (w) {  // at most two survivors per word (never 8-adjacent)
                 const int k = (__ffs(w) - 1) >> 3;
                 const unsigned u = (w >> (8 * k)) & 0xffu;

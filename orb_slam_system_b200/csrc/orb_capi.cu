@@ -134,7 +134,7 @@ struct orb_extractor {
     int lanes = 2;
     // host-buffer pipeline: copies in and out run on their own streams, chunk by chunk
     cudaStream_t streamIn = nullptr, streamOut = nullptr, streamCnt = nullptr;
-    enum { MAX_CHUNKS = 8, NUM_SLOTS = 2 };
+    enum { MAX_CHUNKS = 8, NUM_SLOTS = 3 };
     cudaEvent_t evFree = nullptr;
     // One in-flight host batch: its landing / result staging buffers, its events, and where the results go.
     struct HostSlot {
@@ -751,7 +751,7 @@ static int submit_impl(orb_extractor* h, int n, const uint8_t* imgs, int rows, i
     const int srcRows = ingest ? I.srows : rows;
     if (stride < rowBytes) return fail(ORB_ERR_INVALID, ingest ? "stride < src_cols * channels" : "stride < cols");
     orb_extractor::HostSlot& S = h->slot[h->next_slot];
-    if (S.busy) return fail(ORB_ERR_INVALID, "two batches are already in flight: call orb_extract_batch_wait first");
+    if (S.busy) return fail(ORB_ERR_INVALID, "three batches are already in flight: call orb_extract_batch_wait first");
     CUDA_TRY(cudaSetDevice(h->device));
     if (h->plan.rows != rows || h->plan.cols != cols) {
         for (int k = 0; k < orb_extractor::NUM_SLOTS; ++k)

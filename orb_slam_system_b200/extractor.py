@@ -115,7 +115,7 @@ class ORBextractor:
         self._last_frames = n
 
     def submit_batch_pinned(self, images, kps, desc, counts, cap):
-        """Asynchronous extract_batch_pinned: returns a ticket for wait_batch; two batches may be in flight."""
+        """Asynchronous extract_batch_pinned: returns a ticket for wait_batch; three batches may be in flight."""
         n, rows, cols = images.shape
         t = C.c_int(-1)
         check(lib().orb_extract_batch_submit(self._h, n, ptr(images), rows, cols,

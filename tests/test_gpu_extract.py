@@ -120,25 +120,27 @@ def test_empty_and_error_shapes():
     ex.close()
 
 
-def test_async_submit_wait_two_in_flight():
-    # orb_extract_batch_submit / _wait: two batches in flight give the same bytes as the synchronous call
+def test_async_submit_wait_three_in_flight():
+    # orb_extract_batch_submit / _wait: three batches in flight give the same bytes as the synchronous call
     rows, cols, nf, B = 200, 300, 500, 8
     ex = ORBextractor(nf, 1.2, 8, 20, 7, max_batch=B)
     cap = ex.keypoint_bound(rows, cols)
-    batches = [np.stack([oracle.synth_frame(rows, cols, frame=10 * b + f) for f in range(B)]) for b in range(3)]
+    batches = [np.stack([oracle.synth_frame(rows, cols, frame=10 * b + f) for f in range(B)]) for b in range(4)]
     want = [ex.extract_batch(b, cap=cap) for b in batches]
     from orb_slam_system_b200 import KP_DTYPE
-    outs = [(np.zeros((B, cap), KP_DTYPE), np.zeros((B, cap, 32), np.uint8), np.zeros(B, np.int32)) for _ in range(3)]
+    outs = [(np.zeros((B, cap), KP_DTYPE), np.zeros((B, cap, 32), np.uint8), np.zeros(B, np.int32)) for _ in range(4)]
     t0 = ex.submit_batch_pinned(batches[0], *outs[0], cap)
     t1 = ex.submit_batch_pinned(batches[1], *outs[1], cap)
-    from orb_slam_system_b200 import OrbError
-    with pytest.raises(OrbError):  # a third batch needs a wait first
-        ex.submit_batch_pinned(batches[2], *outs[2], cap)
-    ex.wait_batch(t0)
     t2 = ex.submit_batch_pinned(batches[2], *outs[2], cap)
+    from orb_slam_system_b200 import OrbError
+    with pytest.raises(OrbError):  # a fourth batch needs a wait first
+        ex.submit_batch_pinned(batches[3], *outs[3], cap)
+    ex.wait_batch(t0)
+    t3 = ex.submit_batch_pinned(batches[3], *outs[3], cap)
     ex.wait_batch(t1)
     ex.wait_batch(t2)
-    for b in range(3):
+    ex.wait_batch(t3)
+    for b in range(4):
         k, d, c = outs[b]
         for f in range(B):
             wk, wd = want[b][f]
