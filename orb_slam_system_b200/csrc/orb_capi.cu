@@ -442,7 +442,8 @@ static int build_plan(orb_extractor* h, int rows, int cols) {
 }
 
 static int ensure_out(orb_extractor* h, orb_extractor::HostSlot& S, int cap) {
-    if (!S.d_counts) CUDA_TRY(cudaMalloc((void**)&S.d_counts, sizeof(int) * h->max_batch));
+    // counts, and behind them this batch's own copy of the octree status flags
+    if (!S.d_counts) CUDA_TRY(cudaMalloc((void**)&S.d_counts, sizeof(int) * 2 * h->max_batch));
     if (!S.h_status) CUDA_TRY(cudaMallocHost((void**)&S.h_status, sizeof(int) * h->max_batch));
     if (cap <= S.out_cap) return ORB_OK;
     CUDA_TRY(cudaStreamSynchronize(h->streamOut));
@@ -766,12 +767,15 @@ static int submit_impl(orb_extractor* h, int n, const uint8_t* imgs, int rows, i
     // results D2H (streamOut, issued by orb_extract_batch_wait), so that PCIe in, compute and PCIe out of
     // neighbouring chunks -- and of the neighbouring batch in flight -- overlap.  While per-stage profiling is
     // on, one chunk is used (stage times then describe whole-batch launches).
-    // Chunking only pays when this batch has nothing else to overlap with: with another batch in flight the
-    // copies of one batch already hide behind the kernels of the other, and a single chunk keeps the launches
-    // large and the host-side enqueue cost at its minimum (measured on B200: 61.5k vs 51.7k frames/s at 64 frames).
+    // Fine chunking only pays when this batch has nothing else to overlap with: with another batch in flight the
+    // copies of one batch already hide behind the kernels of the other, so one chunk per kernel lane keeps the
+    // launches large and the host-side enqueue cost low (measured on B200 at 64 frames, three batches in flight:
+    // 74.7k frames/s with two 32-frame chunks, 71.3k with one chunk, 51.7k with four 16-frame chunks).
+    // Measured too: while the copy engines move this data the kernels run ~15 % slower than on resident frames (a
+    // copy by SM loads from mapped host memory was worse still), which is what keeps e2e below the resident rate.
     bool pipelined = false;
     for (int k = 0; k < orb_extractor::NUM_SLOTS; ++k) pipelined |= h->slot[k].busy;
-    const int chunkFrames = getenv("ORB_B200_CHUNK") ? std::max(1, atoi(getenv("ORB_B200_CHUNK"))) : (pipelined ? n : 16);
+    const int chunkFrames = getenv("ORB_B200_CHUNK") ? std::max(1, atoi(getenv("ORB_B200_CHUNK"))) : (pipelined ? std::max(16, (n + h->lanes - 1) / std::max(1, h->lanes)) : 16);
     int nchunks = h->profiling ? 1 : std::min<int>(orb_extractor::MAX_CHUNKS, std::max(1, n / chunkFrames));
     const int per = (n + nchunks - 1) / nchunks;
     nchunks = (n + per - 1) / per;
@@ -789,11 +793,8 @@ static int submit_impl(orb_extractor* h, int n, const uint8_t* imgs, int rows, i
         S.dense_cap = want;
     }
     // everything enqueued so far on the main stream (the previous batch's kernels: every lane joins there)
-    // must finish before this batch touches the shared level / scratch buffers -- including the small
-    // count / status copies of a batch still in flight, which read the shared status flags
-    for (int k = 0; k < orb_extractor::NUM_SLOTS; ++k)
-        if (h->slot[k].busy)
-            for (int c = 0; c < h->slot[k].nchunks; ++c) CUDA_TRY(cudaStreamWaitEvent(h->stream, h->slot[k].evCnt[c], 0));
+    // finishes before this batch touches the shared level / scratch buffers; a batch's status flags are copied
+    // into its own slot at the end of its kernels, so the next batch does not have to wait for the count copies
     h->last_l0 = h->level0;
     CUDA_TRY(cudaEventRecord(h->evFree, h->stream));
     if (!dense) CUDA_TRY(cudaStreamWaitEvent(h->streamIn, h->evFree, 0));  // non-dense copies write level 0 directly
@@ -837,13 +838,14 @@ static int submit_impl(orb_extractor* h, int n, const uint8_t* imgs, int rows, i
         const OrbPlan P = plan_slice(h->plan, f0);
         CUDA_TRY(orbk_run_extract(P, nf, S.d_kps + (size_t)f0 * S.out_cap, S.d_desc + (size_t)f0 * S.out_cap * 32, S.out_cap,
                                   S.d_counts + f0, ls, h->d_maps, h->next_events()));
+        CUDA_TRY(cudaMemcpyAsync(S.d_counts + h->max_batch + f0, h->plan.status + f0, sizeof(int) * nf, cudaMemcpyDeviceToDevice, ls.st));
         CUDA_TRY(cudaEventRecord(S.evDone[c], ls.st));
         if (ls.st != h->stream) CUDA_TRY(cudaStreamWaitEvent(h->stream, S.evDone[c], 0));  // the main stream stays the join point
         // counts (and the octree status flags) travel on their own small stream so that the bulk result copies
         // of chunk c -- issued once its counts are known -- are not queued behind the kernels of later chunks
         CUDA_TRY(cudaStreamWaitEvent(h->streamCnt, S.evDone[c], 0));
         CUDA_TRY(cudaMemcpyAsync(counts + f0, S.d_counts + f0, sizeof(int) * nf, cudaMemcpyDeviceToHost, h->streamCnt));
-        CUDA_TRY(cudaMemcpyAsync(S.h_status + f0, h->plan.status + f0, sizeof(int) * nf, cudaMemcpyDeviceToHost, h->streamCnt));
+        CUDA_TRY(cudaMemcpyAsync(S.h_status + f0, S.d_counts + h->max_batch + f0, sizeof(int) * nf, cudaMemcpyDeviceToHost, h->streamCnt));
         CUDA_TRY(cudaEventRecord(S.evCnt[c], h->streamCnt));
     }
     S.busy = true;
