@@ -216,6 +216,7 @@ def next_rows(device):
     exi.set_ingest((rows, cols, 3), maps=(mx, my))
     t_ing = best_of(lambda: exi.ingest_extract_batch(raw), 5)
     gi = exi.ingest_extract_batch(raw)
+    level0 = exi.pyramid_level(0)  # the reference's mImGray of frame 0
     t0 = time.perf_counter()
     gray0 = oracle.cvt_gray(oracle.remap_linear(raw[0], mx, my))
     t_cpu_ing = time.perf_counter() - t0
@@ -227,7 +228,7 @@ def next_rows(device):
     same = len(gi[0][0]) == len(ok0) and all(np.array_equal(gi[0][0][k], ok0[k]) for k in ("x", "y", "size", "angle", "response", "octave"))
     out["ingest"] = {"workload": f"{nfr} raw 752x480x3 frames: remap (CV_32FC1 maps, INTER_LINEAR) + RGB2GRAY fused into the level-0 load, then extraction",
                      "frames_per_s": nfr / t_ing, "ms_per_call": 1e3 * t_ing, "ms_per_call_gray_frames_no_ingest": 1e3 * t_plain,
-                     "identical_to_oracle": bool(same and np.array_equal(gi[0][1], od0) and np.array_equal(exi.pyramid_level(0), gray0)),
+                     "identical_to_oracle": bool(same and np.array_equal(gi[0][1], od0) and np.array_equal(level0, gray0)),
                      "cpu_ms_per_frame": 1e3 * (t_cpu_ing + t_cpu_ex0), "cpu_ingest_ms_per_frame": 1e3 * t_cpu_ing, "cpu_cores": 1}
     exi.close()
     ex.close()
@@ -525,8 +526,9 @@ def main():
                        "l2": f"inputs rotate through {R} distinct batches ({R * B * ROWS * pitch / 1e6:.0f} MB > 126 MB L2)"},
             "roofline": {"bound": "hbm", "kernel": "k_" + dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak,
-                         # dram__bytes_read.sum + dram__bytes_write.sum of k_detect, ncu --set full (profiles/r01f: 2 x 32-frame launches)
-                         "traffic": 87.9e6 if dom == "detect" else None, "traffic_source": "profiles/r01f_ncu_summary.txt",
+                         # dram__bytes_read.sum + dram__bytes_write.sum of k_detect, ncu --set full (profiles/r01g: 2 x 32-frame
+                         # launches of 43.25 + 0.74 MB make one 64-frame step)
+                         "traffic": 88.0e6 if dom == "detect" else None, "traffic_source": "profiles/r01g_ncu_summary.txt",
                          "peak_source": peak_kind,
                          "algo_bytes_per_launch": algo, "launch_ms": per_launch_ms,
                          "stage_ms_per_step": {k: v / max(ncalls, 1) for k, v in stage_ms.items()},
