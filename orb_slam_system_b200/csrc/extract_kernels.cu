@@ -294,7 +294,8 @@ __global__ void __launch_bounds__(DET_THREADS) k_detect(const __grid_constant__ 
     }
     {
         // cellOf[cx + 4] for cx in [-4, CW + 4): cell index of candidate column cx (255 left of the tile)
-        for (int i = tid; i < CW + 8; i += DET_THREADS) sm.cellOf[i] = i < 4 ? (unsigned char)255 : (unsigned char)((i - 4) / wCell);
+        const unsigned wcMagic = 0xffffffffu / (unsigned)wCell + 1u;  // (i - 4) / wCell as a multiply-high
+        for (int i = tid; i < CW + 8; i += DET_THREADS) sm.cellOf[i] = i < 4 ? (unsigned char)255 : (unsigned char)__umulhi((unsigned)(i - 4), wcMagic);
         if (tid < 16) sm.cellHasIni[tid] = 0;
         if (tid == 0) {
             sm.nWords = 0;
@@ -591,10 +592,38 @@ __device__ __forceinline__ bool path_code(const OrbLevel& L, int x, int y, unsig
     return true;
 }
 
+// The same replay cut at `depth` <= OCTF_MAX_DEPTH halvings (k_octree_fast never looks deeper than its tables):
+// code = [root][c_1:2]...[c_depth:2].
+__device__ __forceinline__ bool path_code_to(const OrbLevel& L, int x, int y, int depth, unsigned& code) {
+    const int root = (int)__fdiv_rn((float)x, L.hX);
+    if (!(root >= 0 && root < L.nIni)) return false;
+    int ulx = (int)__fmul_rn(L.hX, (float)root);
+    int urx = (int)__fmul_rn(L.hX, (float)(root + 1));
+    int uly = 0, bly = L.H;
+    code = (unsigned)root;
+#pragma unroll
+    for (int d = 0; d < 7; ++d) {
+        if (d < depth) {
+            const int midx = ulx + ((urx - ulx) >> 1);
+            const int midy = uly + ((bly - uly) >> 1);
+            const unsigned cx = x >= midx, cy = y >= midy;
+            if (cx) ulx = midx; else urx = midx;
+            if (cy) uly = midy; else bly = midy;
+            code = (code << 2) | (cy << 1) | cx;
+        }
+    }
+    return true;
+}
+
 // Candidate order (cells row-major, then row-major inside the cell) as one integer that also
 // carries the coordinates: cell index << 26 | y << 13 | x.
 __device__ __forceinline__ unsigned long long cand_order(const OrbLevel& L, unsigned x, unsigned y) {
     const unsigned cj = (x - 3) / (unsigned)L.wCell, ci = (y - 3) / (unsigned)L.hCell;
+    return ((unsigned long long)(ci * (unsigned)L.nCols + cj) << 26) | (y << 13) | x;
+}
+// Same with the two divisions as multiply-high by magic = 0xffffffff / d + 1 (exact for operands below 2^16).
+__device__ __forceinline__ unsigned long long cand_order_magic(const OrbLevel& L, unsigned x, unsigned y, unsigned wMagic, unsigned hMagic) {
+    const unsigned cj = __umulhi(x - 3, wMagic), ci = __umulhi(y - 3, hMagic);
     return ((unsigned long long)(ci * (unsigned)L.nCols + cj) << 26) | (y << 13) | x;
 }
 
@@ -657,10 +686,10 @@ __global__ void __launch_bounds__(OCTF_THREADS) k_octree_fast(const __grid_const
     for (int i = tid; i < n; i += OCTF_THREADS) {
         const uint2 c = cand[i];
         unsigned code = 0xffffffffu;
-        if (path_code(L, (int)(c.x & 0xffff), (int)(c.x >> 16), code)) {
+        if (path_code_to(L, (int)(c.x & 0xffff), (int)(c.x >> 16), tmax, code)) {
             int off = 0;
             for (int t = 0; t <= tmax; ++t) {
-                atomicAdd(&sm.cnt[off + (code >> (2 * (OCT_D - t)))], 1u);
+                atomicAdd(&sm.cnt[off + (code >> (2 * (tmax - t)))], 1u);
                 off += nIni << (2 * t);
             }
         } else {
@@ -724,12 +753,13 @@ __global__ void __launch_bounds__(OCTF_THREADS) k_octree_fast(const __grid_const
     __syncthreads();
     // ---- pass 2: first max-response key per depth-p* node
     const unsigned long long ORDMAX = (1ull << 44) - 1;
+    const unsigned wMagic = 0xffffffffu / (unsigned)L.wCell + 1u, hMagic = 0xffffffffu / (unsigned)L.hCell + 1u;
     for (int i = tid; i < n; i += OCTF_THREADS) {
         const unsigned code = codes[i];
         if (code == 0xffffffffu) continue;
         const uint2 c = cand[i];
-        const unsigned long long key = ((unsigned long long)c.y << 48) | (ORDMAX - cand_order(L, c.x & 0xffff, c.x >> 16));
-        atomicMax(&sm.best[code >> (2 * (OCT_D - pstar))], key);
+        const unsigned long long key = ((unsigned long long)c.y << 48) | (ORDMAX - cand_order_magic(L, c.x & 0xffff, c.x >> 16, wMagic, hMagic));
+        atomicMax(&sm.best[code >> (2 * (tmax - pstar))], key);
     }
     __syncthreads();
     // ---- final node of every non-empty depth-p* entry -> slot in the ordered tables
