@@ -22,6 +22,10 @@ static unsigned long long g_launches = 0;
 __device__ __forceinline__ unsigned vmax3(unsigned a, unsigned b, unsigned c) { return __vimax3_u16x2(a, b, c); }
 __device__ __forceinline__ unsigned vmin3(unsigned a, unsigned b, unsigned c) { return __vimin3_u16x2(a, b, c); }
 // four unsigned bytes (pixels) times four signed bytes (weights), accumulated into a signed int
+// n / d for n < 2^16 as a multiply-high by magic = div_magic(d); d == 1 has no 32-bit magic and is passed through.
+__device__ __forceinline__ unsigned div_magic(unsigned d) { return d <= 1u ? 0u : 0xffffffffu / d + 1u; }
+__device__ __forceinline__ unsigned div_by(unsigned n, unsigned magic) { return magic ? __umulhi(n, magic) : n; }
+
 __device__ __forceinline__ int dp4a_us(unsigned a, int b, int c) {
     int d;
     asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
@@ -337,9 +341,9 @@ __global__ void __launch_bounds__(DET_THREADS) k_detect(const __grid_constant__ 
     const int q = tid & 63, grp = tid >> 6;  // (pass B mapping)
     {
         // items (row, group) flattened over all threads so that no lane idles when QR < 64
-        const unsigned qrMagic = 0xffffffffu / (unsigned)QR + 1u;  // item / QR == umulhi(item, magic) for item < 2^16
+        const unsigned qrMagic = div_magic((unsigned)QR);  // item / QR for item < 2^16
         for (int item = tid; item < CH * QR; item += DET_THREADS) {
-            const int r = (int)__umulhi((unsigned)item, qrMagic);
+            const int r = (int)div_by((unsigned)item, qrMagic);
             const int q = item - r * QR;
             // h = word of pixel pair P0 in E; ring offset dx: even -> E[h + dx/2], odd -> O[h + (dx-1)/2]; P1 is the next word
             const unsigned* e = &E[r][DET_EPAD + 2 * (wo + q)];
@@ -1057,16 +1061,18 @@ __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ OrbPlan pl
     if (!vec_ok) { jlo = 0; jhi = -1; }
     const int nvec = max(jhi - jlo + 1, 0);
     // pass 1: the inside vectors, 16 bytes per thread
+    const unsigned nvMagic = div_magic((unsigned)nvec);
     for (int i = tid; i < rowsHere * nvec; i += 256) {
-        const int r = i / nvec, j = jlo + (i - r * nvec);
+        const int r = (int)div_by((unsigned)i, nvMagic), j = jlo + (i - r * nvec);
         const int yy = reflect101(y0 - 3 + r, L.rows);
         *reinterpret_cast<uint4*>(&tile[r][4 * j]) = __ldg(reinterpret_cast<const uint4*>(src + (size_t)yy * L.pitch + (x0 - 16 + 16 * j)));
     }
     // pass 2: the words left and right of them (row ends of the image only): reflect-101 per byte
     const int nleft = nvec ? 4 * jlo : BLUR_SW, nright = nvec ? BLUR_SW - 4 * (jhi + 1) : 0;
     const int nb = nleft + nright;
+    const unsigned nbMagic = div_magic((unsigned)nb);
     for (int i = tid; i < rowsHere * nb; i += 256) {
-        const int r = i / nb, kk = i - r * nb;
+        const int r = (int)div_by((unsigned)i, nbMagic), kk = i - r * nb;
         const int k = kk < nleft ? kk : 4 * (jhi + 1) + (kk - nleft);
         const int x = x0 - 16 + 4 * k;
         unsigned w = 0;
@@ -1093,41 +1099,51 @@ __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ OrbPlan pl
     if (xq >= L.cols) return;
     const int rbase = g * BLUR_RPT;  // first output row of this thread inside the tile
     if (y0 + rbase >= L.rows) return;
-    uint8_t* dst = L.blur + (size_t)f * L.plane;
+    uint8_t* dstp = L.blur + (size_t)f * L.plane + (size_t)(y0 + rbase) * L.pitch + xq;  // output row of this thread, bumped per row
     const unsigned WLO = 18u | (34u << 8) | (48u << 16) | (56u << 24);
     const unsigned WHI = 48u | (34u << 8) | (18u << 16);
-    int H[7][4];
+    // Vertical pass on row PAIRS: the horizontal sums are < 2^16, so two consecutive rows of one pixel share a register
+    // (P[r] = H[r] | H[r+1] << 16) and the 7 taps are three IDP.2A plus one multiply-add:
+    //   acc(y) = 32768 + (18, 34).P[y] + (48, 56).P[y+2] + (48, 34).P[y+4] + 18 H[y+6];   out = byte 2 of acc.
+    const unsigned W01 = 18u | (34u << 8), W23 = 48u | (56u << 8), W45 = 48u | (34u << 8);
+    unsigned P[6][4], Hprev[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
     for (int rr = 0; rr < BLUR_RPT + 6; ++rr) {
         const int r = rbase + rr;
-        int h0 = 0, h1 = 0, h2 = 0, h3 = 0;
+        unsigned h[4] = {0u, 0u, 0u, 0u};
         if (r < rowsHere) {
             // words q+3, q+4, q+5 = smem bytes 4q+12 .. 4q+23 = b0..b11; output pixel k (smem byte
             // 16 + 4q + k) reads b(1+k)..b(7+k)
             const unsigned w0 = tile[r][q + 3], w1 = tile[r][q + 4], w2 = tile[r][q + 5];
-            h0 = __dp4a(__byte_perm(w0, w1, 0x4321), WLO, __dp4a(__byte_perm(w1, w2, 0x4321), WHI, 0u));
-            h1 = __dp4a(__byte_perm(w0, w1, 0x5432), WLO, __dp4a(__byte_perm(w1, w2, 0x5432), WHI, 0u));
-            h2 = __dp4a(__byte_perm(w0, w1, 0x6543), WLO, __dp4a(__byte_perm(w1, w2, 0x6543), WHI, 0u));
-            h3 = __dp4a(w1, WLO, __dp4a(w2, WHI, 0u));
+            h[0] = __dp4a(__byte_perm(w0, w1, 0x4321), WLO, __dp4a(__byte_perm(w1, w2, 0x4321), WHI, 0u));
+            h[1] = __dp4a(__byte_perm(w0, w1, 0x5432), WLO, __dp4a(__byte_perm(w1, w2, 0x5432), WHI, 0u));
+            h[2] = __dp4a(__byte_perm(w0, w1, 0x6543), WLO, __dp4a(__byte_perm(w1, w2, 0x6543), WHI, 0u));
+            h[3] = __dp4a(w1, WLO, __dp4a(w2, WHI, 0u));
         }
-        H[rr % 7][0] = h0;
-        H[rr % 7][1] = h1;
-        H[rr % 7][2] = h2;
-        H[rr % 7][3] = h3;
+        if (rr >= 1) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) P[(rr - 1) % 6][k] = __byte_perm(Hprev[k], h[k], 0x5410);
+        }
         if (rr >= 6) {
             const int y = y0 + rbase + rr - 6;
             if (y < L.rows) {
-                unsigned outw = 0;
+                unsigned acc[4];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     // rows rr-6 .. rr of the window, taps 18 34 48 56 48 34 18
-                    const int acc = 18 * (H[(rr - 6) % 7][k] + H[rr % 7][k]) + 34 * (H[(rr - 5) % 7][k] + H[(rr - 1) % 7][k]) +
-                                    48 * (H[(rr - 4) % 7][k] + H[(rr - 2) % 7][k]) + 56 * H[(rr - 3) % 7][k];
-                    outw |= (unsigned)((acc + 32768) >> 16) << (8 * k);
+                    unsigned a = __dp2a_lo(P[(rr - 6) % 6][k], W01, 32768u);
+                    a = __dp2a_lo(P[(rr - 4) % 6][k], W23, a);
+                    a = __dp2a_lo(P[(rr - 2) % 6][k], W45, a);
+                    acc[k] = a + 18u * h[k];
                 }
-                *reinterpret_cast<unsigned*>(dst + (size_t)y * L.pitch + xq) = outw;
+                // byte 2 of every accumulator (acc < 2^24)
+                const unsigned outw = __byte_perm(__byte_perm(acc[0], acc[1], 0x0062), __byte_perm(acc[2], acc[3], 0x0062), 0x5410);
+                *reinterpret_cast<unsigned*>(dstp) = outw;
+                dstp += L.pitch;
             }
         }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) Hprev[k] = h[k];
     }
 }
 

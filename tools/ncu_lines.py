@@ -1,14 +1,17 @@
 #!/usr/bin/env python3
 """Per-source-line share of executed warp instructions and stall samples of the first kernel in an .ncu-rep
-(needs -lineinfo and --import-source on).  Usage: tools/ncu_lines.py report.ncu-rep [min_pct]"""
+(needs -lineinfo and --import-source on).  Usage: tools/ncu_lines.py report.ncu-rep [min_pct [kernel_name]]"""
 import collections
 import csv
 import subprocess
 import sys
 
 
-def main(path, min_pct=0.5):
-    out = subprocess.run(["ncu", "-i", path, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
+def main(path, min_pct=0.5, kernel=None):
+    cmd = ["ncu", "-i", path, "--page", "source", "--csv", "--print-source", "cuda,sass"]
+    if kernel:
+        cmd += ["--kernel-name", kernel, "--launch-count", "1"]
+    out = subprocess.run(cmd, capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     for i, r in enumerate(rows):
         if "Source" in r and "Instructions Executed" in r:
@@ -36,4 +39,4 @@ def main(path, min_pct=0.5):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1], float(sys.argv[2]) if len(sys.argv) > 2 else 0.5)
+    main(sys.argv[1], float(sys.argv[2]) if len(sys.argv) > 2 else 0.5, sys.argv[3] if len(sys.argv) > 3 else None)
