@@ -544,9 +544,11 @@ def main():
                         "ms_per_launch": match_ms,
                         "algo_bytes_per_launch": NP * (32 * 2 * NQ + 12 * NQ),
                         "hbm_frac": NP * (32 * 2 * NQ + 12 * NQ) / (match_ms * 1e-3) / 1e9 / peak,
-                        "popc_per_s": world * 6 * NP * NQ * NQ / (match_ms * 1e-3),
-                        "note": "POPC-pipe bound (quarter-rate pipe, ~4.5e12 POPC/s per GPU); 6 POPC per pair because words 6-7 of "
-                                "this fork's descriptors are zero (checked on the data, 8 otherwise)"},
+                        "popc_per_s": world * 3 * NP * NQ * NQ / (match_ms * 1e-3),
+                        "logic_ops_per_s": world * 19 * NP * NQ * NQ / (match_ms * 1e-3),
+                        "note": "logic-pipe bound: the 6 live XOR words of a pair (words 6-7 of this fork's descriptors are zero, checked on "
+                                "the data; 8 otherwise) go through a LOP3 carry-save tree to 3 POPC instead of 6, ~19 logic-pipe "
+                                "instructions per pair against a pipe rate of 64 lanes/clk/SM = 0.97e12 pairs/s per GPU"},
         }
         if shard is not None:
             line["shard_match"] = shard

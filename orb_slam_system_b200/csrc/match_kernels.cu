@@ -1,7 +1,7 @@
 // Hand-written sm_100a Hamming-search kernels.
 //
 // Unit: ORBmatcher::DescriptorDistance (reference src/ORBmatcher.cc:896-908) = popcount of
-// the XOR of two 256-bit descriptors; here 2 x 128-bit loads + 8 x POPC.
+// the XOR of two 256-bit descriptors; here 2 x 128-bit loads, XOR, and a carry-save adder tree that leaves 3 or 4 words to POPC (k_match_all) or 8 x POPC.
 // Scan semantics (src/ORBmatcher.cc:49-55, :225-231, :321-327): candidates in list order,
 // strict '<' updates of (best, second); best = first minimum, second = second smallest of
 // the multiset.  Tensor cores are not used: this is not a dense contraction.
@@ -16,6 +16,18 @@ __device__ __forceinline__ int hamming256(const uint4& a0, const uint4& a1, cons
            __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
 }
 
+// Carry-save adder halves as single LOP3s.
+__device__ __forceinline__ unsigned xor3(unsigned a, unsigned b, unsigned c) {
+    unsigned r;
+    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+__device__ __forceinline__ unsigned maj3(unsigned a, unsigned b, unsigned c) {
+    unsigned r;
+    asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+
 // ------------------------------------------------------------------------------------------
 // Brute force: one thread per query, train descriptors staged through shared memory in
 // tiles and read back as warp-wide broadcasts.  blockIdx.y = (query set, train set) pair.
@@ -27,7 +39,7 @@ __global__ void __launch_bounds__(MA_THREADS) k_match_all(const uint8_t* __restr
                                                           size_t q_stride, const uint8_t* __restrict__ t,
                                                           const int* __restrict__ nt, size_t t_stride,
                                                           int* __restrict__ best_idx, int* __restrict__ best_dist,
-                                                          int* __restrict__ second_dist, size_t out_stride) {
+                                                          int* __restrict__ second_dist, size_t out_stride, unsigned key_scale) {
     __shared__ uint4 tile[MA_TILE][2];
     const int p = blockIdx.y;
     const int nQ = nq[p], nT = nt[p];
@@ -40,12 +52,24 @@ __global__ void __launch_bounds__(MA_THREADS) k_match_all(const uint8_t* __restr
         q0 = __ldg(Q + 2 * (size_t)qi);
         q1 = __ldg(Q + 2 * (size_t)qi + 1);
     }
-    int best = INT_MAX, second = INT_MAX, idx = -1;
     // This fork's descriptors have bits 182..255 always zero, i.e. words 6 and 7 are zero.
     // When that holds for every query of the warp and every train row of the tile (checked on the data,
-    // so the result is exact for any input) the distance needs 6 POPC instead of 8 -- the POPC pipe
-    // (quarter rate) is what bounds this kernel.
+    // so the result is exact for any input) the distance needs 6 words instead of 8.
+    //
+    // POPC is a quarter-rate pipe and bounds a popcount-per-word scan, so the XOR words of a pair first go through a
+    // carry-save adder tree on the full-rate logic pipe (LOP3: sum = a^b^c, carry = maj(a,b,c)) that leaves one word
+    // per binary weight: 6 words -> (ones, twos, fours), 8 words -> (ones, twos, fours, eights), i.e. 3 / 4 POPC instead
+    // of 6 / 8, and d = p1 + 2 p2 + 4 p4 (+ 8 p8).
+    // Scan state as keys d << 22 | j (j = train index < 2^22): key order refines distance order and the smallest key of
+    // equal distances is the first one, so  best = min(best, key), second = min(second, max(key, best_before))  is the
+    // reference's  if (d < best) {second = best; best = d; idx = j} else if (d < second) second = d.
     const bool qUpperZero = __all_sync(0xffffffffu, (q1.z | q1.w) == 0u);
+    unsigned bestk = 0xffffffffu, seck = 0xffffffffu;
+    int best = INT_MAX, second = INT_MAX, idx = -1;  // scan state of the plain path (train sets of 2^22 rows and more)
+    const bool keyed = nT < (1 << 22);
+    // key_scale = 1 << 22 arrives as a kernel argument so that the weighted sums stay multiply-adds on the FMA pipe
+    // (as immediates ptxas turns them into shift-adds on the logic pipe, which is the busy one here)
+    const unsigned C1 = key_scale, C2 = 2u * key_scale, C4 = 4u * key_scale, C8 = 8u * key_scale;
     for (int t0 = 0; t0 < nT; t0 += MA_TILE) {
         const int cnt = min(MA_TILE, nT - t0);
         __syncthreads();
@@ -56,23 +80,7 @@ __global__ void __launch_bounds__(MA_THREADS) k_match_all(const uint8_t* __restr
             if (i & 1) upper |= v.z | v.w;
         }
         const bool tUpperZero = __syncthreads_or(upper != 0u) == 0;
-        if (qUpperZero && tUpperZero) {
-#pragma unroll 4
-            for (int j = 0; j < cnt; ++j) {
-                const uint4 a = tile[j][0];
-                const uint2 b = *reinterpret_cast<const uint2*>(&tile[j][1]);
-                const int d = __popc(q0.x ^ a.x) + __popc(q0.y ^ a.y) + __popc(q0.z ^ a.z) + __popc(q0.w ^ a.w) +
-                              __popc(q1.x ^ b.x) + __popc(q1.y ^ b.y);
-                if (d < best) {
-                    second = best;
-                    best = d;
-                    idx = t0 + j;
-                } else if (d < second) {
-                    second = d;
-                }
-            }
-        } else {
-#pragma unroll 4
+        if (!keyed) {
             for (int j = 0; j < cnt; ++j) {
                 const int d = hamming256(q0, q1, tile[j][0], tile[j][1]);
                 if (d < best) {
@@ -83,7 +91,50 @@ __global__ void __launch_bounds__(MA_THREADS) k_match_all(const uint8_t* __restr
                     second = d;
                 }
             }
+        } else if (qUpperZero && tUpperZero) {
+#pragma unroll 4
+            for (int j = 0; j < cnt; ++j) {
+                const uint4 a = tile[j][0];
+                const uint2 b = *reinterpret_cast<const uint2*>(&tile[j][1]);
+                const unsigned x0 = q0.x ^ a.x, x1 = q0.y ^ a.y, x2 = q0.z ^ a.z, x3 = q0.w ^ a.w, x4 = q1.x ^ b.x, x5 = q1.y ^ b.y;
+                const unsigned s1 = xor3(x0, x1, x2), c1 = maj3(x0, x1, x2);
+                const unsigned s2 = xor3(x3, x4, x5), c2 = maj3(x3, x4, x5);
+                const unsigned ones = s1 ^ s2, c3 = s1 & s2;
+                const unsigned twos = xor3(c1, c2, c3), fours = maj3(c1, c2, c3);
+                unsigned key = (unsigned)__popc(ones) * C1 + (unsigned)(t0 + j);
+                key = (unsigned)__popc(twos) * C2 + key;
+                key = (unsigned)__popc(fours) * C4 + key;
+                seck = min(seck, max(key, bestk));
+                bestk = min(bestk, key);
+            }
+        } else {
+#pragma unroll 4
+            for (int j = 0; j < cnt; ++j) {
+                const uint4 a = tile[j][0], b = tile[j][1];
+                const unsigned x0 = q0.x ^ a.x, x1 = q0.y ^ a.y, x2 = q0.z ^ a.z, x3 = q0.w ^ a.w;
+                const unsigned x4 = q1.x ^ b.x, x5 = q1.y ^ b.y, x6 = q1.z ^ b.z, x7 = q1.w ^ b.w;
+                const unsigned s1 = xor3(x0, x1, x2), c1 = maj3(x0, x1, x2);
+                const unsigned s2 = xor3(x3, x4, x5), c2 = maj3(x3, x4, x5);
+                const unsigned s3 = xor3(x6, x7, s1), c3 = maj3(x6, x7, s1);
+                const unsigned ones = s2 ^ s3, c4 = s2 & s3;
+                const unsigned t1 = xor3(c1, c2, c3), f1 = maj3(c1, c2, c3);
+                const unsigned twos = t1 ^ c4, f2 = t1 & c4;
+                const unsigned fours = f1 ^ f2, eights = f1 & f2;
+                unsigned key = (unsigned)__popc(ones) * C1 + (unsigned)(t0 + j);
+                key = (unsigned)__popc(twos) * C2 + key;
+                key = (unsigned)__popc(fours) * C4 + key;
+                key = (unsigned)__popc(eights) * C8 + key;
+                seck = min(seck, max(key, bestk));
+                bestk = min(bestk, key);
+            }
         }
+    }
+    if (keyed) {
+        if (bestk != 0xffffffffu) {
+            best = (int)(bestk >> 22);
+            idx = (int)(bestk & ((1u << 22) - 1u));
+        }
+        if (seck != 0xffffffffu) second = (int)(seck >> 22);
     }
     if (qi < nQ) {
         best_idx[p * out_stride + qi] = idx;
@@ -570,7 +621,7 @@ cudaError_t orbk_match_all(const uint8_t* q, const int* nq, size_t q_stride, con
                            size_t out_stride, cudaStream_t st) {
     if (npairs <= 0 || max_nq <= 0) return cudaSuccess;
     dim3 grid((max_nq + MA_THREADS - 1) / MA_THREADS, npairs);
-    k_match_all<<<grid, MA_THREADS, 0, st>>>(q, nq, q_stride, t, nt, t_stride, best_idx, best_dist, second_dist, out_stride);
+    k_match_all<<<grid, MA_THREADS, 0, st>>>(q, nq, q_stride, t, nt, t_stride, best_idx, best_dist, second_dist, out_stride, 1u << 22);
     orbk_count_launch(1);
     return cudaGetLastError();
 }
