@@ -106,6 +106,21 @@ def test_other_parameters():
         ex.close()
 
 
+def test_dense_quota_runs_describe_tiles_in_rounds():
+    # a quota far above the image's corner count keeps (nearly) every FAST candidate: describe tiles (160 x 96 positions)
+    # then hold many more than the 256 keypoints one round takes, and the kernel walks the kept lists slice by slice
+    rows, cols, nf = 240, 400, 30000
+    img = oracle.synth_frame(rows, cols, frame=21)
+    ko, do = oracle.extract(img, nfeatures=nf, cap=4 * nf)
+    ex = ORBextractor(nf, 1.2, 8, 20, 7)
+    kg, dg = ex(img)
+    info = compare(kg, dg, ko, do, tag="dense quota")
+    per_level = np.bincount(ko["octave"], minlength=8)
+    assert per_level[0] + per_level[1] > 2400, per_level   # levels 0 and 1 share 9 tiles: ~290 keypoints per tile
+    assert info["desc_bit_mismatch"] == 0
+    ex.close()
+
+
 def test_empty_and_error_shapes():
     from orb_slam_system_b200 import OrbError
     ex = ORBextractor(1000, 1.2, 8, 20, 7)
