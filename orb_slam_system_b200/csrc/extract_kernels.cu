@@ -93,31 +93,36 @@ __global__ void __launch_bounds__(256) k_resize4(const uint8_t* __restrict__ src
     const unsigned pw = (unsigned)spitch >> 2;
     const unsigned i0 = (unsigned)xg.x, i1 = min(i0 + 1u, pw - 1u), i2 = min(i0 + 2u, pw - 1u);
     const unsigned* S = reinterpret_cast<const unsigned*>(src + f * splane);
-    uint8_t* D = dst + f * dplane + 4 * g;
+    uint8_t* D = dst + f * dplane + 4 * g + (size_t)y0 * dpitch;
+    // Horizontal pass of one source row for the 4 columns: R = S[s] * a0 + S[s1] * a1 (A.2), one IDP.2A each.
+    auto hpass = [&](unsigned row, int (&r)[4]) {
+        const unsigned* R = S + row * pw;
+        const unsigned u0 = __ldg(R + i0), u1 = __ldg(R + i1), u2 = __ldg(R + i2);
+        const unsigned p0 = gather8(u0, u1, u2, (unsigned)xg.y, (unsigned)xg.w & 0xffffu);
+        const unsigned p1 = gather8(u0, u1, u2, (unsigned)xg.z, (unsigned)xg.w >> 16);
+        r[0] = (int)__dp2a_lo((unsigned)xc.x, p0, 0u);
+        r[1] = (int)__dp2a_hi((unsigned)xc.y, p0, 0u);
+        r[2] = (int)__dp2a_lo((unsigned)xc.z, p1, 0u);
+        r[3] = (int)__dp2a_hi((unsigned)xc.w, p1, 0u);
+    };
+    // (Reusing the horizontal sums of a source row shared by consecutive output rows was tried: the row-dependent branches
+    // keep the compiler from issuing all 24 loads of the thread up front, and the kernel, which waits on loads, got slower.)
 #pragma unroll
     for (int dy = 0; dy < 4; ++dy) {
         const int y = y0 + dy;
         if (y < drows) {
             const int yt = __ldg(ytab + y), yc = __ldg(ycoef + y);
-            const int b0 = yc & 0xffff, b1 = yc >> 16;
-            const unsigned* R0 = S + (unsigned)(yt & 0xffff) * pw;
-            const unsigned* R1 = S + (unsigned)(yt >> 16) * pw;
-            const unsigned u0 = __ldg(R0 + i0), u1 = __ldg(R0 + i1), u2 = __ldg(R0 + i2);
-            const unsigned v0 = __ldg(R1 + i0), v1 = __ldg(R1 + i1), v2 = __ldg(R1 + i2);
-            const unsigned p0 = gather8(u0, u1, u2, (unsigned)xg.y, (unsigned)xg.w & 0xffffu);
-            const unsigned p1 = gather8(u0, u1, u2, (unsigned)xg.z, (unsigned)xg.w >> 16);
-            const unsigned q0 = gather8(v0, v1, v2, (unsigned)xg.y, (unsigned)xg.w & 0xffffu);
-            const unsigned q1 = gather8(v0, v1, v2, (unsigned)xg.z, (unsigned)xg.w >> 16);
-            const int ra0 = (int)__dp2a_lo((unsigned)xc.x, p0, 0u), ra1 = (int)__dp2a_hi((unsigned)xc.y, p0, 0u);
-            const int ra2 = (int)__dp2a_lo((unsigned)xc.z, p1, 0u), ra3 = (int)__dp2a_hi((unsigned)xc.w, p1, 0u);
-            const int rb0 = (int)__dp2a_lo((unsigned)xc.x, q0, 0u), rb1 = (int)__dp2a_hi((unsigned)xc.y, q0, 0u);
-            const int rb2 = (int)__dp2a_lo((unsigned)xc.z, q1, 0u), rb3 = (int)__dp2a_hi((unsigned)xc.w, q1, 0u);
-            const unsigned o0 = (unsigned)((((b0 * (ra0 >> 4)) >> 16) + ((b1 * (rb0 >> 4)) >> 16) + 2) >> 2);
-            const unsigned o1 = (unsigned)((((b0 * (ra1 >> 4)) >> 16) + ((b1 * (rb1 >> 4)) >> 16) + 2) >> 2);
-            const unsigned o2 = (unsigned)((((b0 * (ra2 >> 4)) >> 16) + ((b1 * (rb2 >> 4)) >> 16) + 2) >> 2);
-            const unsigned o3 = (unsigned)((((b0 * (ra3 >> 4)) >> 16) + ((b1 * (rb3 >> 4)) >> 16) + 2) >> 2);
-            *reinterpret_cast<unsigned*>(D + (size_t)y * dpitch) = o0 | (o1 << 8) | (o2 << 16) | (o3 << 24);
+            // ((b * (R >> 4)) >> 16) as one multiply-high with b << 16
+            const unsigned b0 = (unsigned)(yc & 0xffff) << 16, b1 = (unsigned)(yc >> 16) << 16;
+            int ra[4], rb[4];
+            hpass((unsigned)(yt & 0xffff), ra);
+            hpass((unsigned)(yt >> 16), rb);
+            unsigned o[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) o[k] = (__umulhi(b0, (unsigned)ra[k] >> 4) + __umulhi(b1, (unsigned)rb[k] >> 4) + 2u) >> 2;
+            *reinterpret_cast<unsigned*>(D) = __byte_perm(__byte_perm(o[0], o[1], 0x0040), __byte_perm(o[2], o[3], 0x0040), 0x5410);
         }
+        D += dpitch;
     }
 }
 
