@@ -1257,6 +1257,7 @@ struct DescTileSmem {
     unsigned xy[DSC_LIST];        // x | y << 16, level coordinates
     unsigned resp[DSC_LIST];      // FAST response
     unsigned lo[DSC_LIST];        // level << 24 | output index
+    unsigned twin[DSC_LIST];      // 1 + output index of the same keypoint in the alias level's list (0: none)
     int m01[DSC_LIST], m10[DSC_LIST];
     float angle[DSC_LIST], ca[DSC_LIST], sb[DSC_LIST];
     int levels[ORB_MAX_LEVELS];   // levels whose keypoints live on this source's pixels,
@@ -1348,15 +1349,35 @@ __global__ void __launch_bounds__(DSC_THREADS, 4) k_describe_tile(const __grid_c
             const int base = sm.lvBase[j];
             const uint2* kept = L.kept + (size_t)f * L.kmax;
             const int r1 = sliced ? min(nK, sr0 + DSC_LIST) : nK;
+            // A level and its same-size alias (levels 0 and 1 of this fork: the scale table starts {1, 1, ...}) run
+            // their octrees on the same candidates; when both stop at the same depth their kept lists are equal entry by
+            // entry.  Rank r of the source level then also serves rank r of the alias (its "twin"): orientation and descriptor
+            // are computed once and written twice.  dup(r) is evaluated identically from both sides.
+            const bool twinSide = nLv > 1 && j < 2;
+            const uint2* other = nullptr;
+            int nOther = 0, twinBase = 0;
+            if (twinSide) {
+                const OrbLevel& Lo = plan.lv[sm.levels[1 - j]];
+                other = Lo.kept + (size_t)f * Lo.kmax;
+                nOther = sm.lvCount[1 - j];
+                twinBase = sm.lvBase[1];
+            }
             for (int r = (sliced ? sr0 : 0) + tid; r < r1; r += DSC_THREADS) {
                 const uint2 k = kept[r];
                 const unsigned x = k.x & 0xffffu, y = k.x >> 16;
                 if (x - xlo < (unsigned)DSC_W && y - ylo < (unsigned)DSC_H && base + r < cap) {
+                    bool dup = false;
+                    if (twinSide && r < nOther && twinBase + r < cap) {
+                        const uint2 ko = other[r];
+                        dup = ko.x == k.x && ko.y == k.y;
+                    }
+                    if (dup && j == 1) continue;  // served by the source level's entry
                     const int slot = atomicAdd(&sm.count, 1);
                     if (slot < DSC_LIST) {
                         sm.xy[slot] = k.x;
                         sm.resp[slot] = k.y;
                         sm.lo[slot] = ((unsigned)l << 24) | (unsigned)(base + r);
+                        sm.twin[slot] = dup ? (unsigned)(twinBase + r + 1) : 0u;
                     }
                 }
             }
@@ -1452,12 +1473,14 @@ __global__ void __launch_bounds__(DSC_THREADS, 4) k_describe_tile(const __grid_c
                         const unsigned t0 = lds_u8(pb + r0 * DSC_BOX_W + c0);
                         const unsigned t1 = lds_u8(pb + r1 * DSC_BOX_W + c1);
                         const unsigned wbits = __ballot_sync(0xffffffffu, t0 < t1);
-                        if (lane == wq) myWord = wbits;
+                        if ((lane & 7) == wq) myWord = wbits;
                     }
-                    const unsigned lo = sm.lo[i];
-                    const int o = (int)(lo & 0xffffffu), l = (int)(lo >> 24);
-                    if (lane < 8) reinterpret_cast<unsigned*>(desc + ((size_t)f * cap + o) * 32)[lane] = myWord;
-                    if (lane == 8) {
+                    const unsigned lo = sm.lo[i], twin = sm.twin[i];
+                    // lanes 0-7 / 16: descriptor and record of the keypoint; lanes 8-15 / 17: of its twin in the alias level
+                    const bool second = (lane & 8) || lane == 17;
+                    const int o = second ? (int)twin - 1 : (int)(lo & 0xffffffu), l = second ? sm.levels[1] : (int)(lo >> 24);
+                    if (lane < 16 && o >= 0) reinterpret_cast<unsigned*>(desc + ((size_t)f * cap + o) * 32)[lane & 7] = myWord;
+                    if ((lane == 16 || lane == 17) && o >= 0) {
                         const OrbLevel& L = plan.lv[l];
                         const float sc = l != 0 ? L.scale : 1.0f;  // keypoint.pt *= scale for level != 0 (:486-491)
                         orb_keypoint_dev kp;
