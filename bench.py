@@ -399,6 +399,9 @@ def main():
     for i in range(W):
         ex.wait_batch(submit(i))
     barrier()
+    sampler2 = ClockSampler(local_rank)
+    if rank == 0:
+        sampler2.start()
     t0 = time.perf_counter()
     pending = [submit(i) for i in range(min(DEPTH - 1, K))]
     for i in range(len(pending), K):
@@ -408,6 +411,7 @@ def main():
         ex.wait_batch(pending.pop(0))
     barrier()
     e2e_s = time.perf_counter() - t0
+    e2e_clocks = sampler2.stop() if rank == 0 else None
     maxc = int(h_counts.max().item())
     h2d = B * ROWS * COLS
     d2h = B * 4 + B * maxc * 28 + B * maxc * 32
@@ -537,7 +541,8 @@ def main():
                          "path": {"algo_bytes_per_step": path_bytes, "achieved": path_gbs, "frac": path_gbs / peak}},
             "e2e": {"value": frames / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "orb_extract_batch_submit/_wait, three 64-frame steps in flight, pinned host buffers",
-                    "sync_call_value": frames / e2e_sync_s, "sync_call_api": "orb_extract_batch, one step at a time"},
+                    "sync_call_value": frames / e2e_sync_s, "sync_call_api": "orb_extract_batch, one step at a time",
+                    "clocks": e2e_clocks},
             "gpu_launches": int(launches), "host_enqueue_ms_per_step": host_enqueue_ms, "clocks": clocks,
             "hamming": {"metric": "Hamming pairs/s (brute force, best + second best)", "value": world * NP * NQ * NQ / (match_ms * 1e-3),
                         "unit": "pairs/s", "workload": f"{NP} keyframe pairs x {NQ} x {NQ} descriptors per GPU (BASELINE config 4)",
