@@ -127,6 +127,81 @@ __global__ void __launch_bounds__(256) k_resize4(const uint8_t* __restrict__ src
 }
 
 // ------------------------------------------------------------------------------------------
+// k_resize_tile: k_resize4's arithmetic on a source tile staged in shared memory by one TMA box load.
+// k_resize4 waits on its global loads (each thread's 24 loads follow a table load); here one elected thread
+// issues the bulk copy of the 256 x RSZ_BOX_H source box while the others fetch their table entries, and the
+// gathers become shared-memory reads.  One CTA = RSZ_W x RSZ_H output pixels; thread = 4 columns x 4 rows.
+// The host checks (build_plan, rszTiled) that every tile's source words lie inside its box, whose x start is the
+// 16-byte aligned column of the tile's first gather word and whose y start is the tile's first source row.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count);
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes);
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity);
+__device__ __forceinline__ void tma_load_3d(unsigned dst, const CUtensorMap* map, int x, int y, int z, unsigned bar);
+__device__ __forceinline__ unsigned smem_u32(const void* p);
+
+__global__ void __launch_bounds__(RSZ_THREADS) k_resize_tile(const CUtensorMap* __restrict__ map, int frameBase, uint8_t* __restrict__ dst,
+                                                             int dpitch, unsigned long long dplane, int drows, int dcols,
+                                                             const int4* __restrict__ xgrp, const int4* __restrict__ xcoef4,
+                                                             const int* __restrict__ ytab, const int* __restrict__ ycoef) {
+    __shared__ __align__(128) unsigned box[RSZ_BOX_H][64];
+    __shared__ unsigned long long barMem;
+    const int tid = threadIdx.x, tg = tid % (RSZ_W / 4), tr = tid / (RSZ_W / 4);
+    const int ngroups = (dcols + 3) >> 2;
+    const int g0 = blockIdx.x * (RSZ_W / 4), Y0 = blockIdx.y * RSZ_H, f = blockIdx.z;
+    const int bx0 = (4 * __ldg(&xgrp[g0].x)) & ~15, by0 = __ldg(ytab + Y0) & 0xffff;
+    const unsigned bar = smem_u32(&barMem);
+    if (tid == 0) mbar_init(bar, 1);
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(bar, (unsigned)sizeof(box));
+        tma_load_3d(smem_u32(&box[0][0]), map, bx0, by0, f + frameBase, bar);
+    }
+    const int g = g0 + tg, y0 = Y0 + 4 * tr;
+    const bool live = g < ngroups && y0 < drows;
+    int4 xg = make_int4(0, 0, 0, 0), xc = xg;
+    int yt[4] = {0, 0, 0, 0}, yc[4] = {0, 0, 0, 0};
+    if (live) {
+        xg = __ldg(xgrp + g);
+        xc = __ldg(xcoef4 + g);
+#pragma unroll
+        for (int dy = 0; dy < 4; ++dy)
+            if (y0 + dy < drows) {
+                yt[dy] = __ldg(ytab + y0 + dy);
+                yc[dy] = __ldg(ycoef + y0 + dy);
+            }
+    }
+    mbar_wait(bar, 0);
+    if (!live) return;
+    const unsigned* B = &box[0][0] + (xg.x - (bx0 >> 2));
+    uint8_t* D = dst + f * dplane + 4 * g + (size_t)y0 * dpitch;
+    auto hpass = [&](int row, int (&r)[4]) {
+        const unsigned* R = B + (row - by0) * 64;
+        const unsigned u0 = R[0], u1 = R[1], u2 = R[2];
+        const unsigned p0 = gather8(u0, u1, u2, (unsigned)xg.y, (unsigned)xg.w & 0xffffu);
+        const unsigned p1 = gather8(u0, u1, u2, (unsigned)xg.z, (unsigned)xg.w >> 16);
+        r[0] = (int)__dp2a_lo((unsigned)xc.x, p0, 0u);
+        r[1] = (int)__dp2a_hi((unsigned)xc.y, p0, 0u);
+        r[2] = (int)__dp2a_lo((unsigned)xc.z, p1, 0u);
+        r[3] = (int)__dp2a_hi((unsigned)xc.w, p1, 0u);
+    };
+#pragma unroll
+    for (int dy = 0; dy < 4; ++dy) {
+        if (y0 + dy < drows) {
+            const unsigned b0 = (unsigned)(yc[dy] & 0xffff) << 16, b1 = (unsigned)(yc[dy] >> 16) << 16;
+            int ra[4], rb[4];
+            hpass(yt[dy] & 0xffff, ra);
+            hpass(yt[dy] >> 16, rb);
+            unsigned o[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) o[k] = (__umulhi(b0, (unsigned)ra[k] >> 4) + __umulhi(b1, (unsigned)rb[k] >> 4) + 2u) >> 2;
+            *reinterpret_cast<unsigned*>(D) = __byte_perm(__byte_perm(o[0], o[1], 0x0040), __byte_perm(o[2], o[3], 0x0040), 0x5410);
+        }
+        D += dpitch;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // k_detect: per-cell FAST-9/16 + cell-local NMS + iniTh/minTh retry.
 //
 // One CTA = one tile = `tileCells` FAST cells of one cell row of one level of one frame,
@@ -1702,7 +1777,11 @@ cudaError_t orbk_run_extract(const OrbPlan& plan, int nframes, orb_keypoint_dev*
         const OrbLevel& D = plan.lv[l];
         if (D.src != l) continue;
         const OrbLevel& S = plan.lv[plan.lv[l - 1].src];
-        if (D.xgrp) {
+        if (D.xgrp && D.rszTiled) {
+            dim3 grid((D.cols + RSZ_W - 1) / RSZ_W, (D.rows + RSZ_H - 1) / RSZ_H, nframes);
+            k_resize_tile<<<grid, RSZ_THREADS, 0, st>>>(&d_maps->rsz[l], plan.frameBase, D.img, D.pitch, D.plane, D.rows, D.cols, D.xgrp,
+                                                        D.xcoef4, D.ytab, D.ycoef);
+        } else if (D.xgrp) {
             dim3 block(64, 4), grid((D.cols + 255) / 256, (D.rows + 15) / 16, nframes);
             k_resize4<<<grid, block, 0, st>>>(S.img, S.pitch, S.plane, D.img, D.pitch, D.plane, D.rows, D.cols, D.xgrp,
                                               D.xcoef4, D.ytab, D.ycoef);

@@ -378,6 +378,21 @@ static int build_plan(orb_extractor* h, int rows, int cols) {
                 CUDA_TRY(cudaMemcpy(dxc4, xc4.data(), xc4.size() * sizeof(int4), cudaMemcpyHostToDevice));
                 L.xgrp = dxg;
                 L.xcoef4 = dxc4;
+                // k_resize_tile: does every output tile's source fit one 16-byte aligned 256 x RSZ_BOX_H box?
+                bool tiled = (S.pitch & 15) == 0;
+                for (int g0 = 0; g0 < ng && tiled; g0 += RSZ_W / 4) {
+                    const int g1 = std::min(ng, g0 + RSZ_W / 4) - 1;
+                    const int bx0 = (4 * xg[g0].x) & ~15;
+                    for (int g = g0; g <= g1; ++g)
+                        if (4 * xg[g].x < bx0 || 4 * (xg[g].x + 3) > bx0 + 256) tiled = false;  // words wb .. wb + 2 inside the box
+                }
+                for (int y0 = 0; y0 < L.rows && tiled; y0 += RSZ_H) {
+                    const int y1 = std::min(L.rows, y0 + RSZ_H) - 1;
+                    const int by0 = yt[y0] & 0xffff;
+                    for (int y = y0; y <= y1; ++y)
+                        if ((yt[y] & 0xffff) < by0 || (yt[y] >> 16) >= by0 + RSZ_BOX_H) tiled = false;
+                }
+                L.rszTiled = tiled ? 1 : 0;
             }
         }
     }
@@ -425,6 +440,10 @@ static int build_plan(orb_extractor* h, int rows, int cols) {
         const OrbLevel& L = P.lv[l];
         if (L.src != l) continue;
         if (L.nTiles > 0) CUDA_TRY(orbk_encode_level_map(&h->maps.m[l], L.img, L.cols, L.rows, B, L.pitch, L.plane, DET_TILE_W, L.boxH));
+        if (l > 0 && L.rszTiled) {
+            const OrbLevel& S = P.lv[P.lv[l - 1].src];
+            CUDA_TRY(orbk_encode_level_map(&h->maps.rsz[l], S.img, S.cols, S.rows, B, S.pitch, S.plane, 256, RSZ_BOX_H));
+        }
         if (L.dTiles > 0) {
             CUDA_TRY(orbk_encode_level_map(&h->maps.raw[l], L.img, L.cols, L.rows, B, L.pitch, L.plane, DSC_BOX_W, DSC_BOX_H));
             CUDA_TRY(orbk_encode_level_map(&h->maps.blur[l], L.blur, L.cols, L.rows, B, L.pitch, L.plane, DSC_BOX_W, DSC_BOX_H));
@@ -639,12 +658,17 @@ static int extract_device_impl(orb_extractor* h, int n, const uint8_t* d_imgs, i
         // same layout as the internal level-0 buffer: read the caller's frames in place
         for (int l = 0; l < P.nlevels; ++l)
             if (P.lv[l].src == 0) P.lv[l].img = const_cast<uint8_t*>(d_imgs);
-        if (h->user_base != d_imgs && (P.lv[0].nTiles > 0 || P.lv[0].dTiles > 0)) {
+        if (h->user_base != d_imgs) {
             const OrbLevel& L0 = P.lv[0];
             if (L0.nTiles > 0)
                 CUDA_TRY(orbk_encode_level_map(&h->maps_user.m[0], d_imgs, L0.cols, L0.rows, n, L0.pitch, L0.plane, DET_TILE_W, L0.boxH));
             if (L0.dTiles > 0)
                 CUDA_TRY(orbk_encode_level_map(&h->maps_user.raw[0], d_imgs, L0.cols, L0.rows, n, L0.pitch, L0.plane, DSC_BOX_W, DSC_BOX_H));
+            for (int l = 1; l < P.nlevels; ++l)  // the level(s) resized from level 0
+                if (P.lv[l].src == l && P.lv[l].rszTiled && P.lv[l - 1].src == 0) {
+                    CUDA_TRY(orbk_encode_level_map(&h->maps_user.rsz[l], d_imgs, L0.cols, L0.rows, n, L0.pitch, L0.plane, 256, RSZ_BOX_H));
+                    CUDA_TRY(cudaMemcpyAsync(&h->d_maps_user->rsz[l], &h->maps_user.rsz[l], sizeof(CUtensorMap), cudaMemcpyHostToDevice, h->stream));
+                }
             // stream-ordered update of the device copy (pageable source: staged before the call returns)
             CUDA_TRY(cudaMemcpyAsync(&h->d_maps_user->m[0], &h->maps_user.m[0], sizeof(CUtensorMap), cudaMemcpyHostToDevice, h->stream));
             CUDA_TRY(cudaMemcpyAsync(&h->d_maps_user->raw[0], &h->maps_user.raw[0], sizeof(CUtensorMap), cudaMemcpyHostToDevice, h->stream));

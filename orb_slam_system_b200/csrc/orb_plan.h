@@ -19,6 +19,12 @@
 #define DET_SP 272           // smem pitch of the image tile (bytes)
 #define DET_THREADS 256
 
+// resize tile: RSZ_W x RSZ_H output pixels of level l from a 256 x RSZ_BOX_H box of level l-1 staged by TMA
+#define RSZ_W 192
+#define RSZ_H 32
+#define RSZ_BOX_H 48
+#define RSZ_THREADS ((RSZ_W / 4) * (RSZ_H / 4))
+
 // describe tile: keypoints whose level position lies in a DSC_W x DSC_H core; the raw and the blurred level are
 // staged with an 18-px halo (the rBRIEF pattern reaches 18 px after rotation, IC_Angle 15) by one TMA box each,
 // one after the other into the same shared-memory buffer.
@@ -48,6 +54,7 @@ struct OrbLevel {
     const int* ycoef;        // [rows] packed: b0 | b1<<16
     const int4* xgrp;        // [ceil(cols/4)] k_resize4 gather descriptors (null: use k_resize)
     const int4* xcoef4;      // [ceil(cols/4)] a0 | a1<<16 of the 4 columns of a group
+    int rszTiled;            // every RSZ_W x RSZ_H output tile's source pixels fit one 256 x RSZ_BOX_H TMA box (k_resize_tile)
     // FAST cell grid over [16, cols-16) x [16, rows-16)
     int W, H;                // maxBorder - minBorder
     int nCols, nRows, wCell, hCell;  // 0 cells when the level is smaller than one cell
