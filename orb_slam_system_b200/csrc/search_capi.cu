@@ -564,7 +564,9 @@ struct orb_vocabulary {
     // grow-only scratch for the features and the per-feature results
     uint8_t* d_feat = nullptr;
     int* d_out = nullptr;
+    int* h_out = nullptr;  // pinned landing buffer of the per-feature results (2 ints per feature)
     size_t cap = 0;
+    std::vector<unsigned long long> keys;  // host assembly scratch
 };
 
 extern "C" void orb_vocabulary_destroy(orb_vocabulary* v) {
@@ -576,6 +578,7 @@ extern "C" void orb_vocabulary_destroy(orb_vocabulary* v) {
     cudaFree(v->d_desc);
     cudaFree(v->d_feat);
     cudaFree(v->d_out);
+    if (v->h_out) cudaFreeHost(v->h_out);
     if (v->stream) cudaStreamDestroy(v->stream);
     delete v;
 }
@@ -661,26 +664,33 @@ extern "C" int orb_vocabulary_transform(orb_vocabulary* v, const uint8_t* desc, 
         CUDA_TRY(cudaStreamSynchronize(v->stream));
         cudaFree(v->d_feat);
         cudaFree(v->d_out);
+        if (v->h_out) cudaFreeHost(v->h_out);
         v->d_feat = nullptr;
         v->d_out = nullptr;
+        v->h_out = nullptr;
         v->cap = 0;
         const size_t want = (size_t)n + (size_t)n / 4 + 64;
         CUDA_TRY(cudaMalloc((void**)&v->d_feat, want * 32));
         CUDA_TRY(cudaMalloc((void**)&v->d_out, want * 2 * sizeof(int)));
+        CUDA_TRY(cudaMallocHost((void**)&v->h_out, want * 2 * sizeof(int)));
         v->cap = want;
     }
-    std::vector<int32_t> leaf((size_t)n), nid((size_t)n);
     CUDA_TRY(cudaMemcpyAsync(v->d_feat, desc, (size_t)n * 32, cudaMemcpyHostToDevice, v->stream));
     CUDA_TRY(orbk_voc_descent(v->d_feat, n, v->d_child_off, v->d_children, v->d_desc, v->depth_l - levelsup, v->d_out, v->d_out + n, v->stream));
-    CUDA_TRY(cudaMemcpyAsync(leaf.data(), v->d_out, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, v->stream));
-    CUDA_TRY(cudaMemcpyAsync(nid.data(), v->d_out + n, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, v->stream));
+    CUDA_TRY(cudaMemcpyAsync(v->h_out, v->d_out, sizeof(int) * 2 * (size_t)n, cudaMemcpyDeviceToHost, v->stream));
     CUDA_TRY(cudaStreamSynchronize(v->stream));
-    // ---- the two maps, in feature order (:1143-1180)
+    const int32_t* leaf = v->h_out;
+    const int32_t* nid = v->h_out + n;
+    // ---- the two maps (:1143-1180).  The reference fills two std::maps feature by feature; the same contents come
+    // out of sorting (key, feature index) pairs: a word's BoW value is its node weight added once per occurrence (every
+    // occurrence adds the same double, so the sum does not depend on the order), a node's feature list is in ascending
+    // feature index.
     const bool tf = v->weighting == ORB_VOC_TF_IDF || v->weighting == ORB_VOC_TF;
     const bool must = v->scoring != ORB_VOC_DOT_PRODUCT;       // ScoringObject.h:74-89
     const bool l2 = v->scoring == ORB_VOC_L2_NORM;
-    std::map<int32_t, double> bow;                              // BowVector
-    std::map<int32_t, std::vector<int32_t>> fvec;               // FeatureVector
+    std::vector<unsigned long long>& keys = v->keys;
+    keys.clear();
+    keys.reserve(2 * (size_t)n);
     for (int i = 0; i < n; ++i) {
         const int32_t id = v->word[leaf[i]];
         const double w = v->weight[leaf[i]];
@@ -689,47 +699,66 @@ extern "C" int orb_vocabulary_transform(orb_vocabulary* v, const uint8_t* desc, 
         if (w > 0) {  // not stopped
             if (nid[i] < 0)
                 return orb_fail(ORB_ERR_SHAPE, "feature %d reaches a leaf above level L - levelsup (the reference stores an unset node id)", i);
-            auto it = bow.lower_bound(id);
-            if (it != bow.end() && it->first == id) {
-                if (tf) it->second += w;  // addWeight; addIfNotExist leaves an existing entry alone
-            } else {
-                bow.insert(it, std::make_pair(id, w));
-            }
-            fvec[nid[i]].push_back(i);
+            keys.push_back(((unsigned long long)(unsigned)id << 32) | (unsigned)i);
         }
     }
-    if (tf && !bow.empty() && !must) {  // :1159-1165
-        const double nd = (double)bow.size();
-        for (auto& e : bow) e.second /= nd;
+    const size_t m = keys.size();  // features that count
+    for (size_t k = 0; k < m; ++k) keys.push_back(((unsigned long long)(unsigned)nid[(int)(keys[k] & 0xffffffffu)] << 32) | (keys[k] & 0xffffffffu));
+    std::sort(keys.begin(), keys.begin() + m);
+    std::sort(keys.begin() + m, keys.end());
+    // distinct words / nodes
+    int nb = 0, nf = 0;
+    for (size_t k = 0; k < m; ++k) {
+        nb += k == 0 || (keys[k] >> 32) != (keys[k - 1] >> 32);
+        nf += k == 0 || (keys[m + k] >> 32) != (keys[m + k - 1] >> 32);
+    }
+    *bow_n = nb;
+    *fv_n = nf;
+    if (nb > bow_cap || nf > fv_cap) return orb_fail(ORB_ERR_CAPACITY, "needs %d BoW entries and %d feature-vector nodes", nb, nf);
+    if ((nb && (!bow_ids || !bow_values)) || !fv_off || (nf && (!fv_nodes || !fv_idx))) return orb_fail(ORB_ERR_INVALID, "null output arrays");
+    // BowVector: addWeight / addIfNotExist per occurrence, in ascending word id
+    {
+        int k = -1;
+        for (size_t j = 0; j < m; ++j) {
+            const int32_t id = (int32_t)(keys[j] >> 32);
+            const double w = v->weight[leaf[(int)(keys[j] & 0xffffffffu)]];
+            if (k < 0 || bow_ids[k] != id) {
+                ++k;
+                bow_ids[k] = id;
+                bow_values[k] = w;
+            } else if (tf) {
+                bow_values[k] += w;  // addWeight; addIfNotExist leaves an existing entry alone
+            }
+        }
+    }
+    if (tf && nb > 0 && !must) {  // :1159-1165
+        const double nd = (double)nb;
+        for (int k = 0; k < nb; ++k) bow_values[k] /= nd;
     }
     if (must) {  // BowVector::normalize, BowVector.cpp:62-84
         double norm = 0.0;
         if (!l2) {
-            for (auto& e : bow) norm += fabs(e.second);
+            for (int k = 0; k < nb; ++k) norm += fabs(bow_values[k]);
         } else {
-            for (auto& e : bow) norm += e.second * e.second;
+            for (int k = 0; k < nb; ++k) norm += bow_values[k] * bow_values[k];
             norm = sqrt(norm);
         }
         if (norm > 0.0)
-            for (auto& e : bow) e.second /= norm;
+            for (int k = 0; k < nb; ++k) bow_values[k] /= norm;
     }
-    *bow_n = (int)bow.size();
-    *fv_n = (int)fvec.size();
-    if (*bow_n > bow_cap || *fv_n > fv_cap) return orb_fail(ORB_ERR_CAPACITY, "needs %d BoW entries and %d feature-vector nodes", *bow_n, *fv_n);
-    if ((*bow_n && (!bow_ids || !bow_values)) || !fv_off || (*fv_n && (!fv_nodes || !fv_idx))) return orb_fail(ORB_ERR_INVALID, "null output arrays");
-    int k = 0;
-    for (auto& e : bow) {
-        bow_ids[k] = e.first;
-        bow_values[k] = e.second;
-        ++k;
-    }
-    k = 0;
-    int c = 0;
-    fv_off[0] = 0;
-    for (auto& e : fvec) {
-        fv_nodes[k] = e.first;
-        for (int32_t idx : e.second) fv_idx[c++] = idx;
-        fv_off[++k] = c;
+    // FeatureVector: node -> feature indices, ascending
+    {
+        int k = -1;
+        fv_off[0] = 0;
+        for (size_t j = 0; j < m; ++j) {
+            const int32_t node = (int32_t)(keys[m + j] >> 32);
+            if (k < 0 || fv_nodes[k] != node) {
+                ++k;
+                fv_nodes[k] = node;
+            }
+            fv_idx[j] = (int32_t)(keys[m + j] & 0xffffffffu);
+            fv_off[k + 1] = (int)j + 1;
+        }
     }
     return ORB_OK;
 }
