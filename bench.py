@@ -40,6 +40,23 @@ def measured_peaks():
     return 6650.0, "fallback"
 
 
+def pin_to_gpu_numa_node(index):
+    """Run this rank on the CPUs NVML lists as local to its GPU, so that the pinned host buffers (first touch) and the
+    thread that feeds the copy engines sit on the GPU's own NUMA node.  Best effort: any failure leaves the affinity alone."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, mask in enumerate(words) for b in range(64) if (int(mask) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+    except Exception:
+        pass
+
+
 class ClockSampler:
     """SM clock and throttle reasons sampled through NVML every few milliseconds while the timed
     regions run (same counters as `nvidia-smi --query-gpu=clocks.sm,clocks_event_reasons.*`)."""
@@ -319,6 +336,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    pin_to_gpu_numa_node(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -565,6 +583,9 @@ def main():
                         "hbm_frac": NP * (32 * 2 * NQ + 12 * NQ) / (match_ms * 1e-3) / 1e9 / peak,
                         "popc_per_s": world * 3 * NP * NQ * NQ / (match_ms * 1e-3),
                         "logic_ops_per_s": world * 19 * NP * NQ * NQ / (match_ms * 1e-3),
+                        # pipe peaks per GPU from tools/probes/pipe_probe: POPC 16, LOP3 / VIMNMX 64 lanes per clock and SM
+                        "popc_pipe_frac": 3 * NP * NQ * NQ / (match_ms * 1e-3) / (16 * 148 * 1.965e9),
+                        "logic_pipe_frac": 19 * NP * NQ * NQ / (match_ms * 1e-3) / (64 * 148 * 1.965e9),
                         "note": "logic-pipe bound: the 6 live XOR words of a pair (words 6-7 of this fork's descriptors are zero, checked on "
                                 "the data; 8 otherwise) go through a LOP3 carry-save tree to 3 POPC instead of 6, ~19 logic-pipe "
                                 "instructions per pair against a pipe rate of 64 lanes/clk/SM = 0.97e12 pairs/s per GPU"},
