@@ -16,6 +16,32 @@
 
 static unsigned long long g_launches = 0;
 
+// Programmatic dependent launch: a kernel launched with launch_pdl may be scheduled while its predecessor in the stream is
+// still draining; it calls pdl_enter() before touching anything the predecessor wrote (griddepcontrol.wait returns once
+// the predecessor grid has completed and its writes are visible) and, by issuing launch_dependents right away, lets its
+// own successor do the same.  The launch latency of the dependent chains (six pyramid levels, detect -> octree -> describe)
+// then overlaps the tail of the previous kernel.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_release() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter() {
+    pdl_wait();
+    pdl_release();
+}
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ------------------------------------------------------------------------------------------
 // small helpers
 // ------------------------------------------------------------------------------------------
@@ -41,6 +67,7 @@ __global__ void __launch_bounds__(256) k_resize(const uint8_t* __restrict__ src,
                                                 int dpitch, unsigned long long dplane, int drows, int dcols,
                                                 const int* __restrict__ xtab, const int* __restrict__ xcoef,
                                                 const int* __restrict__ ytab, const int* __restrict__ ycoef) {
+    pdl_enter();
     const int x4 = (blockIdx.x * 64 + threadIdx.x) * 4;
     const int y = blockIdx.y * 4 + threadIdx.y;
     if (x4 >= dcols || y >= drows) return;
@@ -83,6 +110,7 @@ __global__ void __launch_bounds__(256) k_resize4(const uint8_t* __restrict__ src
                                                  uint8_t* __restrict__ dst, int dpitch, unsigned long long dplane, int drows,
                                                  int dcols, const int4* __restrict__ xgrp, const int4* __restrict__ xcoef4,
                                                  const int* __restrict__ ytab, const int* __restrict__ ycoef) {
+    pdl_enter();
     const int g = blockIdx.x * 64 + threadIdx.x;
     const int ngroups = (dcols + 3) >> 2;
     const int y0 = (blockIdx.y * 4 + threadIdx.y) * 4;
@@ -144,6 +172,7 @@ __global__ void __launch_bounds__(RSZ_THREADS) k_resize_tile(const CUtensorMap* 
                                                              int dpitch, unsigned long long dplane, int drows, int dcols,
                                                              const int4* __restrict__ xgrp, const int4* __restrict__ xcoef4,
                                                              const int* __restrict__ ytab, const int* __restrict__ ycoef) {
+    pdl_release();  // the tables read below are static; the source level is first touched by the TMA load
     __shared__ __align__(128) unsigned box[RSZ_BOX_H][64];
     __shared__ unsigned long long barMem;
     const int tid = threadIdx.x, tg = tid % (RSZ_W / 4), tr = tid / (RSZ_W / 4);
@@ -154,6 +183,7 @@ __global__ void __launch_bounds__(RSZ_THREADS) k_resize_tile(const CUtensorMap* 
     if (tid == 0) mbar_init(bar, 1);
     __syncthreads();
     if (tid == 0) {
+        pdl_wait();  // the previous level is complete and visible
         mbar_expect_tx(bar, (unsigned)sizeof(box));
         tma_load_3d(smem_u32(&box[0][0]), map, bx0, by0, f + frameBase, bar);
     }
@@ -330,6 +360,7 @@ __device__ __forceinline__ unsigned odd_lanes(unsigned w) { return __byte_perm(w
 
 __global__ void __launch_bounds__(DET_THREADS) k_detect(const __grid_constant__ OrbPlan plan,
                                                         const CUtensorMap* __restrict__ maps) {
+    pdl_release();  // nothing before the TMA load below depends on the pyramid kernels
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int detRows = plan.detRows;
     unsigned (*E)[DET_EP] = reinterpret_cast<unsigned (*)[DET_EP]>(smem_raw);
@@ -373,6 +404,7 @@ __global__ void __launch_bounds__(DET_THREADS) k_detect(const __grid_constant__ 
     if (tid == 0) mbar_init(bar, 1);
     __syncthreads();
     if (tid == 0) {
+        pdl_wait();  // the level is complete and visible
         mbar_expect_tx(bar, (unsigned)(DET_TILE_W * L.boxH));
         tma_load_3d(smem_u32(stage), maps + l, X0 - (X0 & 15), Y0, f + plan.frameBase, bar);
     }
@@ -738,6 +770,7 @@ struct OctFastSmem {
 };
 
 __global__ void __launch_bounds__(OCTF_THREADS) k_octree_fast(const __grid_constant__ OrbPlan plan) {
+    pdl_enter();
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     OctFastSmem& sm = *reinterpret_cast<OctFastSmem*>(smem_raw);
     const int lt = blockIdx.x, f = blockIdx.y, tid = threadIdx.x;
@@ -908,6 +941,7 @@ __global__ void __launch_bounds__(OCTF_THREADS) k_octree_fast(const __grid_const
 // (level, frame) problems k_octree_fast flagged.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(OCT_THREADS) k_octree(const __grid_constant__ OrbPlan plan) {
+    pdl_enter();
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned long long* smA = reinterpret_cast<unsigned long long*>(smem_raw);
     unsigned long long* smB = smA + OCT_SMEM_A;
@@ -1113,6 +1147,7 @@ __device__ __forceinline__ int reflect101(int p, int n) {
 }
 
 __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ OrbPlan plan) {
+    pdl_enter();
     __shared__ __align__(16) unsigned tile[BLUR_TH + 6][BLUR_SW];
     const int f = blockIdx.y;
     int t = blockIdx.x, l = 0;
@@ -1357,6 +1392,7 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __global__ void __launch_bounds__(DSC_THREADS, 4) k_describe_tile(const __grid_constant__ OrbPlan plan, const DetectMaps* __restrict__ maps,
                                                                   orb_keypoint_dev* __restrict__ kps, uint8_t* __restrict__ desc,
                                                                   int cap, int* __restrict__ counts) {
+    pdl_enter();
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const unsigned char* tileT = smem_raw;  // the raw tile (phase 1), then the blurred tile (phase 3)
     DescTileSmem& sm = *reinterpret_cast<DescTileSmem*>(smem_raw + kDescTileBytes);
@@ -1675,6 +1711,7 @@ __global__ void __launch_bounds__(256) k_ingest(const uint8_t* __restrict__ raw,
                                                 int channels, int bgr, int variant, const float* __restrict__ mapx,
                                                 const float* __restrict__ mapy, int drows, int dcols, uint8_t* __restrict__ dst,
                                                 int dpitch, unsigned long long dplane) {
+    pdl_enter();
     const int x4 = (blockIdx.x * 64 + threadIdx.x) * 4, y = blockIdx.y * 4 + threadIdx.y, f = blockIdx.z;
     if (x4 >= dcols || y >= drows) return;
     const uint8_t* S = raw + (size_t)f * sframe;
@@ -1702,6 +1739,7 @@ cudaError_t orbk_ingest(const uint8_t* raw, int nframes, int srows, int scols, s
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_repitch(const uint8_t* __restrict__ dense, int rows, int cols, uint8_t* __restrict__ dst,
                                                  int pitch, unsigned long long plane) {
+    pdl_enter();
     const int k = blockIdx.x * 256 + threadIdx.x;  // output word in the row
     const int y = blockIdx.y, f = blockIdx.z;
     if (4 * k >= cols) return;
@@ -1779,8 +1817,8 @@ cudaError_t orbk_run_extract(const OrbPlan& plan, int nframes, orb_keypoint_dev*
         const OrbLevel& S = plan.lv[plan.lv[l - 1].src];
         if (D.xgrp && D.rszTiled) {
             dim3 grid((D.cols + RSZ_W - 1) / RSZ_W, (D.rows + RSZ_H - 1) / RSZ_H, nframes);
-            k_resize_tile<<<grid, RSZ_THREADS, 0, st>>>(&d_maps->rsz[l], plan.frameBase, D.img, D.pitch, D.plane, D.rows, D.cols, D.xgrp,
-                                                        D.xcoef4, D.ytab, D.ycoef);
+            launch_pdl(k_resize_tile, grid, dim3(RSZ_THREADS), 0, st, &d_maps->rsz[l], plan.frameBase, D.img, D.pitch, D.plane, D.rows, D.cols,
+                       D.xgrp, D.xcoef4, D.ytab, D.ycoef);
         } else if (D.xgrp) {
             dim3 block(64, 4), grid((D.cols + 255) / 256, (D.rows + 15) / 16, nframes);
             k_resize4<<<grid, block, 0, st>>>(S.img, S.pitch, S.plane, D.img, D.pitch, D.plane, D.rows, D.cols, D.xgrp,
@@ -1809,12 +1847,12 @@ cudaError_t orbk_run_extract(const OrbPlan& plan, int nframes, orb_keypoint_dev*
         if (e != cudaSuccess) return e;
     }
     if (plan.totalTiles > 0) {
-        k_detect<<<dim3(plan.totalTiles, nframes), DET_THREADS, detect_smem_bytes(plan.detRows), st>>>(plan, d_maps->m);
+        launch_pdl(k_detect, dim3(plan.totalTiles, nframes), dim3(DET_THREADS), detect_smem_bytes(plan.detRows), st, plan, d_maps->m);
         ++g_launches;
     }
     if (ev) cudaEventRecord(ev[2], st);
-    k_octree_fast<<<dim3(plan.nlevels, nframes), OCTF_THREADS, kOctFastSmem, st>>>(plan);
-    k_octree<<<dim3(plan.nlevels, nframes), OCT_THREADS, kOctreeSmem, st>>>(plan);
+    launch_pdl(k_octree_fast, dim3(plan.nlevels, nframes), dim3(OCTF_THREADS), kOctFastSmem, st, plan);
+    launch_pdl(k_octree, dim3(plan.nlevels, nframes), dim3(OCT_THREADS), kOctreeSmem, st, plan);
     g_launches += 2;
     if (ev) {
         // profiling: stages back to back on one stream, blur after the octree
@@ -1830,7 +1868,8 @@ cudaError_t orbk_run_extract(const OrbPlan& plan, int nframes, orb_keypoint_dev*
         e = cudaStreamWaitEvent(st, ss.join, 0);
         if (e != cudaSuccess) return e;
     }
-    k_describe_tile<<<dim3(std::max(1, plan.totalDescTiles), nframes), DSC_THREADS, kDescSmem, st>>>(plan, d_maps, d_kps, d_desc, cap, d_counts);
+    launch_pdl(k_describe_tile, dim3(std::max(1, plan.totalDescTiles), nframes), dim3(DSC_THREADS), kDescSmem, st, plan, d_maps, d_kps, d_desc, cap,
+               d_counts);
     ++g_launches;
     if (ev) cudaEventRecord(ev[5], st);
     return cudaGetLastError();
