@@ -210,3 +210,38 @@ def test_stage_profiling_counts_calls():
     assert set(times) == {"pyramid", "detect", "octree", "blur", "describe"} and all(v > 0 for v in times.values())
     ex.set_profiling(False)
     ex.close()
+
+
+def test_random_shapes_and_parameters():
+    # a seeded sweep over shapes that move every tiling boundary (TMA boxes of the detect / resize / describe tiles,
+    # blur vector edges, cells per tile) and over extractor parameters; shapes the reference faults on must give the
+    # same verdict from both sides
+    from orb_slam_system_b200 import OrbError
+    rng = np.random.default_rng(20261018)
+    checked = 0
+    for it in range(32):
+        rows = int(rng.integers(70, 420))
+        cols = rows + int(rng.integers(10, 600)) if it % 7 != 6 else int(rng.integers(60, rows + 1))  # mostly landscape
+        nf = int(rng.choice([200, 500, 1000, 3000]))
+        sf = float(rng.choice([1.2, 1.2, 1.1, 1.3, 1.5, 2.0]))
+        nl = int(rng.integers(1, 9))
+        ini, mn = int(rng.choice([20, 30, 12])), int(rng.choice([7, 5, 12]))
+        img = oracle.synth_frame(rows, cols, frame=100 + it, variant=int(it % 3 == 0))
+        try:
+            ko, do = oracle.extract(img, nfeatures=nf, scaleFactor=sf, nlevels=nl, iniThFAST=ini, minThFAST=mn, cap=16 * nf)
+            ref_ok = True
+        except Exception:
+            ref_ok = False
+        try:
+            ex = ORBextractor(nf, sf, nl, ini, mn)
+            kg, dg = ex(img)
+            ex.close()
+            got_ok = True
+        except OrbError:
+            got_ok = False
+        assert ref_ok == got_ok, f"case {it} {rows}x{cols} sf={sf} nl={nl}: oracle ok={ref_ok}, gpu ok={got_ok}"
+        if ref_ok:
+            info = compare(kg, dg, ko, do, tag=f"case {it} {rows}x{cols} nf={nf} sf={sf} nl={nl} th={ini}/{mn}")
+            assert info["desc_bit_mismatch"] == 0, info
+            checked += 1
+    assert checked >= 18
