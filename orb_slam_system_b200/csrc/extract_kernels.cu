@@ -321,6 +321,13 @@ __device__ __forceinline__ void minmax_fma(unsigned a, unsigned b, unsigned& lo,
     asm("sub.f16x2 %0, %1, %2;" : "=r"(lo) : "r"(a), "r"(d));
 }
 
+// Per 16-bit lane: 0xffff where a > b, else 0 (lanes hold small non-negative integers = fp16 subnormals; HSET2.BM).
+__device__ __forceinline__ unsigned gt_mask2(unsigned a, unsigned b) {
+    unsigned r;
+    asm("set.gt.u32.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+}
+
 __device__ __forceinline__ void fast_score_pairs(const unsigned (&r)[16], unsigned c2, unsigned low2,
                                                  unsigned neglow2, unsigned& u) {
     // A = min over the 16 arcs of 9 contiguous ring pixels of the arc's maximum, B = max over arcs of the arc's
@@ -347,11 +354,14 @@ __device__ __forceinline__ void fast_score_pairs(const unsigned (&r)[16], unsign
     }
     const unsigned A = __vminu2(vmin3(tA[0], tA[1], tA[2]), vmin3(vmin3(tA[3], tA[4], tA[5]), tA[6], tA[7]));
     const unsigned B = __vmaxu2(vmax3(tB[0], tB[1], tB[2]), vmax3(vmax3(tB[3], tB[4], tB[5]), tB[6], tB[7]));
-    // m = max(c - A, B - c) per signed 16-bit lane; u = max(m, low) - low
-    const unsigned d1 = __vsub2(c2, A);
-    const unsigned d2 = __vsub2(B, c2);
-    const unsigned m = __vmaxs2(d1, d2);
-    u = __vadd2(__vmaxs2(m, low2), neglow2);
+    // m = max(c - A, B - c); u = max(m, low) - low = sat(max(sat(c - A), sat(B - c)) - low) for low >= 0: the
+    // saturating differences are HADD2.SAT on the FMA pipe (fp16 subnormal lanes, exact), one VIMNMX joins them
+    unsigned d1, d2;
+    asm("sub.sat.f16x2 %0, %1, %2;" : "=r"(d1) : "r"(c2), "r"(A));
+    asm("sub.sat.f16x2 %0, %1, %2;" : "=r"(d2) : "r"(B), "r"(c2));
+    const unsigned m = __vmaxu2(d1, d2);
+    asm("sub.sat.f16x2 %0, %1, %2;" : "=r"(u) : "r"(m), "r"(low2));
+    (void)neglow2;
 }
 
 // bytes 0 and 2 / bytes 1 and 3 of a word as two zero-extended 16-bit lanes
@@ -565,9 +575,8 @@ __global__ void __launch_bounds__(DET_THREADS) k_detect(const __grid_constant__ 
                 const unsigned Lo = vBe & mLo;
                 const unsigned Ro = __byte_perm(vBe, vCe, 0x5432) & mRo;
                 const unsigned nbE = vmax3(Le, Re, vCenE), nbO = vmax3(Lo, Ro, vCenO);
-                // keep u where u > nb: t = u - min(u, nb) is non-zero exactly there
-                const unsigned tE = midBe - __vminu2(midBe, nbE), tO = midBo - __vminu2(midBo, nbO);
-                const unsigned kE = __vminu2(tE, 0x00010001u) * 0xffu, kO = __vminu2(tO, 0x00010001u) * 0xffu;
+                // keep u where u > nb: one packed fp16 compare per lane pair (the lanes hold 0..255, exact as subnormals)
+                const unsigned kE = gt_mask2(midBe, nbE), kO = gt_mask2(midBo, nbO);
                 const unsigned outw = active ? ((midBe & kE) | ((midBo & kO) << 8)) : 0u;
                 const unsigned nz = __ballot_sync(0xffffffffu, outw != 0u);
                 if (outw) {  // this warp's private list region: no atomics
