@@ -1144,10 +1144,12 @@ __global__ void __launch_bounds__(OCT_THREADS) k_octree(const __grid_constant__ 
 // IDP.4A per pixel on byte windows cut from three aligned words, the vertical pass runs on a
 // 7-row register window.  Exact integers throughout, one 32-bit store per 4 pixels.
 // ------------------------------------------------------------------------------------------
-#define BLUR_TW 256
+#define BLUR_TW 224                    // output columns per tile: 16 + 224 + 3 halo columns fit the 256-byte TMA box
 #define BLUR_TH 64
 #define BLUR_RPT 16                    // output rows per thread
-#define BLUR_SW ((BLUR_TW + 32) / 4)   // smem words per row: 16-byte left pad + tile + 16-byte right halo
+#define BLUR_SW 64                     // smem words per row = the box: 16 bytes left of the tile, the tile, right halo
+#define BLUR_BOX_H (BLUR_TH + 6)
+#define BLUR_THREADS ((BLUR_TW / 4) * (BLUR_TH / BLUR_RPT))
 
 __device__ __forceinline__ int reflect101(int p, int n) {
     if (n == 1) return 0;
@@ -1155,9 +1157,13 @@ __device__ __forceinline__ int reflect101(int p, int n) {
     return p;
 }
 
-__global__ void __launch_bounds__(256) k_blur(const __grid_constant__ OrbPlan plan) {
+// The tile with its 3-pixel halo is one TMA box load (box byte (r, c) = level pixel (y0 - 3 + r, x0 - 16 + c), zero outside
+// the image); tiles on the image border then rebuild BORDER_REFLECT_101 in shared memory: whole rows above / below the
+// image first, then the three columns left / right of it.
+__global__ void __launch_bounds__(BLUR_THREADS) k_blur(const __grid_constant__ OrbPlan plan, const CUtensorMap* __restrict__ maps) {
     pdl_enter();
-    __shared__ __align__(16) unsigned tile[BLUR_TH + 6][BLUR_SW];
+    __shared__ __align__(128) unsigned tile[BLUR_BOX_H][BLUR_SW];
+    __shared__ unsigned long long barMem;
     const int f = blockIdx.y;
     int t = blockIdx.x, l = 0;
     int tilesX = 0;
@@ -1173,52 +1179,45 @@ __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ OrbPlan pl
     const OrbLevel& L = plan.lv[l];
     const int ty = t / tilesX, tx = t - ty * tilesX;
     const int x0 = tx * BLUR_TW, y0 = ty * BLUR_TH;
-    const uint8_t* src = L.img + (size_t)f * L.plane;
     const int tid = threadIdx.x;
     const int rowsHere = min(BLUR_TH, L.rows - y0) + 6;
-    // smem byte column c of tile row r  <->  pixel (reflect(y0 - 3 + r), reflect(x0 - 16 + c));
-    // staged as 16-byte vectors (18 per row) when the level rows are 16-byte aligned
-    const bool vec_ok = ((L.pitch & 15) == 0) && ((((size_t)src) & 15) == 0);
-    // vectors jlo..jhi of a tile row lie completely inside the image row (x0 is a multiple of 256)
-    int jlo = x0 >= 16 ? 0 : 1;
-    int jhi = min((L.cols - x0) / 16, BLUR_SW / 4 - 1);  // x0 - 16 + 16 j + 15 < cols  <=>  j <= (cols - x0) / 16; may be < jlo
-    if (!vec_ok) { jlo = 0; jhi = -1; }
-    const int nvec = max(jhi - jlo + 1, 0);
-    // pass 1: the inside vectors, 16 bytes per thread
-    const unsigned nvMagic = div_magic((unsigned)nvec);
-    for (int i = tid; i < rowsHere * nvec; i += 256) {
-        const int r = (int)div_by((unsigned)i, nvMagic), j = jlo + (i - r * nvec);
-        const int yy = reflect101(y0 - 3 + r, L.rows);
-        *reinterpret_cast<uint4*>(&tile[r][4 * j]) = __ldg(reinterpret_cast<const uint4*>(src + (size_t)yy * L.pitch + (x0 - 16 + 16 * j)));
+    const unsigned bar = smem_u32(&barMem);
+    if (tid == 0) mbar_init(bar, 1);
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(bar, (unsigned)sizeof(tile));
+        tma_load_3d(smem_u32(&tile[0][0]), maps + l, x0 - 16, y0 - 3, f + plan.frameBase, bar);
     }
-    // pass 2: the words left and right of them (row ends of the image only): reflect-101 per byte
-    const int nleft = nvec ? 4 * jlo : BLUR_SW, nright = nvec ? BLUR_SW - 4 * (jhi + 1) : 0;
-    const int nb = nleft + nright;
-    const unsigned nbMagic = div_magic((unsigned)nb);
-    for (int i = tid; i < rowsHere * nb; i += 256) {
-        const int r = (int)div_by((unsigned)i, nbMagic), kk = i - r * nb;
-        const int k = kk < nleft ? kk : 4 * (jhi + 1) + (kk - nleft);
-        const int x = x0 - 16 + 4 * k;
-        unsigned w = 0;
-        if (x + 3 >= -3 && x < L.cols + 3) {  // touches the image or its 3-px halo
-            const int yy = reflect101(y0 - 3 + r, L.rows);
-            const uint8_t* row = src + (size_t)yy * L.pitch;
-            if (x >= 0 && x + 3 < L.cols) {
-                w = __ldg(reinterpret_cast<const unsigned*>(row + x));
-            } else {
-#pragma unroll
-                for (int bb = 0; bb < 4; ++bb) {
-                    int xx = x + bb;
-                    xx = xx < 0 ? -xx : (xx >= L.cols ? 2 * L.cols - 2 - xx : xx);  // one reflection is enough within 3 px
-                    xx = min(max(xx, 0), L.cols - 1);                               // (degenerate tiny levels)
-                    w |= (unsigned)__ldg(row + xx) << (8 * bb);
-                }
+    mbar_wait(bar, 0);
+    const bool rowFix = y0 == 0 || y0 - 3 + rowsHere > L.rows;
+    const bool colFix = x0 == 0 || x0 + BLUR_TW + 3 > L.cols;
+    if (rowFix) {  // rows above / below the image <- their mirror rows (inside the tile: at most 3 rows away from the edge)
+        for (int i = tid; i < rowsHere * BLUR_SW; i += BLUR_THREADS) {
+            const int r = i >> 6, w = i & 63;
+            const int yy = y0 - 3 + r;
+            if (yy < 0 || yy >= L.rows) {
+                const int rs = reflect101(yy, L.rows) - (y0 - 3);
+                if (rs >= 0 && rs < BLUR_BOX_H) tile[r][w] = tile[rs][w];
             }
         }
-        tile[r][k] = w;
+        __syncthreads();
     }
-    __syncthreads();
-    const int q = tid & 63, g = tid >> 6;
+    if (colFix) {  // the three columns left / right of the image <- their mirror columns
+        unsigned char* tb = reinterpret_cast<unsigned char*>(&tile[0][0]);
+        for (int i = tid; i < rowsHere * 6; i += BLUR_THREADS) {
+            const int r = i / 6, k = i - r * 6;
+            const int x = k < 3 ? k - 3 : L.cols + (k - 3);
+            const int c = x - (x0 - 16);
+            if (c >= 0 && c < 4 * BLUR_SW) {
+                int xs = x < 0 ? -x : 2 * L.cols - 2 - x;  // one reflection is enough within 3 px
+                xs = min(max(xs, 0), L.cols - 1);          // (degenerate tiny levels)
+                const int cs = xs - (x0 - 16);
+                if (cs >= 0 && cs < 4 * BLUR_SW) tb[r * (4 * BLUR_SW) + c] = tb[r * (4 * BLUR_SW) + cs];
+            }
+        }
+    }
+    if (rowFix || colFix) __syncthreads();
+    const int q = tid % (BLUR_TW / 4), g = tid / (BLUR_TW / 4);
     const int xq = x0 + 4 * q;
     if (xq >= L.cols) return;
     const int rbase = g * BLUR_RPT;  // first output row of this thread inside the tile
@@ -1850,7 +1849,7 @@ cudaError_t orbk_run_extract(const OrbPlan& plan, int nframes, orb_keypoint_dev*
         if (e != cudaSuccess) return e;
         e = cudaStreamWaitEvent(st2, ss.fork, 0);
         if (e != cudaSuccess) return e;
-        k_blur<<<dim3(blurTiles, nframes), 256, 0, st2>>>(plan);
+        k_blur<<<dim3(blurTiles, nframes), BLUR_THREADS, 0, st2>>>(plan, d_maps->blr);
         ++g_launches;
         e = cudaEventRecord(ss.join, st2);
         if (e != cudaSuccess) return e;
@@ -1867,7 +1866,7 @@ cudaError_t orbk_run_extract(const OrbPlan& plan, int nframes, orb_keypoint_dev*
         // profiling: stages back to back on one stream, blur after the octree
         cudaEventRecord(ev[3], st);
         cudaEventRecord(ev[6], st);
-        k_blur<<<dim3(blurTiles, nframes), 256, 0, st>>>(plan);
+        k_blur<<<dim3(blurTiles, nframes), BLUR_THREADS, 0, st>>>(plan, d_maps->blr);
         ++g_launches;
         cudaEventRecord(ev[7], st);
     }

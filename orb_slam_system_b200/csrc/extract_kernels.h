@@ -28,6 +28,7 @@ struct DetectMaps {
     CUtensorMap m[ORB_MAX_LEVELS];     // raw level, 256 x boxH box (k_detect)
     CUtensorMap raw[ORB_MAX_LEVELS];   // raw level, DSC_BOX_W x DSC_BOX_H box (k_describe_tile: IC_Angle)
     CUtensorMap blur[ORB_MAX_LEVELS];  // blurred level, same box (k_describe_tile: rBRIEF)
+    CUtensorMap blr[ORB_MAX_LEVELS];   // raw level, 256 x 70 box (k_blur: 224 x 64 tile + halo)
     CUtensorMap rsz[ORB_MAX_LEVELS];   // entry l: the SOURCE image of level l (level l-1), 256 x RSZ_BOX_H box (k_resize_tile)
 };
 // Encodes the (cols x rows x frames) uint8 tensor of one level with a boxW x boxH x 1 box.
