@@ -32,7 +32,7 @@
 // 16-byte aligned for the TMA unit without any slack.  The 224-byte box pitch (56 words) puts four consecutive
 // tile rows into four disjoint 8-bank groups, which makes the IC_Angle loads conflict-free.
 #define DSC_W 160
-#define DSC_H 96
+#define DSC_H 128
 #define DSC_HALO 18
 #define DSC_BOX_W 224
 #define DSC_BOX_H (DSC_H + 2 * DSC_HALO)
