@@ -263,6 +263,7 @@ __global__ void __launch_bounds__(RSZ_THREADS) k_resize_tile(const CUtensorMap* 
 struct DetectTail {
     unsigned short wlist[(DET_THREADS / 32) * DET_WLIST_PER_WARP];  // per warp: (row << 6 | word) of its non-zero F words
     int wcount[DET_THREADS / 32];
+    unsigned qmask[64];                        // per 4-column group: byte mask of the columns that are candidates
     unsigned char cellOf[DET_TILE_W + 8];      // candidate column -> cell index inside the tile
     int cellHasIni[16];
     int nWords;
@@ -423,6 +424,13 @@ __global__ void __launch_bounds__(DET_THREADS) k_detect(const __grid_constant__ 
         const unsigned wcMagic = 0xffffffffu / (unsigned)wCell + 1u;  // (i - 4) / wCell as a multiply-high
         for (int i = tid; i < CW + 8; i += DET_THREADS) sm.cellOf[i] = i < 4 ? (unsigned char)255 : (unsigned char)__umulhi((unsigned)(i - 4), wcMagic);
         if (tid < 16) sm.cellHasIni[tid] = 0;
+        if (tid < 64) {  // group q, byte k <-> cx = 4q + k - ph: keep 0 <= cx < CW
+            unsigned mk = 0xffffffffu;
+            const int rem = CW + ph - 4 * tid;  // bytes of this group left of the candidate area's end
+            if (rem < 4) mk = rem > 0 ? (1u << (8 * rem)) - 1u : 0u;
+            if (tid == 0) mk &= 0xffffffffu << (8 * ph);  // bytes before candidate column 0
+            sm.qmask[tid] = mk;
+        }
         if (tid == 0) {
             sm.nWords = 0;
             sm.nSurv = 0;
@@ -518,10 +526,7 @@ __global__ void __launch_bounds__(DET_THREADS) k_detect(const __grid_constant__ 
             unsigned u01, u23;
             fast_score_pairs(r0, cen.x, low2, neglow2, u01);
             fast_score_pairs(r1, cen.y, low2, neglow2, u23);
-            unsigned word = __byte_perm(u01, u23, 0x6420);  // bytes: p0, p1, p2, p3
-            const int rem = CW + ph - 4 * q;  // bytes of this group left of the candidate area's end
-            if (rem < 4) word &= (1u << (8 * rem)) - 1u;
-            if (q == 0) word &= 0xffffffffu << (8 * ph);  // bytes before candidate column 0
+            const unsigned word = __byte_perm(u01, u23, 0x6420) & sm.qmask[q];  // bytes: p0, p1, p2, p3, candidates only
             sc[r + 1][q + 1] = word;
         }
     }
@@ -1144,12 +1149,6 @@ __global__ void __launch_bounds__(OCT_THREADS) k_octree(const __grid_constant__ 
 // IDP.4A per pixel on byte windows cut from three aligned words, the vertical pass runs on a
 // 7-row register window.  Exact integers throughout, one 32-bit store per 4 pixels.
 // ------------------------------------------------------------------------------------------
-#define BLUR_TW 224                    // output columns per tile: 16 + 224 + 3 halo columns fit the 256-byte TMA box
-#define BLUR_TH 64
-#define BLUR_RPT 16                    // output rows per thread
-#define BLUR_SW 64                     // smem words per row = the box: 16 bytes left of the tile, the tile, right halo
-#define BLUR_BOX_H (BLUR_TH + 6)
-#define BLUR_THREADS ((BLUR_TW / 4) * (BLUR_TH / BLUR_RPT))
 
 __device__ __forceinline__ int reflect101(int p, int n) {
     if (n == 1) return 0;

@@ -440,7 +440,7 @@ static int build_plan(orb_extractor* h, int rows, int cols) {
         const OrbLevel& L = P.lv[l];
         if (L.src != l) continue;
         if (L.nTiles > 0) CUDA_TRY(orbk_encode_level_map(&h->maps.m[l], L.img, L.cols, L.rows, B, L.pitch, L.plane, DET_TILE_W, L.boxH));
-        CUDA_TRY(orbk_encode_level_map(&h->maps.blr[l], L.img, L.cols, L.rows, B, L.pitch, L.plane, 256, 70));
+        CUDA_TRY(orbk_encode_level_map(&h->maps.blr[l], L.img, L.cols, L.rows, B, L.pitch, L.plane, 256, BLUR_BOX_H));
         if (l > 0 && L.rszTiled) {
             const OrbLevel& S = P.lv[P.lv[l - 1].src];
             CUDA_TRY(orbk_encode_level_map(&h->maps.rsz[l], S.img, S.cols, S.rows, B, S.pitch, S.plane, 256, RSZ_BOX_H));
@@ -665,7 +665,7 @@ static int extract_device_impl(orb_extractor* h, int n, const uint8_t* d_imgs, i
                 CUDA_TRY(orbk_encode_level_map(&h->maps_user.m[0], d_imgs, L0.cols, L0.rows, n, L0.pitch, L0.plane, DET_TILE_W, L0.boxH));
             if (L0.dTiles > 0)
                 CUDA_TRY(orbk_encode_level_map(&h->maps_user.raw[0], d_imgs, L0.cols, L0.rows, n, L0.pitch, L0.plane, DSC_BOX_W, DSC_BOX_H));
-            CUDA_TRY(orbk_encode_level_map(&h->maps_user.blr[0], d_imgs, L0.cols, L0.rows, n, L0.pitch, L0.plane, 256, 70));
+            CUDA_TRY(orbk_encode_level_map(&h->maps_user.blr[0], d_imgs, L0.cols, L0.rows, n, L0.pitch, L0.plane, 256, BLUR_BOX_H));
             CUDA_TRY(cudaMemcpyAsync(&h->d_maps_user->blr[0], &h->maps_user.blr[0], sizeof(CUtensorMap), cudaMemcpyHostToDevice, h->stream));
             for (int l = 1; l < P.nlevels; ++l)  // the level(s) resized from level 0
                 if (P.lv[l].src == l && P.lv[l].rszTiled && P.lv[l - 1].src == 0) {

@@ -19,6 +19,14 @@
 #define DET_SP 272           // smem pitch of the image tile (bytes)
 #define DET_THREADS 256
 
+// blur tile (k_blur)
+#define BLUR_TW 224                    // output columns per tile: 16 + 224 + 3 halo columns fit the 256-byte TMA box
+#define BLUR_TH 128
+#define BLUR_RPT 32                    // output rows per thread
+#define BLUR_SW 64                     // smem words per row = the box: 16 bytes left of the tile, the tile, right halo
+#define BLUR_BOX_H (BLUR_TH + 6)
+#define BLUR_THREADS ((BLUR_TW / 4) * (BLUR_TH / BLUR_RPT))
+
 // resize tile: RSZ_W x RSZ_H output pixels of level l from a 256 x RSZ_BOX_H box of level l-1 staged by TMA
 #define RSZ_W 192
 #define RSZ_H 32
