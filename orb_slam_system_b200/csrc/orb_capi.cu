@@ -168,6 +168,7 @@ struct orb_extractor {
     DetectMaps* d_maps = nullptr;        // device copies (global memory)
     DetectMaps* d_maps_user = nullptr;
     const uint8_t* user_base = nullptr;
+    int user_n = 0;          // frames the user maps were encoded for
     std::vector<void*> allocs;  // everything the plan points at
     uint8_t* level0 = nullptr;  // internal level-0 buffer (host-input path)
     const uint8_t* last_l0 = nullptr;  // where level 0 of the last call lives (the caller's frames when read in place)
@@ -659,7 +660,7 @@ static int extract_device_impl(orb_extractor* h, int n, const uint8_t* d_imgs, i
         // same layout as the internal level-0 buffer: read the caller's frames in place
         for (int l = 0; l < P.nlevels; ++l)
             if (P.lv[l].src == 0) P.lv[l].img = const_cast<uint8_t*>(d_imgs);
-        if (h->user_base != d_imgs) {
+        if (h->user_base != d_imgs || n > h->user_n) {
             const OrbLevel& L0 = P.lv[0];
             if (L0.nTiles > 0)
                 CUDA_TRY(orbk_encode_level_map(&h->maps_user.m[0], d_imgs, L0.cols, L0.rows, n, L0.pitch, L0.plane, DET_TILE_W, L0.boxH));
@@ -676,6 +677,7 @@ static int extract_device_impl(orb_extractor* h, int n, const uint8_t* d_imgs, i
             CUDA_TRY(cudaMemcpyAsync(&h->d_maps_user->m[0], &h->maps_user.m[0], sizeof(CUtensorMap), cudaMemcpyHostToDevice, h->stream));
             CUDA_TRY(cudaMemcpyAsync(&h->d_maps_user->raw[0], &h->maps_user.raw[0], sizeof(CUtensorMap), cudaMemcpyHostToDevice, h->stream));
             h->user_base = d_imgs;
+            h->user_n = n;
         }
         maps = h->d_maps_user;
         h->last_l0 = d_imgs;

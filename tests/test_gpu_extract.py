@@ -198,6 +198,35 @@ def test_device_resident_batch_matches_host_path():
     ex.close()
 
 
+def test_device_resident_in_place_growing_batch_and_lanes():
+    # frames read in place from the caller's buffer: a small batch first, then a larger one from the same base address
+    # (the cached tensor maps must grow with it), large enough to be split over the concurrent kernel lanes
+    import torch
+    rows, cols, nf, B = 240, 320, 500, 40
+    frames = np.stack([oracle.synth_frame(rows, cols, frame=f) for f in range(B)])
+    ex = ORBextractor(nf, 1.2, 8, 20, 7, max_batch=B)
+    cap = ex.keypoint_bound(rows, cols)
+    pitch = (cols + 63) // 64 * 64
+    d_in = torch.zeros((B, rows, pitch), dtype=torch.uint8, device="cuda")
+    d_in[:, :, :cols] = torch.from_numpy(frames).cuda()
+    d_k = torch.zeros((B, cap, 28), dtype=torch.uint8, device="cuda")
+    d_d = torch.zeros((B, cap, 32), dtype=torch.uint8, device="cuda")
+    d_c = torch.zeros((B,), dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    for n in (2, B, 7):
+        d_k.zero_(); d_d.zero_(); d_c.zero_()
+        torch.cuda.synchronize()
+        ex.extract_batch_device(d_in[:n, :, :cols], d_k[:n], d_d[:n], d_c[:n], cap)
+        ex.sync()
+        k, d, c = d_k.cpu().numpy(), d_d.cpu().numpy(), d_c.cpu().numpy()
+        for f in list(range(min(n, 3))) + [n - 1]:
+            ko, do = oracle.extract(frames[f], nfeatures=nf, cap=16 * nf)
+            assert c[f] == len(ko), (n, f)
+            assert k[f, :c[f]].tobytes() == ko.tobytes(), (n, f)
+            assert (d[f, :c[f]] == do).all(), (n, f)
+    ex.close()
+
+
 def test_stage_profiling_counts_calls():
     ex = ORBextractor(1000, 1.2, 8, 20, 7, max_batch=2)
     img = oracle.synth_frame(480, 640)
