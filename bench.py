@@ -562,9 +562,9 @@ def main():
                        "l2": f"inputs rotate through {R} distinct batches ({R * B * ROWS * pitch / 1e6:.0f} MB > 126 MB L2)"},
             "roofline": {"bound": "hbm", "kernel": "k_" + dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak,
-                         # dram__bytes_read.sum + dram__bytes_write.sum of k_detect, ncu --set full (profiles/r01i: 2 x 32-frame
-                         # launches of 43.25 + 0.59 MB make one 64-frame step)
-                         "traffic": 87.7e6 if dom == "detect" else None, "traffic_source": "profiles/r01i_ncu_summary.txt",
+                         # dram__bytes_read.sum + dram__bytes_write.sum of k_detect, ncu --set full (profiles/r01j: 2 x 32-frame
+                         # launches of 43.25 + 0.53 MB make one 64-frame step)
+                         "traffic": 87.6e6 if dom == "detect" else None, "traffic_source": "profiles/r01j_ncu_summary.txt",
                          "peak_source": peak_kind,
                          "algo_bytes_per_launch": algo, "launch_ms": per_launch_ms,
                          "stage_ms_per_step": {k: v / max(ncalls, 1) for k, v in stage_ms.items()},
