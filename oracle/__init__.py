@@ -252,7 +252,7 @@ def _featvec_csr(fv):
     return nodes, off, np.array(flat, np.int32)
 
 
-def search_by_bow_kf(kf1, kf2, nnratio=0.6, checkOri=True):
+def search_by_bow_kf(kf1, kf2, nnratio=0.6, checkOri=True, impl=None):
     """ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*): kf = dict(desc, keys[KP_DTYPE], has_mp[bool], featvec{node: [idx]})."""
     d1, d2 = np.ascontiguousarray(kf1["desc"], np.uint8), np.ascontiguousarray(kf2["desc"], np.uint8)
     a1, a2 = np.ascontiguousarray(kf1["keys"]["angle"], np.float32), np.ascontiguousarray(kf2["keys"]["angle"], np.float32)
@@ -260,13 +260,12 @@ def search_by_bow_kf(kf1, kf2, nnratio=0.6, checkOri=True):
     n1, o1, i1 = _featvec_csr(kf1["featvec"])
     n2, o2, i2 = _featvec_csr(kf2["featvec"])
     out = np.zeros(len(d1), np.int32)
-    lib().orc_search_by_bow_kf.restype = C.c_int
-    n = lib().orc_search_by_bow_kf(_p(d1), _p(a1), _p(h1), len(d1), _p(d2), _p(a2), _p(h2), len(d2), _p(n1), _p(o1), _p(i1), len(n1),
+    n = _search_fn("search_by_bow_kf", impl)(_p(d1), _p(a1), _p(h1), len(d1), _p(d2), _p(a2), _p(h2), len(d2), _p(n1), _p(o1), _p(i1), len(n1),
                                    _p(n2), _p(o2), _p(i2), len(n2), C.c_float(nnratio), int(checkOri), _p(out))
     return int(n), out
 
 
-def search_for_triangulation(kf1, kf2, F12, checkOri=False):
+def search_for_triangulation(kf1, kf2, F12, checkOri=False, impl=None):
     """ORBmatcher::SearchForTriangulation (bOnlyStereo=false): kf as above plus 'sigma2' (mvLevelSigma2) for kf2."""
     d1, d2 = np.ascontiguousarray(kf1["desc"], np.uint8), np.ascontiguousarray(kf2["desc"], np.uint8)
     k1, k2 = kf1["keys"], kf2["keys"]
@@ -279,11 +278,45 @@ def search_for_triangulation(kf1, kf2, F12, checkOri=False):
     F = f(np.asarray(F12, np.float32).reshape(9))
     s2 = f(kf2["sigma2"])
     out = np.zeros(len(d1), np.int32)
-    lib().orc_search_for_triangulation.restype = C.c_int
-    n = lib().orc_search_for_triangulation(_p(d1), _p(x1), _p(y1), _p(a1), _p(h1), len(d1), _p(d2), _p(x2), _p(y2), _p(a2), _p(oc2),
+    n = _search_fn("search_for_triangulation", impl)(_p(d1), _p(x1), _p(y1), _p(a1), _p(h1), len(d1), _p(d2), _p(x2), _p(y2), _p(a2), _p(oc2),
                                            _p(h2), len(d2), _p(n1), _p(o1), _p(i1), len(n1), _p(n2), _p(o2), _p(i2), len(n2), _p(F),
                                            _p(s2), int(checkOri), _p(out))
     return int(n), out
+
+
+_REF_MATCH = os.path.join(_HERE, "_ref", "libref_match.so")
+_ref_match = None
+
+
+def ref_match_lib():
+    """CDLL of the reference's own src/ORBmatcher.cc compiled unmodified against oracle/mshim (oracle/Makefile refmatch),
+    or None when it is neither prebuilt nor buildable (no /root/reference)."""
+    global _ref_match
+    if _ref_match is None:
+        if not os.path.exists(_REF_MATCH) and os.path.exists("/root/reference/src/ORBmatcher.cc"):
+            subprocess.check_call(["make", "-s", "-C", _HERE, "refmatch"])
+        if not os.path.exists(_REF_MATCH):
+            return None
+        _ref_match = C.CDLL(_REF_MATCH)
+    return _ref_match
+
+
+def _search_fn(name, impl):
+    """orc_<name> of the oracle restatement, or refm_<name> of the compiled reference (impl="reference")."""
+    if impl == "reference":
+        L = ref_match_lib()
+        assert L is not None, "oracle/_ref/libref_match.so is not available"
+        fn = getattr(L, "refm_" + name)
+    else:
+        fn = getattr(lib(), "orc_" + name)
+    fn.restype = C.c_int
+    return fn
+
+
+def ref_descriptor_distance(a, b):
+    """ORBmatcher::DescriptorDistance of the compiled reference."""
+    a, b = np.ascontiguousarray(a, np.uint8), np.ascontiguousarray(b, np.uint8)
+    return int(ref_match_lib().refm_descriptor_distance(_p(a), _p(b)))
 
 
 class _OrcFrame(C.Structure):
@@ -324,7 +357,7 @@ def features_in_area(F, x, y, r, min_level=None, max_level=None):
         cap = tot
 
 
-def search_by_projection_map(F, occupied, qdesc, proj_x, proj_y, proj_xr, level, view_cos, th, nnratio, q_observed=None):
+def search_by_projection_map(F, occupied, qdesc, proj_x, proj_y, proj_xr, level, view_cos, th, nnratio, q_observed=None, impl=None):
     q = np.ascontiguousarray(qdesc, np.uint8).reshape(-1, 32)
     out = np.zeros(len(q), np.int32)
     fr = _frame(F)
@@ -332,14 +365,13 @@ def search_by_projection_map(F, occupied, qdesc, proj_x, proj_y, proj_xr, level,
     px, py, pxr, vc = f(proj_x), f(proj_y), f(proj_xr), f(view_cos)
     lv = np.ascontiguousarray(level, np.int32)
     qo = _opt(q_observed, np.uint8)
-    lib().orc_search_by_projection_map.restype = C.c_int
-    n = lib().orc_search_by_projection_map(C.byref(fr), _pp(_opt(F.mvuRight, np.float32)), _p(occupied), _p(f(F.mvScaleFactors)), len(q),
+    n = _search_fn("search_by_projection_map", impl)(C.byref(fr), _pp(_opt(F.mvuRight, np.float32)), _p(occupied), _p(f(F.mvScaleFactors)), len(q),
                                            _p(q), _p(px), _p(py), _p(pxr), _p(lv), _p(vc), _pp(qo), C.c_float(th), C.c_float(nnratio),
                                            _p(out))
     return int(n), out
 
 
-def search_by_projection_last(Cur, claimed, qdesc, u, v, last_octave, last_angle, th, forward, backward, checkOri):
+def search_by_projection_last(Cur, claimed, qdesc, u, v, last_octave, last_angle, th, forward, backward, checkOri, impl=None):
     """Returns (nmatches, feature_of_query); nmatches is None when the reference would index rotHist out of bounds (D9)."""
     q = np.ascontiguousarray(qdesc, np.uint8).reshape(-1, 32)
     out = np.zeros(len(q), np.int32)
@@ -347,8 +379,7 @@ def search_by_projection_last(Cur, claimed, qdesc, u, v, last_octave, last_angle
     f = lambda a: np.ascontiguousarray(a, np.float32)
     uu, vv, la = f(u), f(v), f(last_angle)
     lo = np.ascontiguousarray(last_octave, np.int32)
-    lib().orc_search_by_projection_last.restype = C.c_int
-    n = lib().orc_search_by_projection_last(C.byref(fr), _p(claimed), _p(f(Cur.mvScaleFactors)), len(q), _p(q), _p(uu), _p(vv), _p(lo),
+    n = _search_fn("search_by_projection_last", impl)(C.byref(fr), _p(claimed), _p(f(Cur.mvScaleFactors)), len(q), _p(q), _p(uu), _p(vv), _p(lo),
                                             _p(la), C.c_float(th), int(forward), int(backward), int(checkOri), _p(out))
     return (None if n == -2147483648 else int(n)), out
 
@@ -378,14 +409,13 @@ def search_kf_window(KF, claimed, qdesc, u, v, radius, level, max_dist):
     return int(n), out
 
 
-def search_for_initialization(keys1, desc1, F2, prev_matched, window_size, nnratio, checkOri):
+def search_for_initialization(keys1, desc1, F2, prev_matched, window_size, nnratio, checkOri, impl=None):
     k1 = np.ascontiguousarray(keys1, KP_DTYPE)
     d1 = np.ascontiguousarray(desc1, np.uint8).reshape(-1, 32)
     assert prev_matched.dtype == np.float32 and prev_matched.flags.c_contiguous
     out = np.zeros(len(k1), np.int32)
     fr = _frame(F2)
-    lib().orc_search_for_initialization.restype = C.c_int
-    n = lib().orc_search_for_initialization(_p(k1), _p(d1), len(k1), C.byref(fr), _p(prev_matched), int(window_size), C.c_float(nnratio),
+    n = _search_fn("search_for_initialization", impl)(_p(k1), _p(d1), len(k1), C.byref(fr), _p(prev_matched), int(window_size), C.c_float(nnratio),
                                             int(checkOri), _p(out))
     return int(n), out
 
