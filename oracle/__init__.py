@@ -384,15 +384,14 @@ def search_by_projection_last(Cur, claimed, qdesc, u, v, last_octave, last_angle
     return (None if n == -2147483648 else int(n)), out
 
 
-def search_by_projection_reloc(Cur, claimed, qdesc, u, v, predicted_level, kf_angle, th, ORBdist, checkOri):
+def search_by_projection_reloc(Cur, claimed, qdesc, u, v, predicted_level, kf_angle, th, ORBdist, checkOri, impl=None):
     q = np.ascontiguousarray(qdesc, np.uint8).reshape(-1, 32)
     out = np.zeros(len(q), np.int32)
     fr = _frame(Cur)
     f = lambda a: np.ascontiguousarray(a, np.float32)
     uu, vv, ka = f(u), f(v), f(kf_angle)
     pl = np.ascontiguousarray(predicted_level, np.int32)
-    lib().orc_search_by_projection_reloc.restype = C.c_int
-    n = lib().orc_search_by_projection_reloc(C.byref(fr), _p(claimed), _p(f(Cur.mvScaleFactors)), len(q), _p(q), _p(uu), _p(vv), _p(pl),
+    n = _search_fn("search_by_projection_reloc", impl)(C.byref(fr), _p(claimed), _p(f(Cur.mvScaleFactors)), len(q), _p(q), _p(uu), _p(vv), _p(pl),
                                              _p(ka), C.c_float(th), int(ORBdist), int(checkOri), _p(out))
     return int(n), out
 
@@ -406,6 +405,33 @@ def search_kf_window(KF, claimed, qdesc, u, v, radius, level, max_dist):
     lv = _opt(level, np.int32)
     lib().orc_search_kf_window.restype = C.c_int
     n = lib().orc_search_kf_window(C.byref(fr), _pp(claimed), len(q), _p(q), _p(uu), _p(vv), _p(rr), _pp(lv), int(max_dist), _p(out))
+    return int(n), out
+
+
+def ref_search_by_projection_loop(KF, claimed, qdesc, u, v, radius):
+    """The compiled reference's SearchByProjection(KeyFrame*, Scw, vpPoints, vpMatched, th) (src/ORBmatcher.cc:121-195) searching
+    the windows (u, v, radius); the oracle's counterpart is search_kf_window(KF, claimed, ..., level=None, max_dist=TH_LOW)."""
+    q = np.ascontiguousarray(qdesc, np.uint8).reshape(-1, 32)
+    out = np.zeros(len(q), np.int32)
+    fr = _frame(KF)
+    f = lambda a: np.ascontiguousarray(a, np.float32)
+    fn = ref_match_lib().refm_search_by_projection_loop
+    fn.restype = C.c_int
+    n = fn(C.byref(fr), _p(claimed), len(q), _p(q), _p(f(u)), _p(f(v)), _p(f(radius)), _p(out))
+    return int(n), out
+
+
+def ref_search_by_sim3(KF2, qdesc, u, v, level, th):
+    """The compiled reference's SearchBySim3 (src/ORBmatcher.cc:636-730) with s12 = 1, R12 = I, t12 = 0; the oracle's counterpart is
+    search_kf_window(KF2, None, ..., radius = th * scale[level], level, max_dist=TH_HIGH)."""
+    q = np.ascontiguousarray(qdesc, np.uint8).reshape(-1, 32)
+    out = np.zeros(len(q), np.int32)
+    fr = _frame(KF2)
+    f = lambda a: np.ascontiguousarray(a, np.float32)
+    fn = ref_match_lib().refm_search_by_sim3
+    fn.restype = C.c_int
+    n = fn(C.byref(fr), _p(f(KF2.mvScaleFactors)), len(q), _p(q), _p(f(u)), _p(f(v)), _p(np.ascontiguousarray(level, np.int32)), C.c_float(th),
+           _p(out))
     return int(n), out
 
 

@@ -250,6 +250,109 @@ int refm_search_for_initialization(const OKP* keys1, const uint8_t* desc1, int n
     return n;
 }
 
+// ORBmatcher::SearchByProjection(Frame &CurrentFrame, KeyFrame *pKF, const set<MapPoint*>&, th, ORBdist), src/ORBmatcher.cc:820-894
+// (relocalisation).  Query i = map point i of the keyframe, at (u, v, 1); kfAngle = pKF->mvKeys[i].angle.
+int refm_search_by_projection_reloc(const OrcFrame* Cur, uint8_t* curHasMapPoint, const float* mvScaleFactors, int nq, const uint8_t* qdesc,
+                                    const float* u, const float* v, const int* predictedLevel, const float* kfAngle, float th,
+                                    int ORBdist, int checkOri, int* featureOfQuery) {
+    Frame C;
+    fill_frame(C, Cur, mvScaleFactors, NSCALE);
+    Pool pool;
+    for (int i = 0; i < Cur->N; ++i)
+        if (curHasMapPoint[i]) C.mvpMapPoints.v[i] = pool.make(-1);
+    KeyFrame K;
+    K.N = nq;
+    K.mvKeys.resize(nq);
+    K.mapPoints.assign(nq, nullptr);
+    for (int i = 0; i < nq; ++i) {
+        MapPoint* p = pool.make(i);
+        p->desc = desc_mat(qdesc + 32 * (size_t)i, 1);
+        p->pos = vec3(u[i], v[i], 1.0f);
+        p->predictedLevel = predictedLevel[i];
+        K.mapPoints[i] = p;
+        K.mvKeys[i].angle = kfAngle[i];
+        featureOfQuery[i] = -1;
+    }
+    std::set<MapPoint*> found;
+    ORBmatcher m(0.9f, checkOri != 0);
+    const int n = m.SearchByProjection(C, &K, found, th, ORBdist);
+    std::vector<int> owner(Cur->N, -1);
+    for (auto& e : C.mvpMapPoints.log) {
+        if (e.second) {
+            featureOfQuery[e.second->id] = (int)e.first;
+            owner[e.first] = e.second->id;
+        } else if (owner[e.first] >= 0) {
+            featureOfQuery[owner[e.first]] = -1;
+            owner[e.first] = -1;
+        }
+    }
+    for (int i = 0; i < Cur->N; ++i) curHasMapPoint[i] = C.mvpMapPoints.v[i] != nullptr;
+    return n;
+}
+
+// ORBmatcher::SearchByProjection(KeyFrame* pKF, cv::Mat Scw, vpPoints, vpMatched, th), src/ORBmatcher.cc:121-195 (loop closing).
+// The method's radius is th * pKF->mvScaleFactors[PredictScale()]: with th = 1, PredictScale() = the query's own index and
+// mvScaleFactors[i] = radius[i] it searches exactly the window the caller asks for.  claimed = vpMatched[idx] != NULL.
+int refm_search_by_projection_loop(const OrcFrame* KF, uint8_t* claimed, int nq, const uint8_t* qdesc, const float* u, const float* v,
+                                   const float* radius, int* featureOfQuery) {
+    KeyFrame K;
+    fill_grid(K.grid, KF);
+    K.N = KF->N;
+    for (int i = 0; i < KF->N; ++i) K.mvKeysUn.push_back(to_cv(KF->keysUn[i]));
+    K.mDescriptors = desc_mat(KF->desc, KF->N);
+    K.mvScaleFactors.assign(radius, radius + nq);
+    Pool pool;
+    std::vector<MapPoint*> matched(KF->N, nullptr), pts;
+    for (int i = 0; i < KF->N; ++i)
+        if (claimed[i]) matched[i] = pool.make(-1);
+    for (int i = 0; i < nq; ++i) {
+        MapPoint* p = pool.make(i);
+        p->desc = desc_mat(qdesc + 32 * (size_t)i, 1);
+        p->pos = vec3(u[i], v[i], 1.0f);
+        p->normal = vec3(0.0f, 0.0f, 1e6f);  // passes the viewing-angle gate PO.Pn >= 0.5 |PO|
+        p->predictedLevel = i;
+        pts.push_back(p);
+        featureOfQuery[i] = -1;
+    }
+    ORBmatcher m(0.75f, true);
+    const int n = m.SearchByProjection(&K, cv::Mat::eye(4, 4, CV_32F), pts, matched, 1);
+    for (int i = 0; i < KF->N; ++i) {
+        if (matched[i] && matched[i]->id >= 0) featureOfQuery[matched[i]->id] = i;
+        claimed[i] = matched[i] != nullptr;
+    }
+    return n;
+}
+
+// ORBmatcher::SearchBySim3(pKF1, pKF2, vpMatches12, s12 = 1, R12 = I, t12 = 0, th), src/ORBmatcher.cc:636-730.  Query i = map point
+// i of KF1 at (u, v, 1) with PredictScale() = level[i]; every feature of KF2 holds a map point, so vpMatches12[i] names the feature.
+int refm_search_by_sim3(const OrcFrame* KF2, const float* mvScaleFactors, int nq, const uint8_t* qdesc, const float* u, const float* v,
+                        const int* level, float th, int* featureOfQuery) {
+    KeyFrame K1, K2;
+    fill_grid(K2.grid, KF2);
+    K2.N = KF2->N;
+    for (int i = 0; i < KF2->N; ++i) K2.mvKeysUn.push_back(to_cv(KF2->keysUn[i]));
+    K2.mDescriptors = desc_mat(KF2->desc, KF2->N);
+    K2.mvScaleFactors.assign(mvScaleFactors, mvScaleFactors + NSCALE);
+    Pool pool;
+    K2.mapPoints.assign(KF2->N, nullptr);
+    for (int i = 0; i < KF2->N; ++i) K2.mapPoints[i] = pool.make(i);
+    K1.N = nq;
+    K1.mapPoints.assign(nq, nullptr);
+    for (int i = 0; i < nq; ++i) {
+        MapPoint* p = pool.make(-1);
+        p->desc = desc_mat(qdesc + 32 * (size_t)i, 1);
+        p->pos = vec3(u[i], v[i], 1.0f);
+        p->predictedLevel = level[i];
+        K1.mapPoints[i] = p;
+    }
+    std::vector<MapPoint*> m12(nq, nullptr);
+    ORBmatcher m(0.75f, true);
+    const float s12 = 1.0f;
+    const int n = m.SearchBySim3(&K1, &K2, m12, s12, cv::Mat::eye(3, 3, CV_32F), cv::Mat::zeros(3, 1, CV_32F), th);
+    for (int i = 0; i < nq; ++i) featureOfQuery[i] = m12[i] ? m12[i]->id : -1;
+    return n;
+}
+
 // ORBmatcher::DescriptorDistance, src/ORBmatcher.cc:896-908.
 int refm_descriptor_distance(const uint8_t* a, const uint8_t* b) { return ORBmatcher::DescriptorDistance(desc_mat(a, 1), desc_mat(b, 1)); }
 }

@@ -123,6 +123,64 @@ def case_initialization(impl, seed, window, nnratio, check_ori):
     return n, m12, prev
 
 
+def _inside(F, u, v):
+    """The reference drops projections outside the image before it searches (IsInImage / the mnMin..mnMax test)."""
+    return (u >= F.mnMinX) & (u < F.mnMinX + 64.0 / F.mfGridElementWidthInv) & (v >= F.mnMinY) & (v < F.mnMinY + 48.0 / F.mfGridElementHeightInv)
+
+
+def case_reloc(impl, seed, check_ori, th, orb_dist):
+    rng = np.random.default_rng(seed)
+    Cur = make_frame(rng, 2000)
+    src, q, u, v, level, angle = projected_queries(rng, Cur, 1400, max_flips=70, outside=0.0)
+    keep = _inside(Cur, u, v)
+    q, u, v, level, angle = q[keep], u[keep], v[keep], level[keep], angle[keep]
+    claimed = (rng.random(Cur.N) < 0.1).astype(np.uint8)
+    if impl == "gpu":
+        m = _gpu(0.9, check_ori)
+        n, fq = m.SearchByProjectionReloc(Cur, claimed, q, u, v, level, angle, th, orb_dist)
+        m.close()
+        return n, fq, claimed
+    n, fq = oracle.search_by_projection_reloc(Cur, claimed, q, u, v, level, angle, th, orb_dist, check_ori, impl=impl)
+    return n, fq, claimed
+
+
+def case_loop(impl, seed, th):
+    rng = np.random.default_rng(seed)
+    KF = make_frame(rng, 1800)
+    src, q, u, v, level, _ = projected_queries(rng, KF, 1200, max_flips=40, outside=0.0)
+    keep = _inside(KF, u, v)
+    q, u, v, level = q[keep], u[keep], v[keep], level[keep]
+    radius = (np.float32(th) * SCALE[level]).astype(np.float32)
+    claimed = (rng.random(KF.N) < 0.15).astype(np.uint8)
+    if impl == "gpu":
+        m = _gpu(0.75, True)
+        n, fq = m.SearchByProjectionKF(KF, claimed, q, u, v, radius)
+        m.close()
+        return n, fq, claimed
+    if impl == "reference":
+        n, fq = oracle.ref_search_by_projection_loop(KF, claimed, q, u, v, radius)
+    else:
+        n, fq = oracle.search_kf_window(KF, claimed, q, u, v, radius, None, 50)
+    return n, fq, claimed
+
+
+def case_sim3(impl, seed, th):
+    rng = np.random.default_rng(seed)
+    KF2 = make_frame(rng, 1800)
+    src, q, u, v, level, _ = projected_queries(rng, KF2, 1200, max_flips=60, outside=0.0)
+    keep = _inside(KF2, u, v)
+    q, u, v, level = q[keep], u[keep], v[keep], level[keep]
+    radius = (np.float32(th) * SCALE[level]).astype(np.float32)
+    if impl == "gpu":
+        m = _gpu(0.75, True)
+        r = m.SearchBySim3(KF2, q, u, v, radius, level)
+        m.close()
+        return r
+    if impl == "reference":
+        return oracle.ref_search_by_sim3(KF2, q, u, v, level, th)
+    return oracle.search_kf_window(KF2, None, q, u, v, radius, level, 100)
+
+
 CASES = {
     "projection_map_mono": lambda impl: case_projection_map(impl, 11, 1.0, False, 0.8, False),
     "projection_map_stereo_th3": lambda impl: case_projection_map(impl, 12, 3.0, True, 0.8, True),
@@ -130,6 +188,10 @@ CASES = {
     "projection_last_normal": lambda impl: case_projection_last(impl, 21, "normal", True, 7.0),
     "projection_last_forward": lambda impl: case_projection_last(impl, 22, "forward", True, 15.0),
     "projection_last_backward_noori": lambda impl: case_projection_last(impl, 23, "backward", False, 7.0),
+    "reloc_ori": lambda impl: case_reloc(impl, 61, True, 10.0, 100),
+    "reloc_noori_tight": lambda impl: case_reloc(impl, 62, False, 3.0, 64),
+    "loop_th10": lambda impl: case_loop(impl, 71, 10),
+    "sim3_th75": lambda impl: case_sim3(impl, 81, 7.5),
     "bow_ori": lambda impl: case_bow(impl, 31, 0.75, True),
     "bow_noori_tight": lambda impl: case_bow(impl, 32, 0.6, False),
     "triangulation": lambda impl: case_triangulation(impl, 41, False),
