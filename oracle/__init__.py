@@ -241,6 +241,65 @@ def compute_stereo_matches(img_l, img_r, kl, dl, kr, dr, bf, fx, scaleFactor=1.2
     return ur, dep
 
 
+_REF_FRAME = os.path.join(_HERE, "_ref", "libref_frame.so")
+_ref_frame = None
+
+
+def ref_frame_lib():
+    """CDLL of the reference's own src/Frame.cc compiled unmodified behind oracle/mshim/frame_objects.h (oracle/Makefile
+    refframe), or None when it is neither prebuilt nor buildable (no /root/reference)."""
+    global _ref_frame
+    if _ref_frame is None:
+        if not os.path.exists(_REF_FRAME) and os.path.exists("/root/reference/src/Frame.cc"):
+            subprocess.check_call(["make", "-s", "-C", _HERE, "refframe"])
+        if not os.path.exists(_REF_FRAME):
+            return None
+        _ref_frame = C.CDLL(_REF_FRAME)
+    return _ref_frame
+
+
+def ref_compute_stereo_matches(img_l, img_r, kl, dl, kr, dr, bf, fx, scaleFactor=1.2, nlevels=8):
+    """Frame::ComputeStereoMatches of the COMPILED reference (its stereo constructor run on stub extractors that hand out these
+    keypoints / descriptors and the pyramids of the two images): (mvuRight, mvDepth)."""
+    kl = np.ascontiguousarray(kl, KP_DTYPE)
+    kr = np.ascontiguousarray(kr, KP_DTYPE)
+    dl = np.ascontiguousarray(dl, np.uint8)
+    dr = np.ascontiguousarray(dr, np.uint8)
+    pl = [pyramid_level(img_l, l, scaleFactor, nlevels) for l in range(nlevels)]
+    pr = [pyramid_level(img_r, l, scaleFactor, nlevels) for l in range(nlevels)]
+    rows = np.array([p.shape[0] for p in pl], np.int32)
+    cols = np.array([p.shape[1] for p in pl], np.int32)
+    bl = np.concatenate([np.ascontiguousarray(p).ravel() for p in pl])
+    br = np.concatenate([np.ascontiguousarray(p).ravel() for p in pr])
+    scale = tables(1000, scaleFactor, nlevels)["scale"].astype(np.float32)
+    ur = np.zeros(len(kl), np.float32)
+    dep = np.zeros(len(kl), np.float32)
+    fn = ref_frame_lib().refm_compute_stereo_matches
+    fn.restype = C.c_int
+    rc = fn(_p(kl), _p(dl), len(kl), _p(kr), _p(dr), len(kr), _p(scale), nlevels, _p(bl), _p(br), _p(rows), _p(cols), C.c_float(bf),
+            C.c_float(fx), _p(ur), _p(dep))
+    if rc != 0:
+        raise RuntimeError(f"compiled reference threw (rc={rc})")
+    return ur, dep
+
+
+def ref_frame_features_in_area(keys, rows, cols, x, y, r, min_level=None, max_level=None):
+    """Frame::AssignFeaturesToGrid + Frame::GetFeaturesInArea of the COMPILED reference on a rows x cols frame: (offsets, cand)."""
+    k = np.ascontiguousarray(keys, KP_DTYPE)
+    x, y, r = (np.ascontiguousarray(a, np.float32) for a in (x, y, r))
+    lo, hi = _opt(min_level, np.int32), _opt(max_level, np.int32)
+    off = np.zeros(len(x) + 1, np.int32)
+    cap = max(64, 64 * len(x))
+    fn = ref_frame_lib().refm_frame_features_in_area
+    fn.restype = C.c_int
+    while True:
+        cand = np.zeros(cap, np.int32)
+        tot = fn(_p(k), len(k), int(rows), int(cols), len(x), _p(x), _p(y), _p(r), _pp(lo), _pp(hi), _p(off), _p(cand), cap)
+        if tot <= cap:
+            return off, cand[:tot].copy()
+        cap = tot
+
+
 def _featvec_csr(fv):
     """dict node -> list of feature indices  ->  (sorted nodes, offsets, flat indices) int32 arrays."""
     nodes = np.array(sorted(fv), np.int32)

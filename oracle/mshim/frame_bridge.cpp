@@ -1,0 +1,129 @@
+// C entry points over the reference's own ORB_SLAM2::Frame, compiled UNMODIFIED from /root/reference/src/Frame.cc against
+// oracle/mshim/frame_objects.h -- TEST INFRASTRUCTURE ONLY.
+//   refm_compute_stereo_matches: the stereo constructor Frame(imLeft, imRight, ...) (src/Frame.cc:41-97) runs ExtractORB (the
+//     stub extractors hand out the given keypoints / descriptors / pyramids), UndistortKeyPoints (no distortion),
+//     ComputeStereoMatches (:446-619) and AssignFeaturesToGrid; mvuRight / mvDepth are read back.
+//   refm_frame_features_in_area: the monocular constructor (:154-208: ExtractORB, UndistortKeyPoints, ComputeImageBounds,
+//     AssignFeaturesToGrid), then Frame::GetFeaturesInArea (:307-360) per query.
+// Frame::mb is not initialised before ComputeStereoMatches reads it (`mb = mbf / fx` comes after the call, :94; in the
+// running system the temporary Frame lands on the stack slot of the previous one and finds its mb there): the bridge
+// constructs the Frame in storage whose mb already holds mbf / fx.
+#include "Frame.h"
+
+#include <cstddef>
+#include <cstring>
+#include <memory>
+#include <new>
+
+using namespace ORB_SLAM2;
+typedef orb_oracle::KeyPoint OKP;
+
+namespace {
+cv::Mat image_mat(const uint8_t* p, int rows, int cols, int step) {
+    cv::Mat m(rows, cols, CV_8U);
+    for (int y = 0; y < rows; ++y) memcpy(m.data + (size_t)y * m.step, p + (size_t)y * step, cols);
+    return m;
+}
+void load(ORBextractor& ex, const OKP* k, const uint8_t* d, int n, const float* scale, int nlevels) {
+    for (int i = 0; i < n; ++i) {
+        cv::KeyPoint c;
+        c.pt = cv::Point2f(k[i].x, k[i].y);
+        c.size = k[i].size;
+        c.angle = k[i].angle;
+        c.response = k[i].response;
+        c.octave = k[i].octave;
+        c.class_id = k[i].class_id;
+        ex.keys.push_back(c);
+    }
+    ex.desc = cv::Mat(std::max(n, 1), 32, CV_8U);
+    if (n) memcpy(ex.desc.data, d, (size_t)n * 32);
+    for (int l = 0; l < nlevels; ++l) {
+        ex.scale.push_back(scale[l]);
+        ex.invScale.push_back(1.0f / scale[l]);
+        ex.sigma2.push_back(scale[l] * scale[l]);
+        ex.invSigma2.push_back(1.0f / (scale[l] * scale[l]));
+    }
+}
+struct FrameBox {  // a Frame constructed in storage whose `mb` was pre-set
+    alignas(Frame) unsigned char raw[sizeof(Frame)];
+    Frame* f = nullptr;
+    ~FrameBox() {
+        if (f) f->~Frame();
+    }
+};
+}  // namespace
+
+extern "C" {
+
+// pyrL / pyrR: the nlevels pyramid levels of the two extractors, level l = rows[l] x cols[l] bytes, dense, back to back.
+int refm_compute_stereo_matches(const OKP* kl, const uint8_t* dl, int nl, const OKP* kr, const uint8_t* dr, int nr, const float* scale,
+                                int nlevels, const uint8_t* pyrL, const uint8_t* pyrR, const int* rows, const int* cols, float bf,
+                                float fx, float* uRight, float* depth) {
+    ORBextractor exL, exR;
+    load(exL, kl, dl, nl, scale, nlevels);
+    load(exR, kr, dr, nr, scale, nlevels);
+    size_t off = 0;
+    for (int l = 0; l < nlevels; ++l) {
+        exL.mvImagePyramid.push_back(image_mat(pyrL + off, rows[l], cols[l], cols[l]));
+        exR.mvImagePyramid.push_back(image_mat(pyrR + off, rows[l], cols[l], cols[l]));
+        off += (size_t)rows[l] * cols[l];
+    }
+    cv::Mat K = cv::Mat::eye(3, 3, CV_32F);
+    K.at<float>(0, 0) = fx;
+    K.at<float>(1, 1) = fx;
+    K.at<float>(0, 2) = cols[0] * 0.5f;
+    K.at<float>(1, 2) = rows[0] * 0.5f;
+    cv::Mat dist = cv::Mat::zeros(4, 1, CV_32F);
+    ORBVocabulary voc;
+    Frame::mbInitialComputations = true;
+    FrameBox box;
+    memset(box.raw, 0, sizeof box.raw);
+    const float mb = bf / fx;
+    memcpy(box.raw + offsetof(Frame, mb), &mb, sizeof mb);
+    try {
+        box.f = new (box.raw) Frame(exL.mvImagePyramid[0], exR.mvImagePyramid[0], 0.0, &exL, &exR, &voc, K, dist, bf, 40.0f);
+    } catch (const std::exception&) {
+        return -2;
+    }
+    for (int i = 0; i < nl; ++i) {
+        uRight[i] = box.f->mvuRight[i];
+        depth[i] = box.f->mvDepth[i];
+    }
+    return 0;
+}
+
+// Frame::AssignFeaturesToGrid + Frame::GetFeaturesInArea of the reference on a frame of `cols` x `rows` pixels with the given
+// (undistorted = raw) keypoints; CSR result like orc_features_in_area.  Returns the total number of candidates.
+int refm_frame_features_in_area(const OKP* keys, int n, int rows, int cols, int nq, const float* x, const float* y, const float* r,
+                                const int* minLevel, const int* maxLevel, int* offsets, int* cand, int cap) {
+    ORBextractor exL, exR;
+    const float scale[8] = {1.f, 1.f, 1.2f, 1.44f, 1.728f, 2.0736f, 2.48832f, 2.985984f};
+    std::vector<uint8_t> zeros((size_t)std::max(n, 1) * 32, 0);
+    load(exL, keys, zeros.data(), n, scale, 8);
+    load(exR, keys, zeros.data(), 0, scale, 8);
+    cv::Mat img(rows, cols, CV_8U);
+    for (int l = 0; l < 8; ++l) {
+        exL.mvImagePyramid.push_back(img);
+        exR.mvImagePyramid.push_back(img);
+    }
+    cv::Mat K = cv::Mat::eye(3, 3, CV_32F), dist = cv::Mat::zeros(4, 1, CV_32F);
+    ORBVocabulary voc;
+    Frame::mbInitialComputations = true;
+    FrameBox box;
+    memset(box.raw, 0, sizeof box.raw);
+    const float mb = 1.0f;
+    memcpy(box.raw + offsetof(Frame, mb), &mb, sizeof mb);
+    box.f = new (box.raw) Frame(img, 0.0, &exL, &voc, K, dist, 1.0f, 40.0f);  // the monocular constructor (:154-208): no stereo step
+    int total = 0;
+    offsets[0] = 0;
+    for (int i = 0; i < nq; ++i) {
+        const std::vector<size_t> v = box.f->GetFeaturesInArea(x[i], y[i], r[i], minLevel ? minLevel[i] : -1, maxLevel ? maxLevel[i] : -1);
+        for (size_t idx : v) {
+            if (total < cap) cand[total] = (int)idx;
+            ++total;
+        }
+        offsets[i + 1] = total;
+    }
+    return total;
+}
+}

@@ -4,6 +4,8 @@
 // with identity cameras, so every product and sum the matcher forms with these is exact in any evaluation order and the
 // arithmetic of OpenCV's gemm does not enter the comparison.
 #pragma once
+#include <algorithm>
+#include <climits>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -52,6 +54,12 @@ public:
         data = buf_->data();
     }
     static Mat zeros(int r, int c, int type) { return Mat(r, c, type); }
+    static Mat ones(int r, int c, int type) {
+        Mat m(r, c, type);
+        for (int i = 0; i < r; ++i)
+            for (int j = 0; j < c; ++j) m.at<float>(i, j) = 1.0f;
+        return m;
+    }
     static Mat eye(int r, int c, int type) {
         Mat m(r, c, type);
         for (int i = 0; i < r && i < c; ++i) m.at<float>(i, i) = 1.0f;
@@ -93,6 +101,20 @@ public:
         for (int r = 0; r < rows; ++r) std::memcpy(m.data + (size_t)r * m.step, data + (size_t)r * step, (size_t)cols * esz_);
         return m;
     }
+    // 8U -> 32F or a plain copy; the destination may be the source (cv::Mat::convertTo allows it)
+    void convertTo(Mat& dst, int type) const {
+        Mat m(rows, cols, type);
+        for (int r = 0; r < rows; ++r)
+            for (int c = 0; c < cols; ++c) {
+                if (type == CV_32F)
+                    m.at<float>(r, c) = type_ == CV_32F ? at<float>(r, c) : (float)at<uchar>(r, c);
+                else
+                    m.at<uchar>(r, c) = at<uchar>(r, c);
+            }
+        dst = m;
+    }
+    void copyTo(Mat& dst) const { dst = clone(); }
+    Mat reshape(int) const { return *this; }  // only on the distortion path, which the bridges never take
     Mat t() const {
         Mat m(cols, rows, CV_32F);
         for (int r = 0; r < rows; ++r)
@@ -145,4 +167,33 @@ inline Mat operator-(const Mat& a) { return mshim_map(a, [](float v) { return -v
 inline Mat operator+(const Mat& a, const Mat& b) { return mshim_zip(a, b, [](float x, float y) { return x + y; }); }
 inline Mat operator-(const Mat& a, const Mat& b) { return mshim_zip(a, b, [](float x, float y) { return x - y; }); }
 inline double norm(const Mat& a) { return std::sqrt(a.dot(a)); }
+enum { NORM_L1 = 2 };
+inline double norm(const Mat& a, const Mat& b, int /*NORM_L1*/) {
+    double s = 0;
+    for (int r = 0; r < a.rows; ++r)
+        for (int c = 0; c < a.cols; ++c) s += std::fabs((double)a.at<float>(r, c) - (double)b.at<float>(r, c));
+    return s;
+}
+// (cv::Mat_<float>(r, c) << a, b, c): comma initialiser
+template <typename T>
+class Mat_ : public Mat {
+public:
+    Mat_(int r, int c) : Mat(r, c, CV_32F) {}
+    struct Init {
+        Mat_* m;
+        int k;
+        Init operator,(T v) {
+            m->template at<T>(k / m->cols, k % m->cols) = v;
+            return Init{m, k + 1};
+        }
+        operator Mat() const { return *m; }
+    };
+    Init operator<<(T v) {
+        this->template at<T>(0, 0) = v;
+        return Init{this, 1};
+    }
+};
+inline void undistortPoints(const Mat&, Mat&, const Mat&, const Mat&, const Mat&, const Mat&) {
+    throw std::logic_error("cv::undistortPoints is not part of the stand-in: the bridges use zero distortion");
+}
 }  // namespace cv

@@ -9,7 +9,9 @@
 #pragma once
 #define MAPPOINT_H
 #define KEYFRAME_H
+#ifndef MSHIM_REAL_FRAME  // frame_objects.h keeps the reference's own include/Frame.h
 #define FRAME_H
+#endif
 
 #include <map>
 #include <set>
@@ -124,6 +126,7 @@ public:
     std::vector<size_t> GetFeaturesInArea(const float& x, const float& y, const float& r) const { return grid.area(x, y, r, -1, -1); }
 };
 
+#ifndef MSHIM_REAL_FRAME
 class Frame {
 public:
     GridHolder grid;
@@ -142,6 +145,7 @@ public:
         return grid.area(x, y, r, minLevel, maxLevel);
     }
 };
+#endif
 }  // namespace ORB_SLAM2
 
 // The reference's headers leak `using namespace std` into ORBmatcher.h (it writes `pair<size_t, size_t>` unqualified).
