@@ -11,10 +11,12 @@
 
 #include <algorithm>
 
+#include <atomic>
+
 #include "orb_plan.h"
 #include "extract_kernels.h"
 
-static unsigned long long g_launches = 0;
+static std::atomic<unsigned long long> g_launches{0};  // handles are used from several threads (src/Frame.cc:58-61)
 
 // Programmatic dependent launch: a kernel launched with launch_pdl may be scheduled while its predecessor in the stream is
 // still draining; it calls pdl_enter() before touching anything the predecessor wrote (griddepcontrol.wait returns once
@@ -1771,15 +1773,14 @@ cudaError_t orbk_encode_level_map(CUtensorMap* out, const uint8_t* base, int col
     typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-    static EncodeFn fn = nullptr;
-    if (!fn) {
+    static const EncodeFn fn = []() -> EncodeFn {  // looked up once, thread-safe
         void* p = nullptr;
         cudaDriverEntryPointQueryResult q;
-        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
-        if (e != cudaSuccess) return e;
-        if (q != cudaDriverEntryPointSuccess || !p) return cudaErrorNotSupported;
-        fn = (EncodeFn)p;
-    }
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            return nullptr;
+        return (EncodeFn)p;
+    }();
+    if (!fn) return cudaErrorNotSupported;
     if (((uintptr_t)base & 15) || (pitch & 15) || (plane & 15)) return cudaErrorMisalignedAddress;
     cuuint64_t gdim[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)(frames > 0 ? frames : 1)};
     cuuint64_t gstr[2] = {(cuuint64_t)pitch, (cuuint64_t)plane};
@@ -1790,7 +1791,7 @@ cudaError_t orbk_encode_level_map(CUtensorMap* out, const uint8_t* base, int col
     return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
 
-unsigned long long orbk_launch_count() { return g_launches; }
+unsigned long long orbk_launch_count() { return g_launches.load(); }
 void orbk_count_launch(int n) { g_launches += n; }
 
 static const size_t kOctreeSmem = (size_t)(OCT_SMEM_A + OCT_SMEM_B) * 8 + sizeof(OctShared);

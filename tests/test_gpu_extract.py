@@ -227,6 +227,33 @@ def test_device_resident_in_place_growing_batch_and_lanes():
     ex.close()
 
 
+def test_two_handles_on_two_threads():
+    # the reference runs its left and right extractor instances on two std::threads (src/Frame.cc:58-61)
+    import threading
+    rows, cols, nf = 376, 1241, 2000
+    imgs = [oracle.synth_frame(rows, cols, frame=8, right=r) for r in (0, 1)]
+    want = [oracle.extract(im, nfeatures=nf, cap=16 * nf) for im in imgs]
+    exs = [ORBextractor(nf, 1.2, 8, 20, 7) for _ in range(2)]
+    errors = []
+
+    def work(i):
+        try:
+            for _ in range(25):
+                k, d = exs[i](imgs[i])
+                assert k.tobytes() == want[i][0].tobytes() and (d == want[i][1]).all()
+        except Exception as e:  # surfaced in the main thread
+            errors.append((i, repr(e)))
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errors, errors
+    for e in exs:
+        e.close()
+
+
 def test_stage_profiling_counts_calls():
     ex = ORBextractor(1000, 1.2, 8, 20, 7, max_batch=2)
     img = oracle.synth_frame(480, 640)
