@@ -300,6 +300,34 @@ def ref_frame_features_in_area(keys, rows, cols, x, y, r, min_level=None, max_le
         cap = tot
 
 
+_REF_KEYFRAME = os.path.join(_HERE, "_ref", "libref_keyframe.so")
+_ref_keyframe = None
+
+
+def ref_keyframe_features_in_area(keys, rows, cols, x, y, r):
+    """KeyFrame::GetFeaturesInArea of the COMPILED reference (src/KeyFrame.cc:549-588) on the KeyFrame it builds from a
+    rows x cols Frame holding these keypoints: (offsets, cand); None when oracle/_ref/libref_keyframe.so is unavailable."""
+    global _ref_keyframe
+    if _ref_keyframe is None:
+        if not os.path.exists(_REF_KEYFRAME) and os.path.exists("/root/reference/src/KeyFrame.cc"):
+            subprocess.check_call(["make", "-s", "-C", _HERE, "refkeyframe"])
+        if not os.path.exists(_REF_KEYFRAME):
+            return None
+        _ref_keyframe = C.CDLL(_REF_KEYFRAME)
+    k = np.ascontiguousarray(keys, KP_DTYPE)
+    x, y, r = (np.ascontiguousarray(a, np.float32) for a in (x, y, r))
+    off = np.zeros(len(x) + 1, np.int32)
+    cap = max(64, 64 * len(x))
+    fn = _ref_keyframe.refm_keyframe_features_in_area
+    fn.restype = C.c_int
+    while True:
+        cand = np.zeros(cap, np.int32)
+        tot = fn(_p(k), len(k), int(rows), int(cols), len(x), _p(x), _p(y), _p(r), _p(off), _p(cand), cap)
+        if tot <= cap:
+            return off, cand[:tot].copy()
+        cap = tot
+
+
 def _featvec_csr(fv):
     """dict node -> list of feature indices  ->  (sorted nodes, offsets, flat indices) int32 arrays."""
     nodes = np.array(sorted(fv), np.int32)

@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <list>
 #include <memory>
 #include <stdexcept>
 #include <vector>
@@ -113,7 +114,15 @@ public:
             }
         dst = m;
     }
-    void copyTo(Mat& dst) const { dst = clone(); }
+    // like cv::Mat::copyTo: a destination of the right shape is written in place (it may be a view), otherwise replaced
+    void copyTo(Mat& dst) const {
+        if (dst.data && dst.rows == rows && dst.cols == cols && dst.type_ == type_) {
+            for (int r = 0; r < rows; ++r) std::memmove(dst.data + (size_t)r * dst.step, data + (size_t)r * step, (size_t)cols * esz_);
+        } else {
+            dst = clone();
+        }
+    }
+    void copyTo(Mat&& dst) const { copyTo(dst); }
     Mat reshape(int) const { return *this; }  // only on the distortion path, which the bridges never take
     Mat t() const {
         Mat m(cols, rows, CV_32F);

@@ -8,7 +8,9 @@
 // come from the oracle's restatement, which tests/test_search_oracle.py pins separately.
 #pragma once
 #define MAPPOINT_H
+#ifndef MSHIM_REAL_KEYFRAME  // keyframe_objects.h keeps the reference's own include/KeyFrame.h
 #define KEYFRAME_H
+#endif
 #ifndef MSHIM_REAL_FRAME  // frame_objects.h keeps the reference's own include/Frame.h
 #define FRAME_H
 #endif
@@ -63,6 +65,8 @@ public:
         return it == indexIn.end() ? -1 : it->second;
     }
     bool IsInKeyFrame(KeyFrame* kf) { return indexIn.count(kf) != 0; }
+    std::map<KeyFrame*, size_t> GetObservations() { return std::map<KeyFrame*, size_t>(); }
+    void EraseObservation(KeyFrame*) {}
     void AddObservation(KeyFrame* kf, size_t idx) { addedObservations.push_back({kf, idx}); }
     void Replace(MapPoint* p) { replacedBy = p; }
 };
@@ -103,6 +107,7 @@ struct GridHolder {  // what GetFeaturesInArea needs, in the oracle's layout
     }
 };
 
+#ifndef MSHIM_REAL_KEYFRAME
 class KeyFrame {
 public:
     GridHolder grid;
@@ -125,6 +130,7 @@ public:
     bool IsInImage(const float& x, const float& y) const { return x >= grid.mnMinX && x < grid.mnMaxX && y >= grid.mnMinY && y < grid.mnMaxY; }
     std::vector<size_t> GetFeaturesInArea(const float& x, const float& y, const float& r) const { return grid.area(x, y, r, -1, -1); }
 };
+#endif
 
 #ifndef MSHIM_REAL_FRAME
 class Frame {

@@ -82,6 +82,21 @@ def test_oracle_equals_compiled_reference(name):
         assert a.tobytes() == b.tobytes(), name   # floats compared bit for bit
 
 
+@needs_ref
+def test_keyframe_windows_equal_compiled_reference():
+    """KeyFrame::GetFeaturesInArea (src/KeyFrame.cc:549-588) of the compiled reference against the oracle's walk without level test."""
+    for seed, clustered in ((3, False), (4, True)):
+        rng = np.random.default_rng(seed)
+        rows, cols = 480, 752
+        F = make_frame(rng, 1500, cols=cols, rows=rows, clustered=clustered)
+        _, _, u, v, _, _ = projected_queries(rng, F, 400, outside=0.1)
+        r = rng.choice([2.5, 4.0, 10.0, 37.5, 100.0], 400).astype(np.float32)
+        ref = oracle.ref_keyframe_features_in_area(F.keys_un, rows, cols, u, v, r)
+        assert ref is not None
+        off, cand = oracle.features_in_area(F, u, v, r, None, None)
+        assert np.array_equal(off, ref[0]) and np.array_equal(cand, ref[1]) and len(cand) > 3000
+
+
 def test_oracle_matches_committed_reference_digests():
     gold = json.load(open(GOLDEN))
     for name in sorted(CASES):
