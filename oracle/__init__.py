@@ -508,6 +508,20 @@ def ref_search_by_projection_loop(KF, claimed, qdesc, u, v, radius):
     return int(n), out
 
 
+def ref_fuse_search(KF, qdesc, u, v, level, th, variant=0):
+    """The compiled reference's Fuse (src/ORBmatcher.cc:504-568, variant 1: the Scw overload :570-634), search part; the oracle's
+    counterpart is search_kf_window(KF, None, ..., radius = th * scale[level], level, max_dist=TH_LOW)."""
+    q = np.ascontiguousarray(qdesc, np.uint8).reshape(-1, 32)
+    out = np.zeros(len(q), np.int32)
+    fr = _frame(KF)
+    f = lambda a: np.ascontiguousarray(a, np.float32)
+    fn = ref_match_lib().refm_fuse_search
+    fn.restype = C.c_int
+    n = fn(C.byref(fr), _p(f(KF.mvScaleFactors)), len(q), _p(q), _p(f(u)), _p(f(v)), _p(np.ascontiguousarray(level, np.int32)), C.c_float(th),
+           int(variant), _p(out))
+    return int(n), out
+
+
 def ref_search_by_sim3(KF2, qdesc, u, v, level, th):
     """The compiled reference's SearchBySim3 (src/ORBmatcher.cc:636-730) with s12 = 1, R12 = I, t12 = 0; the oracle's counterpart is
     search_kf_window(KF2, None, ..., radius = th * scale[level], level, max_dist=TH_HIGH)."""

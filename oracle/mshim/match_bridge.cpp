@@ -353,6 +353,45 @@ int refm_search_by_sim3(const OrcFrame* KF2, const float* mvScaleFactors, int nq
     return n;
 }
 
+// ORBmatcher::Fuse(pKF, vpMapPoints, th) (src/ORBmatcher.cc:504-568; variant 0) and Fuse(pKF, Scw, vpPoints, th, vpReplacePoint)
+// (:570-634; variant 1), search part.  Every second feature of the keyframe holds a map point with more observations than the
+// queries, so a hit on it shows up as pMP->Replace(that point) / vpReplacePoint, a hit on a free feature as pMP->AddObservation(pKF, idx):
+// either way the feature the reference chose is recorded.
+int refm_fuse_search(const OrcFrame* KF, const float* mvScaleFactors, int nq, const uint8_t* qdesc, const float* u, const float* v,
+                     const int* level, float th, int variant, int* featureOfQuery) {
+    KeyFrame K;
+    fill_grid(K.grid, KF);
+    K.N = KF->N;
+    for (int i = 0; i < KF->N; ++i) K.mvKeysUn.push_back(to_cv(KF->keysUn[i]));
+    K.mDescriptors = desc_mat(KF->desc, KF->N);
+    K.mvScaleFactors.assign(mvScaleFactors, mvScaleFactors + NSCALE);
+    Pool pool;
+    K.mapPoints.assign(KF->N, nullptr);
+    for (int i = 0; i < KF->N; i += 2) {
+        K.mapPoints[i] = pool.make(i);
+        K.mapPoints[i]->nObs = 5;
+    }
+    std::vector<MapPoint*> pts;
+    for (int i = 0; i < nq; ++i) {
+        MapPoint* p = pool.make(-1);
+        p->desc = desc_mat(qdesc + 32 * (size_t)i, 1);
+        p->pos = vec3(u[i], v[i], 1.0f);
+        p->normal = vec3(0.0f, 0.0f, 1e6f);
+        p->predictedLevel = level[i];
+        pts.push_back(p);
+        featureOfQuery[i] = -1;
+    }
+    ORBmatcher m(0.6f, true);
+    std::vector<MapPoint*> repl(nq, nullptr);
+    const int n = variant == 0 ? m.Fuse(&K, pts, th) : m.Fuse(&K, cv::Mat::eye(4, 4, CV_32F), pts, th, repl);
+    for (int i = 0; i < nq; ++i) {
+        if (!pts[i]->addedObservations.empty()) featureOfQuery[i] = (int)pts[i]->addedObservations[0].second;
+        if (pts[i]->replacedBy) featureOfQuery[i] = pts[i]->replacedBy->id;
+        if (repl[i]) featureOfQuery[i] = repl[i]->id;
+    }
+    return n;
+}
+
 // ORBmatcher::DescriptorDistance, src/ORBmatcher.cc:896-908.
 int refm_descriptor_distance(const uint8_t* a, const uint8_t* b) { return ORBmatcher::DescriptorDistance(desc_mat(a, 1), desc_mat(b, 1)); }
 }

@@ -181,6 +181,23 @@ def case_sim3(impl, seed, th):
     return oracle.search_kf_window(KF2, None, q, u, v, radius, level, 100)
 
 
+def case_fuse(impl, seed, th, variant):
+    rng = np.random.default_rng(seed)
+    KF = make_frame(rng, 1800)
+    src, q, u, v, level, _ = projected_queries(rng, KF, 1200, max_flips=40, outside=0.0)
+    keep = _inside(KF, u, v)
+    q, u, v, level = q[keep], u[keep], v[keep], level[keep]
+    radius = (np.float32(th) * SCALE[level]).astype(np.float32)
+    if impl == "gpu":
+        m = _gpu(0.6, True)
+        r = m.FuseSearch(KF, q, u, v, radius, level)
+        m.close()
+        return r
+    if impl == "reference":
+        return oracle.ref_fuse_search(KF, q, u, v, level, th, variant)
+    return oracle.search_kf_window(KF, None, q, u, v, radius, level, 50)
+
+
 CASES = {
     "projection_map_mono": lambda impl: case_projection_map(impl, 11, 1.0, False, 0.8, False),
     "projection_map_stereo_th3": lambda impl: case_projection_map(impl, 12, 3.0, True, 0.8, True),
@@ -192,6 +209,8 @@ CASES = {
     "reloc_noori_tight": lambda impl: case_reloc(impl, 62, False, 3.0, 64),
     "loop_th10": lambda impl: case_loop(impl, 71, 10),
     "sim3_th75": lambda impl: case_sim3(impl, 81, 7.5),
+    "fuse_th3": lambda impl: case_fuse(impl, 91, 3.0, 0),
+    "fuse_scw_th4": lambda impl: case_fuse(impl, 92, 4.0, 1),
     "bow_ori": lambda impl: case_bow(impl, 31, 0.75, True),
     "bow_noori_tight": lambda impl: case_bow(impl, 32, 0.6, False),
     "triangulation": lambda impl: case_triangulation(impl, 41, False),
