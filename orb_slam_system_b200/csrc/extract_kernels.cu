@@ -372,7 +372,7 @@ __device__ __forceinline__ unsigned even_lanes(unsigned w) { return w & 0x00ff00
 __device__ __forceinline__ unsigned odd_lanes(unsigned w) { return __byte_perm(w, 0u, 0x4341); }
 
 __global__ void __launch_bounds__(DET_THREADS) k_detect(const __grid_constant__ OrbPlan plan,
-                                                        const CUtensorMap* __restrict__ maps) {
+                                                        const CUtensorMap* __restrict__ maps, int tileOffset) {
     pdl_release();  // nothing before the TMA load below depends on the pyramid kernels
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int detRows = plan.detRows;
@@ -383,7 +383,7 @@ __global__ void __launch_bounds__(DET_THREADS) k_detect(const __grid_constant__ 
     DetectTail& sm = *reinterpret_cast<DetectTail*>(smem_raw + det_img_bytes(detRows) + det_sc_bytes(detRows));
 
     const int f = blockIdx.y;
-    int tile = blockIdx.x;
+    int tile = blockIdx.x + tileOffset;
     int l = 0;
     for (; l < plan.nlevels; ++l) {
         const OrbLevel& L = plan.lv[l];
@@ -1818,24 +1818,44 @@ cudaError_t orbk_run_extract(const OrbPlan& plan, int nframes, orb_keypoint_dev*
     e = cudaMemsetAsync(plan.status, 0, sizeof(int) * nframes, st);
     if (e != cudaSuccess) return e;
     if (ev) cudaEventRecord(ev[0], st);
+    // Level 0 is the input: its detect tiles do not need the pyramid.  Outside profiling the pyramid chain (six dependent,
+    // shrinking launches that mostly wait) therefore runs on the second stream next to the level-0 detect, followed there by the
+    // blur; the first stream picks the other levels up once the pyramid is complete.
+    const int tiles0 = plan.lv[0].src == 0 ? plan.lv[0].nTiles : 0;
+    const bool split = !ev && tiles0 > 0 && plan.lv[0].tileBase == 0;
+    cudaStream_t stp = split ? st2 : st;  // where the pyramid is built
+    if (split) {
+        e = cudaEventRecord(ss.fork, st);
+        if (e != cudaSuccess) return e;
+        e = cudaStreamWaitEvent(st2, ss.fork, 0);
+        if (e != cudaSuccess) return e;
+        k_detect<<<dim3(tiles0, nframes), DET_THREADS, detect_smem_bytes(plan.detRows), st>>>(plan, d_maps->m, 0);
+        ++g_launches;
+    }
     // pyramid: level l = resize(level l-1); same-size levels alias their source
+    bool first = true;
     for (int l = 1; l < plan.nlevels; ++l) {
         const OrbLevel& D = plan.lv[l];
         if (D.src != l) continue;
         const OrbLevel& S = plan.lv[plan.lv[l - 1].src];
         if (D.xgrp && D.rszTiled) {
             dim3 grid((D.cols + RSZ_W - 1) / RSZ_W, (D.rows + RSZ_H - 1) / RSZ_H, nframes);
-            launch_pdl(k_resize_tile, grid, dim3(RSZ_THREADS), 0, st, &d_maps->rsz[l], plan.frameBase, D.img, D.pitch, D.plane, D.rows, D.cols,
-                       D.xgrp, D.xcoef4, D.ytab, D.ycoef);
+            if (first && split)  // first kernel behind an event wait: a plain launch
+                k_resize_tile<<<grid, RSZ_THREADS, 0, stp>>>(&d_maps->rsz[l], plan.frameBase, D.img, D.pitch, D.plane, D.rows, D.cols, D.xgrp,
+                                                             D.xcoef4, D.ytab, D.ycoef);
+            else
+                launch_pdl(k_resize_tile, grid, dim3(RSZ_THREADS), 0, stp, &d_maps->rsz[l], plan.frameBase, D.img, D.pitch, D.plane, D.rows,
+                           D.cols, D.xgrp, D.xcoef4, D.ytab, D.ycoef);
         } else if (D.xgrp) {
             dim3 block(64, 4), grid((D.cols + 255) / 256, (D.rows + 15) / 16, nframes);
-            k_resize4<<<grid, block, 0, st>>>(S.img, S.pitch, S.plane, D.img, D.pitch, D.plane, D.rows, D.cols, D.xgrp,
-                                              D.xcoef4, D.ytab, D.ycoef);
+            k_resize4<<<grid, block, 0, stp>>>(S.img, S.pitch, S.plane, D.img, D.pitch, D.plane, D.rows, D.cols, D.xgrp,
+                                               D.xcoef4, D.ytab, D.ycoef);
         } else {
             dim3 block(64, 4), grid((D.cols + 255) / 256, (D.rows + 3) / 4, nframes);
-            k_resize<<<grid, block, 0, st>>>(S.img, S.pitch, S.plane, D.img, D.pitch, D.plane, D.rows, D.cols, D.xtab,
-                                             D.xcoef, D.ytab, D.ycoef);
+            k_resize<<<grid, block, 0, stp>>>(S.img, S.pitch, S.plane, D.img, D.pitch, D.plane, D.rows, D.cols, D.xtab,
+                                              D.xcoef, D.ytab, D.ycoef);
         }
+        first = false;
         ++g_launches;
     }
     if (ev) cudaEventRecord(ev[1], st);
@@ -1844,18 +1864,30 @@ cudaError_t orbk_run_extract(const OrbPlan& plan, int nframes, orb_keypoint_dev*
         if (plan.lv[l].src == l)
             blurTiles += ((plan.lv[l].cols + BLUR_TW - 1) / BLUR_TW) * ((plan.lv[l].rows + BLUR_TH - 1) / BLUR_TH);
     if (!ev) {
-        // fork: the blur needs only the pyramid and overlaps detect + octree on the second stream
-        e = cudaEventRecord(ss.fork, st);
-        if (e != cudaSuccess) return e;
-        e = cudaStreamWaitEvent(st2, ss.fork, 0);
-        if (e != cudaSuccess) return e;
+        // the blur needs only the pyramid and overlaps detect + octree on the second stream
+        if (split) {
+            e = cudaEventRecord(ss.pyr, st2);
+            if (e != cudaSuccess) return e;
+        } else {
+            e = cudaEventRecord(ss.fork, st);
+            if (e != cudaSuccess) return e;
+            e = cudaStreamWaitEvent(st2, ss.fork, 0);
+            if (e != cudaSuccess) return e;
+        }
         k_blur<<<dim3(blurTiles, nframes), BLUR_THREADS, 0, st2>>>(plan, d_maps->blr);
         ++g_launches;
         e = cudaEventRecord(ss.join, st2);
         if (e != cudaSuccess) return e;
     }
-    if (plan.totalTiles > 0) {
-        launch_pdl(k_detect, dim3(plan.totalTiles, nframes), dim3(DET_THREADS), detect_smem_bytes(plan.detRows), st, plan, d_maps->m);
+    if (split) {
+        if (plan.totalTiles > tiles0) {
+            e = cudaStreamWaitEvent(st, ss.pyr, 0);
+            if (e != cudaSuccess) return e;
+            k_detect<<<dim3(plan.totalTiles - tiles0, nframes), DET_THREADS, detect_smem_bytes(plan.detRows), st>>>(plan, d_maps->m, tiles0);
+            ++g_launches;
+        }
+    } else if (plan.totalTiles > 0) {
+        launch_pdl(k_detect, dim3(plan.totalTiles, nframes), dim3(DET_THREADS), detect_smem_bytes(plan.detRows), st, plan, d_maps->m, 0);
         ++g_launches;
     }
     if (ev) cudaEventRecord(ev[2], st);

@@ -39,6 +39,7 @@ cudaError_t orbk_encode_level_map(CUtensorMap* out, const uint8_t* base, int col
 struct OrbStreams {
     cudaStream_t st, st2;
     cudaEvent_t fork, join;
+    cudaEvent_t pyr;  // the pyramid is complete (recorded on st2 when it builds the pyramid next to the level-0 detect)
 };
 cudaError_t orbk_run_extract(const OrbPlan& plan, int nframes, orb_keypoint_dev* d_kps, uint8_t* d_desc, int cap,
                              int* d_counts, const OrbStreams& ss, const DetectMaps* d_maps, cudaEvent_t* ev = nullptr);

@@ -125,12 +125,12 @@ struct orb_extractor {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t stream2 = nullptr;  // blur runs here, concurrently with detect + octree
-    cudaEvent_t evFork = nullptr, evJoin = nullptr;
+    cudaEvent_t evFork = nullptr, evJoin = nullptr, evPyr = nullptr;
     // second kernel lane: the device-resident path runs the two halves of a batch concurrently
     enum { MAX_LANES = 4 };
     cudaStream_t laneSt[MAX_LANES] = {}, laneSt2[MAX_LANES] = {};
-    cudaEvent_t laneFork[MAX_LANES] = {}, laneJoin[MAX_LANES] = {}, laneMerge[MAX_LANES] = {}, evSplit = nullptr;
-    OrbStreams lane(int i) const { return i == 0 ? streams() : OrbStreams{laneSt[i], laneSt2[i], laneFork[i], laneJoin[i]}; }
+    cudaEvent_t laneFork[MAX_LANES] = {}, laneJoin[MAX_LANES] = {}, laneMerge[MAX_LANES] = {}, lanePyr[MAX_LANES] = {}, evSplit = nullptr;
+    OrbStreams lane(int i) const { return i == 0 ? streams() : OrbStreams{laneSt[i], laneSt2[i], laneFork[i], laneJoin[i], lanePyr[i]}; }
     int lanes = 2;
     // host-buffer pipeline: copies in and out run on their own streams, chunk by chunk
     cudaStream_t streamIn = nullptr, streamOut = nullptr, streamCnt = nullptr;
@@ -160,7 +160,7 @@ struct orb_extractor {
         int srows = 0, scols = 0, channels = 1, bgr = 0, variant = 4, drows = 0, dcols = 0;
         float *d_mapx = nullptr, *d_mapy = nullptr;
     } ing;
-    OrbStreams streams() const { return OrbStreams{stream, stream2, evFork, evJoin}; }
+    OrbStreams streams() const { return OrbStreams{stream, stream2, evFork, evJoin, evPyr}; }
     int max_batch = 1;
     OrbPlan plan;            // current shape (plan.rows == 0: none)
     DetectMaps maps;         // TMA descriptors of the internal level buffers (host copy)
@@ -501,12 +501,14 @@ extern "C" int orb_extractor_create(const orb_params* params, int max_rows, int 
     if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking);
     if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&h->evFork, cudaEventDisableTiming);
     if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&h->evJoin, cudaEventDisableTiming);
+    if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&h->evPyr, cudaEventDisableTiming);
     for (int i = 1; i < orb_extractor::MAX_LANES && ce == cudaSuccess; ++i) {
         ce = cudaStreamCreateWithFlags(&h->laneSt[i], cudaStreamNonBlocking);
         if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&h->laneSt2[i], cudaStreamNonBlocking);
         if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&h->laneFork[i], cudaEventDisableTiming);
         if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&h->laneJoin[i], cudaEventDisableTiming);
         if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&h->laneMerge[i], cudaEventDisableTiming);
+        if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&h->lanePyr[i], cudaEventDisableTiming);
     }
     if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&h->evSplit, cudaEventDisableTiming);
     if (const char* e = getenv("ORB_B200_LANES")) h->lanes = std::min<int>(orb_extractor::MAX_LANES, std::max(1, atoi(e)));
@@ -561,6 +563,7 @@ extern "C" void orb_extractor_destroy(orb_extractor* h) {
         if (h->laneFork[i]) cudaEventDestroy(h->laneFork[i]);
         if (h->laneJoin[i]) cudaEventDestroy(h->laneJoin[i]);
         if (h->laneMerge[i]) cudaEventDestroy(h->laneMerge[i]);
+        if (h->lanePyr[i]) cudaEventDestroy(h->lanePyr[i]);
         if (h->laneSt2[i]) cudaStreamDestroy(h->laneSt2[i]);
         if (h->laneSt[i]) cudaStreamDestroy(h->laneSt[i]);
     }
@@ -570,6 +573,7 @@ extern "C" void orb_extractor_destroy(orb_extractor* h) {
     if (h->streamCnt) cudaStreamDestroy(h->streamCnt);
     if (h->evFork) cudaEventDestroy(h->evFork);
     if (h->evJoin) cudaEventDestroy(h->evJoin);
+    if (h->evPyr) cudaEventDestroy(h->evPyr);
     if (h->stream2) cudaStreamDestroy(h->stream2);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
