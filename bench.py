@@ -594,7 +594,7 @@ def main():
             line["shard_match"] = shard
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            nfr = max(16, 2 * cores)
+            nfr = max(64, 8 * cores)  # ~1 s of wall clock, 10-20 s of CPU work on 16 cores
             rate, kind, _ = cpu_reference_rate(nfr, cores)
             line["cpu_baseline"] = {"value": rate, "unit": "frames/s", "cores": cores, "kind": kind,
                                     "sample": f"{nfr} synthetic KITTI-shape frames, one frame per host thread"}
