@@ -400,6 +400,22 @@ def _search_fn(name, impl):
     return fn
 
 
+def ref_bruteforce_many(q, t, nthreads):
+    """BASELINE config 4 with the reference's own DescriptorDistance on the host: q [npairs, nq, 32], t [npairs, nt, 32].
+    Returns (seconds, best_idx, best_dist, second_dist)."""
+    L = ref_match_lib()
+    q = np.ascontiguousarray(q, np.uint8)
+    t = np.ascontiguousarray(t, np.uint8)
+    npairs, nq, _ = q.shape
+    nt = t.shape[1]
+    bi = np.zeros((npairs, nq), np.int32)
+    bd = np.zeros((npairs, nq), np.int32)
+    sd = np.zeros((npairs, nq), np.int32)
+    L.refm_bruteforce_many.restype = C.c_double
+    secs = L.refm_bruteforce_many(_p(q), _p(t), npairs, nq, nt, int(nthreads), _p(bi), _p(bd), _p(sd))
+    return secs, bi, bd, sd
+
+
 def ref_descriptor_distance(a, b):
     """ORBmatcher::DescriptorDistance of the compiled reference."""
     a, b = np.ascontiguousarray(a, np.uint8), np.ascontiguousarray(b, np.uint8)
@@ -670,6 +686,22 @@ def ref_lib():
     return _ref
 
 
+_ref_fast = None
+_REF_FAST_LIB = os.path.join(os.path.dirname(_REF_LIB), "libref_orb_fast.so")
+
+
+def ref_fast_lib():
+    """CDLL of the timing-only build of the reference extractor (oracle/Makefile reffast: -O3 -march=x86-64-v3), or None."""
+    global _ref_fast
+    if _ref_fast is None:
+        if not os.path.exists(_REF_FAST_LIB):
+            return None
+        _ref_fast = C.CDLL(_REF_FAST_LIB)
+        _ref_fast.ref_extract_many.restype = C.c_double
+        _ref_fast.ref_extract_many.argtypes = ref_lib().ref_extract_many.argtypes if ref_lib() is not None else None
+    return _ref_fast
+
+
 def ref_extract(img, nfeatures=1000, scaleFactor=1.2, nlevels=8, iniThFAST=20, minThFAST=7, cap=None):
     img = _img(img)
     cap = cap or 8 * max(nfeatures, 64)
@@ -684,11 +716,13 @@ def ref_extract(img, nfeatures=1000, scaleFactor=1.2, nlevels=8, iniThFAST=20, m
     return kps[: cnt.value].copy(), desc[: cnt.value].copy()
 
 
-def ref_extract_many(rows, cols, nframes, nthreads, first_frame=0, seed=7, **params):
+def ref_extract_many(rows, cols, nframes, nthreads, first_frame=0, seed=7, fast=False, **params):
+    """Seconds the reference extractor needs for nframes synthetic frames on nthreads host threads (frame synthesis is
+    outside the clock) and the keypoint total.  fast: the -O3 timing-only build (ref_fast_lib) instead of the parity build."""
     p = dict(DEFAULT)
     p.update(params)
     tot = C.c_longlong(0)
-    secs = ref_lib().ref_extract_many(p["nfeatures"], C.c_float(p["scaleFactor"]), p["nlevels"],
+    secs = (ref_fast_lib() if fast else ref_lib()).ref_extract_many(p["nfeatures"], C.c_float(p["scaleFactor"]), p["nlevels"],
                                       p["iniThFAST"], p["minThFAST"], rows, cols, seed, first_frame,
                                       nframes, nthreads, C.byref(tot))
     return secs, tot.value

@@ -5,6 +5,9 @@
 // flattens what it wrote.  Cameras are the identity (R = I, t = 0, fx = fy = 1, cx = cy = 0) and map points sit at depth 1,
 // so a point meant to project to pixel (u, v) is the world point (u, v, 1) and the reference's own projection arithmetic
 // returns exactly (u, v): the searches start from the same numbers on both sides.
+#include <chrono>
+#include <climits>
+#include <thread>
 #include "ORBmatcher.h"  // the reference's header; its three object headers are replaced by orbslam_objects.h
 
 #include <climits>
@@ -394,4 +397,39 @@ int refm_fuse_search(const OrcFrame* KF, const float* mvScaleFactors, int nq, co
 
 // ORBmatcher::DescriptorDistance, src/ORBmatcher.cc:896-908.
 int refm_descriptor_distance(const uint8_t* a, const uint8_t* b) { return ORBmatcher::DescriptorDistance(desc_mat(a, 1), desc_mat(b, 1)); }
+
+// BASELINE config 4 on the host cores: the shared scan (src/ORBmatcher.cc:49-55) over all train rows in index order, every
+// distance from the reference's own ORBmatcher::DescriptorDistance; npairs independent (query set, train set) pairs of
+// nq x nt rows spread over nthreads std::threads.  Returns the wall-clock seconds of the scan (buffers are the caller's).
+double refm_bruteforce_many(const uint8_t* q, const uint8_t* t, int npairs, int nq, int nt, int nthreads, int32_t* best_idx,
+                            int32_t* best_dist, int32_t* second_dist) {
+    auto work = [&](int p0, int p1) {
+        for (int p = p0; p < p1; ++p) {
+            const cv::Mat Q = desc_mat(q + (size_t)p * nq * 32, nq), T = desc_mat(t + (size_t)p * nt * 32, nt);
+            for (int i = 0; i < nq; ++i) {
+                const cv::Mat dq = Q.row(i);
+                int best = INT_MAX, second = INT_MAX, idx = -1;
+                for (int j = 0; j < nt; ++j) {
+                    const int d = ORBmatcher::DescriptorDistance(dq, T.row(j));
+                    if (d < best) {
+                        second = best;
+                        best = d;
+                        idx = j;
+                    } else if (d < second) {
+                        second = d;
+                    }
+                }
+                best_idx[(size_t)p * nq + i] = idx;
+                best_dist[(size_t)p * nq + i] = best;
+                second_dist[(size_t)p * nq + i] = second;
+            }
+        }
+    };
+    const auto t0 = std::chrono::steady_clock::now();
+    nthreads = std::max(1, std::min(nthreads, npairs));
+    std::vector<std::thread> th;
+    for (int k = 0; k < nthreads; ++k) th.emplace_back(work, (int)((long long)npairs * k / nthreads), (int)((long long)npairs * (k + 1) / nthreads));
+    for (auto& x : th) x.join();
+    return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
 }

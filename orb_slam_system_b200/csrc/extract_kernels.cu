@@ -1746,21 +1746,25 @@ cudaError_t orbk_ingest(const uint8_t* raw, int nframes, int srows, int scols, s
 // linear transfer per chunk (row-by-row 2D copies are several times slower over PCIe), are laid
 // out with the internal 64-byte aligned pitch here.  4 bytes per thread, funnel-shifted loads.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_repitch(const uint8_t* __restrict__ dense, int rows, int cols, uint8_t* __restrict__ dst,
-                                                 int pitch, unsigned long long plane) {
+// `dense` is the 4-byte aligned base of the whole landing buffer and frame0 the first frame of this chunk inside it: a
+// chunk's own first byte (frame0 * rows * cols) need not be word aligned (odd-area frames), so the word index and the
+// funnel shift are both taken from the offset relative to the aligned base.
+__global__ void __launch_bounds__(256) k_repitch(const uint8_t* __restrict__ dense, int frame0, int rows, int cols,
+                                                 uint8_t* __restrict__ dst, int pitch, unsigned long long plane) {
     pdl_enter();
     const int k = blockIdx.x * 256 + threadIdx.x;  // output word in the row
     const int y = blockIdx.y, f = blockIdx.z;
     if (4 * k >= cols) return;
-    const size_t off = ((size_t)f * rows + y) * cols + 4 * (size_t)k;  // byte offset in the dense buffer
+    const size_t off = ((size_t)(frame0 + f) * rows + y) * cols + 4 * (size_t)k;  // byte offset in the dense buffer
     const unsigned* w = reinterpret_cast<const unsigned*>(dense) + (off >> 2);
     const unsigned lo = __ldg(w), hi = __ldg(w + 1);  // the staging buffer has 8 bytes of slack
     *reinterpret_cast<unsigned*>(dst + f * plane + (size_t)y * pitch + 4 * k) = __funnelshift_r(lo, hi, (unsigned)(off & 3) * 8);
 }
 
-cudaError_t orbk_repitch(const uint8_t* dense, int nframes, int rows, int cols, uint8_t* dst, int pitch, unsigned long long plane,
-                         cudaStream_t st) {
-    k_repitch<<<dim3((cols + 1023) / 1024, rows, nframes), 256, 0, st>>>(dense, rows, cols, dst, pitch, plane);
+cudaError_t orbk_repitch(const uint8_t* dense, int frame0, int nframes, int rows, int cols, uint8_t* dst, int pitch,
+                         unsigned long long plane, cudaStream_t st) {
+    if ((uintptr_t)dense & 3) return cudaErrorMisalignedAddress;
+    k_repitch<<<dim3((cols + 1023) / 1024, rows, nframes), 256, 0, st>>>(dense, frame0, rows, cols, dst, pitch, plane);
     orbk_count_launch(1);
     return cudaGetLastError();
 }

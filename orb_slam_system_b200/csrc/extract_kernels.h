@@ -45,9 +45,10 @@ cudaError_t orbk_run_extract(const OrbPlan& plan, int nframes, orb_keypoint_dev*
                              int* d_counts, const OrbStreams& ss, const DetectMaps* d_maps, cudaEvent_t* ev = nullptr);
 void orbk_build_ic_table(int2* out /* 8*32 */);
 void orbk_build_pair_table(float4* out /* 182 */);
-// Dense frames (row stride == cols) in `dense` -> pitched level-0 layout.
-cudaError_t orbk_repitch(const uint8_t* dense, int nframes, int rows, int cols, uint8_t* dst, int pitch, unsigned long long plane,
-                         cudaStream_t st);
+// Dense frames (row stride == cols) frame0 .. frame0 + nframes of the landing buffer `dense` (4-byte aligned base of
+// the whole buffer) -> pitched level-0 layout at dst.
+cudaError_t orbk_repitch(const uint8_t* dense, int frame0, int nframes, int rows, int cols, uint8_t* dst, int pitch,
+                         unsigned long long plane, cudaStream_t st);
 unsigned long long orbk_launch_count();
 void orbk_count_launch(int n);
 // Ingest fused into the level-0 load: cv::remap (INTER_LINEAR, CV_32FC1 maps; mapx == NULL: none) and / or

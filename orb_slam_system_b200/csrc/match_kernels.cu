@@ -8,6 +8,8 @@
 #include <cuda_runtime.h>
 #include <limits.h>
 #include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "match_kernels.h"
 
@@ -39,11 +41,13 @@ __global__ void __launch_bounds__(MA_THREADS) k_match_all(const uint8_t* __restr
                                                           size_t q_stride, const uint8_t* __restrict__ t,
                                                           const int* __restrict__ nt, size_t t_stride,
                                                           int* __restrict__ best_idx, int* __restrict__ best_dist,
-                                                          int* __restrict__ second_dist, size_t out_stride, unsigned key_scale) {
+                                                          int* __restrict__ second_dist, size_t out_stride, unsigned key_scale,
+                                                          int only_huge) {
     __shared__ uint4 tile[MA_TILE][2];
     const int p = blockIdx.y;
     const int nQ = nq[p], nT = nt[p];
     if ((int)(blockIdx.x * MA_THREADS) >= nQ) return;
+    if (only_huge && nT < (1 << 22)) return;  // the tensor-core kernel (match_mma.cu) has done this pair
     const int qi = blockIdx.x * MA_THREADS + threadIdx.x;
     const uint4* Q = reinterpret_cast<const uint4*>(q + p * q_stride);
     const uint4* T = reinterpret_cast<const uint4*>(t + p * t_stride);
@@ -616,14 +620,40 @@ __global__ void __launch_bounds__(256) k_voc_descent(const uint8_t* __restrict__
 // ------------------------------------------------------------------------------------------
 void orbk_count_launch(int n);
 
-cudaError_t orbk_match_all(const uint8_t* q, const int* nq, size_t q_stride, const uint8_t* t, const int* nt,
-                           size_t t_stride, int npairs, int max_nq, int* best_idx, int* best_dist, int* second_dist,
-                           size_t out_stride, cudaStream_t st) {
+cudaError_t orbk_match_all_popc(const uint8_t* q, const int* nq, size_t q_stride, const uint8_t* t, const int* nt, size_t t_stride,
+                                int npairs, int max_nq, int* best_idx, int* best_dist, int* second_dist, size_t out_stride,
+                                int only_huge, cudaStream_t st) {
     if (npairs <= 0 || max_nq <= 0) return cudaSuccess;
     dim3 grid((max_nq + MA_THREADS - 1) / MA_THREADS, npairs);
-    k_match_all<<<grid, MA_THREADS, 0, st>>>(q, nq, q_stride, t, nt, t_stride, best_idx, best_dist, second_dist, out_stride, 1u << 22);
+    k_match_all<<<grid, MA_THREADS, 0, st>>>(q, nq, q_stride, t, nt, t_stride, best_idx, best_dist, second_dist, out_stride, 1u << 22,
+                                             only_huge);
     orbk_count_launch(1);
     return cudaGetLastError();
+}
+
+cudaError_t orbk_match_all_mma(const uint8_t* q, const int* nq, size_t q_stride, const uint8_t* t, const int* nt, size_t t_stride,
+                               int npairs, int max_nq, int* best_idx, int* best_dist, int* second_dist, size_t out_stride, int kind,
+                               int variant, cudaStream_t st);
+
+// Brute-force scan of npairs (query set, train set) pairs.  The tensor-core kernel (match_mma.cu) does every pair whose
+// train set has fewer than 2^22 rows; k_match_all's plain path takes the rest (max_nt < 0: not known on the host, both
+// kernels are enqueued and each leaves the other's pairs alone).  ORB_B200_MATCH=popc selects the POPC / LOP3 kernel for
+// everything (the comparator of the parity tests); ORB_B200_MMA_KIND=f8 the e4m3 form of the contraction.
+cudaError_t orbk_match_all(const uint8_t* q, const int* nq, size_t q_stride, const uint8_t* t, const int* nt,
+                           size_t t_stride, int npairs, int max_nq, int max_nt, int* best_idx, int* best_dist, int* second_dist,
+                           size_t out_stride, cudaStream_t st) {
+    if (npairs <= 0 || max_nq <= 0) return cudaSuccess;
+    const char* sel = getenv("ORB_B200_MATCH");
+    if (sel && !strcmp(sel, "popc"))
+        return orbk_match_all_popc(q, nq, q_stride, t, nt, t_stride, npairs, max_nq, best_idx, best_dist, second_dist, out_stride, 0, st);
+    const char* kind = getenv("ORB_B200_MMA_KIND");
+    const char* var = getenv("ORB_B200_MMA_VARIANT");
+    cudaError_t e = orbk_match_all_mma(q, nq, q_stride, t, nt, t_stride, npairs, max_nq, best_idx, best_dist, second_dist, out_stride,
+                                       kind && !strcmp(kind, "f8") ? 1 : 0, var ? atoi(var) : 0, st);
+    if (e != cudaSuccess) return e;
+    if (max_nt < 0 || max_nt >= (1 << 22))
+        return orbk_match_all_popc(q, nq, q_stride, t, nt, t_stride, npairs, max_nq, best_idx, best_dist, second_dist, out_stride, 1, st);
+    return cudaSuccess;
 }
 
 cudaError_t orbk_match_csr(const uint8_t* q, int nq, const uint8_t* t, const int* offsets, const int* cand, int tie_last,

@@ -17,8 +17,9 @@ struct OrbStereoLevels {
     float scale[16], inv_scale[16];
 };
 
+// max_nt: largest train set, or -1 when the counts live on the device only.
 cudaError_t orbk_match_all(const uint8_t* q, const int* nq, size_t q_stride, const uint8_t* t, const int* nt,
-                           size_t t_stride, int npairs, int max_nq, int* best_idx, int* best_dist, int* second_dist,
+                           size_t t_stride, int npairs, int max_nq, int max_nt, int* best_idx, int* best_dist, int* second_dist,
                            size_t out_stride, cudaStream_t st);
 cudaError_t orbk_match_csr(const uint8_t* q, int nq, const uint8_t* t, const int* offsets, const int* cand, int tie_last,
                            int max_dist, int* best_idx, int* best_dist, int* second_dist, cudaStream_t st);

@@ -145,15 +145,19 @@ struct orb_extractor {
         uint8_t* d_desc = nullptr;
         int* d_counts = nullptr;
         int out_cap = 0;
-        cudaEvent_t evIn[MAX_CHUNKS] = {}, evDone[MAX_CHUNKS] = {}, evCnt[MAX_CHUNKS] = {};
+        cudaEvent_t evIn[MAX_CHUNKS] = {}, evDone[MAX_CHUNKS] = {};
+        cudaEvent_t evOut = nullptr;  // counts, status flags and the speculative result copies of every chunk are in host memory
         // the submitted call
         int n = 0, cap = 0, nchunks = 0, per = 0;
+        int spec_w = 0;  // keypoint rows per frame whose copies were enqueued at submit time
         orb_keypoint* kps = nullptr;
         uint8_t* desc = nullptr;
         int* counts = nullptr;
         int* h_status = nullptr;  // pinned, max_batch ints: octree status flags of the submitted batch
     } slot[NUM_SLOTS];
-    int next_slot = 0;
+    // Result rows per frame to copy back before the counts are known on the host (see submit_impl): the largest count
+    // of the previous batch of this shape plus a margin; 0 = nothing known yet (copy up to the caller's capacity).
+    int spec_rows = 0;
     // image ingest (orb_extractor_set_ingest): raw frames -> remap -> gray, fused into the level-0 load
     struct Ingest {
         bool on = false;
@@ -519,8 +523,9 @@ extern "C" int orb_extractor_create(const orb_params* params, int max_rows, int 
         for (int i = 0; i < orb_extractor::MAX_CHUNKS && ce == cudaSuccess; ++i) {
             ce = cudaEventCreateWithFlags(&h->slot[k].evIn[i], cudaEventDisableTiming);
             if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&h->slot[k].evDone[i], cudaEventDisableTiming);
-            if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&h->slot[k].evCnt[i], cudaEventDisableTiming);
         }
+    for (int k = 0; k < orb_extractor::NUM_SLOTS && ce == cudaSuccess; ++k)
+        ce = cudaEventCreateWithFlags(&h->slot[k].evOut, cudaEventDisableTiming);
     if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&h->evFree, cudaEventDisableTiming);
     if (ce != cudaSuccess) {
         orb_extractor_destroy(h);
@@ -553,8 +558,8 @@ extern "C" void orb_extractor_destroy(orb_extractor* h) {
         for (int i = 0; i < orb_extractor::MAX_CHUNKS; ++i) {
             if (S.evIn[i]) cudaEventDestroy(S.evIn[i]);
             if (S.evDone[i]) cudaEventDestroy(S.evDone[i]);
-            if (S.evCnt[i]) cudaEventDestroy(S.evCnt[i]);
         }
+        if (S.evOut) cudaEventDestroy(S.evOut);
     }
     if (h->evFree) cudaEventDestroy(h->evFree);
     if (h->ing.d_mapx) cudaFree(h->ing.d_mapx);
@@ -767,54 +772,35 @@ extern "C" const char* orb_stage_name(int stage) {
     return stage >= 0 && stage < ORB_STAGES ? names[stage] : "";
 }
 
+// Everything of one host batch that is enqueued on the device: called by submit_impl, which cleans up after a failure.
 // rows x cols: the image the extractor sees.  ingest: imgs holds raw frames described by h->ing (stride / frame_stride are
 // theirs), which land in the slot's dense buffer and reach level 0 through k_ingest instead of k_repitch.
-static int submit_impl(orb_extractor* h, int n, const uint8_t* imgs, int rows, int cols, size_t stride, size_t frame_stride,
-                       orb_keypoint* kps, uint8_t* desc, int cap, int* counts, int* ticket, bool ingest) {
-    if (!h || !counts || !ticket) return fail(ORB_ERR_INVALID, "null argument");
-    *ticket = -1;
-    if (n < 0 || n > h->max_batch) return fail(ORB_ERR_INVALID, "n=%d exceeds max_batch=%d", n, h->max_batch);
-    if (n == 0) return ORB_OK;
-    if (!imgs || rows <= 0 || cols <= 0) {  // empty image: silent return (ORBextractor.cc:444-445)
-        for (int f = 0; f < n; ++f) counts[f] = 0;
-        return ORB_OK;
-    }
-    if (!kps || !desc || cap <= 0) return fail(ORB_ERR_INVALID, "null output buffer");
+static int enqueue_batch(orb_extractor* h, orb_extractor::HostSlot& S, int n, const uint8_t* imgs, int rows, int cols, size_t stride,
+                         size_t frame_stride, orb_keypoint* kps, uint8_t* desc, int cap, int* counts, bool ingest, bool pipelined) {
     const orb_extractor::Ingest& I = h->ing;
     const size_t rowBytes = ingest ? (size_t)I.scols * I.channels : (size_t)cols;
     const int srcRows = ingest ? I.srows : rows;
-    if (stride < rowBytes) return fail(ORB_ERR_INVALID, ingest ? "stride < src_cols * channels" : "stride < cols");
-    orb_extractor::HostSlot& S = h->slot[h->next_slot];
-    if (S.busy) return fail(ORB_ERR_INVALID, "three batches are already in flight: call orb_extract_batch_wait first");
-    CUDA_TRY(cudaSetDevice(h->device));
-    if (h->plan.rows != rows || h->plan.cols != cols) {
-        for (int k = 0; k < orb_extractor::NUM_SLOTS; ++k)
-            if (h->slot[k].busy) return fail(ORB_ERR_INVALID, "cannot change the image shape while a batch is in flight");
-    }
-    int rc = build_plan(h, rows, cols);
-    if (rc != ORB_OK) return rc;
-    rc = ensure_out(h, S, cap);
-    if (rc != ORB_OK) return rc;
     const OrbLevel& L0 = h->plan.lv[0];
-    // Pipeline over chunks of frames: H2D copy (streamIn) -> kernels (kernel lanes) -> counts (streamCnt) and
-    // results D2H (streamOut, issued by orb_extract_batch_wait), so that PCIe in, compute and PCIe out of
-    // neighbouring chunks -- and of the neighbouring batch in flight -- overlap.  While per-stage profiling is
-    // on, one chunk is used (stage times then describe whole-batch launches).
+    // Pipeline over chunks of frames: H2D copy (streamIn) -> kernels (kernel lanes) -> counts, status flags and result
+    // rows D2H (streamOut), all enqueued here, so that PCIe in, compute and PCIe out of neighbouring chunks -- and of the
+    // neighbouring batches in flight -- overlap and the host never sits between a chunk's kernels and its result copy.
+    // The number of result rows per frame is not known on the host at this point: the copies take the largest count of
+    // the previous batch plus a margin (h->spec_rows; the caller's capacity before anything is known), and
+    // orb_extract_batch_wait tops up the rare frame that produced more.  While per-stage profiling is on, one chunk is
+    // used (stage times then describe whole-batch launches).
     // Fine chunking only pays when this batch has nothing else to overlap with: with another batch in flight the
     // copies of one batch already hide behind the kernels of the other, so one chunk per kernel lane keeps the
     // launches large and the host-side enqueue cost low (measured on B200 at 64 frames, three batches in flight:
     // 74.7k frames/s with two 32-frame chunks, 71.3k with one chunk, 51.7k with four 16-frame chunks).
     // Measured too: while the copy engines move this data the kernels run ~15 % slower than on resident frames (a
     // copy by SM loads from mapped host memory was worse still), which is what keeps e2e below the resident rate.
-    bool pipelined = false;
-    for (int k = 0; k < orb_extractor::NUM_SLOTS; ++k) pipelined |= h->slot[k].busy;
     const int chunkFrames = getenv("ORB_B200_CHUNK") ? std::max(1, atoi(getenv("ORB_B200_CHUNK"))) : (pipelined ? std::max(16, (n + h->lanes - 1) / std::max(1, h->lanes)) : 16);
     int nchunks = h->profiling ? 1 : std::min<int>(orb_extractor::MAX_CHUNKS, std::max(1, n / chunkFrames));
     const int per = (n + nchunks - 1) / nchunks;
     nchunks = (n + per - 1) / per;
     const size_t landFrame = rowBytes * srcRows;  // one frame in the dense landing buffer
     const bool linear = stride == rowBytes && frame_stride == landFrame;
-    const bool dense = ingest || (linear && ((uintptr_t)imgs & 3) == 0 && cols >= 4);
+    const bool dense = ingest || (linear && cols >= 4);
     if (dense && S.dense_cap < (size_t)n * landFrame + 16) {
         CUDA_TRY(cudaStreamSynchronize(h->streamIn));
         CUDA_TRY(cudaStreamSynchronize(h->stream));
@@ -825,9 +811,10 @@ static int submit_impl(orb_extractor* h, int n, const uint8_t* imgs, int rows, i
         CUDA_TRY(cudaMalloc((void**)&S.d_dense, want));
         S.dense_cap = want;
     }
+    const int spec = std::min(cap, h->spec_rows > 0 ? h->spec_rows : cap);
     // everything enqueued so far on the main stream (the previous batch's kernels: every lane joins there)
     // finishes before this batch touches the shared level / scratch buffers; a batch's status flags are copied
-    // into its own slot at the end of its kernels, so the next batch does not have to wait for the count copies
+    // into its own slot at the end of its kernels, so the next batch does not have to wait for the result copies
     h->last_l0 = h->level0;
     CUDA_TRY(cudaEventRecord(h->evFree, h->stream));
     if (!dense) CUDA_TRY(cudaStreamWaitEvent(h->streamIn, h->evFree, 0));  // non-dense copies write level 0 directly
@@ -853,7 +840,9 @@ static int submit_impl(orb_extractor* h, int n, const uint8_t* imgs, int rows, i
                 CUDA_TRY(orbk_ingest(land, nf, I.srows, I.scols, rowBytes, landFrame, I.channels, I.bgr, I.variant, I.d_mapx, I.d_mapy, rows, cols,
                                      h->level0 + f0 * L0.plane, L0.pitch, L0.plane, ls.st));
             } else {
-                CUDA_TRY(orbk_repitch(land, nf, rows, cols, h->level0 + f0 * L0.plane, L0.pitch, L0.plane, ls.st));
+                // the chunk's first byte need not be word aligned (odd-area frames): the kernel reads relative to the
+                // aligned base of the landing buffer
+                CUDA_TRY(orbk_repitch(S.d_dense, f0, nf, rows, cols, h->level0 + f0 * L0.plane, L0.pitch, L0.plane, ls.st));
             }
         } else {
             if (nf == 1 || frame_stride == stride * (size_t)rows) {
@@ -874,23 +863,70 @@ static int submit_impl(orb_extractor* h, int n, const uint8_t* imgs, int rows, i
         CUDA_TRY(cudaMemcpyAsync(S.d_counts + h->max_batch + f0, h->plan.status + f0, sizeof(int) * nf, cudaMemcpyDeviceToDevice, ls.st));
         CUDA_TRY(cudaEventRecord(S.evDone[c], ls.st));
         if (ls.st != h->stream) CUDA_TRY(cudaStreamWaitEvent(h->stream, S.evDone[c], 0));  // the main stream stays the join point
-        // counts (and the octree status flags) travel on their own small stream so that the bulk result copies
-        // of chunk c -- issued once its counts are known -- are not queued behind the kernels of later chunks
-        CUDA_TRY(cudaStreamWaitEvent(h->streamCnt, S.evDone[c], 0));
-        CUDA_TRY(cudaMemcpyAsync(counts + f0, S.d_counts + f0, sizeof(int) * nf, cudaMemcpyDeviceToHost, h->streamCnt));
-        CUDA_TRY(cudaMemcpyAsync(S.h_status + f0, S.d_counts + h->max_batch + f0, sizeof(int) * nf, cudaMemcpyDeviceToHost, h->streamCnt));
-        CUDA_TRY(cudaEventRecord(S.evCnt[c], h->streamCnt));
+        // results of chunk c: counts and status flags first (small), then `spec` rows of every frame
+        CUDA_TRY(cudaStreamWaitEvent(h->streamOut, S.evDone[c], 0));
+        CUDA_TRY(cudaMemcpyAsync(counts + f0, S.d_counts + f0, sizeof(int) * nf, cudaMemcpyDeviceToHost, h->streamOut));
+        CUDA_TRY(cudaMemcpyAsync(S.h_status + f0, S.d_counts + h->max_batch + f0, sizeof(int) * nf, cudaMemcpyDeviceToHost, h->streamOut));
+        CUDA_TRY(cudaMemcpy2DAsync(kps + (size_t)f0 * cap, (size_t)cap * sizeof(orb_keypoint), S.d_kps + (size_t)f0 * S.out_cap,
+                                   (size_t)S.out_cap * sizeof(orb_keypoint), (size_t)spec * sizeof(orb_keypoint), nf, cudaMemcpyDeviceToHost,
+                                   h->streamOut));
+        CUDA_TRY(cudaMemcpy2DAsync(desc + (size_t)f0 * cap * 32, (size_t)cap * 32, S.d_desc + (size_t)f0 * S.out_cap * 32,
+                                   (size_t)S.out_cap * 32, (size_t)spec * 32, nf, cudaMemcpyDeviceToHost, h->streamOut));
     }
-    S.busy = true;
+    CUDA_TRY(cudaEventRecord(S.evOut, h->streamOut));
     S.n = n;
     S.cap = cap;
     S.nchunks = nchunks;
     S.per = per;
+    S.spec_w = spec;
     S.kps = kps;
     S.desc = desc;
     S.counts = counts;
-    *ticket = h->next_slot;
-    h->next_slot = (h->next_slot + 1) % orb_extractor::NUM_SLOTS;
+    return ORB_OK;
+}
+
+static int submit_impl(orb_extractor* h, int n, const uint8_t* imgs, int rows, int cols, size_t stride, size_t frame_stride,
+                       orb_keypoint* kps, uint8_t* desc, int cap, int* counts, int* ticket, bool ingest) {
+    if (!h || !counts || !ticket) return fail(ORB_ERR_INVALID, "null argument");
+    *ticket = -1;
+    if (n < 0 || n > h->max_batch) return fail(ORB_ERR_INVALID, "n=%d exceeds max_batch=%d", n, h->max_batch);
+    if (n == 0) return ORB_OK;
+    if (!imgs || rows <= 0 || cols <= 0) {  // empty image: silent return (ORBextractor.cc:444-445)
+        for (int f = 0; f < n; ++f) counts[f] = 0;
+        return ORB_OK;
+    }
+    if (!kps || !desc || cap <= 0) return fail(ORB_ERR_INVALID, "null output buffer");
+    const orb_extractor::Ingest& I = h->ing;
+    if (stride < (ingest ? (size_t)I.scols * I.channels : (size_t)cols))
+        return fail(ORB_ERR_INVALID, ingest ? "stride < src_cols * channels" : "stride < cols");
+    int slot = -1;
+    bool pipelined = false;
+    for (int k = 0; k < orb_extractor::NUM_SLOTS; ++k) {
+        if (h->slot[k].busy) pipelined = true;
+        else if (slot < 0) slot = k;
+    }
+    if (slot < 0) return fail(ORB_ERR_INVALID, "three batches are already in flight: call orb_extract_batch_wait first");
+    orb_extractor::HostSlot& S = h->slot[slot];
+    CUDA_TRY(cudaSetDevice(h->device));
+    if (h->plan.rows != rows || h->plan.cols != cols) {
+        if (pipelined) return fail(ORB_ERR_INVALID, "cannot change the image shape while a batch is in flight");
+        h->spec_rows = 0;
+    }
+    int rc = build_plan(h, rows, cols);
+    if (rc != ORB_OK) return rc;
+    rc = ensure_out(h, S, cap);
+    if (rc != ORB_OK) return rc;
+    rc = enqueue_batch(h, S, n, imgs, rows, cols, stride, frame_stride, kps, desc, cap, counts, ingest, pipelined);
+    if (rc != ORB_OK) {
+        // part of the batch may be enqueued and still reading / writing the caller's buffers: drain it before the
+        // error returns (the message of the first failure is kept)
+        const std::string msg = orb_last_error();
+        cudaDeviceSynchronize();
+        cudaGetLastError();
+        return fail(rc, "%s", msg.c_str());
+    }
+    S.busy = true;
+    *ticket = slot;
     return ORB_OK;
 }
 
@@ -967,11 +1003,11 @@ extern "C" int orb_extract_batch_wait(orb_extractor* h, int ticket) {
     orb_extractor::HostSlot& S = h->slot[ticket];
     S.busy = false;
     CUDA_TRY(cudaSetDevice(h->device));
-    // results: as each chunk's counts arrive, copy exactly the rows it produced
+    CUDA_TRY(cudaEventSynchronize(S.evOut));  // counts, status flags and the first spec_w rows of every frame are here
     int maxAll = 0, bad = -1;
+    bool topup = false;
     for (int c = 0; c < S.nchunks; ++c) {
         const int f0 = c * S.per, nf = std::min(S.per, S.n - f0);
-        CUDA_TRY(cudaEventSynchronize(S.evCnt[c]));  // counts of chunk c are on the host, its kernels are done
         int maxc = 0;
         for (int f = f0; f < f0 + nf; ++f) {
             maxc = std::max(maxc, S.counts[f]);
@@ -979,15 +1015,19 @@ extern "C" int orb_extract_batch_wait(orb_extractor* h, int ticket) {
         }
         maxAll = std::max(maxAll, maxc);
         const int w = std::min(maxc, S.cap);
-        if (w > 0) {
-            CUDA_TRY(cudaMemcpy2DAsync(S.kps + (size_t)f0 * S.cap, (size_t)S.cap * sizeof(orb_keypoint), S.d_kps + (size_t)f0 * S.out_cap,
-                                       (size_t)S.out_cap * sizeof(orb_keypoint), (size_t)w * sizeof(orb_keypoint), nf,
-                                       cudaMemcpyDeviceToHost, h->streamOut));
-            CUDA_TRY(cudaMemcpy2DAsync(S.desc + (size_t)f0 * S.cap * 32, (size_t)S.cap * 32, S.d_desc + (size_t)f0 * S.out_cap * 32,
-                                       (size_t)S.out_cap * 32, (size_t)w * 32, nf, cudaMemcpyDeviceToHost, h->streamOut));
+        if (w > S.spec_w) {  // a frame kept more rows than were copied ahead of the counts: fetch the rest of the chunk
+            const size_t o = (size_t)S.spec_w, m = (size_t)(w - S.spec_w);
+            CUDA_TRY(cudaMemcpy2DAsync(S.kps + (size_t)f0 * S.cap + o, (size_t)S.cap * sizeof(orb_keypoint),
+                                       S.d_kps + (size_t)f0 * S.out_cap + o, (size_t)S.out_cap * sizeof(orb_keypoint),
+                                       m * sizeof(orb_keypoint), nf, cudaMemcpyDeviceToHost, h->streamCnt));
+            CUDA_TRY(cudaMemcpy2DAsync(S.desc + ((size_t)f0 * S.cap + o) * 32, (size_t)S.cap * 32, S.d_desc + ((size_t)f0 * S.out_cap + o) * 32,
+                                       (size_t)S.out_cap * 32, m * 32, nf, cudaMemcpyDeviceToHost, h->streamCnt));
+            topup = true;
         }
     }
-    CUDA_TRY(cudaStreamSynchronize(h->streamOut));
+    if (topup) CUDA_TRY(cudaStreamSynchronize(h->streamCnt));
+    // next batch: this batch's largest count + ~3 %, in whole 64-row steps
+    h->spec_rows = std::max(64, (maxAll + maxAll / 32 + 63) / 64 * 64);
     if (bad >= 0) return fail(ORB_ERR_UNSEPARABLE, "frame %d: octree cannot separate its keys (reference would not terminate)", bad);
     if (maxAll > S.cap) return fail(ORB_ERR_CAPACITY, "frame needs %d keypoints, cap is %d", maxAll, S.cap);
     return ORB_OK;
@@ -1104,7 +1144,7 @@ extern "C" int orb_match_all_batch(orb_matcher* m, int npairs, const uint8_t* q,
         if (((uintptr_t)q & 15) || ((uintptr_t)t & 15)) return fail(ORB_ERR_INVALID, "descriptor arrays must be 16-byte aligned");
         // max query count is not known on the host: launch for the stride
         const int max_nq = (int)(out_stride);
-        CUDA_TRY(orbk_match_all(q, nq, q_stride, t, nt, t_stride, npairs, max_nq, best_idx, best_dist, second_dist, out_stride, m->stream));
+        CUDA_TRY(orbk_match_all(q, nq, q_stride, t, nt, t_stride, npairs, max_nq, -1, best_idx, best_dist, second_dist, out_stride, m->stream));
         return ORB_OK;
     }
     int max_nq = 0, max_nt = 0;
@@ -1133,7 +1173,7 @@ extern "C" int orb_match_all_batch(orb_matcher* m, int npairs, const uint8_t* q,
     int* o0 = (int*)dout;
     int* o1 = (int*)((char*)dout + obytes);
     int* o2 = (int*)((char*)dout + 2 * obytes);
-    CUDA_TRY(orbk_match_all((const uint8_t*)dq, dnq, q_stride, (const uint8_t*)dt, dnt, t_stride, npairs, max_nq, o0, o1, o2, out_stride, m->stream));
+    CUDA_TRY(orbk_match_all((const uint8_t*)dq, dnq, q_stride, (const uint8_t*)dt, dnt, t_stride, npairs, max_nq, max_nt, o0, o1, o2, out_stride, m->stream));
     if (obytes) {
         CUDA_TRY(cudaMemcpyAsync(best_idx, o0, obytes, cudaMemcpyDeviceToHost, m->stream));
         CUDA_TRY(cudaMemcpyAsync(best_dist, o1, obytes, cudaMemcpyDeviceToHost, m->stream));

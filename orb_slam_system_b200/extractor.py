@@ -86,16 +86,22 @@ class ORBextractor:
         image = np.ascontiguousarray(image, np.uint8) if image is not None else None
         if image is None or image.size == 0:
             return np.zeros(0, KP_DTYPE), np.zeros((0, 32), np.uint8)
-        assert image.ndim == 2, "CV_8UC1 image expected"
+        if image.ndim != 2:
+            raise ValueError("CV_8UC1 image expected")
         res = self.extract_batch(image[None], cap=cap)
         return res[0]
 
     def extract_batch(self, images, cap=None):
         """n same-shape host frames [n, rows, cols] -> list of (keypoints, descriptors)."""
         images = np.ascontiguousarray(images, np.uint8)
+        if images.ndim != 3:
+            raise ValueError("images must be [n, rows, cols] uint8 (CV_8UC1 frames)")
         n, rows, cols = images.shape
-        assert n <= self.max_batch
-        cap = cap or self.keypoint_bound(rows, cols)
+        if n > self.max_batch:
+            raise ValueError(f"{n} frames exceed max_batch={self.max_batch}")
+        cap = int(cap) if cap is not None else max(1, self.keypoint_bound(rows, cols))
+        if cap < 1:
+            raise ValueError("cap must be positive")
         kps = np.zeros((n, cap), KP_DTYPE)
         desc = np.zeros((n, cap, 32), np.uint8)
         counts = np.zeros(n, np.int32)
@@ -157,7 +163,8 @@ class ORBextractor:
         if maps is not None:
             mx = np.ascontiguousarray(maps[0], np.float32)
             my = np.ascontiguousarray(maps[1], np.float32)
-            assert mx.ndim == 2 and mx.shape == my.shape
+            if mx.ndim != 2 or mx.shape != my.shape:
+                raise ValueError("map_x and map_y must be 2-D arrays of the same shape")
             cfg.dst_rows, cfg.dst_cols = mx.shape
             cfg.map_x, cfg.map_y = mx.ctypes.data, my.ctypes.data
             keep = (mx, my)
@@ -170,10 +177,14 @@ class ORBextractor:
         of the remapped / gray-converted frames."""
         raw = np.ascontiguousarray(raw, np.uint8)
         n = raw.shape[0]
-        assert getattr(self, "_ingest", None) is not None, "set_ingest first"
-        assert n <= self.max_batch and raw.shape[1:3] == self._ingest[:2]
+        if getattr(self, "_ingest", None) is None:
+            raise ValueError("set_ingest first")
+        if n > self.max_batch or raw.shape[1:3] != self._ingest[:2]:
+            raise ValueError(f"raw frames {raw.shape} do not match the ingest configuration {self._ingest[:2]} / max_batch={self.max_batch}")
         drows, dcols = self._ingest[3:5]
-        cap = cap or self.keypoint_bound(drows, dcols)
+        cap = int(cap) if cap is not None else max(1, self.keypoint_bound(drows, dcols))
+        if cap < 1:
+            raise ValueError("cap must be positive")
         kps = np.zeros((n, cap), KP_DTYPE)
         desc = np.zeros((n, cap, 32), np.uint8)
         counts = np.zeros(n, np.int32)

@@ -301,3 +301,74 @@ def test_random_shapes_and_parameters():
             assert info["desc_bit_mismatch"] == 0, info
             checked += 1
     assert checked >= 18
+
+
+def _pinned(shape, dtype):
+    import torch
+    return torch.empty(shape, dtype=dtype).pin_memory()
+
+
+def _check_batch_against_oracle(frames, nf, k, d, c, tag, every=1):
+    for f in range(0, len(frames), every):
+        ko, do = oracle.extract(frames[f], nfeatures=nf, cap=16 * nf)
+        assert c[f] == len(ko), (tag, f, int(c[f]), len(ko))
+        assert k[f, :c[f]].tobytes() == ko.tobytes(), (tag, f)
+        assert (d[f, :c[f]] == do).all(), (tag, f)
+
+
+@pytest.mark.parametrize("rows,cols,n,chunk", [
+    (375, 1242, 34, None),   # odd area (area % 4 == 2), two chunks of 17 frames: the second chunk lands word-misaligned
+    (375, 1242, 50, None),
+    (121, 161, 144, None),   # area % 4 == 1, eight chunks of 18
+    (121, 161, 7, "1"),      # ORB_B200_CHUNK=1: one frame per chunk, every offset residue
+    (376, 1241, 64, None),   # the benchmark batch
+])
+def test_pipelined_host_batches_match_oracle(rows, cols, n, chunk, monkeypatch):
+    # the multi-chunk host pipeline (dense landing buffer -> k_repitch on the kernel lanes, results copied back ahead of
+    # the counts) with pinned buffers and three batches in flight; every frame against the oracle
+    import torch
+    from orb_slam_system_b200 import KP_DTYPE
+    if chunk is not None:
+        monkeypatch.setenv("ORB_B200_CHUNK", chunk)
+    nf = 2000 if cols > 1000 else 300
+    ex = ORBextractor(nf, 1.2, 8, 20, 7, max_batch=n)
+    cap = ex.keypoint_bound(rows, cols)
+    frames = np.stack([oracle.synth_frame(rows, cols, frame=300 + f, right=f & 1) for f in range(n)])
+    pin = _pinned((3, n, rows, cols), torch.uint8)
+    for r in range(3):
+        pin.numpy()[r] = np.roll(frames, r, axis=0)
+    outs = [(_pinned((n, cap, 28), torch.uint8), _pinned((n, cap, 32), torch.uint8), _pinned((n,), torch.int32)) for _ in range(3)]
+    tickets = [ex.submit_batch_pinned(pin[r], *outs[r], cap) for r in range(3)]
+    # tickets may be waited on in any order, and a freed slot is reusable at once
+    ex.wait_batch(tickets[1])
+    again = ex.submit_batch_pinned(pin[1], *outs[1], cap)
+    ex.wait_batch(tickets[0])
+    ex.wait_batch(tickets[2])
+    ex.wait_batch(again)
+    for r in range(3):  # every frame of the first batch, a sample of the other two
+        k = outs[r][0].numpy().view(KP_DTYPE).reshape(n, cap)
+        _check_batch_against_oracle(np.roll(frames, r, axis=0), nf, k, outs[r][1].numpy(), outs[r][2].numpy(), (rows, cols, n, r),
+                                    every=1 if r == 0 else max(1, n // 6))
+    ex.close()
+
+
+def test_result_copies_ahead_of_counts_are_topped_up():
+    # the result rows of a batch are copied back before its counts reach the host, sized by the previous batch; a batch
+    # that keeps many more keypoints than its predecessor must still deliver every row
+    from orb_slam_system_b200 import KP_DTYPE
+    rows, cols, nf, B = 240, 320, 1000, 20
+    ex = ORBextractor(nf, 1.2, 8, 20, 7, max_batch=B)
+    cap = ex.keypoint_bound(rows, cols)
+    sparse = np.stack([np.full((rows, cols), 90, np.uint8) for _ in range(B)])
+    for f in range(B):  # a few corners only: small squares on a flat frame
+        for j in range(3 + f % 4):
+            sparse[f, 60 + 30 * j:72 + 30 * j, 80 + 40 * j:92 + 40 * j] = 200
+    dense = np.stack([oracle.synth_frame(rows, cols, frame=500 + f) for f in range(B)])
+    for batch, tag in ((sparse, "sparse"), (dense, "dense after sparse"), (sparse, "sparse after dense"), (dense, "dense")):
+        k = np.zeros((B, cap), KP_DTYPE)
+        d = np.zeros((B, cap, 32), np.uint8)
+        c = np.zeros(B, np.int32)
+        ex.wait_batch(ex.submit_batch_pinned(batch, k, d, c, cap))
+        _check_batch_against_oracle(batch, nf, k, d, c, tag)
+    assert c.max() > 3 * 64  # the dense batch really is larger than what the sparse one predicted
+    ex.close()
