@@ -25,9 +25,20 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-ROWS, COLS, NFEAT, NLEVELS = 376, 1241, 2000, 8
-SCALE, INI_TH, MIN_TH = 1.2, 20, 7
-METRIC = "ORB frames/s @KITTI 1241x376 2k feats"
+NLEVELS, SCALE, INI_TH, MIN_TH = 8, 1.2, 20, 7
+DEPTH = 3  # ORB_MAX_IN_FLIGHT: host batches in flight in the end-to-end regions
+# The three shapes BASELINE.json / SURVEY 8a name (settings files of the reference); kitti is the headline (config 3).
+SHAPES = {
+    "kitti": dict(rows=376, cols=1241, nfeat=2000, metric="ORB frames/s @KITTI 1241x376 2k feats",
+                  label="KITTI-shape stereo 1241x376, 2000 features, 8 levels, scale 1.2, FAST 20/7, 64 frames/GPU batch (BASELINE config 3; "
+                        "Examples/Stereo/KITTI00-02.yaml:38-51)"),
+    "tum": dict(rows=480, cols=640, nfeat=1000, metric="ORB frames/s @TUM 640x480 1k feats",
+                label="TUM1-shape monocular 640x480, 1000 features, 8 levels, scale 1.2, FAST 20/7, 64 frames/GPU batch (BASELINE config 1 "
+                      "batched; Examples/Monocular/TUM1.yaml:30-43)"),
+    "euroc": dict(rows=480, cols=752, nfeat=1200, metric="ORB frames/s @EuRoC 752x480 1.2k feats", bf=47.90639384423901, fx=435.2046959714599,
+                  label="EuRoC-shape stereo 752x480, 1200 features per image, 8 levels, scale 1.2, FAST 20/7, 64 stereo pairs = 128 images/GPU "
+                        "batch (BASELINE config 2 batched; Examples/Stereo/EuRoC.yaml:88-101)"),
+}
 
 
 def measured_peaks():
@@ -112,8 +123,23 @@ class ClockSampler:
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
-def level_pixels():
-    """P_l of the BASELINE shape."""
+def slice_cpus(local_rank, world):
+    """With several ranks on one box, give each its own contiguous slice of the CPUs the process may run on, so that the
+    ranks' submit / wait threads (which poll CUDA events) do not migrate over each other.  Best effort."""
+    if world <= 1:
+        return
+    try:
+        cpus = sorted(os.sched_getaffinity(0))
+        per = len(cpus) // world
+        if per >= 1 and len(cpus) > per:
+            os.sched_setaffinity(0, set(cpus[local_rank * per:(local_rank + 1) * per]))
+    except Exception:
+        pass
+
+
+def level_pixels(shape="kitti"):
+    """P_l of a BASELINE shape."""
+    ROWS, COLS = SHAPES[shape]["rows"], SHAPES[shape]["cols"]
     sc = [1.0, 1.0]
     acc = np.float32(1.0)
     for _ in range(NLEVELS - 2):
@@ -126,12 +152,63 @@ def level_pixels():
     return P
 
 
-def make_frames(n, first):
+def make_frames(shape, n, first):
     from orb_slam_system_b200.synth import synth_frame
-    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+    ROWS, COLS = SHAPES[shape]["rows"], SHAPES[shape]["cols"]
+    with ThreadPoolExecutor(max_workers=min(8, len(os.sched_getaffinity(0)) or 1)) as ex:
         # stereo pairs: even = left, odd = right image of the same scene
         frames = list(ex.map(lambda f: synth_frame(ROWS, COLS, seed=7, frame=(first + f) // 2, right=(first + f) & 1), range(n)))
     return np.stack(frames)
+
+
+def euroc_stereo(sb, m, K, barrier, max_over_ranks, world):
+    """BASELINE config 2 batched: a step = 64 EuRoC-shape stereo pairs = both images of every pair through the host-buffer
+    extraction call (left = even, right = odd frames of the batch) + Frame::ComputeStereoMatches (orb_compute_stereo_matches:
+    Hamming search, SAD refinement on the pyramids the extraction left on the device, median cut) for every pair as its
+    results arrive; three steps in flight."""
+    from orb_slam_system_b200 import KP_DTYPE
+    S, B = sb.S, sb.B
+    npairs = B // 2
+    matched = [0]
+
+    def stereo_of_step(i):
+        k, d, c = sb.outs[i % DEPTH]
+        kn, dn, cn = k.numpy(), d.numpy(), c.numpy()
+        tot = 0
+        for p in range(npairs):
+            cl, cr = int(cn[2 * p]), int(cn[2 * p + 1])
+            ur, _ = m.ComputeStereoMatches(sb.ex, sb.ex, kn[2 * p, :cl].view(KP_DTYPE).ravel(), dn[2 * p, :cl], kn[2 * p + 1, :cr].view(KP_DTYPE).ravel(),
+                                           dn[2 * p + 1, :cr], S["bf"], S["fx"], 2 * p, 2 * p + 1)
+            tot += int((ur >= 0).sum())
+        matched[0] = tot
+
+    # the pyramids of a step are read where its extraction left them, so a step's stereo matching must run before the
+    # next step's kernels overwrite the level buffers: one step at a time here (the latency form of the pipeline)
+    Ks = max(2, min(K, 5))
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(Ks):
+        sb.ex.wait_batch(sb.submit(i))
+        stereo_of_step(i)
+    secs = max_over_ranks([time.perf_counter() - t0])[0]
+    return {"workload": f"{npairs} stereo pairs per step: extraction of both images + Frame::ComputeStereoMatches per pair, host buffers",
+            "pairs_per_s": world * npairs * Ks / secs, "ms_per_pair": 1e3 * secs / (npairs * Ks), "steps": Ks,
+            "stereo_matches_per_pair": matched[0] / npairs}
+
+
+def hamming_cpu_baseline(ham_sets, cores):
+    """The reference's own DescriptorDistance (src/ORBmatcher.cc:896-908, compiled from source: oracle/_ref/libref_match.so)
+    in the brute-force best / second-best scan over the same 2000 x 2000 descriptor pairs, one keyframe pair per host thread."""
+    import oracle
+    if oracle.ref_match_lib() is None:
+        return {"unavailable": "oracle/_ref/libref_match.so not built"}
+    dq, dt = ham_sets
+    n = max(2, min(cores, dq.shape[0]))
+    q = dq[:n].cpu().numpy()
+    t = dt[:n].cpu().numpy()
+    secs, bi, bd, sd = oracle.ref_bruteforce_many(q, t, cores)
+    return {"value": n * q.shape[1] * t.shape[1] / secs, "unit": "pairs/s", "cores": cores, "kind": "reference",
+            "sample": f"{n} keyframe pairs of {q.shape[1]} x {t.shape[1]} descriptors, one pair per host thread"}
 
 
 def next_rows(device):
@@ -267,19 +344,29 @@ def next_rows(device):
     return out
 
 
-def cpu_reference_rate(nframes, threads):
-    """The reference's own CPU extractor (oracle/_ref, compiled from the reference sources
-    against oracle/cvshim) when present, else the oracle port; one frame per host thread."""
+def cpu_reference_rate(nframes, threads, shape="kitti", fast=False):
+    """The reference's own CPU extractor (oracle/_ref, compiled from the reference sources against oracle/cvshim) when
+    present, else the oracle port; one frame per host thread.  fast: the timing-only -O3 build (oracle/Makefile reffast)
+    instead of the -O2 -ffp-contract=off parity build."""
     import oracle
-    if oracle.ref_lib() is not None:
-        secs, kp = oracle.ref_extract_many(ROWS, COLS, nframes, threads, nfeatures=NFEAT, scaleFactor=SCALE, nlevels=NLEVELS,
-                                           iniThFAST=INI_TH, minThFAST=MIN_TH)
+    S = SHAPES[shape]
+    kw = dict(nfeatures=S["nfeat"], scaleFactor=SCALE, nlevels=NLEVELS, iniThFAST=INI_TH, minThFAST=MIN_TH)
+    if fast and oracle.ref_lib() is not None and oracle.ref_fast_lib() is not None:
+        secs, kp = oracle.ref_extract_many(S["rows"], S["cols"], nframes, threads, fast=True, **kw)
+        kind = "reference-O3"
+    elif oracle.ref_lib() is not None:
+        secs, kp = oracle.ref_extract_many(S["rows"], S["cols"], nframes, threads, **kw)
         kind = "reference"
     else:
-        secs, kp = oracle.extract_many(ROWS, COLS, nframes, threads, nfeatures=NFEAT, scaleFactor=SCALE, nlevels=NLEVELS,
-                                       iniThFAST=INI_TH, minThFAST=MIN_TH)
+        secs, kp = oracle.extract_many(S["rows"], S["cols"], nframes, threads, **kw)
         kind = "port"
     return nframes / secs, kind, kp
+
+
+CPU_NOTE = ("the reference's ORBextractor.cc compiled from source against oracle/cvshim: cv::FAST / resize / GaussianBlur are scalar "
+            "models of OpenCV's arithmetic, not OpenCV's SIMD code (OpenCV is not in this image), so this arm is roughly 2x slower than "
+            "the reference linked against a real OpenCV 3.4 build would be; kind reference-O3 = -O3 -march=x86-64-v3 "
+            "(the reference's CMakeLists.txt:10-11 uses -O3 -march=native), kind reference = the -O2 -ffp-contract=off parity build")
 
 
 def run_reference(args, rank, world):
@@ -288,26 +375,326 @@ def run_reference(args, rank, world):
     cores = os.cpu_count() or 1
     per_step = max(8, cores)  # bounded sample: one frame per host thread per step
     for _ in range(args.warmup):
-        cpu_reference_rate(per_step, cores)
+        cpu_reference_rate(per_step, cores, args.workload, fast=True)
     t0 = time.perf_counter()
     kind, secs = "port", 0.0
     for _ in range(args.steps):
-        rate, kind, _ = cpu_reference_rate(per_step, cores)
+        rate, kind, _ = cpu_reference_rate(per_step, cores, args.workload, fast=True)
         secs += per_step / rate  # extraction time only; frame synthesis is outside the clock
     el = time.perf_counter() - t0
     value = args.steps * per_step / secs
+    parity_rate, parity_kind, _ = cpu_reference_rate(per_step, cores, args.workload, fast=False)
+    S = SHAPES[args.workload]
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+        "impl": "reference", "metric": S["metric"], "value": value, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * per_step / value, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "KITTI-shape stereo 1241x376, 2000 features, 8 levels, scale 1.2, FAST 20/7 (BASELINE config 3)",
-                   "frames_per_step": per_step},
+        "config": {"workload": S["label"], "frames_per_step": per_step},
         "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": kind,
-                         "sample": f"{per_step} synthetic frames per step, one frame per host thread, {args.steps} steps"},
+                         "sample": f"{per_step} synthetic frames per step, one frame per host thread, {args.steps} steps",
+                         "parity_build": {"value": parity_rate, "kind": parity_kind}, "note": CPU_NOTE},
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": el,
     }
     print(json.dumps(line), flush=True)
+
+
+def newest_profile():
+    """The newest profiles/*_kernels.json (tools/ncu_kernels_json.py on an `ncu --set full` capture of this bench): per-frame
+    DRAM bytes and executed warp instructions per kernel."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_kernels.json")))
+    if not files:
+        return None, None
+    try:
+        return json.load(open(files[-1])), os.path.relpath(files[-1], ROOT)
+    except Exception:
+        return None, None
+
+
+def median(v):
+    return float(np.median(np.asarray(v, np.float64)))
+
+
+class ShapeBench:
+    """One extractor handle on one workload shape: device-resident and host-buffer (end-to-end) timing of batches of B frames."""
+
+    def __init__(self, shape, B, rank, local_rank, torch):
+        self.t = torch
+        S = SHAPES[shape]
+        self.S, self.B, self.shape = S, B, shape
+        rows, cols = S["rows"], S["cols"]
+        from orb_slam_system_b200 import ORBextractor
+        self.ex = ORBextractor(S["nfeat"], SCALE, NLEVELS, INI_TH, MIN_TH, max_batch=B, device=local_rank, max_rows=rows, max_cols=cols)
+        self.cap = self.ex.keypoint_bound(rows, cols)
+        self.pitch = (cols + 63) // 64 * 64
+        # enough distinct batches that the inputs of consecutive steps cannot sit in the 126 MB L2
+        self.R = R = max(3, -(-140_000_000 // (B * rows * self.pitch)))
+        host = make_frames(shape, B * R, first=rank * B * R).reshape(R, B, rows, cols)
+        self.pinned_in = torch.empty((R, B, rows, cols), dtype=torch.uint8, pin_memory=True)
+        self.pinned_in.numpy()[:] = host
+        self.d_in = torch.zeros((R, B, rows, self.pitch), dtype=torch.uint8, device="cuda")
+        self.d_in[:, :, :, :cols] = self.pinned_in.cuda()
+        cap = self.cap
+        self.d_kps = torch.zeros((B, cap, 28), dtype=torch.uint8, device="cuda")
+        self.d_desc = torch.zeros((B, cap, 32), dtype=torch.uint8, device="cuda")
+        self.d_counts = torch.zeros((B,), dtype=torch.int32, device="cuda")
+        self.outs = [(torch.empty((B, cap, 28), dtype=torch.uint8, pin_memory=True), torch.empty((B, cap, 32), dtype=torch.uint8, pin_memory=True),
+                      torch.empty((B,), dtype=torch.int32, pin_memory=True)) for _ in range(DEPTH)]
+        torch.cuda.synchronize()
+        self.stream = torch.cuda.ExternalStream(self.ex.stream, device=torch.device("cuda", local_rank))
+
+    def close(self):
+        self.ex.close()
+
+    def step_device(self, i):
+        self.ex.extract_batch_device(self.d_in[i % self.R][:, :, :self.S["cols"]], self.d_kps, self.d_desc, self.d_counts, self.cap)
+
+    def resident(self, K, reps, barrier):
+        """reps regions of K device-resident steps, each bracketed by barrier + synchronize; ms per region, host enqueue ms per step."""
+        t = self.t
+        out, enq = [], []
+        for _ in range(reps):
+            barrier()
+            e0, e1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
+            e0.record(self.stream)
+            th0 = time.perf_counter()
+            for i in range(K):
+                self.step_device(i)
+            enq.append(1e3 * (time.perf_counter() - th0) / K)
+            e1.record(self.stream)
+            self.ex.sync()
+            barrier()
+            out.append(e0.elapsed_time(e1))
+        return out, median(enq)
+
+    def stage_profile(self, K):
+        self.ex.set_profiling(True)
+        for i in range(K):
+            self.step_device(i)
+        stage_ms, ncalls = self.ex.stage_times()
+        self.ex.set_profiling(False)
+        return stage_ms, ncalls
+
+    def submit(self, i):
+        o = self.outs[i % DEPTH]
+        return self.ex.submit_batch_pinned(self.pinned_in[i % self.R], o[0], o[1], o[2], self.cap)
+
+    def e2e_sync(self, K, barrier):
+        o = self.outs[0]
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(K):
+            self.ex.extract_batch_pinned(self.pinned_in[i % self.R], o[0], o[1], o[2], self.cap)
+        return time.perf_counter() - t0
+
+    def e2e_async(self, K, reps, barrier, after_wait=None):
+        """reps regions of K steps through orb_extract_batch_submit / _wait with DEPTH steps in flight.  Every region starts
+        after a barrier + synchronize and ends when this rank's last result is in host memory; the clock is the rank's own
+        (no collective inside it) and the caller takes the maximum over ranks."""
+        out = []
+        for _ in range(reps):
+            barrier()
+            t0 = time.perf_counter()
+            pending = []
+            for i in range(K):
+                pending.append((i, self.submit(i)))
+                if len(pending) >= DEPTH:
+                    j, tk = pending.pop(0)
+                    self.ex.wait_batch(tk)
+                    if after_wait:
+                        after_wait(j)
+            while pending:
+                j, tk = pending.pop(0)
+                self.ex.wait_batch(tk)
+                if after_wait:
+                    after_wait(j)
+            out.append(time.perf_counter() - t0)
+        return out
+
+    def e2e_steady(self, K, regions):
+        """One continuous run of (regions + 1) * K steps; seconds of each K-step window between result arrivals, i.e.
+        the serving rate without the fill and drain of the three-deep pipeline."""
+        stamps, pending = [], []
+        n = (regions + 1) * K
+        for i in range(n):
+            pending.append(self.submit(i))
+            if len(pending) >= DEPTH:
+                self.ex.wait_batch(pending.pop(0))
+                stamps.append(time.perf_counter())
+        while pending:
+            self.ex.wait_batch(pending.pop(0))
+            stamps.append(time.perf_counter())
+        return [stamps[(r + 1) * K - 1] - stamps[r * K - 1] for r in range(1, regions + 1)]
+
+    def algo_bytes_per_frame(self, k_mean):
+        P = level_pixels(self.shape)
+        Psum = sum(P)
+        return {"pyramid": (Psum - P[-1]) + (Psum - P[0]), "detect": Psum, "octree": 0, "blur": 2 * Psum, "describe": 60 * k_mean,
+                "path": 5 * Psum - P[0] - P[-1] + 60 * k_mean}
+
+
+def platform_ceiling(sb, seconds, barrier, torch):
+    """What the host <-> device link of this box carries when every rank moves exactly one step's bytes in each direction
+    concurrently from / to pinned memory with no kernel at all: steps per second of this rank (tools/probes/pcie_ceiling.py
+    is the stand-alone form).  The e2e figure cannot exceed the sum over ranks of this number x frames per step."""
+    B, S = sb.B, sb.S
+    h2d = B * S["rows"] * S["cols"]
+    maxc = int(sb.outs[0][2].max().item())
+    d2h = B * maxc * 60 + 4 * B
+    d_land = torch.empty(h2d, dtype=torch.uint8, device="cuda")
+    d_res = torch.zeros(d2h, dtype=torch.uint8, device="cuda")
+    h_res = torch.empty(d2h, dtype=torch.uint8, pin_memory=True)
+    s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+    flat = [sb.pinned_in[r].reshape(-1) for r in range(sb.R)]
+    barrier()
+    t0 = time.perf_counter()
+    steps = 0
+    while time.perf_counter() - t0 < seconds:
+        for i in range(4):
+            with torch.cuda.stream(s_in):
+                d_land.copy_(flat[(steps + i) % sb.R], non_blocking=True)
+            with torch.cuda.stream(s_out):
+                h_res.copy_(d_res, non_blocking=True)
+        steps += 4
+        s_in.synchronize()
+        s_out.synchronize()
+    return steps / (time.perf_counter() - t0), h2d, d2h
+
+
+def hamming_block(m, pool, mstream, barrier, world, peak_hbm, torch):
+    """Second half of the metric (BASELINE config 4): 256 keyframe pairs of 2000 x 2000 descriptors, device resident.  The
+    tensor-core kernel on the extractor's own descriptors (182 live bits) and on 256-live-bit rows, the POPC kernel as
+    the comparator of both."""
+    NP, NQ = 256, 2000
+    B = pool.shape[0]
+    qsel = torch.arange(NP, device="cuda") % B
+    tsel = (torch.arange(NP, device="cuda") + 1) % B
+    sets = {"182": (pool[qsel].contiguous(), pool[tsel].contiguous())}
+    g = torch.Generator(device="cuda").manual_seed(11)
+    noise = torch.randint(0, 256, (NP + 1, NQ, 32), dtype=torch.uint8, device="cuda", generator=g)
+    sets["256"] = (noise[:NP].contiguous(), noise[1:].contiguous())
+    nq = torch.full((NP,), NQ, dtype=torch.int32, device="cuda")
+    outs = {impl: [torch.empty((NP, NQ), dtype=torch.int32, device="cuda") for _ in range(3)] for impl in ("mma", "popc")}
+    res = {}
+    MREP = 10
+    saved = os.environ.get("ORB_B200_MATCH")
+    for live, (dq, dt) in sets.items():
+        for impl in ("mma", "popc"):
+            os.environ["ORB_B200_MATCH"] = impl
+            o = outs[impl]
+            for _ in range(2):
+                m.match_all_batch_device(dq, nq, dt, nq, *o)
+            m.sync()
+            barrier()
+            m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            m0.record(mstream)
+            for _ in range(MREP if impl == "mma" else 3):
+                m.match_all_batch_device(dq, nq, dt, nq, *o)
+            m1.record(mstream)
+            m.sync()
+            barrier()
+            res[f"{impl}_{live}_ms"] = m0.elapsed_time(m1) / (MREP if impl == "mma" else 3)
+        res[f"identical_{live}"] = all(bool((a == b).all().item()) for a, b in zip(outs["mma"], outs["popc"]))
+    if saved is None:
+        os.environ.pop("ORB_B200_MATCH", None)
+    else:
+        os.environ["ORB_B200_MATCH"] = saved
+    return NP, NQ, res, sets["182"]
+
+
+def config5(sb, m, mstream, rank, world, torch, dist):
+    """BASELINE config 5 as SURVEY 8(e) states it: 4096 KITTI-shape frames over 8 ranks = 512 per rank, extracted as 8
+    launches of 64 straight into the rank's keyframe block (fixed stride Kmax x 32 B per frame + an int32 count per
+    frame), ONE all-gather of the blocks over NCCL / NVLink, then every rank brute-force matches its local frames against
+    the gathered keyframes of every other rank (same frame index: world - 1 keyframes per local frame)."""
+    from orb_slam_system_b200.sharding import all_gather_descriptors
+    F, KMAX = 512, 4480  # SURVEY 8a: the KITTI-shape octree keeps at most nIni * 4^p = 4480 keypoints per frame
+    B = sb.B
+    launches = F // B
+    block = torch.zeros((F, KMAX, 32), dtype=torch.uint8, device="cuda")
+    cnts = torch.zeros((F,), dtype=torch.int32, device="cuda")
+    kps = torch.zeros((B, KMAX, 28), dtype=torch.uint8, device="cuda")
+
+    def extract_all():
+        for s in range(launches):
+            sb.ex.extract_batch_device(sb.d_in[s % sb.R][:, :, :sb.S["cols"]], kps, block[s * B:(s + 1) * B], cnts[s * B:(s + 1) * B], KMAX)
+
+    extract_all()
+    sb.ex.sync()
+    assert int(cnts.max().item()) <= KMAX, "a frame kept more than Kmax keypoints"
+    dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(sb.stream)
+    extract_all()
+    e1.record(sb.stream)
+    sb.ex.sync()
+    extract_ms = e0.elapsed_time(e1)
+    for _ in range(2):
+        all_d, all_c = all_gather_descriptors(block, cnts)
+    torch.cuda.synchronize()
+    dist.barrier()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    GREP = 5
+    g0.record()
+    for _ in range(GREP):
+        all_d, all_c = all_gather_descriptors(block, cnts)
+    g1.record()
+    torch.cuda.synchronize()
+    gather_ms = g0.elapsed_time(g1) / GREP
+    sb_ = torch.empty((world - 1, F, KMAX), dtype=torch.int32, device="cuda")
+    sd1, sd2 = torch.empty_like(sb_), torch.empty_like(sb_)
+
+    def match_all_neighbours():
+        for d in range(1, world):
+            o = (rank + d) % world
+            m.match_all_batch_device(block, cnts, all_d[o * F:(o + 1) * F], all_c[o * F:(o + 1) * F], sb_[d - 1], sd1[d - 1], sd2[d - 1])
+
+    match_all_neighbours()
+    m.sync()
+    dist.barrier()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record(mstream)
+    match_all_neighbours()
+    s1.record(mstream)
+    m.sync()
+    match_ms = s0.elapsed_time(s1)
+    # ---- checks, outside every clock: (1) every rank's block arrived intact (a checksum travels beside it);
+    # (2) one cross-shard pair against the CPU oracle's brute-force scan
+    w = (torch.arange(32, device="cuda", dtype=torch.int64) + 1)
+    mine = (block.to(torch.int64) * w).sum().reshape(1)
+    sums = torch.empty((world,), dtype=torch.int64, device="cuda")
+    dist.all_gather_into_tensor(sums, mine)
+    got = torch.stack([(all_d[r * F:(r + 1) * F].to(torch.int64) * w).sum() for r in range(world)])
+    gathered_ok = bool((got == sums).all().item()) and bool((all_c.view(world, F)[rank] == cnts).all().item())
+    oracle_ok = None
+    if rank == 0:
+        try:
+            import oracle
+            o = 1 % world
+            nq0, nt0 = int(cnts[0].item()), int(all_c[o * F].item())
+            oi, od, os_ = oracle.match_all(block[0, :nq0].cpu().numpy(), all_d[o * F, :nt0].cpu().numpy())
+            oracle_ok = bool((sb_[0, 0, :nq0].cpu().numpy() == oi).all() and (sd1[0, 0, :nq0].cpu().numpy() == od).all()
+                             and (sd2[0, 0, :nq0].cpu().numpy() == os_).all())
+        except Exception as e:
+            oracle_ok = repr(e)
+    npairs = float((cnts.double().unsqueeze(0) * torch.stack([all_c[((rank + d) % world) * F:((rank + d) % world + 1) * F] for d in range(1, world)]).double()).sum().item())
+    t = torch.tensor([extract_ms, gather_ms, match_ms], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    tp = torch.tensor([npairs, 1.0 if gathered_ok else 0.0], dtype=torch.float64, device="cuda")
+    dist.all_reduce(tp)
+    recv = (world - 1) * (block.numel() + cnts.numel() * 4)
+    extract_ms, gather_ms, match_ms = (float(x) for x in t.tolist())
+    return {"workload": f"{world * F} KITTI-shape frames = {F} per rank ({launches} launches of {B} over the rank's {sb.R * B} resident synthetic frames, cycled); "
+                        f"keyframe block {F} x Kmax {KMAX} x 32 B + counts per rank; one all-gather; every local frame against the same-index "
+                        f"keyframe of each of the {world - 1} other ranks (BASELINE config 5, SURVEY 8e)",
+            "extract_ms": extract_ms, "extract_frames_per_s": world * F / (extract_ms * 1e-3),
+            "allgather_ms": gather_ms, "allgather_bytes_per_rank": block.numel() + cnts.numel() * 4,
+            "allgather_recv_GBps_per_gpu": recv / (gather_ms * 1e-3) / 1e9, "nvlink_peak_GBps_per_direction": 900.0,
+            "allgather_frac_of_nvlink": recv / (gather_ms * 1e-3) / 1e9 / 900.0,
+            "match_ms": match_ms, "match_frame_pairs": world * (world - 1) * F, "match_pairs_per_s": float(tp[0].item()) / (match_ms * 1e-3),
+            "gathered_blocks_match_their_checksums_on_all_ranks": bool(tp[1].item() == world),
+            "cross_shard_pair_identical_to_oracle": oracle_ok}
 
 
 def main():
@@ -316,10 +703,12 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="kitti", choices=sorted(SHAPES), help="shape of the headline line (default: BASELINE config 3)")
     ap.add_argument("--frames-per-gpu", type=int, default=64)
-    ap.add_argument("--rotate", type=int, default=5, help="distinct input batches cycled through (5 x 30 MB > L2)")
+    ap.add_argument("--repeats", type=int, default=5, help="timed regions of --steps steps each; the line reports the median")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-next-rows", action="store_true", help="skip the stereo / search / vocabulary side measurements")
+    ap.add_argument("--no-other-shapes", action="store_true", help="skip the TUM / EuRoC rows")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -336,275 +725,219 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    torch.set_num_threads(1)
     pin_to_gpu_numa_node(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    from orb_slam_system_b200 import KP_DTYPE, ORBextractor, kernel_launch_count
+    from orb_slam_system_b200 import ORBmatcher, kernel_launch_count
 
-    B, R, K, W = args.frames_per_gpu, args.rotate, args.steps, max(args.warmup, 3)
-    ex = ORBextractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, max_batch=B, device=local_rank, max_rows=ROWS, max_cols=COLS)
-    cap = ex.keypoint_bound(ROWS, COLS)
-    pitch = (COLS + 63) // 64 * 64
-
-    # ---- synthetic input: R distinct batches per rank, frames differ across ranks
-    host = make_frames(B * R, first=rank * B * R).reshape(R, B, ROWS, COLS)
-    pinned_in = torch.empty((R, B, ROWS, COLS), dtype=torch.uint8, pin_memory=True)
-    pinned_in.numpy()[:] = host
-    d_in = torch.zeros((R, B, ROWS, pitch), dtype=torch.uint8, device="cuda")
-    d_in[:, :, :, :COLS] = pinned_in.cuda()
-    d_kps = torch.zeros((B, cap, 28), dtype=torch.uint8, device="cuda")
-    d_desc = torch.zeros((B, cap, 32), dtype=torch.uint8, device="cuda")
-    d_counts = torch.zeros((B,), dtype=torch.int32, device="cuda")
-    h_kps = torch.empty((B, cap, 28), dtype=torch.uint8, pin_memory=True)
-    h_desc = torch.empty((B, cap, 32), dtype=torch.uint8, pin_memory=True)
-    h_counts = torch.empty((B,), dtype=torch.int32, pin_memory=True)
-    torch.cuda.synchronize()
-    stream = torch.cuda.ExternalStream(ex.stream, device=torch.device("cuda", local_rank))
-
-    def step_device(i):
-        ex.extract_batch_device(d_in[i % R][:, :, :COLS], d_kps, d_desc, d_counts, cap)
-
-    def step_host(i):
-        ex.extract_batch_pinned(pinned_in[i % R], h_kps, h_desc, h_counts, cap)
+    B, K, W, REPS = args.frames_per_gpu, args.steps, max(args.warmup, 3), max(1, args.repeats)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident timing (value)
-    for i in range(W):
-        step_device(i)
-    ex.sync()
-    k_mean = float(d_counts.float().mean().item())
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    barrier()
-    l0 = kernel_launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    th0 = time.perf_counter()
-    for i in range(K):
-        step_device(W + i)
-    host_enqueue_ms = 1e3 * (time.perf_counter() - th0) / K
-    e1.record(stream)
-    ex.sync()
-    barrier()
-    launches = kernel_launch_count() - l0
-    ms_total = e0.elapsed_time(e1)
-    # same K steps again with CUDA events around every kernel stage (stages back to back on one
-    # stream, so each duration is the kernel's own): per-kernel launch times for the roofline
-    ex.set_profiling(True)
-    for i in range(K):
-        step_device(W + i)
-    stage_ms, ncalls = ex.stage_times()
-    ex.set_profiling(False)
-    clocks = sampler.stop() if rank == 0 else None
-
-    # ---- end to end through the host-buffer C ABI (e2e): pinned host frames in, keypoints + descriptors
-    # back in pinned host memory, every step.  (a) the synchronous call orb_extract_batch, one step at a
-    # time; (b) the asynchronous pair orb_extract_batch_submit / _wait with three steps in flight (the uploads of
-    # steps i+1, i+2 overlap step i's kernels, step i's download overlaps step i+1's kernels) -- the serving form,
-    # reported as e2e; both move the same bytes per step inside the timed region.
-    for i in range(W):
-        step_host(i)
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(K):
-        step_host(W + i)
-    barrier()
-    e2e_sync_s = time.perf_counter() - t0
-    h_kps2 = torch.empty_like(h_kps).pin_memory()
-    h_desc2 = torch.empty_like(h_desc).pin_memory()
-    h_counts2 = torch.empty_like(h_counts).pin_memory()
-    DEPTH = 3  # ORB_MAX_IN_FLIGHT
-    outs = [(h_kps, h_desc, h_counts), (h_kps2, h_desc2, h_counts2),
-            (torch.empty_like(h_kps).pin_memory(), torch.empty_like(h_desc).pin_memory(), torch.empty_like(h_counts).pin_memory())]
-
-    def submit(i):
-        o = outs[i % DEPTH]
-        return ex.submit_batch_pinned(pinned_in[i % R], o[0], o[1], o[2], cap)
-
-    for i in range(W):
-        ex.wait_batch(submit(i))
-    barrier()
-    sampler2 = ClockSampler(local_rank)
-    if rank == 0:
-        sampler2.start()
-    t0 = time.perf_counter()
-    pending = [submit(i) for i in range(min(DEPTH - 1, K))]
-    for i in range(len(pending), K):
-        pending.append(submit(i))
-        ex.wait_batch(pending.pop(0))
-    while pending:
-        ex.wait_batch(pending.pop(0))
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    e2e_clocks = sampler2.stop() if rank == 0 else None
-    maxc = int(h_counts.max().item())
-    h2d = B * ROWS * COLS
-    d2h = B * 4 + B * maxc * 28 + B * maxc * 32
-
-    # ---- second half of the metric: brute-force Hamming matching (BASELINE config 4): 256 keyframe
-    # pairs of 2000 x 2000 descriptors drawn from the extractor's own output, device resident
-    from orb_slam_system_b200 import ORBmatcher
-    NP, NQ = 256, 2000
-    m = ORBmatcher(0.6, True, device=local_rank)
-    pool = d_desc[:, :NQ, :].contiguous()  # [B, 2000, 32] real descriptors of the last step
-    qsel = torch.arange(NP, device="cuda") % B
-    tsel = (torch.arange(NP, device="cuda") + 1) % B
-    dq, dt = pool[qsel].contiguous(), pool[tsel].contiguous()
-    nq = torch.full((NP,), NQ, dtype=torch.int32, device="cuda")
-    nt = torch.full((NP,), NQ, dtype=torch.int32, device="cuda")
-    obi = torch.empty((NP, NQ), dtype=torch.int32, device="cuda")
-    obd = torch.empty_like(obi)
-    osd = torch.empty_like(obi)
-    torch.cuda.synchronize()
-    mstream = torch.cuda.ExternalStream(m.stream, device=torch.device("cuda", local_rank))
-    for _ in range(3):
-        m.match_all_batch_device(dq, nq, dt, nt, obi, obd, osd)
-    m.sync()
-    barrier()
-    m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    MREP = 10
-    m0.record(mstream)
-    for _ in range(MREP):
-        m.match_all_batch_device(dq, nq, dt, nt, obi, obd, osd)
-    m1.record(mstream)
-    m.sync()
-    barrier()
-    match_ms = m0.elapsed_time(m1) / MREP
-
-    # ---- BASELINE config 5 (N > 1): NCCL all-gather of every rank's keyframe descriptor block over NVLink,
-    # then each rank brute-force matches its local frames against the same-index keyframes of the next rank
-    shard = None
-    if world > 1:
-        from orb_slam_system_b200.sharding import all_gather_descriptors, cross_shard_pairs
-        KF = 2000  # descriptor rows exchanged per keyframe (fixed stride, counts travel with them)
-        block = d_desc[:, :KF, :].contiguous()
-        cnts = torch.clamp(d_counts, max=KF).to(torch.int32)
-        for _ in range(2):
-            all_d, all_c = all_gather_descriptors(block, cnts)
-        torch.cuda.synchronize()
-        dist.barrier()
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        g0.record()
-        GREP = 5
-        for _ in range(GREP):
-            all_d, all_c = all_gather_descriptors(block, cnts)
-        g1.record()
-        torch.cuda.synchronize()
-        gather_ms = g0.elapsed_time(g1) / GREP
-        pairs = torch.from_numpy(cross_shard_pairs(B, rank, world, neighbours=1)).cuda()
-        tq = block[pairs[:, 0]].contiguous()
-        tt = all_d[pairs[:, 1]].contiguous()
-        tnq = cnts[pairs[:, 0]].contiguous()
-        tnt = all_c[pairs[:, 1]].contiguous()
-        sb = torch.empty((len(pairs), KF), dtype=torch.int32, device="cuda")
-        sd1, sd2 = torch.empty_like(sb), torch.empty_like(sb)
-        torch.cuda.synchronize()
-        for _ in range(2):
-            m.match_all_batch_device(tq, tnq, tt, tnt, sb, sd1, sd2)
-        m.sync()
-        dist.barrier()
-        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s0.record(mstream)
-        for _ in range(GREP):
-            m.match_all_batch_device(tq, tnq, tt, tnt, sb, sd1, sd2)
-        s1.record(mstream)
-        m.sync()
-        smatch_ms = s0.elapsed_time(s1) / GREP
-        tt2 = torch.tensor([gather_ms, smatch_ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tt2, op=dist.ReduceOp.MAX)
-        gather_ms, smatch_ms = float(tt2[0].item()), float(tt2[1].item())
-        recv_bytes = (world - 1) * (block.numel() + cnts.numel() * 4)
-        npairs_total = float((tnq.double() * tnt.double()).sum().item())
-        tp = torch.tensor([npairs_total], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tp)
-        shard = {"workload": f"all-gather of {B} keyframes x {KF} x 32 B per rank + cross-shard brute-force matching (BASELINE config 5)",
-                 "allgather_ms": gather_ms, "allgather_recv_GBps_per_gpu": recv_bytes / (gather_ms * 1e-3) / 1e9,
-                 "match_ms": smatch_ms, "match_pairs_per_s": float(tp[0].item()) / (smatch_ms * 1e-3)}
-
-    if world > 1:
-        t = torch.tensor([ms_total, e2e_s, match_ms, e2e_sync_s], dtype=torch.float64, device="cuda")
+    def max_over_ranks(vals):
+        if world == 1:
+            return [float(v) for v in vals]
+        t = torch.tensor(list(vals), dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total, e2e_s, match_ms, e2e_sync_s = float(t[0].item()), float(t[1].item()), float(t[2].item()), float(t[3].item())
+        return [float(v) for v in t.tolist()]
+
+    def sum_over_ranks(vals):
+        if world == 1:
+            return [float(v) for v in vals]
+        t = torch.tensor(list(vals), dtype=torch.float64, device="cuda")
+        dist.all_reduce(t)
+        return [float(v) for v in t.tolist()]
+
+    def measure_shape(shape, Bs, reps, full):
+        """Resident and end-to-end rates of one workload shape (max over ranks per region, median over regions)."""
+        sb = ShapeBench(shape, Bs, rank, local_rank, torch)
+        slice_cpus(local_rank, world)  # after the frame synthesis (which uses a thread pool)
+        for i in range(W):
+            sb.step_device(i)
+        sb.ex.sync()
+        k_mean = float(sb.d_counts.float().mean().item())
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        barrier()
+        l0 = kernel_launch_count()
+        res_ms, enq_ms = sb.resident(K, reps, barrier)
+        launches = (kernel_launch_count() - l0) // reps
+        res_ms = max_over_ranks(res_ms)
+        stage_ms, ncalls = sb.stage_profile(K) if full else ({}, 0)
+        clocks = sampler.stop() if rank == 0 else None
+        # ---- end to end through the host-buffer C ABI: pinned host frames in, keypoints + descriptors back in pinned
+        # host memory, every step.  (a) the synchronous call orb_extract_batch, one step at a time; (b) the asynchronous
+        # pair orb_extract_batch_submit / _wait with three steps in flight -- the serving form, reported as e2e; both
+        # move the same bytes per step inside the timed region.
+        for i in range(W):
+            sb.ex.wait_batch(sb.submit(i))
+        sync_s = max_over_ranks([sb.e2e_sync(K, barrier)])[0] if full else None
+        sampler2 = ClockSampler(local_rank)
+        if rank == 0:
+            sampler2.start()
+        e2e_s = max_over_ranks(sb.e2e_async(K, reps, barrier))
+        barrier()
+        steady_s = max_over_ranks(sb.e2e_steady(K, reps))
+        e2e_clocks = sampler2.stop() if rank == 0 else None
+        ceil_steps, h2d, d2h = platform_ceiling(sb, 0.25, barrier, torch)
+        ceil_total = sum_over_ranks([ceil_steps])[0]
+        frames = Bs * K * world
+        r = {"sb": sb, "k_mean": k_mean, "res_ms": res_ms, "enq_ms": enq_ms, "launches": int(launches), "stage_ms": stage_ms, "ncalls": ncalls,
+             "clocks": clocks, "e2e_clocks": e2e_clocks, "sync_s": sync_s, "e2e_s": e2e_s, "steady_s": steady_s, "frames": frames,
+             "h2d": h2d, "d2h": d2h, "ceiling_frames_s": ceil_total * Bs}
+        return r
+
+    def shape_row(shape, r, peak):
+        """The compact row of a non-headline shape."""
+        sb = r["sb"]
+        ab = sb.algo_bytes_per_frame(r["k_mean"])
+        ms = median(r["res_ms"])
+        value = r["frames"] / (ms * 1e-3)
+        e2e = r["frames"] / median(r["e2e_s"])
+        gbs = ab["path"] * r["frames"] / (ms * 1e-3) / 1e9
+        return {"workload": sb.S["label"], "frames_per_gpu_per_step": sb.B, "keypoints_per_frame": r["k_mean"],
+                "value": value, "unit": "frames/s", "ms_per_step": ms / K, "value_min_max": [r["frames"] / (max(r["res_ms"]) * 1e-3), r["frames"] / (min(r["res_ms"]) * 1e-3)],
+                "e2e": {"value": e2e, "steady_state_value": r["frames"] / median(r["steady_s"]), "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"],
+                        "platform_ceiling_frames_s": r["ceiling_frames_s"], "frac_of_platform_ceiling": e2e / r["ceiling_frames_s"]},
+                "algo_bytes_per_frame": ab["path"], "path_GBps": gbs, "hbm_frac": gbs / peak}
+
+    peak, peak_kind = measured_peaks()
+    head = measure_shape(args.workload, B, REPS, True)
+    sb = head["sb"]
+
+    # ---- second half of the metric: brute-force Hamming matching (BASELINE config 4)
+    m = ORBmatcher(0.6, True, device=local_rank)
+    mstream = torch.cuda.ExternalStream(m.stream, device=torch.device("cuda", local_rank))
+    sb.step_device(0)
+    sb.ex.sync()
+    pool = sb.d_desc[:, :2000, :].contiguous()  # real descriptors of one step
+    NP, NQ, ham, ham_sets = hamming_block(m, pool, mstream, barrier, world, peak, torch)
+    ham_ms = max_over_ranks([ham[k] for k in ("mma_182_ms", "mma_256_ms", "popc_182_ms", "popc_256_ms")])
+
+    shard = config5(sb, m, mstream, rank, world, torch, dist) if (world > 1 and args.workload == "kitti") else None
+
+    others = {}
+    if not args.no_other_shapes:
+        for shape in ("tum", "euroc", "kitti"):
+            if shape == args.workload:
+                continue
+            Bo = 128 if shape == "euroc" else 64  # EuRoC: 64 stereo pairs = 128 images per step
+            r = measure_shape(shape, Bo, 3, False)
+            row = shape_row(shape, r, peak)
+            if shape == "euroc":
+                row["stereo"] = euroc_stereo(r["sb"], m, K, barrier, max_over_ranks, world)
+            others[shape] = row
+            r["sb"].close()
 
     if rank == 0:
-        frames = B * K * world
-        value = frames / (ms_total * 1e-3)
-        peak, peak_kind = measured_peaks()
-        P = level_pixels()
-        Psum = sum(P)
-        # dominant stage and its algorithmic bytes per launch (DESIGN.md "roofline")
+        S = sb.S
+        frames = head["frames"]
+        ms_med = median(head["res_ms"])
+        value = frames / (ms_med * 1e-3)
+        ab = sb.algo_bytes_per_frame(head["k_mean"])
+        stage_ms, ncalls = head["stage_ms"], max(head["ncalls"], 1)
         dom = max(stage_ms, key=stage_ms.get)
-        per_launch_ms = stage_ms[dom] / max(ncalls, 1)
-        stage_bytes = {
-            "pyramid": (Psum - P[-1]) + (Psum - P[0]),
-            "detect": Psum,
-            "octree": 0,
-            "blur": 2 * Psum,
-            "describe": 60 * k_mean,
-        }
-        algo = stage_bytes[dom] * B
+        per_launch_ms = stage_ms[dom] / ncalls
+        algo = ab[dom] * B
         achieved = algo / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms > 0 else 0.0
-        path_bytes = (5 * Psum - P[0] - P[-1] + 60 * k_mean) * B
-        path_gbs = path_bytes / (ms_total / K * 1e-3) / 1e9
+        path_gbs = ab["path"] * B / (ms_med / K * 1e-3) / 1e9
+        prof, prof_path = newest_profile() if args.workload == "kitti" else (None, None)
+        kname = {"pyramid": "k_resize_tile", "detect": "k_detect", "octree": "k_octree_fast", "blur": "k_blur", "describe": "k_describe_tile"}[dom]
+        traffic = issue = None
+        if prof and prof.get("per_frame"):
+            pf = prof["per_frame"]
+            if kname in pf:  # per launch of the dominant stage = one 64-frame step's worth
+                traffic = (pf[kname]["dram_read_bytes"] + pf[kname]["dram_write_bytes"]) * B
+            sm_hz = ((head["clocks"] or {}).get("sm_mhz") or 1965.0) * 1e6
+            inst = prof["per_frame_total"]["warp_inst"] * B
+            peak_issue = 148 * 4 * sm_hz  # one warp instruction per SM sub-partition and clock
+            issue = {"warp_instr_per_step": inst, "peak_warp_instr_per_s": peak_issue, "floor_ms_per_step": 1e3 * inst / peak_issue,
+                     "frac": inst / (ms_med / K * 1e-3) / peak_issue, "source": prof_path,
+                     "note": "smsp__inst_executed.sum of every kernel of the step (ncu) / measured step time, against 148 SMs x 4 issue "
+                             "slots x the SM clock sampled during the run: the path is bound by instruction issue, not by HBM"}
+        e2e_med = median(head["e2e_s"])
+        e2e_val = frames / e2e_med
         line = {
-            "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "metric": S["metric"], "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_med / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "KITTI-shape stereo 1241x376, 2000 features, 8 levels, scale 1.2, FAST 20/7, 64 frames/GPU batch (BASELINE config 3)",
-                       "frames_per_gpu_per_step": B, "keypoints_per_frame": k_mean,
-                       "l2": f"inputs rotate through {R} distinct batches ({R * B * ROWS * pitch / 1e6:.0f} MB > 126 MB L2)"},
-            "roofline": {"bound": "hbm", "kernel": "k_" + dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak,
-                         # dram__bytes_read.sum + dram__bytes_write.sum of k_detect, ncu --set full (profiles/r01j: 2 x 32-frame
-                         # launches of 43.25 + 0.53 MB make one 64-frame step)
-                         "traffic": 87.6e6 if dom == "detect" else None, "traffic_source": "profiles/r01j_ncu_summary.txt",
-                         "peak_source": peak_kind,
+            "config": {"workload": S["label"], "frames_per_gpu_per_step": B, "keypoints_per_frame": head["k_mean"],
+                       "l2": f"inputs rotate through {sb.R} distinct batches ({sb.R * B * S['rows'] * sb.pitch / 1e6:.0f} MB > 126 MB L2)",
+                       "repeats": f"{REPS} timed regions of {K} steps, each bracketed by barrier + synchronize; value, ms_per_step and e2e are "
+                                  "the median region (max over ranks per region)"},
+            "value_min_max": [frames / (max(head["res_ms"]) * 1e-3), frames / (min(head["res_ms"]) * 1e-3)],
+            "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "traffic_source": prof_path, "peak_source": peak_kind,
                          "algo_bytes_per_launch": algo, "launch_ms": per_launch_ms,
-                         "stage_ms_per_step": {k: v / max(ncalls, 1) for k, v in stage_ms.items()},
+                         "stage_ms_per_step": {k: v / ncalls for k, v in stage_ms.items()},
                          "stage_note": "stage times from a second pass of the same steps with the stages serialised on one stream; "
                                        "in the timed region the blur overlaps detect + octree on a second stream",
-                         "path": {"algo_bytes_per_step": path_bytes, "achieved": path_gbs, "frac": path_gbs / peak}},
-            "e2e": {"value": frames / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "api": "orb_extract_batch_submit/_wait, three 64-frame steps in flight, pinned host buffers",
-                    "sync_call_value": frames / e2e_sync_s, "sync_call_api": "orb_extract_batch, one step at a time",
-                    "clocks": e2e_clocks},
-            "gpu_launches": int(launches), "host_enqueue_ms_per_step": host_enqueue_ms, "clocks": clocks,
-            "hamming": {"metric": "Hamming pairs/s (brute force, best + second best)", "value": world * NP * NQ * NQ / (match_ms * 1e-3),
-                        "unit": "pairs/s", "workload": f"{NP} keyframe pairs x {NQ} x {NQ} descriptors per GPU (BASELINE config 4)",
-                        "ms_per_launch": match_ms,
-                        "algo_bytes_per_launch": NP * (32 * 2 * NQ + 12 * NQ),
-                        "hbm_frac": NP * (32 * 2 * NQ + 12 * NQ) / (match_ms * 1e-3) / 1e9 / peak,
-                        "popc_per_s": world * 3 * NP * NQ * NQ / (match_ms * 1e-3),
-                        "logic_ops_per_s": world * 19 * NP * NQ * NQ / (match_ms * 1e-3),
-                        # pipe peaks per GPU from tools/probes/pipe_probe: POPC 16, LOP3 / VIMNMX 64 lanes per clock and SM
-                        "popc_pipe_frac": 3 * NP * NQ * NQ / (match_ms * 1e-3) / (16 * 148 * 1.965e9),
-                        "logic_pipe_frac": 19 * NP * NQ * NQ / (match_ms * 1e-3) / (64 * 148 * 1.965e9),
-                        "note": "logic-pipe bound: the 6 live XOR words of a pair (words 6-7 of this fork's descriptors are zero, checked on "
-                                "the data; 8 otherwise) go through a LOP3 carry-save tree to 3 POPC instead of 6, ~19 logic-pipe "
-                                "instructions per pair against a pipe rate of 64 lanes/clk/SM = 0.97e12 pairs/s per GPU"},
+                         "path": {"algo_bytes_per_step": ab["path"] * B, "achieved": path_gbs, "frac": path_gbs / peak},
+                         "issue": issue},
+            "e2e": {"value": e2e_val, "unit": "frames/s", "h2d_bytes_per_step": head["h2d"], "d2h_bytes_per_step": head["d2h"],
+                    "api": "orb_extract_batch_submit/_wait, three 64-frame steps in flight, pinned host buffers; every region starts after a "
+                           "barrier + synchronize and ends when the rank's last result is in host memory (the rank's own clock, max over ranks)",
+                    "value_min_max": [frames / max(head["e2e_s"]), frames / min(head["e2e_s"])],
+                    "steady_state_value": frames / median(head["steady_s"]),
+                    "steady_state_note": "K-step windows between result arrivals inside one continuous run: the serving rate without the "
+                                         "fill and drain of the three-deep pipeline that every bracketed region pays",
+                    "platform_ceiling_frames_s": head["ceiling_frames_s"], "frac_of_platform_ceiling": e2e_val / head["ceiling_frames_s"],
+                    "platform_ceiling_note": "all ranks copying one step's bytes host -> device and device -> host concurrently from pinned memory "
+                                             "with no kernels (same run, same box): no e2e figure on this box can exceed it",
+                    "sync_call_value": frames / head["sync_s"], "sync_call_api": "orb_extract_batch, one step at a time",
+                    "clocks": head["e2e_clocks"]},
+            "gpu_launches": head["launches"] * K // K, "host_enqueue_ms_per_step": head["enq_ms"], "clocks": head["clocks"],
         }
+        line["gpu_launches"] = head["launches"]
+        pairs = NP * NQ * NQ
+        mma182, mma256, popc182, popc256 = ham_ms
+        # tensor pipe: one tcgen05.mma 128 x 128 x 32 (8-bit operands) per 64 clocks and SM (B300_MICROARCH: max(M, 128) * N / 256)
+        kfrac = lambda ms, ksteps: (pairs / (128 * 128)) * ksteps * 64 / (148 * 1.965e9) / (ms * 1e-3)
+        line["hamming"] = {
+            "metric": "Hamming pairs/s (brute force, best + second best)", "value": world * pairs / (mma182 * 1e-3), "unit": "pairs/s",
+            "workload": f"{NP} keyframe pairs x {NQ} x {NQ} descriptors per GPU (BASELINE config 4), the extractor's own descriptors (182 live bits)",
+            "kernel": "k_match_mma (tcgen05.mma kind::i8 128x128x32, accumulators in TMEM, in-kernel bit expansion)",
+            "ms_per_launch": mma182, "value_256_live_bits": world * pairs / (mma256 * 1e-3), "ms_per_launch_256_live_bits": mma256,
+            "popc_kernel_value": world * pairs / (popc182 * 1e-3), "popc_kernel_value_256_live_bits": world * pairs / (popc256 * 1e-3),
+            "identical_to_popc_kernel": bool(ham["identical_182"] and ham["identical_256"]),
+            "algo_bytes_per_launch": NP * (32 * 2 * NQ + 12 * NQ), "hbm_frac": NP * (32 * 2 * NQ + 12 * NQ) / (mma182 * 1e-3) / 1e9 / peak,
+            "mma_pipe_frac": kfrac(mma182, 6), "mma_pipe_frac_256_live_bits": kfrac(mma256, 8),
+            "mma_ops_per_s": world * pairs * 2 * 192 / (mma182 * 1e-3),
+            "note": "d(a, b) = |a| - a'.b with a' = 2a - 1 in {-1, +1}, b in {0, 1}: exact in int8 with int32 accumulation.  K = 192 (6 K-steps) "
+                    "when words 6-7 of a train tile are zero (checked on the data), else 256.  mma_pipe_frac = issued tcgen05.mma time / "
+                    "kernel time at 64 clocks per 128 x 128 x 32 instruction; the rest is the epilogue (tcgen05.ld + packed 16-bit key "
+                    "tournament, ~2.3 instructions per distance) and the bit expansion, which share the SM with the tensor pipe"}
         if shard is not None:
             line["shard_match"] = shard
+        if others:
+            line["other_shapes"] = others
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             nfr = max(64, 8 * cores)  # ~1 s of wall clock, 10-20 s of CPU work on 16 cores
-            rate, kind, _ = cpu_reference_rate(nfr, cores)
+            rate, kind, _ = cpu_reference_rate(nfr, cores, args.workload, fast=True)
+            rate2, kind2, _ = cpu_reference_rate(nfr // 2, cores, args.workload, fast=False)
             line["cpu_baseline"] = {"value": rate, "unit": "frames/s", "cores": cores, "kind": kind,
-                                    "sample": f"{nfr} synthetic KITTI-shape frames, one frame per host thread"}
+                                    "sample": f"{nfr} synthetic {args.workload}-shape frames, one frame per host thread",
+                                    "parity_build": {"value": rate2, "kind": kind2}, "note": CPU_NOTE}
+            try:
+                line["hamming"]["cpu_baseline"] = hamming_cpu_baseline(ham_sets, cores)
+            except Exception as e:
+                line["hamming"]["cpu_baseline"] = {"error": repr(e)}
             if not args.no_next_rows:
                 try:
                     line["next_rows"] = next_rows(local_rank)
                 except Exception as e:  # side measurements must never cost the headline line
                     line["next_rows"] = {"error": repr(e)}
         print(json.dumps(line), flush=True)
-    ex.close()
+    sb.close()
+    m.close()
     if world > 1:
         dist.destroy_process_group()
 

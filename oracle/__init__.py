@@ -388,12 +388,33 @@ def ref_match_lib():
     return _ref_match
 
 
+_ADAPTER_MATCH = os.path.join(_HERE, "_ref", "libadapter_match.so")
+_adapter_match = None
+
+
+def adapter_match_lib():
+    """CDLL of the drop-in ORB_SLAM2::ORBmatcher (orb_slam_system_b200/adapter/ORBmatcher_b200.cc over liborb_b200.so) behind the
+    same bridge as the compiled reference (oracle/Makefile adaptermatch), or None.  Needs a GPU to do anything."""
+    global _adapter_match
+    if _adapter_match is None:
+        if not os.path.exists(_ADAPTER_MATCH):
+            return None
+        _adapter_match = C.CDLL(_ADAPTER_MATCH)
+    return _adapter_match
+
+
+def _bridge_lib(impl):
+    """The library whose refm_* entry points run the ORBmatcher class: the compiled reference or the GPU adapter."""
+    L = adapter_match_lib() if impl == "adapter" else ref_match_lib()
+    assert L is not None, f"oracle/_ref library for impl={impl!r} is not available"
+    return L
+
+
 def _search_fn(name, impl):
-    """orc_<name> of the oracle restatement, or refm_<name> of the compiled reference (impl="reference")."""
-    if impl == "reference":
-        L = ref_match_lib()
-        assert L is not None, "oracle/_ref/libref_match.so is not available"
-        fn = getattr(L, "refm_" + name)
+    """orc_<name> of the oracle restatement, or refm_<name> of the compiled reference (impl="reference") / of the drop-in
+    adapter class behind the same bridge (impl="adapter")."""
+    if impl in ("reference", "adapter"):
+        fn = getattr(_bridge_lib(impl), "refm_" + name)
     else:
         fn = getattr(lib(), "orc_" + name)
     fn.restype = C.c_int
@@ -511,41 +532,41 @@ def search_kf_window(KF, claimed, qdesc, u, v, radius, level, max_dist):
     return int(n), out
 
 
-def ref_search_by_projection_loop(KF, claimed, qdesc, u, v, radius):
+def ref_search_by_projection_loop(KF, claimed, qdesc, u, v, radius, impl="reference"):
     """The compiled reference's SearchByProjection(KeyFrame*, Scw, vpPoints, vpMatched, th) (src/ORBmatcher.cc:121-195) searching
     the windows (u, v, radius); the oracle's counterpart is search_kf_window(KF, claimed, ..., level=None, max_dist=TH_LOW)."""
     q = np.ascontiguousarray(qdesc, np.uint8).reshape(-1, 32)
     out = np.zeros(len(q), np.int32)
     fr = _frame(KF)
     f = lambda a: np.ascontiguousarray(a, np.float32)
-    fn = ref_match_lib().refm_search_by_projection_loop
+    fn = _bridge_lib(impl).refm_search_by_projection_loop
     fn.restype = C.c_int
     n = fn(C.byref(fr), _p(claimed), len(q), _p(q), _p(f(u)), _p(f(v)), _p(f(radius)), _p(out))
     return int(n), out
 
 
-def ref_fuse_search(KF, qdesc, u, v, level, th, variant=0):
+def ref_fuse_search(KF, qdesc, u, v, level, th, variant=0, impl="reference"):
     """The compiled reference's Fuse (src/ORBmatcher.cc:504-568, variant 1: the Scw overload :570-634), search part; the oracle's
     counterpart is search_kf_window(KF, None, ..., radius = th * scale[level], level, max_dist=TH_LOW)."""
     q = np.ascontiguousarray(qdesc, np.uint8).reshape(-1, 32)
     out = np.zeros(len(q), np.int32)
     fr = _frame(KF)
     f = lambda a: np.ascontiguousarray(a, np.float32)
-    fn = ref_match_lib().refm_fuse_search
+    fn = _bridge_lib(impl).refm_fuse_search
     fn.restype = C.c_int
     n = fn(C.byref(fr), _p(f(KF.mvScaleFactors)), len(q), _p(q), _p(f(u)), _p(f(v)), _p(np.ascontiguousarray(level, np.int32)), C.c_float(th),
            int(variant), _p(out))
     return int(n), out
 
 
-def ref_search_by_sim3(KF2, qdesc, u, v, level, th):
+def ref_search_by_sim3(KF2, qdesc, u, v, level, th, impl="reference"):
     """The compiled reference's SearchBySim3 (src/ORBmatcher.cc:636-730) with s12 = 1, R12 = I, t12 = 0; the oracle's counterpart is
     search_kf_window(KF2, None, ..., radius = th * scale[level], level, max_dist=TH_HIGH)."""
     q = np.ascontiguousarray(qdesc, np.uint8).reshape(-1, 32)
     out = np.zeros(len(q), np.int32)
     fr = _frame(KF2)
     f = lambda a: np.ascontiguousarray(a, np.float32)
-    fn = ref_match_lib().refm_search_by_sim3
+    fn = _bridge_lib(impl).refm_search_by_sim3
     fn.restype = C.c_int
     n = fn(C.byref(fr), _p(f(KF2.mvScaleFactors)), len(q), _p(q), _p(f(u)), _p(f(v)), _p(np.ascontiguousarray(level, np.int32)), C.c_float(th),
            _p(out))

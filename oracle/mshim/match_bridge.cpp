@@ -57,6 +57,8 @@ void fill_frame(Frame& Fr, const OrcFrame* F, const float* scale, int nscale) {
     Fr.mnMinY = Fr.grid.mnMinY;
     Fr.mnMaxX = Fr.grid.mnMaxX;
     Fr.mnMaxY = Fr.grid.mnMaxY;
+    Fr.mfGridElementWidthInv = Fr.grid.wInv;
+    Fr.mfGridElementHeightInv = Fr.grid.hInv;
     for (int i = 0; i < F->N; ++i) Fr.mvKeysUn.push_back(to_cv(F->keysUn[i]));
     Fr.mvKeys = Fr.mvKeysUn;  // UndistortKeyPoints moves pt only (src/Frame.cc:384-414): angles and octaves are shared
     Fr.mDescriptors = desc_mat(F->desc, F->N);
@@ -300,6 +302,7 @@ int refm_search_by_projection_loop(const OrcFrame* KF, uint8_t* claimed, int nq,
                                    const float* radius, int* featureOfQuery) {
     KeyFrame K;
     fill_grid(K.grid, KF);
+    K.grid_members();
     K.N = KF->N;
     for (int i = 0; i < KF->N; ++i) K.mvKeysUn.push_back(to_cv(KF->keysUn[i]));
     K.mDescriptors = desc_mat(KF->desc, KF->N);
@@ -332,6 +335,7 @@ int refm_search_by_sim3(const OrcFrame* KF2, const float* mvScaleFactors, int nq
                         const int* level, float th, int* featureOfQuery) {
     KeyFrame K1, K2;
     fill_grid(K2.grid, KF2);
+    K2.grid_members();
     K2.N = KF2->N;
     for (int i = 0; i < KF2->N; ++i) K2.mvKeysUn.push_back(to_cv(KF2->keysUn[i]));
     K2.mDescriptors = desc_mat(KF2->desc, KF2->N);
@@ -364,6 +368,7 @@ int refm_fuse_search(const OrcFrame* KF, const float* mvScaleFactors, int nq, co
                      const int* level, float th, int variant, int* featureOfQuery) {
     KeyFrame K;
     fill_grid(K.grid, KF);
+    K.grid_members();
     K.N = KF->N;
     for (int i = 0; i < KF->N; ++i) K.mvKeysUn.push_back(to_cv(KF->keysUn[i]));
     K.mDescriptors = desc_mat(KF->desc, KF->N);

@@ -113,6 +113,17 @@ public:
     GridHolder grid;
     int N = 0;
     float fx = 1, fy = 1, cx = 0, cy = 0;
+    // include/KeyFrame.h:112-113, :165-168 under the reference's own names (read by adapter/ORBmatcher_b200.cc); the bridge
+    // fills them from `grid` with grid_members()
+    float mnMinX = 0, mnMinY = 0, mnMaxX = 0, mnMaxY = 0, mfGridElementWidthInv = 0, mfGridElementHeightInv = 0;
+    void grid_members() {
+        mnMinX = grid.mnMinX;
+        mnMinY = grid.mnMinY;
+        mnMaxX = grid.mnMaxX;
+        mnMaxY = grid.mnMaxY;
+        mfGridElementWidthInv = grid.wInv;
+        mfGridElementHeightInv = grid.hInv;
+    }
     std::vector<cv::KeyPoint> mvKeys, mvKeysUn;
     std::vector<float> mvuRight, mvScaleFactors, mvLevelSigma2;
     cv::Mat mDescriptors;
@@ -139,6 +150,7 @@ public:
     int N = 0;
     float fx = 1, fy = 1, cx = 0, cy = 0, mb = 1;
     float mnMinX = 0, mnMaxX = 0, mnMinY = 0, mnMaxY = 0;
+    float mfGridElementWidthInv = 0, mfGridElementHeightInv = 0;  // include/Frame.h:139-140 (static there)
     std::vector<cv::KeyPoint> mvKeys, mvKeysUn;
     std::vector<float> mvuRight, mvScaleFactors;
     std::vector<bool> mvbOutlier;

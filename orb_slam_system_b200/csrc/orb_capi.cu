@@ -145,7 +145,7 @@ struct orb_extractor {
         uint8_t* d_desc = nullptr;
         int* d_counts = nullptr;
         int out_cap = 0;
-        cudaEvent_t evIn[MAX_CHUNKS] = {}, evDone[MAX_CHUNKS] = {};
+        cudaEvent_t evIn[MAX_CHUNKS] = {}, evDone[MAX_CHUNKS] = {}, evCnt[MAX_CHUNKS] = {};  // evCnt: the chunk's counts are on the host
         cudaEvent_t evOut = nullptr;  // counts, status flags and the speculative result copies of every chunk are in host memory
         // the submitted call
         int n = 0, cap = 0, nchunks = 0, per = 0;
@@ -158,6 +158,9 @@ struct orb_extractor {
     // Result rows per frame to copy back before the counts are known on the host (see submit_impl): the largest count
     // of the previous batch of this shape plus a margin; 0 = nothing known yet (copy up to the caller's capacity).
     int spec_rows = 0;
+    // ORB_B200_EAGER_D2H (default 1): result copies are enqueued by submit behind the chunk's kernels; 0: by wait, once the
+    // chunk's counts are on the host (one host round trip per chunk, exact row counts).
+    bool eager_out = true;
     // image ingest (orb_extractor_set_ingest): raw frames -> remap -> gray, fused into the level-0 load
     struct Ingest {
         bool on = false;
@@ -515,6 +518,7 @@ extern "C" int orb_extractor_create(const orb_params* params, int max_rows, int 
         if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&h->lanePyr[i], cudaEventDisableTiming);
     }
     if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&h->evSplit, cudaEventDisableTiming);
+    if (const char* e = getenv("ORB_B200_EAGER_D2H")) h->eager_out = atoi(e) != 0;
     if (const char* e = getenv("ORB_B200_LANES")) h->lanes = std::min<int>(orb_extractor::MAX_LANES, std::max(1, atoi(e)));
     if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&h->streamIn, cudaStreamNonBlocking);
     if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&h->streamOut, cudaStreamNonBlocking);
@@ -523,6 +527,7 @@ extern "C" int orb_extractor_create(const orb_params* params, int max_rows, int 
         for (int i = 0; i < orb_extractor::MAX_CHUNKS && ce == cudaSuccess; ++i) {
             ce = cudaEventCreateWithFlags(&h->slot[k].evIn[i], cudaEventDisableTiming);
             if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&h->slot[k].evDone[i], cudaEventDisableTiming);
+            if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&h->slot[k].evCnt[i], cudaEventDisableTiming);
         }
     for (int k = 0; k < orb_extractor::NUM_SLOTS && ce == cudaSuccess; ++k)
         ce = cudaEventCreateWithFlags(&h->slot[k].evOut, cudaEventDisableTiming);
@@ -558,6 +563,7 @@ extern "C" void orb_extractor_destroy(orb_extractor* h) {
         for (int i = 0; i < orb_extractor::MAX_CHUNKS; ++i) {
             if (S.evIn[i]) cudaEventDestroy(S.evIn[i]);
             if (S.evDone[i]) cudaEventDestroy(S.evDone[i]);
+            if (S.evCnt[i]) cudaEventDestroy(S.evCnt[i]);
         }
         if (S.evOut) cudaEventDestroy(S.evOut);
     }
@@ -811,7 +817,7 @@ static int enqueue_batch(orb_extractor* h, orb_extractor::HostSlot& S, int n, co
         CUDA_TRY(cudaMalloc((void**)&S.d_dense, want));
         S.dense_cap = want;
     }
-    const int spec = std::min(cap, h->spec_rows > 0 ? h->spec_rows : cap);
+    const int spec = h->eager_out ? std::min(cap, h->spec_rows > 0 ? h->spec_rows : cap) : 0;
     // everything enqueued so far on the main stream (the previous batch's kernels: every lane joins there)
     // finishes before this batch touches the shared level / scratch buffers; a batch's status flags are copied
     // into its own slot at the end of its kernels, so the next batch does not have to wait for the result copies
@@ -867,11 +873,14 @@ static int enqueue_batch(orb_extractor* h, orb_extractor::HostSlot& S, int n, co
         CUDA_TRY(cudaStreamWaitEvent(h->streamOut, S.evDone[c], 0));
         CUDA_TRY(cudaMemcpyAsync(counts + f0, S.d_counts + f0, sizeof(int) * nf, cudaMemcpyDeviceToHost, h->streamOut));
         CUDA_TRY(cudaMemcpyAsync(S.h_status + f0, S.d_counts + h->max_batch + f0, sizeof(int) * nf, cudaMemcpyDeviceToHost, h->streamOut));
-        CUDA_TRY(cudaMemcpy2DAsync(kps + (size_t)f0 * cap, (size_t)cap * sizeof(orb_keypoint), S.d_kps + (size_t)f0 * S.out_cap,
-                                   (size_t)S.out_cap * sizeof(orb_keypoint), (size_t)spec * sizeof(orb_keypoint), nf, cudaMemcpyDeviceToHost,
-                                   h->streamOut));
-        CUDA_TRY(cudaMemcpy2DAsync(desc + (size_t)f0 * cap * 32, (size_t)cap * 32, S.d_desc + (size_t)f0 * S.out_cap * 32,
-                                   (size_t)S.out_cap * 32, (size_t)spec * 32, nf, cudaMemcpyDeviceToHost, h->streamOut));
+        if (spec > 0) {
+            CUDA_TRY(cudaMemcpy2DAsync(kps + (size_t)f0 * cap, (size_t)cap * sizeof(orb_keypoint), S.d_kps + (size_t)f0 * S.out_cap,
+                                       (size_t)S.out_cap * sizeof(orb_keypoint), (size_t)spec * sizeof(orb_keypoint), nf, cudaMemcpyDeviceToHost,
+                                       h->streamOut));
+            CUDA_TRY(cudaMemcpy2DAsync(desc + (size_t)f0 * cap * 32, (size_t)cap * 32, S.d_desc + (size_t)f0 * S.out_cap * 32,
+                                       (size_t)S.out_cap * 32, (size_t)spec * 32, nf, cudaMemcpyDeviceToHost, h->streamOut));
+        }
+        CUDA_TRY(cudaEventRecord(S.evCnt[c], h->streamOut));
     }
     CUDA_TRY(cudaEventRecord(S.evOut, h->streamOut));
     S.n = n;
@@ -1003,11 +1012,13 @@ extern "C" int orb_extract_batch_wait(orb_extractor* h, int ticket) {
     orb_extractor::HostSlot& S = h->slot[ticket];
     S.busy = false;
     CUDA_TRY(cudaSetDevice(h->device));
-    CUDA_TRY(cudaEventSynchronize(S.evOut));  // counts, status flags and the first spec_w rows of every frame are here
+    // eager copies: counts, status flags and the first spec_w rows of every frame arrive together
+    if (S.spec_w > 0) CUDA_TRY(cudaEventSynchronize(S.evOut));
     int maxAll = 0, bad = -1;
     bool topup = false;
     for (int c = 0; c < S.nchunks; ++c) {
         const int f0 = c * S.per, nf = std::min(S.per, S.n - f0);
+        if (S.spec_w == 0) CUDA_TRY(cudaEventSynchronize(S.evCnt[c]));  // counts of chunk c are on the host, its kernels are done
         int maxc = 0;
         for (int f = f0; f < f0 + nf; ++f) {
             maxc = std::max(maxc, S.counts[f]);

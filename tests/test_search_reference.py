@@ -25,7 +25,9 @@ def digest(*arrays):
 
 
 # ---- seeded cases: every call returns the flattened result of one method for impl = None (oracle), "reference" (the
-# compiled src/ORBmatcher.cc) or "gpu" (the CUDA library through its host mirror) ----
+# compiled src/ORBmatcher.cc), "gpu" (the CUDA library through its host mirror) or "adapter" (the drop-in
+# ORB_SLAM2::ORBmatcher class of orb_slam_system_b200/adapter, compiled against the same stand-in objects and driven
+# through the very bridge that drives the compiled reference: oracle/Makefile adaptermatch) ----
 def _gpu(nnratio, check_ori):
     from orb_slam_system_b200 import ORBmatcher
     return ORBmatcher(nnratio, check_ori)
@@ -157,8 +159,8 @@ def case_loop(impl, seed, th):
         n, fq = m.SearchByProjectionKF(KF, claimed, q, u, v, radius)
         m.close()
         return n, fq, claimed
-    if impl == "reference":
-        n, fq = oracle.ref_search_by_projection_loop(KF, claimed, q, u, v, radius)
+    if impl in ("reference", "adapter"):
+        n, fq = oracle.ref_search_by_projection_loop(KF, claimed, q, u, v, radius, impl=impl)
     else:
         n, fq = oracle.search_kf_window(KF, claimed, q, u, v, radius, None, 50)
     return n, fq, claimed
@@ -176,8 +178,8 @@ def case_sim3(impl, seed, th):
         r = m.SearchBySim3(KF2, q, u, v, radius, level)
         m.close()
         return r
-    if impl == "reference":
-        return oracle.ref_search_by_sim3(KF2, q, u, v, level, th)
+    if impl in ("reference", "adapter"):
+        return oracle.ref_search_by_sim3(KF2, q, u, v, level, th, impl=impl)
     return oracle.search_kf_window(KF2, None, q, u, v, radius, level, 100)
 
 
@@ -193,8 +195,8 @@ def case_fuse(impl, seed, th, variant):
         r = m.FuseSearch(KF, q, u, v, radius, level)
         m.close()
         return r
-    if impl == "reference":
-        return oracle.ref_fuse_search(KF, q, u, v, level, th, variant)
+    if impl in ("reference", "adapter"):
+        return oracle.ref_fuse_search(KF, q, u, v, level, th, variant, impl=impl)
     return oracle.search_kf_window(KF, None, q, u, v, radius, level, 50)
 
 
@@ -258,6 +260,31 @@ def test_gpu_matches_committed_reference_digests(name):
     g = CASES[name]("gpu")
     assert gold[name]["matches"] == int(g[0]), name
     assert gold[name]["sha256_24"] == digest(*g[1:]), name
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_adapter_class_matches_committed_reference_digests(name):
+    """The drop-in ORB_SLAM2::ORBmatcher (adapter/ORBmatcher.h + ORBmatcher_b200.cc: the reference's signatures, Frame& /
+    KeyFrame* / MapPoint* arguments, gather and write-back around the orb_search_* calls) run through the bridge that
+    runs the reference's own class, against the digests of the compiled reference."""
+    if oracle.adapter_match_lib() is None:
+        pytest.skip("oracle/_ref/libadapter_match.so not built (oracle/Makefile adaptermatch)")
+    gold = json.load(open(GOLDEN))
+    a = CASES[name]("adapter")
+    assert gold[name]["matches"] == int(a[0]), name
+    assert gold[name]["sha256_24"] == digest(*a[1:]), name
+
+
+@pytest.mark.gpu
+def test_adapter_descriptor_distance():
+    if oracle.adapter_match_lib() is None:
+        pytest.skip("oracle/_ref/libadapter_match.so not built")
+    rng = np.random.default_rng(6)
+    a, b = rand_desc(rng, 40, live_bits=256), rand_desc(rng, 40, live_bits=256)
+    fn = oracle.adapter_match_lib().refm_descriptor_distance
+    for i in range(40):
+        assert fn(a[i].ctypes.data, b[i].ctypes.data) == int(np.unpackbits(a[i] ^ b[i]).sum())
 
 
 if __name__ == "__main__":  # regenerate the golden digests from the compiled reference
