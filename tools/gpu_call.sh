@@ -1,10 +1,12 @@
 mkdir -p gpurun_out
-O=gpurun_out/r02b_e2e.txt; : > $O
-for eager in 1 0; do for conn in "" 32; do for depth in 3 2; do
-  if [ -n "$conn" ]; then export CUDA_DEVICE_MAX_CONNECTIONS=$conn; else unset CUDA_DEVICE_MAX_CONNECTIONS; fi
-  DEPTH=$depth ORB_B200_EAGER_D2H=$eager timeout 120 python tools/e2e_probe.py >> $O 2>&1
-done; done; done
-export CUDA_DEVICE_MAX_CONNECTIONS=32
-for lanes in 1 3; do ORB_B200_LANES=$lanes timeout 120 python tools/e2e_probe.py >> $O 2>&1; done
-for chunk in 16 64; do ORB_B200_CHUNK=$chunk timeout 120 python tools/e2e_probe.py >> $O 2>&1; done
-cat $O
+P=gpurun_out/r02c
+timeout 900 python bench.py > ${P}_bench_default.json 2> ${P}_bench_default.err; echo "bench rc=$?"
+timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > ${P}_bench_reference.json 2>> ${P}_bench_default.err
+timeout 300 python tools/probes/match_bench.py > ${P}_match_bench.txt 2>&1
+SHORT="python bench.py --steps 2 --warmup 1 --repeats 1 --no-cpu-baseline --no-next-rows --no-other-shapes"
+timeout 600 $SHORT > ${P}_bench_short.json 2> ${P}_bench_short.err && \
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 500 --csv --log-file ${P}_launches.csv $SHORT > ${P}_ncu1.log 2>&1
+timeout 1200 ncu --set full --clock-control none -k regex:'k_(detect|octree|blur|describe|resize|repitch)' -c 26 -o ${P}_prof_extract $SHORT > ${P}_ncu2.log 2>&1
+MB="python tools/probes/match_bench.py --only mma --reps 1"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_match_mma -s 2 -c 2 -o ${P}_prof_match $MB > ${P}_ncu3.log 2>&1
+du -sh gpurun_out; ls -la gpurun_out

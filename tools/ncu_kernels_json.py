@@ -23,7 +23,11 @@ def main(src, dst):
     want = {"time_us": "gpu__time_duration.sum", "dram_read_bytes": "dram__bytes_read.sum", "dram_write_bytes": "dram__bytes_write.sum",
             "warp_inst": "smsp__inst_executed.sum"}
     kernels, frames = {}, 0
-    for r in rows[2:]:
+    body = rows[2:]
+    # whole launch sequences only: a capture cut by -c may end with the first kernels of a sequence whose describe
+    # launch (which tells how many frames it covered) is missing
+    last = max((i for i, r in enumerate(body) if r[col["Kernel Name"]].startswith("k_describe")), default=len(body) - 1)
+    for r in body[:last + 1]:
         name = r[col["Kernel Name"]].split("(")[0].strip()
         grid = [int(x) for x in re.findall(r"\d+", r[col["Grid Size"]])]
         k = kernels.setdefault(name, {"launches": 0, **{w: 0.0 for w in want}})
