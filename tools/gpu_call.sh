@@ -1,12 +1,9 @@
 mkdir -p gpurun_out
-P=gpurun_out/r02c
-timeout 900 python bench.py > ${P}_bench_default.json 2> ${P}_bench_default.err; echo "bench rc=$?"
-timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > ${P}_bench_reference.json 2>> ${P}_bench_default.err
-timeout 300 python tools/probes/match_bench.py > ${P}_match_bench.txt 2>&1
-SHORT="python bench.py --steps 2 --warmup 1 --repeats 1 --no-cpu-baseline --no-next-rows --no-other-shapes"
-timeout 600 $SHORT > ${P}_bench_short.json 2> ${P}_bench_short.err && \
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 500 --csv --log-file ${P}_launches.csv $SHORT > ${P}_ncu1.log 2>&1
-timeout 1200 ncu --set full --clock-control none -k regex:'k_(detect|octree|blur|describe|resize|repitch)' -c 26 -o ${P}_prof_extract $SHORT > ${P}_ncu2.log 2>&1
-MB="python tools/probes/match_bench.py --only mma --reps 1"
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_match_mma -s 2 -c 2 -o ${P}_prof_match $MB > ${P}_ncu3.log 2>&1
-du -sh gpurun_out; ls -la gpurun_out
+P=gpurun_out/r02d
+nvidia-smi topo -m > ${P}_topo.txt 2>&1; nproc >> ${P}_topo.txt; free -g >> ${P}_topo.txt
+timeout 600 python tools/probes/pcie_ceiling.py --ns 1,2,4,8 --seconds 1.0 --out ${P}_pcie_ceiling.json > ${P}_pcie_ceiling.txt 2>&1
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511"
+timeout 900 $TR bench.py --gpus 8 > ${P}_bench_n8.json 2> ${P}_bench_n8.err; echo "bench8 rc=$?"
+ORB_B200_EAGER_D2H=0 timeout 600 $TR bench.py --gpus 8 --no-other-shapes > ${P}_bench_n8_lazy.json 2> ${P}_bench_n8_lazy.err; echo "bench8 lazy rc=$?"
+timeout 600 python -m pytest tests/test_gpu_multi.py -m gpu -q > ${P}_pytest_multi.txt 2>&1
+tail -n 3 ${P}_pytest_multi.txt; cat ${P}_pcie_ceiling.txt | cut -c1-400
