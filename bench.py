@@ -341,6 +341,33 @@ def next_rows(device):
     exi.close()
     ex.close()
     m.close()
+    # ---- one KITTI frame at a time through the C++ drop-in class ORB_SLAM2::ORBextractor::operator() (adapter/ORBextractor_b200.cc
+    # compiled against the cv:: stand-in, oracle/Makefile adapter), one persistent instance, host cv::Mat in, std::vector<cv::KeyPoint>
+    # + cv::Mat out: with mvImagePyramid refilled after every call (what the reference's Frame::ComputeStereoMatches reads) and without
+    try:
+        import ctypes as C
+        from orb_slam_system_b200 import ORBextractor as _E
+        lib_path = os.path.join(ROOT, "oracle", "_ref", "libadapter_orb.so")
+        if os.path.exists(lib_path):
+            A = C.CDLL(lib_path)
+            A.ref_extract_many.restype = C.c_double
+            A.ref_extract_many.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_int,
+                                           C.POINTER(C.c_longlong)]
+            tot = C.c_longlong(0)
+            row = {"workload": "one 1241x376 frame per call through ORB_SLAM2::ORBextractor::operator() (C++ adapter class, persistent instance, 50 calls)"}
+            for key, env in (("ms_per_frame_with_mvImagePyramid", "1"), ("ms_per_frame_without_mvImagePyramid", "0")):
+                os.environ["ORB_B200_IMAGE_PYRAMID"] = env
+                A.ref_extract_many(2000, SCALE, NLEVELS, INI_TH, MIN_TH, 376, 1241, 7, 0, 10, 1, C.byref(tot))
+                secs = A.ref_extract_many(2000, SCALE, NLEVELS, INI_TH, MIN_TH, 376, 1241, 7, 0, 50, 1, C.byref(tot))
+                row[key] = 1e3 * secs / 50
+            os.environ.pop("ORB_B200_IMAGE_PYRAMID", None)
+            exl = _E(2000, SCALE, NLEVELS, INI_TH, MIN_TH, max_batch=1, device=device)
+            img = oracle.synth_frame(376, 1241, frame=0)
+            row["ms_per_frame_c_abi_orb_extract"] = 1e3 * best_of(lambda: exl(img), 30)
+            exl.close()
+            out["adapter_latency"] = row
+    except Exception as e:
+        out["adapter_latency"] = {"error": repr(e)}
     return out
 
 

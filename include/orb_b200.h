@@ -161,6 +161,11 @@ int orb_ingest_extract_batch_device(orb_extractor* h, int n, const uint8_t* d_ra
 int orb_get_pyramid_level(orb_extractor* h, int frame, int level, uint8_t* dst, size_t dst_stride,
                           int* rows, int* cols);
 
+/* All levels of frame `frame` in one go: dst[l] / dst_stride[l] for l < nlevels of the extractor (dst[l] NULL: level skipped).
+ * The copies are enqueued together and waited for once -- what the adapter uses to refill mvImagePyramid
+ * (2 x nlevels synchronous calls otherwise). */
+int orb_get_pyramid_levels(orb_extractor* h, int frame, uint8_t* const* dst, const size_t* dst_stride);
+
 /* Counters of the last call for frame `frame` (arrays of nlevels; NULL skipped):
  * FAST candidates handed to the octree and keypoints kept, per level. */
 int orb_extractor_level_stats(orb_extractor* h, int frame, int32_t* candidates, int32_t* kept);

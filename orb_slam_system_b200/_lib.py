@@ -72,7 +72,7 @@ _lib = None
 EXPORTS = [
     "orb_extractor_create", "orb_extractor_destroy", "orb_extractor_tables",
     "orb_extractor_keypoint_bound", "orb_extract", "orb_extract_batch", "orb_extract_batch_submit", "orb_extract_batch_wait", "orb_extract_batch_device",
-    "orb_extractor_sync", "orb_extractor_stream", "orb_get_pyramid_level",
+    "orb_extractor_sync", "orb_extractor_stream", "orb_get_pyramid_level", "orb_get_pyramid_levels",
     "orb_extractor_set_ingest", "orb_ingest_extract_batch", "orb_ingest_extract_batch_submit", "orb_ingest_extract_batch_device",
     "orb_extractor_level_stats", "orb_extractor_set_profiling", "orb_extractor_stage_times",
     "orb_stage_name", "orb_matcher_create", "orb_matcher_destroy", "orb_match_all",
@@ -111,6 +111,7 @@ def lib():
         L.orb_extractor_stream.argtypes = [vp]
         L.orb_extractor_stream.restype = vp
         L.orb_get_pyramid_level.argtypes = [vp, i32, i32, vp, sz, C.POINTER(i32), C.POINTER(i32)]
+        L.orb_get_pyramid_levels.argtypes = [vp, i32, vp, vp]
         L.orb_extractor_level_stats.argtypes = [vp, i32, vp, vp]
         L.orb_extractor_set_profiling.argtypes = [vp, i32]
         L.orb_extractor_stage_times.argtypes = [vp, vp, C.POINTER(i32)]

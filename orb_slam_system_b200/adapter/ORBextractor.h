@@ -43,6 +43,14 @@ public:
     // the last call where they live on the device (an addition; nothing in the reference calls it).
     orb_extractor* handle() const { return handle_; }
 
+    // Two switches the reference does not have (process-wide, read when an instance is constructed / called):
+    // the CUDA device of the instances constructed afterwards (default: ORB_B200_DEVICE in the environment, else 0), and
+    // whether operator() copies the pyramid back into mvImagePyramid (default on, or ORB_B200_IMAGE_PYRAMID=0).  With
+    // Frame::ComputeStereoMatches routed through orb_compute_stereo_matches the pyramid is read on the device and the
+    // copy (1.9 MB per KITTI frame) can be switched off.
+    static void UseDevice(int device);
+    static void KeepImagePyramid(bool on);
+
     // Refilled after every call (tight level images inside a 19-px reflected border, exactly the
     // layout Frame::ComputeStereoMatches reads, reference src/Frame.cc:453,543-560).
     std::vector<cv::Mat> mvImagePyramid;

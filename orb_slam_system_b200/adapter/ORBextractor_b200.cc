@@ -5,7 +5,9 @@
 // error) is raised as cv::Exception, the only error channel operator() has.
 #include "ORBextractor.h"
 
+#include <cstdlib>
 #include <string>
+#include <vector>
 
 #include <opencv2/core/core.hpp>
 #include <opencv2/imgproc/imgproc.hpp>
@@ -15,6 +17,23 @@
 namespace ORB_SLAM2 {
 
 static const int EDGE_THRESHOLD = 19;
+
+static int g_device = -1;      // UseDevice
+static int g_keep_pyramid = -1;  // KeepImagePyramid; -1: ask the environment
+
+void ORBextractor::UseDevice(int device) { g_device = device; }
+void ORBextractor::KeepImagePyramid(bool on) { g_keep_pyramid = on ? 1 : 0; }
+
+static int device_ordinal() {
+    if (g_device >= 0) return g_device;
+    const char* e = getenv("ORB_B200_DEVICE");
+    return e ? atoi(e) : 0;
+}
+static bool keep_pyramid() {
+    if (g_keep_pyramid >= 0) return g_keep_pyramid != 0;
+    const char* e = getenv("ORB_B200_IMAGE_PYRAMID");
+    return !(e && atoi(e) == 0);
+}
 
 [[noreturn]] static void raise(const char* what) {
     throw cv::Exception(std::string("orb_b200: ") + what + ": " + orb_last_error());
@@ -29,7 +48,7 @@ ORBextractor::ORBextractor(int _nfeatures, float _scaleFactor, int _nlevels, int
     p.nlevels = _nlevels;
     p.ini_th_fast = _iniThFAST;
     p.min_th_fast = _minThFAST;
-    if (orb_extractor_create(&p, 0, 0, 1, 0, &handle_) != ORB_OK) raise("orb_extractor_create");
+    if (orb_extractor_create(&p, 0, 0, 1, device_ordinal(), &handle_) != ORB_OK) raise("orb_extractor_create");
     mvScaleFactor.resize(nlevels);
     mvInvScaleFactor.resize(nlevels);
     mvLevelSigma2.resize(nlevels);
@@ -58,16 +77,24 @@ void ORBextractor::operator()(cv::InputArray _image, cv::InputArray /*mask*/, st
                     desc.ptr<uint8_t>(0), bound, &count) != ORB_OK)
         raise("orb_extract");
 
-    // mvImagePyramid: level ROI inside a (w+38) x (h+38) buffer with a reflected border (src/ORBextractor.cc:497-515)
-    for (int level = 0; level < nlevels; ++level) {
-        int r = 0, c = 0;
-        if (orb_get_pyramid_level(handle_, 0, level, nullptr, 0, &r, &c) != ORB_OK) raise("orb_get_pyramid_level");
-        cv::Mat temp(cv::Size(c + 2 * EDGE_THRESHOLD, r + 2 * EDGE_THRESHOLD), image.type());
-        mvImagePyramid[level] = temp(cv::Rect(EDGE_THRESHOLD, EDGE_THRESHOLD, c, r));
-        if (orb_get_pyramid_level(handle_, 0, level, mvImagePyramid[level].ptr<uint8_t>(0), (size_t)mvImagePyramid[level].step, &r, &c) != ORB_OK)
-            raise("orb_get_pyramid_level");
-        cv::copyMakeBorder(mvImagePyramid[level], temp, EDGE_THRESHOLD, EDGE_THRESHOLD, EDGE_THRESHOLD, EDGE_THRESHOLD,
-                           cv::BORDER_REFLECT_101 + cv::BORDER_ISOLATED);
+    // mvImagePyramid: level ROI inside a (w+38) x (h+38) buffer with a reflected border (src/ORBextractor.cc:497-515);
+    // all levels are fetched with one set of copies and one synchronisation
+    if (keep_pyramid()) {
+        std::vector<cv::Mat> padded(nlevels);
+        std::vector<uint8_t*> dst(nlevels);
+        std::vector<size_t> stride(nlevels);
+        for (int level = 0; level < nlevels; ++level) {
+            int r = 0, c = 0;
+            if (orb_get_pyramid_level(handle_, 0, level, nullptr, 0, &r, &c) != ORB_OK) raise("orb_get_pyramid_level");  // sizes only
+            padded[level] = cv::Mat(cv::Size(c + 2 * EDGE_THRESHOLD, r + 2 * EDGE_THRESHOLD), image.type());
+            mvImagePyramid[level] = padded[level](cv::Rect(EDGE_THRESHOLD, EDGE_THRESHOLD, c, r));
+            dst[level] = mvImagePyramid[level].ptr<uint8_t>(0);
+            stride[level] = (size_t)mvImagePyramid[level].step;
+        }
+        if (orb_get_pyramid_levels(handle_, 0, dst.data(), stride.data()) != ORB_OK) raise("orb_get_pyramid_levels");
+        for (int level = 0; level < nlevels; ++level)
+            cv::copyMakeBorder(mvImagePyramid[level], padded[level], EDGE_THRESHOLD, EDGE_THRESHOLD, EDGE_THRESHOLD, EDGE_THRESHOLD,
+                               cv::BORDER_REFLECT_101 + cv::BORDER_ISOLATED);
     }
 
     if (count == 0) {

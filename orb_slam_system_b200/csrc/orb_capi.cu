@@ -1074,6 +1074,22 @@ extern "C" int orb_get_pyramid_level(orb_extractor* h, int frame, int level, uin
     return ORB_OK;
 }
 
+extern "C" int orb_get_pyramid_levels(orb_extractor* h, int frame, uint8_t* const* dst, const size_t* dst_stride) {
+    if (!h || !dst || !dst_stride) return fail(ORB_ERR_INVALID, "null argument");
+    if (h->plan.rows == 0) return fail(ORB_ERR_INVALID, "no frame extracted yet");
+    if (frame < 0 || frame >= h->max_batch) return fail(ORB_ERR_INVALID, "bad frame");
+    CUDA_TRY(cudaSetDevice(h->device));
+    for (int l = 0; l < h->plan.nlevels; ++l) {
+        if (!dst[l]) continue;
+        const OrbLevel& L = h->plan.lv[l];
+        if (dst_stride[l] < (size_t)L.cols) return fail(ORB_ERR_INVALID, "dst_stride < cols (level %d)", l);
+        const uint8_t* base = (L.src == 0 && h->last_l0) ? h->last_l0 : L.img;
+        CUDA_TRY(cudaMemcpy2DAsync(dst[l], dst_stride[l], base + (size_t)frame * L.plane, L.pitch, L.cols, L.rows, cudaMemcpyDeviceToHost, h->stream));
+    }
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return ORB_OK;
+}
+
 extern "C" int orb_extractor_level_stats(orb_extractor* h, int frame, int32_t* candidates, int32_t* kept) {
     if (!h || h->plan.rows == 0) return fail(ORB_ERR_INVALID, "no frame extracted yet");
     if (frame < 0 || frame >= h->max_batch) return fail(ORB_ERR_INVALID, "bad frame");

@@ -221,11 +221,23 @@ class ORBextractor:
         check(lib().orb_get_pyramid_level(self._h, frame, level, ptr(out), out.strides[0], C.byref(r), C.byref(c)))
         return out
 
+    def pyramid_levels(self, frame=0):
+        """All level images of one frame of the last call with one set of copies and one synchronisation."""
+        r, c = C.c_int(0), C.c_int(0)
+        outs = []
+        for l in range(self.nlevels):
+            check(lib().orb_get_pyramid_level(self._h, frame, l, None, 0, C.byref(r), C.byref(c)))
+            outs.append(np.zeros((r.value, c.value), np.uint8))
+        dst = (C.c_void_p * self.nlevels)(*[o.ctypes.data for o in outs])
+        stride = (C.c_size_t * self.nlevels)(*[o.strides[0] for o in outs])
+        check(lib().orb_get_pyramid_levels(self._h, frame, dst, stride))
+        return outs
+
     @property
     def mvImagePyramid(self):
         """Level images of frame 0 of the last call (tight crops; the reference keeps a 19-px
         reflected border around each, which nothing on this path reads)."""
-        return [self.pyramid_level(l) for l in range(self.nlevels)]
+        return self.pyramid_levels(0)
 
     def set_profiling(self, on=True):
         check(lib().orb_extractor_set_profiling(self._h, 1 if on else 0))

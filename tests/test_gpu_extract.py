@@ -79,6 +79,17 @@ def test_pyramid_levels_match_oracle():
     ex.close()
 
 
+def test_pyramid_levels_in_one_call():
+    imgs = np.stack([oracle.synth_frame(200, 300, frame=4 + f) for f in range(3)])
+    ex = ORBextractor(500, 1.2, 8, 20, 7, max_batch=3)
+    ex.extract_batch(imgs)
+    for f in range(3):
+        got = ex.pyramid_levels(f)
+        for l in range(8):
+            assert np.array_equal(got[l], oracle.pyramid_level(imgs[f], l)), (f, l)
+    ex.close()
+
+
 def test_batch_equals_single_and_is_deterministic():
     rows, cols, nf = 376, 1241, 2000
     frames = np.stack([oracle.synth_frame(rows, cols, frame=f, right=f & 1) for f in range(6)])
