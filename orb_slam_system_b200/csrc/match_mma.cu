@@ -301,6 +301,357 @@ __global__ void __launch_bounds__(MM_THREADS, 2) k_match_mma(const uint8_t* __re
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// k_match_mma2: the same contraction, warp-specialised.  One CTA per SM = 256 queries (two 128-row A tiles that share
+// every expanded train tile) and three roles that meet only at mbarriers:
+//   producers  4 warps, one train row per thread and tile: 2 x 128-bit loads, expansion into one of three B stages,
+//              fence.proxy.async, arrive on full[stage]; wait on empty[stage] (committed by the MMAs that read it)
+//   MMA        one thread: waits for full[stage] and for the epilogue to have drained the accumulator stage, issues
+//              2 x (6 | 8) tcgen05.mma 128 x 128 x 32 (A tile 0 and A tile 1 against the same B stage), commits to
+//              empty[stage] and to tfull[accumulator stage]
+//   epilogue   8 warps, one query row per thread (all 128 columns of a tile: two 64-column slabs): tcgen05.ld, packed key
+//              tournament, running keys; releases the accumulator stage as soon as its second slab is in registers
+// No block-wide barrier inside the tile loop; the train-tile expansion is paid once per 256 queries instead of once per 128.
+// ------------------------------------------------------------------------------------------
+#define M2_PROD_WARPS 4
+#define M2_THREADS(EW) (((EW) + M2_PROD_WARPS + 1) * 32)
+#define M2_STAGES 3
+#define M2_OFF_B (2 * MM_TILE_BYTES)
+#define M2_OFF_BAR (M2_OFF_B + M2_STAGES * MM_TILE_BYTES)  // full[3], empty[3], tfull[2], tempty[2]
+#define M2_OFF_TMEM (M2_OFF_BAR + 10 * 8)
+#define M2_OFF_FLAGS (M2_OFF_TMEM + 8)
+#define M2_OFF_MERGE (M2_OFF_FLAGS + 32)  // 256 rows x (best, second) of the upper column half (16 epilogue warps)
+#define M2_SMEM (M2_OFF_MERGE + 2 * MM_M * 8)
+
+__device__ __forceinline__ void mm_mbar_arrive(unsigned bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+// 64 accumulator columns (two tcgen05.ld of 32) -> 32 packed key pairs; low lane: column i, high lane: column 32 + i,
+// key = (256 - acc) << 6 | column; columns >= lim (past the last train row) become 0xffff
+template <int KIND>
+__device__ __forceinline__ void mm_slab_keys(unsigned (&acc0)[32], unsigned (&acc1)[32], const MmParams& prm, int lim, unsigned (&P)[32]) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        if (KIND == 1) {  // binary32 accumulators holding integers: + 1.5 * 2^23 leaves the integer in the low mantissa bits
+            acc0[i] = __float_as_uint(__fadd_rn(__uint_as_float(acc0[i]), 12582912.0f)) - 0x4B400000u;
+            acc1[i] = __float_as_uint(__fadd_rn(__uint_as_float(acc1[i]), 12582912.0f)) - 0x4B400000u;
+        }
+        const unsigned c = (256u * 64u + (unsigned)i) | ((256u * 64u + 32u + (unsigned)i) << 16);
+        P[i] = acc1[i] * prm.neg_hi + (acc0[i] * prm.neg_lo + c);
+    }
+    if (lim < 64) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) P[i] |= (i < lim ? 0u : 0x0000ffffu) | (i + 32 < lim ? 0u : 0xffff0000u);
+    }
+}
+
+// min / second-min tournament over 32 packed key pairs; both halves of b2 / s2 hold the slab's best / second 16-bit key
+__device__ __forceinline__ void mm_tournament(const unsigned (&P)[32], unsigned& b2, unsigned& s2) {
+    unsigned lo[16], hi[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        lo[i] = __vminu2(P[2 * i], P[2 * i + 1]);
+        hi[i] = __vmaxu2(P[2 * i], P[2 * i + 1]);
+    }
+#pragma unroll
+    for (int n = 8; n >= 1; n >>= 1) {
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+            const unsigned b = __vminu2(lo[2 * i], lo[2 * i + 1]);
+            const unsigned m = __vmaxu2(lo[2 * i], lo[2 * i + 1]);
+            hi[i] = __vimin3_u16x2(m, hi[2 * i], hi[2 * i + 1]);
+            lo[i] = b;
+        }
+    }
+    const unsigned bs = __byte_perm(lo[0], 0u, 0x1032), ss = __byte_perm(hi[0], 0u, 0x1032);
+    b2 = __vminu2(lo[0], bs);
+    s2 = __vimin3_u16x2(__vmaxu2(lo[0], bs), hi[0], ss);
+}
+
+// 32 accumulator columns (one tcgen05.ld) -> 16 packed key pairs; low lane: column i, high lane: column 16 + i
+template <int KIND>
+__device__ __forceinline__ void mm_unit_keys(unsigned (&acc)[32], const MmParams& prm, int lim, unsigned (&P)[16]) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        if (KIND == 1) {
+            acc[i] = __float_as_uint(__fadd_rn(__uint_as_float(acc[i]), 12582912.0f)) - 0x4B400000u;
+            acc[i + 16] = __float_as_uint(__fadd_rn(__uint_as_float(acc[i + 16]), 12582912.0f)) - 0x4B400000u;
+        }
+        const unsigned c = (256u * 64u + (unsigned)i) | ((256u * 64u + 16u + (unsigned)i) << 16);
+        P[i] = acc[i + 16] * prm.neg_hi + (acc[i] * prm.neg_lo + c);
+    }
+    if (lim < 32) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) P[i] |= (i < lim ? 0u : 0x0000ffffu) | (i + 16 < lim ? 0u : 0xffff0000u);
+    }
+}
+
+__device__ __forceinline__ void mm_tournament16(const unsigned (&P)[16], unsigned& b2, unsigned& s2) {
+    unsigned lo[8], hi[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        lo[i] = __vminu2(P[2 * i], P[2 * i + 1]);
+        hi[i] = __vmaxu2(P[2 * i], P[2 * i + 1]);
+    }
+#pragma unroll
+    for (int n = 4; n >= 1; n >>= 1) {
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+            const unsigned b = __vminu2(lo[2 * i], lo[2 * i + 1]);
+            const unsigned m = __vmaxu2(lo[2 * i], lo[2 * i + 1]);
+            hi[i] = __vimin3_u16x2(m, hi[2 * i], hi[2 * i + 1]);
+            lo[i] = b;
+        }
+    }
+    const unsigned bs = __byte_perm(lo[0], 0u, 0x1032), ss = __byte_perm(hi[0], 0u, 0x1032);
+    b2 = __vminu2(lo[0], bs);
+    s2 = __vimin3_u16x2(__vmaxu2(lo[0], bs), hi[0], ss);
+}
+
+// EW = 8 (shipped): one query row per epilogue thread (all 128 columns of a tile).  EW = 16: two threads per query row, 64
+// columns each in units of 32, 80 registers per thread so that 21 warps fit the register file; measured on B200: 3.59 T
+// pairs/s against 3.83 T with EW = 8 (more warps do not help: the epilogue is bound by the ALU pipe's issue rate, and
+// the 32-column units cost more instructions per distance), kept as a comparator.
+template <int KIND, int EW>
+__global__ void __launch_bounds__(M2_THREADS(EW), 1) k_match_mma2(const uint8_t* __restrict__ q, const int* __restrict__ nq, size_t q_stride,
+                                                              const uint8_t* __restrict__ t, const int* __restrict__ nt, size_t t_stride,
+                                                              int* __restrict__ best_idx, int* __restrict__ best_dist,
+                                                              int* __restrict__ second_dist, size_t out_stride, MmParams prm) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int p = blockIdx.y;
+    const int nQ = nq[p], nT = nt[p];
+    const int q0 = blockIdx.x * 2 * MM_M;
+    if (q0 >= nQ || nT >= (1 << 22)) return;
+    const uint4* Q = reinterpret_cast<const uint4*>(q + p * q_stride);
+    const uint4* T = reinterpret_cast<const uint4*>(t + p * t_stride);
+    const unsigned sA = mm_smem_u32(smem);
+    const unsigned bFull = sA + M2_OFF_BAR, bEmpty = bFull + 8 * M2_STAGES, bTfull = bEmpty + 8 * M2_STAGES, bTempty = bTfull + 16;
+    unsigned* tmem_slot = reinterpret_cast<unsigned*>(smem + M2_OFF_TMEM);
+    volatile int* flags = reinterpret_cast<volatile int*>(smem + M2_OFF_FLAGS);
+    const int ntiles = (nT + MM_N - 1) / MM_N;
+
+    if (warp == EW + M2_PROD_WARPS) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(mm_smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 0) {
+        for (int s = 0; s < M2_STAGES; ++s) {
+            mm_mbar_init(bFull + 8 * s, M2_PROD_WARPS * 32);
+            mm_mbar_init(bEmpty + 8 * s, 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mm_mbar_init(bTfull + 8 * a, 1);
+            mm_mbar_init(bTempty + 8 * a, EW);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // both A tiles (256 query rows x 2 halves), +-1 bytes
+    for (int item = tid; item < 4 * MM_M; item += M2_THREADS(EW)) {
+        const int er = (item & 7) | ((item >> 4) << 3), ehf = (item >> 3) & 1;
+        const int row = q0 + er;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (row < nQ) v = __ldg(Q + 2 * (size_t)row + ehf);
+        mm_expand_half_row(smem + (er >> 7) * MM_TILE_BYTES, er & 127, ehf, v, prm.lut_a, 4);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    mm_fence_before();
+    __syncthreads();
+    mm_fence_after();
+    const unsigned tmem = *tmem_slot;
+
+    if (EW == 16 && warp < EW) {
+        // ---------------- epilogue, 16 warps: (A tile, lane quarter, column half) per warp ----------------
+        const int tileA = (warp >> 2) & 1, half = warp >> 3;
+        const unsigned trow = tmem + ((unsigned)(warp & 3) << 21) + (unsigned)(tileA * MM_N + half * 64);
+        unsigned bestk = 0xffffffffu, seck = 0xffffffffu;
+        auto merge = [&](unsigned b2, unsigned s2, int unit) {  // train index = unit * 32 + column
+            const unsigned kb = (b2 & 0xffc0001fu) | ((unsigned)unit << 5);
+            const unsigned mx = max(kb, bestk);
+            seck = min(seck, min(mx, s2));
+            bestk = min(bestk, kb);
+        };
+        unsigned acc[32];
+        if (ntiles > 0) {
+            mm_mbar_wait(bTfull, 0u);
+            mm_fence_after();
+            mm_tmem_ld32(trow, acc);
+        }
+        for (int tt = 0; tt < ntiles; ++tt) {
+            const int a = tt & 1;
+            const unsigned ta = trow + (unsigned)(a * 2 * MM_N);
+            unsigned P[16], b2, s2;
+            mm_tmem_ld_wait();
+            mm_unit_keys<KIND>(acc, prm, nT - tt * MM_N - half * 64, P);
+            mm_tmem_ld32(ta + 32, acc);
+            mm_tournament16(P, b2, s2);
+            merge(b2, s2, tt * 4 + half * 2);
+            mm_tmem_ld_wait();
+            mm_fence_before();
+            __syncwarp();
+            if (lane == 0) mm_mbar_arrive(bTempty + 8 * a);
+            mm_unit_keys<KIND>(acc, prm, nT - tt * MM_N - half * 64 - 32, P);
+            if (tt + 1 < ntiles) {
+                mm_mbar_wait(bTfull + 8 * (a ^ 1), (unsigned)((tt + 1) >> 1) & 1u);
+                mm_fence_after();
+                mm_tmem_ld32(trow + (unsigned)((a ^ 1) * 2 * MM_N), acc);
+            }
+            mm_tournament16(P, b2, s2);
+            merge(b2, s2, tt * 4 + half * 2 + 1);
+        }
+        // the two column halves of a row meet in shared memory (named barrier 2: the epilogue warps only)
+        uint2* mrg = reinterpret_cast<uint2*>(smem + M2_OFF_MERGE);
+        const int rowInCta = tileA * MM_M + (warp & 3) * 32 + lane;
+        if (half == 1) mrg[rowInCta] = make_uint2(bestk, seck);
+        asm volatile("bar.sync 2, %0;" ::"n"(EW * 32) : "memory");
+        if (half == 0) {
+            const uint2 o = mrg[rowInCta];
+            const unsigned mx = max(bestk, o.x);
+            seck = min(min(seck, o.y), mx);
+            bestk = min(bestk, o.x);
+            const int qi = q0 + rowInCta;
+            if (qi < nQ) {
+                const uint4 a0 = __ldg(Q + 2 * (size_t)qi), a1 = __ldg(Q + 2 * (size_t)qi + 1);
+                const int na = __popc(a0.x) + __popc(a0.y) + __popc(a0.z) + __popc(a0.w) + __popc(a1.x) + __popc(a1.y) + __popc(a1.z) + __popc(a1.w);
+                int idx = -1, bd = INT_MAX, sd = INT_MAX;
+                if ((bestk >> 22) <= 512u) {
+                    idx = (int)(bestk & 0x3fffffu);
+                    bd = (int)(bestk >> 22) - 256 + na;
+                }
+                if ((seck >> 22) <= 512u) sd = (int)(seck >> 22) - 256 + na;
+                best_idx[p * out_stride + qi] = idx;
+                best_dist[p * out_stride + qi] = bd;
+                second_dist[p * out_stride + qi] = sd;
+            }
+        }
+        mm_fence_before();
+    } else if (warp < EW) {
+        // ---------------- epilogue, 8 warps: one query row per thread ----------------
+        const int tileA = warp >> 2;
+        const unsigned trow = tmem + ((unsigned)(warp & 3) << 21) + (unsigned)(tileA * MM_N);
+        unsigned bestk = 0xffffffffu, seck = 0xffffffffu;
+        auto merge = [&](unsigned b2, unsigned s2, int slab) {
+            // 32-bit keys: (256 - acc) << 22 | train index (slab * 64 + column); the second key only carries its distance
+            const unsigned kb = (b2 & 0xffc0003fu) | ((unsigned)slab << 6);
+            const unsigned mx = max(kb, bestk);
+            seck = min(seck, min(mx, s2));
+            bestk = min(bestk, kb);
+        };
+        // The accumulator loads run one slab ahead of the arithmetic: the tcgen05.ld of the next 64 columns is in flight
+        // while the tournament of the previous 64 runs.
+        unsigned acc0[32], acc1[32];
+        if (ntiles > 0) {
+            mm_mbar_wait(bTfull, 0u);
+            mm_fence_after();
+            mm_tmem_ld32(trow, acc0);
+            mm_tmem_ld32(trow + 32, acc1);
+        }
+        for (int tt = 0; tt < ntiles; ++tt) {
+            const int a = tt & 1;
+            const unsigned ta = trow + (unsigned)(a * 2 * MM_N);
+            unsigned P[32], b2, s2;
+            mm_tmem_ld_wait();  // columns 0..63 of tile tt
+            mm_slab_keys<KIND>(acc0, acc1, prm, nT - tt * MM_N, P);
+            mm_tmem_ld32(ta + 64, acc0);
+            mm_tmem_ld32(ta + 96, acc1);
+            mm_tournament(P, b2, s2);
+            merge(b2, s2, tt * 2);
+            mm_tmem_ld_wait();  // columns 64..127: this warp is done with the accumulator stage, the MMAs of tile tt + 2 may overwrite it
+            mm_fence_before();
+            __syncwarp();
+            if (lane == 0) mm_mbar_arrive(bTempty + 8 * a);
+            mm_slab_keys<KIND>(acc0, acc1, prm, nT - tt * MM_N - 64, P);
+            if (tt + 1 < ntiles) {
+                mm_mbar_wait(bTfull + 8 * (a ^ 1), (unsigned)((tt + 1) >> 1) & 1u);
+                mm_fence_after();
+                const unsigned tn = trow + (unsigned)((a ^ 1) * 2 * MM_N);
+                mm_tmem_ld32(tn, acc0);
+                mm_tmem_ld32(tn + 32, acc1);
+            }
+            mm_tournament(P, b2, s2);
+            merge(b2, s2, tt * 2 + 1);
+        }
+        const int qi = q0 + tileA * MM_M + (warp & 3) * 32 + lane;
+        if (qi < nQ) {
+            const uint4 a0 = __ldg(Q + 2 * (size_t)qi), a1 = __ldg(Q + 2 * (size_t)qi + 1);
+            const int na = __popc(a0.x) + __popc(a0.y) + __popc(a0.z) + __popc(a0.w) + __popc(a1.x) + __popc(a1.y) + __popc(a1.z) + __popc(a1.w);
+            int idx = -1, bd = INT_MAX, sd = INT_MAX;
+            if ((bestk >> 22) <= 512u) {
+                idx = (int)(bestk & 0x3fffffu);
+                bd = (int)(bestk >> 22) - 256 + na;
+            }
+            if ((seck >> 22) <= 512u) sd = (int)(seck >> 22) - 256 + na;
+            best_idx[p * out_stride + qi] = idx;
+            best_dist[p * out_stride + qi] = bd;
+            second_dist[p * out_stride + qi] = sd;
+        }
+        mm_fence_before();
+    } else if (warp < EW + M2_PROD_WARPS) {
+        // ---------------- producers: one train row per thread and tile ----------------
+        const int r = tid - EW * 32;
+        uint4 n0 = make_uint4(0, 0, 0, 0), n1 = n0;
+        if (r < nT) {
+            n0 = __ldg(T + 2 * (size_t)r);
+            n1 = __ldg(T + 2 * (size_t)r + 1);
+        }
+        for (int tt = 0; tt < ntiles; ++tt) {
+            const int s = tt % M2_STAGES;
+            const uint4 v0 = n0, v1 = n1;
+            {
+                const int row = (tt + 1) * MM_N + r;
+                n0 = n1 = make_uint4(0, 0, 0, 0);
+                if (row < nT) {
+                    n0 = __ldg(T + 2 * (size_t)row);
+                    n1 = __ldg(T + 2 * (size_t)row + 1);
+                }
+            }
+            // words 6-7 of every row of the tile zero => the MMAs skip the last two K-steps and nobody expands them
+            unsigned upper;
+            asm volatile(
+                "{\n.reg .pred p, q;\nsetp.ne.u32 p, %1, 0;\nbar.red.or.pred q, 1, %2, p;\nselp.u32 %0, 1, 0, q;\n}\n"
+                : "=r"(upper)
+                : "r"(v1.z | v1.w), "n"(M2_PROD_WARPS * 32)
+                : "memory");
+            mm_mbar_wait(bEmpty + 8 * s, ((unsigned)(tt / M2_STAGES) & 1u) ^ 1u);
+            uint8_t* tileB = smem + M2_OFF_B + s * MM_TILE_BYTES;
+            mm_expand_half_row(tileB, r, 0, v0, prm.lut_b, 4);
+            mm_expand_half_row(tileB, r, 1, v1, prm.lut_b, upper ? 4 : 2);
+            if (r == 0) flags[s] = (int)upper;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mm_mbar_arrive(bFull + 8 * s);
+        }
+    } else if (lane == 0) {
+        // ---------------- MMA issuer ----------------
+        const unsigned long long dA0 = prm.desc_base | (unsigned long long)((sA & 0x3ffffu) >> 4);
+        const unsigned long long dA1 = prm.desc_base | (unsigned long long)(((sA + MM_TILE_BYTES) & 0x3ffffu) >> 4);
+        for (int tt = 0; tt < ntiles; ++tt) {
+            const int s = tt % M2_STAGES, a = tt & 1;
+            mm_mbar_wait(bFull + 8 * s, (unsigned)(tt / M2_STAGES) & 1u);
+            mm_mbar_wait(bTempty + 8 * a, ((unsigned)(tt >> 1) & 1u) ^ 1u);
+            mm_fence_after();
+            const unsigned long long dB = prm.desc_base | (unsigned long long)(((sA + M2_OFF_B + s * MM_TILE_BYTES) & 0x3ffffu) >> 4);
+            const int ksteps = flags[s] ? 8 : 6;
+            const unsigned d0 = tmem + (unsigned)(a * 2 * MM_N);
+            for (int k = 0; k < ksteps; ++k) {
+                const unsigned long long o = (unsigned long long)((k * 2 * MM_LBO) >> 4);
+                mm_mma<KIND>(d0, dA0 + o, dB + o, prm.idesc, k > 0 ? 1u : 0u);
+            }
+            for (int k = 0; k < ksteps; ++k) {
+                const unsigned long long o = (unsigned long long)((k * 2 * MM_LBO) >> 4);
+                mm_mma<KIND>(d0 + MM_N, dA1 + o, dB + o, prm.idesc, k > 0 ? 1u : 0u);
+            }
+            mm_commit(bEmpty + 8 * s);
+            mm_commit(bTfull + 8 * a);
+        }
+    }
+    __syncthreads();
+    if (warp == EW + M2_PROD_WARPS) {
+        mm_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+    }
+}
+
 // Train sets the tensor-core kernel leaves alone (2^22 rows and more): k_match_all's plain path, see match_kernels.cu.
 cudaError_t orbk_match_all_popc(const uint8_t* q, const int* nq, size_t q_stride, const uint8_t* t, const int* nt, size_t t_stride,
                                 int npairs, int max_nq, int* best_idx, int* best_dist, int* second_dist, size_t out_stride,
@@ -309,11 +660,20 @@ cudaError_t orbk_match_all_popc(const uint8_t* q, const int* nq, size_t q_stride
 cudaError_t orbk_match_mma_init() {
     cudaError_t e = cudaFuncSetAttribute(k_match_mma<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, MM_SMEM);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k_match_mma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, MM_SMEM);
+    e = cudaFuncSetAttribute(k_match_mma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, MM_SMEM);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_match_mma2<0, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, M2_SMEM);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_match_mma2<0, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, M2_SMEM);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_match_mma2<1, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, M2_SMEM);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_match_mma2<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, M2_SMEM);
 }
 
-// kind: 0 = kind::i8, 1 = kind::f8f6f4 (e4m3).  variant: 0 = the documented encoding; other values exist for
-// tools/probes/mma_probe.py only (1: leading / stride byte offsets swapped, 2: descriptor version bits clear).
+// kind: 0 = kind::i8, 1 = kind::f8f6f4 (e4m3).  variant: 0 = the warp-specialised kernel (8 epilogue warps) with the documented
+// encoding; 10 = the first form of the kernel (k_match_mma); 20 = warp-specialised with 16 epilogue warps; 1 / 2 (11 / 12)
+// exist for tools/probes/mma_probe.py only (leading / stride byte offsets swapped, descriptor version bits clear).
 cudaError_t orbk_match_all_mma(const uint8_t* q, const int* nq, size_t q_stride, const uint8_t* t, const int* nt, size_t t_stride,
                                int npairs, int max_nq, int* best_idx, int* best_dist, int* second_dist, size_t out_stride, int kind,
                                int variant, cudaStream_t st) {
@@ -324,10 +684,10 @@ cudaError_t orbk_match_all_mma(const uint8_t* q, const int* nq, size_t q_stride,
     prm.neg_lo = (unsigned)-64;
     prm.neg_hi = (unsigned)(-64 * 65536);
     unsigned lbo = MM_LBO, sbo = MM_SBO;
-    if (variant == 1) std::swap(lbo, sbo);
+    if (variant % 10 == 1) std::swap(lbo, sbo);
     // matrix descriptor: start address >> 4 [0,14), leading byte offset >> 4 [16,30), stride byte offset >> 4 [32,46),
     // descriptor version 1 [46,48), base offset 0, layout type 0 = no swizzle [61,64)
-    prm.desc_base = ((unsigned long long)(lbo >> 4) << 16) | ((unsigned long long)(sbo >> 4) << 32) | (variant == 2 ? 0ull : (1ull << 46));
+    prm.desc_base = ((unsigned long long)(lbo >> 4) << 16) | ((unsigned long long)(sbo >> 4) << 32) | (variant % 10 == 2 ? 0ull : (1ull << 46));
     // instruction descriptor: D format [4,6), A format [7,10), B format [10,13), A / B major [15], [16] = 0 (K-major),
     // N >> 3 [17,23), M >> 4 [24,29)
     const unsigned shape = ((unsigned)(MM_N >> 3) << 17) | ((unsigned)(MM_M >> 4) << 24);
@@ -340,11 +700,24 @@ cudaError_t orbk_match_all_mma(const uint8_t* q, const int* nq, size_t q_stride,
         prm.lut_a = 0x000038b8u;        // e4m3: 0xb8 = -1.0, 0x38 = +1.0
         prm.lut_b = 0x00003800u;
     }
-    dim3 grid((max_nq + MM_M - 1) / MM_M, npairs);
-    if (kind == 0)
-        k_match_mma<0><<<grid, MM_THREADS, MM_SMEM, st>>>(q, nq, q_stride, t, nt, t_stride, best_idx, best_dist, second_dist, out_stride, prm);
-    else
-        k_match_mma<1><<<grid, MM_THREADS, MM_SMEM, st>>>(q, nq, q_stride, t, nt, t_stride, best_idx, best_dist, second_dist, out_stride, prm);
+    if (variant >= 10 && variant < 20) {  // the first form of the kernel (2 CTAs per SM, block barriers): kept as a comparator
+        dim3 grid((max_nq + MM_M - 1) / MM_M, npairs);
+        if (kind == 0)
+            k_match_mma<0><<<grid, MM_THREADS, MM_SMEM, st>>>(q, nq, q_stride, t, nt, t_stride, best_idx, best_dist, second_dist, out_stride, prm);
+        else
+            k_match_mma<1><<<grid, MM_THREADS, MM_SMEM, st>>>(q, nq, q_stride, t, nt, t_stride, best_idx, best_dist, second_dist, out_stride, prm);
+    } else {
+        dim3 grid((max_nq + 2 * MM_M - 1) / (2 * MM_M), npairs);
+        const bool e8 = variant < 20;  // 20: sixteen epilogue warps (two threads per query row): measured slower, kept as a comparator
+        if (kind == 0 && !e8)
+            k_match_mma2<0, 16><<<grid, M2_THREADS(16), M2_SMEM, st>>>(q, nq, q_stride, t, nt, t_stride, best_idx, best_dist, second_dist, out_stride, prm);
+        else if (kind == 0)
+            k_match_mma2<0, 8><<<grid, M2_THREADS(8), M2_SMEM, st>>>(q, nq, q_stride, t, nt, t_stride, best_idx, best_dist, second_dist, out_stride, prm);
+        else if (!e8)
+            k_match_mma2<1, 16><<<grid, M2_THREADS(16), M2_SMEM, st>>>(q, nq, q_stride, t, nt, t_stride, best_idx, best_dist, second_dist, out_stride, prm);
+        else
+            k_match_mma2<1, 8><<<grid, M2_THREADS(8), M2_SMEM, st>>>(q, nq, q_stride, t, nt, t_stride, best_idx, best_dist, second_dist, out_stride, prm);
+    }
     orbk_count_launch(1);
     return cudaGetLastError();
 }

@@ -36,10 +36,12 @@ def main():
     res = {}
     for live, data in (("182", full & mask), ("256", full)):
         q, t = data[:NP].contiguous(), data[1:].contiguous()
-        for impl in ("popc", "mma"):
+        # mma1: the first form of the tensor-core kernel (ORB_B200_MMA_VARIANT=10); mma16: warp-specialised with 16 epilogue warps (20)
+        for impl in ("popc", "mma1", "mma16", "mma"):
             if a.only and impl != a.only:
                 continue
-            os.environ["ORB_B200_MATCH"] = impl
+            os.environ["ORB_B200_MATCH"] = "popc" if impl == "popc" else "mma"
+            os.environ["ORB_B200_MMA_VARIANT"] = {"mma1": "10", "mma16": "20"}.get(impl, "0")
             o = ref if impl == "popc" else out
             for _ in range(2):
                 m.match_all_batch_device(q, nq, t, nq, *o)

@@ -2,7 +2,8 @@
 """Which encodings of the tcgen05 operands does the device accept for k_match_mma?  Runs the brute-force search on
 seeded descriptors with the POPC kernel (ORB_B200_MATCH=popc) and with the tensor-core kernel for each
 (ORB_B200_MMA_KIND, ORB_B200_MMA_VARIANT), every combination in its own process (a faulting launch poisons its context),
-and prints how many rows agree.  Variant 0 / kind i8 is what the library ships.
+and prints how many rows agree.  Variant 0 / kind i8 is what the library ships (the warp-specialised kernel); 10 = the
+first form of the kernel; 1, 2, 11, 12 = deliberately different descriptor encodings.
 
     python tools/probes/mma_probe.py [--kinds i8,f8] [--variants 0,1,2]
 """
@@ -45,7 +46,7 @@ def child():
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--kinds", default="i8,f8")
-    ap.add_argument("--variants", default="0,1,2")
+    ap.add_argument("--variants", default="0,10")
     ap.add_argument("--child", action="store_true")
     a = ap.parse_args()
     if a.child:
