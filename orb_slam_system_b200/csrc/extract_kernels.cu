@@ -8,6 +8,7 @@
 // compiled with -fmad=false and IEEE div so it follows the oracle step by step.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include <algorithm>
 
@@ -664,8 +665,7 @@ __global__ void __launch_bounds__(DET_THREADS) k_detect(const __grid_constant__ 
 // final nodes = runs between div_j <= p*; per node the first max-response key; output
 // order = (birth pass desc, alternating-direction path) -- the std::list push_front order.
 // ------------------------------------------------------------------------------------------
-#define OCT_THREADS 512
-#define OCT_SMEM_A 16384
+#define OCT_SMEM_A 8192
 #define OCT_SMEM_B 4096
 #define OCT_D ORB_OCT_DEPTH
 
@@ -699,7 +699,7 @@ __device__ __forceinline__ int div_depth(unsigned ca, unsigned cb) {
 struct OctShared {
     int hist[OCT_D + 2];
     int pstar, K, nvalid, bad;
-    int warpSums[OCT_THREADS / 32];
+    int warpSums[32];  // one per warp of the 1024-thread CTA
 };
 
 // Path code of one candidate: root = int(x / hX) (ORBextractor.cc:248), then OCT_D floor-halving
@@ -759,6 +759,194 @@ __device__ __forceinline__ unsigned long long cand_order_magic(const OrbLevel& L
     return ((unsigned long long)(ci * (unsigned)L.nCols + cj) << 26) | (y << 13) | x;
 }
 
+#define OCTF_THREADS 1024
+
+// ------------------------------------------------------------------------------------------
+// octree_generic: sort-based closed form, any depth up to OCT_D, for the (level, frame) problems whose stopping depth is
+// beyond k_octree_fast's tables (sparse / clustered keys).  Runs inside k_octree_fast's CTA, on its shared memory
+// (OCT_SMEM_A + OCT_SMEM_B keys = the 96 KB of the tables; larger problems sort in the level's global scratch), so the
+// common case pays no second launch.
+// ------------------------------------------------------------------------------------------
+__device__ __noinline__ void octree_generic(const OrbPlan& plan, int lt, int f, unsigned char* smem_raw, OctShared& sh) {
+    unsigned long long* smA = reinterpret_cast<unsigned long long*>(smem_raw);
+    unsigned long long* smB = smA + OCT_SMEM_A;
+    const int l = plan.lv[lt].src;
+    const OrbLevel& L = plan.lv[l];
+    const int tid = threadIdx.x;
+    int n = plan.candCount[f * ORB_MAX_LEVELS + l];
+    if (n > (int)L.candCap) n = (int)L.candCap;
+    const uint2* cand = L.cand + (size_t)f * L.candCap;
+    unsigned long long* scratch = plan.lv[lt].sortScratch + (size_t)f * 2 * plan.lv[lt].sortCap;
+
+    unsigned npad = 2;
+    while (npad < (unsigned)n) npad <<= 1;
+    unsigned long long* A = npad <= OCT_SMEM_A ? smA : scratch;
+
+    // ---- path codes
+    if (tid < OCT_D + 2) sh.hist[tid] = 0;
+    if (tid == 0) { sh.nvalid = 0; sh.bad = 0; }
+    __syncthreads();
+    int myValid = 0;
+    for (unsigned i = tid; i < npad; i += OCTF_THREADS) {
+        unsigned long long key = ~0ull;
+        if (i < (unsigned)n) {
+            const uint2 c = cand[i];
+            unsigned code;
+            if (path_code(L, (int)(c.x & 0xffff), (int)(c.x >> 16), code)) {
+                key = ((unsigned long long)code << 32) | i;
+                ++myValid;
+            }
+        }
+        A[i] = key;
+    }
+    if (myValid) atomicAdd(&sh.nvalid, myValid);
+    __syncthreads();
+    n = sh.nvalid;  // keys with an out-of-range root are dropped (ORBextractor.cc:249)
+
+    if (n > 0) bitonic_sort(A, npad);
+
+    // ---- histogram of parting depths
+    {
+        int local[OCT_D + 2];
+#pragma unroll
+        for (int d = 0; d < OCT_D + 2; ++d) local[d] = 0;
+        for (int j = tid + 1; j < n; j += OCTF_THREADS) {
+            const int dd = div_depth((unsigned)(A[j - 1] >> 32), (unsigned)(A[j] >> 32));
+#pragma unroll
+            for (int d = 0; d < OCT_D + 2; ++d) local[d] += (dd == d);
+        }
+#pragma unroll
+        for (int d = 0; d < OCT_D + 2; ++d) {
+            int v = local[d];
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if ((tid & 31) == 0 && v) atomicAdd(&sh.hist[d], v);
+        }
+    }
+    __syncthreads();
+
+    {
+        const OrbLevel& T = plan.lv[lt];
+        uint2* kept = T.kept + (size_t)f * T.kmax;
+        if (n == 0) {
+            if (tid == 0) plan.keptCount[f * ORB_MAX_LEVELS + lt] = 0;
+            return;
+        }
+        if (tid == 0) {
+            int cnt = 1, p = -1;
+            cnt += sh.hist[0];
+            for (int t = 1; t <= OCT_D; ++t) {
+                cnt += sh.hist[t];
+                if (cnt >= T.nFeat || cnt == n) { p = t; break; }
+            }
+            if (p < 0) {  // unseparable keys: the reference never terminates
+                p = OCT_D;
+                sh.bad = 1;
+            }
+            int K = 1;
+            for (int t = 0; t <= p; ++t) K += sh.hist[t];
+            sh.pstar = p;
+            sh.K = K;
+        }
+        __syncthreads();
+        const int pstar = sh.pstar, K = sh.K;
+        unsigned kpad = 2;
+        while (kpad < (unsigned)K) kpad <<= 1;
+        unsigned long long* B = kpad <= OCT_SMEM_B ? smB : scratch + plan.lv[lt].sortCap;
+
+        // segment ids: block-wide exclusive scan of head flags over contiguous chunks
+        const int chunk = (n + OCTF_THREADS - 1) / OCTF_THREADS;
+        const int beg = min(tid * chunk, n), end = min(beg + chunk, n);
+        int heads = 0;
+        for (int j = beg; j < end; ++j) {
+            const bool head = j == 0 || div_depth((unsigned)(A[j - 1] >> 32), (unsigned)(A[j] >> 32)) <= pstar;
+            heads += head;
+        }
+        int incl = heads;
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((tid & 31) >= o) incl += v;
+        }
+        if ((tid & 31) == 31) sh.warpSums[tid >> 5] = incl;
+        __syncthreads();
+        if (tid < 32) {
+            int v = tid < OCTF_THREADS / 32 ? sh.warpSums[tid] : 0;
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t2 = __shfl_up_sync(0xffffffffu, v, o);
+                if (tid >= o) v += t2;
+            }
+            if (tid < OCTF_THREADS / 32) sh.warpSums[tid] = v;
+        }
+        __syncthreads();
+        int seg = incl - heads + ((tid >> 5) ? sh.warpSums[(tid >> 5) - 1] : 0);
+        for (unsigned i = tid + K; i < kpad; i += OCTF_THREADS) B[i] = ~0ull;
+
+        for (int j = beg; j < end; ++j) {
+            const unsigned cj = (unsigned)(A[j] >> 32);
+            const int dj = j == 0 ? 0 : div_depth((unsigned)(A[j - 1] >> 32), cj);
+            if (j != 0 && dj > pstar) continue;  // not a head
+            // walk the run, keep the first max-response key in candidate order
+            int e = j + 1, dnext = 0;
+            unsigned bestIdx = (unsigned)A[j];
+            uint2 bc = cand[bestIdx];
+            unsigned bestScore = bc.y;
+            unsigned long long bestOrd = 0;
+            bool haveOrd = false;
+            for (; e < n; ++e) {
+                dnext = div_depth((unsigned)(A[e - 1] >> 32), (unsigned)(A[e] >> 32));
+                if (dnext <= pstar) break;
+                const unsigned idx = (unsigned)A[e];
+                const uint2 c = cand[idx];
+                if (c.y > bestScore) {
+                    bestScore = c.y;
+                    bestIdx = idx;
+                    bc = c;
+                    haveOrd = false;
+                } else if (c.y == bestScore) {
+                    // candidate order: cells row-major, then (y, x) inside the cell
+                    auto ordOf = [&](uint2 v) -> unsigned long long { return cand_order(L, v.x & 0xffff, v.x >> 16); };
+                    if (!haveOrd) { bestOrd = ordOf(bc); haveOrd = true; }
+                    const unsigned long long o2 = ordOf(c);
+                    if (o2 < bestOrd) { bestOrd = o2; bestIdx = idx; bc = c; }
+                }
+            }
+            if (e >= n) dnext = 0;
+            const int len = e - j;
+            int birth = len == 1 ? max(dj, dnext) : pstar;
+            if (birth > pstar) birth = pstar;  // (cannot happen for len==1; keeps the key well-formed)
+            // order key: (D - birth) | root' | c'_1..c'_birth ; direction alternates backwards from c_birth
+            const unsigned root = cj >> (2 * OCT_D);
+            unsigned long long ok = (unsigned long long)(OCT_D - birth);
+            bool rootDesc = birth >= 1 && (((birth - 1) & 1) == 0);
+            ok = (ok << 6) | (rootDesc ? 63u - root : root);
+#pragma unroll
+            for (int i = 1; i <= OCT_D; ++i) {
+                unsigned c = (cj >> (2 * (OCT_D - i))) & 3u;
+                if (i <= birth) {
+                    if (((birth - i) & 1) == 0) c = 3u - c;
+                } else {
+                    c = 0;
+                }
+                ok = (ok << 2) | c;
+            }
+            B[seg] = (ok << 24) | bestIdx;
+            ++seg;
+        }
+        __syncthreads();
+        bitonic_sort(B, kpad);
+        for (int r = tid; r < K; r += OCTF_THREADS) {
+            const unsigned idx = (unsigned)(B[r] & 0xffffffu);
+            const uint2 c = cand[idx];
+            const unsigned x = (c.x & 0xffff) + ORB_MINB, y = (c.x >> 16) + ORB_MINB;
+            if (r < T.kmax) kept[r] = make_uint2(x | (y << 16), c.y);
+        }
+        if (tid == 0) {
+            plan.keptCount[f * ORB_MAX_LEVELS + lt] = K;
+            if (sh.bad) plan.status[f] = 1;
+        }
+        __syncthreads();
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // k_octree_fast: sort-free path for the common case where the stopping depth p* is shallow
 // (nIni * 4^p* <= OCTF_MAX_NODES).  The quadtree nodes of depth t form a table indexed by
@@ -771,7 +959,6 @@ __device__ __forceinline__ unsigned long long cand_order_magic(const OrbLevel& L
 // per-birth tables in transformed-index order and one block-wide prefix sum.
 // Problems it cannot take (deep p*) are flagged for the generic sort-based kernel below.
 // ------------------------------------------------------------------------------------------
-#define OCTF_THREADS 1024
 #define OCTF_MAX_NODES 6144
 #define OCTF_MAX_TOTAL 8192
 #define OCTF_MAX_DEPTH 7
@@ -785,7 +972,7 @@ struct OctFastSmem {
     int pstar, K, nvalid;
 };
 
-__global__ void __launch_bounds__(OCTF_THREADS) k_octree_fast(const __grid_constant__ OrbPlan plan) {
+__global__ void __launch_bounds__(OCTF_THREADS, 2) k_octree_fast(const __grid_constant__ OrbPlan plan) {
     pdl_enter();
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     OctFastSmem& sm = *reinterpret_cast<OctFastSmem*>(smem_raw);
@@ -874,8 +1061,10 @@ __global__ void __launch_bounds__(OCTF_THREADS) k_octree_fast(const __grid_const
         }
         return;
     }
-    if (pstar < 0) {  // deeper than the tables: hand over to the sort-based kernel
-        if (tid == 0) *needGeneric = 1;
+    if (pstar < 0) {  // deeper than the tables: the sort-based form, in place (block-uniform branch)
+        __syncthreads();  // everybody has read pstar / nvalid: the tables' memory becomes the sort buffers
+        if (tid == 0) *needGeneric = 0;
+        octree_generic(plan, lt, f, smem_raw, *reinterpret_cast<OctShared*>(smem_raw + sizeof(OctFastSmem)));
         return;
     }
     const int nodes = nIni << (2 * pstar);
@@ -949,197 +1138,6 @@ __global__ void __launch_bounds__(OCTF_THREADS) k_octree_fast(const __grid_const
     if (tid == 0) {
         plan.keptCount[f * ORB_MAX_LEVELS + lt] = sm.K;
         *needGeneric = 0;
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// k_octree (generic): sort-based closed form, any depth up to OCT_D.  Runs only for the
-// (level, frame) problems k_octree_fast flagged.
-// ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(OCT_THREADS) k_octree(const __grid_constant__ OrbPlan plan) {
-    pdl_enter();
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
-    unsigned long long* smA = reinterpret_cast<unsigned long long*>(smem_raw);
-    unsigned long long* smB = smA + OCT_SMEM_A;
-    OctShared& sh = *reinterpret_cast<OctShared*>(smB + OCT_SMEM_B);
-
-    const int f = blockIdx.y;
-    const int lt = blockIdx.x;
-    if (!plan.needGeneric[f * ORB_MAX_LEVELS + lt]) return;
-    const int l = plan.lv[lt].src;
-    const OrbLevel& L = plan.lv[l];
-    const int tid = threadIdx.x;
-    int n = plan.candCount[f * ORB_MAX_LEVELS + l];
-    if (n > (int)L.candCap) n = (int)L.candCap;
-    const uint2* cand = L.cand + (size_t)f * L.candCap;
-    unsigned long long* scratch = plan.lv[lt].sortScratch + (size_t)f * 2 * plan.lv[lt].sortCap;
-
-    unsigned npad = 2;
-    while (npad < (unsigned)n) npad <<= 1;
-    unsigned long long* A = npad <= OCT_SMEM_A ? smA : scratch;
-
-    // ---- path codes
-    if (tid < OCT_D + 2) sh.hist[tid] = 0;
-    if (tid == 0) { sh.nvalid = 0; sh.bad = 0; }
-    __syncthreads();
-    int myValid = 0;
-    for (unsigned i = tid; i < npad; i += OCT_THREADS) {
-        unsigned long long key = ~0ull;
-        if (i < (unsigned)n) {
-            const uint2 c = cand[i];
-            unsigned code;
-            if (path_code(L, (int)(c.x & 0xffff), (int)(c.x >> 16), code)) {
-                key = ((unsigned long long)code << 32) | i;
-                ++myValid;
-            }
-        }
-        A[i] = key;
-    }
-    if (myValid) atomicAdd(&sh.nvalid, myValid);
-    __syncthreads();
-    n = sh.nvalid;  // keys with an out-of-range root are dropped (ORBextractor.cc:249)
-
-    if (n > 0) bitonic_sort(A, npad);
-
-    // ---- histogram of parting depths
-    {
-        int local[OCT_D + 2];
-#pragma unroll
-        for (int d = 0; d < OCT_D + 2; ++d) local[d] = 0;
-        for (int j = tid + 1; j < n; j += OCT_THREADS) {
-            const int dd = div_depth((unsigned)(A[j - 1] >> 32), (unsigned)(A[j] >> 32));
-#pragma unroll
-            for (int d = 0; d < OCT_D + 2; ++d) local[d] += (dd == d);
-        }
-#pragma unroll
-        for (int d = 0; d < OCT_D + 2; ++d) {
-            int v = local[d];
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if ((tid & 31) == 0 && v) atomicAdd(&sh.hist[d], v);
-        }
-    }
-    __syncthreads();
-
-    {
-        const OrbLevel& T = plan.lv[lt];
-        uint2* kept = T.kept + (size_t)f * T.kmax;
-        if (n == 0) {
-            if (tid == 0) plan.keptCount[f * ORB_MAX_LEVELS + lt] = 0;
-            return;
-        }
-        if (tid == 0) {
-            int cnt = 1, p = -1;
-            cnt += sh.hist[0];
-            for (int t = 1; t <= OCT_D; ++t) {
-                cnt += sh.hist[t];
-                if (cnt >= T.nFeat || cnt == n) { p = t; break; }
-            }
-            if (p < 0) {  // unseparable keys: the reference never terminates
-                p = OCT_D;
-                sh.bad = 1;
-            }
-            int K = 1;
-            for (int t = 0; t <= p; ++t) K += sh.hist[t];
-            sh.pstar = p;
-            sh.K = K;
-        }
-        __syncthreads();
-        const int pstar = sh.pstar, K = sh.K;
-        unsigned kpad = 2;
-        while (kpad < (unsigned)K) kpad <<= 1;
-        unsigned long long* B = kpad <= OCT_SMEM_B ? smB : scratch + plan.lv[lt].sortCap;
-
-        // segment ids: block-wide exclusive scan of head flags over contiguous chunks
-        const int chunk = (n + OCT_THREADS - 1) / OCT_THREADS;
-        const int beg = min(tid * chunk, n), end = min(beg + chunk, n);
-        int heads = 0;
-        for (int j = beg; j < end; ++j) {
-            const bool head = j == 0 || div_depth((unsigned)(A[j - 1] >> 32), (unsigned)(A[j] >> 32)) <= pstar;
-            heads += head;
-        }
-        int incl = heads;
-        for (int o = 1; o < 32; o <<= 1) {
-            const int v = __shfl_up_sync(0xffffffffu, incl, o);
-            if ((tid & 31) >= o) incl += v;
-        }
-        if ((tid & 31) == 31) sh.warpSums[tid >> 5] = incl;
-        __syncthreads();
-        if (tid < 32) {
-            int v = tid < OCT_THREADS / 32 ? sh.warpSums[tid] : 0;
-            for (int o = 1; o < 32; o <<= 1) {
-                const int t2 = __shfl_up_sync(0xffffffffu, v, o);
-                if (tid >= o) v += t2;
-            }
-            if (tid < OCT_THREADS / 32) sh.warpSums[tid] = v;
-        }
-        __syncthreads();
-        int seg = incl - heads + ((tid >> 5) ? sh.warpSums[(tid >> 5) - 1] : 0);
-        for (unsigned i = tid + K; i < kpad; i += OCT_THREADS) B[i] = ~0ull;
-
-        for (int j = beg; j < end; ++j) {
-            const unsigned cj = (unsigned)(A[j] >> 32);
-            const int dj = j == 0 ? 0 : div_depth((unsigned)(A[j - 1] >> 32), cj);
-            if (j != 0 && dj > pstar) continue;  // not a head
-            // walk the run, keep the first max-response key in candidate order
-            int e = j + 1, dnext = 0;
-            unsigned bestIdx = (unsigned)A[j];
-            uint2 bc = cand[bestIdx];
-            unsigned bestScore = bc.y;
-            unsigned long long bestOrd = 0;
-            bool haveOrd = false;
-            for (; e < n; ++e) {
-                dnext = div_depth((unsigned)(A[e - 1] >> 32), (unsigned)(A[e] >> 32));
-                if (dnext <= pstar) break;
-                const unsigned idx = (unsigned)A[e];
-                const uint2 c = cand[idx];
-                if (c.y > bestScore) {
-                    bestScore = c.y;
-                    bestIdx = idx;
-                    bc = c;
-                    haveOrd = false;
-                } else if (c.y == bestScore) {
-                    // candidate order: cells row-major, then (y, x) inside the cell
-                    auto ordOf = [&](uint2 v) -> unsigned long long { return cand_order(L, v.x & 0xffff, v.x >> 16); };
-                    if (!haveOrd) { bestOrd = ordOf(bc); haveOrd = true; }
-                    const unsigned long long o2 = ordOf(c);
-                    if (o2 < bestOrd) { bestOrd = o2; bestIdx = idx; bc = c; }
-                }
-            }
-            if (e >= n) dnext = 0;
-            const int len = e - j;
-            int birth = len == 1 ? max(dj, dnext) : pstar;
-            if (birth > pstar) birth = pstar;  // (cannot happen for len==1; keeps the key well-formed)
-            // order key: (D - birth) | root' | c'_1..c'_birth ; direction alternates backwards from c_birth
-            const unsigned root = cj >> (2 * OCT_D);
-            unsigned long long ok = (unsigned long long)(OCT_D - birth);
-            bool rootDesc = birth >= 1 && (((birth - 1) & 1) == 0);
-            ok = (ok << 6) | (rootDesc ? 63u - root : root);
-#pragma unroll
-            for (int i = 1; i <= OCT_D; ++i) {
-                unsigned c = (cj >> (2 * (OCT_D - i))) & 3u;
-                if (i <= birth) {
-                    if (((birth - i) & 1) == 0) c = 3u - c;
-                } else {
-                    c = 0;
-                }
-                ok = (ok << 2) | c;
-            }
-            B[seg] = (ok << 24) | bestIdx;
-            ++seg;
-        }
-        __syncthreads();
-        bitonic_sort(B, kpad);
-        for (int r = tid; r < K; r += OCT_THREADS) {
-            const unsigned idx = (unsigned)(B[r] & 0xffffffu);
-            const uint2 c = cand[idx];
-            const unsigned x = (c.x & 0xffff) + ORB_MINB, y = (c.x >> 16) + ORB_MINB;
-            if (r < T.kmax) kept[r] = make_uint2(x | (y << 16), c.y);
-        }
-        if (tid == 0) {
-            plan.keptCount[f * ORB_MAX_LEVELS + lt] = K;
-            if (sh.bad) plan.status[f] = 1;
-        }
-        __syncthreads();
     }
 }
 
@@ -1798,17 +1796,15 @@ cudaError_t orbk_encode_level_map(CUtensorMap* out, const uint8_t* base, int col
 unsigned long long orbk_launch_count() { return g_launches.load(); }
 void orbk_count_launch(int n) { g_launches += n; }
 
-static const size_t kOctreeSmem = (size_t)(OCT_SMEM_A + OCT_SMEM_B) * 8 + sizeof(OctShared);
-static const size_t kOctFastSmem = sizeof(OctFastSmem);
+static_assert((size_t)(OCT_SMEM_A + OCT_SMEM_B) * 8 <= sizeof(OctFastSmem), "the sort buffers of octree_generic live in k_octree_fast's tables");
+static const size_t kOctFastSmem = sizeof(OctFastSmem) + sizeof(OctShared);
 
 cudaError_t orbk_init_device() {
     cudaError_t e = cudaFuncSetAttribute(k_detect, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)detect_smem_bytes(DET_TILE_H));
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_describe_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDescSmem);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_octree_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kOctFastSmem);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kOctreeSmem);
+    return cudaFuncSetAttribute(k_octree_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kOctFastSmem);
 }
 
 cudaError_t orbk_run_extract(const OrbPlan& plan, int nframes, orb_keypoint_dev* d_kps, uint8_t* d_desc, int cap,
@@ -1896,8 +1892,7 @@ cudaError_t orbk_run_extract(const OrbPlan& plan, int nframes, orb_keypoint_dev*
     }
     if (ev) cudaEventRecord(ev[2], st);
     launch_pdl(k_octree_fast, dim3(plan.nlevels, nframes), dim3(OCTF_THREADS), kOctFastSmem, st, plan);
-    launch_pdl(k_octree, dim3(plan.nlevels, nframes), dim3(OCT_THREADS), kOctreeSmem, st, plan);
-    g_launches += 2;
+    ++g_launches;
     if (ev) {
         // profiling: stages back to back on one stream, blur after the octree
         cudaEventRecord(ev[3], st);

@@ -504,14 +504,21 @@ extern "C" int orb_extractor_create(const orb_params* params, int max_rows, int 
     h->device = device;
     h->max_batch = max_batch;
     memset(&h->plan, 0, sizeof h->plan);
-    cudaError_t ce = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
-    if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking);
+    // The second stream of every lane (pyramid chain + blur: small dependent launches) gets the highest stream priority, so
+    // its blocks are scheduled ahead of the queued blocks of the other lane's large kernels: 99.1 k -> 99.7 k frames/s.
+    // ORB_B200_PRIO=0 switches it off, 2 gives the priority to the first stream instead (96.9 k).
+    int prioLo = 0, prioHi = 0;
+    cudaDeviceGetStreamPriorityRange(&prioLo, &prioHi);
+    const int prioMode = getenv("ORB_B200_PRIO") ? atoi(getenv("ORB_B200_PRIO")) : 1;
+    const int prio2 = prioMode == 1 ? prioHi : prioLo, prio1 = prioMode == 2 ? prioHi : prioLo;
+    cudaError_t ce = cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, prio1);
+    if (ce == cudaSuccess) ce = cudaStreamCreateWithPriority(&h->stream2, cudaStreamNonBlocking, prio2);
     if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&h->evFork, cudaEventDisableTiming);
     if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&h->evJoin, cudaEventDisableTiming);
     if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&h->evPyr, cudaEventDisableTiming);
     for (int i = 1; i < orb_extractor::MAX_LANES && ce == cudaSuccess; ++i) {
-        ce = cudaStreamCreateWithFlags(&h->laneSt[i], cudaStreamNonBlocking);
-        if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&h->laneSt2[i], cudaStreamNonBlocking);
+        ce = cudaStreamCreateWithPriority(&h->laneSt[i], cudaStreamNonBlocking, prio1);
+        if (ce == cudaSuccess) ce = cudaStreamCreateWithPriority(&h->laneSt2[i], cudaStreamNonBlocking, prio2);
         if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&h->laneFork[i], cudaEventDisableTiming);
         if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&h->laneJoin[i], cudaEventDisableTiming);
         if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&h->laneMerge[i], cudaEventDisableTiming);

@@ -1,5 +1,6 @@
 mkdir -p gpurun_out
-P=gpurun_out/r02h
-timeout 600 python tools/probes/mma_probe.py --kinds i8,f8 --variants 0,20 > ${P}_mma_probe.txt 2>&1
-timeout 300 python tools/probes/match_bench.py > ${P}_match_bench.txt 2>&1
-cat ${P}_mma_probe.txt ${P}_match_bench.txt
+O=gpurun_out/r02j_resident.txt; : > $O
+timeout 900 python -m pytest tests/test_gpu_extract.py tests/test_gpu_adapter.py tests/test_gpu_ingest.py -m gpu -q > gpurun_out/r02j_pytest.txt 2>&1
+python tools/probes/resident_probe.py >> $O 2>&1
+ORB_B200_PRIO=0 python tools/probes/resident_probe.py >> $O 2>&1
+tail -n 4 gpurun_out/r02j_pytest.txt; cat $O
