@@ -92,6 +92,65 @@ int refm_compute_stereo_matches(const OKP* kl, const uint8_t* dl, int nl, const 
     return 0;
 }
 
+#ifdef ADAPTER_FRAME
+// The adapter arm (oracle/Makefile adapterframe): the reference's stereo constructor, compiled unmodified, with
+// Frame::ComputeStereoMatches supplied by orb_slam_system_b200/adapter/Frame_stereo_b200.cc (the reference's own definition
+// is weakened in the object file).  Two C-ABI extractors extract the two images on the GPU -- their pyramids stay on the
+// device --, the stub extractors hand the resulting keypoints / descriptors to the constructor and carry the handles.
+// Returns the number of left keypoints (<= cap) or a negative error; kl_out / dl_out receive them.
+}  // extern "C"
+#include "orb_b200.h"
+extern "C" {
+int adpf_stereo_frame(const uint8_t* imgL, const uint8_t* imgR, int rows, int cols, int nfeatures, float scaleFactor, int nlevels,
+                      int iniTh, int minTh, float bf, float fx, float* uRight, float* depth, OKP* kl_out, uint8_t* dl_out, int cap) {
+    orb_params prm = {nfeatures, scaleFactor, nlevels, iniTh, minTh};
+    orb_extractor *gl = nullptr, *gr = nullptr;
+    if (orb_extractor_create(&prm, rows, cols, 1, 0, &gl) != ORB_OK || orb_extractor_create(&prm, rows, cols, 1, 0, &gr) != ORB_OK) return -4;
+    int bound = 0;
+    orb_extractor_keypoint_bound(gl, rows, cols, &bound);
+    std::vector<orb_keypoint> kl(bound), kr(bound);
+    std::vector<uint8_t> dl((size_t)bound * 32), dr((size_t)bound * 32);
+    int nl = 0, nr = 0, rc = -1;
+    if (orb_extract(gl, imgL, rows, cols, cols, kl.data(), dl.data(), bound, &nl) == ORB_OK &&
+        orb_extract(gr, imgR, rows, cols, cols, kr.data(), dr.data(), bound, &nr) == ORB_OK && nl <= cap) {
+        std::vector<float> scale(nlevels);
+        orb_extractor_tables(gl, scale.data(), nullptr, nullptr, nullptr, nullptr);
+        ORBextractor exL, exR;
+        static_assert(sizeof(OKP) == sizeof(orb_keypoint), "keypoint layouts");
+        load(exL, reinterpret_cast<const OKP*>(kl.data()), dl.data(), nl, scale.data(), nlevels);
+        load(exR, reinterpret_cast<const OKP*>(kr.data()), dr.data(), nr, scale.data(), nlevels);
+        exL.gpu = gl;
+        exR.gpu = gr;
+        cv::Mat im = image_mat(imgL, rows, cols, cols);
+        cv::Mat K = cv::Mat::eye(3, 3, CV_32F);
+        K.at<float>(0, 0) = fx;
+        K.at<float>(1, 1) = fx;
+        K.at<float>(0, 2) = cols * 0.5f;
+        K.at<float>(1, 2) = rows * 0.5f;
+        cv::Mat dist = cv::Mat::zeros(4, 1, CV_32F);
+        ORBVocabulary voc;
+        Frame::mbInitialComputations = true;
+        FrameBox box;
+        memset(box.raw, 0, sizeof box.raw);
+        try {
+            box.f = new (box.raw) Frame(im, im, 0.0, &exL, &exR, &voc, K, dist, bf, 40.0f);
+            for (int i = 0; i < nl; ++i) {
+                uRight[i] = box.f->mvuRight[i];
+                depth[i] = box.f->mvDepth[i];
+            }
+            memcpy(kl_out, kl.data(), (size_t)nl * sizeof(OKP));
+            memcpy(dl_out, dl.data(), (size_t)nl * 32);
+            rc = nl;
+        } catch (const std::exception&) {
+            rc = -2;
+        }
+    }
+    orb_extractor_destroy(gl);
+    orb_extractor_destroy(gr);
+    return rc;
+}
+#endif
+
 // Frame::AssignFeaturesToGrid + Frame::GetFeaturesInArea of the reference on a frame of `cols` x `rows` pixels with the given
 // (undistorted = raw) keypoints; CSR result like orc_features_in_area.  Returns the total number of candidates.
 int refm_frame_features_in_area(const OKP* keys, int n, int rows, int cols, int nq, const float* x, const float* y, const float* r,

@@ -11,9 +11,15 @@
 #include "Thirdparty/DBoW2/DBoW2/BowVector.h"
 #include "orbslam_objects.h"
 
+struct orb_extractor;  // include/orb_b200.h (adapter arm only)
+
 namespace ORB_SLAM2 {
 class ORBextractor {
 public:
+    // adapter arm (oracle/Makefile adapterframe): the C-ABI extractor whose last call left this image's pyramid on the
+    // device, what adapter/ORBextractor.h's handle() returns in a real build
+    orb_extractor* gpu = nullptr;
+    orb_extractor* handle() const { return gpu; }
     std::vector<cv::KeyPoint> keys;
     cv::Mat desc;
     std::vector<float> scale, invScale, sigma2, invSigma2;

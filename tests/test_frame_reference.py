@@ -15,6 +15,7 @@ from search_cases import make_frame, projected_queries
 
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "reference_frame.json")
 HAVE_REF = oracle.ref_frame_lib() is not None
+ADAPTER_FRAME = os.path.join(os.path.dirname(oracle.__file__), "_ref", "libadapter_frame.so")
 needs_ref = pytest.mark.skipif(not HAVE_REF, reason="oracle/_ref/libref_frame.so needs /root/reference to build")
 
 
@@ -28,6 +29,20 @@ def digest(*arrays):
 def case_stereo(impl, rows, cols, nf, bf, fx, frame):
     il = oracle.synth_frame(rows, cols, frame=frame)
     ir = oracle.synth_frame(rows, cols, frame=frame, right=1)
+    if impl == "adapter":
+        # the reference's own stereo Frame constructor (src/Frame.cc:41-97, compiled unmodified) with Frame::ComputeStereoMatches
+        # supplied by orb_slam_system_b200/adapter/Frame_stereo_b200.cc (oracle/Makefile adapterframe)
+        import ctypes as C
+        L = C.CDLL(ADAPTER_FRAME)
+        cap = 16 * nf
+        ur = np.zeros(cap, np.float32)
+        dep = np.zeros(cap, np.float32)
+        kl = np.zeros(cap, oracle.KP_DTYPE)
+        dl = np.zeros((cap, 32), np.uint8)
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        n = L.adpf_stereo_frame(p(il), p(ir), rows, cols, nf, C.c_float(1.2), 8, 20, 7, C.c_float(bf), C.c_float(fx), p(ur), p(dep), p(kl), p(dl), cap)
+        assert n >= 0, n
+        return int((ur[:n] >= 0).sum()), ur[:n].copy(), dep[:n].copy()
     if impl == "gpu":
         from orb_slam_system_b200 import ORBextractor, ORBmatcher
         exl, exr = ORBextractor(nf, 1.2, 8, 20, 7), ORBextractor(nf, 1.2, 8, 20, 7)
@@ -112,6 +127,22 @@ def test_gpu_matches_committed_reference_digests(name):
     g = CASES[name]("gpu")
     assert gold[name]["count"] == g[0], name
     assert gold[name]["sha256_24"] == digest(*g[1:]), name
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["stereo_euroc", "stereo_kitti"])
+def test_adapter_frame_stereo_matches_committed_reference_digests(name):
+    """Frame::ComputeStereoMatches through the drop-in member function (adapter/Frame_stereo_b200.cc) called by the reference's
+    own stereo Frame constructor: mvuRight / mvDepth against the digests of the compiled reference."""
+    if not os.path.exists(ADAPTER_FRAME):
+        pytest.skip("oracle/_ref/libadapter_frame.so not built (oracle/Makefile adapterframe)")
+    from orb_slam_system_b200 import kernel_launch_count
+    gold = json.load(open(GOLDEN))
+    before = kernel_launch_count()
+    a = CASES[name]("adapter")
+    assert kernel_launch_count() > before  # the member function ran on the GPU, not the reference's body
+    assert gold[name]["count"] == a[0], name
+    assert gold[name]["sha256_24"] == digest(*a[1:]), name
 
 
 if __name__ == "__main__":  # regenerate the golden digests from the compiled reference
