@@ -247,6 +247,15 @@ int orb_compute_stereo_matches(orb_matcher* m, orb_extractor* ex_left, int frame
                                const orb_keypoint* kps_right, const uint8_t* desc_right, int n_right, float bf,
                                float fx, float* u_right, float* depth);
 
+/* The same with Frame::mb given as the reference's function reads it (minZ = mb, maxD = mbf / minZ, src/Frame.cc:476-478)
+ * instead of derived from fx: inside the stereo Frame constructor ComputeStereoMatches runs BEFORE the static fx and
+ * `mb = mbf / fx` are assigned (:70 vs :86-94), so the drop-in member function (adapter/Frame_stereo_b200.cc) must take
+ * mb from the object exactly as the reference does. */
+int orb_compute_stereo_matches_mb(orb_matcher* m, orb_extractor* ex_left, int frame_left, orb_extractor* ex_right,
+                                  int frame_right, const orb_keypoint* kps_left, const uint8_t* desc_left, int n_left,
+                                  const orb_keypoint* kps_right, const uint8_t* desc_right, int n_right, float bf,
+                                  float mb, float* u_right, float* depth);
+
 int orb_matcher_sync(orb_matcher* m);
 void* orb_matcher_stream(orb_matcher* m);
 

@@ -132,6 +132,8 @@ int adpf_stereo_frame(const uint8_t* imgL, const uint8_t* imgR, int rows, int co
         Frame::mbInitialComputations = true;
         FrameBox box;
         memset(box.raw, 0, sizeof box.raw);
+        const float mb = bf / fx;  // as in refm_compute_stereo_matches: the storage's mb holds the running system's value
+        memcpy(box.raw + offsetof(Frame, mb), &mb, sizeof mb);
         try {
             box.f = new (box.raw) Frame(im, im, 0.0, &exL, &exR, &voc, K, dist, bf, 40.0f);
             for (int i = 0; i < nl; ++i) {

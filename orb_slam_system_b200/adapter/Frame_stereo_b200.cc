@@ -15,9 +15,11 @@ namespace ORB_SLAM2 {
 void Frame::ComputeStereoMatches() {
     // one GPU matcher handle per calling thread (the tracking thread builds the frames)
     thread_local orb_b200::Matcher gpu(getenv("ORB_B200_DEVICE") ? atoi(getenv("ORB_B200_DEVICE")) : 0);
-    // mvuRight / mvDepth = N x -1.0f, then the matches (:448-449, :600-601, :614-617); mb = mbf / fx as the running system has it
-    gpu.ComputeStereoMatches(mpORBextractorLeft->handle(), mpORBextractorRight->handle(), mvKeys, mDescriptors, mvKeysRight,
-                             mDescriptorsRight, mbf, fx, mvuRight, mvDepth);
+    // mvuRight / mvDepth = N x -1.0f, then the matches (:448-449, :600-601, :614-617).  The disparity range comes from the
+    // member `mb` exactly as in the reference (minZ = mb, :476-478): the constructor calls this function before it assigns the
+    // static fx and `mb = mbf / fx` (:70 vs :86-94), so deriving mb from fx here would read a value that is not set yet.
+    gpu.ComputeStereoMatchesMb(mpORBextractorLeft->handle(), mpORBextractorRight->handle(), mvKeys, mDescriptors, mvKeysRight,
+                               mDescriptorsRight, mbf, mb, mvuRight, mvDepth);
 }
 
 }  // namespace ORB_SLAM2

@@ -194,6 +194,18 @@ public:
                                          (int)mvKeysRight.size(), mbf, fx, mvuRight.data(), mvDepth.data()));
     }
 
+    // The same with Frame::mb as the reference's function reads it (see orb_compute_stereo_matches_mb).
+    void ComputeStereoMatchesMb(orb_extractor* left, orb_extractor* right, const std::vector<cv::KeyPoint>& mvKeys, const cv::Mat& mDescriptors,
+                                const std::vector<cv::KeyPoint>& mvKeysRight, const cv::Mat& mDescriptorsRight, float mbf, float mb,
+                                std::vector<float>& mvuRight, std::vector<float>& mvDepth) {
+        mvuRight.assign(mvKeys.size(), -1.0f);
+        mvDepth.assign(mvKeys.size(), -1.0f);
+        check(orb_compute_stereo_matches_mb(m_, left, 0, right, 0, reinterpret_cast<const orb_keypoint*>(mvKeys.data()),
+                                            mDescriptors.ptr<uint8_t>(0), (int)mvKeys.size(),
+                                            reinterpret_cast<const orb_keypoint*>(mvKeysRight.data()), mDescriptorsRight.ptr<uint8_t>(0),
+                                            (int)mvKeysRight.size(), mbf, mb, mvuRight.data(), mvDepth.data()));
+    }
+
 private:
     static Scan make(int n) {
         Scan s;

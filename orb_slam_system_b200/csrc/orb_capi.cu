@@ -1332,6 +1332,13 @@ extern "C" int orb_stereo_match(orb_matcher* m, const orb_keypoint* kl, const ui
 extern "C" int orb_compute_stereo_matches(orb_matcher* m, orb_extractor* ex_left, int frame_left, orb_extractor* ex_right,
                                           int frame_right, const orb_keypoint* kl, const uint8_t* dl, int nl, const orb_keypoint* kr,
                                           const uint8_t* dr, int nr, float bf, float fx, float* u_right, float* depth) {
+    // mb = mbf / fx (src/Frame.cc:94, :215)
+    return orb_compute_stereo_matches_mb(m, ex_left, frame_left, ex_right, frame_right, kl, dl, nl, kr, dr, nr, bf, bf / fx, u_right, depth);
+}
+
+extern "C" int orb_compute_stereo_matches_mb(orb_matcher* m, orb_extractor* ex_left, int frame_left, orb_extractor* ex_right,
+                                             int frame_right, const orb_keypoint* kl, const uint8_t* dl, int nl, const orb_keypoint* kr,
+                                             const uint8_t* dr, int nr, float bf, float mb, float* u_right, float* depth) {
     if (!m || !ex_left || !ex_right || !u_right || !depth) return fail(ORB_ERR_INVALID, "null argument");
     if (nl < 0 || nr < 0) return fail(ORB_ERR_INVALID, "bad count");
     if (ex_left->plan.rows == 0 || ex_right->plan.rows == 0) return fail(ORB_ERR_INVALID, "no frame extracted yet");
@@ -1358,8 +1365,7 @@ extern "C" int orb_compute_stereo_matches(orb_matcher* m, orb_extractor* ex_left
     for (int i = 0; i < nl; ++i)
         if (!(kl[i].y >= 0.0f && kl[i].y < (float)rows)) return fail(ORB_ERR_SHAPE, "left keypoint %d: row outside the image", i);
     CUDA_TRY(cudaSetDevice(m->device));
-    const float mb = bf / fx;    // src/Frame.cc:215
-    const float maxD = bf / mb;  // :476-478
+    const float maxD = bf / mb;  // minZ = mb, maxD = mbf / minZ (:476-478)
     void *dkl, *ddl, *dkr, *ddr, *dsc, *dri, *dout, *dres;
     int rc;
     if ((rc = scratch(m, 0, (size_t)nl * 32 + 32, &ddl)) || (rc = scratch(m, 1, (size_t)nr * 32 + 32, &ddr)) ||

@@ -1,6 +1,3 @@
 mkdir -p gpurun_out
-O=gpurun_out/r02j_resident.txt; : > $O
-timeout 900 python -m pytest tests/test_gpu_extract.py tests/test_gpu_adapter.py tests/test_gpu_ingest.py -m gpu -q > gpurun_out/r02j_pytest.txt 2>&1
-python tools/probes/resident_probe.py >> $O 2>&1
-ORB_B200_PRIO=0 python tools/probes/resident_probe.py >> $O 2>&1
-tail -n 4 gpurun_out/r02j_pytest.txt; cat $O
+timeout 900 python -m pytest tests/test_frame_reference.py tests/test_search_reference.py -m gpu -q > gpurun_out/r02k_pytest.txt 2>&1
+tail -n 15 gpurun_out/r02k_pytest.txt
