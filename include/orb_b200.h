@@ -256,6 +256,18 @@ int orb_compute_stereo_matches_mb(orb_matcher* m, orb_extractor* ex_left, int fr
                                   const orb_keypoint* kps_right, const uint8_t* desc_right, int n_right, float bf,
                                   float mb, float* u_right, float* depth);
 
+/* Frame::ComputeStereoMatches for every stereo pair of ONE extractor batch (BASELINE config 2 / 3 batched): pair p = frames
+ * (2p, 2p + 1) of ex's last call (left = even, right = odd frame), keypoints / descriptors / counts in the batch layout of
+ * orb_extract_batch ([frame][cap] rows).  u_right / depth: [npairs][cap] floats (Frame::mvuRight / mvDepth of pair p in row p).
+ * on_device != 0: every pointer is a device pointer (the outputs of orb_extract_batch_device, untouched), asynchronous on the
+ * matcher's stream; status (optional, npairs ints) receives a non-zero flag word for a pair on which the reference faults
+ * (its rows are then all -1).  on_device == 0: host buffers, synchronous; status (optional) receives ORB_OK / ORB_ERR_SHAPE /
+ * ORB_ERR_INVALID per pair, without it the first refused pair is the call's error.  The four steps (row-band table, Hamming
+ * search, SAD refinement, median cut) run as four launches over all pairs. */
+int orb_compute_stereo_matches_batch(orb_matcher* m, orb_extractor* ex, int npairs, const orb_keypoint* kps, const uint8_t* desc,
+                                     int cap, const int32_t* counts, float bf, float fx, float* u_right, float* depth,
+                                     int32_t* status, int on_device);
+
 int orb_matcher_sync(orb_matcher* m);
 void* orb_matcher_stream(orb_matcher* m);
 

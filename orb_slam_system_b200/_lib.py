@@ -76,7 +76,7 @@ EXPORTS = [
     "orb_extractor_set_ingest", "orb_ingest_extract_batch", "orb_ingest_extract_batch_submit", "orb_ingest_extract_batch_device",
     "orb_extractor_level_stats", "orb_extractor_set_profiling", "orb_extractor_stage_times",
     "orb_stage_name", "orb_matcher_create", "orb_matcher_destroy", "orb_match_all",
-    "orb_match_all_batch", "orb_match_csr", "orb_distances_csr", "orb_stereo_match", "orb_compute_stereo_matches", "orb_compute_stereo_matches_mb", "orb_matcher_sync",
+    "orb_match_all_batch", "orb_match_csr", "orb_distances_csr", "orb_stereo_match", "orb_compute_stereo_matches", "orb_compute_stereo_matches_mb", "orb_compute_stereo_matches_batch", "orb_matcher_sync",
     "orb_matcher_stream", "orb_window_search", "orb_search_by_projection_map", "orb_search_by_projection_best",
     "orb_search_for_initialization", "orb_search_by_bow", "orb_search_for_triangulation", "orb_vocabulary_create", "orb_vocabulary_destroy", "orb_vocabulary_transform",
     "orb_last_error", "orb_kernel_launch_count", "orb_version",
@@ -126,6 +126,7 @@ def lib():
         L.orb_distances_csr.argtypes = [vp, vp, i32, vp, i32, vp, vp, vp]
         L.orb_stereo_match.argtypes = [vp, vp, vp, i32, vp, vp, i32, vp, i32, i32, C.c_float, C.c_float, vp, vp]
         L.orb_compute_stereo_matches.argtypes = [vp, vp, i32, vp, i32, vp, vp, i32, vp, vp, i32, C.c_float, C.c_float, vp, vp]
+        L.orb_compute_stereo_matches_batch.argtypes = [vp, vp, i32, vp, vp, i32, vp, C.c_float, C.c_float, vp, vp, vp, i32]
         L.orb_compute_stereo_matches_mb.argtypes = [vp, vp, i32, vp, i32, vp, vp, i32, vp, vp, i32, C.c_float, C.c_float, vp, vp]
         L.orb_matcher_sync.argtypes = [vp]
         L.orb_matcher_stream.argtypes = [vp]

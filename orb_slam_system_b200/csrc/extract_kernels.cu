@@ -1748,21 +1748,23 @@ cudaError_t orbk_ingest(const uint8_t* raw, int nframes, int srows, int scols, s
 // chunk's own first byte (frame0 * rows * cols) need not be word aligned (odd-area frames), so the word index and the
 // funnel shift are both taken from the offset relative to the aligned base.
 __global__ void __launch_bounds__(256) k_repitch(const uint8_t* __restrict__ dense, int frame0, int rows, int cols,
-                                                 uint8_t* __restrict__ dst, int pitch, unsigned long long plane) {
+                                                 uint8_t* __restrict__ dst, int pitch, unsigned long long plane, size_t nwords) {
     pdl_enter();
     const int k = blockIdx.x * 256 + threadIdx.x;  // output word in the row
     const int y = blockIdx.y, f = blockIdx.z;
     if (4 * k >= cols) return;
     const size_t off = ((size_t)(frame0 + f) * rows + y) * cols + 4 * (size_t)k;  // byte offset in the dense buffer
     const unsigned* w = reinterpret_cast<const unsigned*>(dense) + (off >> 2);
-    const unsigned lo = __ldg(w), hi = __ldg(w + 1);  // the staging buffer has 8 bytes of slack
+    // nwords = 32-bit words of the dense buffer: the word behind the last one is not read (a caller's buffer has no slack)
+    const unsigned lo = __ldg(w), hi = (off >> 2) + 1 < nwords ? __ldg(w + 1) : 0u;
     *reinterpret_cast<unsigned*>(dst + f * plane + (size_t)y * pitch + 4 * k) = __funnelshift_r(lo, hi, (unsigned)(off & 3) * 8);
 }
 
 cudaError_t orbk_repitch(const uint8_t* dense, int frame0, int nframes, int rows, int cols, uint8_t* dst, int pitch,
                          unsigned long long plane, cudaStream_t st) {
     if ((uintptr_t)dense & 3) return cudaErrorMisalignedAddress;
-    k_repitch<<<dim3((cols + 1023) / 1024, rows, nframes), 256, 0, st>>>(dense, frame0, rows, cols, dst, pitch, plane);
+    const size_t nwords = ((size_t)(frame0 + nframes) * rows * cols + 3) / 4;
+    k_repitch<<<dim3((cols + 1023) / 1024, rows, nframes), 256, 0, st>>>(dense, frame0, rows, cols, dst, pitch, plane, nwords);
     orbk_count_launch(1);
     return cudaGetLastError();
 }

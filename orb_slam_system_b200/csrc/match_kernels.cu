@@ -416,9 +416,7 @@ __global__ void __launch_bounds__(1024) k_scan_counts(const int* __restrict__ in
 // vRowIndices it would be listed in (:463-473).  k_stereo_match: one warp per left keypoint,
 // right keypoints scanned in ascending index order (the order vRowIndices lists them in).
 // ------------------------------------------------------------------------------------------
-__global__ void k_stereo_prep(const orb_kp28* __restrict__ kr, int nr, const float* __restrict__ scale, int4* __restrict__ out) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nr) return;
+__device__ __forceinline__ void stereo_prep_one(const orb_kp28* __restrict__ kr, const float* __restrict__ scale, int4* __restrict__ out, int i) {
     const float y = kr[i].y;
     const float r = __fmul_rn(2.0f, scale[kr[i].octave]);
     const int maxr = (int)ceilf(__fadd_rn(y, r));
@@ -426,11 +424,15 @@ __global__ void k_stereo_prep(const orb_kp28* __restrict__ kr, int nr, const flo
     out[i] = make_int4(minr, maxr, __float_as_int(kr[i].x), kr[i].octave);
 }
 
-__global__ void __launch_bounds__(256) k_stereo_match(const orb_kp28* __restrict__ kl, const uint8_t* __restrict__ dl, int nl,
-                                                      const int4* __restrict__ rinfo, const uint8_t* __restrict__ dr, int nr,
-                                                      float maxD, int* __restrict__ best_r, int* __restrict__ best_dist) {
-    const int warp = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (warp >= nl) return;
+__global__ void k_stereo_prep(const orb_kp28* __restrict__ kr, int nr, const float* __restrict__ scale, int4* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nr) return;
+    stereo_prep_one(kr, scale, out, i);
+}
+
+__device__ __forceinline__ void stereo_match_one(const orb_kp28* __restrict__ kl, const uint8_t* __restrict__ dl,
+                                                 const int4* __restrict__ rinfo, const uint8_t* __restrict__ dr, int nr, float maxD,
+                                                 int* __restrict__ best_r, int* __restrict__ best_dist, int warp, int lane) {
     const float uL = kl[warp].x, vL = kl[warp].y;
     const int levelL = kl[warp].octave;
     const int row = (int)vL;  // vRowIndices[(size_t)vL]
@@ -469,6 +471,14 @@ __global__ void __launch_bounds__(256) k_stereo_match(const orb_kp28* __restrict
     }
 }
 
+__global__ void __launch_bounds__(256) k_stereo_match(const orb_kp28* __restrict__ kl, const uint8_t* __restrict__ dl, int nl,
+                                                      const int4* __restrict__ rinfo, const uint8_t* __restrict__ dr, int nr,
+                                                      float maxD, int* __restrict__ best_r, int* __restrict__ best_dist) {
+    const int warp = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= nl) return;
+    stereo_match_one(kl, dl, rinfo, dr, nr, maxD, best_r, best_dist, warp, lane);
+}
+
 // ------------------------------------------------------------------------------------------
 // Stereo refinement: the rest of Frame::ComputeStereoMatches after the Hamming search
 // (reference src/Frame.cc:531-603): 11x11 SAD of the centre-subtracted patches over 11 shifts on the
@@ -479,16 +489,14 @@ __global__ void __launch_bounds__(256) k_stereo_match(const orb_kp28* __restrict
 // the median cut (:606-619), which the caller does once it has all of them.
 // flags[0] |= 1 when a rowRange / colRange would leave the level image (cv::Exception in the reference).
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_stereo_refine(const orb_kp28* __restrict__ kl, int nl, const orb_kp28* __restrict__ kr,
-                                                       const int* __restrict__ best_r, const int* __restrict__ best_dist,
-                                                       const OrbStereoLevels lv, float mbf, float maxD, float* __restrict__ u_right,
-                                                       float* __restrict__ depth, int* __restrict__ sad, int* __restrict__ flags) {
-    __shared__ int s_l[8][121];
-    __shared__ int s_r[8][11 * 21];
-    __shared__ int s_d[8][12];
+// frameL / frameR: which frames of the level buffers the pair lives in (lv.left[l] + frameL * lv.plane[l], ...)
+__device__ __forceinline__ void stereo_refine_one(const orb_kp28* __restrict__ kl, const orb_kp28* __restrict__ kr,
+                                                  const int* __restrict__ best_r, const int* __restrict__ best_dist,
+                                                  const OrbStereoLevels& lv, size_t frameL, size_t frameR, float mbf, float maxD,
+                                                  float* __restrict__ u_right, float* __restrict__ depth, int* __restrict__ sad,
+                                                  int* __restrict__ flags, int i, int (&s_l)[8][121], int (&s_r)[8][11 * 21],
+                                                  int (&s_d)[8][12]) {
     const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int i = (blockIdx.x * 256 + threadIdx.x) >> 5;
-    if (i >= nl) return;
     float outU = -1.0f, outD = -1.0f;
     int outS = -1;
     const int bi = best_r[i];
@@ -514,8 +522,8 @@ __global__ void __launch_bounds__(256) k_stereo_refine(const orb_kp28* __restric
             ok = false;
         }
         if (ok) {
-            const uint8_t* PL = lv.left[oct] + (size_t)r0 * lv.pitch[oct] + c0;
-            const uint8_t* PR = lv.right[oct] + (size_t)r0 * lv.pitch[oct] + q0;
+            const uint8_t* PL = lv.left[oct] + frameL * lv.plane[oct] + (size_t)r0 * lv.pitch[oct] + c0;
+            const uint8_t* PR = lv.right[oct] + frameR * lv.plane[oct] + (size_t)r0 * lv.pitch[oct] + q0;
             for (int e = lane; e < 121; e += 32) s_l[wib][e] = PL[(e / 11) * lv.pitch[oct] + (e % 11)];
             for (int e = lane; e < 231; e += 32) s_r[wib][e] = PR[(e / 21) * lv.pitch[oct] + (e % 21)];
             __syncwarp();
@@ -563,6 +571,130 @@ __global__ void __launch_bounds__(256) k_stereo_refine(const orb_kp28* __restric
         u_right[i] = outU;
         depth[i] = outD;
         sad[i] = outS;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_stereo_refine(const orb_kp28* __restrict__ kl, int nl, const orb_kp28* __restrict__ kr,
+                                                       const int* __restrict__ best_r, const int* __restrict__ best_dist,
+                                                       const OrbStereoLevels lv, float mbf, float maxD, float* __restrict__ u_right,
+                                                       float* __restrict__ depth, int* __restrict__ sad, int* __restrict__ flags) {
+    __shared__ int s_l[8][121];
+    __shared__ int s_r[8][11 * 21];
+    __shared__ int s_d[8][12];
+    const int i = (blockIdx.x * 256 + threadIdx.x) >> 5;
+    if (i >= nl) return;
+    stereo_refine_one(kl, kr, best_r, best_dist, lv, 0, 0, mbf, maxD, u_right, depth, sad, flags, i, s_l, s_r, s_d);
+}
+
+// ------------------------------------------------------------------------------------------
+// Frame::ComputeStereoMatches for every stereo pair of one extractor batch (pair p = frames 2p / 2p + 1, keypoints and
+// descriptors in the batch layout [frame][cap]): the same three steps with blockIdx.y = pair, then the median cut
+// (src/Frame.cc:606-619) on the device, one CTA per pair.  flags[p]: bit 0 = a row band / SAD window leaves the image
+// (the reference faults), bit 1 = an octave out of range.
+// ------------------------------------------------------------------------------------------
+__global__ void k_stereo_prep_batch(const orb_kp28* __restrict__ kps, const int* __restrict__ counts, int cap, int nlevels, int rows,
+                                    const float* __restrict__ scale, int4* __restrict__ rinfo, int* __restrict__ flags) {
+    const int p = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+    const orb_kp28* kl = kps + (size_t)(2 * p) * cap;
+    const orb_kp28* kr = kps + (size_t)(2 * p + 1) * cap;
+    const int nl = min(counts[2 * p], cap), nr = min(counts[2 * p + 1], cap);
+    if (i < nr) {
+        const int oct = kr[i].octave;
+        if (oct < 0 || oct >= nlevels) {
+            atomicOr(flags + p, 2);
+            rinfo[(size_t)p * cap + i] = make_int4(1, 0, 0, 0);  // an empty row band: never a candidate
+        } else {
+            stereo_prep_one(kr, scale, rinfo + (size_t)p * cap, i);
+            const int4 ri = rinfo[(size_t)p * cap + i];
+            if (ri.x < 0 || ri.y >= rows) atomicOr(flags + p, 1);  // vRowIndices[yi] out of bounds in the reference (:463-473)
+        }
+    }
+    if (i < nl) {
+        const int oct = kl[i].octave;
+        if (oct < 0 || oct >= nlevels) atomicOr(flags + p, 2);
+        if (!(kl[i].y >= 0.0f && kl[i].y < (float)rows)) atomicOr(flags + p, 1);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_stereo_match_batch(const orb_kp28* __restrict__ kps, const uint8_t* __restrict__ desc,
+                                                            const int* __restrict__ counts, int cap, const int4* __restrict__ rinfo,
+                                                            float maxD, const int* __restrict__ flags, int* __restrict__ best_r,
+                                                            int* __restrict__ best_dist) {
+    const int p = blockIdx.y;
+    const int warp = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int nl = min(counts[2 * p], cap), nr = min(counts[2 * p + 1], cap);
+    if (warp >= nl || flags[p]) return;
+    const size_t L = (size_t)(2 * p) * cap, R = (size_t)(2 * p + 1) * cap;
+    stereo_match_one(kps + L, desc + L * 32, rinfo + (size_t)p * cap, desc + R * 32, nr, maxD, best_r + (size_t)p * cap,
+                     best_dist + (size_t)p * cap, warp, lane);
+}
+
+__global__ void __launch_bounds__(256) k_stereo_refine_batch(const orb_kp28* __restrict__ kps, const int* __restrict__ counts, int cap,
+                                                             const int* __restrict__ best_r, const int* __restrict__ best_dist,
+                                                             const OrbStereoLevels lv, float mbf, float maxD, float* __restrict__ u_right,
+                                                             float* __restrict__ depth, int* __restrict__ sad, int* __restrict__ flags) {
+    __shared__ int s_l[8][121];
+    __shared__ int s_r[8][11 * 21];
+    __shared__ int s_d[8][12];
+    const int p = blockIdx.y;
+    const int i = (blockIdx.x * 256 + threadIdx.x) >> 5;
+    const int nl = min(counts[2 * p], cap);
+    if (i >= nl || flags[p]) return;  // a refused pair: its rows are reset by the median kernel
+    const size_t L = (size_t)(2 * p) * cap, R = (size_t)(2 * p + 1) * cap, O = (size_t)p * cap;
+    stereo_refine_one(kps + L, kps + R, best_r + O, best_dist + O, lv, (size_t)(2 * p), (size_t)(2 * p + 1), mbf, maxD, u_right + O, depth + O,
+                      sad + O, flags + p, i, s_l, s_r, s_d);
+}
+
+// Median cut of one pair per CTA: median = element size / 2 of the sorted SAD values of the accepted matches, everything
+// with !(sad < 1.5f * 1.4f * median) is reset.  Rows of refused pairs (flags) are all reset.
+#define STEREO_MED_THREADS 1024
+__global__ void __launch_bounds__(STEREO_MED_THREADS) k_stereo_median_batch(const int* __restrict__ counts, int cap, const int* __restrict__ sad,
+                                                                            const int* __restrict__ flags, unsigned npad,
+                                                                            float* __restrict__ u_right, float* __restrict__ depth) {
+    extern __shared__ int keys[];  // npad ints
+    __shared__ int nvalid;
+    const int p = blockIdx.x, tid = threadIdx.x;
+    const int nl = min(counts[2 * p], cap);
+    const size_t O = (size_t)p * cap;
+    if (flags[p]) {
+        for (int i = tid; i < nl; i += STEREO_MED_THREADS) {
+            u_right[O + i] = -1.0f;
+            depth[O + i] = -1.0f;
+        }
+        return;
+    }
+    if (tid == 0) nvalid = 0;
+    __syncthreads();
+    int mine = 0;
+    for (unsigned i = tid; i < npad; i += STEREO_MED_THREADS) {
+        const int v = (int)i < nl ? sad[O + i] : -1;
+        keys[i] = v >= 0 ? v : 0x7fffffff;
+        mine += v >= 0;
+    }
+    if (mine) atomicAdd(&nvalid, mine);
+    __syncthreads();
+    for (unsigned k = 2; k <= npad; k <<= 1)
+        for (unsigned j = k >> 1; j > 0; j >>= 1) {
+            for (unsigned i = tid; i < (npad >> 1); i += STEREO_MED_THREADS) {
+                const unsigned lo = ((i & ~(j - 1)) << 1) | (i & (j - 1)), hi = lo | j;
+                const bool up = (lo & k) == 0;
+                const int x = keys[lo], y = keys[hi];
+                if ((x > y) == up) {
+                    keys[lo] = y;
+                    keys[hi] = x;
+                }
+            }
+            __syncthreads();
+        }
+    const int nv = nvalid;
+    if (nv == 0) return;  // an empty list is left alone (the reference reads past an empty vector)
+    const float thDist = 1.5f * 1.4f * (float)keys[nv / 2];
+    for (int i = tid; i < nl; i += STEREO_MED_THREADS) {
+        const int v = sad[O + i];
+        if (v >= 0 && !((float)v < thDist)) {
+            u_right[O + i] = -1.0f;
+            depth[O + i] = -1.0f;
+        }
     }
 }
 
@@ -718,6 +850,30 @@ cudaError_t orbk_stereo_refine(const orb_kp28* kl, int nl, const orb_kp28* kr, c
     if (nl <= 0) return cudaSuccess;
     k_stereo_refine<<<(nl + 7) / 8, 256, 0, st>>>(kl, nl, kr, best_r, best_dist, lv, mbf, maxD, u_right, depth, sad, flags);
     orbk_count_launch(1);
+    return cudaGetLastError();
+}
+
+cudaError_t orbk_stereo_batch(const orb_kp28* kps, const uint8_t* desc, const int* counts, int cap, int npairs, int nlevels, int rows,
+                              const float* d_scale, const OrbStereoLevels& lv, float mbf, float maxD, int4* d_rinfo, int* d_best_r,
+                              int* d_best_dist, int* d_sad, int* d_flags, float* u_right, float* depth, cudaStream_t st) {
+    if (npairs <= 0 || cap <= 0) return cudaSuccess;
+    cudaError_t e = cudaMemsetAsync(d_flags, 0, sizeof(int) * npairs, st);
+    if (e != cudaSuccess) return e;
+    k_stereo_prep_batch<<<dim3((cap + 255) / 256, npairs), 256, 0, st>>>(kps, counts, cap, nlevels, rows, d_scale, d_rinfo, d_flags);
+    k_stereo_match_batch<<<dim3((cap + 7) / 8, npairs), 256, 0, st>>>(kps, desc, counts, cap, d_rinfo, maxD, d_flags, d_best_r, d_best_dist);
+    k_stereo_refine_batch<<<dim3((cap + 7) / 8, npairs), 256, 0, st>>>(kps, counts, cap, d_best_r, d_best_dist, lv, mbf, maxD, u_right, depth,
+                                                                       d_sad, d_flags);
+    unsigned npad = 2;
+    while (npad < (unsigned)cap) npad <<= 1;
+    static bool attr = false;
+    if (!attr) {
+        e = cudaFuncSetAttribute(k_stereo_median_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        if (e != cudaSuccess) return e;
+        attr = true;
+    }
+    if ((size_t)npad * 4 > 160 * 1024) return cudaErrorInvalidValue;
+    k_stereo_median_batch<<<npairs, STEREO_MED_THREADS, (size_t)npad * 4, st>>>(counts, cap, d_sad, d_flags, npad, u_right, depth);
+    orbk_count_launch(4);
     return cudaGetLastError();
 }
 

@@ -15,6 +15,7 @@ struct OrbStereoLevels {
     const uint8_t* right[16];
     int pitch[16], rows[16], cols[16];
     float scale[16], inv_scale[16];
+    unsigned long long plane[16];  // bytes between the frames of a level buffer (batched form; unused by the single-pair kernels)
 };
 
 // max_nt: largest train set, or -1 when the counts live on the device only.
@@ -41,6 +42,11 @@ cudaError_t orbk_window_fill(const orb_kp28* keys, const uint8_t* tdesc, const i
 cudaError_t orbk_stereo_refine(const orb_kp28* kl, int nl, const orb_kp28* kr, const int* best_r, const int* best_dist,
                                const OrbStereoLevels& lv, float mbf, float maxD, float* u_right, float* depth, int* sad, int* flags,
                                cudaStream_t st);
+// Frame::ComputeStereoMatches for npairs stereo pairs of one extractor batch (pair p = frames 2p, 2p + 1; kps / desc in the
+// batch layout [frame][cap]); scratch: d_rinfo, d_best_r, d_best_dist, d_sad [npairs][cap], d_flags [npairs].
+cudaError_t orbk_stereo_batch(const orb_kp28* kps, const uint8_t* desc, const int* counts, int cap, int npairs, int nlevels, int rows,
+                              const float* d_scale, const OrbStereoLevels& lv, float mbf, float maxD, int4* d_rinfo, int* d_best_r,
+                              int* d_best_dist, int* d_sad, int* d_flags, float* u_right, float* depth, cudaStream_t st);
 // DBoW2 TemplatedVocabulary::transform descent for n features: leaf node and the node at level nid_level of each.
 cudaError_t orbk_voc_descent(const uint8_t* feat, int n, const int* child_off, const int* children, const uint8_t* node_desc,
                              int nid_level, int* leaf_node, int* node_at_level, cudaStream_t st);

@@ -703,6 +703,10 @@ static int extract_device_impl(orb_extractor* h, int n, const uint8_t* d_imgs, i
         }
         maps = h->d_maps_user;
         h->last_l0 = d_imgs;
+    } else if (stride == (size_t)cols && frame_stride == (size_t)rows * cols && cols >= 4) {
+        // densely packed device frames: one pitch-conversion kernel into the internal level-0 buffer
+        h->last_l0 = h->level0;
+        CUDA_TRY(orbk_repitch(d_imgs, 0, n, rows, cols, h->level0, h->plan.lv[0].pitch, h->plan.lv[0].plane, h->stream));
     } else {
         h->last_l0 = h->level0;
         // pitch conversion into the internal level-0 buffer (blur/describe share its pitch)
@@ -1438,5 +1442,99 @@ extern "C" int orb_compute_stereo_matches_mb(orb_matcher* m, orb_extractor* ex_l
                 depth[i] = -1;
             }
     }
+    return ORB_OK;
+}
+
+// Frame::ComputeStereoMatches for the stereo pairs of one extractor batch.  Pair p = frames (2p, 2p + 1) of ex's last call
+// (left = even, right = odd frame).
+extern "C" int orb_compute_stereo_matches_batch(orb_matcher* m, orb_extractor* ex, int npairs, const orb_keypoint* kps, const uint8_t* desc,
+                                                int cap, const int32_t* counts, float bf, float fx, float* u_right, float* depth,
+                                                int32_t* status, int on_device) {
+    if (!m || !ex || !kps || !desc || !counts || !u_right || !depth) return fail(ORB_ERR_INVALID, "null argument");
+    if (npairs < 0 || cap <= 0) return fail(ORB_ERR_INVALID, "bad count");
+    if (npairs == 0) return ORB_OK;
+    if (ex->plan.rows == 0) return fail(ORB_ERR_INVALID, "no frame extracted yet");
+    if (2 * npairs > ex->max_batch) return fail(ORB_ERR_INVALID, "%d pairs exceed the extractor's max_batch=%d", npairs, ex->max_batch);
+    if (ex->device != m->device) return fail(ORB_ERR_INVALID, "handles live on different devices");
+    const OrbPlan& P = ex->plan;
+    const int nlevels = P.nlevels;
+    CUDA_TRY(cudaSetDevice(m->device));
+    const float mb = bf / fx;    // src/Frame.cc:94
+    const float maxD = bf / mb;  // :476-478
+    const size_t rowsN = (size_t)npairs * cap, frames = 2 * (size_t)npairs;
+    void *dri, *dwork, *dsc, *dk = nullptr, *dd = nullptr, *dc = nullptr, *dres = nullptr;
+    int rc;
+    if ((rc = scratch(m, 7, sizeof(int4) * rowsN, &dri)) || (rc = scratch(m, 3, sizeof(int) * (3 * rowsN + npairs), &dwork)) ||
+        (rc = scratch(m, 6, sizeof(float) * ORB_MAX_LEVELS, &dsc)))
+        return rc;
+    cudaStream_t st = m->stream;
+    // the pyramids were written on the extractor's stream
+    cudaEvent_t ev;
+    CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    cudaError_t e1 = cudaEventRecord(ev, ex->stream);
+    if (e1 == cudaSuccess) e1 = cudaStreamWaitEvent(st, ev, 0);
+    cudaEventDestroy(ev);
+    CUDA_TRY(e1);
+    const orb_kp28* d_kps = (const orb_kp28*)kps;
+    const uint8_t* d_desc = desc;
+    const int* d_counts = counts;
+    float *d_ur = u_right, *d_dep = depth;
+    if (!on_device) {
+        if ((rc = scratch(m, 4, frames * cap * 28, &dk)) || (rc = scratch(m, 0, frames * cap * 32, &dd)) ||
+            (rc = scratch(m, 5, sizeof(int) * frames, &dc)) || (rc = scratch(m, 2, sizeof(float) * 2 * rowsN, &dres)))
+            return rc;
+        int maxc = 0;
+        for (size_t f = 0; f < frames; ++f) maxc = std::max(maxc, std::min(counts[f], cap));
+        if (maxc > 0) {
+            CUDA_TRY(cudaMemcpy2DAsync(dk, (size_t)cap * 28, kps, (size_t)cap * 28, (size_t)maxc * 28, frames, cudaMemcpyHostToDevice, st));
+            CUDA_TRY(cudaMemcpy2DAsync(dd, (size_t)cap * 32, desc, (size_t)cap * 32, (size_t)maxc * 32, frames, cudaMemcpyHostToDevice, st));
+        }
+        CUDA_TRY(cudaMemcpyAsync(dc, counts, sizeof(int) * frames, cudaMemcpyHostToDevice, st));
+        d_kps = (const orb_kp28*)dk;
+        d_desc = (const uint8_t*)dd;
+        d_counts = (const int*)dc;
+        d_ur = (float*)dres;
+        d_dep = d_ur + rowsN;
+    }
+    CUDA_TRY(cudaMemcpyAsync(dsc, ex->tab.scale.data(), sizeof(float) * nlevels, cudaMemcpyHostToDevice, st));
+    OrbStereoLevels lv;
+    memset(&lv, 0, sizeof lv);
+    for (int l = 0; l < nlevels; ++l) {
+        const OrbLevel& A = P.lv[l];
+        const uint8_t* base = (A.src == 0 && ex->last_l0) ? ex->last_l0 : A.img;
+        lv.left[l] = lv.right[l] = base;
+        lv.plane[l] = A.plane;
+        lv.pitch[l] = A.pitch;
+        lv.rows[l] = A.rows;
+        lv.cols[l] = A.cols;
+        lv.scale[l] = ex->tab.scale[l];
+        lv.inv_scale[l] = ex->tab.inv_scale[l];
+    }
+    int* w = (int*)dwork;
+    int *d_best_r = w, *d_best_dist = w + rowsN, *d_sad = w + 2 * rowsN, *d_flags = w + 3 * rowsN;
+    CUDA_TRY(orbk_stereo_batch(d_kps, d_desc, d_counts, cap, npairs, nlevels, P.rows, (const float*)dsc, lv, bf, maxD, (int4*)dri, d_best_r,
+                               d_best_dist, d_sad, d_flags, d_ur, d_dep, st));
+    if (on_device) {
+        // status[p] (device, optional): the flag word of pair p, 0 = ok, non-zero = the reference faults on this pair (rows reset to -1)
+        if (status) CUDA_TRY(cudaMemcpyAsync(status, d_flags, sizeof(int) * npairs, cudaMemcpyDeviceToDevice, st));
+        return ORB_OK;
+    }
+    std::vector<int> flags(npairs);
+    int maxl = 0;
+    for (int p = 0; p < npairs; ++p) maxl = std::max(maxl, std::min(counts[2 * p], cap));
+    if (maxl > 0) {
+        CUDA_TRY(cudaMemcpy2DAsync(u_right, (size_t)cap * 4, d_ur, (size_t)cap * 4, (size_t)maxl * 4, npairs, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpy2DAsync(depth, (size_t)cap * 4, d_dep, (size_t)cap * 4, (size_t)maxl * 4, npairs, cudaMemcpyDeviceToHost, st));
+    }
+    CUDA_TRY(cudaMemcpyAsync(flags.data(), d_flags, sizeof(int) * npairs, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    int bad = -1;
+    for (int p = 0; p < npairs; ++p) {
+        if (status) status[p] = flags[p] ? ((flags[p] & 2) ? ORB_ERR_INVALID : ORB_ERR_SHAPE) : ORB_OK;
+        if (flags[p] && bad < 0) bad = p;
+    }
+    if (bad >= 0 && !status)
+        return fail((flags[bad] & 2) ? ORB_ERR_INVALID : ORB_ERR_SHAPE, "pair %d: %s", bad,
+                    (flags[bad] & 2) ? "keypoint octave out of range" : "a row band or SAD window leaves the image (the reference faults here)");
     return ORB_OK;
 }

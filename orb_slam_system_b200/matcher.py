@@ -192,6 +192,26 @@ class ORBmatcher:
                                                ptr(kr), ptr(dr), len(kr), C.c_float(bf), C.c_float(fx), ptr(ur), ptr(dep)))
         return ur, dep
 
+    def ComputeStereoMatchesBatch(self, ex, kps, desc, counts, cap, bf, fx):
+        """Frame::ComputeStereoMatches for every stereo pair of one extractor batch (pair p = frames 2p, 2p + 1 of ex's last
+        call).  Host arrays in the batch layout: kps [2P, cap] KP_DTYPE (or bytes [2P, cap, 28]), desc [2P, cap, 32], counts [2P].
+        Returns (u_right [P, cap], depth [P, cap], status [P]); rows of pair p are valid up to counts[2p]."""
+        counts = np.ascontiguousarray(counts, np.int32)
+        P = len(counts) // 2
+        ur = np.full((P, cap), -1, np.float32)
+        dep = np.full((P, cap), -1, np.float32)
+        status = np.zeros(P, np.int32)
+        check(lib().orb_compute_stereo_matches_batch(self._h, ex._h, P, ptr(kps), ptr(desc), cap, ptr(counts), C.c_float(bf), C.c_float(fx),
+                                                     ptr(ur), ptr(dep), ptr(status), 0))
+        return ur, dep, status
+
+    def ComputeStereoMatchesBatchDevice(self, ex, d_kps, d_desc, d_counts, cap, bf, fx, d_u_right, d_depth, d_status=None):
+        """The same on the device-resident outputs of ORBextractor.extract_batch_device (torch CUDA tensors), asynchronous on
+        the matcher's stream."""
+        P = int(d_counts.shape[0]) // 2
+        check(lib().orb_compute_stereo_matches_batch(self._h, ex._h, P, ptr(d_kps), ptr(d_desc), cap, ptr(d_counts), C.c_float(bf), C.c_float(fx),
+                                                     ptr(d_u_right), ptr(d_depth), ptr(d_status) if d_status is not None else None, 1))
+
     # ---- candidate windows: Frame::GetFeaturesInArea for many queries (src/Frame.cc:307-360) ----
     def window_search(self, F, qdesc, x, y, r, min_level=None, max_level=None):
         """Returns (offsets[nq+1], cand, dist): reference candidate order and DescriptorDistance of each."""

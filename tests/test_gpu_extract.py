@@ -383,3 +383,24 @@ def test_result_copies_ahead_of_counts_are_topped_up():
         _check_batch_against_oracle(batch, nf, k, d, c, tag)
     assert c.max() > 3 * 64  # the dense batch really is larger than what the sparse one predicted
     ex.close()
+
+
+def test_device_resident_dense_frames():
+    # densely packed device frames (row stride == cols, odd area): one pitch-conversion kernel, no slack behind the buffer
+    import torch
+    rows, cols, nf, B = 121, 164, 300, 5
+    frames = np.stack([oracle.synth_frame(rows, cols, frame=40 + f) for f in range(B)])
+    ex = ORBextractor(nf, 1.2, 8, 20, 7, max_batch=B)
+    cap = ex.keypoint_bound(rows, cols)
+    d_in = torch.from_numpy(frames).cuda()
+    d_k = torch.zeros((B, cap, 28), dtype=torch.uint8, device="cuda")
+    d_d = torch.zeros((B, cap, 32), dtype=torch.uint8, device="cuda")
+    d_c = torch.zeros((B,), dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    ex.extract_batch_device(d_in, d_k, d_d, d_c, cap)
+    ex.sync()
+    k, d, c = d_k.cpu().numpy(), d_d.cpu().numpy(), d_c.cpu().numpy()
+    for f in range(B):
+        ko, do = oracle.extract(frames[f], nfeatures=nf, cap=16 * nf)
+        assert c[f] == len(ko) and k[f, :c[f]].tobytes() == ko.tobytes() and (d[f, :c[f]] == do).all(), f
+    ex.close()

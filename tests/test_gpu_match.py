@@ -141,3 +141,57 @@ def test_compute_stereo_matches_whole(rows, cols, nf, frame):
     for e in (exl, exr, exb):
         e.close()
     m.close()
+
+
+@pytest.mark.parametrize("rows,cols,nf,npairs", [(480, 752, 1200, 3), (376, 1241, 2000, 2)])
+def test_compute_stereo_matches_batch(rows, cols, nf, npairs):
+    # Frame::ComputeStereoMatches for all stereo pairs of one extractor batch (four launches over all pairs, median cut on
+    # the device) against the oracle pair by pair: host buffers and the device-resident form
+    import torch
+    from orb_slam_system_b200 import KP_DTYPE
+    bf, fx = 47.90639384423901, 435.2046959714599
+    frames = np.stack([oracle.synth_frame(rows, cols, frame=20 + f // 2, right=f & 1) for f in range(2 * npairs)])
+    ex = ORBextractor(nf, 1.2, 8, 20, 7, max_batch=2 * npairs)
+    cap = ex.keypoint_bound(rows, cols)
+    kps = np.zeros((2 * npairs, cap), KP_DTYPE)
+    desc = np.zeros((2 * npairs, cap, 32), np.uint8)
+    counts = np.zeros(2 * npairs, np.int32)
+    ex.extract_batch_pinned(frames, kps, desc, counts, cap)
+    m = ORBmatcher()
+    ur, dep, status = m.ComputeStereoMatchesBatch(ex, kps, desc, counts, cap, bf, fx)
+    assert (status == 0).all()
+    want = []
+    for p in range(npairs):
+        cl, cr = counts[2 * p], counts[2 * p + 1]
+        our, odep = oracle.compute_stereo_matches(frames[2 * p], frames[2 * p + 1], kps[2 * p, :cl], desc[2 * p, :cl], kps[2 * p + 1, :cr],
+                                                  desc[2 * p + 1, :cr], bf, fx)
+        want.append((our, odep))
+        assert ur[p, :cl].tobytes() == our.tobytes() and dep[p, :cl].tobytes() == odep.tobytes(), p
+        assert (our >= 0).sum() > 500
+    # device resident: the outputs of extract_batch_device go in untouched
+    pitch = (cols + 63) // 64 * 64
+    d_in = torch.zeros((2 * npairs, rows, pitch), dtype=torch.uint8, device="cuda")
+    d_in[:, :, :cols] = torch.from_numpy(frames).cuda()
+    d_k = torch.zeros((2 * npairs, cap, 28), dtype=torch.uint8, device="cuda")
+    d_d = torch.zeros((2 * npairs, cap, 32), dtype=torch.uint8, device="cuda")
+    d_c = torch.zeros((2 * npairs,), dtype=torch.int32, device="cuda")
+    d_ur = torch.full((npairs, cap), -7.0, dtype=torch.float32, device="cuda")
+    d_dep = torch.full((npairs, cap), -7.0, dtype=torch.float32, device="cuda")
+    d_st = torch.full((npairs,), 9, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    ex.extract_batch_device(d_in[:, :, :cols], d_k, d_d, d_c, cap)
+    m.ComputeStereoMatchesBatchDevice(ex, d_k, d_d, d_c, cap, bf, fx, d_ur, d_dep, d_st)
+    m.sync()
+    assert (d_st.cpu().numpy() == 0).all()
+    for p in range(npairs):
+        cl = counts[2 * p]
+        assert d_ur[p, :cl].cpu().numpy().tobytes() == want[p][0].tobytes() and d_dep[p, :cl].cpu().numpy().tobytes() == want[p][1].tobytes(), p
+    # a pair on which the reference faults (a right keypoint whose row band leaves the image) is refused, the others are not
+    bad = kps.copy()
+    bad[1, 0]["y"] = 0.5
+    ur2, dep2, st2 = m.ComputeStereoMatchesBatch(ex, bad, desc, counts, cap, bf, fx)
+    assert st2[0] != 0 and (st2[1:] == 0).all()
+    assert (ur2[0, :counts[0]] == -1).all()
+    assert ur2[1, :counts[2]].tobytes() == want[1][0].tobytes()
+    ex.close()
+    m.close()
