@@ -1,3 +1,6 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_frame_reference.py tests/test_search_reference.py -m gpu -q > gpurun_out/r02k_pytest.txt 2>&1
-tail -n 15 gpurun_out/r02k_pytest.txt
+O=gpurun_out/r02m_resident.txt; : > $O
+python tools/probes/resident_probe.py >> $O 2>&1
+LATE_ENV=ORB_B200_PROBE_SKIP_RESIZE=1 python tools/probes/resident_probe.py >> $O 2>&1
+LATE_ENV=ORB_B200_PROBE_SKIP_RESIZE=2 python tools/probes/resident_probe.py >> $O 2>&1
+cat $O

@@ -19,6 +19,9 @@ st = torch.cuda.ExternalStream(ex.stream)
 def step(i): ex.extract_batch_device(d_in[i % R][:, :, :COLS], dk, dd, dc, cap)
 for i in range(5): step(i)
 ex.sync()
+if os.environ.get("LATE_ENV"):  # KEY=VALUE set only after the warm-up (timing probes that must start from filled buffers)
+    k, v = os.environ["LATE_ENV"].split("=")
+    os.environ[k] = v
 ms = []
 for rep in range(5):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
