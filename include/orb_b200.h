@@ -394,6 +394,12 @@ int orb_vocabulary_transform(orb_vocabulary* v, const uint8_t* desc, int n, int 
 
 /* ---- misc ------------------------------------------------------------------------------- */
 
+/* Page-locked host memory for the caller's frame and result buffers: copies from / to it run at full PCIe rate and
+ * asynchronously, pageable memory is staged by the driver.  (cudaHostAlloc / cudaFreeHost behind a C name, so that the
+ * adapter classes and other callers need not link the CUDA runtime themselves.) */
+int orb_host_alloc(size_t bytes, void** out);
+void orb_host_free(void* p);
+
 /* Thread-local description of the last error on this thread ("" if none). */
 const char* orb_last_error(void);
 /* Number of kernels this library has launched in this process (for bench accounting). */

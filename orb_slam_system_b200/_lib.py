@@ -79,7 +79,7 @@ EXPORTS = [
     "orb_match_all_batch", "orb_match_csr", "orb_distances_csr", "orb_stereo_match", "orb_compute_stereo_matches", "orb_compute_stereo_matches_mb", "orb_compute_stereo_matches_batch", "orb_matcher_sync",
     "orb_matcher_stream", "orb_window_search", "orb_search_by_projection_map", "orb_search_by_projection_best",
     "orb_search_for_initialization", "orb_search_by_bow", "orb_search_for_triangulation", "orb_vocabulary_create", "orb_vocabulary_destroy", "orb_vocabulary_transform",
-    "orb_last_error", "orb_kernel_launch_count", "orb_version",
+    "orb_host_alloc", "orb_host_free", "orb_last_error", "orb_kernel_launch_count", "orb_version",
 ]
 
 

@@ -69,8 +69,12 @@ protected:
     std::vector<float> mvInvLevelSigma2;
 
 private:
+    // page-locked staging of the frame, the results and the pyramid levels (grown on demand): the caller's cv::Mat /
+    // std::vector are pageable, and copies from / to pageable memory are several times slower and not asynchronous
+    void pinned(size_t which, size_t bytes);
     orb_extractor* handle_;
-    std::vector<unsigned char> kpbuf_;
+    void* pin_[4] = {nullptr, nullptr, nullptr, nullptr};  // frame, keypoints, descriptors, pyramid
+    size_t pinBytes_[4] = {0, 0, 0, 0};
 };
 
 }  // namespace ORB_SLAM2

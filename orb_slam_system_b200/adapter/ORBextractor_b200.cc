@@ -6,6 +6,7 @@
 #include "ORBextractor.h"
 
 #include <cstdlib>
+#include <cstring>
 #include <string>
 #include <vector>
 
@@ -59,7 +60,19 @@ ORBextractor::ORBextractor(int _nfeatures, float _scaleFactor, int _nlevels, int
     mvImagePyramid.resize(nlevels);
 }
 
-ORBextractor::~ORBextractor() { orb_extractor_destroy(handle_); }
+ORBextractor::~ORBextractor() {
+    orb_extractor_destroy(handle_);
+    for (void* p : pin_) orb_host_free(p);
+}
+
+void ORBextractor::pinned(size_t which, size_t bytes) {
+    if (bytes <= pinBytes_[which]) return;
+    orb_host_free(pin_[which]);
+    pin_[which] = nullptr;
+    pinBytes_[which] = 0;
+    if (orb_host_alloc(bytes + bytes / 4, &pin_[which]) != ORB_OK) raise("orb_host_alloc");
+    pinBytes_[which] = bytes + bytes / 4;
+}
 
 void ORBextractor::operator()(cv::InputArray _image, cv::InputArray /*mask*/, std::vector<cv::KeyPoint>& _keypoints,
                               cv::OutputArray _descriptors) {
@@ -70,31 +83,45 @@ void ORBextractor::operator()(cv::InputArray _image, cv::InputArray /*mask*/, st
     int bound = 0;
     if (orb_extractor_keypoint_bound(handle_, image.rows, image.cols, &bound) != ORB_OK) raise("unsupported image shape");
     static_assert(sizeof(cv::KeyPoint) == sizeof(orb_keypoint), "cv::KeyPoint must be the 28-byte POD the C ABI writes");
-    kpbuf_.resize((size_t)bound * sizeof(orb_keypoint));
-    cv::Mat desc(bound, 32, CV_8UC1);
+    const size_t rowBytes = (size_t)image.cols;
+    pinned(0, rowBytes * image.rows);
+    pinned(1, (size_t)bound * sizeof(orb_keypoint));
+    pinned(2, (size_t)bound * 32);
+    uint8_t* pimg = static_cast<uint8_t*>(pin_[0]);
+    for (int y = 0; y < image.rows; ++y) memcpy(pimg + (size_t)y * rowBytes, image.ptr<uint8_t>(y), rowBytes);
+    orb_keypoint* pk = static_cast<orb_keypoint*>(pin_[1]);
+    uint8_t* pd = static_cast<uint8_t*>(pin_[2]);
     int count = 0;
-    if (orb_extract(handle_, image.ptr<uint8_t>(0), image.rows, image.cols, (size_t)image.step, (orb_keypoint*)kpbuf_.data(),
-                    desc.ptr<uint8_t>(0), bound, &count) != ORB_OK)
-        raise("orb_extract");
+    if (orb_extract(handle_, pimg, image.rows, image.cols, rowBytes, pk, pd, bound, &count) != ORB_OK) raise("orb_extract");
 
     // mvImagePyramid: level ROI inside a (w+38) x (h+38) buffer with a reflected border (src/ORBextractor.cc:497-515);
-    // all levels are fetched with one set of copies and one synchronisation
+    // all levels land in page-locked staging with one set of copies and one synchronisation
     if (keep_pyramid()) {
         std::vector<cv::Mat> padded(nlevels);
         std::vector<uint8_t*> dst(nlevels);
         std::vector<size_t> stride(nlevels);
+        std::vector<int> lr(nlevels), lc(nlevels);
+        size_t total = 0;
         for (int level = 0; level < nlevels; ++level) {
-            int r = 0, c = 0;
-            if (orb_get_pyramid_level(handle_, 0, level, nullptr, 0, &r, &c) != ORB_OK) raise("orb_get_pyramid_level");  // sizes only
-            padded[level] = cv::Mat(cv::Size(c + 2 * EDGE_THRESHOLD, r + 2 * EDGE_THRESHOLD), image.type());
-            mvImagePyramid[level] = padded[level](cv::Rect(EDGE_THRESHOLD, EDGE_THRESHOLD, c, r));
-            dst[level] = mvImagePyramid[level].ptr<uint8_t>(0);
-            stride[level] = (size_t)mvImagePyramid[level].step;
+            if (orb_get_pyramid_level(handle_, 0, level, nullptr, 0, &lr[level], &lc[level]) != ORB_OK) raise("orb_get_pyramid_level");  // sizes only
+            total += (size_t)lr[level] * lc[level];
+        }
+        pinned(3, total);
+        size_t off = 0;
+        for (int level = 0; level < nlevels; ++level) {
+            dst[level] = static_cast<uint8_t*>(pin_[3]) + off;
+            stride[level] = (size_t)lc[level];
+            off += (size_t)lr[level] * lc[level];
         }
         if (orb_get_pyramid_levels(handle_, 0, dst.data(), stride.data()) != ORB_OK) raise("orb_get_pyramid_levels");
-        for (int level = 0; level < nlevels; ++level)
+        for (int level = 0; level < nlevels; ++level) {
+            const int r = lr[level], c = lc[level];
+            padded[level] = cv::Mat(cv::Size(c + 2 * EDGE_THRESHOLD, r + 2 * EDGE_THRESHOLD), image.type());
+            mvImagePyramid[level] = padded[level](cv::Rect(EDGE_THRESHOLD, EDGE_THRESHOLD, c, r));
+            for (int y = 0; y < r; ++y) memcpy(mvImagePyramid[level].ptr<uint8_t>(y), dst[level] + (size_t)y * c, (size_t)c);
             cv::copyMakeBorder(mvImagePyramid[level], padded[level], EDGE_THRESHOLD, EDGE_THRESHOLD, EDGE_THRESHOLD, EDGE_THRESHOLD,
                                cv::BORDER_REFLECT_101 + cv::BORDER_ISOLATED);
+        }
     }
 
     if (count == 0) {
@@ -103,8 +130,8 @@ void ORBextractor::operator()(cv::InputArray _image, cv::InputArray /*mask*/, st
     }
     _descriptors.create(count, 32, CV_8U);
     cv::Mat out = _descriptors.getMat();
-    for (int i = 0; i < count; ++i) memcpy(out.ptr<uint8_t>(i), desc.ptr<uint8_t>(i), 32);
-    const cv::KeyPoint* k = reinterpret_cast<const cv::KeyPoint*>(kpbuf_.data());
+    for (int i = 0; i < count; ++i) memcpy(out.ptr<uint8_t>(i), pd + 32 * (size_t)i, 32);
+    const cv::KeyPoint* k = reinterpret_cast<const cv::KeyPoint*>(pk);
     _keypoints.assign(k, k + count);
 }
 

@@ -853,6 +853,15 @@ cudaError_t orbk_stereo_refine(const orb_kp28* kl, int nl, const orb_kp28* kr, c
     return cudaGetLastError();
 }
 
+cudaError_t orbk_match_mma_init();
+
+// Per-device function attributes of the matcher kernels (dynamic shared memory above 48 KB); orb_matcher_create calls it.
+cudaError_t orbk_match_init_device() {
+    cudaError_t e = cudaFuncSetAttribute(k_stereo_median_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    if (e != cudaSuccess) return e;
+    return orbk_match_mma_init();
+}
+
 cudaError_t orbk_stereo_batch(const orb_kp28* kps, const uint8_t* desc, const int* counts, int cap, int npairs, int nlevels, int rows,
                               const float* d_scale, const OrbStereoLevels& lv, float mbf, float maxD, int4* d_rinfo, int* d_best_r,
                               int* d_best_dist, int* d_sad, int* d_flags, float* u_right, float* depth, cudaStream_t st) {
@@ -865,13 +874,7 @@ cudaError_t orbk_stereo_batch(const orb_kp28* kps, const uint8_t* desc, const in
                                                                        d_sad, d_flags);
     unsigned npad = 2;
     while (npad < (unsigned)cap) npad <<= 1;
-    static bool attr = false;
-    if (!attr) {
-        e = cudaFuncSetAttribute(k_stereo_median_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-        if (e != cudaSuccess) return e;
-        attr = true;
-    }
-    if ((size_t)npad * 4 > 160 * 1024) return cudaErrorInvalidValue;
+    if ((size_t)npad * 4 > 160 * 1024) return cudaErrorInvalidValue;  // cap above 40960 keypoints per frame
     k_stereo_median_batch<<<npairs, STEREO_MED_THREADS, (size_t)npad * 4, st>>>(counts, cap, d_sad, d_flags, npad, u_right, depth);
     orbk_count_launch(4);
     return cudaGetLastError();

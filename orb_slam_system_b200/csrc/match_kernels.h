@@ -18,6 +18,8 @@ struct OrbStereoLevels {
     unsigned long long plane[16];  // bytes between the frames of a level buffer (batched form; unused by the single-pair kernels)
 };
 
+// Function attributes of the matcher kernels for the current device (called once per matcher handle).
+cudaError_t orbk_match_init_device();
 // max_nt: largest train set, or -1 when the counts live on the device only.
 cudaError_t orbk_match_all(const uint8_t* q, const int* nq, size_t q_stride, const uint8_t* t, const int* nt,
                            size_t t_stride, int npairs, int max_nq, int max_nt, int* best_idx, int* best_dist, int* second_dist,

@@ -657,6 +657,7 @@ cudaError_t orbk_match_all_popc(const uint8_t* q, const int* nq, size_t q_stride
                                 int npairs, int max_nq, int* best_idx, int* best_dist, int* second_dist, size_t out_stride,
                                 int only_huge, cudaStream_t st);
 
+// Function attributes are per device: called by orb_matcher_create for the handle's device.
 cudaError_t orbk_match_mma_init() {
     cudaError_t e = cudaFuncSetAttribute(k_match_mma<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, MM_SMEM);
     if (e != cudaSuccess) return e;
@@ -678,8 +679,6 @@ cudaError_t orbk_match_all_mma(const uint8_t* q, const int* nq, size_t q_stride,
                                int npairs, int max_nq, int* best_idx, int* best_dist, int* second_dist, size_t out_stride, int kind,
                                int variant, cudaStream_t st) {
     if (npairs <= 0 || max_nq <= 0) return cudaSuccess;
-    static const cudaError_t init = orbk_match_mma_init();
-    if (init != cudaSuccess) return init;
     MmParams prm;
     prm.neg_lo = (unsigned)-64;
     prm.neg_hi = (unsigned)(-64 * 65536);

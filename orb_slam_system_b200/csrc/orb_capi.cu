@@ -41,6 +41,16 @@ int orb_fail(int code, const char* fmt, ...) {
 #define fail orb_fail
 
 extern "C" const char* orb_last_error(void) { return t_err.c_str(); }
+extern "C" int orb_host_alloc(size_t bytes, void** out) {
+    if (!out) return orb_fail(ORB_ERR_INVALID, "null argument");
+    *out = nullptr;
+    cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault);
+    if (e != cudaSuccess) return orb_fail(ORB_ERR_CUDA, "cudaHostAlloc(%zu): %s", bytes, cudaGetErrorString(e));
+    return ORB_OK;
+}
+extern "C" void orb_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
 extern "C" uint64_t orb_kernel_launch_count(void) { return orbk_launch_count(); }
 extern "C" const char* orb_version(void) { return "orb_b200 0.1 (sm_100a)"; }
 
@@ -1142,6 +1152,7 @@ extern "C" int orb_matcher_create(int device, orb_matcher** out) {
         return fail(ORB_ERR_CUDA, "no CUDA device: %s (liborb_b200 has no CPU fallback)", cudaGetErrorString(e));
     if (device < 0 || device >= ndev) return fail(ORB_ERR_INVALID, "device %d out of range", device);
     CUDA_TRY(cudaSetDevice(device));
+    CUDA_TRY(orbk_match_init_device());
     orb_matcher* m = new orb_matcher();
     m->device = device;
     cudaError_t ce = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
