@@ -384,16 +384,11 @@ __global__ void __launch_bounds__(DET_THREADS) k_detect(const __grid_constant__ 
     DetectTail& sm = *reinterpret_cast<DetectTail*>(smem_raw + det_img_bytes(detRows) + det_sc_bytes(detRows));
 
     const int f = blockIdx.y;
-    int tile = blockIdx.x + tileOffset;
-    int l = 0;
-    for (; l < plan.nlevels; ++l) {
-        const OrbLevel& L = plan.lv[l];
-        if (L.src == l && tile >= L.tileBase && tile < L.tileBase + L.nTiles) break;
-    }
-    if (l >= plan.nlevels) return;
+    const int tile = blockIdx.x + tileOffset;
+    if (tile >= plan.totalTiles) return;
+    const unsigned te = __ldg(plan.detTileTab + tile);  // level | cell row << 4 | tile column << 18
+    const int l = (int)(te & 15u), ci = (int)((te >> 4) & 0x3fffu), tx = (int)(te >> 18);
     const OrbLevel& L = plan.lv[l];
-    tile -= L.tileBase;
-    const int ci = tile / L.tilesX, tx = tile - ci * L.tilesX;
     const int j0 = tx * L.tileCells, j1 = min(j0 + L.tileCells, L.nCols);
     const int maxBX = L.cols - ORB_MINB, maxBY = L.rows - ORB_MINB;
     const int X0 = ORB_MINB + j0 * L.wCell;
@@ -1164,19 +1159,10 @@ __global__ void __launch_bounds__(BLUR_THREADS) k_blur(const __grid_constant__ O
     __shared__ __align__(128) unsigned tile[BLUR_BOX_H][BLUR_SW];
     __shared__ unsigned long long barMem;
     const int f = blockIdx.y;
-    int t = blockIdx.x, l = 0;
-    int tilesX = 0;
-    for (; l < plan.nlevels; ++l) {
-        const OrbLevel& L = plan.lv[l];
-        if (L.src != l) continue;
-        tilesX = (L.cols + BLUR_TW - 1) / BLUR_TW;
-        const int nt = tilesX * ((L.rows + BLUR_TH - 1) / BLUR_TH);
-        if (t < nt) break;
-        t -= nt;
-    }
-    if (l >= plan.nlevels) return;
+    if ((int)blockIdx.x >= plan.blurTiles) return;
+    const unsigned te = __ldg(plan.blurTileTab + blockIdx.x);  // level | tile row << 4 | tile column << 18
+    const int l = (int)(te & 15u), ty = (int)((te >> 4) & 0x3fffu), tx = (int)(te >> 18);
     const OrbLevel& L = plan.lv[l];
-    const int ty = t / tilesX, tx = t - ty * tilesX;
     const int x0 = tx * BLUR_TW, y0 = ty * BLUR_TH;
     const int tid = threadIdx.x;
     const int rowsHere = min(BLUR_TH, L.rows - y0) + 6;
@@ -1191,13 +1177,17 @@ __global__ void __launch_bounds__(BLUR_THREADS) k_blur(const __grid_constant__ O
     const bool rowFix = y0 == 0 || y0 - 3 + rowsHere > L.rows;
     const bool colFix = x0 == 0 || x0 + BLUR_TW + 3 > L.cols;
     if (rowFix) {  // rows above / below the image <- their mirror rows (inside the tile: at most 3 rows away from the edge)
-        for (int i = tid; i < rowsHere * BLUR_SW; i += BLUR_THREADS) {
-            const int r = i >> 6, w = i & 63;
-            const int yy = y0 - 3 + r;
-            if (yy < 0 || yy >= L.rows) {
-                const int rs = reflect101(yy, L.rows) - (y0 - 3);
-                if (rs >= 0 && rs < BLUR_BOX_H) tile[r][w] = tile[rs][w];
-            }
+        // only the rows outside the image are visited: box rows 0..2 of the top tiles (level rows -3..-1) and the box rows
+        // from firstBot on (level rows >= L.rows) of the bottom tiles
+        const int nTop = y0 == 0 ? 3 : 0;
+        const int firstBot = max(L.rows - (y0 - 3), nTop);
+        const int nFix = nTop + max(0, rowsHere - firstBot);
+        static_assert(BLUR_SW == 64, "row index by shift");
+        for (int i = tid; i < nFix * BLUR_SW; i += BLUR_THREADS) {
+            const int k = i >> 6, w = i & 63;
+            const int r = k < nTop ? k : firstBot + (k - nTop);
+            const int rs = reflect101(y0 - 3 + r, L.rows) - (y0 - 3);
+            if (rs >= 0 && rs < BLUR_BOX_H) tile[r][w] = tile[rs][w];
         }
         __syncthreads();
     }
@@ -1410,15 +1400,9 @@ __global__ void __launch_bounds__(DSC_THREADS, 4) k_describe_tile(const __grid_c
         for (int i = 0; i < plan.nlevels; ++i) tot += kc[i];
         counts[f] = tot;
     }
-    int tile = blockIdx.x, s = 0;
-    for (; s < plan.nlevels; ++s) {
-        const OrbLevel& L = plan.lv[s];
-        if (L.src == s && tile >= L.dTileBase && tile < L.dTileBase + L.dTiles) break;
-    }
-    if (s >= plan.nlevels) return;
-    const OrbLevel& S = plan.lv[s];
-    tile -= S.dTileBase;
-    const int ty = tile / S.dTilesX, tx = tile - ty * S.dTilesX;
+    if ((int)blockIdx.x >= plan.totalDescTiles) return;
+    const unsigned te = __ldg(plan.descTileTab + blockIdx.x);  // source level | tile row << 4 | tile column << 18
+    const int s = (int)(te & 15u), ty = (int)((te >> 4) & 0x3fffu), tx = (int)(te >> 18);
     const int bx0 = DSC_W * tx, by0 = 1 + DSC_H * ty;            // level pixel of box byte (0, 0)
     const unsigned xlo = ORB_EDGE + DSC_W * tx, ylo = ORB_EDGE + DSC_H * ty;  // core: [xlo, xlo + DSC_W) x [ylo, ylo + DSC_H)
 
@@ -1861,10 +1845,7 @@ cudaError_t orbk_run_extract(const OrbPlan& plan, int nframes, orb_keypoint_dev*
         ++g_launches;
     }
     if (ev) cudaEventRecord(ev[1], st);
-    int blurTiles = 0;
-    for (int l = 0; l < plan.nlevels; ++l)
-        if (plan.lv[l].src == l)
-            blurTiles += ((plan.lv[l].cols + BLUR_TW - 1) / BLUR_TW) * ((plan.lv[l].rows + BLUR_TH - 1) / BLUR_TH);
+    const int blurTiles = plan.blurTiles;
     if (!ev) {
         // the blur needs only the pyramid and overlaps detect + octree on the second stream
         if (split) {

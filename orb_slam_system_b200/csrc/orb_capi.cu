@@ -432,6 +432,31 @@ static int build_plan(orb_extractor* h, int rows, int cols) {
         if (P.lv[l].src == l && P.lv[l].nTiles > 0) P.detRows = std::max(P.detRows, P.lv[l].boxH);
     if (P.detRows > DET_TILE_H) return fail(ORB_ERR_SHAPE, "detect tile of %d rows exceeds %d", P.detRows, DET_TILE_H);
     P.totalKmax = keptBase;
+    {
+        // tile tables of the detect / blur / describe launches (same tile order as the launches' tile ids)
+        auto pack = [](int l, int ty, int tx) { return (unsigned)l | ((unsigned)ty << 4) | ((unsigned)tx << 18); };
+        std::vector<unsigned> det, blr, dsc;
+        for (int l = 0; l < P.nlevels; ++l) {
+            const OrbLevel& L = P.lv[l];
+            if (L.src != l) continue;
+            for (int t = 0; t < L.nTiles; ++t) det.push_back(pack(l, t / L.tilesX, t % L.tilesX));
+            const int bx = (L.cols + BLUR_TW - 1) / BLUR_TW, by = (L.rows + BLUR_TH - 1) / BLUR_TH;
+            for (int t = 0; t < bx * by; ++t) blr.push_back(pack(l, t / bx, t % bx));
+            for (int t = 0; t < L.dTiles; ++t) dsc.push_back(pack(l, t / L.dTilesX, t % L.dTilesX));
+        }
+        if ((int)det.size() != P.totalTiles || (int)dsc.size() != P.totalDescTiles) return fail(ORB_ERR_INVALID, "tile table mismatch");
+        P.blurTiles = (int)blr.size();
+        unsigned *dDet, *dBlr, *dDsc;
+        CUDA_TRY(dev_alloc(h, &dDet, det.size() + 1));
+        CUDA_TRY(dev_alloc(h, &dBlr, blr.size() + 1));
+        CUDA_TRY(dev_alloc(h, &dDsc, dsc.size() + 1));
+        if (!det.empty()) CUDA_TRY(cudaMemcpy(dDet, det.data(), det.size() * 4, cudaMemcpyHostToDevice));
+        if (!blr.empty()) CUDA_TRY(cudaMemcpy(dBlr, blr.data(), blr.size() * 4, cudaMemcpyHostToDevice));
+        if (!dsc.empty()) CUDA_TRY(cudaMemcpy(dDsc, dsc.data(), dsc.size() * 4, cudaMemcpyHostToDevice));
+        P.detTileTab = dDet;
+        P.blurTileTab = dBlr;
+        P.descTileTab = dDsc;
+    }
     CUDA_TRY(dev_alloc(h, &P.candCount, (size_t)B * ORB_MAX_LEVELS));
     CUDA_TRY(dev_alloc(h, &P.keptCount, (size_t)B * ORB_MAX_LEVELS));
     CUDA_TRY(dev_alloc(h, &P.status, (size_t)B));

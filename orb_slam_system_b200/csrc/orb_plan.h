@@ -100,6 +100,12 @@ struct OrbPlan {
     int* keptCount;          // [batch][ORB_MAX_LEVELS]
     int* status;             // [batch] octree status flags (non-zero: unseparable keys)
     int* needGeneric;        // [batch][ORB_MAX_LEVELS] problems the table-based octree handed over
+    // tile id -> (level, tile row, tile column) of the detect / blur / describe launches, packed level | row << 4 | col << 18:
+    // one load instead of every thread of every CTA walking the level table
+    const unsigned* detTileTab;   // [totalTiles]
+    const unsigned* blurTileTab;  // [blurTiles]
+    const unsigned* descTileTab;  // [totalDescTiles]
+    int blurTiles;           // blur tiles per frame
     const int2* icTab;       // [8][32] IC_Angle dp4a weights: step it, lane (row it*4 + lane/8, word lane%8)
     const float4* pairTab;   // [182] rBRIEF test pairs (x0, y0, x1, y1)
     OrbLevel lv[ORB_MAX_LEVELS];
