@@ -652,6 +652,230 @@ __global__ void __launch_bounds__(M2_THREADS(EW), 1) k_match_mma2(const uint8_t*
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// k_match_mma3: k_match_mma2 made persistent.  One CTA per SM walks the work items (pair, block of 256 queries) with
+// stride gridDim.x; the three roles keep running barrier counters across the items, the two A tiles of the NEXT item
+// are expanded into a second A buffer while the MMAs of the current one still read the first, and the TMEM allocation,
+// the barrier set-up and the fill / drain of the pipeline are paid once per CTA instead of once per 256 queries.
+// Shared memory: 2 x 64 KB of A, 3 x 32 KB of B = 224 KB + barriers.
+// ------------------------------------------------------------------------------------------
+#define M3_EW 8
+#define M3_THREADS ((M3_EW + M2_PROD_WARPS + 1) * 32)
+#define M3_STAGES 3
+#define M3_OFF_B (4 * MM_TILE_BYTES)
+#define M3_OFF_BAR (M3_OFF_B + M3_STAGES * MM_TILE_BYTES)  // full[3], empty[3], tfull[2], tempty[2], afull[2], aempty[2]
+#define M3_OFF_TMEM (M3_OFF_BAR + 14 * 8)
+#define M3_OFF_FLAGS (M3_OFF_TMEM + 8)
+#define M3_SMEM (M3_OFF_FLAGS + 32)
+
+template <int KIND>
+__global__ void __launch_bounds__(M3_THREADS, 1) k_match_mma3(const uint8_t* __restrict__ q, const int* __restrict__ nq, size_t q_stride,
+                                                              const uint8_t* __restrict__ t, const int* __restrict__ nt, size_t t_stride,
+                                                              int* __restrict__ best_idx, int* __restrict__ best_dist,
+                                                              int* __restrict__ second_dist, size_t out_stride, int npairs, int qblocks,
+                                                              MmParams prm) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const unsigned sA = mm_smem_u32(smem);
+    const unsigned bFull = sA + M3_OFF_BAR, bEmpty = bFull + 8 * M3_STAGES, bTfull = bEmpty + 8 * M3_STAGES, bTempty = bTfull + 16,
+                   bAfull = bTempty + 16, bAempty = bAfull + 16;
+    unsigned* tmem_slot = reinterpret_cast<unsigned*>(smem + M3_OFF_TMEM);
+    volatile int* flags = reinterpret_cast<volatile int*>(smem + M3_OFF_FLAGS);
+    const int nitems = npairs * qblocks;
+
+    if (warp == M3_EW + M2_PROD_WARPS) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(mm_smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 0) {
+        for (int s = 0; s < M3_STAGES; ++s) {
+            mm_mbar_init(bFull + 8 * s, M2_PROD_WARPS * 32);
+            mm_mbar_init(bEmpty + 8 * s, 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mm_mbar_init(bTfull + 8 * a, 1);
+            mm_mbar_init(bTempty + 8 * a, M3_EW);
+            mm_mbar_init(bAfull + 8 * a, M2_PROD_WARPS * 32);
+            mm_mbar_init(bAempty + 8 * a, 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    mm_fence_before();
+    __syncthreads();
+    mm_fence_after();
+    const unsigned tmem = *tmem_slot;
+
+    // every role enumerates the same work items and skips the same ones
+#define M3_FOR_ITEMS                                                            \
+    for (int it = blockIdx.x; it < nitems; it += gridDim.x) {                   \
+        const int p = it / qblocks, q0 = (it - p * qblocks) * 2 * MM_M;          \
+        const int nQ = nq[p], nT = nt[p];                                       \
+        if (q0 >= nQ || nT >= (1 << 22)) continue;                              \
+        const int ntiles = (nT + MM_N - 1) / MM_N;                              \
+        const uint4* Q = reinterpret_cast<const uint4*>(q + p * q_stride);      \
+        const uint4* T = reinterpret_cast<const uint4*>(t + p * t_stride);      \
+        (void)Q;                                                                \
+        (void)T;
+
+    if (warp < M3_EW) {
+        // ---------------- epilogue: one query row per thread ----------------
+        const int tileA = warp >> 2;
+        const unsigned trow = tmem + ((unsigned)(warp & 3) << 21) + (unsigned)(tileA * MM_N);
+        unsigned acount = 0;  // accumulator tiles consumed so far (stage = acount & 1, phase = (acount >> 1) & 1)
+        M3_FOR_ITEMS
+            unsigned bestk = 0xffffffffu, seck = 0xffffffffu;
+            auto merge = [&](unsigned b2, unsigned s2, int slab) {
+                const unsigned kb = (b2 & 0xffc0003fu) | ((unsigned)slab << 6);
+                const unsigned mx = max(kb, bestk);
+                seck = min(seck, min(mx, s2));
+                bestk = min(bestk, kb);
+            };
+            unsigned acc0[32], acc1[32];
+            if (ntiles > 0) {
+                mm_mbar_wait(bTfull + 8 * (acount & 1u), (acount >> 1) & 1u);
+                mm_fence_after();
+                const unsigned ta = trow + (acount & 1u) * 2 * MM_N;
+                mm_tmem_ld32(ta, acc0);
+                mm_tmem_ld32(ta + 32, acc1);
+            }
+            for (int tt = 0; tt < ntiles; ++tt) {
+                const unsigned a = acount & 1u;
+                const unsigned ta = trow + a * 2 * MM_N;
+                unsigned P[32], b2, s2;
+                mm_tmem_ld_wait();
+                mm_slab_keys<KIND>(acc0, acc1, prm, nT - tt * MM_N, P);
+                mm_tmem_ld32(ta + 64, acc0);
+                mm_tmem_ld32(ta + 96, acc1);
+                mm_tournament(P, b2, s2);
+                merge(b2, s2, tt * 2);
+                mm_tmem_ld_wait();
+                mm_fence_before();
+                __syncwarp();
+                if (lane == 0) mm_mbar_arrive(bTempty + 8 * a);
+                mm_slab_keys<KIND>(acc0, acc1, prm, nT - tt * MM_N - 64, P);
+                ++acount;
+                if (tt + 1 < ntiles) {
+                    mm_mbar_wait(bTfull + 8 * (acount & 1u), (acount >> 1) & 1u);
+                    mm_fence_after();
+                    const unsigned tn = trow + (acount & 1u) * 2 * MM_N;
+                    mm_tmem_ld32(tn, acc0);
+                    mm_tmem_ld32(tn + 32, acc1);
+                }
+                mm_tournament(P, b2, s2);
+                merge(b2, s2, tt * 2 + 1);
+            }
+            const int qi = q0 + tileA * MM_M + (warp & 3) * 32 + lane;
+            if (qi < nQ) {
+                const uint4 a0 = __ldg(Q + 2 * (size_t)qi), a1 = __ldg(Q + 2 * (size_t)qi + 1);
+                const int na = __popc(a0.x) + __popc(a0.y) + __popc(a0.z) + __popc(a0.w) + __popc(a1.x) + __popc(a1.y) + __popc(a1.z) + __popc(a1.w);
+                int idx = -1, bd = INT_MAX, sd = INT_MAX;
+                if ((bestk >> 22) <= 512u) {
+                    idx = (int)(bestk & 0x3fffffu);
+                    bd = (int)(bestk >> 22) - 256 + na;
+                }
+                if ((seck >> 22) <= 512u) sd = (int)(seck >> 22) - 256 + na;
+                best_idx[p * out_stride + qi] = idx;
+                best_dist[p * out_stride + qi] = bd;
+                second_dist[p * out_stride + qi] = sd;
+            }
+        }
+        mm_fence_before();
+    } else if (warp < M3_EW + M2_PROD_WARPS) {
+        // ---------------- producers ----------------
+        const int r = tid - M3_EW * 32;
+        unsigned tcount = 0, icount = 0;  // B tiles / A buffers produced so far
+        M3_FOR_ITEMS
+            if (ntiles == 0) continue;
+            uint4 n0 = make_uint4(0, 0, 0, 0), n1 = n0;
+            if (r < nT) {
+                n0 = __ldg(T + 2 * (size_t)r);
+                n1 = __ldg(T + 2 * (size_t)r + 1);
+            }
+            // the item's two A tiles (256 query rows x 2 halves, +-1 bytes) into the A buffer the MMAs of item - 2 have left
+            const unsigned ab = icount & 1u;
+            mm_mbar_wait(bAempty + 8 * ab, ((icount >> 1) & 1u) ^ 1u);
+            uint8_t* bufA = smem + ab * 2 * MM_TILE_BYTES;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int j = r + 128 * k;
+                const int er = (j & 7) | ((j >> 4) << 3), ehf = (j >> 3) & 1;
+                const int row = q0 + er;
+                uint4 v = make_uint4(0, 0, 0, 0);
+                if (row < nQ) v = __ldg(Q + 2 * (size_t)row + ehf);
+                mm_expand_half_row(bufA + (er >> 7) * MM_TILE_BYTES, er & 127, ehf, v, prm.lut_a, 4);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mm_mbar_arrive(bAfull + 8 * ab);
+            ++icount;
+            for (int tt = 0; tt < ntiles; ++tt) {
+                const unsigned s = tcount % M3_STAGES;
+                const uint4 v0 = n0, v1 = n1;
+                {
+                    const int row = (tt + 1) * MM_N + r;
+                    n0 = n1 = make_uint4(0, 0, 0, 0);
+                    if (row < nT) {
+                        n0 = __ldg(T + 2 * (size_t)row);
+                        n1 = __ldg(T + 2 * (size_t)row + 1);
+                    }
+                }
+                unsigned upper;
+                asm volatile(
+                    "{\n.reg .pred p, q;\nsetp.ne.u32 p, %1, 0;\nbar.red.or.pred q, 1, %2, p;\nselp.u32 %0, 1, 0, q;\n}\n"
+                    : "=r"(upper)
+                    : "r"(v1.z | v1.w), "n"(M2_PROD_WARPS * 32)
+                    : "memory");
+                mm_mbar_wait(bEmpty + 8 * s, ((tcount / M3_STAGES) & 1u) ^ 1u);
+                uint8_t* tileB = smem + M3_OFF_B + s * MM_TILE_BYTES;
+                mm_expand_half_row(tileB, r, 0, v0, prm.lut_b, 4);
+                mm_expand_half_row(tileB, r, 1, v1, prm.lut_b, upper ? 4 : 2);
+                if (r == 0) flags[s] = (int)upper;
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mm_mbar_arrive(bFull + 8 * s);
+                ++tcount;
+            }
+        }
+    } else if (lane == 0) {
+        // ---------------- MMA issuer ----------------
+        unsigned tcount = 0, acount = 0, icount = 0;
+        M3_FOR_ITEMS
+            if (ntiles == 0) continue;
+            const unsigned ab = icount & 1u;
+            mm_mbar_wait(bAfull + 8 * ab, (icount >> 1) & 1u);
+            const unsigned long long dA0 = prm.desc_base | (unsigned long long)(((sA + ab * 2 * MM_TILE_BYTES) & 0x3ffffu) >> 4);
+            const unsigned long long dA1 = prm.desc_base | (unsigned long long)(((sA + ab * 2 * MM_TILE_BYTES + MM_TILE_BYTES) & 0x3ffffu) >> 4);
+            for (int tt = 0; tt < ntiles; ++tt) {
+                const unsigned s = tcount % M3_STAGES, a = acount & 1u;
+                mm_mbar_wait(bFull + 8 * s, (tcount / M3_STAGES) & 1u);
+                mm_mbar_wait(bTempty + 8 * a, ((acount >> 1) & 1u) ^ 1u);
+                mm_fence_after();
+                const unsigned long long dB = prm.desc_base | (unsigned long long)(((sA + M3_OFF_B + s * MM_TILE_BYTES) & 0x3ffffu) >> 4);
+                const int ksteps = flags[s] ? 8 : 6;
+                const unsigned d0 = tmem + a * 2 * MM_N;
+                for (int k = 0; k < ksteps; ++k) {
+                    const unsigned long long o = (unsigned long long)((k * 2 * MM_LBO) >> 4);
+                    mm_mma<KIND>(d0, dA0 + o, dB + o, prm.idesc, k > 0 ? 1u : 0u);
+                }
+                for (int k = 0; k < ksteps; ++k) {
+                    const unsigned long long o = (unsigned long long)((k * 2 * MM_LBO) >> 4);
+                    mm_mma<KIND>(d0 + MM_N, dA1 + o, dB + o, prm.idesc, k > 0 ? 1u : 0u);
+                }
+                mm_commit(bEmpty + 8 * s);
+                mm_commit(bTfull + 8 * a);
+                ++tcount;
+                ++acount;
+            }
+            mm_commit(bAempty + 8 * ab);  // this A buffer is free once the MMAs issued so far have completed
+            ++icount;
+        }
+    }
+#undef M3_FOR_ITEMS
+    __syncthreads();
+    if (warp == M3_EW + M2_PROD_WARPS) {
+        mm_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+    }
+}
+
 // Train sets the tensor-core kernel leaves alone (2^22 rows and more): k_match_all's plain path, see match_kernels.cu.
 cudaError_t orbk_match_all_popc(const uint8_t* q, const int* nq, size_t q_stride, const uint8_t* t, const int* nt, size_t t_stride,
                                 int npairs, int max_nq, int* best_idx, int* best_dist, int* second_dist, size_t out_stride,
@@ -663,6 +887,10 @@ cudaError_t orbk_match_mma_init() {
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_match_mma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, MM_SMEM);
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_match_mma3<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, M3_SMEM);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_match_mma3<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, M3_SMEM);
+    if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_match_mma2<0, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, M2_SMEM);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_match_mma2<0, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, M2_SMEM);
@@ -672,9 +900,10 @@ cudaError_t orbk_match_mma_init() {
     return cudaFuncSetAttribute(k_match_mma2<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, M2_SMEM);
 }
 
-// kind: 0 = kind::i8, 1 = kind::f8f6f4 (e4m3).  variant: 0 = the warp-specialised kernel (8 epilogue warps) with the documented
-// encoding; 10 = the first form of the kernel (k_match_mma); 20 = warp-specialised with 16 epilogue warps; 1 / 2 (11 / 12)
-// exist for tools/probes/mma_probe.py only (leading / stride byte offsets swapped, descriptor version bits clear).
+// kind: 0 = kind::i8, 1 = kind::f8f6f4 (e4m3).  variant: 0 = the persistent warp-specialised kernel (k_match_mma3) with the
+// documented encoding; comparators: 10 = the first form of the kernel (k_match_mma), 20 = warp-specialised, one CTA per 256
+// queries, 16 epilogue warps, 30 = the same with 8 epilogue warps; 1 / 2 (11 / 12) exist for tools/probes/mma_probe.py only
+// (leading / stride byte offsets swapped, descriptor version bits clear).
 cudaError_t orbk_match_all_mma(const uint8_t* q, const int* nq, size_t q_stride, const uint8_t* t, const int* nt, size_t t_stride,
                                int npairs, int max_nq, int* best_idx, int* best_dist, int* second_dist, size_t out_stride, int kind,
                                int variant, cudaStream_t st) {
@@ -699,7 +928,23 @@ cudaError_t orbk_match_all_mma(const uint8_t* q, const int* nq, size_t q_stride,
         prm.lut_a = 0x000038b8u;        // e4m3: 0xb8 = -1.0, 0x38 = +1.0
         prm.lut_b = 0x00003800u;
     }
-    if (variant >= 10 && variant < 20) {  // the first form of the kernel (2 CTAs per SM, block barriers): kept as a comparator
+    if (variant < 10) {  // one CTA per SM walks the (pair, 256 queries) items
+        static int smsOf[64];
+        int dev = 0;
+        cudaGetDevice(&dev);
+        int sms = dev < 64 ? smsOf[dev] : 0;
+        if (sms == 0) {
+            if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+            if (dev < 64) smsOf[dev] = sms;
+        }
+        const int qblocks = (max_nq + 2 * MM_M - 1) / (2 * MM_M);
+        const long long nitems = (long long)npairs * qblocks;
+        const int grid = (int)(nitems < sms ? nitems : sms);
+        if (kind == 0)
+            k_match_mma3<0><<<grid, M3_THREADS, M3_SMEM, st>>>(q, nq, q_stride, t, nt, t_stride, best_idx, best_dist, second_dist, out_stride, npairs, qblocks, prm);
+        else
+            k_match_mma3<1><<<grid, M3_THREADS, M3_SMEM, st>>>(q, nq, q_stride, t, nt, t_stride, best_idx, best_dist, second_dist, out_stride, npairs, qblocks, prm);
+    } else if (variant >= 10 && variant < 20) {  // the first form of the kernel (2 CTAs per SM, block barriers): kept as a comparator
         dim3 grid((max_nq + MM_M - 1) / MM_M, npairs);
         if (kind == 0)
             k_match_mma<0><<<grid, MM_THREADS, MM_SMEM, st>>>(q, nq, q_stride, t, nt, t_stride, best_idx, best_dist, second_dist, out_stride, prm);
@@ -707,7 +952,7 @@ cudaError_t orbk_match_all_mma(const uint8_t* q, const int* nq, size_t q_stride,
             k_match_mma<1><<<grid, MM_THREADS, MM_SMEM, st>>>(q, nq, q_stride, t, nt, t_stride, best_idx, best_dist, second_dist, out_stride, prm);
     } else {
         dim3 grid((max_nq + 2 * MM_M - 1) / (2 * MM_M), npairs);
-        const bool e8 = variant < 20;  // 20: sixteen epilogue warps (two threads per query row): measured slower, kept as a comparator
+        const bool e8 = variant >= 30;  // 20: sixteen epilogue warps (two threads per query row): measured slower still
         if (kind == 0 && !e8)
             k_match_mma2<0, 16><<<grid, M2_THREADS(16), M2_SMEM, st>>>(q, nq, q_stride, t, nt, t_stride, best_idx, best_dist, second_dist, out_stride, prm);
         else if (kind == 0)

@@ -53,6 +53,36 @@ def test_match_all_batch_ragged():
     m.close()
 
 
+def test_match_all_batch_many_items_per_cta(monkeypatch):
+    """More (pair, 256-query) items than SMs, ragged and empty pairs in between: the persistent kernel's running barrier
+    phases, A-buffer hand-over and skipped items, against the popcount kernel on every pair and the oracle on a few."""
+    rng = np.random.default_rng(11)
+    P, Q, T = 230, 600, 700
+    nq = rng.integers(0, Q + 1, P).astype(np.int32)
+    nt = rng.integers(0, T + 1, P).astype(np.int32)
+    nq[[3, 77]] = 0
+    nt[[5, 78, 200]] = 0
+    nq[[9, 100]] = Q
+    nt[[9, 101]] = T
+    nt[[10, 150]] = [1, 129]
+    t = rand_desc(rng, T, 182)[rng.integers(0, T, (P, T))]
+    q = rand_desc(rng, Q, 182)[rng.integers(0, Q, (P, Q))]
+    q[:, ::3] = t[:, :Q:3]  # exact hits and, through the repeated rows, ties
+    m = ORBmatcher()
+    monkeypatch.setenv("ORB_B200_MATCH", "mma")
+    got = m.match_all_batch(q, nq, t, nt)
+    monkeypatch.setenv("ORB_B200_MATCH", "popc")
+    want = m.match_all_batch(q, nq, t, nt)
+    for p in range(P):
+        for g, w in zip(got, want):
+            assert (g[p, :nq[p]] == w[p, :nq[p]]).all(), p
+    for p in (0, 9, 10, 78, 150, 229):
+        o = oracle.match_all(q[p, :nq[p]], t[p, :nt[p]])
+        for g, w in zip(got, o):
+            assert (g[p, :nq[p]] == w).all(), p
+    m.close()
+
+
 @pytest.mark.parametrize("tie_last", [False, True])
 def test_match_csr(tie_last):
     rng = np.random.default_rng(11 + tie_last)
