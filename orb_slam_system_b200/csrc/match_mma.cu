@@ -66,6 +66,23 @@ __device__ __forceinline__ void mm_mbar_wait(unsigned bar, unsigned parity) {
         if (spins > (1u << 24)) __trap();
     }
 }
+// The same with a suspend-time hint (nanoseconds): the roles that run ahead of the bottleneck park in the barrier unit instead
+// of re-issuing the poll, which would take issue slots from the epilogue warps on their scheduler.
+__device__ __forceinline__ void mm_mbar_wait_parked(unsigned bar, unsigned parity, unsigned hint_ns) {
+    unsigned done = 0;
+    for (unsigned spins = 0; !done; ++spins) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(bar), "r"(parity), "r"(hint_ns)
+            : "memory");
+        if (spins > (1u << 24)) __trap();
+    }
+}
 __device__ __forceinline__ void mm_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void mm_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -83,6 +100,26 @@ __device__ __forceinline__ void mm_mma(unsigned tmem_d, unsigned long long adesc
             "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
             "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
             : "memory");
+}
+// The same with the descriptors' words apart: only the low word (start address, leading byte offset) changes from K-step to
+// K-step and from stage to stage, so the issuing thread keeps 32-bit values and no 64-bit arithmetic between two MMAs.
+template <int KIND, int ACC>
+__device__ __forceinline__ void mm_mma_w(unsigned tmem_d, unsigned alo, unsigned blo, unsigned hi, unsigned idesc) {
+    if (KIND == 0)
+        asm volatile(
+            "{\n.reg .pred p;\n.reg .b64 da, db;\nsetp.ne.b32 p, %5, 0;\nmov.b64 da, {%1, %3};\nmov.b64 db, {%2, %3};\n"
+            "tcgen05.mma.cta_group::1.kind::i8 [%0], da, db, %4, p;\n}\n" ::"r"(tmem_d), "r"(alo), "r"(blo), "r"(hi), "r"(idesc), "n"(ACC)
+            : "memory");
+    else
+        asm volatile(
+            "{\n.reg .pred p;\n.reg .b64 da, db;\nsetp.ne.b32 p, %5, 0;\nmov.b64 da, {%1, %3};\nmov.b64 db, {%2, %3};\n"
+            "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], da, db, %4, p;\n}\n" ::"r"(tmem_d), "r"(alo), "r"(blo), "r"(hi), "r"(idesc), "n"(ACC)
+            : "memory");
+}
+__device__ __forceinline__ bool mm_elect_one() {
+    unsigned pred;
+    asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void mm_commit(unsigned bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -103,22 +140,39 @@ __device__ __forceinline__ void mm_tmem_ld32(unsigned taddr, unsigned (&r)[32]) 
 }
 __device__ __forceinline__ void mm_tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// One 32-bit descriptor word -> 32 bytes (two 16-byte K-chunks), one byte per bit: byte = lut.byte[bit].
-// (w >> m) & 0x11111111 leaves bit 4n + m in nibble n; PRMT takes its selectors from the low four nibbles.
-__device__ __forceinline__ void mm_expand_word(unsigned w, unsigned lut, uint4& c0, uint4& c1) {
-    const unsigned m0 = w & 0x11111111u, m1 = (w >> 1) & 0x11111111u, m2 = (w >> 2) & 0x11111111u, m3 = (w >> 3) & 0x11111111u;
-    c0.x = __byte_perm(lut, 0u, m0);
-    c0.y = __byte_perm(lut, 0u, m1);
-    c0.z = __byte_perm(lut, 0u, m2);
-    c0.w = __byte_perm(lut, 0u, m3);
-    c1.x = __byte_perm(lut, 0u, m0 >> 16);
-    c1.y = __byte_perm(lut, 0u, m1 >> 16);
-    c1.z = __byte_perm(lut, 0u, m2 >> 16);
-    c1.w = __byte_perm(lut, 0u, m3 >> 16);
+// One 32-bit descriptor word -> 32 bytes (two 16-byte K-chunks), one byte per bit.  PRMT reads four selector nibbles from
+// the low 16 bits of its third operand; a nibble's low three bits pick one of the eight bytes of (a, b) and its top bit asks
+// for sign replication.  With the top bits cleared (w & 0x77777777) the tables {v0 v1 v0 v1 | v0 v1 v0 v1}, {v0 v0 v1 v1 | ...}
+// and {v0 v0 v0 v0 | v1 v1 v1 v1} read bit 0, 1 and 2 of every nibble without isolating it first; bit 3 is bit 2 of w >> 1.
+// 13 integer instructions per word (2 LOP3, 3 SHF, 8 PRMT).  Byte j of c0 / c1 is NOT bit j: queries and train rows go through
+// the same permutation of the K positions, which a dot product does not see.
+struct MmLut {
+    unsigned t0, t1, t2a, t2b;
+};
+__device__ __forceinline__ MmLut mm_lut(unsigned lut) {
+    MmLut L;
+    L.t0 = __byte_perm(lut, 0u, 0x1010);
+    L.t1 = __byte_perm(lut, 0u, 0x1100);
+    L.t2a = __byte_perm(lut, 0u, 0x0000);
+    L.t2b = __byte_perm(lut, 0u, 0x1111);
+    return L;
+}
+__device__ __forceinline__ void mm_expand_word(unsigned w, const MmLut& L, uint4& c0, uint4& c1) {
+    const unsigned x = w & 0x77777777u, y = (w >> 1) & 0x77777777u;
+    const unsigned xh = x >> 16, yh = y >> 16;
+    c0.x = __byte_perm(L.t0, L.t0, x);
+    c0.y = __byte_perm(L.t1, L.t1, x);
+    c0.z = __byte_perm(L.t2a, L.t2b, x);
+    c0.w = __byte_perm(L.t2a, L.t2b, y);
+    c1.x = __byte_perm(L.t0, L.t0, xh);
+    c1.y = __byte_perm(L.t1, L.t1, xh);
+    c1.z = __byte_perm(L.t2a, L.t2b, xh);
+    c1.w = __byte_perm(L.t2a, L.t2b, yh);
 }
 
 // words [w0, w0 + nw) of one row into its place of a tile: row r, K-chunk kc at (r / 8) * SBO + kc * LBO + (r % 8) * 16
-__device__ __forceinline__ void mm_expand_half_row(uint8_t* tile, int r, int hf, const uint4& v, unsigned lut, int nw) {
+__device__ __forceinline__ void mm_expand_half_row(uint8_t* tile, int r, int hf, const uint4& v, unsigned lut_bytes, int nw) {
+    const MmLut lut = mm_lut(lut_bytes);
     uint8_t* base = tile + (r >> 3) * MM_SBO + (r & 7) * 16 + hf * 8 * MM_LBO;
     const unsigned w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
@@ -138,6 +192,7 @@ struct MmParams {
     unsigned idesc;                // tcgen05 instruction descriptor (M = 128, N = 128, K-major A and B)
     unsigned long long desc_base;  // shared-memory matrix descriptor without its start address
     unsigned lut_a, lut_b;         // byte values of a query bit (0, 1) / of a train bit (0, 1)
+    unsigned park_ns;              // suspend-time hint of the producer / MMA waits (0: plain polling)
 };
 
 template <int KIND>
@@ -346,6 +401,30 @@ __device__ __forceinline__ void mm_slab_keys(unsigned (&acc0)[32], unsigned (&ac
     }
 }
 
+// The same result in two passes, 0.9 instead of 1.3 ALU-pipe instructions per key pair.  Pass 1: lane-wise minimum M of the
+// 32 words (VIMNMX3).  Pass 2: lane-wise minimum of key + ~M (16-bit wrap-around add, done by VIADDMNMX together with the
+// running minimum): the lane's own minimum becomes 0xffff and drops out -- keys of a lane are distinct, except for the
+// 0xffff of masked columns, which can only be the minimum when the whole lane is masked -- and every other key becomes
+// key - M - 1 >= 0, order kept.  The lane's second key is that minimum + M + 1, again with wrap-around adds (all-masked lane:
+// 0xffff + 0xffff + 1 = 0xffff).
+__device__ __forceinline__ void mm_min2(const unsigned (&P)[32], unsigned& b2, unsigned& s2) {
+    unsigned m[11];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) m[i] = __vimin3_u16x2(P[3 * i], P[3 * i + 1], P[3 * i + 2]);
+    m[10] = __vminu2(P[30], P[31]);
+    const unsigned m0 = __vimin3_u16x2(m[0], m[1], m[2]), m1 = __vimin3_u16x2(m[3], m[4], m[5]), m2 = __vimin3_u16x2(m[6], m[7], m[8]);
+    const unsigned M = __vminu2(__vimin3_u16x2(m0, m1, m2), __vminu2(m[9], m[10]));
+    const unsigned nM = ~M;
+    unsigned R[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+#pragma unroll
+    for (int i = 0; i < 32; ++i) R[i & 3] = __viaddmin_u16x2(P[i], nM, R[i & 3]);
+    const unsigned r = __vminu2(__vimin3_u16x2(R[0], R[1], R[2]), R[3]);
+    const unsigned S = __viaddmin_u16x2(__viaddmin_u16x2(r, M, 0xffffffffu), 0x00010001u, 0xffffffffu);
+    const unsigned bs = __byte_perm(M, 0u, 0x1032), ss = __byte_perm(S, 0u, 0x1032);
+    b2 = __vminu2(M, bs);
+    s2 = __vimin3_u16x2(__vmaxu2(M, bs), S, ss);
+}
+
 // min / second-min tournament over 32 packed key pairs; both halves of b2 / s2 hold the slab's best / second 16-bit key
 __device__ __forceinline__ void mm_tournament(const unsigned (&P)[32], unsigned& b2, unsigned& s2) {
     unsigned lo[16], hi[16];
@@ -367,6 +446,26 @@ __device__ __forceinline__ void mm_tournament(const unsigned (&P)[32], unsigned&
     const unsigned bs = __byte_perm(lo[0], 0u, 0x1032), ss = __byte_perm(hi[0], 0u, 0x1032);
     b2 = __vminu2(lo[0], bs);
     s2 = __vimin3_u16x2(__vmaxu2(lo[0], bs), hi[0], ss);
+}
+
+// mm_unit_keys in two parts, so that a caller can put other straight-line work between the arithmetic and the (rare) masking
+template <int KIND>
+__device__ __forceinline__ void mm_unit_keys_raw(unsigned (&acc)[32], const MmParams& prm, unsigned (&P)[16]) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        if (KIND == 1) {
+            acc[i] = __float_as_uint(__fadd_rn(__uint_as_float(acc[i]), 12582912.0f)) - 0x4B400000u;
+            acc[i + 16] = __float_as_uint(__fadd_rn(__uint_as_float(acc[i + 16]), 12582912.0f)) - 0x4B400000u;
+        }
+        const unsigned c = (256u * 64u + (unsigned)i) | ((256u * 64u + 16u + (unsigned)i) << 16);
+        P[i] = acc[i + 16] * prm.neg_hi + (acc[i] * prm.neg_lo + c);
+    }
+}
+__device__ __forceinline__ void mm_unit_mask(unsigned (&P)[16], int lim) {
+    if (lim < 32) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) P[i] |= (i < lim ? 0u : 0x0000ffffu) | (i + 16 < lim ? 0u : 0xffff0000u);
+    }
 }
 
 // 32 accumulator columns (one tcgen05.ld) -> 16 packed key pairs; low lane: column i, high lane: column 16 + i
@@ -668,7 +767,9 @@ __global__ void __launch_bounds__(M2_THREADS(EW), 1) k_match_mma2(const uint8_t*
 #define M3_OFF_FLAGS (M3_OFF_TMEM + 8)
 #define M3_SMEM (M3_OFF_FLAGS + 32)
 
-template <int KIND>
+// DBG (timing experiments, -DORB_B200_MMA_KNOCKOUT builds only): 1 = no tcgen05.mma issued, 2 = producers skip the expansion,
+// 4 = epilogue skips the key arithmetic, 8 = and the TMEM loads; the barrier traffic stays, the results are garbage.
+template <int KIND, int DBG>
 __global__ void __launch_bounds__(M3_THREADS, 1) k_match_mma3(const uint8_t* __restrict__ q, const int* __restrict__ nq, size_t q_stride,
                                                               const uint8_t* __restrict__ t, const int* __restrict__ nt, size_t t_stride,
                                                               int* __restrict__ best_idx, int* __restrict__ best_dist,
@@ -682,6 +783,16 @@ __global__ void __launch_bounds__(M3_THREADS, 1) k_match_mma3(const uint8_t* __r
     unsigned* tmem_slot = reinterpret_cast<unsigned*>(smem + M3_OFF_TMEM);
     volatile int* flags = reinterpret_cast<volatile int*>(smem + M3_OFF_FLAGS);
     const int nitems = npairs * qblocks;
+    // DBG & 16: CTA 0 writes clock() of its hand-over events into second_dist (role * 4 + event, 256 tiles each)
+    auto trace = [&](int slot, unsigned n) {
+        if ((DBG & 16) && blockIdx.x == 0 && n < 256u) second_dist[slot * 256 + n] = (int)clock();
+    };
+    auto wait_ahead = [&](unsigned bar, unsigned parity) {  // producers and the MMA thread: ahead of the epilogue most of the time
+        if (prm.park_ns)
+            mm_mbar_wait_parked(bar, parity, prm.park_ns);
+        else
+            mm_mbar_wait(bar, parity);
+    };
 
     if (warp == M3_EW + M2_PROD_WARPS) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(mm_smem_u32(tmem_slot)), "r"(512) : "memory");
@@ -743,26 +854,38 @@ __global__ void __launch_bounds__(M3_THREADS, 1) k_match_mma3(const uint8_t* __r
                 const unsigned ta = trow + a * 2 * MM_N;
                 unsigned P[32], b2, s2;
                 mm_tmem_ld_wait();
-                mm_slab_keys<KIND>(acc0, acc1, prm, nT - tt * MM_N, P);
-                mm_tmem_ld32(ta + 64, acc0);
-                mm_tmem_ld32(ta + 96, acc1);
-                mm_tournament(P, b2, s2);
-                merge(b2, s2, tt * 2);
+                if (!(DBG & 4)) mm_slab_keys<KIND>(acc0, acc1, prm, nT - tt * MM_N, P);
+                if (!(DBG & 8)) {
+                    mm_tmem_ld32(ta + 64, acc0);
+                    mm_tmem_ld32(ta + 96, acc1);
+                }
+                if (!(DBG & 4)) {
+                    mm_min2(P, b2, s2);
+                    merge(b2, s2, tt * 2);
+                }
                 mm_tmem_ld_wait();
                 mm_fence_before();
                 __syncwarp();
                 if (lane == 0) mm_mbar_arrive(bTempty + 8 * a);
-                mm_slab_keys<KIND>(acc0, acc1, prm, nT - tt * MM_N - 64, P);
+                if (tid == 0) trace(9, acount);
+                if (!(DBG & 4)) mm_slab_keys<KIND>(acc0, acc1, prm, nT - tt * MM_N - 64, P);
                 ++acount;
                 if (tt + 1 < ntiles) {
                     mm_mbar_wait(bTfull + 8 * (acount & 1u), (acount >> 1) & 1u);
+                    if (tid == 0) trace(8, acount);
                     mm_fence_after();
                     const unsigned tn = trow + (acount & 1u) * 2 * MM_N;
-                    mm_tmem_ld32(tn, acc0);
-                    mm_tmem_ld32(tn + 32, acc1);
+                    if (!(DBG & 8)) {
+                        mm_tmem_ld32(tn, acc0);
+                        mm_tmem_ld32(tn + 32, acc1);
+                    }
                 }
-                mm_tournament(P, b2, s2);
-                merge(b2, s2, tt * 2 + 1);
+                if (!(DBG & 4)) {
+                    mm_min2(P, b2, s2);
+                    merge(b2, s2, tt * 2 + 1);
+                } else {
+                    bestk ^= acc0[0] ^ acc1[31];
+                }
             }
             const int qi = q0 + tileA * MM_M + (warp & 3) * 32 + lane;
             if (qi < nQ) {
@@ -793,7 +916,7 @@ __global__ void __launch_bounds__(M3_THREADS, 1) k_match_mma3(const uint8_t* __r
             }
             // the item's two A tiles (256 query rows x 2 halves, +-1 bytes) into the A buffer the MMAs of item - 2 have left
             const unsigned ab = icount & 1u;
-            mm_mbar_wait(bAempty + 8 * ab, ((icount >> 1) & 1u) ^ 1u);
+            wait_ahead(bAempty + 8 * ab, ((icount >> 1) & 1u) ^ 1u);
             uint8_t* bufA = smem + ab * 2 * MM_TILE_BYTES;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -824,47 +947,66 @@ __global__ void __launch_bounds__(M3_THREADS, 1) k_match_mma3(const uint8_t* __r
                     : "=r"(upper)
                     : "r"(v1.z | v1.w), "n"(M2_PROD_WARPS * 32)
                     : "memory");
-                mm_mbar_wait(bEmpty + 8 * s, ((tcount / M3_STAGES) & 1u) ^ 1u);
+                if (r == 0) trace(0, tcount);
+                wait_ahead(bEmpty + 8 * s, ((tcount / M3_STAGES) & 1u) ^ 1u);
+                if (r == 0) trace(1, tcount);
                 uint8_t* tileB = smem + M3_OFF_B + s * MM_TILE_BYTES;
-                mm_expand_half_row(tileB, r, 0, v0, prm.lut_b, 4);
-                mm_expand_half_row(tileB, r, 1, v1, prm.lut_b, upper ? 4 : 2);
+                if (!(DBG & 2)) {
+                    mm_expand_half_row(tileB, r, 0, v0, prm.lut_b, 4);
+                    mm_expand_half_row(tileB, r, 1, v1, prm.lut_b, upper ? 4 : 2);
+                }
                 if (r == 0) flags[s] = (int)upper;
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 mm_mbar_arrive(bFull + 8 * s);
+                if (r == 0) trace(2, tcount);
                 ++tcount;
             }
         }
-    } else if (lane == 0) {
-        // ---------------- MMA issuer ----------------
+    } else {
+        // ---------------- MMA issuer: the whole warp walks the loop, one elected lane issues ----------------
         unsigned tcount = 0, acount = 0, icount = 0;
+        const unsigned dhi = (unsigned)(prm.desc_base >> 32), dlo = (unsigned)prm.desc_base;
+        constexpr unsigned KSTEP = (2 * MM_LBO) >> 4;  // one K-step further on, in descriptor units of 16 bytes
         M3_FOR_ITEMS
             if (ntiles == 0) continue;
             const unsigned ab = icount & 1u;
-            mm_mbar_wait(bAfull + 8 * ab, (icount >> 1) & 1u);
-            const unsigned long long dA0 = prm.desc_base | (unsigned long long)(((sA + ab * 2 * MM_TILE_BYTES) & 0x3ffffu) >> 4);
-            const unsigned long long dA1 = prm.desc_base | (unsigned long long)(((sA + ab * 2 * MM_TILE_BYTES + MM_TILE_BYTES) & 0x3ffffu) >> 4);
+            wait_ahead(bAfull + 8 * ab, (icount >> 1) & 1u);
+            const unsigned a0 = dlo | (((sA + ab * 2 * MM_TILE_BYTES) & 0x3ffffu) >> 4), a1 = a0 + (MM_TILE_BYTES >> 4);
             for (int tt = 0; tt < ntiles; ++tt) {
                 const unsigned s = tcount % M3_STAGES, a = acount & 1u;
-                mm_mbar_wait(bFull + 8 * s, (tcount / M3_STAGES) & 1u);
-                mm_mbar_wait(bTempty + 8 * a, ((acount >> 1) & 1u) ^ 1u);
+                wait_ahead(bFull + 8 * s, (tcount / M3_STAGES) & 1u);
+                if (lane == 0) trace(4, tcount);
+                wait_ahead(bTempty + 8 * a, ((acount >> 1) & 1u) ^ 1u);
+                if (lane == 0) trace(5, tcount);
                 mm_fence_after();
-                const unsigned long long dB = prm.desc_base | (unsigned long long)(((sA + M3_OFF_B + s * MM_TILE_BYTES) & 0x3ffffu) >> 4);
-                const int ksteps = flags[s] ? 8 : 6;
-                const unsigned d0 = tmem + a * 2 * MM_N;
-                for (int k = 0; k < ksteps; ++k) {
-                    const unsigned long long o = (unsigned long long)((k * 2 * MM_LBO) >> 4);
-                    mm_mma<KIND>(d0, dA0 + o, dB + o, prm.idesc, k > 0 ? 1u : 0u);
+                const unsigned b0 = dlo | (((sA + M3_OFF_B + s * MM_TILE_BYTES) & 0x3ffffu) >> 4);
+                const bool upper = flags[s] != 0;
+                const unsigned d0 = tmem + a * 2 * MM_N, d1 = d0 + MM_N;
+                if (mm_elect_one()) {
+                    if (!(DBG & 1)) {
+                        mm_mma_w<KIND, 0>(d0, a0, b0, dhi, prm.idesc);
+#pragma unroll
+                        for (int k = 1; k < 6; ++k) mm_mma_w<KIND, 1>(d0, a0 + k * KSTEP, b0 + k * KSTEP, dhi, prm.idesc);
+                        mm_mma_w<KIND, 0>(d1, a1, b0, dhi, prm.idesc);
+#pragma unroll
+                        for (int k = 1; k < 6; ++k) mm_mma_w<KIND, 1>(d1, a1 + k * KSTEP, b0 + k * KSTEP, dhi, prm.idesc);
+                        if (upper) {
+#pragma unroll
+                            for (int k = 6; k < 8; ++k) mm_mma_w<KIND, 1>(d0, a0 + k * KSTEP, b0 + k * KSTEP, dhi, prm.idesc);
+#pragma unroll
+                            for (int k = 6; k < 8; ++k) mm_mma_w<KIND, 1>(d1, a1 + k * KSTEP, b0 + k * KSTEP, dhi, prm.idesc);
+                        }
+                    }
+                    mm_commit(bEmpty + 8 * s);
+                    mm_commit(bTfull + 8 * a);
                 }
-                for (int k = 0; k < ksteps; ++k) {
-                    const unsigned long long o = (unsigned long long)((k * 2 * MM_LBO) >> 4);
-                    mm_mma<KIND>(d0 + MM_N, dA1 + o, dB + o, prm.idesc, k > 0 ? 1u : 0u);
-                }
-                mm_commit(bEmpty + 8 * s);
-                mm_commit(bTfull + 8 * a);
+                __syncwarp();
+                if (lane == 0) trace(6, tcount);
                 ++tcount;
                 ++acount;
             }
-            mm_commit(bAempty + 8 * ab);  // this A buffer is free once the MMAs issued so far have completed
+            if (mm_elect_one()) mm_commit(bAempty + 8 * ab);  // this A buffer is free once the MMAs issued so far have completed
+            __syncwarp();
             ++icount;
         }
     }
@@ -887,10 +1029,14 @@ cudaError_t orbk_match_mma_init() {
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_match_mma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, MM_SMEM);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_match_mma3<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, M3_SMEM);
+#define M3_ATTR(K, F)                                                                                             \
+    e = cudaFuncSetAttribute(k_match_mma3<K, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, M3_SMEM); \
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_match_mma3<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, M3_SMEM);
-    if (e != cudaSuccess) return e;
+    M3_ATTR(0, 0) M3_ATTR(1, 0)
+#ifdef ORB_B200_MMA_KNOCKOUT
+    M3_ATTR(0, 1) M3_ATTR(0, 2) M3_ATTR(0, 3) M3_ATTR(0, 4) M3_ATTR(0, 12) M3_ATTR(0, 13) M3_ATTR(0, 14) M3_ATTR(0, 15) M3_ATTR(1, 14) M3_ATTR(0, 16) M3_ATTR(0, 30) M3_ATTR(0, 31)
+#endif
+#undef M3_ATTR
     e = cudaFuncSetAttribute(k_match_mma2<0, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, M2_SMEM);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_match_mma2<0, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, M2_SMEM);
@@ -911,6 +1057,10 @@ cudaError_t orbk_match_all_mma(const uint8_t* q, const int* nq, size_t q_stride,
     MmParams prm;
     prm.neg_lo = (unsigned)-64;
     prm.neg_hi = (unsigned)(-64 * 65536);
+    {
+        const char* e = getenv("ORB_B200_MMA_PARK");
+        prm.park_ns = e ? (unsigned)atoi(e) : 0u;
+    }
     unsigned lbo = MM_LBO, sbo = MM_SBO;
     if (variant % 10 == 1) std::swap(lbo, sbo);
     // matrix descriptor: start address >> 4 [0,14), leading byte offset >> 4 [16,30), stride byte offset >> 4 [32,46),
@@ -940,10 +1090,47 @@ cudaError_t orbk_match_all_mma(const uint8_t* q, const int* nq, size_t q_stride,
         const int qblocks = (max_nq + 2 * MM_M - 1) / (2 * MM_M);
         const long long nitems = (long long)npairs * qblocks;
         const int grid = (int)(nitems < sms ? nitems : sms);
-        if (kind == 0)
-            k_match_mma3<0><<<grid, M3_THREADS, M3_SMEM, st>>>(q, nq, q_stride, t, nt, t_stride, best_idx, best_dist, second_dist, out_stride, npairs, qblocks, prm);
+#define M3_GO(K, F) k_match_mma3<K, F><<<grid, M3_THREADS, M3_SMEM, st>>>(q, nq, q_stride, t, nt, t_stride, best_idx, best_dist, second_dist, out_stride, npairs, qblocks, prm)
+        int dbg = 0;
+#ifdef ORB_B200_MMA_KNOCKOUT  // timing experiments only (results are garbage): see the DBG bits in k_match_mma3
+        const char* ed = getenv("ORB_B200_MMA_DEBUG");
+        dbg = ed ? atoi(ed) : 0;
+#endif
+#ifdef ORB_B200_MMA_KNOCKOUT
+        if (kind != 0 && dbg == 14)
+            M3_GO(1, 14);
         else
-            k_match_mma3<1><<<grid, M3_THREADS, M3_SMEM, st>>>(q, nq, q_stride, t, nt, t_stride, best_idx, best_dist, second_dist, out_stride, npairs, qblocks, prm);
+#endif
+        if (kind != 0)
+            M3_GO(1, 0);
+#ifdef ORB_B200_MMA_KNOCKOUT
+        else if (dbg == 1)
+            M3_GO(0, 1);
+        else if (dbg == 2)
+            M3_GO(0, 2);
+        else if (dbg == 3)
+            M3_GO(0, 3);
+        else if (dbg == 4)
+            M3_GO(0, 4);
+        else if (dbg == 12)
+            M3_GO(0, 12);
+        else if (dbg == 13)
+            M3_GO(0, 13);
+        else if (dbg == 14)
+            M3_GO(0, 14);
+        else if (dbg == 15)
+            M3_GO(0, 15);
+        else if (dbg == 16)
+            M3_GO(0, 16);
+        else if (dbg == 30)
+            M3_GO(0, 30);
+        else if (dbg == 31)
+            M3_GO(0, 31);
+#endif
+        else
+            M3_GO(0, 0);
+        (void)dbg;
+#undef M3_GO
     } else if (variant >= 10 && variant < 20) {  // the first form of the kernel (2 CTAs per SM, block barriers): kept as a comparator
         dim3 grid((max_nq + MM_M - 1) / MM_M, npairs);
         if (kind == 0)

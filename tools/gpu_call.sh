@@ -1,10 +1,7 @@
 mkdir -p gpurun_out
-O=gpurun_out/r02s_mma3.txt; : > $O
-timeout 600 python -m pytest tests/test_gpu_match.py -m gpu -q -x > gpurun_out/r02s_pytest.txt 2>&1
-tail -n 5 gpurun_out/r02s_pytest.txt
-python tools/probes/mma_probe.py --kinds i8,f8 --variants 0,30 >> $O 2>&1
-python tools/probes/match_bench.py --only mma >> $O 2>&1
-cat $O
-ncu --set full --import-source on --clock-control none -k regex:k_match_mma3 -s 3 -c 1 -o gpurun_out/r02s_mma3 python tools/probes/match_bench.py --only mma --reps 2 > gpurun_out/r02s_ncu.log 2>&1
-tail -n 3 gpurun_out/r02s_ncu.log
-ls -la gpurun_out/r02s_mma3.ncu-rep
+O=gpurun_out/r02aa_min2.txt; : > $O
+./tools/probes/pipe_probe 2>&1 | grep "SMSP 2" > gpurun_out/r02_pipe_probe2.txt
+ORB_B200_MMA_PARK=2000 python tools/probes/mma_probe.py --kinds i8,f8 --variants 0 >> $O 2>&1
+python tools/probes/match_sweep.py --env ORB_B200_MMA_DEBUG=0,3,14 >> $O 2>&1
+timeout 600 python -m pytest tests/test_gpu_match.py -m gpu -q -x 2>&1 | tail -n 3 >> $O
+cat gpurun_out/r02_pipe_probe2.txt $O
