@@ -1,107 +1,139 @@
-// Issue rates of the instructions the matcher's epilogue is made of, per SM sub-partition (SMSP), on B200:
-// W warps per SMSP run ILP-8 chains of one opcode (or of two opcodes interleaved) and report warp instructions per clock.
-//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o pipe_probe pipe_probe.cu && ./pipe_probe
-#include <cstdio>
+// Which pipes do the integer / fp16x2 instructions of the detect, blur and describe kernels use on
+// sm_100a?  Each mode runs independent chains of one instruction class (or an interleaved mix of two)
+// and reports warp-instructions per clock per SM for each class.  If a mix takes max(a, b) instead of
+// a + b, the two classes issue to different pipes.
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
+#include <stdio.h>
 
-enum Op { VMIN2, VMIN3, HMIN2, IMAD, FMNMX, LOP3, PRMT, MIX_V_H, MIX_V_I, MIX_V3_I, MIX_H_I, VADDMIN, MIX_VA_I, N_OPS };
-static const char* NAMES[] = {"VIMNMX.U16x2", "VIMNMX3.U16x2", "HMNMX2", "IMAD", "FMNMX", "LOP3", "PRMT",
-                              "VIMNMX+HMNMX2", "VIMNMX+IMAD", "VIMNMX3+IMAD", "HMNMX2+IMAD", "VIADDMNMX", "VIADDMNMX+IMAD"};
+#define ITERS 2048
+#define CHAINS 8
 
-__device__ __forceinline__ unsigned hmin2u(unsigned a, unsigned b) {
-    unsigned d;
-    asm volatile("min.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
-    return d;
-}
-__device__ __forceinline__ unsigned hmax2u(unsigned a, unsigned b) {
-    unsigned d;
-    asm volatile("max.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
-    return d;
-}
-__device__ __forceinline__ unsigned vmin2(unsigned a, unsigned b) {
-    unsigned d;
-    asm volatile("vmin2.u32.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(0u));
-    return d;
-}
+enum { HMAX2B = 2048, PRMTI = 4096, LDS = 8192, VIMNMX2 = 16384, HADD2 = 32768, VIMNMX3 = 1, HMNMX2 = 2, HFMA2 = 4, PRMT = 8, LOP3 = 16, IMAD = 32, IDP4A = 64, HRELU = 128, POPC = 256, IADD3 = 512, SHF = 1024 };
 
-template <int OP>
-__global__ void k(int iters, unsigned seed, unsigned mul, unsigned* out, long long* cycles) {
-    unsigned x[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) x[i] = seed * (threadIdx.x + 1) + i * 0x01010101u;
-    unsigned y = seed ^ 0x12345678u;
+template <int MODE>
+__global__ void k(unsigned* out, unsigned seed, long long* cycles) {
+    unsigned a[CHAINS], b[CHAINS];
+    __shared__ unsigned sm[1024];
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) sm[i] = i * seed;
     __syncthreads();
+#pragma unroll
+    for (int i = 0; i < CHAINS; ++i) {
+        a[i] = (threadIdx.x * 2654435761u + i * 40503u + seed) & 0x00ff00ffu | 0x64006400u;
+        b[i] = (threadIdx.x * 40503u + i * 2654435761u + seed) & 0x00ff00ffu | 0x64006400u;
+    }
+    const unsigned c = (seed * 77u) & 0x00ff00ffu | 0x64006400u;
     const long long t0 = clock64();
-    for (int it = 0; it < iters; ++it) {
+    for (int it = 0; it < ITERS; ++it) {
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            unsigned z[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const unsigned a = x[i], b = x[(i + 3) & 7];  // partner from another chain: nothing folds, ILP stays 8
-                unsigned d = 0;
-                if (OP == VMIN2) d = (r & 1) ? __vminu2(a, b) : __vmaxu2(a, b);
-                if (OP == VMIN3) d = (r & 1) ? __vimin3_u16x2(a, b, y) : __vimax3_u16x2(a, b, y);
-                if (OP == HMIN2) d = (r & 1) ? hmin2u(a, b) : hmax2u(a, b);
-                if (OP == IMAD) d = a * mul + b;
-                if (OP == FMNMX) d = __float_as_uint((r & 1) ? fminf(__uint_as_float(a), __uint_as_float(b)) : fmaxf(__uint_as_float(a), __uint_as_float(b)));
-                if (OP == LOP3) d = (a & b) ^ mul;
-                if (OP == PRMT) d = __byte_perm(a, b, mul);
-                if (OP == MIX_V_H) d = (i & 1) ? ((r & 1) ? __vminu2(a, b) : __vmaxu2(a, b)) : ((r & 1) ? hmin2u(a, b) : hmax2u(a, b));
-                if (OP == MIX_V_I) d = (i & 1) ? ((r & 1) ? __vminu2(a, b) : __vmaxu2(a, b)) : a * mul + b;
-                if (OP == MIX_V3_I) d = (i & 1) ? ((r & 1) ? __vimin3_u16x2(a, b, y) : __vimax3_u16x2(a, b, y)) : a * mul + b;
-                if (OP == MIX_H_I) d = (i & 1) ? ((r & 1) ? hmin2u(a, b) : hmax2u(a, b)) : a * mul + b;
-                if (OP == VADDMIN) d = __viaddmin_u16x2(a, b, y);
-                if (OP == MIX_VA_I) d = (i & 1) ? __viaddmin_u16x2(a, b, y) : a * mul + b;
-                z[i] = d;
+        for (int i = 0; i < CHAINS; ++i) {
+            if (MODE & VIMNMX3) a[i] = __vimax3_u16x2(a[i], a[(i + 1) % CHAINS], c + it);
+            if (MODE & HMNMX2) {
+                __half2 x = *reinterpret_cast<__half2*>(&b[i]), y = *reinterpret_cast<const __half2*>(&c);
+                x = __hmin2(x, y);
+                b[i] = *reinterpret_cast<unsigned*>(&x);
             }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) x[i] = z[i];
+            if (MODE & HFMA2) {
+                __half2 x = *reinterpret_cast<__half2*>(&b[i]), y = *reinterpret_cast<const __half2*>(&c);
+                x = __hfma2(x, y, x);
+                b[i] = *reinterpret_cast<unsigned*>(&x);
+            }
+            if (MODE & HRELU) {
+                __half2 x = *reinterpret_cast<__half2*>(&b[i]), y = *reinterpret_cast<const __half2*>(&c);
+                x = __hfma2_relu(x, y, x);
+                b[i] = *reinterpret_cast<unsigned*>(&x);
+            }
+            if (MODE & HMAX2B) {  // a second, independent HMNMX2 stream on the a[] registers
+                __half2 x = *reinterpret_cast<__half2*>(&a[i]), y = *reinterpret_cast<__half2*>(&a[(i + 1) % CHAINS]);
+                x = __hmax2(x, y);
+                a[i] = *reinterpret_cast<unsigned*>(&x);
+            }
+            if (MODE & PRMTI) b[i] = __byte_perm(b[i], c, 0x5432);
+            if (MODE & LDS) b[i] ^= sm[(threadIdx.x + i * 32 + (b[i] & 1)) & 1023];
+            if (MODE & VIMNMX2) a[i] = __vmaxu2(a[i], a[(i + 1) % CHAINS]);
+            if (MODE & HADD2) {
+                __half2 x = *reinterpret_cast<__half2*>(&b[i]), y = *reinterpret_cast<const __half2*>(&c);
+                x = __hadd2(x, y);
+                b[i] = *reinterpret_cast<unsigned*>(&x);
+            }
+            if (MODE & PRMT) b[i] = __byte_perm(b[i], c, b[(i + 3) % CHAINS]);
+            if (MODE & LOP3) b[i] = (b[i] & (c + it)) ^ b[(i + 3) % CHAINS];
+            if (MODE & IMAD) b[i] = b[i] * c + b[(i + 3) % CHAINS];
+            if (MODE & IDP4A) b[i] = __dp4a(b[i], c, b[i]);
+            if (MODE & POPC) b[i] = __popc(b[i]) + 0x5555;
+            if (MODE & IADD3) b[i] = b[i] + (c ^ it) + b[(i + 3) % CHAINS];
+            if (MODE & SHF) b[i] = __funnelshift_l(b[i], c, it);
         }
     }
     const long long t1 = clock64();
-    unsigned s = 0;
+    unsigned r = 0;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) s ^= x[i];
-    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
-    if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+    for (int i = 0; i < CHAINS; ++i) r ^= a[i] ^ b[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = r;
+    if (threadIdx.x == 0 && blockIdx.x == 0) *cycles = t1 - t0;
 }
 
-template <int OP>
-void run(int warpsPerSmsp, unsigned* out, long long* cyc) {
-    const int iters = 2000, threads = warpsPerSmsp * 4 * 32, blocks = 148;
-    k<OP><<<blocks, threads>>>(iters, 3u, 5u, out, cyc);
-    k<OP><<<blocks, threads>>>(iters, 3u, 5u, out, cyc);
+template <int MODE>
+void run(unsigned* d, long long* dc, const char* name, int nclasses) {
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    int nb = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k<MODE>, 256, 0);
+    k<MODE><<<148 * 8, 256>>>(d, 1, dc);
+    cudaEventRecord(e0);
+    k<MODE><<<148 * 8, 256>>>(d, 2, dc);
+    cudaEventRecord(e1);
     cudaDeviceSynchronize();
-    long long h[148];
-    cudaMemcpy(h, cyc, sizeof(h), cudaMemcpyDeviceToHost);
-    double avg = 0;
-    for (int i = 0; i < 148; ++i) avg += (double)h[i] / 148;
-    const double inst = (double)iters * 32 * warpsPerSmsp;  // warp instructions per SMSP
-    printf("%-16s warps/SMSP %d: %.3f warp-instr / clk / SMSP\n", NAMES[OP], warpsPerSmsp, inst / avg);
+    float ms;
+    cudaEventElapsedTime(&ms, e0, e1);
+    long long cyc;
+    cudaMemcpy(&cyc, dc, 8, cudaMemcpyDeviceToHost);
+    // 8 CTAs x 8 warps per SM (64 warps)
+    const double per_class = 64.0 * ITERS * CHAINS / (double)cyc;
+    printf("%-24s occ %d  %8.1f us  %10lld cycles  %.3f warp-instr/clk/SM per class, %.3f total\n", name, nb, ms * 1e3, cyc, per_class, per_class * nclasses);
 }
 
 int main() {
-    unsigned* out;
-    long long* cyc;
-    cudaMalloc(&out, 148 * 1024 * 4);
-    cudaMalloc(&cyc, 148 * 8);
-    for (int w : {1, 2, 4}) {
-        run<VMIN2>(w, out, cyc);
-        run<VMIN3>(w, out, cyc);
-        run<HMIN2>(w, out, cyc);
-        run<IMAD>(w, out, cyc);
-        run<FMNMX>(w, out, cyc);
-        run<LOP3>(w, out, cyc);
-        run<PRMT>(w, out, cyc);
-        run<MIX_V_H>(w, out, cyc);
-        run<MIX_V_I>(w, out, cyc);
-        run<MIX_V3_I>(w, out, cyc);
-        run<MIX_H_I>(w, out, cyc);
-        run<VADDMIN>(w, out, cyc);
-        run<MIX_VA_I>(w, out, cyc);
-    }
-    printf("%s\n", cudaGetErrorString(cudaGetLastError()));
+    unsigned* d;
+    long long* dc;
+    cudaMalloc(&d, 148 * 8 * 256 * 4);
+    cudaMalloc(&dc, 8);
+    run<HMAX2B>(d, dc, "HMNMX2 (a-chain)", 1);
+    run<VIMNMX2>(d, dc, "VIMNMX.U16x2 2-input", 1);
+    run<PRMTI>(d, dc, "PRMT imm", 1);
+    run<LDS>(d, dc, "LDS+LOP", 2);
+    run<HADD2>(d, dc, "HADD2", 1);
+    run<HMAX2B | HMNMX2>(d, dc, "HMNMX2 + HMNMX2", 2);
+    run<HMAX2B | PRMTI>(d, dc, "HMNMX2 + PRMT imm", 2);
+    run<HMAX2B | LOP3>(d, dc, "HMNMX2 + LOP3", 2);
+    run<HMAX2B | IADD3>(d, dc, "HMNMX2 + IADD3", 2);
+    run<HMAX2B | LDS>(d, dc, "HMNMX2 + LDS+LOP", 3);
+    run<HMAX2B | HADD2>(d, dc, "HMNMX2 + HADD2", 2);
+    run<HMAX2B | IMAD>(d, dc, "HMNMX2 + IMAD", 2);
+    run<VIMNMX3 | LDS>(d, dc, "VIMNMX3 + LDS+LOP", 3);
+    run<VIMNMX3>(d, dc, "VIMNMX3.U16x2", 1);
+    run<HMNMX2>(d, dc, "HMNMX2", 1);
+    run<HFMA2>(d, dc, "HFMA2", 1);
+    run<HRELU>(d, dc, "HFMA2.RELU", 1);
+    run<PRMT>(d, dc, "PRMT", 1);
+    run<LOP3>(d, dc, "LOP3", 1);
+    run<IMAD>(d, dc, "IMAD", 1);
+    run<IDP4A>(d, dc, "IDP.4A", 1);
+    run<POPC>(d, dc, "POPC+IADD", 2);
+    run<IADD3>(d, dc, "IADD3", 1);
+    run<SHF>(d, dc, "SHF", 1);
+    run<VIMNMX3 | HMNMX2>(d, dc, "VIMNMX3 + HMNMX2", 2);
+    run<VIMNMX3 | HFMA2>(d, dc, "VIMNMX3 + HFMA2", 2);
+    run<VIMNMX3 | HRELU>(d, dc, "VIMNMX3 + HFMA2.RELU", 2);
+    run<VIMNMX3 | PRMT>(d, dc, "VIMNMX3 + PRMT", 2);
+    run<VIMNMX3 | LOP3>(d, dc, "VIMNMX3 + LOP3", 2);
+    run<VIMNMX3 | IMAD>(d, dc, "VIMNMX3 + IMAD", 2);
+    run<VIMNMX3 | IDP4A>(d, dc, "VIMNMX3 + IDP.4A", 2);
+    run<IDP4A | IMAD>(d, dc, "IDP.4A + IMAD", 2);
+    run<PRMT | IMAD>(d, dc, "PRMT + IMAD", 2);
+    run<LOP3 | IADD3>(d, dc, "LOP3 + IADD3", 2);
+    run<SHF | VIMNMX3>(d, dc, "SHF + VIMNMX3", 2);
+    run<SHF | IMAD>(d, dc, "SHF + IMAD", 2);
     return 0;
 }
