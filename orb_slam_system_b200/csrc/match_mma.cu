@@ -116,6 +116,20 @@ __device__ __forceinline__ void mm_mma_w(unsigned tmem_d, unsigned alo, unsigned
             "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], da, db, %4, p;\n}\n" ::"r"(tmem_d), "r"(alo), "r"(blo), "r"(hi), "r"(idesc), "n"(ACC)
             : "memory");
 }
+// accumulate one more K-step whose two descriptors have high words of their own
+template <int KIND>
+__device__ __forceinline__ void mm_mma_x(unsigned tmem_d, unsigned alo, unsigned blo, unsigned ahi, unsigned bhi, unsigned idesc) {
+    if (KIND == 0)
+        asm volatile(
+            "{\n.reg .pred p;\n.reg .b64 da, db;\nsetp.ne.b32 p, 1, 0;\nmov.b64 da, {%1, %3};\nmov.b64 db, {%2, %4};\n"
+            "tcgen05.mma.cta_group::1.kind::i8 [%0], da, db, %5, p;\n}\n" ::"r"(tmem_d), "r"(alo), "r"(blo), "r"(ahi), "r"(bhi), "r"(idesc)
+            : "memory");
+    else
+        asm volatile(
+            "{\n.reg .pred p;\n.reg .b64 da, db;\nsetp.ne.b32 p, 1, 0;\nmov.b64 da, {%1, %3};\nmov.b64 db, {%2, %4};\n"
+            "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], da, db, %5, p;\n}\n" ::"r"(tmem_d), "r"(alo), "r"(blo), "r"(ahi), "r"(bhi), "r"(idesc)
+            : "memory");
+}
 __device__ __forceinline__ bool mm_elect_one() {
     unsigned pred;
     asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
@@ -193,6 +207,7 @@ struct MmParams {
     unsigned long long desc_base;  // shared-memory matrix descriptor without its start address
     unsigned lut_a, lut_b;         // byte values of a query bit (0, 1) / of a train bit (0, 1)
     unsigned park_ns;              // suspend-time hint of the producer / MMA waits (0: plain polling)
+    unsigned shl16;                // 65536 as a run-time value (IMAD instead of a shift + add on the ALU pipe)
 };
 
 template <int KIND>
@@ -398,6 +413,21 @@ __device__ __forceinline__ void mm_slab_keys(unsigned (&acc0)[32], unsigned (&ac
     if (lim < 64) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) P[i] |= (i < lim ? 0u : 0x0000ffffu) | (i + 32 < lim ? 0u : 0xffff0000u);
+    }
+}
+
+// BK = 1: the accumulators already are the keys (bias K-step, see k_match_mma3): one IMAD packs two of them
+template <int KIND, int BK>
+__device__ __forceinline__ void mm_slab_keys_any(unsigned (&acc0)[32], unsigned (&acc1)[32], const MmParams& prm, int lim, unsigned (&P)[32]) {
+    if (BK) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) P[i] = acc1[i] * prm.shl16 + acc0[i];
+        if (lim < 64) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) P[i] |= (i < lim ? 0u : 0x0000ffffu) | (i + 32 < lim ? 0u : 0xffff0000u);
+        }
+    } else {
+        mm_slab_keys<KIND>(acc0, acc1, prm, lim, P);
     }
 }
 
@@ -759,17 +789,23 @@ __global__ void __launch_bounds__(M2_THREADS(EW), 1) k_match_mma2(const uint8_t*
 // Shared memory: 2 x 64 KB of A, 3 x 32 KB of B = 224 KB + barriers.
 // ------------------------------------------------------------------------------------------
 #define M3_EW 8
-#define M3_THREADS ((M3_EW + M2_PROD_WARPS + 1) * 32)
+#define M3_MMA_WARPS 2
+#define M3_THREADS ((M3_EW + M2_PROD_WARPS + M3_MMA_WARPS) * 32)
 #define M3_STAGES 3
 #define M3_OFF_B (4 * MM_TILE_BYTES)
-#define M3_OFF_BAR (M3_OFF_B + M3_STAGES * MM_TILE_BYTES)  // full[3], empty[3], tfull[2], tempty[2], afull[2], aempty[2]
+#define M3_OFF_AX (M3_OFF_B + M3_STAGES * MM_TILE_BYTES)
+#define M3_AX_BYTES 256   // bias K-step, query side: 8 rows x 2 K-chunks, every row group reads the same rows
+#define M3_BX_BYTES 2048  // bias K-step, train side: 128 rows x 1 K-chunk, both K-chunks read the same bytes
+#define M3_OFF_BX (M3_OFF_AX + M3_AX_BYTES)
+#define M3_OFF_BAR (M3_OFF_BX + M3_BX_BYTES)  // full[3], empty[3], tfull[2], tempty[2], afull[2], aempty[2]
 #define M3_OFF_TMEM (M3_OFF_BAR + 14 * 8)
 #define M3_OFF_FLAGS (M3_OFF_TMEM + 8)
 #define M3_SMEM (M3_OFF_FLAGS + 32)
+static_assert(M3_OFF_AX % 128 == 0 && M3_SMEM <= 232448, "k_match_mma3 shared memory");
 
 // DBG (timing experiments, -DORB_B200_MMA_KNOCKOUT builds only): 1 = no tcgen05.mma issued, 2 = producers skip the expansion,
 // 4 = epilogue skips the key arithmetic, 8 = and the TMEM loads; the barrier traffic stays, the results are garbage.
-template <int KIND, int DBG>
+template <int KIND, int DBG, int BK>
 __global__ void __launch_bounds__(M3_THREADS, 1) k_match_mma3(const uint8_t* __restrict__ q, const int* __restrict__ nq, size_t q_stride,
                                                               const uint8_t* __restrict__ t, const int* __restrict__ nt, size_t t_stride,
                                                               int* __restrict__ best_idx, int* __restrict__ best_dist,
@@ -807,9 +843,23 @@ __global__ void __launch_bounds__(M3_THREADS, 1) k_match_mma3(const uint8_t* __r
             mm_mbar_init(bTfull + 8 * a, 1);
             mm_mbar_init(bTempty + 8 * a, M3_EW);
             mm_mbar_init(bAfull + 8 * a, M2_PROD_WARPS * 32);
-            mm_mbar_init(bAempty + 8 * a, 1);
+            mm_mbar_init(bAempty + 8 * a, M3_MMA_WARPS);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (BK && tid < 16 + 128) {
+        // the bias K-step: 32 more K positions whose products add 64 * 256 + (train row & 63) to every accumulator, so that with
+        // the query bits as -+64 the accumulator IS the 16-bit key (256 - a'.b) * 64 + column.  Query side: bytes {8, 1, 64, 64,
+        // 64, 64, 0 ...} in K-chunk 0 and zeros in K-chunk 1, the same for every row (stride byte offset 0).  Train side: bytes
+        // {column >> 3, column & 7, 64, 64, 64, 64, 0 ...}, read for both K-chunks (leading byte offset 0; chunk 1 meets zeros).
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (tid < 8) v = make_uint4(0x40400108u, 0x00004040u, 0, 0);
+        if (tid >= 16) {
+            const unsigned col = (unsigned)(tid - 16) & 63u;
+            v = make_uint4(0x40400000u | (col >> 3) | ((col & 7u) << 8), 0x00004040u, 0, 0);
+        }
+        *reinterpret_cast<uint4*>(smem + M3_OFF_AX + tid * 16) = v;  // rows 8g + r of the train side sit at g * 128 + r * 16
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     mm_fence_before();
     __syncthreads();
@@ -833,6 +883,11 @@ __global__ void __launch_bounds__(M3_THREADS, 1) k_match_mma3(const uint8_t* __r
         const int tileA = warp >> 2;
         const unsigned trow = tmem + ((unsigned)(warp & 3) << 21) + (unsigned)(tileA * MM_N);
         unsigned acount = 0;  // accumulator tiles consumed so far (stage = acount & 1, phase = (acount >> 1) & 1)
+        if ((DBG & 32) && tileA == 1) {  // experiment: the second warp of every scheduler starts late
+            const long long t0 = clock64();
+            while (clock64() - t0 < (long long)prm.park_ns) {
+            }
+        }
         M3_FOR_ITEMS
             unsigned bestk = 0xffffffffu, seck = 0xffffffffu;
             auto merge = [&](unsigned b2, unsigned s2, int slab) {
@@ -854,7 +909,7 @@ __global__ void __launch_bounds__(M3_THREADS, 1) k_match_mma3(const uint8_t* __r
                 const unsigned ta = trow + a * 2 * MM_N;
                 unsigned P[32], b2, s2;
                 mm_tmem_ld_wait();
-                if (!(DBG & 4)) mm_slab_keys<KIND>(acc0, acc1, prm, nT - tt * MM_N, P);
+                if (!(DBG & 4)) mm_slab_keys_any<KIND, BK>(acc0, acc1, prm, nT - tt * MM_N, P);
                 if (!(DBG & 8)) {
                     mm_tmem_ld32(ta + 64, acc0);
                     mm_tmem_ld32(ta + 96, acc1);
@@ -868,7 +923,7 @@ __global__ void __launch_bounds__(M3_THREADS, 1) k_match_mma3(const uint8_t* __r
                 __syncwarp();
                 if (lane == 0) mm_mbar_arrive(bTempty + 8 * a);
                 if (tid == 0) trace(9, acount);
-                if (!(DBG & 4)) mm_slab_keys<KIND>(acc0, acc1, prm, nT - tt * MM_N - 64, P);
+                if (!(DBG & 4)) mm_slab_keys_any<KIND, BK>(acc0, acc1, prm, nT - tt * MM_N - 64, P);
                 ++acount;
                 if (tt + 1 < ntiles) {
                     mm_mbar_wait(bTfull + 8 * (acount & 1u), (acount >> 1) & 1u);
@@ -963,20 +1018,31 @@ __global__ void __launch_bounds__(M3_THREADS, 1) k_match_mma3(const uint8_t* __r
             }
         }
     } else {
-        // ---------------- MMA issuer: the whole warp walks the loop, one elected lane issues ----------------
-        unsigned tcount = 0, acount = 0, icount = 0;
+        // ---------------- MMA issuers: two warps, one per accumulator stage (tile parity) ----------------
+        // tcgen05.mma blocks its thread while the tensor core's queue is full, and a barrier poll that succeeds at once still
+        // takes ~150 cycles; with a single issuing warp those polls sat between the last MMA of one tile and the first of the
+        // next and the tensor pipe idled ~500 of every 1300 cycles (tools/probes/mma_timeline.py).  With two warps one polls
+        // while the other is blocked in its issue.  Each warp walks every tile and acts on its own parity; the whole warp
+        // stays converged and one elected lane issues.
+        const unsigned mw = (unsigned)(warp - (M3_EW + M2_PROD_WARPS));
+        unsigned tcount = 0, icount = 0;  // tiles (= accumulator tiles) / A buffers so far
         const unsigned dhi = (unsigned)(prm.desc_base >> 32), dlo = (unsigned)prm.desc_base;
         constexpr unsigned KSTEP = (2 * MM_LBO) >> 4;  // one K-step further on, in descriptor units of 16 bytes
+        // bias K-step descriptors: query side LBO 128 / SBO 0, train side LBO 0 / SBO 128; version bits as in desc_base
+        const unsigned ver = dhi & 0xffffc000u;
+        const unsigned ax_lo = (((sA + M3_OFF_AX) & 0x3ffffu) >> 4) | ((128u >> 4) << 16), x_hi = ver;
+        const unsigned bx_lo = ((sA + M3_OFF_BX) & 0x3ffffu) >> 4, bx_hi = ver | (128u >> 4);
         M3_FOR_ITEMS
             if (ntiles == 0) continue;
             const unsigned ab = icount & 1u;
             wait_ahead(bAfull + 8 * ab, (icount >> 1) & 1u);
             const unsigned a0 = dlo | (((sA + ab * 2 * MM_TILE_BYTES) & 0x3ffffu) >> 4), a1 = a0 + (MM_TILE_BYTES >> 4);
-            for (int tt = 0; tt < ntiles; ++tt) {
-                const unsigned s = tcount % M3_STAGES, a = acount & 1u;
+            for (int tt = 0; tt < ntiles; ++tt, ++tcount) {
+                if ((tcount & 1u) != mw) continue;
+                const unsigned s = tcount % M3_STAGES, a = mw;
                 wait_ahead(bFull + 8 * s, (tcount / M3_STAGES) & 1u);
                 if (lane == 0) trace(4, tcount);
-                wait_ahead(bTempty + 8 * a, ((acount >> 1) & 1u) ^ 1u);
+                wait_ahead(bTempty + 8 * a, ((tcount >> 1) & 1u) ^ 1u);
                 if (lane == 0) trace(5, tcount);
                 mm_fence_after();
                 const unsigned b0 = dlo | (((sA + M3_OFF_B + s * MM_TILE_BYTES) & 0x3ffffu) >> 4);
@@ -990,6 +1056,10 @@ __global__ void __launch_bounds__(M3_THREADS, 1) k_match_mma3(const uint8_t* __r
                         mm_mma_w<KIND, 0>(d1, a1, b0, dhi, prm.idesc);
 #pragma unroll
                         for (int k = 1; k < 6; ++k) mm_mma_w<KIND, 1>(d1, a1 + k * KSTEP, b0 + k * KSTEP, dhi, prm.idesc);
+                        if (BK) {
+                            mm_mma_x<KIND>(d0, ax_lo, bx_lo, x_hi, bx_hi, prm.idesc);
+                            mm_mma_x<KIND>(d1, ax_lo, bx_lo, x_hi, bx_hi, prm.idesc);
+                        }
                         if (upper) {
 #pragma unroll
                             for (int k = 6; k < 8; ++k) mm_mma_w<KIND, 1>(d0, a0 + k * KSTEP, b0 + k * KSTEP, dhi, prm.idesc);
@@ -1002,10 +1072,9 @@ __global__ void __launch_bounds__(M3_THREADS, 1) k_match_mma3(const uint8_t* __r
                 }
                 __syncwarp();
                 if (lane == 0) trace(6, tcount);
-                ++tcount;
-                ++acount;
             }
-            if (mm_elect_one()) mm_commit(bAempty + 8 * ab);  // this A buffer is free once the MMAs issued so far have completed
+            // this A buffer is free once the MMAs both warps have issued so far are complete (an arrival from each)
+            if (mm_elect_one()) mm_commit(bAempty + 8 * ab);
             __syncwarp();
             ++icount;
         }
@@ -1030,11 +1099,13 @@ cudaError_t orbk_match_mma_init() {
     e = cudaFuncSetAttribute(k_match_mma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, MM_SMEM);
     if (e != cudaSuccess) return e;
 #define M3_ATTR(K, F)                                                                                             \
-    e = cudaFuncSetAttribute(k_match_mma3<K, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, M3_SMEM); \
+    e = cudaFuncSetAttribute(k_match_mma3<K, F, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, M3_SMEM); \
+    if (e != cudaSuccess) return e;                                                                      \
+    if (K == 0) e = cudaFuncSetAttribute(k_match_mma3<0, F, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, M3_SMEM); \
     if (e != cudaSuccess) return e;
     M3_ATTR(0, 0) M3_ATTR(1, 0)
 #ifdef ORB_B200_MMA_KNOCKOUT
-    M3_ATTR(0, 1) M3_ATTR(0, 2) M3_ATTR(0, 3) M3_ATTR(0, 4) M3_ATTR(0, 12) M3_ATTR(0, 13) M3_ATTR(0, 14) M3_ATTR(0, 15) M3_ATTR(1, 14) M3_ATTR(0, 16) M3_ATTR(0, 30) M3_ATTR(0, 31)
+    M3_ATTR(0, 1) M3_ATTR(0, 2) M3_ATTR(0, 3) M3_ATTR(0, 4) M3_ATTR(0, 12) M3_ATTR(0, 13) M3_ATTR(0, 14) M3_ATTR(0, 15) M3_ATTR(1, 14) M3_ATTR(0, 16) M3_ATTR(0, 30) M3_ATTR(0, 31) M3_ATTR(0, 32) M3_ATTR(0, 35)
 #endif
 #undef M3_ATTR
     e = cudaFuncSetAttribute(k_match_mma2<0, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, M2_SMEM);
@@ -1061,6 +1132,7 @@ cudaError_t orbk_match_all_mma(const uint8_t* q, const int* nq, size_t q_stride,
         const char* e = getenv("ORB_B200_MMA_PARK");
         prm.park_ns = e ? (unsigned)atoi(e) : 0u;
     }
+    prm.shl16 = 65536u;
     unsigned lbo = MM_LBO, sbo = MM_SBO;
     if (variant % 10 == 1) std::swap(lbo, sbo);
     // matrix descriptor: start address >> 4 [0,14), leading byte offset >> 4 [16,30), stride byte offset >> 4 [32,46),
@@ -1090,7 +1162,18 @@ cudaError_t orbk_match_all_mma(const uint8_t* q, const int* nq, size_t q_stride,
         const int qblocks = (max_nq + 2 * MM_M - 1) / (2 * MM_M);
         const long long nitems = (long long)npairs * qblocks;
         const int grid = (int)(nitems < sms ? nitems : sms);
-#define M3_GO(K, F) k_match_mma3<K, F><<<grid, M3_THREADS, M3_SMEM, st>>>(q, nq, q_stride, t, nt, t_stride, best_idx, best_dist, second_dist, out_stride, npairs, qblocks, prm)
+        const char* ebk = getenv("ORB_B200_MMA_BK");
+        const bool bk = kind == 0 && !(ebk && atoi(ebk) == 0);
+        if (bk) prm.lut_a = 0x0000c040u;  // query bit 0 -> +64, 1 -> -64: the accumulator is -64 a'.b (+ the bias K-step)
+#define M3_GO(K, F)                                                                                                                        \
+    do {                                                                                                                                   \
+        if (bk)                                                                                                                            \
+            k_match_mma3<0, F, 1><<<grid, M3_THREADS, M3_SMEM, st>>>(q, nq, q_stride, t, nt, t_stride, best_idx, best_dist, second_dist, \
+                                                                       out_stride, npairs, qblocks, prm);                                  \
+        else                                                                                                                               \
+            k_match_mma3<K, F, 0><<<grid, M3_THREADS, M3_SMEM, st>>>(q, nq, q_stride, t, nt, t_stride, best_idx, best_dist, second_dist, \
+                                                                       out_stride, npairs, qblocks, prm);                                  \
+    } while (0)
         int dbg = 0;
 #ifdef ORB_B200_MMA_KNOCKOUT  // timing experiments only (results are garbage): see the DBG bits in k_match_mma3
         const char* ed = getenv("ORB_B200_MMA_DEBUG");
@@ -1124,6 +1207,10 @@ cudaError_t orbk_match_all_mma(const uint8_t* q, const int* nq, size_t q_stride,
             M3_GO(0, 16);
         else if (dbg == 30)
             M3_GO(0, 30);
+        else if (dbg == 32)
+            M3_GO(0, 32);
+        else if (dbg == 35)
+            M3_GO(0, 35);
         else if (dbg == 31)
             M3_GO(0, 31);
 #endif

@@ -1,7 +1,6 @@
 mkdir -p gpurun_out
-O=gpurun_out/r02aa_min2.txt; : > $O
-./tools/probes/pipe_probe 2>&1 | grep "SMSP 2" > gpurun_out/r02_pipe_probe2.txt
-ORB_B200_MMA_PARK=2000 python tools/probes/mma_probe.py --kinds i8,f8 --variants 0 >> $O 2>&1
-python tools/probes/match_sweep.py --env ORB_B200_MMA_DEBUG=0,3,14 >> $O 2>&1
+O=gpurun_out/r02ad_bk.txt; : > $O
+python tools/probes/mma_probe.py --kinds i8,f8 --variants 0 >> $O 2>&1
+python tools/probes/match_sweep.py --env ORB_B200_MMA_BK=0,1 --env ORB_B200_MMA_DEBUG=0,3,14 >> $O 2>&1
 timeout 600 python -m pytest tests/test_gpu_match.py -m gpu -q -x 2>&1 | tail -n 3 >> $O
-cat gpurun_out/r02_pipe_probe2.txt $O
+cat $O
