@@ -982,17 +982,18 @@ def main():
         line["hamming"] = {
             "metric": "Hamming pairs/s (brute force, best + second best)", "value": world * pairs / (mma182 * 1e-3), "unit": "pairs/s",
             "workload": f"{NP} keyframe pairs x {NQ} x {NQ} descriptors per GPU (BASELINE config 4), the extractor's own descriptors (182 live bits)",
-            "kernel": "k_match_mma (tcgen05.mma kind::i8 128x128x32, accumulators in TMEM, in-kernel bit expansion)",
+            "kernel": "k_match_mma3 (persistent; tcgen05.mma kind::i8 128x128x32, accumulators in TMEM, in-kernel bit expansion)",
             "ms_per_launch": mma182, "value_256_live_bits": world * pairs / (mma256 * 1e-3), "ms_per_launch_256_live_bits": mma256,
             "popc_kernel_value": world * pairs / (popc182 * 1e-3), "popc_kernel_value_256_live_bits": world * pairs / (popc256 * 1e-3),
             "identical_to_popc_kernel": bool(ham["identical_182"] and ham["identical_256"]),
             "algo_bytes_per_launch": NP * (32 * 2 * NQ + 12 * NQ), "hbm_frac": NP * (32 * 2 * NQ + 12 * NQ) / (mma182 * 1e-3) / 1e9 / peak,
-            "mma_pipe_frac": kfrac(mma182, 6), "mma_pipe_frac_256_live_bits": kfrac(mma256, 8),
+            "mma_pipe_frac": kfrac(mma182, 7), "mma_pipe_frac_256_live_bits": kfrac(mma256, 9),
             "mma_ops_per_s": world * pairs * 2 * 192 / (mma182 * 1e-3),
             "note": "d(a, b) = |a| - a'.b with a' = 2a - 1 in {-1, +1}, b in {0, 1}: exact in int8 with int32 accumulation.  K = 192 (6 K-steps) "
-                    "when words 6-7 of a train tile are zero (checked on the data), else 256.  mma_pipe_frac = issued tcgen05.mma time / "
-                    "kernel time at 64 clocks per 128 x 128 x 32 instruction; the rest is the epilogue (tcgen05.ld + packed 16-bit key "
-                    "tournament, ~2.3 instructions per distance) and the bit expansion, which share the SM with the tensor pipe"}
+                    "when words 6-7 of a train tile are zero (checked on the data), else 256, plus one K-step that adds the key's bias and "
+                    "column so that the accumulator is the packed 16-bit key.  mma_pipe_frac = issued tcgen05.mma time / kernel time at "
+                    "64 clocks per 128 x 128 x 32 instruction (7 / 9 K-steps); the rest is the epilogue (tcgen05.ld, one IMAD and two "
+                    "ALU-pipe instructions per key pair, both half-rate pipes) and the bit expansion, which share the SM with the tensor pipe"}
         if shard is not None:
             line["shard_match"] = shard
         if others:

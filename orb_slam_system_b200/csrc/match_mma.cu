@@ -782,11 +782,22 @@ __global__ void __launch_bounds__(M2_THREADS(EW), 1) k_match_mma2(const uint8_t*
 }
 
 // ------------------------------------------------------------------------------------------
-// k_match_mma3: k_match_mma2 made persistent.  One CTA per SM walks the work items (pair, block of 256 queries) with
-// stride gridDim.x; the three roles keep running barrier counters across the items, the two A tiles of the NEXT item
-// are expanded into a second A buffer while the MMAs of the current one still read the first, and the TMEM allocation,
-// the barrier set-up and the fill / drain of the pipeline are paid once per CTA instead of once per 256 queries.
-// Shared memory: 2 x 64 KB of A, 3 x 32 KB of B = 224 KB + barriers.
+// k_match_mma3 (the kernel that ships): k_match_mma2 made persistent, and what the timeline of its hand-overs
+// (tools/probes/mma_timeline.py) and knock-out timings (tools/probes/match_sweep.py on a -DORB_B200_MMA_KNOCKOUT build) asked for:
+//  * one CTA per SM walks the work items (pair, block of 256 queries) with stride gridDim.x; the roles keep running barrier
+//    counters across the items, the two A tiles of the NEXT item are expanded into a second A buffer while the MMAs of the
+//    current one still read the first; TMEM allocation, barrier set-up and the fill / drain of the pipeline are paid once per
+//    CTA instead of once per 256 queries;
+//  * two MMA-issuing warps, one per accumulator stage: tcgen05.mma blocks its thread while the tensor core's queue is full and
+//    a barrier poll takes ~150 cycles even when it succeeds at once, so a single issuing warp left the tensor pipe idle 40 %
+//    of the time; the issuing warps stay converged (elect.sync), which lets ptxas keep the descriptors in uniform registers;
+//  * the bias K-step: query bits become -+64, and one more K = 32 step per A tile multiplies {8, 1, 64, 64, 64, 64} by
+//    {column >> 3, column & 7, 64, 64, 64, 64}, so the accumulator IS the 16-bit key (256 - a'.b) * 64 + column and one IMAD
+//    packs two of them (IMAD issues at half rate on B200, like the integer min / max: tools/probes/epi_pipe_probe.cu).  Its
+//    operands take 2.3 KB: the query side is one 8-row group read by all 16 groups (stride byte offset 0), the train side one
+//    K-chunk read twice (leading byte offset 0) against a zero second chunk on the query side;
+//  * min / second-min in two passes (mm_min2) instead of the tournament.
+// Shared memory: 2 x 64 KB of A, 3 x 32 KB of B, 2.3 KB of bias operands = 226.4 KB.
 // ------------------------------------------------------------------------------------------
 #define M3_EW 8
 #define M3_MMA_WARPS 2
@@ -883,11 +894,6 @@ __global__ void __launch_bounds__(M3_THREADS, 1) k_match_mma3(const uint8_t* __r
         const int tileA = warp >> 2;
         const unsigned trow = tmem + ((unsigned)(warp & 3) << 21) + (unsigned)(tileA * MM_N);
         unsigned acount = 0;  // accumulator tiles consumed so far (stage = acount & 1, phase = (acount >> 1) & 1)
-        if ((DBG & 32) && tileA == 1) {  // experiment: the second warp of every scheduler starts late
-            const long long t0 = clock64();
-            while (clock64() - t0 < (long long)prm.park_ns) {
-            }
-        }
         M3_FOR_ITEMS
             unsigned bestk = 0xffffffffu, seck = 0xffffffffu;
             auto merge = [&](unsigned b2, unsigned s2, int slab) {
@@ -1105,7 +1111,7 @@ cudaError_t orbk_match_mma_init() {
     if (e != cudaSuccess) return e;
     M3_ATTR(0, 0) M3_ATTR(1, 0)
 #ifdef ORB_B200_MMA_KNOCKOUT
-    M3_ATTR(0, 1) M3_ATTR(0, 2) M3_ATTR(0, 3) M3_ATTR(0, 4) M3_ATTR(0, 12) M3_ATTR(0, 13) M3_ATTR(0, 14) M3_ATTR(0, 15) M3_ATTR(1, 14) M3_ATTR(0, 16) M3_ATTR(0, 30) M3_ATTR(0, 31) M3_ATTR(0, 32) M3_ATTR(0, 35)
+    M3_ATTR(0, 1) M3_ATTR(0, 2) M3_ATTR(0, 3) M3_ATTR(0, 4) M3_ATTR(0, 12) M3_ATTR(0, 13) M3_ATTR(0, 14) M3_ATTR(0, 15) M3_ATTR(0, 16) M3_ATTR(0, 30) M3_ATTR(0, 31)
 #endif
 #undef M3_ATTR
     e = cudaFuncSetAttribute(k_match_mma2<0, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, M2_SMEM);
@@ -1174,49 +1180,27 @@ cudaError_t orbk_match_all_mma(const uint8_t* q, const int* nq, size_t q_stride,
             k_match_mma3<K, F, 0><<<grid, M3_THREADS, M3_SMEM, st>>>(q, nq, q_stride, t, nt, t_stride, best_idx, best_dist, second_dist, \
                                                                        out_stride, npairs, qblocks, prm);                                  \
     } while (0)
-        int dbg = 0;
 #ifdef ORB_B200_MMA_KNOCKOUT  // timing experiments only (results are garbage): see the DBG bits in k_match_mma3
         const char* ed = getenv("ORB_B200_MMA_DEBUG");
-        dbg = ed ? atoi(ed) : 0;
-#endif
-#ifdef ORB_B200_MMA_KNOCKOUT
-        if (kind != 0 && dbg == 14)
-            M3_GO(1, 14);
-        else
-#endif
+        switch (kind == 0 && ed ? atoi(ed) : 0) {
+#define M3_CASE(F)   \
+    case F:          \
+        M3_GO(0, F); \
+        break;
+            M3_CASE(1) M3_CASE(2) M3_CASE(3) M3_CASE(4) M3_CASE(12) M3_CASE(13) M3_CASE(14) M3_CASE(15) M3_CASE(16) M3_CASE(30) M3_CASE(31)
+#undef M3_CASE
+            default:
+                if (kind != 0)
+                    M3_GO(1, 0);
+                else
+                    M3_GO(0, 0);
+        }
+#else
         if (kind != 0)
             M3_GO(1, 0);
-#ifdef ORB_B200_MMA_KNOCKOUT
-        else if (dbg == 1)
-            M3_GO(0, 1);
-        else if (dbg == 2)
-            M3_GO(0, 2);
-        else if (dbg == 3)
-            M3_GO(0, 3);
-        else if (dbg == 4)
-            M3_GO(0, 4);
-        else if (dbg == 12)
-            M3_GO(0, 12);
-        else if (dbg == 13)
-            M3_GO(0, 13);
-        else if (dbg == 14)
-            M3_GO(0, 14);
-        else if (dbg == 15)
-            M3_GO(0, 15);
-        else if (dbg == 16)
-            M3_GO(0, 16);
-        else if (dbg == 30)
-            M3_GO(0, 30);
-        else if (dbg == 32)
-            M3_GO(0, 32);
-        else if (dbg == 35)
-            M3_GO(0, 35);
-        else if (dbg == 31)
-            M3_GO(0, 31);
-#endif
         else
             M3_GO(0, 0);
-        (void)dbg;
+#endif
 #undef M3_GO
     } else if (variant >= 10 && variant < 20) {  // the first form of the kernel (2 CTAs per SM, block barriers): kept as a comparator
         dim3 grid((max_nq + MM_M - 1) / MM_M, npairs);
