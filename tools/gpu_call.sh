@@ -1,7 +1,5 @@
 mkdir -p gpurun_out
 P=gpurun_out/r02r
-python tools/probes/match_bench.py > ${P}_match_bench.txt 2>&1
-python tools/probes/match_bench.py --pairs 37 --n 1900 >> ${P}_match_bench.txt 2>&1
-python tools/probes/match_bench.py --pairs 1 --n 2000 --reps 50 >> ${P}_match_bench.txt 2>&1
-timeout 900 ncu --set full --import-source on --clock-control none -k regex:k_match_mma3 -s 3 -c 1 -o ${P}_prof_match python tools/probes/match_bench.py --only mma --reps 2 > ${P}_ncu3.log 2>&1
-cat ${P}_match_bench.txt; tail -n 2 ${P}_ncu3.log
+timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 8 > ${P}_bench_n8.json 2> ${P}_bench_n8.err
+timeout 200 python bench.py --no-cpu-baseline --no-next-rows --no-other-shapes > ${P}_bench_n1_samebox.json 2> ${P}_bench_n1_samebox.err
+tail -c 1500 ${P}_bench_n8.json; tail -n 3 ${P}_bench_n8.err; tail -c 300 ${P}_bench_n1_samebox.json
