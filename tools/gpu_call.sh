@@ -1,4 +1,7 @@
 mkdir -p gpurun_out
-timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_match.py -m gpu -q -x -k "match_all" > gpurun_out/r02ak_memcheck.txt 2>&1
-echo "rc=$?" >> gpurun_out/r02ak_memcheck.txt
-tail -n 12 gpurun_out/r02ak_memcheck.txt
+O=gpurun_out/r02am_graph.txt; : > $O
+ORB_B200_GRAPH=1 timeout 900 python -m pytest tests/test_gpu_extract.py tests/test_gpu_ingest.py -m gpu -q -x 2>&1 | tail -n 4 >> $O
+for g in 0 1; do ORB_B200_GRAPH=$g python tools/probes/resident_probe.py 2>&1 | tail -n 1 >> $O; done
+for g in 0 1; do ORB_B200_GRAPH=$g python tools/e2e_probe.py 2>&1 | tail -n 1 >> $O; done
+for g in 0 1; do ORB_B200_GRAPH=$g python tools/e2e_probe.py 2>&1 | tail -n 1 >> $O; done
+cat $O
