@@ -53,6 +53,26 @@ def test_match_all_batch_ragged():
     m.close()
 
 
+@pytest.mark.parametrize("nt", [1, 63, 64, 65, 128, 129, 640])
+def test_match_all_extreme_rows(nt):
+    """All-zero and all-one descriptors on both sides: a'.b reaches -256 and +256, the ends of the 16-bit key range the
+    tensor-core kernel packs (distance codes 0 and 512), on every slab / tile boundary of the train set."""
+    rng = np.random.default_rng(nt)
+    t = rng.integers(0, 256, (nt, 32), dtype=np.uint8)
+    q = rng.integers(0, 256, (300, 32), dtype=np.uint8)
+    t[::5] = 0
+    t[1::7] = 255
+    q[::3] = 0
+    q[1::4] = 255
+    t[nt - 1] = 255 if nt % 2 else 0
+    m = ORBmatcher()
+    got = m.match_all(q, t)
+    want = oracle.match_all(q, t)
+    for g, w in zip(got, want):
+        assert (g == w).all()
+    m.close()
+
+
 def test_match_all_batch_many_items_per_cta(monkeypatch):
     """More (pair, 256-query) items than SMs, ragged and empty pairs in between: the persistent kernel's running barrier
     phases, A-buffer hand-over and skipped items, against the popcount kernel on every pair and the oracle on a few."""

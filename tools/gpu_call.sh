@@ -1,7 +1,10 @@
 mkdir -p gpurun_out
-O=gpurun_out/r02am_graph.txt; : > $O
-ORB_B200_GRAPH=1 timeout 900 python -m pytest tests/test_gpu_extract.py tests/test_gpu_ingest.py -m gpu -q -x 2>&1 | tail -n 4 >> $O
-for g in 0 1; do ORB_B200_GRAPH=$g python tools/probes/resident_probe.py 2>&1 | tail -n 1 >> $O; done
-for g in 0 1; do ORB_B200_GRAPH=$g python tools/e2e_probe.py 2>&1 | tail -n 1 >> $O; done
-for g in 0 1; do ORB_B200_GRAPH=$g python tools/e2e_probe.py 2>&1 | tail -n 1 >> $O; done
-cat $O
+timeout 1500 python -m pytest tests -m gpu -q -x > gpurun_out/r02ao_pytest.txt 2>&1
+tail -n 4 gpurun_out/r02ao_pytest.txt
+python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -n 2
+timeout 600 python bench.py --no-other-shapes > gpurun_out/r02ao_bench.json 2> gpurun_out/r02ao_bench.err; tail -n 3 gpurun_out/r02ao_bench.err
+python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/r02ao_bench.json').read().strip().splitlines()[-1])
+print(d['value'], d['e2e']['value'], d['gpu_launches'], d['next_rows']['adapter_latency'], d['next_rows']['stereo_euroc']['ms_per_pair'])
+PY
