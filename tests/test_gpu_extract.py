@@ -385,6 +385,26 @@ def test_result_copies_ahead_of_counts_are_topped_up():
     ex.close()
 
 
+def test_single_chunk_graph_replay_and_recapture():
+    """Batches of one chunk replay their kernel sequence as a CUDA graph while the arguments stay the same (ORB_B200_GRAPH
+    default): the same call repeated, other frames through the same buffers, then a change of shape, of batch size and of
+    capacity on ONE handle must each time give the oracle's result (replay, replay with new data, re-capture)."""
+    from orb_slam_system_b200 import KP_DTYPE
+    nf = 800
+    ex = ORBextractor(nf, 1.2, 8, 20, 7, max_batch=4, max_rows=480, max_cols=752)
+    plan = [(240, 320, 1, None), (240, 320, 1, None), (240, 320, 1, None), (480, 752, 2, None), (480, 752, 2, None), (240, 320, 1, None),
+            (240, 320, 3, None), (240, 320, 3, 64), (375, 499, 1, None), (375, 499, 1, None)]
+    for it, (rows, cols, n, extra) in enumerate(plan):
+        cap = ex.keypoint_bound(rows, cols) + (extra or 0)  # a larger capacity: other output strides, other buffers
+        batch = np.stack([oracle.synth_frame(rows, cols, frame=40 + it + f, right=f & 1) for f in range(n)])
+        k = np.zeros((n, cap), KP_DTYPE)
+        d = np.zeros((n, cap, 32), np.uint8)
+        c = np.zeros(n, np.int32)
+        ex.wait_batch(ex.submit_batch_pinned(batch, k, d, c, cap))
+        _check_batch_against_oracle(batch, nf, k, d, c, f"call {it}")
+    ex.close()
+
+
 def test_device_resident_dense_frames():
     # densely packed device frames (row stride == cols, odd area): one pitch-conversion kernel, no slack behind the buffer
     import torch
