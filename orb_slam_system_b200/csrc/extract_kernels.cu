@@ -1799,10 +1799,18 @@ cudaError_t orbk_run_extract(const OrbPlan& plan, int nframes, orb_keypoint_dev*
     // event-timed duration is its own (no overlap); otherwise the blur overlaps detect + octree
     cudaStream_t st = ss.st, st2 = ss.st2;
     cudaError_t e;
+#ifdef ORB_B200_STAGE_KNOCKOUT  // timing probe (tools/probes/resident_probe.py LATE_ENV): stages left out once the buffers are filled
+    const char* ko = getenv("ORB_B200_SKIP");
+    const int skip = ko ? atoi(ko) : 0;  // 1 pyramid, 2 detect, 4 octree, 8 blur, 16 describe
+#else
+    const int skip = 0;
+#endif
+    if (!(skip & 2)) {
     e = cudaMemsetAsync(plan.candCount, 0, sizeof(int) * ORB_MAX_LEVELS * nframes, st);
     if (e != cudaSuccess) return e;
     e = cudaMemsetAsync(plan.status, 0, sizeof(int) * nframes, st);
     if (e != cudaSuccess) return e;
+    }
     if (ev) cudaEventRecord(ev[0], st);
     // Level 0 is the input: its detect tiles do not need the pyramid.  Outside profiling the pyramid chain (six dependent,
     // shrinking launches that mostly wait) therefore runs on the second stream next to the level-0 detect, followed there by the
@@ -1815,14 +1823,16 @@ cudaError_t orbk_run_extract(const OrbPlan& plan, int nframes, orb_keypoint_dev*
         if (e != cudaSuccess) return e;
         e = cudaStreamWaitEvent(st2, ss.fork, 0);
         if (e != cudaSuccess) return e;
-        k_detect<<<dim3(tiles0, nframes), DET_THREADS, detect_smem_bytes(plan.detRows), st>>>(plan, d_maps->m, 0);
-        ++g_launches;
+        if (!(skip & 2)) {
+            k_detect<<<dim3(tiles0, nframes), DET_THREADS, detect_smem_bytes(plan.detRows), st>>>(plan, d_maps->m, 0);
+            ++g_launches;
+        }
     }
     // pyramid: level l = resize(level l-1); same-size levels alias their source
     bool first = true;
     for (int l = 1; l < plan.nlevels; ++l) {
         const OrbLevel& D = plan.lv[l];
-        if (D.src != l) continue;
+        if (D.src != l || (skip & 1)) continue;
         const OrbLevel& S = plan.lv[plan.lv[l - 1].src];
         if (D.xgrp && D.rszTiled) {
             dim3 grid((D.cols + RSZ_W - 1) / RSZ_W, (D.rows + RSZ_H - 1) / RSZ_H, nframes);
@@ -1857,8 +1867,10 @@ cudaError_t orbk_run_extract(const OrbPlan& plan, int nframes, orb_keypoint_dev*
             e = cudaStreamWaitEvent(st2, ss.fork, 0);
             if (e != cudaSuccess) return e;
         }
-        k_blur<<<dim3(blurTiles, nframes), BLUR_THREADS, 0, st2>>>(plan, d_maps->blr);
-        ++g_launches;
+        if (!(skip & 8)) {
+            k_blur<<<dim3(blurTiles, nframes), BLUR_THREADS, 0, st2>>>(plan, d_maps->blr);
+            ++g_launches;
+        }
         e = cudaEventRecord(ss.join, st2);
         if (e != cudaSuccess) return e;
     }
@@ -1866,16 +1878,20 @@ cudaError_t orbk_run_extract(const OrbPlan& plan, int nframes, orb_keypoint_dev*
         if (plan.totalTiles > tiles0) {
             e = cudaStreamWaitEvent(st, ss.pyr, 0);
             if (e != cudaSuccess) return e;
-            k_detect<<<dim3(plan.totalTiles - tiles0, nframes), DET_THREADS, detect_smem_bytes(plan.detRows), st>>>(plan, d_maps->m, tiles0);
-            ++g_launches;
+            if (!(skip & 2)) {
+                k_detect<<<dim3(plan.totalTiles - tiles0, nframes), DET_THREADS, detect_smem_bytes(plan.detRows), st>>>(plan, d_maps->m, tiles0);
+                ++g_launches;
+            }
         }
     } else if (plan.totalTiles > 0) {
         launch_pdl(k_detect, dim3(plan.totalTiles, nframes), dim3(DET_THREADS), detect_smem_bytes(plan.detRows), st, plan, d_maps->m, 0);
         ++g_launches;
     }
     if (ev) cudaEventRecord(ev[2], st);
-    launch_pdl(k_octree_fast, dim3(plan.nlevels, nframes), dim3(OCTF_THREADS), kOctFastSmem, st, plan);
-    ++g_launches;
+    if (!(skip & 4)) {
+        launch_pdl(k_octree_fast, dim3(plan.nlevels, nframes), dim3(OCTF_THREADS), kOctFastSmem, st, plan);
+        ++g_launches;
+    }
     if (ev) {
         // profiling: stages back to back on one stream, blur after the octree
         cudaEventRecord(ev[3], st);
@@ -1890,9 +1906,11 @@ cudaError_t orbk_run_extract(const OrbPlan& plan, int nframes, orb_keypoint_dev*
         e = cudaStreamWaitEvent(st, ss.join, 0);
         if (e != cudaSuccess) return e;
     }
-    launch_pdl(k_describe_tile, dim3(std::max(1, plan.totalDescTiles), nframes), dim3(DSC_THREADS), kDescSmem, st, plan, d_maps, d_kps, d_desc, cap,
-               d_counts);
-    ++g_launches;
+    if (!(skip & 16)) {
+        launch_pdl(k_describe_tile, dim3(std::max(1, plan.totalDescTiles), nframes), dim3(DSC_THREADS), kDescSmem, st, plan, d_maps, d_kps, d_desc, cap,
+                   d_counts);
+        ++g_launches;
+    }
     if (ev) cudaEventRecord(ev[5], st);
     return cudaGetLastError();
 }

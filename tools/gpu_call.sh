@@ -1,3 +1,4 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_extract.py -m gpu -q -x -k "graph or topped or dense_frames or pipelined" > gpurun_out/r02aq_pytest.txt 2>&1
-tail -n 6 gpurun_out/r02aq_pytest.txt
+O=gpurun_out/r02ar_stage_knockout.txt; : > $O
+for m in 0 1 2 4 8 16 6 3 24; do LATE_ENV=ORB_B200_SKIP=$m python tools/probes/resident_probe.py 2>&1 | tail -n 1 >> $O; done
+cat $O
