@@ -1,4 +1,7 @@
-// k_match_mma: brute-force Hamming search (BASELINE config 4) on the 5th-generation tensor cores.
+// Brute-force Hamming search (BASELINE config 4) on the 5th-generation tensor cores.  Three generations of the same
+// contraction live here: k_match_mma3 (persistent, warp-specialised, bias K-step: the kernel orbk_match_all launches),
+// k_match_mma2 (warp-specialised, one CTA per 256 queries) and k_match_mma (the first form, described below); the two older
+// ones stay selectable (ORB_B200_MMA_VARIANT) as comparators for the numbers in DESIGN.md section 4 and 9.
 //
 // Unit: ORBmatcher::DescriptorDistance (reference src/ORBmatcher.cc:896-908) = popcount(a ^ b) over 256 bits.
 // With the query bits as a' = 2a - 1 in {-1, +1} and the train bits as b in {0, 1}
@@ -8,8 +11,8 @@
 // accumulator: the distances are bit-identical to the reference's.  The scan semantics on top of them are the shared
 // ones (src/ORBmatcher.cc:49-55): best = first minimum in train order, second = second smallest of the multiset.
 //
-// One CTA = 128 queries (the M of the MMA, one TMEM lane each) of one (query set, train set) pair; it walks the train
-// rows in tiles of 128 (the N of the MMA):
+// k_match_mma, the first form.  One CTA = 128 queries (the M of the MMA, one TMEM lane each) of one (query set, train set)
+// pair; it walks the train rows in tiles of 128 (the N of the MMA):
 //   expand    every thread takes half a train row (one 128-bit load) and spreads its bits to bytes straight into the
 //             canonical K-major no-swizzle UMMA layout in shared memory (8 x 16-byte core matrices, PRMT with the bit
 //             nibbles as selectors; the bit -> K position map is a fixed permutation, the same for both operands, which
