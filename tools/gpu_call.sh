@@ -1,7 +1,11 @@
 mkdir -p gpurun_out
-P=gpurun_out/r02t
-SHORT="python bench.py --steps 2 --warmup 1 --repeats 1 --no-cpu-baseline --no-next-rows --no-other-shapes"
-timeout 600 $SHORT > ${P}_bench_short.json 2> ${P}_bench_short.err && \
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file ${P}_launches.csv $SHORT > ${P}_ncu1.log 2>&1
-timeout 1200 ncu --set full --clock-control none -k regex:'k_(detect|octree|blur|describe|resize|repitch)' -c 26 -o ${P}_prof_extract $SHORT > ${P}_ncu2.log 2>&1
-tail -n 2 ${P}_ncu1.log ${P}_ncu2.log | cut -c1-300; ls -la gpurun_out | grep r02t
+timeout 1500 python -m pytest tests -m gpu -q -x > gpurun_out/r02u_pytest.txt 2>&1
+tail -n 3 gpurun_out/r02u_pytest.txt
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -n 1
+timeout 900 python bench.py > gpurun_out/r02u_bench_default.json 2> gpurun_out/r02u_bench_default.err; tail -n 2 gpurun_out/r02u_bench_default.err
+timeout 600 python bench.py --impl reference > gpurun_out/r02u_bench_reference.json 2> gpurun_out/r02u_bench_reference.err; tail -c 600 gpurun_out/r02u_bench_reference.json
+python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/r02u_bench_default.json').read().strip().splitlines()[-1])
+print(d['value'], d['ms_per_step'], d['e2e']['value'], d['e2e']['steady_state_value'], d['e2e']['platform_ceiling_frames_s'], d['roofline']['issue']['frac'], d['hamming']['value'], d['cpu_baseline']['value'])
+PY
