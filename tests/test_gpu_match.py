@@ -73,6 +73,34 @@ def test_match_all_extreme_rows(nt):
     m.close()
 
 
+@pytest.mark.parametrize("env", [
+    {"ORB_B200_MMA_BK": "0"},                                  # k_match_mma3 without the bias K-step
+    {"ORB_B200_MMA_KIND": "f8"},                               # e4m3 / f32 twin
+    {"ORB_B200_MMA_VARIANT": "30"},                            # k_match_mma2, 8 epilogue warps
+    {"ORB_B200_MMA_VARIANT": "20"},                            # k_match_mma2, 16 epilogue warps
+    {"ORB_B200_MMA_VARIANT": "10"},                            # k_match_mma, the first form
+    {"ORB_B200_MMA_VARIANT": "10", "ORB_B200_MMA_KIND": "f8"},
+    {"ORB_B200_MATCH": "popc"},                                # the POPC kernel
+])
+def test_comparator_kernels_stay_exact(env, monkeypatch):
+    """The kernels DESIGN.md keeps as comparators (and the POPC kernel) give the oracle's result on a ragged batch."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    rng = np.random.default_rng(21)
+    P, Q, T = 4, 520, 777
+    nq = np.array([520, 257, 0, 31], np.int32)
+    nt = np.array([777, 129, 40, 0], np.int32)
+    t = rand_desc(rng, P * T, 182).reshape(P, T, 32)
+    q = rand_desc(rng, P * Q, 182, flip_from=t.reshape(-1, 32)).reshape(P, Q, 32)
+    t[1, :64] = rng.integers(0, 256, (64, 32), dtype=np.uint8)  # 256 live bits in one train tile: the 8-K-step path
+    m = ORBmatcher()
+    bi, bd, sd = m.match_all_batch(q, nq, t, nt)
+    for p in range(P):
+        oi, od, os_ = oracle.match_all(q[p, :nq[p]], t[p, :nt[p]])
+        assert (bi[p, :nq[p]] == oi).all() and (bd[p, :nq[p]] == od).all() and (sd[p, :nq[p]] == os_).all(), (env, p)
+    m.close()
+
+
 def test_match_all_batch_many_items_per_cta(monkeypatch):
     """More (pair, 256-query) items than SMs, ragged and empty pairs in between: the persistent kernel's running barrier
     phases, A-buffer hand-over and skipped items, against the popcount kernel on every pair and the oracle on a few."""
