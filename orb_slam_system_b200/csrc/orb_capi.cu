@@ -771,7 +771,11 @@ static cudaError_t run_chunk(orb_extractor* h, orb_extractor::ChunkGraph& G, con
         G.exec = nullptr;
         const unsigned long long before = orbk_launch_count();
         cudaError_t e = cudaStreamBeginCapture(ls.st, cudaStreamCaptureModeThreadLocal);
-        if (e != cudaSuccess) return e;
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            h->graph_mode = 0;
+            return enqueue_chunk_kernels(a, ls, h->next_events());
+        }
         e = enqueue_chunk_kernels(a, ls, nullptr);
         cudaGraph_t g = nullptr;
         const cudaError_t e2 = cudaStreamEndCapture(ls.st, &g);
@@ -779,8 +783,13 @@ static cudaError_t run_chunk(orb_extractor* h, orb_extractor::ChunkGraph& G, con
         if (e == cudaSuccess) e = cudaGraphInstantiate(&G.exec, g, 0);
         if (g) cudaGraphDestroy(g);
         if (e != cudaSuccess) {
+            // capture or instantiation refused (nothing has run: a capture only records): this handle goes back to plain
+            // stream launches for good
             G.exec = nullptr;
-            return e;
+            cudaGetLastError();
+            orbk_count_launch(-(int)(orbk_launch_count() - before));
+            h->graph_mode = 0;
+            return enqueue_chunk_kernels(a, ls, h->next_events());
         }
         G.launches = (int)(orbk_launch_count() - before);
         orbk_count_launch(-G.launches);  // counted when the graph runs
